@@ -1,0 +1,69 @@
+// Library-internal context: one process per GPU, one stream, stream-ordered memory pool.
+#pragma once
+#include "gl.cuh"
+#include "../../include/deepprove_b200.h"
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+
+struct DpCtx {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::recursive_mutex mu;
+    unsigned long long launches = 0;
+};
+DpCtx &dp_ctx();
+void dp_set_error(const std::string &s);
+int dp_fail(int code, const std::string &s);
+
+#define DP_CUDA(x)                                                                                          \
+    do {                                                                                                    \
+        cudaError_t e_ = (x);                                                                               \
+        if (e_ != cudaSuccess) return dp_fail(DP_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define DP_REQUIRE_CTX()                                                                    \
+    std::lock_guard<std::recursive_mutex> lk_(dp_ctx().mu);                                 \
+    if (!dp_ctx().ready) return dp_fail(DP_ERR_NO_DEVICE, "dp_init() has not succeeded: no CUDA device context")
+#define DP_CHECK(cond, code, msg) \
+    do { if (!(cond)) return dp_fail((code), (msg)); } while (0)
+#define DP_LAUNCHED() (dp_ctx().launches++)
+
+// optional per-kernel timing with CUDA events on the launch stream (bench.py's roofline leg)
+int dp_prof_begin(const char *name, u64 algorithmic_bytes);   // returns a token (or -1 when disabled)
+void dp_prof_end(int token);
+struct DpProfScope {
+    int tok;
+    DpProfScope(const char *name, u64 bytes) : tok(dp_prof_begin(name, bytes)) {}
+    ~DpProfScope() { dp_prof_end(tok); }
+};
+
+// stream-ordered allocation helpers
+int dp_dev_alloc(void **p, size_t bytes);
+int dp_dev_free(void *p);
+
+struct dp_mle {
+    void *data = nullptr;   // u64[len] or gle[len]
+    u64 len = 0;
+    bool is_ext = false;
+    bool owned = true;
+    u32 num_vars() const { u32 l = 0; while ((1ULL << l) < len) l++; return l; }
+    size_t bytes() const { return (size_t)len * (is_ext ? 16 : 8); }
+};
+
+static inline int dp_grid_for(u64 work_items, int threads, int max_ctas_per_sm) {
+    u64 g = (work_items + threads - 1) / threads;
+    u64 cap = (u64)dp_ctx().sm_count * max_ctas_per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---- kernel launchers shared between translation units (mle.cu) ----
+int dpk_eq_build(const gle *point_host, u32 nv, gle *out_dev);                       // K5
+int dpk_fix_high(const void *src, bool src_ext, u64 len, const gle *point_host, u32 k, gle *out_dev);  // K3
+int dpk_fold_low(const void *src, bool src_ext, u64 len, gle r, gle *out_dev);      // K2 (stand-alone)

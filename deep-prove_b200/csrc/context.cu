@@ -1,0 +1,135 @@
+// Context, error reporting and memory-pool plumbing of libdeepprove_b200.so.
+#include "common.cuh"
+
+static thread_local std::string g_err;
+static DpCtx g_ctx;
+DpCtx &dp_ctx() { return g_ctx; }
+void dp_set_error(const std::string &s) { g_err = s; }
+int dp_fail(int code, const std::string &s) { g_err = s; return code; }
+
+int dp_dev_alloc(void **p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    DP_CUDA(cudaMallocAsync(p, bytes, dp_ctx().stream));
+    return DP_OK;
+}
+int dp_dev_free(void *p) {
+    if (!p) return DP_OK;
+    DP_CUDA(cudaFreeAsync(p, dp_ctx().stream));
+    return DP_OK;
+}
+
+// ---- per-kernel event timing --------------------------------------------------------------------
+#include <map>
+struct ProfRec { cudaEvent_t a, b; std::string name; u64 bytes; };
+struct ProfStat { u64 count = 0; double ms = 0; u64 bytes = 0; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_pending;
+static std::vector<cudaEvent_t> g_prof_pool;
+static std::map<std::string, ProfStat> g_prof_stats;
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+int dp_prof_begin(const char *name, u64 bytes) {
+    if (!g_prof_on) return -1;
+    ProfRec r; r.a = prof_event(); r.b = prof_event(); r.name = name; r.bytes = bytes;
+    cudaEventRecord(r.a, g_ctx.stream);
+    g_prof_pending.push_back(r);
+    return (int)g_prof_pending.size() - 1;
+}
+void dp_prof_end(int tok) { if (tok >= 0) cudaEventRecord(g_prof_pending[tok].b, g_ctx.stream); }
+static void prof_resolve() {
+    if (g_prof_pending.empty()) return;
+    cudaStreamSynchronize(g_ctx.stream);
+    for (auto &r : g_prof_pending) {
+        float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+        ProfStat &s = g_prof_stats[r.name]; s.count++; s.ms += ms; s.bytes += r.bytes;
+        g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+    }
+    g_prof_pending.clear();
+}
+
+extern "C" {
+
+int dp_profile_enable(int on) {
+    std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
+    prof_resolve();
+    g_prof_on = on != 0;
+    return DP_OK;
+}
+int dp_profile_reset(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
+    prof_resolve(); g_prof_stats.clear();
+    return DP_OK;
+}
+// Writes up to `cap` entries; returns the number of distinct kernel names seen.
+int dp_profile_read(char (*names)[64], uint64_t *counts, double *total_ms, uint64_t *bytes, int cap) {
+    std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
+    prof_resolve();
+    int i = 0;
+    for (auto &kv : g_prof_stats) {
+        if (i < cap) {
+            snprintf(names[i], 64, "%s", kv.first.c_str());
+            counts[i] = kv.second.count; total_ms[i] = kv.second.ms; bytes[i] = kv.second.bytes;
+        }
+        i++;
+    }
+    return i;
+}
+
+const char *dp_last_error(void) { return g_err.c_str(); }
+const char *dp_version(void) { return "deepprove_b200 0.1 (sm_100a)"; }
+
+int dp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int dp_init(int device) {
+    std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
+    int n = dp_device_count();
+    if (n <= 0) return dp_fail(DP_ERR_NO_DEVICE, "no CUDA device visible: deepprove_b200 has no CPU fallback");
+    if (device < 0 || device >= n) return dp_fail(DP_ERR_INVALID, "dp_init: device index out of range");
+    DP_CUDA(cudaSetDevice(device));
+    if (g_ctx.ready && g_ctx.device == device) return DP_OK;
+    cudaDeviceProp prop;
+    DP_CUDA(cudaGetDeviceProperties(&prop, device));
+    g_ctx.sm_count = prop.multiProcessorCount;
+    if (!g_ctx.stream) { DP_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking)); g_ctx.own_stream = true; }
+    // keep freed blocks in the pool: sumcheck rounds allocate/free ping-pong buffers constantly
+    cudaMemPool_t pool;
+    DP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long thresh = ~0ULL;
+    DP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    g_ctx.device = device;
+    g_ctx.ready = true;
+    return DP_OK;
+}
+
+int dp_shutdown(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
+    if (!g_ctx.ready) return DP_OK;
+    cudaStreamSynchronize(g_ctx.stream);
+    if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
+    g_ctx.stream = nullptr; g_ctx.own_stream = false; g_ctx.ready = false;
+    return DP_OK;
+}
+
+int dp_set_stream(void *s) {
+    DP_REQUIRE_CTX();
+    DP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    if (g_ctx.own_stream) { cudaStreamDestroy(g_ctx.stream); g_ctx.own_stream = false; }
+    g_ctx.stream = (cudaStream_t)s;
+    return DP_OK;
+}
+
+int dp_synchronize(void) {
+    DP_REQUIRE_CTX();
+    DP_CUDA(cudaStreamSynchronize(g_ctx.stream));
+    return DP_OK;
+}
+
+uint64_t dp_kernel_launches(void) { return g_ctx.launches; }
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// Goldilocks F = Z/(2^64 - 2^32 + 1) and E = F[X]/(X^2 - 7) for sm_100a device code (and host code
+// inside the library, for the O(degree)-sized per-round glue).
+// Reference semantics: ff_ext/src/lib.rs:7,13 (p3 Goldilocks / BinomialExtensionField<_,2>, W = 7).
+// All values are canonical (< p) in memory and in registers between operations; E is AoS {c0,c1} so a
+// 16-byte vector load brings one element, exactly the reference's Vec<E> layout.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#define GL_HD __host__ __device__ __forceinline__
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+static constexpr u64 GL_P = 0xFFFFFFFF00000001ULL;
+static constexpr u64 GL_EPS = 0xFFFFFFFFULL;  // 2^64 mod p
+
+GL_HD u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
+GL_HD u64 gl_add(u64 a, u64 b) {
+    u64 s = a + b;
+    // a,b < p: on wrap the true sum is s + 2^64, and (s + 2^64) - p == s - p (mod 2^64)
+    return (s < a || s >= GL_P) ? s - GL_P : s;
+}
+GL_HD u64 gl_sub(u64 a, u64 b) { u64 d = a - b; return a < b ? d + GL_P : d; }
+GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0ULL; }
+GL_HD u64 gl_dbl(u64 a) { return gl_add(a, a); }
+
+GL_HD void gl_mul_wide(u64 a, u64 b, u64 &lo, u64 &hi) {
+#ifdef __CUDA_ARCH__
+    lo = a * b; hi = __umul64hi(a, b);
+#else
+    unsigned __int128 t = (unsigned __int128)a * b; lo = (u64)t; hi = (u64)(t >> 64);
+#endif
+}
+// reduce hi*2^64 + lo (any 128-bit value) to canonical form: 2^64 = 2^32 - 1, 2^96 = -1 (mod p)
+GL_HD u64 gl_reduce128(u64 lo, u64 hi) {
+    u64 hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
+    u64 t0 = lo - hi_hi;
+    if (lo < hi_hi) t0 -= GL_EPS;            // borrow: + p == - EPS (mod 2^64), cannot underflow
+    u64 t1 = hi_lo * GL_EPS;                 // < 2^64
+    u64 r = t0 + t1;
+    if (r < t1) r += GL_EPS;                 // carry: 2^64 == EPS (mod p), cannot overflow again
+    return r >= GL_P ? r - GL_P : r;
+}
+GL_HD u64 gl_mul(u64 a, u64 b) { u64 lo, hi; gl_mul_wide(a, b, lo, hi); return gl_reduce128(lo, hi); }
+GL_HD u64 gl_sqr(u64 a) { return gl_mul(a, a); }
+GL_HD u64 gl_mul7(u64 a) { u64 lo, hi; gl_mul_wide(a, 7ULL, lo, hi); return gl_reduce128(lo, hi); }
+GL_HD u64 gl_pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = gl_mul(r, a); a = gl_sqr(a); e >>= 1; } return r; }
+GL_HD u64 gl_inv(u64 a) { return gl_pow(a, GL_P - 2); }
+
+struct __align__(16) gle {  // one E element
+    u64 c0, c1;
+};
+GL_HD gle e_make(u64 a, u64 b) { gle r; r.c0 = a; r.c1 = b; return r; }
+GL_HD gle e_zero() { return e_make(0, 0); }
+GL_HD gle e_one() { return e_make(1, 0); }
+GL_HD gle e_from_base(u64 a) { return e_make(a, 0); }
+GL_HD gle e_add(gle a, gle b) { return e_make(gl_add(a.c0, b.c0), gl_add(a.c1, b.c1)); }
+GL_HD gle e_sub(gle a, gle b) { return e_make(gl_sub(a.c0, b.c0), gl_sub(a.c1, b.c1)); }
+GL_HD gle e_neg(gle a) { return e_make(gl_neg(a.c0), gl_neg(a.c1)); }
+GL_HD gle e_dbl(gle a) { return e_add(a, a); }
+GL_HD bool e_eq(gle a, gle b) { return a.c0 == b.c0 && a.c1 == b.c1; }
+// (a0 + a1 X)(b0 + b1 X) = (a0 b0 + 7 a1 b1) + (a0 b1 + a1 b0) X.
+// The two limbs are each ONE reduction of a <=131-bit sum of raw 128-bit products (fewer reductions
+// than 4 reduced multiplies; same canonical result because the arithmetic is exact).
+GL_HD u64 gl_reduce160(u64 lo, u64 hi, u64 top) {  // top*2^128 + hi*2^64 + lo, top < 2^32
+    // 2^128 = (2^32-1)^2 mod p = 2^64 - 2^33 + 1 = -2^32 (mod p)  => top*2^128 = -(top << 32)
+    u64 r = gl_reduce128(lo, hi);
+    return gl_sub(r, gl_canon(top << 32));
+}
+GL_HD gle e_mul(gle a, gle b) {
+    u64 l0, h0, l1, h1;
+    // c1 = a0 b1 + a1 b0  (129 bits)
+    gl_mul_wide(a.c0, b.c1, l0, h0); gl_mul_wide(a.c1, b.c0, l1, h1);
+    u64 lo = l0 + l1; u64 c = lo < l0; u64 hi = h0 + h1; u64 top = hi < h0; hi += c; top += (hi < c);
+    u64 c1 = gl_reduce160(lo, hi, top);
+    // c0 = a0 b0 + 7 a1 b1  (131 bits)
+    gl_mul_wide(a.c0, b.c0, l0, h0); gl_mul_wide(a.c1, b.c1, l1, h1);
+    // 7 * (h1:l1) as 192-bit
+    u64 m_lo, m_c; gl_mul_wide(l1, 7ULL, m_lo, m_c);
+    u64 m_hi, m_top; gl_mul_wide(h1, 7ULL, m_hi, m_top);
+    m_hi += m_c; m_top += (m_hi < m_c);
+    lo = l0 + m_lo; c = lo < l0; hi = h0 + m_hi; top = m_top + (hi < h0); hi += c; top += (hi < c);
+    u64 c0 = gl_reduce160(lo, hi, top);
+    return e_make(c0, c1);
+}
+GL_HD gle e_mul_base(gle a, u64 b) { return e_make(gl_mul(a.c0, b), gl_mul(a.c1, b)); }
+GL_HD gle e_sqr(gle a) { return e_mul(a, a); }
+GL_HD gle e_inv(gle a) {
+    u64 n = gl_sub(gl_sqr(a.c0), gl_mul7(gl_sqr(a.c1)));
+    u64 ni = gl_inv(n);
+    return e_make(gl_mul(a.c0, ni), gl_mul(gl_neg(a.c1), ni));
+}
+GL_HD gle e_from_u64(u64 v) { return e_make(gl_canon(v), 0); }
+
+#ifdef __CUDACC__
+// 16-byte vector loads/stores of E and of a Base pair
+__device__ __forceinline__ gle ld_e(const gle *p) { ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p); return e_make(v.x, v.y); }
+__device__ __forceinline__ void st_e(gle *p, gle v) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(v.c0, v.c1); }
+__device__ __forceinline__ ulonglong2 ld_b2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
+__device__ __forceinline__ gle shfl_down_e(gle v, int d) {
+    gle r; r.c0 = __shfl_down_sync(0xffffffffu, v.c0, d); r.c1 = __shfl_down_sync(0xffffffffu, v.c1, d); return r;
+}
+__device__ __forceinline__ gle shfl_xor_e(gle v, int d) {
+    gle r; r.c0 = __shfl_xor_sync(0xffffffffu, v.c0, d); r.c1 = __shfl_xor_sync(0xffffffffu, v.c1, d); return r;
+}
+#endif

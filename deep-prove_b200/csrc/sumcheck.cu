@@ -1,0 +1,439 @@
+// Sumcheck prover rounds on device (K1 + K2 fused).
+// Reference: sumcheck/src/prover.rs:498-741 (prove_parallel / prove_round_and_update_state_parallel),
+// sumcheck_macro/src/lib.rs:46-326 (the per-pair arithmetic), multilinear_extensions/src/mle.rs:631-712
+// (fix_variables_parallel).
+//
+// B200 design: ONE launch per round for the whole VirtualPolynomial.  grid.y = product index, grid.x
+// tiles the pairs; each operand is streamed once with 16-byte loads.  From round 2 on the fold by the
+// previous challenge is fused into the same pass: a thread reads 4 consecutive elements of the old
+// table, folds them to one adjacent pair, the owning product writes the pair to the (half-size)
+// ping-pong table, and every product using the operand feeds the pair straight into the round
+// polynomial accumulators.  Accumulators live in registers, are combined with warp shuffles, then per
+// block through shared memory, and the last block of each product (ticket counter) reduces the block
+// partials -- field addition is exact, so the summation order is free and the result is bit-identical
+// to the reference's rayon fold.  The (deg+1) sums per product go back through a pinned buffer; the
+// O(deg^2) glue (2^k multiplicity, coefficient, barycentric extrapolation -- prover.rs:713-724,
+// util.rs:101-136) runs on the host inside dp_sc_round, exactly where the reference has it.
+#include "common.cuh"
+#include <algorithm>
+
+enum : u32 { OPM_B = 0, OPM_E = 1, OPM_BF = 2, OPM_EF = 3 };
+struct ScOp { const void *src; gle *dst; u32 mode; u32 pad; };
+struct ScProd { ScOp op[5]; u64 npairs; u32 d; u32 allbase; u32 konst; u32 pad; };
+static constexpr int SC_NACC = 6;
+static constexpr int SC_THREADS = 256;
+
+__device__ __forceinline__ gle fold_b(u64 a, u64 b, gle r) { return e_add(e_mul_base(r, gl_sub(b, a)), e_from_base(a)); }
+__device__ __forceinline__ gle fold_e(gle a, gle b, gle r) { return e_add(a, e_mul(e_sub(b, a), r)); }
+
+__device__ __forceinline__ void sc_load_pair(const ScOp &op, u64 i, gle r, gle &lo, gle &hi) {
+    switch (op.mode) {
+    case OPM_B: {
+        ulonglong2 v = ld_b2((const u64 *)op.src + 2 * i);
+        lo = e_from_base(v.x); hi = e_from_base(v.y);
+    } break;
+    case OPM_E: {
+        const gle *s = (const gle *)op.src + 2 * i;
+        lo = ld_e(s); hi = ld_e(s + 1);
+    } break;
+    case OPM_BF: {
+        const u64 *s = (const u64 *)op.src + 4 * i;
+        ulonglong2 v0 = ld_b2(s), v1 = ld_b2(s + 2);
+        lo = fold_b(v0.x, v0.y, r); hi = fold_b(v1.x, v1.y, r);
+        if (op.dst) { st_e(op.dst + 2 * i, lo); st_e(op.dst + 2 * i + 1, hi); }
+    } break;
+    default: {
+        const gle *s = (const gle *)op.src + 4 * i;
+        gle f0 = ld_e(s), f1 = ld_e(s + 1), f2 = ld_e(s + 2), f3 = ld_e(s + 3);
+        lo = fold_e(f0, f1, r); hi = fold_e(f2, f3, r);
+        if (op.dst) { st_e(op.dst + 2 * i, lo); st_e(op.dst + 2 * i + 1, hi); }
+    } break;
+    }
+}
+// length-1 operands (sumcheck_macro/src/lib.rs:236-241): value at every evaluation point
+__device__ __forceinline__ gle sc_load_const(const ScOp &op, gle r) {
+    switch (op.mode) {
+    case OPM_B: return e_from_base(*(const u64 *)op.src);
+    case OPM_E: return ld_e((const gle *)op.src);
+    case OPM_BF: { ulonglong2 v = ld_b2((const u64 *)op.src); gle x = fold_b(v.x, v.y, r); if (op.dst) st_e(op.dst, x); return x; }
+    default: { const gle *s = (const gle *)op.src; gle x = fold_e(ld_e(s), ld_e(s + 1), r); if (op.dst) st_e(op.dst, x); return x; }
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC]) {
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    if (pd.konst) {
+        if (tid == 0) {
+            gle p = sc_load_const(pd.op[0], r);
+#pragma unroll
+            for (int j = 1; j < D; j++) p = e_mul(p, sc_load_const(pd.op[j], r));
+#pragma unroll
+            for (int t = 0; t <= D; t++) acc[t] = p;
+        }
+        return;
+    }
+    if (pd.allbase) {
+        // all operands Base and unfolded: stay in F (sumcheck_macro/src/lib.rs:294-299 lifts at the end)
+        u64 a[D + 1];
+#pragma unroll
+        for (int t = 0; t <= D; t++) a[t] = 0;
+        for (u64 i = tid; i < pd.npairs; i += stride) {
+            u64 cur[D], st[D];
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                ulonglong2 v = ld_b2((const u64 *)pd.op[j].src + 2 * i);
+                cur[j] = v.x; st[j] = gl_sub(v.y, v.x);
+            }
+#pragma unroll
+            for (int t = 0; t <= D; t++) {
+                u64 p = cur[0];
+#pragma unroll
+                for (int j = 1; j < D; j++) p = gl_mul(p, cur[j]);
+                a[t] = gl_add(a[t], p);
+                if (t < D) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) cur[j] = gl_add(cur[j], st[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t <= D; t++) acc[t] = e_from_base(a[t]);
+        return;
+    }
+    gle a[D + 1];
+#pragma unroll
+    for (int t = 0; t <= D; t++) a[t] = e_zero();
+    for (u64 i = tid; i < pd.npairs; i += stride) {
+        gle cur[D], st[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            gle lo, hi;
+            sc_load_pair(pd.op[j], i, r, lo, hi);
+            cur[j] = lo; st[j] = e_sub(hi, lo);
+        }
+#pragma unroll
+        for (int t = 0; t <= D; t++) {
+            gle p = cur[0];
+#pragma unroll
+            for (int j = 1; j < D; j++) p = (pd.op[j].mode == OPM_B) ? e_mul_base(p, cur[j].c0) : e_mul(p, cur[j]);
+            a[t] = e_add(a[t], p);
+            if (t < D) {
+#pragma unroll
+                for (int j = 0; j < D; j++) cur[j] = e_add(cur[j], st[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t <= D; t++) acc[t] = a[t];
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, u32 *__restrict__ counters, gle *__restrict__ out) {
+    __shared__ ScProd pd;
+    __shared__ gle wsum[SC_THREADS / 32][SC_NACC];
+    __shared__ bool is_last;
+    {
+        const u64 *s = (const u64 *)(descs + blockIdx.y);
+        u64 *d = (u64 *)&pd;
+        for (int k = threadIdx.x; k < (int)(sizeof(ScProd) / 8); k += blockDim.x) d[k] = s[k];
+    }
+    __syncthreads();
+    gle acc[SC_NACC];
+#pragma unroll
+    for (int t = 0; t < SC_NACC; t++) acc[t] = e_zero();
+    switch (pd.d) {
+    case 1: sc_body<1>(pd, r, acc); break;
+    case 2: sc_body<2>(pd, r, acc); break;
+    case 3: sc_body<3>(pd, r, acc); break;
+    case 4: sc_body<4>(pd, r, acc); break;
+    default: sc_body<5>(pd, r, acc); break;
+    }
+    const int nacc = pd.d + 1;
+    // warp shuffle reduction, then across warps through shared memory
+    for (int t = 0; t < nacc; t++) {
+        gle v = acc[t];
+        for (int d = 16; d > 0; d >>= 1) v = e_add(v, shfl_down_e(v, d));
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nacc) {
+        gle v = wsum[0][threadIdx.x];
+        for (int w = 1; w < SC_THREADS / 32; w++) v = e_add(v, wsum[w][threadIdx.x]);
+        st_e(partials + ((u64)blockIdx.y * gridDim.x + blockIdx.x) * SC_NACC + threadIdx.x, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 ticket = atomicAdd(counters + blockIdx.y, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        for (int t = 0; t < nacc; t++) {
+            gle v = e_zero();
+            for (u32 x = threadIdx.x; x < gridDim.x; x += 32) {
+                ulonglong2 q = __ldcg(reinterpret_cast<const ulonglong2 *>(partials + ((u64)blockIdx.y * gridDim.x + x) * SC_NACC + t));
+                v = e_add(v, e_make(q.x, q.y));
+            }
+            for (int d = 16; d > 0; d >>= 1) v = e_add(v, shfl_down_e(v, d));
+            if (threadIdx.x == 0) st_e(out + (u64)blockIdx.y * SC_NACC + t, v);
+        }
+        if (threadIdx.x == 0) counters[blockIdx.y] = 0;
+    }
+}
+
+struct ScFin { const void *src; u32 mode; u32 len; };
+__global__ void k_sc_final(const ScFin *__restrict__ f, u32 n, gle r, gle *__restrict__ out) {
+    u32 m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    ScFin d = f[m];
+    gle v;
+    if (d.len == 1) v = d.mode == OPM_E ? ld_e((const gle *)d.src) : e_from_base(*(const u64 *)d.src);
+    else if (d.mode == OPM_E) { const gle *s = (const gle *)d.src; v = fold_e(ld_e(s), ld_e(s + 1), r); }
+    else { ulonglong2 q = ld_b2((const u64 *)d.src); v = fold_b(q.x, q.y, r); }
+    st_e(out + m, v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct ScMle {
+    const void *cur = nullptr; u64 len = 0; bool is_ext = false;
+    gle *work = nullptr;  // [len0/2 + len0/4] E: ping (offset 0) / pong (offset len0/2)
+    u64 len0 = 0; int where = 0;  // 0 = caller's input, 1 = ping, 2 = pong
+};
+struct dp_sc {
+    u32 n_mles = 0, n_products = 0, max_nv = 0, max_deg = 0, round = 0;
+    bool finished = false;
+    std::vector<ScMle> mles;
+    std::vector<dp_sc_product> products;
+    ScProd *d_descs = nullptr, *h_descs = nullptr;
+    gle *d_partials = nullptr, *d_out = nullptr, *h_out = nullptr;
+    u32 *d_counters = nullptr;
+    ScFin *d_fin = nullptr, *h_fin = nullptr;
+    int gx = 1;
+    std::vector<gle> challenges;
+    u64 last_bytes = 0;
+};
+
+static u32 ceil_log2_u64(u64 x) { u32 l = 0; while ((1ULL << l) < x) l++; return l; }
+
+// barycentric extrapolation of a degree-(n-1) polynomial given at 0..n-1 to the point `at`
+// (sumcheck/src/util.rs:19-136; exact arithmetic, so plain Lagrange gives the same element)
+static gle sc_extrapolate(const gle *evals, u32 n, u64 at) {
+    gle res = e_zero();
+    for (u32 j = 0; j < n; j++) {
+        u64 num = 1, den = 1;
+        for (u32 i = 0; i < n; i++) if (i != j) {
+            num = gl_mul(num, gl_sub(gl_canon(at), (u64)i));
+            den = gl_mul(den, gl_sub((u64)j, (u64)i));
+        }
+        res = e_add(res, e_mul_base(evals[j], gl_mul(num, gl_inv(den))));
+    }
+    return res;
+}
+
+static int sc_free_all(dp_sc *s) {
+    for (auto &m : s->mles) if (m.work) { dp_dev_free(m.work); m.work = nullptr; }
+    dp_dev_free(s->d_descs); dp_dev_free(s->d_partials); dp_dev_free(s->d_out); dp_dev_free(s->d_counters); dp_dev_free(s->d_fin);
+    if (s->h_descs) cudaFreeHost(s->h_descs);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->h_fin) cudaFreeHost(s->h_fin);
+    return DP_OK;
+}
+
+extern "C" {
+
+int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *products, uint32_t n_products,
+                 uint32_t max_nv, uint32_t max_deg, dp_sc **out) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(mles && products && out && n_mles > 0 && n_products > 0, DP_ERR_INVALID, "dp_sc_create: null/empty argument");
+    DP_CHECK(max_nv != 0, DP_ERR_INVALID, "Attempt to prove a constant.");  // prover.rs:590-593
+    DP_CHECK(max_nv <= 40, DP_ERR_INVALID, "dp_sc_create: max_num_variables too large");
+    u32 seen_deg = 0;
+    for (u32 p = 0; p < n_products; p++) {
+        const dp_sc_product &pr = products[p];
+        DP_CHECK(pr.n_idx >= 1, DP_ERR_INVALID, "input mle_list is empty");  // virtual_poly.rs:143
+        DP_CHECK(pr.n_idx <= 5, DP_ERR_UNSUPPORTED, "do not support degree > 5");  // prover.rs:710
+        for (u32 j = 0; j < pr.n_idx; j++) {
+            DP_CHECK(pr.idx[j] < n_mles, DP_ERR_INVALID, "dp_sc_create: product index out of range");
+            const dp_mle *m = mles[pr.idx[j]];
+            DP_CHECK(m != nullptr, DP_ERR_INVALID, "dp_sc_create: null MLE");
+            DP_CHECK(m->num_vars() <= max_nv, DP_ERR_INVALID, "invalid max num vars");  // virtual_poly.rs:151-154
+            DP_CHECK(m->len == mles[pr.idx[0]]->len, DP_ERR_INVALID, "mle in mle_list must be in same num_vars() in same product");
+        }
+        seen_deg = std::max(seen_deg, pr.n_idx);
+    }
+    DP_CHECK(seen_deg <= max_deg, DP_ERR_INVALID, "dp_sc_create: max_degree smaller than a product's degree");
+    dp_sc *s = new dp_sc();
+    s->n_mles = n_mles; s->n_products = n_products; s->max_nv = max_nv; s->max_deg = max_deg;
+    s->mles.resize(n_mles);
+    u64 max_pairs = 1;
+    for (u32 i = 0; i < n_mles; i++) {
+        ScMle &m = s->mles[i];
+        m.cur = mles[i]->data; m.len = m.len0 = mles[i]->len; m.is_ext = mles[i]->is_ext; m.where = 0;
+        max_pairs = std::max<u64>(max_pairs, m.len >> 1);
+    }
+    s->products.assign(products, products + n_products);
+    for (auto &pr : s->products) { pr.coef[0] = gl_canon(pr.coef[0]); pr.coef[1] = gl_canon(pr.coef[1]); }
+    s->gx = dp_grid_for(max_pairs, SC_THREADS, 4);
+    int e = 0;
+    if ((e = dp_dev_alloc((void **)&s->d_descs, sizeof(ScProd) * n_products))) return e;
+    if ((e = dp_dev_alloc((void **)&s->d_partials, sizeof(gle) * SC_NACC * (size_t)s->gx * n_products))) return e;
+    if ((e = dp_dev_alloc((void **)&s->d_out, sizeof(gle) * SC_NACC * n_products))) return e;
+    if ((e = dp_dev_alloc((void **)&s->d_counters, sizeof(u32) * n_products))) return e;
+    if ((e = dp_dev_alloc((void **)&s->d_fin, sizeof(ScFin) * n_mles + sizeof(gle) * n_mles))) return e;
+    DP_CUDA(cudaMemsetAsync(s->d_counters, 0, sizeof(u32) * n_products, dp_ctx().stream));
+    DP_CUDA(cudaHostAlloc((void **)&s->h_descs, sizeof(ScProd) * n_products, cudaHostAllocDefault));
+    DP_CUDA(cudaHostAlloc((void **)&s->h_out, sizeof(gle) * std::max<size_t>(SC_NACC * n_products, n_mles), cudaHostAllocDefault));
+    DP_CUDA(cudaHostAlloc((void **)&s->h_fin, sizeof(ScFin) * n_mles, cudaHostAllocDefault));
+    *out = s;
+    return DP_OK;
+}
+
+int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(s && out_evals, DP_ERR_INVALID, "dp_sc_round: null argument");
+    DP_CHECK(!s->finished && s->round < s->max_nv, DP_ERR_STATE, "Prover is not active");  // prover.rs:636-639
+    gle r = e_zero();
+    bool fold = false;
+    if (s->round == 0) {
+        DP_CHECK(challenge == nullptr, DP_ERR_STATE, "first round should be prover first.");  // prover.rs:655
+    } else {
+        DP_CHECK(challenge != nullptr, DP_ERR_STATE, "verifier message is empty");  // prover.rs:657
+        r = e_make(gl_canon(challenge[0]), gl_canon(challenge[1]));
+        s->challenges.push_back(r);
+        fold = true;
+        if (s->challenges.size() == 1)
+            for (auto &m : s->mles) DP_CHECK(m.len > 1, DP_ERR_INVALID, "calling sumcheck on constant");  // prover.rs:667-669
+    }
+    // plan this round's folds: every MLE with >= 1 variable halves (prover.rs:659-684)
+    std::vector<gle *> dst(s->n_mles, nullptr);
+    std::vector<char> folds(s->n_mles, 0), written(s->n_mles, 0);
+    if (fold) {
+        for (u32 i = 0; i < s->n_mles; i++) {
+            ScMle &m = s->mles[i];
+            if (m.len <= 1) continue;
+            if (!m.work) { if (int e = dp_dev_alloc((void **)&m.work, sizeof(gle) * ((m.len0 >> 1) + (m.len0 >> 2) + 1))) return e; }
+            folds[i] = 1;
+            dst[i] = (m.where == 1) ? m.work + (m.len0 >> 1) : m.work;
+        }
+    }
+    u64 bytes = 0;
+    for (u32 p = 0; p < s->n_products; p++) {
+        const dp_sc_product &pr = s->products[p];
+        ScProd &d = s->h_descs[p];
+        memset(&d, 0, sizeof d);
+        d.d = pr.n_idx;
+        // the macro sorts Ext operands first (sumcheck_macro/src/lib.rs:87-140); multiplication commutes,
+        // so only operand 0 must be an Ext one when the product is mixed (the body multiplies INTO it)
+        u32 order[5]; u32 k = 0;
+        for (u32 j = 0; j < pr.n_idx; j++) { const ScMle &m = s->mles[pr.idx[j]]; if (m.is_ext || folds[pr.idx[j]]) order[k++] = j; }
+        for (u32 j = 0; j < pr.n_idx; j++) { const ScMle &m = s->mles[pr.idx[j]]; if (!(m.is_ext || folds[pr.idx[j]])) order[k++] = j; }
+        bool allbase = true;
+        u64 newlen = 0;
+        for (u32 jj = 0; jj < pr.n_idx; jj++) {
+            u32 mi = pr.idx[order[jj]];
+            const ScMle &m = s->mles[mi];
+            ScOp &op = d.op[jj];
+            op.src = m.cur;
+            if (folds[mi]) {
+                op.mode = m.is_ext ? OPM_EF : OPM_BF;
+                if (!written[mi]) { op.dst = dst[mi]; written[mi] = 1; bytes += (m.len >> 1) * 16; }
+                bytes += m.len * (m.is_ext ? 16 : 8);
+                newlen = m.len >> 1;
+                allbase = false;
+            } else {
+                op.mode = m.is_ext ? OPM_E : OPM_B;
+                bytes += m.len * (m.is_ext ? 16 : 8);
+                newlen = m.len;
+                if (m.is_ext) allbase = false;
+            }
+        }
+        d.allbase = allbase ? 1 : 0;
+        d.konst = newlen == 1 ? 1 : 0;
+        d.npairs = newlen >> 1;
+    }
+    cudaStream_t st = dp_ctx().stream;
+    DP_CUDA(cudaMemcpyAsync(s->d_descs, s->h_descs, sizeof(ScProd) * s->n_products, cudaMemcpyHostToDevice, st));
+    // MLEs no product references still have to be folded (cannot happen through add_mle_list, kept for safety)
+    for (u32 i = 0; i < s->n_mles; i++) if (folds[i] && !written[i]) {
+        ScMle &m = s->mles[i];
+        if (int e = dpk_fold_low(m.cur, m.is_ext, m.len, r, dst[i])) return e;
+    }
+    dim3 grid((unsigned)s->gx, s->n_products);
+    {
+        DpProfScope prof(fold ? "k_sc_round(fold+msg)" : "k_sc_round(msg)", bytes);
+        k_sc_round<<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); DP_LAUNCHED();
+    }
+    DP_CUDA(cudaGetLastError());
+    DP_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(gle) * SC_NACC * s->n_products, cudaMemcpyDeviceToHost, st));
+    // commit the folds to the bookkeeping while the GPU works
+    for (u32 i = 0; i < s->n_mles; i++) if (folds[i]) {
+        ScMle &m = s->mles[i];
+        m.cur = dst[i]; m.where = (dst[i] == m.work) ? 1 : 2; m.len >>= 1; m.is_ext = true;
+    }
+    s->round += 1;
+    s->last_bytes = bytes;
+    DP_CUDA(cudaStreamSynchronize(st));
+    // host glue: multiplicity, coefficient, extrapolation, sum over products (prover.rs:694-733)
+    gle msg[SC_NACC + 1];
+    for (u32 t = 0; t <= s->max_deg; t++) msg[t] = e_zero();
+    for (u32 p = 0; p < s->n_products; p++) {
+        const dp_sc_product &pr = s->products[p];
+        u32 d = pr.n_idx;
+        gle sum[16];
+        u64 len = s->mles[pr.idx[0]].len;
+        u32 l2 = std::max<u32>(ceil_log2_u64(len), 1);
+        int mult = (int)s->max_nv - (int)(l2 + s->round - 1);  // sumcheck_macro/src/lib.rs:242
+        DP_CHECK(mult >= 0, DP_ERR_INVALID, "dp_sc_round: negative num_vars multiplicity");
+        gle coef = e_make(pr.coef[0], pr.coef[1]);
+        for (u32 t = 0; t <= d; t++) {
+            gle v = s->h_out[p * SC_NACC + t];
+            if (mult > 0) v = e_mul_base(v, gl_canon(1ULL << mult));
+            sum[t] = e_mul(v, coef);
+        }
+        for (u32 i = 0; i < s->max_deg - d; i++) sum[d + 1 + i] = sc_extrapolate(sum, d + 1, d + 1 + i);
+        for (u32 t = 0; t <= s->max_deg; t++) msg[t] = e_add(msg[t], sum[t]);
+    }
+    for (u32 t = 0; t <= s->max_deg; t++) { out_evals[2 * t] = msg[t].c0; out_evals[2 * t + 1] = msg[t].c1; }
+    return DP_OK;
+}
+
+int dp_sc_finish(dp_sc *s, const uint64_t *last_challenge, uint64_t *out_final) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(s && last_challenge && out_final, DP_ERR_INVALID, "dp_sc_finish: null argument");
+    DP_CHECK(!s->finished && s->round == s->max_nv, DP_ERR_STATE, "dp_sc_finish: rounds not complete");
+    gle r = e_make(gl_canon(last_challenge[0]), gl_canon(last_challenge[1]));
+    s->challenges.push_back(r);
+    for (u32 i = 0; i < s->n_mles; i++) {
+        const ScMle &m = s->mles[i];
+        // get_mle_final_evaluations asserts len == 1 after the last fix (prover.rs:479-483)
+        DP_CHECK(m.len <= 2, DP_ERR_STATE, "mle.evaluations.len() != 1, must be called after prove_round_and_update_state");
+        s->h_fin[i].src = m.cur; s->h_fin[i].mode = m.is_ext ? OPM_E : OPM_B; s->h_fin[i].len = (u32)m.len;
+    }
+    cudaStream_t st = dp_ctx().stream;
+    gle *d_vals = (gle *)((char *)s->d_fin + sizeof(ScFin) * s->n_mles);
+    // d_fin region: [ScFin x n][gle x n]; ScFin is 16 bytes so the gle part stays 16-byte aligned
+    DP_CUDA(cudaMemcpyAsync(s->d_fin, s->h_fin, sizeof(ScFin) * s->n_mles, cudaMemcpyHostToDevice, st));
+    k_sc_final<<<(s->n_mles + 127) / 128, 128, 0, st>>>(s->d_fin, s->n_mles, r, d_vals); DP_LAUNCHED();
+    DP_CUDA(cudaGetLastError());
+    DP_CUDA(cudaMemcpyAsync(s->h_out, d_vals, sizeof(gle) * s->n_mles, cudaMemcpyDeviceToHost, st));
+    DP_CUDA(cudaStreamSynchronize(st));
+    for (u32 i = 0; i < s->n_mles; i++) { out_final[2 * i] = s->h_out[i].c0; out_final[2 * i + 1] = s->h_out[i].c1; }
+    s->finished = true;
+    return DP_OK;
+}
+
+int dp_sc_destroy(dp_sc *s) {
+    if (!s) return DP_OK;
+    std::lock_guard<std::recursive_mutex> lk(dp_ctx().mu);
+    if (dp_ctx().ready) sc_free_all(s);
+    delete s;
+    return DP_OK;
+}
+
+uint64_t dp_sc_last_round_bytes(const dp_sc *s) { return s ? s->last_bytes : 0; }
+
+}  // extern "C"

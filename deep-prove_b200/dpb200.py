@@ -1,0 +1,282 @@
+"""ctypes view of the product: libdeepprove_b200.so (C ABI, include/deepprove_b200.h) and
+libdeepprove_host.so (C++ host mirror of the reference crates).  Plumbing for tests/bench only --
+a Rust host binds the same C ABI directly.  Never imports anything from oracle/.
+Fails loudly when the CUDA library is missing: there is no CPU fallback.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdeepprove_b200.so")
+HOST_LIB_PATH = os.path.join(_HERE, "libdeepprove_host.so")
+
+P = 0xFFFFFFFF00000001
+DP_OK, DP_ERR_INVALID, DP_ERR_CUDA, DP_ERR_NO_DEVICE, DP_ERR_STATE, DP_ERR_UNSUPPORTED = range(6)
+
+# every symbol include/deepprove_b200.h declares (tests check the .so exports each one)
+ABI_SYMBOLS = [
+    "dp_init", "dp_shutdown", "dp_device_count", "dp_last_error", "dp_version", "dp_set_stream", "dp_synchronize",
+    "dp_kernel_launches", "dp_profile_enable", "dp_profile_reset", "dp_profile_read",
+    "dp_mle_upload", "dp_mle_wrap_device", "dp_mle_clone", "dp_mle_download", "dp_mle_info", "dp_mle_device_ptr",
+    "dp_mle_free", "dp_mle_fix_high", "dp_mle_fix_low", "dp_mle_evaluate", "dp_eq_build",
+    "dp_sc_create", "dp_sc_round", "dp_sc_finish", "dp_sc_destroy", "dp_sc_last_round_bytes",
+]
+
+
+class DpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("deepprove_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class ScProduct(C.Structure):
+    _fields_ = [("coef", C.c_uint64 * 2), ("n_idx", C.c_uint32), ("idx", C.c_uint32 * 5)]
+
+
+_lib = None
+_host = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not built: run `make` (or __graft_entry__.build()); the CUDA extension is "
+                              "mandatory, there is no CPU fallback" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _lib.dp_last_error.restype = C.c_char_p
+        _lib.dp_version.restype = C.c_char_p
+        _lib.dp_kernel_launches.restype = C.c_uint64
+        _lib.dp_mle_device_ptr.restype = C.c_void_p
+        _lib.dp_sc_last_round_bytes.restype = C.c_uint64
+        _lib.dp_mle_device_ptr.argtypes = [C.c_void_p]
+        _lib.dp_sc_last_round_bytes.argtypes = [C.c_void_p]
+        _lib.dp_set_stream.argtypes = [C.c_void_p]
+        _lib.dp_mle_upload.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+        _lib.dp_mle_wrap_device.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+        _lib.dp_mle_clone.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        _lib.dp_mle_download.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.dp_mle_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
+        _lib.dp_mle_free.argtypes = [C.c_void_p]
+        _lib.dp_mle_fix_high.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        _lib.dp_mle_fix_low.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+        _lib.dp_mle_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        _lib.dp_eq_build.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+        _lib.dp_sc_create.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(ScProduct), C.c_uint32, C.c_uint32,
+                                      C.c_uint32, C.POINTER(C.c_void_p)]
+        _lib.dp_sc_round.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.dp_sc_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.dp_sc_destroy.argtypes = [C.c_void_p]
+    return _lib
+
+
+def host():
+    global _host
+    if _host is None:
+        lib()
+        if not os.path.exists(HOST_LIB_PATH):
+            raise ImportError("%s not built: run `make`" % HOST_LIB_PATH)
+        _host = C.CDLL(HOST_LIB_PATH)
+        _host.dph_last_error.restype = C.c_char_p
+        _host.dph_transcript_new.restype = C.c_void_p
+        _host.dph_transcript_new.argtypes = [C.c_char_p]
+        _host.dph_transcript_free.argtypes = [C.c_void_p]
+        _host.dph_transcript_append_f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        _host.dph_transcript_append_msg.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+        _host.dph_transcript_append_e.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        _host.dph_transcript_challenge.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        _host.dph_poseidon2_permute.argtypes = [C.c_void_p]
+        _host.dph_sumcheck_prove_parallel.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(ScProduct), C.c_uint32,
+                                                      C.c_uint32, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.POINTER(C.c_uint32)]
+    return _host
+
+
+def check(rc):
+    if rc != 0:
+        raise DpError(rc, lib().dp_last_error().decode())
+
+
+def hcheck(rc):
+    if rc != 0:
+        raise DpError(rc, host().dph_last_error().decode())
+
+
+def init(device=0):
+    check(lib().dp_init(int(device)))
+
+
+def device_count():
+    return lib().dp_device_count()
+
+
+def use_torch_stream():
+    """Launch on torch's current CUDA stream so torch.cuda.Event brackets our kernels."""
+    import torch
+    check(lib().dp_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+def _u64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Mle:
+    """Device-resident DenseMultilinearExtension (handle owner)."""
+
+    def __init__(self, handle, keepalive=None):
+        self.h = C.c_void_p(handle)
+        self._keep = keepalive
+
+    @staticmethod
+    def upload(evals, is_ext):
+        a = _u64(evals).reshape(-1)
+        n = a.size // (2 if is_ext else 1)
+        h = C.c_void_p()
+        check(lib().dp_mle_upload(_ptr(a), n, int(bool(is_ext)), C.byref(h)))
+        return Mle(h.value)
+
+    @staticmethod
+    def wrap_torch(t, is_ext):
+        """Non-owning view of a torch int64/uint64 CUDA tensor holding canonical limbs."""
+        n = t.numel() // (2 if is_ext else 1)
+        h = C.c_void_p()
+        check(lib().dp_mle_wrap_device(C.c_void_p(t.data_ptr()), n, int(bool(is_ext)), C.byref(h)))
+        return Mle(h.value, keepalive=t)
+
+    @staticmethod
+    def eq(point):
+        p = _u64(point).reshape(-1)
+        h = C.c_void_p()
+        check(lib().dp_eq_build(_ptr(p), p.size // 2, C.byref(h)))
+        return Mle(h.value)
+
+    def info(self):
+        ln, ext, nv = C.c_uint64(), C.c_int(), C.c_uint32()
+        check(lib().dp_mle_info(self.h, C.byref(ln), C.byref(ext), C.byref(nv)))
+        return ln.value, bool(ext.value), nv.value
+
+    def download(self):
+        ln, ext, _ = self.info()
+        out = np.empty(ln * (2 if ext else 1), dtype=np.uint64)
+        check(lib().dp_mle_download(self.h, _ptr(out)))
+        return out.reshape(-1, 2) if ext else out
+
+    def fix_high(self, point):
+        p = _u64(point).reshape(-1)
+        check(lib().dp_mle_fix_high(self.h, _ptr(p), p.size // 2))
+        return self
+
+    def fix_low(self, point):
+        p = _u64(point).reshape(-1)
+        h = C.c_void_p()
+        check(lib().dp_mle_fix_low(self.h, _ptr(p), p.size // 2, C.byref(h)))
+        return Mle(h.value)
+
+    def evaluate(self, point):
+        p = _u64(point).reshape(-1)
+        out = np.zeros(2, dtype=np.uint64)
+        check(lib().dp_mle_evaluate(self.h, _ptr(p), p.size // 2, _ptr(out)))
+        return out
+
+    def clone(self):
+        h = C.c_void_p()
+        check(lib().dp_mle_clone(self.h, C.byref(h)))
+        return Mle(h.value)
+
+    def free(self):
+        if self.h:
+            lib().dp_mle_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def profile_enable(on=True):
+    check(lib().dp_profile_enable(int(on)))
+
+
+def profile_reset():
+    check(lib().dp_profile_reset())
+
+
+def profile_read(cap=64):
+    """-> {kernel name: (launches, total_ms, algorithmic_bytes)}"""
+    names = ((C.c_char * 64) * cap)()
+    counts = (C.c_uint64 * cap)()
+    ms = (C.c_double * cap)()
+    by = (C.c_uint64 * cap)()
+    n = lib().dp_profile_read(names, counts, ms, by, cap)
+    return {names[i].value.decode(): (counts[i], ms[i], by[i]) for i in range(min(n, cap))}
+
+
+def make_products(products):
+    """products: list of (coef (c0,c1), [mle indices])"""
+    arr = (ScProduct * len(products))()
+    for i, (coef, idx) in enumerate(products):
+        arr[i].coef[0], arr[i].coef[1] = int(coef[0]), int(coef[1])
+        arr[i].n_idx = len(idx)
+        for j, v in enumerate(idx[:5]):
+            arr[i].idx[j] = int(v)
+    return arr
+
+
+class Sumcheck:
+    """Round-granular device sumcheck prover (dp_sc_*)."""
+
+    def __init__(self, mles, products, max_nv, max_deg):
+        self.mles = list(mles)
+        hs = (C.c_void_p * len(mles))(*[m.h for m in mles])
+        self.prods = make_products(products)
+        self.max_deg = max_deg
+        self.h = C.c_void_p()
+        check(lib().dp_sc_create(hs, len(mles), self.prods, len(products), max_nv, max_deg, C.byref(self.h)))
+
+    def round(self, challenge=None):
+        out = np.zeros(2 * (self.max_deg + 1), dtype=np.uint64)
+        c = None if challenge is None else _u64(challenge)
+        check(lib().dp_sc_round(self.h, None if c is None else _ptr(c), _ptr(out)))
+        return out.reshape(-1, 2)
+
+    def finish(self, challenge):
+        out = np.zeros(2 * len(self.mles), dtype=np.uint64)
+        c = _u64(challenge)
+        check(lib().dp_sc_finish(self.h, _ptr(c), _ptr(out)))
+        return out.reshape(-1, 2)
+
+    def last_round_bytes(self):
+        return lib().dp_sc_last_round_bytes(self.h)
+
+    def destroy(self):
+        if self.h:
+            lib().dp_sc_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def sumcheck_prove_parallel(mles, products, max_nv, label=b"m2vec"):
+    """IOPProverState::prove_parallel through the C++ host mirror (host Poseidon2 Fiat-Shamir).
+    Returns (point[nv,2], msgs[nv,deg+1,2], final_evals[n_mles,2])."""
+    hs = (C.c_void_p * len(mles))(*[m.h for m in mles])
+    prods = make_products(products)
+    max_deg = max(len(p[1]) for p in products)
+    point = np.zeros((max_nv, 2), dtype=np.uint64)
+    msgs = np.zeros((max_nv, max_deg + 1, 2), dtype=np.uint64)
+    fin = np.zeros((len(mles), 2), dtype=np.uint64)
+    deg = C.c_uint32()
+    hcheck(host().dph_sumcheck_prove_parallel(hs, len(mles), prods, len(products), max_nv, label, None, _ptr(point),
+                                              _ptr(msgs), _ptr(fin), C.byref(deg)))
+    return point, msgs, fin

@@ -1,0 +1,58 @@
+// C entry points over the host mirror (for the Python tests / bench; a Rust caller would use its own
+// crates above include/deepprove_b200.h instead).  Nothing here touches oracle/.
+#include "sumcheck.hpp"
+
+using namespace dp;
+static thread_local std::string g_herr;
+#define DPH_TRY try {
+#define DPH_CATCH } catch (const Error &e) { g_herr = e.what(); return e.code ? e.code : 1; } catch (const std::exception &e) { g_herr = e.what(); return 1; }
+
+extern "C" {
+
+const char *dph_last_error() { return g_herr.c_str(); }
+
+void dph_poseidon2_permute(uint64_t *state) { Poseidon2::permute(state); }
+
+void *dph_transcript_new(const char *label) { return new BasicTranscript(label); }
+void dph_transcript_free(void *t) { delete (BasicTranscript *)t; }
+void dph_transcript_append_f(void *t, const uint64_t *f, uint64_t n) { for (uint64_t i = 0; i < n; i++) ((BasicTranscript *)t)->append_field_element(f[i]); }
+void dph_transcript_append_msg(void *t, const uint8_t *m, uint64_t n) { ((BasicTranscript *)t)->append_message(m, n); }
+void dph_transcript_append_e(void *t, const uint64_t *e, uint64_t n) { for (uint64_t i = 0; i < n; i++) ((BasicTranscript *)t)->append_field_element_ext(Ext(e[2 * i], e[2 * i + 1])); }
+void dph_transcript_challenge(void *t, const char *label, uint64_t *out) { Ext c = ((BasicTranscript *)t)->get_and_append_challenge(label); out[0] = c.c0; out[1] = c.c1; }
+
+// IOPProverState::prove_parallel over device MLE handles with BasicTranscript::new(label) (or an
+// existing transcript when `transcript` is non-null).  out_msgs: nv x (max_deg+1) x E.
+int dph_sumcheck_prove_parallel(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *products, uint32_t n_products,
+                                uint32_t max_nv, const char *label, void *transcript, uint64_t *out_point, uint64_t *out_msgs,
+                                uint64_t *out_final, uint32_t *out_max_deg) {
+    DPH_TRY
+    VirtualPolynomial vp(max_nv);
+    std::vector<DeviceMle> views;
+    for (uint32_t i = 0; i < n_mles; i++) {
+        uint64_t len; int ext; check(dp_mle_info(mles[i], &len, &ext, nullptr));
+        views.push_back(DeviceMle::wrap_device(dp_mle_device_ptr(mles[i]), len, ext));
+    }
+    // register in caller order so final evaluations line up with `mles`
+    for (uint32_t p = 0; p < n_products; p++) {
+        std::vector<DeviceMle> l;
+        for (uint32_t j = 0; j < products[p].n_idx; j++) l.push_back(views.at(products[p].idx[j]));
+        vp.add_mle_list(l, Ext(products[p].coef[0], products[p].coef[1]));
+    }
+    std::vector<uint32_t> remap(n_mles, UINT32_MAX);
+    for (size_t k = 0; k < vp.flattened_ml_extensions.size(); k++)
+        for (uint32_t i = 0; i < n_mles; i++) if (vp.flattened_ml_extensions[k].handle() == views[i].handle()) remap[i] = (uint32_t)k;
+    BasicTranscript local(label ? label : "");
+    BasicTranscript &t = transcript ? *(BasicTranscript *)transcript : local;
+    auto res = IOPProverState::prove_parallel(std::move(vp), t);
+    size_t deg = res.first.proofs.empty() ? 0 : res.first.proofs[0].evaluations.size() - 1;
+    *out_max_deg = (uint32_t)deg;
+    for (size_t i = 0; i < res.first.point.size(); i++) { out_point[2 * i] = res.first.point[i].c0; out_point[2 * i + 1] = res.first.point[i].c1; }
+    size_t k = 0;
+    for (auto &m : res.first.proofs) for (auto &e : m.evaluations) { out_msgs[2 * k] = e.c0; out_msgs[2 * k + 1] = e.c1; k++; }
+    const ExtVec &fin = res.second.get_mle_final_evaluations();
+    for (uint32_t i = 0; i < n_mles; i++) if (remap[i] != UINT32_MAX && remap[i] < fin.size()) { out_final[2 * i] = fin[remap[i]].c0; out_final[2 * i + 1] = fin[remap[i]].c1; }
+    return 0;
+    DPH_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// Host mirror of the reference's `multilinear_extensions` + `sumcheck` public API over the C ABI.
+//   DeviceMle            <-> DenseMultilinearExtension      (multilinear_extensions/src/mle.rs:130-181)
+//   VirtualPolynomial    <-> VirtualPolynomial               (virtual_poly.rs:50-180)
+//   IOPProverState::prove_parallel, IOPProof, get_mle_final_evaluations (sumcheck/src/prover.rs:498-585,
+//   :474-490; structs.rs:15-34)
+// Same names, argument meaning and error behaviour: where the reference asserts/panics this throws
+// dp::Error carrying the reference's message.
+#pragma once
+#include "field.hpp"
+#include "transcript.hpp"
+#include "../../include/deepprove_b200.h"
+#include <memory>
+#include <map>
+
+namespace dp {
+
+struct Error : std::runtime_error { int code; Error(int c, const std::string &m) : std::runtime_error(m), code(c) {} };
+inline void check(int rc) { if (rc != DP_OK) throw Error(rc, dp_last_error()); }
+
+class DeviceMle {
+  public:
+    DeviceMle() {}
+    explicit DeviceMle(dp_mle *h) : h_(h, [](dp_mle *p) { dp_mle_free(p); }) {}
+    static DeviceMle from_evaluations_vec(const std::vector<u64> &base) { dp_mle *h; check(dp_mle_upload(base.data(), base.size(), 0, &h)); return DeviceMle(h); }
+    static DeviceMle from_evaluations_ext_vec(const ExtVec &ext) { auto f = flatten(ext); dp_mle *h; check(dp_mle_upload(f.data(), ext.size(), 1, &h)); return DeviceMle(h); }
+    static DeviceMle from_raw(const u64 *data, u64 len, bool is_ext) { dp_mle *h; check(dp_mle_upload(data, len, is_ext, &h)); return DeviceMle(h); }
+    static DeviceMle wrap_device(void *ptr, u64 len, bool is_ext) { dp_mle *h; check(dp_mle_wrap_device(ptr, len, is_ext, &h)); return DeviceMle(h); }
+    static DeviceMle build_eq_x_r(const ExtVec &r) { auto f = flatten(r); dp_mle *h; check(dp_eq_build(f.data(), (uint32_t)r.size(), &h)); return DeviceMle(h); }
+    dp_mle *handle() const { return h_.get(); }
+    bool valid() const { return (bool)h_; }
+    u64 len() const { u64 l; check(dp_mle_info(h_.get(), &l, nullptr, nullptr)); return l; }
+    bool is_ext() const { int e; check(dp_mle_info(h_.get(), nullptr, &e, nullptr)); return e != 0; }
+    uint32_t num_vars() const { uint32_t n; check(dp_mle_info(h_.get(), nullptr, nullptr, &n)); return n; }
+    Ext evaluate(const ExtVec &point) const { auto f = flatten(point); u64 o[2]; check(dp_mle_evaluate(h_.get(), f.data(), (uint32_t)point.size(), o)); return Ext(o[0], o[1]); }
+    void fix_high_variables_in_place(const ExtVec &point) { auto f = flatten(point); check(dp_mle_fix_high(h_.get(), f.data(), (uint32_t)point.size())); }
+    DeviceMle fix_variables(const ExtVec &point) const { auto f = flatten(point); dp_mle *o; check(dp_mle_fix_low(h_.get(), f.data(), (uint32_t)point.size(), &o)); return DeviceMle(o); }
+    DeviceMle clone() const { dp_mle *o; check(dp_mle_clone(h_.get(), &o)); return DeviceMle(o); }
+    std::vector<u64> download() const { std::vector<u64> v(len() * (is_ext() ? 2 : 1)); check(dp_mle_download(h_.get(), v.data())); return v; }
+  private:
+    std::shared_ptr<dp_mle> h_;
+};
+
+struct VPAuxInfo { size_t max_degree = 0, max_num_variables = 0; };
+
+class VirtualPolynomial {
+  public:
+    explicit VirtualPolynomial(size_t max_num_variables = 0) { aux_info.max_num_variables = max_num_variables; }
+    // add_mle_list: MLE identity is the device handle, as the reference's is the Arc pointer
+    void add_mle_list(const std::vector<DeviceMle> &list, Ext coefficient) {
+        if (list.empty()) throw Error(DP_ERR_INVALID, "input mle_list is empty");
+        dp_sc_product pr{};
+        pr.coef[0] = coefficient.c0; pr.coef[1] = coefficient.c1;
+        if (list.size() > 5) throw Error(DP_ERR_UNSUPPORTED, "do not support degree > 5");
+        for (auto &m : list) {
+            if (m.num_vars() > aux_info.max_num_variables) throw Error(DP_ERR_INVALID, "invalid max num vars");
+            if (m.num_vars() != list[0].num_vars()) throw Error(DP_ERR_INVALID, "mle in mle_list must be in same num_vars() in same product");
+            auto it = index_.find(m.handle());
+            uint32_t id;
+            if (it == index_.end()) { id = (uint32_t)flattened_ml_extensions.size(); flattened_ml_extensions.push_back(m); index_[m.handle()] = id; }
+            else id = it->second;
+            pr.idx[pr.n_idx++] = id;
+        }
+        if (list.size() > aux_info.max_degree) aux_info.max_degree = list.size();
+        products.push_back(pr);
+    }
+    VPAuxInfo aux_info;
+    std::vector<dp_sc_product> products;
+    std::vector<DeviceMle> flattened_ml_extensions;
+  private:
+    std::map<dp_mle *, uint32_t> index_;
+};
+
+struct IOPProverMessage { ExtVec evaluations; };
+struct IOPProof {
+    ExtVec point;
+    std::vector<IOPProverMessage> proofs;
+    Ext extract_sum() const { return proofs.at(0).evaluations.at(0) + proofs.at(0).evaluations.at(1); }
+};
+
+class IOPProverState {
+  public:
+    ~IOPProverState() { if (sc_) dp_sc_destroy(sc_); }
+    IOPProverState() {}
+    IOPProverState(IOPProverState &&o) noexcept { *this = std::move(o); }
+    IOPProverState &operator=(IOPProverState &&o) noexcept { std::swap(sc_, o.sc_); challenges = std::move(o.challenges); finals_ = std::move(o.finals_); poly_ = std::move(o.poly_); return *this; }
+    ExtVec challenges;
+    const ExtVec &get_mle_final_evaluations() const { return finals_; }
+
+    // IOPProverState::prove_parallel(poly, transcript) -> (IOPProof, IOPProverState)
+    template <class T>
+    static std::pair<IOPProof, IOPProverState> prove_parallel(VirtualPolynomial poly, T &transcript) {
+        IOPProof proof; IOPProverState st;
+        size_t nv = poly.aux_info.max_num_variables, deg = poly.aux_info.max_degree;
+        if (nv == 0) return {std::move(proof), std::move(st)};  // constant polynomial: IOPProof::default()
+        transcript.append_usize(nv);
+        transcript.append_usize(deg);
+        std::vector<dp_mle *> hs;
+        for (auto &m : poly.flattened_ml_extensions) hs.push_back(m.handle());
+        check(dp_sc_create(hs.data(), (uint32_t)hs.size(), poly.products.data(), (uint32_t)poly.products.size(), (uint32_t)nv, (uint32_t)deg, &st.sc_));
+        std::vector<u64> buf(2 * (deg + 1));
+        Ext challenge; bool have = false;
+        for (size_t i = 0; i < nv; i++) {
+            u64 c[2] = {challenge.c0, challenge.c1};
+            check(dp_sc_round(st.sc_, have ? c : nullptr, buf.data()));
+            IOPProverMessage msg;
+            for (size_t t = 0; t <= deg; t++) msg.evaluations.push_back(Ext(buf[2 * t], buf[2 * t + 1]));
+            transcript.append_field_element_exts(msg.evaluations);
+            proof.proofs.push_back(std::move(msg));
+            challenge = transcript.get_and_append_challenge("Internal round"); have = true;
+            st.challenges.push_back(challenge);
+        }
+        u64 c[2] = {challenge.c0, challenge.c1};
+        std::vector<u64> fin(2 * hs.size());
+        check(dp_sc_finish(st.sc_, c, fin.data()));
+        for (size_t i = 0; i < hs.size(); i++) st.finals_.push_back(Ext(fin[2 * i], fin[2 * i + 1]));
+        proof.point = st.challenges;
+        st.poly_ = std::move(poly);
+        return {std::move(proof), std::move(st)};
+    }
+  private:
+    dp_sc *sc_ = nullptr;
+    ExtVec finals_;
+    VirtualPolynomial poly_;
+};
+
+}  // namespace dp

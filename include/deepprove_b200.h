@@ -1,0 +1,103 @@
+/* deepprove_b200 -- C ABI of the B200-native (sm_100a) prover hot path.
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b): the entry points a Rust `-sys` crate would
+ * bind so that deep-prove's `sumcheck`, `multilinear_extensions` and `mpcs` crates keep their public
+ * API while their O(n) loops run on the GPU.  Fiat-Shamir (transcript), proof structs and the verifier
+ * stay on the host, so the API is ROUND-GRANULAR: the host appends each prover message to its
+ * transcript and hands the squeezed challenge back.
+ *
+ * Conventions
+ *   - F = Goldilocks (p = 2^64 - 2^32 + 1) as one little-endian uint64 limb, canonical (< p) on output;
+ *     inputs may be any u64 (they are canonicalised on upload).
+ *   - E = GoldilocksExt2 = F[X]/(X^2-7) as two limbs [c0, c1]  (ff_ext/src/lib.rs:13).
+ *   - MLE evaluations: little-endian hypercube index, Base = len x u64, Ext = len x [c0,c1] (AoS),
+ *     exactly `DenseMultilinearExtension.evaluations` (multilinear_extensions/src/mle.rs:130-181).
+ *   - Every function returns an int status (DP_OK = 0) and never unwinds across the FFI; the Rust shim
+ *     maps non-zero to `panic!`/`Err` to keep the reference behaviour.  dp_last_error() gives the text.
+ *   - A handle is used by one host thread at a time; the library serialises access to the device
+ *     context internally (PCS::commit is called from rayon workers in the reference).
+ *   - No CPU fallback exists: without a CUDA device every compute entry point returns DP_ERR_NO_DEVICE.
+ */
+#ifndef DEEPPROVE_B200_H
+#define DEEPPROVE_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_OK 0
+#define DP_ERR_INVALID 1      /* bad argument (the reference would assert!/panic) */
+#define DP_ERR_CUDA 2         /* CUDA runtime error */
+#define DP_ERR_NO_DEVICE 3    /* no usable GPU / dp_init not called */
+#define DP_ERR_STATE 4        /* call out of protocol order ("Prover is not active", ...) */
+#define DP_ERR_UNSUPPORTED 5  /* e.g. product degree > 5 (sumcheck/src/prover.rs:710) */
+
+typedef struct dp_mle dp_mle; /* device-resident DenseMultilinearExtension */
+typedef struct dp_sc dp_sc;   /* IOPProverState (sumcheck/src/structs.rs:37-48) on device */
+
+/* ---- context -------------------------------------------------------------------------------- */
+int dp_init(int device);                 /* select GPU `device`, create stream + memory pool */
+int dp_shutdown(void);
+int dp_device_count(void);               /* 0 when no GPU is visible; never fails */
+const char *dp_last_error(void);
+const char *dp_version(void);
+int dp_set_stream(void *cuda_stream);    /* run on a caller-owned cudaStream_t (e.g. torch's current stream) */
+int dp_synchronize(void);
+uint64_t dp_kernel_launches(void);       /* number of kernels this library launched so far */
+/* Per-kernel timing with CUDA events recorded on the launch stream around each hot kernel (off by
+ * default).  dp_profile_read fills parallel arrays (kernel name, launches, summed ms, summed algorithmic
+ * bytes per SURVEY.md 8(d)) and returns the number of distinct kernels. */
+int dp_profile_enable(int on);
+int dp_profile_reset(void);
+int dp_profile_read(char (*names)[64], uint64_t *counts, double *total_ms, uint64_t *bytes, int cap);
+
+/* ---- multilinear_extensions ------------------------------------------------------------------ */
+/* DenseMultilinearExtension::from_evaluations_vec / _ext_vec (mle.rs:183-260): copy host -> HBM. */
+int dp_mle_upload(const uint64_t *evals, uint64_t len, int is_ext, dp_mle **out);
+/* Non-owning view of `len` elements already resident in HBM (must be canonical). */
+int dp_mle_wrap_device(void *dev_ptr, uint64_t len, int is_ext, dp_mle **out);
+int dp_mle_clone(const dp_mle *m, dp_mle **out);
+int dp_mle_download(const dp_mle *m, uint64_t *out_evals);
+int dp_mle_info(const dp_mle *m, uint64_t *len, int *is_ext, uint32_t *num_vars);
+void *dp_mle_device_ptr(const dp_mle *m);
+int dp_mle_free(dp_mle *m);
+/* fix_high_variables_in_place (mle.rs:562-603): fixes the TOP k variables at `point` (k x [c0,c1]),
+ * i.e. for r in point.rev(): lo[i] += (hi[i]-lo[i])*r.  The MLE becomes Ext with num_vars - k. */
+int dp_mle_fix_high(dp_mle *m, const uint64_t *point, uint32_t k);
+/* fix_variables (mle.rs:454-484): fixes the LOW k variables (adjacent pairs), returns a new MLE. */
+int dp_mle_fix_low(const dp_mle *m, const uint64_t *point, uint32_t k, dp_mle **out);
+/* evaluate (mle.rs:607-623): point has num_vars elements; out = [c0,c1]. */
+int dp_mle_evaluate(const dp_mle *m, const uint64_t *point, uint32_t num_vars, uint64_t out[2]);
+/* build_eq_x_r_vec (virtual_poly.rs:414-453) == compute_betas_eval (zkml/src/commit/mod.rs:10-28). */
+int dp_eq_build(const uint64_t *point, uint32_t num_vars, dp_mle **out);
+
+/* ---- sumcheck -------------------------------------------------------------------------------- */
+/* One term  coef * prod_j mles[idx[j]]  of a VirtualPolynomial (virtual_poly.rs:50-60). */
+typedef struct dp_sc_product {
+    uint64_t coef[2];
+    uint32_t n_idx;   /* 1..5 */
+    uint32_t idx[5];
+} dp_sc_product;
+
+/* IOPProverState::prover_init_parallel (sumcheck/src/prover.rs:588-612).  Input MLEs are BORROWED and
+ * never modified (the reference clones on the first fold, prover.rs:659-670); they must stay alive
+ * until dp_sc_destroy.  All MLEs of one product must have equal length (virtual_poly.rs:148-160). */
+int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *products, uint32_t n_products,
+                 uint32_t max_num_variables, uint32_t max_degree, dp_sc **out);
+/* prove_round_and_update_state_parallel (prover.rs:625-741): `challenge` is NULL in round 0 and the
+ * previous round's challenge [c0,c1] afterwards.  out_evals receives (max_degree+1) x [c0,c1]:
+ * the round polynomial at 0..max_degree, products already scaled, extrapolated and summed. */
+int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals);
+/* Tail of prove_parallel (prover.rs:544-568) + get_mle_final_evaluations (:474-490): fixes the last
+ * challenge and writes n_mles x [c0,c1]. */
+int dp_sc_finish(dp_sc *s, const uint64_t *last_challenge, uint64_t *out_final_evals);
+int dp_sc_destroy(dp_sc *s);
+/* Algorithmic HBM bytes moved by the last dp_sc_round (SURVEY.md 8(d) rules), for roofline reports. */
+uint64_t dp_sc_last_round_bytes(const dp_sc *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPPROVE_B200_H */

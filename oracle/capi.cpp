@@ -1,0 +1,137 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  C entry points (ctypes) over the CPU restatement.
+// Loaded only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg.
+#include "sumcheck.hpp"
+#include <thread>
+#include <string>
+
+using namespace dpo;
+
+static std::shared_ptr<MLE> mk_mle(const u64 *data, u64 len, int is_ext) {
+    auto m = std::make_shared<MLE>();
+    m->is_ext = is_ext != 0; m->num_vars = ceil_log2(len);
+    if (is_ext) { m->ext.resize(len); for (u64 i = 0; i < len; i++) m->ext[i] = E(f_from_u64(data[2 * i]), f_from_u64(data[2 * i + 1])); }
+    else { m->base.resize(len); for (u64 i = 0; i < len; i++) m->base[i] = f_from_u64(data[i]); }
+    return m;
+}
+static std::vector<E> mk_point(const u64 *p, u32 k) { std::vector<E> v(k); for (u32 i = 0; i < k; i++) v[i] = E(f_from_u64(p[2 * i]), f_from_u64(p[2 * i + 1])); return v; }
+static void put_e(u64 *out, size_t i, E e) { out[2 * i] = e.c0; out[2 * i + 1] = e.c1; }
+static thread_local std::string g_err;
+
+extern "C" {
+
+const char *dpo_last_error() { return g_err.c_str(); }
+int dpo_num_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// ---- field (vectorised, for the device-arithmetic tests) ----
+void dpo_f_binop(int op, const u64 *a, const u64 *b, u64 n, u64 *out) {
+    for (u64 i = 0; i < n; i++) {
+        u64 x = f_from_u64(a[i]), y = f_from_u64(b[i]);
+        out[i] = op == 0 ? f_add(x, y) : op == 1 ? f_sub(x, y) : f_mul(x, y);
+    }
+}
+void dpo_e_binop(int op, const u64 *a, const u64 *b, u64 n, u64 *out) {
+    for (u64 i = 0; i < n; i++) {
+        E x(f_from_u64(a[2 * i]), f_from_u64(a[2 * i + 1])), y(f_from_u64(b[2 * i]), f_from_u64(b[2 * i + 1]));
+        put_e(out, i, op == 0 ? e_add(x, y) : op == 1 ? e_sub(x, y) : e_mul(x, y));
+    }
+}
+void dpo_e_inv(const u64 *a, u64 n, u64 *out) { for (u64 i = 0; i < n; i++) put_e(out, i, e_inv(E(a[2 * i], a[2 * i + 1]))); }
+void dpo_splitmix_f(u64 seed, u64 n, u64 *out) { SplitMix64 g(seed); for (u64 i = 0; i < n; i++) out[i] = g.next_f(); }
+
+// ---- MLE ----
+int dpo_fix_high(const u64 *evals, u64 len, int is_ext, const u64 *point, u32 k, u64 *out) {
+    try { MLE r = mle_fix_high_variables(*mk_mle(evals, len, is_ext), mk_point(point, k)); for (size_t i = 0; i < r.len(); i++) put_e(out, i, r.get(i)); return 0; }
+    catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int dpo_fix_low(const u64 *evals, u64 len, int is_ext, const u64 *point, u32 k, u64 *out) {
+    try { MLE r = mle_fix_variables(*mk_mle(evals, len, is_ext), mk_point(point, k)); for (size_t i = 0; i < r.len(); i++) put_e(out, i, r.get(i)); return 0; }
+    catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int dpo_evaluate(const u64 *evals, u64 len, int is_ext, const u64 *point, u32 nv, u64 *out) {
+    try { put_e(out, 0, mle_evaluate(*mk_mle(evals, len, is_ext), mk_point(point, nv))); return 0; }
+    catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+void dpo_build_eq(const u64 *point, u32 nv, u64 *out) { auto v = build_eq_x_r_vec(mk_point(point, nv)); for (size_t i = 0; i < v.size(); i++) put_e(out, i, v[i]); }
+void dpo_eq_eval(const u64 *x, const u64 *y, u32 n, u64 *out) { put_e(out, 0, eq_eval(mk_point(x, n), mk_point(y, n))); }
+
+// ---- Poseidon2 / challenger / transcript ----
+void dpo_poseidon2_permute(u64 *state) { poseidon2_permute(state); }
+void dpo_hash_or_noop(const u64 *in, u64 n, u64 *out) { Digest d = hash_or_noop(in, n); memcpy(out, d.v, 32); }
+void dpo_compress(const u64 *x, const u64 *y, u64 *out) { Digest a, b; memcpy(a.v, x, 32); memcpy(b.v, y, 32); Digest d = compress(a, b); memcpy(out, d.v, 32); }
+void *dpo_transcript_new(const char *label) { return new Transcript(label); }
+void dpo_transcript_free(void *t) { delete (Transcript *)t; }
+void dpo_transcript_append_f(void *t, const u64 *f, u64 n) { ((Transcript *)t)->append_field_elements(f, n); }
+void dpo_transcript_append_msg(void *t, const uint8_t *m, u64 n) { ((Transcript *)t)->append_message(m, n); }
+void dpo_transcript_append_e(void *t, const u64 *e, u64 n) { for (u64 i = 0; i < n; i++) ((Transcript *)t)->append_field_element_ext(E(e[2 * i], e[2 * i + 1])); }
+void dpo_transcript_challenge(void *t, const char *label, u64 *out) { put_e(out, 0, ((Transcript *)t)->get_and_append_challenge(label)); }
+void dpo_transcript_read_challenge(void *t, u64 *out) { put_e(out, 0, ((Transcript *)t)->read_challenge()); }
+
+// ---- sumcheck ----
+static VirtualPolynomial mk_vp(u32 n_mles, const u64 *const *data, const u64 *lens, const int *is_ext, u32 n_products,
+                               const u64 *coefs, const u32 *deg, const u32 *idx, u32 max_nv) {
+    VirtualPolynomial vp(max_nv);
+    std::vector<std::shared_ptr<MLE>> ms;
+    for (u32 i = 0; i < n_mles; i++) ms.push_back(mk_mle(data[i], lens[i], is_ext[i]));
+    // keep the caller's MLE numbering: register every MLE in order first
+    for (auto &m : ms) vp.add_mle(m);
+    size_t o = 0;
+    for (u32 p = 0; p < n_products; p++) {
+        std::vector<std::shared_ptr<MLE>> l;
+        for (u32 j = 0; j < deg[p]; j++) l.push_back(ms[idx[o + j]]);
+        o += deg[p];
+        vp.add_mle_list(l, E(f_from_u64(coefs[2 * p]), f_from_u64(coefs[2 * p + 1])));
+    }
+    return vp;
+}
+
+// prove_parallel with BasicTranscript::new(label).  out_point: nv x E; out_msgs: nv x (max_deg+1) x E;
+// out_final: n_mles x E.  Returns max_degree via *out_max_deg.
+int dpo_sumcheck_prove(u32 n_mles, const u64 *const *data, const u64 *lens, const int *is_ext, u32 n_products, const u64 *coefs,
+                       const u32 *deg, const u32 *idx, u32 max_nv, const char *label, u64 *out_point, u64 *out_msgs, u64 *out_final,
+                       u32 *out_max_deg) {
+    try {
+        VirtualPolynomial vp = mk_vp(n_mles, data, lens, is_ext, n_products, coefs, deg, idx, max_nv);
+        Transcript t(label);
+        auto res = sumcheck_prove(vp, t);
+        *out_max_deg = (u32)vp.max_degree;
+        for (size_t i = 0; i < res.first.point.size(); i++) put_e(out_point, i, res.first.point[i]);
+        size_t k = 0;
+        for (auto &m : res.first.proofs) for (E e : m) put_e(out_msgs, k++, e);
+        for (size_t i = 0; i < res.second.size(); i++) put_e(out_final, i, res.second[i]);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+
+// Round-by-round with INJECTED challenges (challenges: max_nv x E; the i-th is used after round i).
+int dpo_sumcheck_rounds_fixed(u32 n_mles, const u64 *const *data, const u64 *lens, const int *is_ext, u32 n_products, const u64 *coefs,
+                              const u32 *deg, const u32 *idx, u32 max_nv, const u64 *challenges, u64 *out_msgs, u64 *out_final) {
+    try {
+        VirtualPolynomial vp = mk_vp(n_mles, data, lens, is_ext, n_products, coefs, deg, idx, max_nv);
+        IOPProverState st(vp);
+        size_t k = 0;
+        for (u32 i = 0; i < max_nv; i++) {
+            E c = i ? E(challenges[2 * (i - 1)], challenges[2 * (i - 1) + 1]) : E();
+            auto msg = st.prove_round(i ? &c : nullptr);
+            for (E e : msg) put_e(out_msgs, k++, e);
+        }
+        st.finish(E(challenges[2 * (max_nv - 1)], challenges[2 * (max_nv - 1) + 1]));
+        auto fin = st.final_evaluations();
+        for (size_t i = 0; i < fin.size(); i++) put_e(out_final, i, fin[i]);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+
+// verify a proof produced with BasicTranscript::new(label); returns 0 and the subclaim on success
+int dpo_sumcheck_verify(const u64 *claimed_sum, u32 nv, u32 max_deg, const u64 *msgs, const char *label, u64 *out_point, u64 *out_expected) {
+    try {
+        IOPProof pr;
+        for (u32 i = 0; i < nv; i++) { std::vector<E> m; for (u32 t = 0; t <= max_deg; t++) { size_t k = (size_t)i * (max_deg + 1) + t; m.push_back(E(msgs[2 * k], msgs[2 * k + 1])); } pr.proofs.push_back(m); }
+        Transcript t(label);
+        auto sc = sumcheck_verify(E(claimed_sum[0], claimed_sum[1]), pr, nv, max_deg, t);
+        for (size_t i = 0; i < sc.point.size(); i++) put_e(out_point, i, sc.point[i]);
+        put_e(out_expected, 0, sc.expected_evaluation);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+
+}  // extern "C"

@@ -1,0 +1,139 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see field.hpp header).
+// Poseidon2 width-8 permutation, duplex challenger, Digest/hash/compress and BasicTranscript.
+// Restates: ff_ext/src/lib.rs:167-254 (NoAllocPoseidon wiring), poseidon/src/{challenger.rs,
+// poseidon_hash.rs,digest.rs}, transcript/src/{lib.rs:22-93,basic.rs}.  The permutation internals and
+// DuplexChallenger live in Plonky3 (p3-poseidon2 / p3-challenger @ f37dc2a), which is NOT vendored in
+// /root/reference; they are restated from the published Poseidon2 design + memory of upstream:
+//   PARITY PARTIALLY PINNED -- see oracle/gen_poseidon2_constants.py docstring for exactly what is and
+//   is not confirmed.  GPU-vs-oracle equality is exact; oracle-vs-reference equality of digests and
+//   challenges is probable but unproven.
+#pragma once
+#include "field.hpp"
+#include "../include/dp_poseidon2_constants.h"
+#include <array>
+#include <cstring>
+
+namespace dpo {
+
+// p3 MDSMat4 = circ(2,3,1,1) applied to 4 lanes (ff_ext/src/lib.rs:193 passes `&MDSMat4`)
+static inline void p2_mat4(u64 *x) {
+    u64 t01 = f_add(x[0], x[1]), t23 = f_add(x[2], x[3]);
+    u64 t0123 = f_add(t01, t23);
+    u64 t01123 = f_add(t0123, x[1]), t01233 = f_add(t0123, x[3]);
+    u64 n3 = f_add(t01233, f_dbl(x[0]));  // 3x0 + x1 + x2 + 2x3
+    u64 n1 = f_add(t01123, f_dbl(x[2]));  // x0 + 2x1 + 3x2 + x3
+    u64 n0 = f_add(t01123, t01);          // 2x0 + 3x1 + x2 + x3
+    u64 n2 = f_add(t01233, t23);          // x0 + x1 + 2x2 + 3x3
+    x[0] = n0; x[1] = n1; x[2] = n2; x[3] = n3;
+}
+// mds_light_permutation, WIDTH = 8: M4 on each 4-chunk, then state[i] += sums[i % 4]
+static inline void p2_mds_light(u64 *s) {
+    p2_mat4(s); p2_mat4(s + 4);
+    u64 sums[4];
+    for (int k = 0; k < 4; k++) sums[k] = f_add(s[k], s[4 + k]);
+    for (int i = 0; i < 8; i++) s[i] = f_add(s[i], sums[i & 3]);
+}
+static inline u64 p2_sbox(u64 x) { u64 x2 = f_mul(x, x), x3 = f_mul(x2, x), x4 = f_mul(x2, x2); return f_mul(x3, x4); }
+
+// NoAllocPoseidon::permute_mut (ff_ext/src/lib.rs:222-228):
+//   external_initial (mds_light, then 4x [add rc, x^7, mds_light]); 22x internal [s0 += rc; s0 ^= 7;
+//   s[i] = s[i]*diag[i] + sum]; external_terminal (4x [add rc, x^7, mds_light]).
+static inline void poseidon2_permute(u64 s[8]) {
+    p2_mds_light(s);
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 8; i++) s[i] = p2_sbox(f_add(s[i], DP_P2_EXT_RC[0][r][i]));
+        p2_mds_light(s);
+    }
+    for (int r = 0; r < 22; r++) {
+        s[0] = p2_sbox(f_add(s[0], DP_P2_INT_RC[r]));
+        u64 sum = 0;
+        for (int i = 0; i < 8; i++) sum = f_add(sum, s[i]);
+        for (int i = 0; i < 8; i++) s[i] = f_add(f_mul(s[i], DP_P2_DIAG[i]), sum);
+    }
+    for (int r = 0; r < 4; r++) {
+        for (int i = 0; i < 8; i++) s[i] = p2_sbox(f_add(s[i], DP_P2_EXT_RC[1][r][i]));
+        p2_mds_light(s);
+    }
+}
+
+// DuplexChallenger<F, P, 8, 4>  (poseidon/src/challenger.rs:14-20; p3-challenger duplex_challenger.rs)
+struct Challenger {
+    u64 state[8];
+    u64 in_buf[4]; int n_in = 0;
+    u64 out_buf[4]; int n_out = 0;
+    u64 n_perm = 0;  // statistics only
+    Challenger() { memset(state, 0, sizeof state); }
+    void duplexing() {
+        for (int i = 0; i < n_in; i++) state[i] = in_buf[i];
+        n_in = 0;
+        poseidon2_permute(state); n_perm++;
+        for (int i = 0; i < 4; i++) out_buf[i] = state[i];
+        n_out = 4;
+    }
+    void observe(u64 v) {
+        n_out = 0;
+        in_buf[n_in++] = v;
+        if (n_in == 4) duplexing();
+    }
+    u64 sample() {
+        if (n_in != 0 || n_out == 0) duplexing();
+        return out_buf[--n_out];  // pops from the END of the rate
+    }
+};
+
+struct Digest {
+    u64 v[4];
+    bool operator==(const Digest &o) const { return memcmp(v, o.v, sizeof v) == 0; }
+};
+
+// PoseidonHash::hash_or_noop (poseidon_hash.rs:22-28): <= 4 elements -> zero-padded copy, no permutation
+static inline Digest hash_or_noop(const u64 *in, size_t n) {
+    Digest d;
+    if (n <= 4) {
+        for (size_t i = 0; i < 4; i++) d.v[i] = i < n ? in[i] : 0;
+        return d;
+    }
+    Challenger c;
+    for (size_t i = 0; i < n; i++) c.observe(in[i]);
+    for (int i = 0; i < 4; i++) d.v[i] = c.sample();
+    return d;
+}
+// compress (poseidon_hash.rs:66-71): observe x(4) -> permute, observe y(4) -> permute, sample 4
+static inline Digest compress(const Digest &x, const Digest &y) {
+    Challenger c;
+    for (int i = 0; i < 4; i++) c.observe(x.v[i]);
+    for (int i = 0; i < 4; i++) c.observe(y.v[i]);
+    Digest d;
+    for (int i = 0; i < 4; i++) d.v[i] = c.sample();
+    return d;
+}
+
+// bytes_to_field_elements (ff_ext/src/lib.rs:262-273): 8-byte LE chunks, last one zero-padded
+static inline std::vector<u64> bytes_to_field_elements(const uint8_t *b, size_t n) {
+    std::vector<u64> out;
+    for (size_t i = 0; i < n; i += 8) {
+        uint8_t a[8] = {0};
+        memcpy(a, b + i, n - i < 8 ? n - i : 8);
+        u64 v; memcpy(&v, a, 8);
+        out.push_back(v);  // from_canonical_u64: caller guarantees < p for labels/usize
+    }
+    return out;
+}
+
+// BasicTranscript (transcript/src/basic.rs) over trait Transcript (transcript/src/lib.rs:22-93)
+struct Transcript {
+    Challenger ch;
+    Transcript() {}
+    explicit Transcript(const char *label) { append_message((const uint8_t *)label, strlen(label)); }
+    void append_field_element(u64 f) { ch.observe(f); }
+    void append_field_elements(const u64 *f, size_t n) { for (size_t i = 0; i < n; i++) ch.observe(f[i]); }
+    void append_message(const uint8_t *m, size_t n) { for (u64 f : bytes_to_field_elements(m, n)) ch.observe(f); }
+    void append_usize(u64 v) { append_message((const uint8_t *)&v, 8); }  // usize.to_le_bytes()
+    void append_field_element_ext(E e) { ch.observe(e.c0); ch.observe(e.c1); }
+    void append_field_element_exts(const std::vector<E> &v) { for (E e : v) append_field_element_ext(e); }
+    E read_challenge() { u64 a = ch.sample(); u64 b = ch.sample(); return E(a, b); }
+    E get_and_append_challenge(const char *label) { append_message((const uint8_t *)label, strlen(label)); return read_challenge(); }
+    std::vector<E> sample_vec(size_t n) { std::vector<E> v; for (size_t i = 0; i < n; i++) v.push_back(read_challenge()); return v; }
+};
+
+}  // namespace dpo

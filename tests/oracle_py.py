@@ -1,0 +1,228 @@
+"""ctypes view of oracle/libdp_oracle.so -- TEST INFRASTRUCTURE.  Imported only from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg."""
+import ctypes as C
+import os
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_PATH = os.path.join(_ROOT, "oracle", "libdp_oracle.so")
+P = 0xFFFFFFFF00000001
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_PATH):
+            raise ImportError("oracle not built: run `make oracle`")
+        _lib = C.CDLL(ORACLE_PATH)
+        _lib.dpo_last_error.restype = C.c_char_p
+        _lib.dpo_transcript_new.restype = C.c_void_p
+        _lib.dpo_transcript_new.argtypes = [C.c_char_p]
+        for name in ("dpo_transcript_free",):
+            getattr(_lib, name).argtypes = [C.c_void_p]
+        _lib.dpo_transcript_append_f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        _lib.dpo_transcript_append_msg.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+        _lib.dpo_transcript_append_e.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        _lib.dpo_transcript_challenge.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        _lib.dpo_transcript_read_challenge.argtypes = [C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def u64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint64))
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def splitmix_f(seed, n):
+    out = np.empty(n, dtype=np.uint64)
+    lib().dpo_splitmix_f(C.c_uint64(seed), C.c_uint64(n), ptr(out))
+    return out
+
+
+def splitmix_e(seed, n):
+    return splitmix_f(seed, 2 * n).reshape(n, 2)
+
+
+def f_binop(op, a, b):
+    a, b = u64(a), u64(b)
+    out = np.empty_like(a)
+    lib().dpo_f_binop(op, ptr(a), ptr(b), C.c_uint64(a.size), ptr(out))
+    return out
+
+
+def e_binop(op, a, b):
+    a, b = u64(a).reshape(-1, 2), u64(b).reshape(-1, 2)
+    out = np.empty_like(a)
+    lib().dpo_e_binop(op, ptr(a), ptr(b), C.c_uint64(a.shape[0]), ptr(out))
+    return out
+
+
+def e_inv(a):
+    a = u64(a).reshape(-1, 2)
+    out = np.empty_like(a)
+    lib().dpo_e_inv(ptr(a), C.c_uint64(a.shape[0]), ptr(out))
+    return out
+
+
+def _mle_call(fn, evals, is_ext, point, out_len):
+    ev = u64(evals).reshape(-1)
+    n = ev.size // (2 if is_ext else 1)
+    pt = u64(point).reshape(-1)
+    out = np.zeros((out_len, 2), dtype=np.uint64)
+    rc = fn(ptr(ev), C.c_uint64(n), int(bool(is_ext)), ptr(pt), C.c_uint32(pt.size // 2), ptr(out))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return out
+
+
+def fix_high(evals, is_ext, point):
+    ev = u64(evals).reshape(-1)
+    n = ev.size // (2 if is_ext else 1)
+    k = u64(point).size // 2
+    return _mle_call(lib().dpo_fix_high, evals, is_ext, point, n >> k)
+
+
+def fix_low(evals, is_ext, point):
+    ev = u64(evals).reshape(-1)
+    n = ev.size // (2 if is_ext else 1)
+    k = u64(point).size // 2
+    return _mle_call(lib().dpo_fix_low, evals, is_ext, point, n >> k)
+
+
+def evaluate(evals, is_ext, point):
+    return _mle_call(lib().dpo_evaluate, evals, is_ext, point, 1)[0]
+
+
+def build_eq(point):
+    pt = u64(point).reshape(-1)
+    nv = pt.size // 2
+    out = np.zeros((1 << nv, 2), dtype=np.uint64)
+    lib().dpo_build_eq(ptr(pt), C.c_uint32(nv), ptr(out))
+    return out
+
+
+def eq_eval(x, y):
+    x, y = u64(x).reshape(-1), u64(y).reshape(-1)
+    out = np.zeros(2, dtype=np.uint64)
+    lib().dpo_eq_eval(ptr(x), ptr(y), C.c_uint32(x.size // 2), ptr(out))
+    return out
+
+
+def poseidon2_permute(state):
+    s = u64(state).copy()
+    lib().dpo_poseidon2_permute(ptr(s))
+    return s
+
+
+def compress(x, y):
+    x, y = u64(x), u64(y)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().dpo_compress(ptr(x), ptr(y), ptr(out))
+    return out
+
+
+def hash_or_noop(v):
+    v = u64(v)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().dpo_hash_or_noop(ptr(v), C.c_uint64(v.size), ptr(out))
+    return out
+
+
+class Transcript:
+    def __init__(self, label=b"m2vec"):
+        self.h = C.c_void_p(lib().dpo_transcript_new(label))
+
+    def append_f(self, f):
+        f = u64(f)
+        lib().dpo_transcript_append_f(self.h, ptr(f), C.c_uint64(f.size))
+
+    def append_msg(self, m):
+        lib().dpo_transcript_append_msg(self.h, m, C.c_uint64(len(m)))
+
+    def append_e(self, e):
+        e = u64(e).reshape(-1, 2)
+        lib().dpo_transcript_append_e(self.h, ptr(e), C.c_uint64(e.shape[0]))
+
+    def challenge(self, label):
+        out = np.zeros(2, dtype=np.uint64)
+        lib().dpo_transcript_challenge(self.h, label, ptr(out))
+        return out
+
+    def __del__(self):
+        try:
+            lib().dpo_transcript_free(self.h)
+        except Exception:
+            pass
+
+
+def _vp_args(mles, products):
+    """mles: list of (np array, is_ext); products: list of (coef(c0,c1), [idx])"""
+    arrs = [u64(m[0]).reshape(-1) for m in mles]
+    n = len(arrs)
+    data = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    lens = u64([a.size // (2 if m[1] else 1) for a, m in zip(arrs, mles)])
+    is_ext = np.ascontiguousarray(np.asarray([int(bool(m[1])) for m in mles], dtype=np.int32))
+    coefs = u64([c for p in products for c in p[0]])
+    deg = np.ascontiguousarray(np.asarray([len(p[1]) for p in products], dtype=np.uint32))
+    idx = np.ascontiguousarray(np.asarray([i for p in products for i in p[1]], dtype=np.uint32))
+    return arrs, data, lens, is_ext, coefs, deg, idx
+
+
+def sumcheck_prove(mles, products, max_nv, label=b"m2vec"):
+    arrs, data, lens, is_ext, coefs, deg, idx = _vp_args(mles, products)
+    max_deg = int(deg.max())
+    point = np.zeros((max_nv, 2), dtype=np.uint64)
+    msgs = np.zeros((max_nv, max_deg + 1, 2), dtype=np.uint64)
+    fin = np.zeros((len(mles), 2), dtype=np.uint64)
+    md = C.c_uint32()
+    rc = lib().dpo_sumcheck_prove(C.c_uint32(len(mles)), data, ptr(lens), ptr(is_ext), C.c_uint32(len(products)), ptr(coefs),
+                                  ptr(deg), ptr(idx), C.c_uint32(max_nv), label, ptr(point), ptr(msgs), ptr(fin), C.byref(md))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return point, msgs, fin
+
+
+def sumcheck_rounds_fixed(mles, products, max_nv, challenges):
+    arrs, data, lens, is_ext, coefs, deg, idx = _vp_args(mles, products)
+    max_deg = int(deg.max())
+    ch = u64(challenges).reshape(-1)
+    msgs = np.zeros((max_nv, max_deg + 1, 2), dtype=np.uint64)
+    fin = np.zeros((len(mles), 2), dtype=np.uint64)
+    rc = lib().dpo_sumcheck_rounds_fixed(C.c_uint32(len(mles)), data, ptr(lens), ptr(is_ext), C.c_uint32(len(products)),
+                                         ptr(coefs), ptr(deg), ptr(idx), C.c_uint32(max_nv), ptr(ch), ptr(msgs), ptr(fin))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return msgs, fin
+
+
+def sumcheck_verify(claimed_sum, nv, max_deg, msgs, label=b"m2vec"):
+    cs = u64(claimed_sum)
+    m = u64(msgs).reshape(-1)
+    point = np.zeros((nv, 2), dtype=np.uint64)
+    exp = np.zeros(2, dtype=np.uint64)
+    rc = lib().dpo_sumcheck_verify(ptr(cs), C.c_uint32(nv), C.c_uint32(max_deg), ptr(m), label, ptr(point), ptr(exp))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return point, exp
+
+
+# ---- tiny pure-Python field helpers for naive cross-checks ----
+def pf_mul(a, b):
+    return (int(a) * int(b)) % P
+
+
+def pe_mul(a, b):
+    a0, a1, b0, b1 = int(a[0]), int(a[1]), int(b[0]), int(b[1])
+    return ((a0 * b0 + 7 * a1 * b1) % P, (a0 * b1 + a1 * b0) % P)
+
+
+def pe_add(a, b):
+    return ((int(a[0]) + int(b[0])) % P, (int(a[1]) + int(b[1])) % P)
+
+
+def pe_sub(a, b):
+    return ((int(a[0]) - int(b[0])) % P, (int(a[1]) - int(b[1])) % P)
