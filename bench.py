@@ -45,28 +45,30 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.samples = []
-        self.stop = False
-        self.th = None
-
-    def _run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.samples.append([x.strip() for x in line.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        self.proc = None
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        # ONE long-running nvidia-smi (-lms 200) for the whole timed region, as in the profiling recipe
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop = True
-        self.th.join(timeout=6)
+        if self.proc is None:
+            return
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.strip().splitlines():
+            self.samples.append([x.strip() for x in line.split(",")])
 
     def summary(self):
         sm, mx, reasons = [], [], set()

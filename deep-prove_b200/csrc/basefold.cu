@@ -1,0 +1,601 @@
+// Basefold multilinear PCS on device: commit (K7 hypercube interpolation, K8 RS/NTT encode, K9 Poseidon2
+// Merkle), open / batch_open commit phase (K10 FRI fold, K11 coefficient-form sumcheck via the sumcheck
+// engine, K12 batch prelude) and query gathering (K13).
+// Reference: mpcs/src/basefold.rs:86-154,304-354,466-770; basefold/{commit_phase.rs,sumcheck.rs,
+// encoding/rs.rs,query_phase.rs:31-138,373-534}; util/{merkle_tree.rs,hash.rs,arithmetic.rs:120-132,
+// arithmetic/hypercube.rs}.
+//
+// Data layout in HBM (per commitment of a 2^nu polynomial): bh_evals = bit-reversed evaluations (8 or
+// 16 B/elt), codeword = bit-reversed RS codeword of 2^(nu+1) elements, digests = Merkle levels >= 1
+// (4 x u64 each; level 0 of the reference is a zero-padded copy of the leaf pair -- hash_or_noop of <= 4
+// elements, poseidon_hash.rs:22-28 -- so it is recomputed from the leaves on demand, never stored).
+// Everything stays resident until the opening: roots and round messages are the only D2H traffic.
+//
+// Linear-algebra shortcuts (exact arithmetic, identical field elements):
+//  * interpolate_over_boolean_hypercube commutes with the bit-reversal permutation, so the coefficient
+//    vector the reference encodes, bitrev(interp(evals)), is interp(bh_evals): one permutation serves both.
+//  * a decimation-in-frequency NTT of the natural-order input yields the spectrum in bit-reversed order,
+//    which IS the stored codeword (basefold.rs:151 bit-reverses the DIT output) -- no final permutation.
+//  * the zero-padded upper half makes the first DIF level a pure copy-and-scale (k_expand).
+#include "common.cuh"
+#include "poseidon2.cuh"
+#include <algorithm>
+
+static constexpr u32 BF_RATE_LOG = 1;            // RSCodeDefaultSpec (rs.rs:192-214)
+static constexpr u32 BF_BASECODE_LOG = 7;
+static constexpr u64 GL_ROOT32 = 1753635133440165772ULL;  // p3 Goldilocks two-adic generator, order 2^32
+
+// ---- root-of-unity / coset power tables: x^e = T0[e & 2047] * T1[(e >> 11) & 2047] * T2[e >> 22] ----
+struct PowTab { const u64 *t0, *t1, *t2; };
+__global__ void k_pow_table(u64 base, u64 *t /* 3 x 2048 */) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 3 * 2048) return;
+    u32 part = k >> 11, idx = k & 2047;
+    u64 e = (u64)idx << (11 * part);
+    t[k] = gl_pow(base, e);
+}
+__device__ __forceinline__ u64 tab_pow(const PowTab &t, u64 e) {
+    return gl_mul(gl_mul(t.t0[e & 2047], t.t1[(e >> 11) & 2047]), t.t2[(e >> 22) & 2047]);
+}
+struct BfGlobals { u64 *root_tab = nullptr; bool p2_ready = false; };
+static BfGlobals g_bf;
+static int bf_prepare() {
+    if (!g_bf.p2_ready) {
+        DP_CUDA(p2_upload_constants((const u64 *)&DP_P2_EXT_RC[0][0][0], (const u64 *)DP_P2_INT_RC, (const u64 *)DP_P2_DIAG));
+        g_bf.p2_ready = true;
+    }
+    if (!g_bf.root_tab) {
+        DP_CUDA(cudaMalloc((void **)&g_bf.root_tab, sizeof(u64) * 3 * 2048));
+        k_pow_table<<<24, 256, 0, dp_ctx().stream>>>(GL_ROOT32, g_bf.root_tab); DP_LAUNCHED();
+        DP_CUDA(cudaGetLastError());
+    }
+    return DP_OK;
+}
+static PowTab root_tab() { PowTab t; t.t0 = g_bf.root_tab; t.t1 = g_bf.root_tab + 2048; t.t2 = g_bf.root_tab + 4096; return t; }
+
+// ---- bit reversal (out of place) ----
+template <typename T>
+__global__ void k_bitrev(const T *__restrict__ in, T *__restrict__ out, u32 lg) {
+    u64 n = 1ULL << lg, i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) { u64 j = lg ? (__brevll(i) >> (64 - lg)) : 0; out[j] = in[i]; }
+}
+
+// ---- generic tiled butterfly pass over levels [a, b) of an n_log-sized array, in place ----
+// level l pairs (i, i + (N >> (l+1))).  MODE 0: Moebius (hi -= lo).  MODE 1: DIF NTT (lo = u+v, hi = (u-v) w).
+__device__ __forceinline__ u64 t_add(u64 a, u64 b) { return gl_add(a, b); }
+__device__ __forceinline__ gle t_add(gle a, gle b) { return e_add(a, b); }
+__device__ __forceinline__ u64 t_sub(u64 a, u64 b) { return gl_sub(a, b); }
+__device__ __forceinline__ gle t_sub(gle a, gle b) { return e_sub(a, b); }
+__device__ __forceinline__ u64 t_mulb(u64 a, u64 w) { return gl_mul(a, w); }
+__device__ __forceinline__ gle t_mulb(gle a, u64 w) { return e_mul_base(a, w); }
+
+template <typename T, int MODE>
+__global__ void k_tile_pass(T *__restrict__ data, u32 n_log, u32 a, u32 b, u32 c_log, PowTab tab) {
+    extern __shared__ unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    const u32 lv = b - a, rows = 1u << lv, C = 1u << c_log;
+    const u64 stride = 1ULL << (n_log - b);             // distance between tile rows
+    const u64 ncolgroups = stride >> c_log;
+    const u64 tile = blockIdx.x;                         // (hi, colgroup)
+    const u64 hi = tile / ncolgroups, cg = tile % ncolgroups;
+    const u64 base = hi * (1ULL << (n_log - a)) + cg * C;
+    const u32 elems = rows * C;
+    for (u32 k = threadIdx.x; k < elems; k += blockDim.x) { u32 t = k >> c_log, c = k & (C - 1); sm[k] = data[base + (u64)t * stride + c]; }
+    __syncthreads();
+    for (u32 s = 0; s < lv; s++) {
+        const u32 l = a + s, hrows = rows >> (s + 1);    // pair distance in rows
+        const u32 npairs = (rows >> 1) * C;
+        for (u32 q = threadIdx.x; q < npairs; q += blockDim.x) {
+            u32 c = q & (C - 1), pr = q >> c_log;
+            u32 t = ((pr / hrows) * 2 * hrows) + (pr % hrows);
+            u32 i0 = t * C + c, i1 = (t + hrows) * C + c;
+            T u = sm[i0], v = sm[i1];
+            if (MODE == 0) sm[i1] = t_sub(v, u);
+            else {
+                u64 gi = base + (u64)t * stride + c;                 // global index of the pair's first element
+                u64 half = 1ULL << (n_log - l - 1);
+                u64 e = (gi & (half - 1)) << l;                      // exponent of w_N
+                u64 w = tab_pow(tab, e << (32 - n_log));
+                sm[i0] = t_add(u, v); sm[i1] = t_mulb(t_sub(u, v), w);
+            }
+        }
+        __syncthreads();
+    }
+    for (u32 k = threadIdx.x; k < elems; k += blockDim.x) { u32 t = k >> c_log, c = k & (C - 1); data[base + (u64)t * stride + c] = sm[k]; }
+}
+
+template <typename T, int MODE>
+static int run_levels(T *data, u32 n_log, u32 from, u32 to) {
+    // levels [from, to): the last chunk is contiguous (C = 1, up to 11 levels), earlier chunks use 16 columns x <= 7 levels
+    DpCtx &c = dp_ctx();
+    PowTab tab = root_tab();
+    u32 b = to;
+    std::vector<std::pair<u32, u32>> chunks;  // processed in increasing level order (required for DIF)
+    if (to == n_log) { u32 lv = std::min<u32>(to - from, sizeof(T) == 8 ? 11 : 10); chunks.push_back({to - lv, to}); b = to - lv; }
+    while (b > from) { u32 lv = std::min<u32>(b - from, 7); chunks.push_back({b - lv, b}); b -= lv; }
+    std::sort(chunks.begin(), chunks.end());
+    for (auto &ch : chunks) {
+        u32 lv = ch.second - ch.first;
+        u32 c_log = (ch.second == n_log) ? 0 : std::min<u32>(4, n_log - ch.second);
+        u64 tiles = 1ULL << (n_log - lv - c_log);
+        size_t smem = sizeof(T) << (lv + c_log);
+        if (smem > 48 * 1024) DP_CUDA(cudaFuncSetAttribute(k_tile_pass<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DpProfScope prof(MODE ? "k_tile_pass(ntt)" : "k_tile_pass(moebius)", (sizeof(T) << n_log) * 2);
+        k_tile_pass<T, MODE><<<(unsigned)tiles, 256, smem, c.stream>>>(data, n_log, ch.first, ch.second, c_log, tab); DP_LAUNCHED();
+    }
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
+
+// zero-pad x2 + coset scale + first DIF level: out[j] = x, out[j + m] = x * w_N^j, x = c[j] * shift^j
+template <typename T>
+__global__ void k_expand(const T *__restrict__ c, T *__restrict__ out, u32 lg_m, PowTab shift_tab, PowTab tab) {
+    u64 m = 1ULL << lg_m, j = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; j < m; j += stride) {
+        T x = t_mulb(c[j], tab_pow(shift_tab, j));
+        out[j] = x;
+        out[j + m] = t_mulb(x, tab_pow(tab, j << (32 - (lg_m + 1))));
+    }
+}
+
+// ---- K9 Merkle ----
+template <bool EXT> __device__ __forceinline__ void leaf_pair_digest(const void *leaves, u64 pair, u64 d[4]) {
+    if (EXT) { const gle *l = (const gle *)leaves + 2 * pair; gle a = ld_e(l), b = ld_e(l + 1); d[0] = a.c0; d[1] = a.c1; d[2] = b.c0; d[3] = b.c1; }
+    else { ulonglong2 v = ld_b2((const u64 *)leaves + 2 * pair); d[0] = v.x; d[1] = v.y; d[2] = 0; d[3] = 0; }
+}
+template <bool EXT>
+__global__ void k_merkle_l1(const void *__restrict__ leaves, u64 n_out, u64 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n_out; i += stride) {
+        u64 x[4], y[4], o[4];
+        leaf_pair_digest<EXT>(leaves, 2 * i, x); leaf_pair_digest<EXT>(leaves, 2 * i + 1, y);
+        p2_compress(x, y, o);
+        *reinterpret_cast<ulonglong2 *>(out + 4 * i) = make_ulonglong2(o[0], o[1]);
+        *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(o[2], o[3]);
+    }
+}
+__global__ void k_merkle_up(const u64 *__restrict__ in, u64 n_out, u64 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n_out; i += stride) {
+        u64 x[4], y[4], o[4];
+        ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(in + 8 * i), b = *reinterpret_cast<const ulonglong2 *>(in + 8 * i + 2);
+        ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(in + 8 * i + 4), d = *reinterpret_cast<const ulonglong2 *>(in + 8 * i + 6);
+        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; y[0] = c.x; y[1] = c.y; y[2] = d.x; y[3] = d.y;
+        p2_compress(x, y, o);
+        *reinterpret_cast<ulonglong2 *>(out + 4 * i) = make_ulonglong2(o[0], o[1]);
+        *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(o[2], o[3]);
+    }
+}
+template <bool EXT> __global__ void k_leafpair_root(const void *leaves, u64 *out) { u64 d[4]; leaf_pair_digest<EXT>(leaves, 0, d); for (int i = 0; i < 4; i++) out[i] = d[i]; }
+
+// A Merkle tree over `n` leaves living in HBM: levels >= 1 packed back to back.
+struct DevTree {
+    const void *leaves = nullptr; bool ext = false; u64 n = 0; u32 lg = 0;
+    u64 *levels = nullptr;            // level l (1-based) at offset lvl_off[l] (in digests)
+    std::vector<u64> lvl_off;         // lvl_off[l] for l = 1..lg-1
+    u64 *root_dev = nullptr;          // 4 limbs
+    bool own_leaves = false;
+};
+static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
+    DpCtx &c = dp_ctx();
+    t.leaves = leaves; t.ext = ext; t.n = n; t.lg = 0; while ((1ULL << t.lg) < n) t.lg++;
+    DP_CHECK(t.lg >= 1, DP_ERR_INVALID, "merkle tree needs at least two leaves");
+    t.lvl_off.assign(t.lg + 1, 0);
+    u64 total = 0;
+    for (u32 l = 1; l < t.lg; l++) { t.lvl_off[l] = total; total += n >> (l + 1); }
+    if (int e = dp_dev_alloc((void **)&t.levels, sizeof(u64) * 4 * (total + 1))) return e;
+    if (t.lg == 1) {
+        if (ext) k_leafpair_root<true><<<1, 1, 0, c.stream>>>(leaves, t.levels); else k_leafpair_root<false><<<1, 1, 0, c.stream>>>(leaves, t.levels);
+        DP_LAUNCHED(); t.root_dev = t.levels;
+    } else {
+        u64 n1 = n >> 2;
+        {
+            DpProfScope prof("k_merkle(poseidon2 compress)", n1 * (ext ? 64 : 32) + n1 * 32);
+            if (ext) k_merkle_l1<true><<<dp_grid_for(n1, 128, 8), 128, 0, c.stream>>>(leaves, n1, t.levels);
+            else k_merkle_l1<false><<<dp_grid_for(n1, 128, 8), 128, 0, c.stream>>>(leaves, n1, t.levels);
+            DP_LAUNCHED();
+        }
+        for (u32 l = 2; l < t.lg; l++) {
+            u64 nl = n >> (l + 1);
+            DpProfScope prof("k_merkle(poseidon2 compress)", nl * 96);
+            k_merkle_up<<<dp_grid_for(nl, 128, 8), 128, 0, c.stream>>>(t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]); DP_LAUNCHED();
+        }
+        t.root_dev = t.levels + 4 * t.lvl_off[t.lg - 1];
+    }
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
+}
+static void tree_free(DevTree &t) { dp_dev_free(t.levels); t.levels = nullptr; if (t.own_leaves) dp_dev_free(const_cast<void *>(t.leaves)); t.leaves = nullptr; }
+
+// ---- K10 FRI fold (commit_phase.rs:511-526, rs.rs:377-410, arithmetic.rs:120-132) ----
+// out[i] = y0 + (r - x0) * (y1 - y0) * w,  x0 = w_{2^(level+1)}^{rev(i, level)} * gamma_lvl,  w = -1/(2 x0)
+__global__ void k_fri_fold(const gle *__restrict__ in, gle *__restrict__ out, u32 level, gle r, u64 gamma_lvl, u64 neg_half_gamma_inv, PowTab tab) {
+    u64 n = 1ULL << level, i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        u64 e = level ? (__brevll(i) >> (64 - level)) : 0;             // rev(i, level), exponent of w_{2^(level+1)}
+        u64 L = 1ULL << (level + 1);
+        u64 x0 = gl_mul(tab_pow(tab, e << (32 - (level + 1))), gamma_lvl);
+        u64 x0inv_root = tab_pow(tab, ((L - e) & (L - 1)) << (32 - (level + 1)));   // w^{-e}
+        u64 w = gl_mul(x0inv_root, neg_half_gamma_inv);                  // -1/(2 x0)
+        gle y0 = ld_e(in + 2 * i), y1 = ld_e(in + 2 * i + 1);
+        gle t = e_mul_base(e_sub(r, e_from_base(x0)), w);
+        st_e(out + i, e_add(y0, e_mul(t, e_sub(y1, y0))));
+    }
+}
+
+// ---- K12 batch prelude: acc[i] (+)= coef * src[i >> rep_log]  (src Base or Ext) ----
+template <bool EXT, bool INIT>
+__global__ void k_axpy_bcast(gle *__restrict__ acc, const void *__restrict__ src, u64 n, u32 rep_log, gle coef) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        gle v = EXT ? e_mul(ld_e((const gle *)src + (i >> rep_log)), coef) : e_mul_base(coef, ((const u64 *)src)[i >> rep_log]);
+        st_e(acc + i, INIT ? v : e_add(ld_e(acc + i), v));
+    }
+}
+__global__ void k_lift(const u64 *__restrict__ src, gle *__restrict__ out, u64 n) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) st_e(out + i, e_from_base(src[i]));
+}
+
+// ---- K13 query gather: per (query, tree): [p0.c0 p0.c1 p1.c0 p1.c1][path digests x (lg-1)] ----
+struct QTree { const void *leaves; const u64 *levels; u64 off[34]; u32 lg; u32 ext; u32 shift; u32 pad; };
+__global__ void k_query_gather(const QTree *__restrict__ trees, u32 n_trees, const u64 *__restrict__ xs, const u64 *__restrict__ out_off, u64 per_query, u64 *__restrict__ out) {
+    u32 q = blockIdx.x, ti = blockIdx.y;
+    QTree t = trees[ti];
+    u64 idx = xs[q] >> t.shift;
+    u64 p0 = (idx | 1) - 1;
+    u64 *o = out + (u64)q * per_query + out_off[ti];
+    for (u32 k = threadIdx.x; k < t.lg; k += blockDim.x) {
+        if (k == 0) {
+            if (t.ext) { gle a = ld_e((const gle *)t.leaves + p0), b = ld_e((const gle *)t.leaves + p0 + 1); o[0] = a.c0; o[1] = a.c1; o[2] = b.c0; o[3] = b.c1; }
+            else { const u64 *l = (const u64 *)t.leaves; o[0] = l[p0]; o[1] = 0; o[2] = l[p0 + 1]; o[3] = 0; }
+        }
+        if (k + 1 < t.lg) {   // path entry k = inner[k][(p0 >> (k+1)) ^ 1]
+            u64 node = (p0 >> (k + 1)) ^ 1;
+            u64 *d = o + 4 + 4 * k;
+            if (k == 0) {
+                if (t.ext) { const gle *l = (const gle *)t.leaves + 2 * node; gle a = ld_e(l), b = ld_e(l + 1); d[0] = a.c0; d[1] = a.c1; d[2] = b.c0; d[3] = b.c1; }
+                else { const u64 *l = (const u64 *)t.leaves + 2 * node; d[0] = l[0]; d[1] = l[1]; d[2] = 0; d[3] = 0; }
+            } else {
+                const u64 *s = t.levels + 4 * (t.off[k] + node);
+                d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+            }
+        }
+    }
+}
+
+// =====================================================================================================
+struct dp_pcs_comm {
+    u32 num_vars = 0, full_log = 0; bool is_base = true, trivial = false;
+    void *bh_evals = nullptr;   // bit-reversed evals (raw evals when trivial)
+    void *codeword = nullptr;   // bit-reversed codeword (== bh_evals when trivial)
+    u64 cw_len = 0;
+    DevTree tree;
+    u64 root[4] = {0, 0, 0, 0};
+};
+
+struct OpenRound { gle *oracle = nullptr; u64 len = 0; DevTree tree; };
+struct dp_pcs_open {
+    u32 num_vars = 0, full_log = 0, num_rounds = 0, round = 0;
+    std::vector<const dp_pcs_comm *> comms; std::vector<gle> coeffs; bool batch = false;
+    gle *oracle0 = nullptr; u64 n0 = 0;        // running oracle of the current round (E)
+    bool oracle0_owned = true;
+    std::vector<OpenRound> rounds;             // trees over the folded oracles (pre-addition copies)
+    gle *pending = nullptr; u64 pending_len = 0;  // folded oracle awaiting its tree/addition
+    dp_mle *eq = nullptr, *evals = nullptr; bool evals_owned = false;
+    dp_sc *sc = nullptr;
+    gle final_msg[1 << BF_BASECODE_LOG]; bool have_final = false;
+    gle *scratch_sum_evals = nullptr;
+};
+
+static void msg_to_coeffs(const uint64_t *ev /* p(0),p(1),p(2) */, uint64_t *out /* c0,c1,c2 */) {
+    gle p0 = e_make(ev[0], ev[1]), p1 = e_make(ev[2], ev[3]), p2 = e_make(ev[4], ev[5]);
+    const u64 inv2 = 0x7FFFFFFF80000001ULL;  // (p+1)/2
+    gle c2 = e_mul_base(e_add(e_sub(p2, e_dbl(p1)), p0), inv2);
+    gle c1 = e_sub(e_sub(p1, p0), c2);
+    out[0] = p0.c0; out[1] = p0.c1; out[2] = c1.c0; out[3] = c1.c1; out[4] = c2.c0; out[5] = c2.c1;
+}
+
+extern "C" {
+
+int dp_poseidon2_init(const uint64_t *ext_rc /*2x4x8*/, const uint64_t *int_rc /*22*/, const uint64_t *diag /*8*/) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(ext_rc && int_rc && diag, DP_ERR_INVALID, "dp_poseidon2_init: null argument");
+    u64 a[64], b[22], d[8];
+    for (int i = 0; i < 64; i++) a[i] = gl_canon(ext_rc[i]);
+    for (int i = 0; i < 22; i++) b[i] = gl_canon(int_rc[i]);
+    for (int i = 0; i < 8; i++) d[i] = gl_canon(diag[i]);
+    DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));
+    DP_CUDA(p2_upload_constants(a, b, d));
+    g_bf.p2_ready = true;
+    return DP_OK;
+}
+
+int dp_pcs_commit(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(poly && out, DP_ERR_INVALID, "dp_pcs_commit: null argument");
+    u32 nv = poly->num_vars();
+    DP_CHECK(nv <= full_log, DP_ERR_INVALID, "PolynomialTooLarge");                 // basefold.rs:97-99
+    DP_CHECK(nv >= 1, DP_ERR_INVALID, "dp_pcs_commit: need at least one variable");
+    if (int e = bf_prepare()) return e;
+    DpCtx &c = dp_ctx();
+    dp_pcs_comm *cm = new dp_pcs_comm();
+    cm->num_vars = nv; cm->full_log = full_log; cm->is_base = !poly->is_ext;
+    size_t esz = poly->is_ext ? 16 : 8;
+    u64 m = poly->len;
+    if (int e = dp_dev_alloc(&cm->bh_evals, esz * m)) return e;
+    if (nv <= BF_BASECODE_LOG) {   // TooSmall: Merkle tree over the raw evaluations (basefold.rs:102-104)
+        cm->trivial = true;
+        DP_CUDA(cudaMemcpyAsync(cm->bh_evals, poly->data, esz * m, cudaMemcpyDeviceToDevice, c.stream));
+        cm->codeword = cm->bh_evals; cm->cw_len = m;
+    } else {
+        u64 N = m << BF_RATE_LOG; u32 n_log = nv + BF_RATE_LOG;
+        cm->cw_len = N;
+        void *coef = nullptr;
+        if (int e = dp_dev_alloc(&coef, esz * m)) return e;
+        if (int e = dp_dev_alloc(&cm->codeword, esz * N)) return e;
+        // coset shift table: shift = 7^(2^(full_log - lg m))  (rs.rs:481-488)
+        u64 shift = 7; for (u32 i = 0; i < full_log - nv; i++) shift = gl_sqr(shift);
+        u64 *stab = nullptr;
+        if (int e = dp_dev_alloc((void **)&stab, sizeof(u64) * 3 * 2048)) return e;
+        k_pow_table<<<24, 256, 0, c.stream>>>(shift, stab); DP_LAUNCHED();
+        PowTab st; st.t0 = stab; st.t1 = stab + 2048; st.t2 = stab + 4096;
+        int g = dp_grid_for(m, 256, 8);
+        if (poly->is_ext) {
+            { DpProfScope p("k_bitrev", esz * m * 2); k_bitrev<gle><<<g, 256, 0, c.stream>>>((const gle *)poly->data, (gle *)cm->bh_evals, nv); DP_LAUNCHED(); }
+            DP_CUDA(cudaMemcpyAsync(coef, cm->bh_evals, esz * m, cudaMemcpyDeviceToDevice, c.stream));
+            if (int e = run_levels<gle, 0>((gle *)coef, nv, 0, nv)) return e;                 // K7
+            { DpProfScope p("k_expand", esz * m * 3); k_expand<gle><<<g, 256, 0, c.stream>>>((const gle *)coef, (gle *)cm->codeword, nv, st, root_tab()); DP_LAUNCHED(); }
+            if (int e = run_levels<gle, 1>((gle *)cm->codeword, n_log, 1, n_log)) return e;  // K8
+        } else {
+            { DpProfScope p("k_bitrev", esz * m * 2); k_bitrev<u64><<<g, 256, 0, c.stream>>>((const u64 *)poly->data, (u64 *)cm->bh_evals, nv); DP_LAUNCHED(); }
+            DP_CUDA(cudaMemcpyAsync(coef, cm->bh_evals, esz * m, cudaMemcpyDeviceToDevice, c.stream));
+            if (int e = run_levels<u64, 0>((u64 *)coef, nv, 0, nv)) return e;
+            { DpProfScope p("k_expand", esz * m * 3); k_expand<u64><<<g, 256, 0, c.stream>>>((const u64 *)coef, (u64 *)cm->codeword, nv, st, root_tab()); DP_LAUNCHED(); }
+            if (int e = run_levels<u64, 1>((u64 *)cm->codeword, n_log, 1, n_log)) return e;
+        }
+        DP_CUDA(cudaGetLastError());
+        dp_dev_free(coef); dp_dev_free(stab);
+    }
+    if (int e = tree_build(cm->tree, cm->codeword, poly->is_ext, cm->cw_len)) return e;   // K9
+    DP_CUDA(cudaMemcpyAsync(cm->root, cm->tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
+    DP_CUDA(cudaStreamSynchronize(c.stream));
+    *out = cm;
+    return DP_OK;
+}
+
+int dp_pcs_comm_info(const dp_pcs_comm *cm, uint32_t *num_vars, int *is_base, int *is_trivial, uint64_t root[4]) {
+    if (!cm) return dp_fail(DP_ERR_INVALID, "dp_pcs_comm_info: null");
+    if (num_vars) *num_vars = cm->num_vars;
+    if (is_base) *is_base = cm->is_base;
+    if (is_trivial) *is_trivial = cm->trivial;
+    if (root) memcpy(root, cm->root, 32);
+    return DP_OK;
+}
+int dp_pcs_comm_codeword(const dp_pcs_comm *cm, dp_mle **view) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(cm && view, DP_ERR_INVALID, "dp_pcs_comm_codeword: null");
+    dp_mle *v = new dp_mle(); v->data = cm->codeword; v->len = cm->cw_len; v->is_ext = !cm->is_base; v->owned = false; *view = v;
+    return DP_OK;
+}
+int dp_pcs_comm_bh_evals(const dp_pcs_comm *cm, dp_mle **view) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(cm && view, DP_ERR_INVALID, "dp_pcs_comm_bh_evals: null");
+    dp_mle *v = new dp_mle(); v->data = cm->bh_evals; v->len = 1ULL << cm->num_vars; v->is_ext = !cm->is_base; v->owned = false; *view = v;
+    return DP_OK;
+}
+int dp_pcs_comm_free(dp_pcs_comm *cm) {
+    if (!cm) return DP_OK;
+    std::lock_guard<std::recursive_mutex> lk(dp_ctx().mu);
+    if (dp_ctx().ready) { tree_free(cm->tree); if (!cm->trivial) dp_dev_free(cm->codeword); dp_dev_free(cm->bh_evals); }
+    delete cm;
+    return DP_OK;
+}
+
+// commit_phase / batch_commit_phase up to and including the first sumcheck message
+int dp_pcs_open_begin(const dp_pcs_comm *const *comms, const uint64_t *coeffs, uint32_t n_comms, const uint64_t *point, uint32_t num_vars,
+                      dp_pcs_open **out, uint64_t first_msg[6]) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(comms && n_comms >= 1 && point && out && first_msg, DP_ERR_INVALID, "dp_pcs_open_begin: null argument");
+    if (int e = bf_prepare()) return e;
+    DpCtx &c = dp_ctx();
+    dp_pcs_open *o = new dp_pcs_open();
+    o->num_vars = num_vars; o->batch = coeffs != nullptr; o->full_log = comms[0]->full_log;
+    for (u32 i = 0; i < n_comms; i++) {
+        DP_CHECK(comms[i] && !comms[i]->trivial, DP_ERR_INVALID, "dp_pcs_open_begin: trivial commitment (open it on the host)");   // basefold.rs:481-483, 562-565
+        DP_CHECK(comms[i]->num_vars <= num_vars && comms[i]->full_log == o->full_log, DP_ERR_INVALID, "dp_pcs_open_begin: commitment larger than the opening");
+        o->comms.push_back(comms[i]);
+        if (coeffs) o->coeffs.push_back(e_make(gl_canon(coeffs[2 * i]), gl_canon(coeffs[2 * i + 1])));
+    }
+    DP_CHECK(num_vars > BF_BASECODE_LOG, DP_ERR_INVALID, "minimum number of variables must be greater than basecode_msg_size_log");
+    if (!o->batch) DP_CHECK(n_comms == 1 && comms[0]->num_vars == num_vars, DP_ERR_INVALID, "dp_pcs_open_begin: single open needs one commitment of num_vars variables");
+    o->num_rounds = num_vars - BF_BASECODE_LOG;
+    u64 N = 1ULL << (num_vars + BF_RATE_LOG), M = 1ULL << num_vars;
+    o->n0 = N;
+    if (int e = dp_dev_alloc((void **)&o->oracle0, sizeof(gle) * N)) return e;
+    dp_mle *ev = new dp_mle(); ev->len = M; ev->owned = false;
+    if (!o->batch) {
+        const dp_pcs_comm *cm = comms[0];
+        if (cm->is_base) { k_lift<<<dp_grid_for(N, 256, 8), 256, 0, c.stream>>>((const u64 *)cm->codeword, o->oracle0, N); DP_LAUNCHED(); }
+        else DP_CUDA(cudaMemcpyAsync(o->oracle0, cm->codeword, sizeof(gle) * N, cudaMemcpyDeviceToDevice, c.stream));
+        ev->data = cm->bh_evals; ev->is_ext = !cm->is_base;     // running_evals = bh_evals (commit_phase.rs:50)
+    } else {
+        // running_oracle = sum of coeff * codeword over the full-size commitments (commit_phase.rs:205-223)
+        bool init = true;
+        for (u32 i = 0; i < n_comms; i++) if (comms[i]->cw_len == N) {
+            int g = dp_grid_for(N, 256, 8);
+            DpProfScope p("k_axpy_bcast", N * 40);
+            if (comms[i]->is_base) { if (init) k_axpy_bcast<false, true><<<g, 256, 0, c.stream>>>(o->oracle0, comms[i]->codeword, N, 0, o->coeffs[i]); else k_axpy_bcast<false, false><<<g, 256, 0, c.stream>>>(o->oracle0, comms[i]->codeword, N, 0, o->coeffs[i]); }
+            else { if (init) k_axpy_bcast<true, true><<<g, 256, 0, c.stream>>>(o->oracle0, comms[i]->codeword, N, 0, o->coeffs[i]); else k_axpy_bcast<true, false><<<g, 256, 0, c.stream>>>(o->oracle0, comms[i]->codeword, N, 0, o->coeffs[i]); }
+            DP_LAUNCHED(); init = false;
+        }
+        if (init) DP_CUDA(cudaMemsetAsync(o->oracle0, 0, sizeof(gle) * N, c.stream));
+        // sum_of_all_evals_for_sumcheck: smaller polynomials are broadcast over chunks (commit_phase.rs:225-236)
+        if (int e = dp_dev_alloc((void **)&o->scratch_sum_evals, sizeof(gle) * M)) return e;
+        for (u32 i = 0; i < n_comms; i++) {
+            u32 rep = num_vars - comms[i]->num_vars; int g = dp_grid_for(M, 256, 8);
+            DpProfScope p("k_axpy_bcast", M * 40);
+            if (comms[i]->is_base) { if (i == 0) k_axpy_bcast<false, true><<<g, 256, 0, c.stream>>>(o->scratch_sum_evals, comms[i]->bh_evals, M, rep, o->coeffs[i]); else k_axpy_bcast<false, false><<<g, 256, 0, c.stream>>>(o->scratch_sum_evals, comms[i]->bh_evals, M, rep, o->coeffs[i]); }
+            else { if (i == 0) k_axpy_bcast<true, true><<<g, 256, 0, c.stream>>>(o->scratch_sum_evals, comms[i]->bh_evals, M, rep, o->coeffs[i]); else k_axpy_bcast<true, false><<<g, 256, 0, c.stream>>>(o->scratch_sum_evals, comms[i]->bh_evals, M, rep, o->coeffs[i]); }
+            DP_LAUNCHED();
+        }
+        ev->data = o->scratch_sum_evals; ev->is_ext = true;
+    }
+    DP_CUDA(cudaGetLastError());
+    o->evals = ev;
+    // eq = bitrev(build_eq_x_r_vec(point)) == build_eq_x_r_vec(reversed point)  (commit_phase.rs:61-64)
+    std::vector<uint64_t> rp(2 * num_vars);
+    for (u32 i = 0; i < num_vars; i++) { rp[2 * i] = point[2 * (num_vars - 1 - i)]; rp[2 * i + 1] = point[2 * (num_vars - 1 - i) + 1]; }
+    if (int e = dp_eq_build(rp.data(), num_vars, &o->eq)) return e;
+    // the Basefold-internal sumcheck (basefold/sumcheck.rs) is a degree-2 LSB-first sumcheck of eq * evals on
+    // the bit-reversed tables; its coefficient-form message is recovered from p(0), p(1), p(2)
+    dp_mle *ms[2] = {o->eq, o->evals};
+    dp_sc_product pr; memset(&pr, 0, sizeof pr); pr.coef[0] = 1; pr.n_idx = 2; pr.idx[0] = 0; pr.idx[1] = 1;
+    if (int e = dp_sc_create(ms, 2, &pr, 1, num_vars, 2, &o->sc)) return e;
+    uint64_t ev3[6];
+    if (int e = dp_sc_round(o->sc, nullptr, ev3)) return e;
+    msg_to_coeffs(ev3, first_msg);
+    *out = o;
+    return DP_OK;
+}
+
+// One commit-phase round (commit_phase.rs:85-171 / :253-352): fold the oracle by `challenge`; unless this is
+// the last round return the next sumcheck message and the root of the folded oracle's tree.
+int dp_pcs_open_round(dp_pcs_open *o, const uint64_t challenge[2], uint64_t next_msg[6], uint64_t root[4], int *is_last) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(o && challenge && is_last, DP_ERR_INVALID, "dp_pcs_open_round: null argument");
+    DP_CHECK(o->round < o->num_rounds, DP_ERR_STATE, "dp_pcs_open_round: commit phase already finished");
+    DpCtx &c = dp_ctx();
+    gle r = e_make(gl_canon(challenge[0]), gl_canon(challenge[1]));
+    u32 i = o->round;
+    if (i > 0 && o->batch) {
+        // merge the commitments whose codeword size matches the running oracle (commit_phase.rs:271-282); the
+        // tree built last round keeps the pre-addition copy
+        u64 len = o->n0; bool any = false;
+        for (auto cm : o->comms) if (cm->cw_len == len) any = true;
+        if (any) {
+            gle *merged = nullptr;
+            if (int e = dp_dev_alloc((void **)&merged, sizeof(gle) * len)) return e;
+            DP_CUDA(cudaMemcpyAsync(merged, o->oracle0, sizeof(gle) * len, cudaMemcpyDeviceToDevice, c.stream));
+            for (size_t k = 0; k < o->comms.size(); k++) if (o->comms[k]->cw_len == len) {
+                int g = dp_grid_for(len, 256, 8);
+                if (o->comms[k]->is_base) k_axpy_bcast<false, false><<<g, 256, 0, c.stream>>>(merged, o->comms[k]->codeword, len, 0, o->coeffs[k]);
+                else k_axpy_bcast<true, false><<<g, 256, 0, c.stream>>>(merged, o->comms[k]->codeword, len, 0, o->coeffs[k]);
+                DP_LAUNCHED();
+            }
+            o->oracle0 = merged; o->oracle0_owned = true;   // the previous buffer stays owned by rounds.back()
+        }
+    }
+    // K10: fold the running oracle
+    u64 len = o->n0; u32 level = 0; while ((2ULL << level) < len) level++;   // log2(len) - 1
+    gle *folded = nullptr;
+    if (int e = dp_dev_alloc((void **)&folded, sizeof(gle) * (len >> 1))) return e;
+    {
+        u32 gexp = o->full_log + BF_RATE_LOG - level - 1;
+        u64 gamma = 7; for (u32 k = 0; k < gexp; k++) gamma = gl_sqr(gamma);
+        u64 nhgi = gl_neg(gl_mul(gl_inv(gamma), 0x7FFFFFFF80000001ULL));   // -(1/gamma_lvl)/2
+        DpProfScope p("k_fri_fold", len * 16 + (len >> 1) * 16);
+        k_fri_fold<<<dp_grid_for(len >> 1, 256, 8), 256, 0, c.stream>>>(o->oracle0, folded, level, r, gamma, nhgi, root_tab()); DP_LAUNCHED();
+        DP_CUDA(cudaGetLastError());
+    }
+    // the oracle just consumed is either round i-1's tree leaves (kept) or the initial / merged buffer (freed)
+    bool consumed_is_tree_leaves = !o->rounds.empty() && o->rounds.back().oracle == o->oracle0;
+    if (!consumed_is_tree_leaves) dp_dev_free(o->oracle0);
+    o->oracle0 = folded; o->n0 = len >> 1;
+    uint64_t ch[2] = {r.c0, r.c1};
+    uint64_t ev3[6];
+    if (i + 1 < o->num_rounds) {
+        if (int e = dp_sc_round(o->sc, ch, ev3)) return e;       // sum_check_challenge_round
+        msg_to_coeffs(ev3, next_msg);
+        OpenRound rd; rd.oracle = folded; rd.len = len >> 1;
+        if (int e = tree_build(rd.tree, folded, true, rd.len)) return e;   // compute_inner_ext
+        DP_CUDA(cudaMemcpyAsync(root, rd.tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
+        DP_CUDA(cudaStreamSynchronize(c.stream));
+        o->rounds.push_back(rd);
+        *is_last = 0;
+    } else {
+        // sum_check_last_round: fold once more, then un-bit-reverse the 2^7 evaluations (commit_phase.rs:132-146)
+        if (int e = dp_sc_round(o->sc, ch, ev3)) return e;       // fold (the message it also computes is unused)
+        dp_mle *view = nullptr;
+        if (int e = dp_sc_current_mle(o->sc, 1, &view)) return e;
+        DP_CHECK(view->len == (1ULL << BF_BASECODE_LOG) && view->is_ext, DP_ERR_STATE, "dp_pcs_open_round: unexpected final message size");
+        gle tmp[1 << BF_BASECODE_LOG];
+        DP_CUDA(cudaMemcpyAsync(tmp, view->data, sizeof tmp, cudaMemcpyDeviceToHost, c.stream));
+        DP_CUDA(cudaStreamSynchronize(c.stream));
+        dp_mle_free(view);
+        for (u32 k = 0; k < (1u << BF_BASECODE_LOG); k++) { u32 j = 0; for (u32 b = 0; b < BF_BASECODE_LOG; b++) if (k >> b & 1) j |= 1u << (BF_BASECODE_LOG - 1 - b); o->final_msg[j] = tmp[k]; }
+        o->have_final = true;
+        *is_last = 1;
+    }
+    o->round++;
+    return DP_OK;
+}
+
+int dp_pcs_open_final_message(dp_pcs_open *o, uint64_t *out) {
+    DP_CHECK(o && out, DP_ERR_INVALID, "dp_pcs_open_final_message: null argument");
+    DP_CHECK(o->have_final, DP_ERR_STATE, "dp_pcs_open_final_message: commit phase not finished");
+    for (u32 k = 0; k < (1u << BF_BASECODE_LOG); k++) { out[2 * k] = o->final_msg[k].c0; out[2 * k + 1] = o->final_msg[k].c1; }
+    return DP_OK;
+}
+
+// u64 words one query occupies in dp_pcs_open_query's output
+uint64_t dp_pcs_open_query_words(const dp_pcs_open *o) {
+    if (!o) return 0;
+    u64 w = 0;
+    for (auto cm : o->comms) { u32 lg = 0; while ((1ULL << lg) < cm->cw_len) lg++; w += 4 + 4 * (u64)(lg - 1); }
+    for (auto &rd : o->rounds) w += 4 + 4 * (u64)(rd.tree.lg - 1);
+    return w;
+}
+
+// K13 (query_phase.rs:373-474): for every x index, for every commitment then every round oracle:
+// [p0.c0 p0.c1 p1.c0 p1.c1] + Merkle path without leaf sibling or root (merkle_tree.rs:139-152).
+int dp_pcs_open_query(dp_pcs_open *o, const uint64_t *x_indices, uint32_t n, uint64_t *out) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(o && x_indices && out && n > 0, DP_ERR_INVALID, "dp_pcs_open_query: null argument");
+    DP_CHECK(o->have_final, DP_ERR_STATE, "dp_pcs_open_query: commit phase not finished");
+    DpCtx &c = dp_ctx();
+    u32 nt = (u32)(o->comms.size() + o->rounds.size());
+    std::vector<QTree> qt(nt); std::vector<u64> off(nt);
+    u32 lgN = o->num_vars + BF_RATE_LOG; u64 w = 0; u32 k = 0;
+    auto fill = [&](const DevTree &t, u32 shift) {
+        QTree &q = qt[k]; memset(&q, 0, sizeof q);
+        q.leaves = t.leaves; q.levels = t.levels; q.lg = t.lg; q.ext = t.ext; q.shift = shift;
+        for (u32 l = 1; l < t.lg && l < 34; l++) q.off[l] = t.lvl_off[l];
+        off[k] = w; w += 4 + 4 * (u64)(t.lg - 1); k++;
+    };
+    for (auto cm : o->comms) fill(cm->tree, lgN - cm->tree.lg);
+    for (size_t i = 0; i < o->rounds.size(); i++) fill(o->rounds[i].tree, (u32)i + 1);
+    QTree *dq = nullptr; u64 *doff = nullptr, *dx = nullptr, *dout = nullptr;
+    if (int e = dp_dev_alloc((void **)&dq, sizeof(QTree) * nt)) return e;
+    if (int e = dp_dev_alloc((void **)&doff, 8 * nt)) return e;
+    if (int e = dp_dev_alloc((void **)&dx, 8 * (size_t)n)) return e;
+    if (int e = dp_dev_alloc((void **)&dout, 8 * w * n)) return e;
+    DP_CUDA(cudaMemcpyAsync(dq, qt.data(), sizeof(QTree) * nt, cudaMemcpyHostToDevice, c.stream));
+    DP_CUDA(cudaMemcpyAsync(doff, off.data(), 8 * nt, cudaMemcpyHostToDevice, c.stream));
+    DP_CUDA(cudaMemcpyAsync(dx, x_indices, 8 * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+    DP_CUDA(cudaStreamSynchronize(c.stream));   // qt/off are stack-owned host buffers
+    k_query_gather<<<dim3(n, nt), 32, 0, c.stream>>>(dq, nt, dx, doff, w, dout); DP_LAUNCHED();
+    DP_CUDA(cudaGetLastError());
+    DP_CUDA(cudaMemcpyAsync(out, dout, 8 * w * n, cudaMemcpyDeviceToHost, c.stream));
+    DP_CUDA(cudaStreamSynchronize(c.stream));
+    dp_dev_free(dq); dp_dev_free(doff); dp_dev_free(dx); dp_dev_free(dout);
+    return DP_OK;
+}
+
+int dp_pcs_open_free(dp_pcs_open *o) {
+    if (!o) return DP_OK;
+    std::lock_guard<std::recursive_mutex> lk(dp_ctx().mu);
+    if (dp_ctx().ready) {
+        if (o->sc) dp_sc_destroy(o->sc);
+        bool oracle_in_rounds = false;
+        for (auto &rd : o->rounds) { if (rd.oracle == o->oracle0) oracle_in_rounds = true; tree_free(rd.tree); dp_dev_free(rd.oracle); }
+        if (!oracle_in_rounds) dp_dev_free(o->oracle0);
+        dp_dev_free(o->scratch_sum_evals);
+    }
+    if (o->eq) dp_mle_free(o->eq);
+    if (o->evals) dp_mle_free(o->evals);
+    delete o;
+    return DP_OK;
+}
+
+}  // extern "C"

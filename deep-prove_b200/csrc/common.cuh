@@ -45,6 +45,9 @@ struct DpProfScope {
 // stream-ordered allocation helpers
 int dp_dev_alloc(void **p, size_t bytes);
 int dp_dev_free(void *p);
+// pinned host staging buffers, cached per context (cudaHostAlloc/cudaFreeHost cost ~ms and synchronise)
+int dp_pinned_alloc(void **p, size_t bytes);
+void dp_pinned_free(void *p);
 
 struct dp_mle {
     void *data = nullptr;   // u64[len] or gle[len]

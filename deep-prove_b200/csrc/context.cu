@@ -18,6 +18,19 @@ int dp_dev_free(void *p) {
     return DP_OK;
 }
 
+struct PinnedBlk { void *p; size_t cap; bool used; };
+static std::vector<PinnedBlk> g_pinned;
+int dp_pinned_alloc(void **p, size_t bytes) {
+    size_t cap = 4096; while (cap < bytes) cap <<= 1;
+    for (auto &b : g_pinned) if (!b.used && b.cap == cap) { b.used = true; *p = b.p; return DP_OK; }
+    void *q = nullptr;
+    DP_CUDA(cudaHostAlloc(&q, cap, cudaHostAllocDefault));
+    g_pinned.push_back({q, cap, true});
+    *p = q;
+    return DP_OK;
+}
+void dp_pinned_free(void *p) { if (!p) return; for (auto &b : g_pinned) if (b.p == p) { b.used = false; return; } }
+
 // ---- per-kernel event timing --------------------------------------------------------------------
 #include <map>
 struct ProfRec { cudaEvent_t a, b; std::string name; u64 bytes; };

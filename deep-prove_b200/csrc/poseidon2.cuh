@@ -1,0 +1,64 @@
+// Poseidon2 (Goldilocks, width 8, x^7, 4+22+4 rounds) with the state held in registers, and the two
+// Merkle hash shapes built on it.  Reference: ff_ext/src/lib.rs:177-235 (NoAllocPoseidon),
+// poseidon/src/poseidon_hash.rs:17-71 over p3 DuplexChallenger<_,_,8,4> (overwrite-mode absorb,
+// outputs popped from the end of the rate).  Constants: include/dp_poseidon2_constants.h (provenance and
+// pinning status are documented in oracle/gen_poseidon2_constants.py).
+#pragma once
+#include "gl.cuh"
+#include "../../include/dp_poseidon2_constants.h"
+
+__constant__ u64 c_p2_ext[2][4][8];
+__constant__ u64 c_p2_int[22];
+__constant__ u64 c_p2_diag[8];
+
+static inline cudaError_t p2_upload_constants(const u64 *ext /*64*/, const u64 *internal /*22*/, const u64 *diag /*8*/) {
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_p2_ext, ext, sizeof(u64) * 64)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_p2_int, internal, sizeof(u64) * 22)) != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_p2_diag, diag, sizeof(u64) * 8);
+}
+
+__device__ __forceinline__ u64 p2_pow7(u64 x) { u64 x2 = gl_sqr(x), x4 = gl_sqr(x2); return gl_mul(gl_mul(x2, x), x4); }
+// p3 MDSMat4 = circ(2,3,1,1) on four lanes
+__device__ __forceinline__ void p2_mat4(u64 &x0, u64 &x1, u64 &x2, u64 &x3) {
+    u64 t01 = gl_add(x0, x1), t23 = gl_add(x2, x3), t = gl_add(t01, t23);
+    u64 a = gl_add(t, x1), b = gl_add(t, x3);
+    u64 n3 = gl_add(b, gl_dbl(x0)), n1 = gl_add(a, gl_dbl(x2));
+    u64 n0 = gl_add(a, t01), n2 = gl_add(b, t23);
+    x0 = n0; x1 = n1; x2 = n2; x3 = n3;
+}
+__device__ __forceinline__ void p2_mds_light(u64 (&s)[8]) {
+    p2_mat4(s[0], s[1], s[2], s[3]); p2_mat4(s[4], s[5], s[6], s[7]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { u64 c = gl_add(s[k], s[k + 4]); s[k] = gl_add(s[k], c); s[k + 4] = gl_add(s[k + 4], c); }
+}
+__device__ __forceinline__ void p2_permute(u64 (&s)[8]) {
+    p2_mds_light(s);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = p2_pow7(gl_add(s[i], c_p2_ext[0][r][i]));
+        p2_mds_light(s);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+        s[0] = p2_pow7(gl_add(s[0], c_p2_int[r]));
+        u64 sum = gl_add(gl_add(gl_add(s[0], s[1]), gl_add(s[2], s[3])), gl_add(gl_add(s[4], s[5]), gl_add(s[6], s[7])));
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = gl_add(gl_mul(s[i], c_p2_diag[i]), sum);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = p2_pow7(gl_add(s[i], c_p2_ext[1][r][i]));
+        p2_mds_light(s);
+    }
+}
+// compress(x, y): absorb x -> permute -> overwrite rate with y -> permute -> [s3, s2, s1, s0]
+__device__ __forceinline__ void p2_compress(const u64 x[4], const u64 y[4], u64 out[4]) {
+    u64 s[8] = {x[0], x[1], x[2], x[3], 0, 0, 0, 0};
+    p2_permute(s);
+    s[0] = y[0]; s[1] = y[1]; s[2] = y[2]; s[3] = y[3];
+    p2_permute(s);
+    out[0] = s[3]; out[1] = s[2]; out[2] = s[1]; out[3] = s[0];
+}

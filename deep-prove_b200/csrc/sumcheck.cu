@@ -60,6 +60,16 @@ __device__ __forceinline__ gle sc_load_const(const ScOp &op, gle r) {
     }
 }
 
+// a[t] += p with a runtime t but register-resident a[] (predicated select, no local memory)
+template <int N> __device__ __forceinline__ void acc_add_dyn(u64 (&a)[N], int t, u64 p) {
+#pragma unroll
+    for (int k = 0; k < N; k++) if (k == t) a[k] = gl_add(a[k], p);
+}
+template <int N> __device__ __forceinline__ void acc_add_dyn_e(gle (&a)[N], int t, gle p) {
+#pragma unroll
+    for (int k = 0; k < N; k++) if (k == t) a[k] = e_add(a[k], p);
+}
+
 template <int D>
 __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC]) {
     const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
@@ -85,12 +95,12 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
                 ulonglong2 v = ld_b2((const u64 *)pd.op[j].src + 2 * i);
                 cur[j] = v.x; st[j] = gl_sub(v.y, v.x);
             }
-#pragma unroll
+#pragma unroll 1
             for (int t = 0; t <= D; t++) {
                 u64 p = cur[0];
 #pragma unroll
                 for (int j = 1; j < D; j++) p = gl_mul(p, cur[j]);
-                a[t] = gl_add(a[t], p);
+                acc_add_dyn<D + 1>(a, t, p);
                 if (t < D) {
 #pragma unroll
                     for (int j = 0; j < D; j++) cur[j] = gl_add(cur[j], st[j]);
@@ -112,12 +122,12 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
             sc_load_pair(pd.op[j], i, r, lo, hi);
             cur[j] = lo; st[j] = e_sub(hi, lo);
         }
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t <= D; t++) {
             gle p = cur[0];
 #pragma unroll
             for (int j = 1; j < D; j++) p = (pd.op[j].mode == OPM_B) ? e_mul_base(p, cur[j].c0) : e_mul(p, cur[j]);
-            a[t] = e_add(a[t], p);
+            acc_add_dyn_e<D + 1>(a, t, p);
             if (t < D) {
 #pragma unroll
                 for (int j = 0; j < D; j++) cur[j] = e_add(cur[j], st[j]);
@@ -128,6 +138,7 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
     for (int t = 0; t <= D; t++) acc[t] = a[t];
 }
 
+template <int DSEL>   // DSEL = 0: any degree (mixed-degree polynomials); 1..5: every product has this degree
 __global__ void __launch_bounds__(SC_THREADS)
 k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, u32 *__restrict__ counters, gle *__restrict__ out) {
     __shared__ ScProd pd;
@@ -142,7 +153,8 @@ k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, 
     gle acc[SC_NACC];
 #pragma unroll
     for (int t = 0; t < SC_NACC; t++) acc[t] = e_zero();
-    switch (pd.d) {
+    if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL>(pd, r, acc);
+    else switch (pd.d) {
     case 1: sc_body<1>(pd, r, acc); break;
     case 2: sc_body<2>(pd, r, acc); break;
     case 3: sc_body<3>(pd, r, acc); break;
@@ -160,8 +172,10 @@ k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, 
     if (threadIdx.x < nacc) {
         gle v = wsum[0][threadIdx.x];
         for (int w = 1; w < SC_THREADS / 32; w++) v = e_add(v, wsum[w][threadIdx.x]);
-        st_e(partials + ((u64)blockIdx.y * gridDim.x + blockIdx.x) * SC_NACC + threadIdx.x, v);
+        if (gridDim.x == 1) st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, v);   // no cross-block stage
+        else st_e(partials + ((u64)blockIdx.y * gridDim.x + blockIdx.x) * SC_NACC + threadIdx.x, v);
     }
+    if (gridDim.x == 1) return;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -171,15 +185,31 @@ k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (threadIdx.x < 32) {
-        for (int t = 0; t < nacc; t++) {
-            gle v = e_zero();
-            for (u32 x = threadIdx.x; x < gridDim.x; x += 32) {
-                ulonglong2 q = __ldcg(reinterpret_cast<const ulonglong2 *>(partials + ((u64)blockIdx.y * gridDim.x + x) * SC_NACC + t));
-                v = e_add(v, e_make(q.x, q.y));
+    // last block of this product: all 256 threads sum the block partials (independent L2 loads in
+    // flight), then the same shuffle + shared-memory tree as above
+    {
+        gle v[SC_NACC];
+#pragma unroll
+        for (int t = 0; t < SC_NACC; t++) v[t] = e_zero();
+        for (u32 x = threadIdx.x; x < gridDim.x; x += blockDim.x) {
+            const gle *pp = partials + ((u64)blockIdx.y * gridDim.x + x) * SC_NACC;
+#pragma unroll
+            for (int t = 0; t < SC_NACC; t++) if (t < nacc) {
+                ulonglong2 q = __ldcg(reinterpret_cast<const ulonglong2 *>(pp + t));
+                v[t] = e_add(v[t], e_make(q.x, q.y));
             }
-            for (int d = 16; d > 0; d >>= 1) v = e_add(v, shfl_down_e(v, d));
-            if (threadIdx.x == 0) st_e(out + (u64)blockIdx.y * SC_NACC + t, v);
+        }
+        __syncthreads();
+        for (int t = 0; t < nacc; t++) {
+            gle w = v[t];
+            for (int d = 16; d > 0; d >>= 1) w = e_add(w, shfl_down_e(w, d));
+            if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = w;
+        }
+        __syncthreads();
+        if (threadIdx.x < nacc) {
+            gle w = wsum[0][threadIdx.x];
+            for (int k = 1; k < SC_THREADS / 32; k++) w = e_add(w, wsum[k][threadIdx.x]);
+            st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, w);
         }
         if (threadIdx.x == 0) counters[blockIdx.y] = 0;
     }
@@ -237,9 +267,7 @@ static gle sc_extrapolate(const gle *evals, u32 n, u64 at) {
 static int sc_free_all(dp_sc *s) {
     for (auto &m : s->mles) if (m.work) { dp_dev_free(m.work); m.work = nullptr; }
     dp_dev_free(s->d_descs); dp_dev_free(s->d_partials); dp_dev_free(s->d_out); dp_dev_free(s->d_counters); dp_dev_free(s->d_fin);
-    if (s->h_descs) cudaFreeHost(s->h_descs);
-    if (s->h_out) cudaFreeHost(s->h_out);
-    if (s->h_fin) cudaFreeHost(s->h_fin);
+    dp_pinned_free(s->h_descs); dp_pinned_free(s->h_out); dp_pinned_free(s->h_fin);
     return DP_OK;
 }
 
@@ -285,9 +313,9 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
     if ((e = dp_dev_alloc((void **)&s->d_counters, sizeof(u32) * n_products))) return e;
     if ((e = dp_dev_alloc((void **)&s->d_fin, sizeof(ScFin) * n_mles + sizeof(gle) * n_mles))) return e;
     DP_CUDA(cudaMemsetAsync(s->d_counters, 0, sizeof(u32) * n_products, dp_ctx().stream));
-    DP_CUDA(cudaHostAlloc((void **)&s->h_descs, sizeof(ScProd) * n_products, cudaHostAllocDefault));
-    DP_CUDA(cudaHostAlloc((void **)&s->h_out, sizeof(gle) * std::max<size_t>(SC_NACC * n_products, n_mles), cudaHostAllocDefault));
-    DP_CUDA(cudaHostAlloc((void **)&s->h_fin, sizeof(ScFin) * n_mles, cudaHostAllocDefault));
+    if ((e = dp_pinned_alloc((void **)&s->h_descs, sizeof(ScProd) * n_products))) return e;
+    if ((e = dp_pinned_alloc((void **)&s->h_out, sizeof(gle) * std::max<size_t>(SC_NACC * n_products, n_mles)))) return e;
+    if ((e = dp_pinned_alloc((void **)&s->h_fin, sizeof(ScFin) * n_mles))) return e;
     *out = s;
     return DP_OK;
 }
@@ -320,7 +348,7 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
             dst[i] = (m.where == 1) ? m.work + (m.len0 >> 1) : m.work;
         }
     }
-    u64 bytes = 0;
+    u64 bytes = 0, round_pairs = 1;
     for (u32 p = 0; p < s->n_products; p++) {
         const dp_sc_product &pr = s->products[p];
         ScProd &d = s->h_descs[p];
@@ -354,7 +382,10 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
         d.allbase = allbase ? 1 : 0;
         d.konst = newlen == 1 ? 1 : 0;
         d.npairs = newlen >> 1;
+        round_pairs = std::max<u64>(round_pairs, d.npairs);
     }
+    // grid sized for THIS round: 2 pairs per thread minimum so small rounds run in a single block
+    int gx = std::min(s->gx, dp_grid_for(round_pairs <= 256 ? round_pairs : (round_pairs + 1) / 2, SC_THREADS, 4));
     cudaStream_t st = dp_ctx().stream;
     DP_CUDA(cudaMemcpyAsync(s->d_descs, s->h_descs, sizeof(ScProd) * s->n_products, cudaMemcpyHostToDevice, st));
     // MLEs no product references still have to be folded (cannot happen through add_mle_list, kept for safety)
@@ -362,10 +393,20 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
         ScMle &m = s->mles[i];
         if (int e = dpk_fold_low(m.cur, m.is_ext, m.len, r, dst[i])) return e;
     }
-    dim3 grid((unsigned)s->gx, s->n_products);
+    dim3 grid((unsigned)gx, s->n_products);
     {
         DpProfScope prof(fold ? "k_sc_round(fold+msg)" : "k_sc_round(msg)", bytes);
-        k_sc_round<<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); DP_LAUNCHED();
+        u32 dsel = s->products[0].n_idx;
+        for (auto &pr : s->products) if (pr.n_idx != dsel) dsel = 0;
+        switch (dsel) {   // one small kernel per uniform degree keeps the instruction footprint low
+        case 1: k_sc_round<1><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
+        case 2: k_sc_round<2><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
+        case 3: k_sc_round<3><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
+        case 4: k_sc_round<4><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
+        case 5: k_sc_round<5><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
+        default: k_sc_round<0><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
+        }
+        DP_LAUNCHED();
     }
     DP_CUDA(cudaGetLastError());
     DP_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(gle) * SC_NACC * s->n_products, cudaMemcpyDeviceToHost, st));
@@ -435,5 +476,15 @@ int dp_sc_destroy(dp_sc *s) {
 }
 
 uint64_t dp_sc_last_round_bytes(const dp_sc *s) { return s ? s->last_bytes : 0; }
+
+int dp_sc_current_mle(dp_sc *s, uint32_t idx, dp_mle **out) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(s && out && idx < s->n_mles, DP_ERR_INVALID, "dp_sc_current_mle: bad argument");
+    const ScMle &m = s->mles[idx];
+    dp_mle *v = new dp_mle();
+    v->data = const_cast<void *>(m.cur); v->len = m.len; v->is_ext = m.is_ext; v->owned = false;
+    *out = v;
+    return DP_OK;
+}
 
 }  // extern "C"

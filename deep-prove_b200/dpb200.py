@@ -20,7 +20,10 @@ ABI_SYMBOLS = [
     "dp_kernel_launches", "dp_profile_enable", "dp_profile_reset", "dp_profile_read",
     "dp_mle_upload", "dp_mle_wrap_device", "dp_mle_clone", "dp_mle_download", "dp_mle_info", "dp_mle_device_ptr",
     "dp_mle_free", "dp_mle_fix_high", "dp_mle_fix_low", "dp_mle_evaluate", "dp_eq_build",
-    "dp_sc_create", "dp_sc_round", "dp_sc_finish", "dp_sc_destroy", "dp_sc_last_round_bytes",
+    "dp_sc_create", "dp_sc_round", "dp_sc_finish", "dp_sc_destroy", "dp_sc_last_round_bytes", "dp_sc_current_mle",
+    "dp_poseidon2_init", "dp_pcs_commit", "dp_pcs_comm_info", "dp_pcs_comm_codeword", "dp_pcs_comm_bh_evals", "dp_pcs_comm_free",
+    "dp_pcs_open_begin", "dp_pcs_open_round", "dp_pcs_open_final_message", "dp_pcs_open_query_words", "dp_pcs_open_query",
+    "dp_pcs_open_free",
 ]
 
 
@@ -280,3 +283,85 @@ def sumcheck_prove_parallel(mles, products, max_nv, label=b"m2vec"):
     hcheck(host().dph_sumcheck_prove_parallel(hs, len(mles), prods, len(products), max_nv, label, None, _ptr(point),
                                               _ptr(msgs), _ptr(fin), C.byref(deg)))
     return point, msgs, fin
+
+
+# ---- mpcs (Basefold) -------------------------------------------------------------------------------
+def _pcs_setup():
+    L = lib()
+    if getattr(L, "_pcs_ready", False):
+        return L
+    L.dp_pcs_commit.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.dp_pcs_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+    L.dp_pcs_comm_codeword.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.dp_pcs_comm_bh_evals.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.dp_pcs_comm_free.argtypes = [C.c_void_p]
+    L.dp_pcs_open_begin.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_void_p]
+    L.dp_pcs_open_round.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    L.dp_pcs_open_final_message.argtypes = [C.c_void_p, C.c_void_p]
+    L.dp_pcs_open_query_words.argtypes = [C.c_void_p]
+    L.dp_pcs_open_query_words.restype = C.c_uint64
+    L.dp_pcs_open_query.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.dp_pcs_open_free.argtypes = [C.c_void_p]
+    L.dp_poseidon2_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    H = host()
+    H.dph_pcs_open.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p]
+    H.dph_pcs_batch_open.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64,
+                                     C.POINTER(C.c_uint64)]
+    L._pcs_ready = True
+    return L
+
+
+class Commitment:
+    """BasefoldCommitmentWithWitness on device (dp_pcs_comm)."""
+
+    def __init__(self, mle, full_log):
+        L = _pcs_setup()
+        self.h = C.c_void_p()
+        check(L.dp_pcs_commit(mle.h, full_log, C.byref(self.h)))
+        nv, b, t = C.c_uint32(), C.c_int(), C.c_int()
+        self.root = np.zeros(4, dtype=np.uint64)
+        check(L.dp_pcs_comm_info(self.h, C.byref(nv), C.byref(b), C.byref(t), _ptr(self.root)))
+        self.num_vars, self.is_base, self.trivial = nv.value, bool(b.value), bool(t.value)
+
+    def codeword(self):
+        v = C.c_void_p()
+        check(lib().dp_pcs_comm_codeword(self.h, C.byref(v)))
+        return Mle(v.value).download()
+
+    def bh_evals(self):
+        v = C.c_void_p()
+        check(lib().dp_pcs_comm_bh_evals(self.h, C.byref(v)))
+        return Mle(v.value).download()
+
+    def free(self):
+        if self.h:
+            lib().dp_pcs_comm_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pcs_open(mle, full_log, point, label=b"m2vec", cap=1 << 24):
+    """Basefold::commit + Basefold::open through the C++ host mirror; returns (root, flat proof)."""
+    _pcs_setup()
+    p = _u64(point).reshape(-1)
+    out = np.zeros(cap, dtype=np.uint64)
+    n = C.c_uint64()
+    root = np.zeros(4, dtype=np.uint64)
+    hcheck(host().dph_pcs_open(mle.h, full_log, _ptr(p), label, _ptr(out), cap, C.byref(n), _ptr(root)))
+    return root, out[: n.value].copy()
+
+
+def pcs_batch_open(mles, full_log, points, label=b"m2vec", cap=1 << 25):
+    """commit each polynomial, then Basefold::batch_open with Evaluation::new(i, i, poly_i(point_i))."""
+    _pcs_setup()
+    hs = (C.c_void_p * len(mles))(*[m.h for m in mles])
+    p = np.concatenate([_u64(x).reshape(-1) for x in points])
+    out = np.zeros(cap, dtype=np.uint64)
+    n = C.c_uint64()
+    hcheck(host().dph_pcs_batch_open(hs, len(mles), full_log, _ptr(p), label, _ptr(out), cap, C.byref(n)))
+    return out[: n.value].copy()

@@ -56,3 +56,53 @@ int dph_sumcheck_prove_parallel(dp_mle *const *mles, uint32_t n_mles, const dp_s
 }
 
 }  // extern "C"
+
+// ---- mpcs (host/mpcs.hpp) ----
+#include "mpcs.hpp"
+extern "C" {
+
+// Basefold::commit + Basefold::open with BasefoldProof flattened (BasefoldProof::flatten layout)
+int dph_pcs_open(dp_mle *poly, uint32_t full_log, const uint64_t *point, const char *label, uint64_t *out, uint64_t cap, uint64_t *out_len, uint64_t *out_root) {
+    DPH_TRY
+    uint64_t len; int ext; uint32_t nv; check(dp_mle_info(poly, &len, &ext, &nv));
+    DeviceMle m = DeviceMle::wrap_device(dp_mle_device_ptr(poly), len, ext);
+    BasefoldProverParams pp; pp.full_message_size_log = full_log;
+    auto comm = Basefold::commit(pp, m);
+    if (out_root) memcpy(out_root, comm.root.v, 32);
+    ExtVec pt; for (uint32_t i = 0; i < nv; i++) pt.push_back(Ext(point[2 * i], point[2 * i + 1]));
+    BasicTranscript t(label);
+    BasefoldProof pr = Basefold::open(pp, m, comm, pt, t);
+    std::vector<uint64_t> f = pr.flatten();
+    *out_len = f.size();
+    if (f.size() > cap) { g_herr = "dph_pcs_open: output buffer too small"; return 2; }
+    memcpy(out, f.data(), 8 * f.size());
+    return 0;
+    DPH_CATCH
+}
+
+int dph_pcs_batch_open(dp_mle *const *polys, uint32_t n, uint32_t full_log, const uint64_t *points, const char *label, uint64_t *out, uint64_t cap,
+                       uint64_t *out_len) {
+    DPH_TRY
+    BasefoldProverParams pp; pp.full_message_size_log = full_log;
+    std::vector<DeviceMle> ms; std::vector<BasefoldCommitmentWithWitness> comms; std::vector<ExtVec> pts; std::vector<Evaluation> evals;
+    size_t o = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t len; int ext; uint32_t nv; check(dp_mle_info(polys[i], &len, &ext, &nv));
+        ms.push_back(DeviceMle::wrap_device(dp_mle_device_ptr(polys[i]), len, ext));
+        comms.push_back(Basefold::commit(pp, ms.back()));
+        ExtVec pt; for (uint32_t k = 0; k < nv; k++) pt.push_back(Ext(points[2 * (o + k)], points[2 * (o + k) + 1]));
+        o += nv; pts.push_back(pt);
+        Evaluation ev; ev.poly = i; ev.point = i; ev.value = ms.back().evaluate(pt);
+        evals.push_back(ev);
+    }
+    BasicTranscript t(label);
+    BasefoldProof pr = Basefold::batch_open(pp, ms, comms, pts, evals, t);
+    std::vector<uint64_t> f = pr.flatten();
+    *out_len = f.size();
+    if (f.size() > cap) { g_herr = "dph_pcs_batch_open: output buffer too small"; return 2; }
+    memcpy(out, f.data(), 8 * f.size());
+    return 0;
+    DPH_CATCH
+}
+
+}  // extern "C"

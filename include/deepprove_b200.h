@@ -94,8 +94,45 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals);
  * challenge and writes n_mles x [c0,c1]. */
 int dp_sc_finish(dp_sc *s, const uint64_t *last_challenge, uint64_t *out_final_evals);
 int dp_sc_destroy(dp_sc *s);
+/* Non-owning view of MLE `idx` as folded so far (valid until the next dp_sc_round / dp_sc_destroy):
+ * the state's `poly.flattened_ml_extensions[idx]` after the rounds run so far. */
+int dp_sc_current_mle(dp_sc *s, uint32_t idx, dp_mle **out_view);
 /* Algorithmic HBM bytes moved by the last dp_sc_round (SURVEY.md 8(d) rules), for roofline reports. */
 uint64_t dp_sc_last_round_bytes(const dp_sc *s);
+
+/* ---- mpcs: Basefold over RS code (rate 1/2, 200 queries, basecode 2^7) + Poseidon2 Merkle trees ------ */
+typedef struct dp_pcs_comm dp_pcs_comm;  /* BasefoldCommitmentWithWitness (mpcs/src/basefold/structure.rs:63-72) */
+typedef struct dp_pcs_open dp_pcs_open;  /* prover state of one commit phase (oracles + their trees) */
+
+/* Optional: replace the built-in Poseidon2 constants (HL Goldilocks width-8 instance) with the ones the
+ * Rust host reads from p3-goldilocks: ext_rc[2][4][8], int_rc[22], diag[8]  (ff_ext/src/lib.rs:179-194). */
+int dp_poseidon2_init(const uint64_t *ext_rc, const uint64_t *int_rc, const uint64_t *diag);
+/* Basefold::commit (basefold.rs:304-354).  `full_message_size_log` is the trimmed parameter size
+ * (RSCodeProverParameters.full_message_size_log, rs.rs:222-227): it fixes the coset shift.  Polynomials
+ * with <= 7 variables get a Merkle tree over their raw evaluations ("TooSmall", basefold.rs:102-104). */
+int dp_pcs_commit(const dp_mle *poly, uint32_t full_message_size_log, dp_pcs_comm **out);
+int dp_pcs_comm_info(const dp_pcs_comm *c, uint32_t *num_vars, int *is_base, int *is_trivial, uint64_t root[4]);
+int dp_pcs_comm_codeword(const dp_pcs_comm *c, dp_mle **out_view);   /* bit-reversed codeword (view) */
+int dp_pcs_comm_bh_evals(const dp_pcs_comm *c, dp_mle **out_view);   /* bit-reversed evaluations (view) */
+int dp_pcs_comm_free(dp_pcs_comm *c);
+/* commit_phase (commit_phase.rs:30-183) when coeffs == NULL (one commitment, num_vars == its size), else
+ * batch_commit_phase (:187-358) with one E coefficient per commitment.  Returns the first sumcheck
+ * message as 3 coefficients [c0,c1,c2] x [limb0,limb1].  The host appends it to the transcript, squeezes
+ * "commit round" and calls dp_pcs_open_round. */
+int dp_pcs_open_begin(const dp_pcs_comm *const *comms, const uint64_t *coeffs, uint32_t n_comms, const uint64_t *point,
+                      uint32_t num_vars, dp_pcs_open **out, uint64_t first_msg[6]);
+/* Fold by `challenge`.  If *is_last == 0: next_msg (3 coefficients) and the root of the folded oracle's
+ * Merkle tree are returned (the host appends msg later and the root now).  If *is_last == 1 the final
+ * message is ready (dp_pcs_open_final_message) and next_msg/root are untouched. */
+int dp_pcs_open_round(dp_pcs_open *o, const uint64_t challenge[2], uint64_t next_msg[6], uint64_t root[4], int *is_last);
+int dp_pcs_open_final_message(dp_pcs_open *o, uint64_t *out /* 2^7 x [c0,c1] */);
+/* Query phase gather (query_phase.rs:373-474).  For each x index, for every commitment (codeword index
+ * x >> (log N - log |codeword|)) and then every round oracle i (index x >> (i+1)):
+ *   [p0.c0 p0.c1 p1.c0 p1.c1] (Base values have c1 = 0) followed by the Merkle path without leaf sibling
+ *   or root (log|leaves| - 1 digests of 4 limbs).  dp_pcs_open_query_words() = words per x index. */
+uint64_t dp_pcs_open_query_words(const dp_pcs_open *o);
+int dp_pcs_open_query(dp_pcs_open *o, const uint64_t *x_indices, uint32_t n, uint64_t *out);
+int dp_pcs_open_free(dp_pcs_open *o);
 
 #ifdef __cplusplus
 }

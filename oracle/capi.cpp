@@ -135,3 +135,78 @@ int dpo_sumcheck_verify(const u64 *claimed_sum, u32 nv, u32 max_deg, const u64 *
 }
 
 }  // extern "C"
+
+// ---- Basefold (oracle/basefold.hpp) ----
+#include "basefold.hpp"
+static FVec mk_fvec(const u64 *data, u64 len, int is_ext) {
+    FVec v; v.is_ext = is_ext != 0;
+    if (is_ext) { v.e.resize(len); for (u64 i = 0; i < len; i++) v.e[i] = E(f_from_u64(data[2 * i]), f_from_u64(data[2 * i + 1])); }
+    else { v.b.resize(len); for (u64 i = 0; i < len; i++) v.b[i] = f_from_u64(data[i]); }
+    return v;
+}
+static void put_fvec(const FVec &v, u64 *out) { if (v.is_ext) for (size_t i = 0; i < v.e.size(); i++) put_e(out, i, v.e[i]); else for (size_t i = 0; i < v.b.size(); i++) out[i] = v.b[i]; }
+
+extern "C" {
+
+// RS encode of an already-prepared coefficient vector (rs.rs encode_internal): out has 2*len elements
+void dpo_rs_encode(const u64 *coeffs, u64 len, int is_ext, u32 full_log, u64 *out) { put_fvec(rs_encode(mk_fvec(coeffs, len, is_ext), full_log), out); }
+void dpo_interpolate_hc(const u64 *evals, u64 len, int is_ext, u64 *out) {
+    FVec v = mk_fvec(evals, len, is_ext);
+    if (is_ext) interpolate_hc<E>(v.e, e_sub); else interpolate_hc<u64>(v.b, f_sub);
+    put_fvec(v, out);
+}
+void dpo_merkle_root(const u64 *leaves, u64 len, int is_ext, u64 *out_root) { auto t = merkelize(mk_fvec(leaves, len, is_ext)); memcpy(out_root, t.back()[0].v, 32); }
+void dpo_folding_coeffs(u32 full_log, u32 level, u64 index, u64 *x0, u64 *w) { folding_coeffs(full_log, level, index, *x0, *w); }
+void dpo_fri_fold(const u64 *vals, u64 len, u32 full_log, const u64 *r, u64 *out) {
+    std::vector<E> v(len); for (u64 i = 0; i < len; i++) v[i] = E(vals[2 * i], vals[2 * i + 1]);
+    auto o = fri_fold(v, full_log, E(r[0], r[1]));
+    for (size_t i = 0; i < o.size(); i++) put_e(out, i, o[i]);
+}
+// commit: root + (optionally) codeword and bh_evals, all bit-reversed as stored by the reference
+int dpo_pcs_commit(const u64 *evals, u64 len, int is_ext, u32 full_log, u64 *out_root, u64 *out_codeword, u64 *out_bh) {
+    try {
+        Commitment c = basefold_commit(mk_fvec(evals, len, is_ext), full_log);
+        memcpy(out_root, c.root().v, 32);
+        if (out_codeword) put_fvec(c.codeword_tree.leaves, out_codeword);
+        if (out_bh) put_fvec(c.bh_evals, out_bh);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int dpo_pcs_open(const u64 *evals, u64 len, int is_ext, u32 full_log, const u64 *point, const char *label, u64 *out, u64 cap, u64 *out_len) {
+    try {
+        Commitment c = basefold_commit(mk_fvec(evals, len, is_ext), full_log);
+        Transcript t(label);
+        BasefoldProof p = basefold_open(full_log, c, mk_point(point, (u32)c.num_vars), t);
+        std::vector<u64> f = flatten_proof(p);
+        *out_len = f.size();
+        if (f.size() > cap) { g_err = "dpo_pcs_open: output buffer too small"; return 2; }
+        memcpy(out, f.data(), 8 * f.size());
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// batch_open with Evaluation::new(i, i, poly_i(point_i)); points are concatenated (poly i has nv_i elements)
+int dpo_pcs_batch_open(u32 n, const u64 *const *data, const u64 *lens, const int *is_ext, u32 full_log, const u64 *points, const char *label,
+                       u64 *out, u64 cap, u64 *out_len) {
+    try {
+        std::vector<FVec> polys; std::vector<Commitment> comms; std::vector<std::vector<E>> pts; std::vector<Evaluation> evals;
+        size_t o = 0;
+        for (u32 i = 0; i < n; i++) {
+            polys.push_back(mk_fvec(data[i], lens[i], is_ext[i]));
+            comms.push_back(basefold_commit(polys.back(), full_log));
+            u32 nv = (u32)ceil_log2(lens[i]);
+            pts.push_back(mk_point(points + 2 * o, nv)); o += nv;
+            MLE m; m.is_ext = polys.back().is_ext; m.num_vars = nv; m.base = polys.back().b; m.ext = polys.back().e;
+            evals.push_back({i, i, mle_evaluate(m, pts.back())});
+        }
+        std::vector<const Commitment *> cp; for (auto &c : comms) cp.push_back(&c);
+        Transcript t(label);
+        BasefoldProof p = basefold_batch_open(full_log, polys, cp, pts, evals, t);
+        std::vector<u64> f = flatten_proof(p);
+        *out_len = f.size();
+        if (f.size() > cap) { g_err = "dpo_pcs_batch_open: output buffer too small"; return 2; }
+        memcpy(out, f.data(), 8 * f.size());
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+
+}  // extern "C"

@@ -226,3 +226,90 @@ def pe_add(a, b):
 
 def pe_sub(a, b):
     return ((int(a[0]) - int(b[0])) % P, (int(a[1]) - int(b[1])) % P)
+
+
+# ---- Basefold ----
+def _fv(a, is_ext):
+    a = u64(a).reshape(-1)
+    return a, a.size // (2 if is_ext else 1)
+
+
+def rs_encode(coeffs, is_ext, full_log):
+    a, n = _fv(coeffs, is_ext)
+    out = np.zeros(2 * a.size, dtype=np.uint64)
+    lib().dpo_rs_encode(ptr(a), C.c_uint64(n), int(is_ext), C.c_uint32(full_log), ptr(out))
+    return out.reshape(-1, 2) if is_ext else out
+
+
+def interpolate_hc(evals, is_ext):
+    a, n = _fv(evals, is_ext)
+    out = np.zeros_like(a)
+    lib().dpo_interpolate_hc(ptr(a), C.c_uint64(n), int(is_ext), ptr(out))
+    return out.reshape(-1, 2) if is_ext else out
+
+
+def merkle_root(leaves, is_ext):
+    a, n = _fv(leaves, is_ext)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().dpo_merkle_root(ptr(a), C.c_uint64(n), int(is_ext), ptr(out))
+    return out
+
+
+def folding_coeffs(full_log, level, index):
+    x0, w = C.c_uint64(), C.c_uint64()
+    lib().dpo_folding_coeffs(C.c_uint32(full_log), C.c_uint32(level), C.c_uint64(index), C.byref(x0), C.byref(w))
+    return x0.value, w.value
+
+
+def fri_fold(vals, full_log, r):
+    a = u64(vals).reshape(-1)
+    n = a.size // 2
+    rr = u64(r)
+    out = np.zeros((n // 2, 2), dtype=np.uint64)
+    lib().dpo_fri_fold(ptr(a), C.c_uint64(n), C.c_uint32(full_log), ptr(rr), ptr(out))
+    return out
+
+
+def pcs_commit(evals, is_ext, full_log, want_codeword=True):
+    a, n = _fv(evals, is_ext)
+    root = np.zeros(4, dtype=np.uint64)
+    nv = n.bit_length() - 1
+    trivial = nv <= 7
+    lim = 2 if is_ext else 1
+    cw = np.zeros((n if trivial else 2 * n) * lim, dtype=np.uint64)
+    bh = np.zeros(n * lim, dtype=np.uint64)
+    rc = lib().dpo_pcs_commit(ptr(a), C.c_uint64(n), int(is_ext), C.c_uint32(full_log), ptr(root), ptr(cw) if want_codeword else None,
+                              ptr(bh) if want_codeword else None)
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    if is_ext:
+        cw, bh = cw.reshape(-1, 2), bh.reshape(-1, 2)
+    return root, cw, bh
+
+
+def pcs_open(evals, is_ext, full_log, point, label=b"m2vec", cap=1 << 24):
+    a, n = _fv(evals, is_ext)
+    p = u64(point).reshape(-1)
+    out = np.zeros(cap, dtype=np.uint64)
+    ln = C.c_uint64()
+    rc = lib().dpo_pcs_open(ptr(a), C.c_uint64(n), int(is_ext), C.c_uint32(full_log), ptr(p), label, ptr(out), C.c_uint64(cap), C.byref(ln))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return out[: ln.value].copy()
+
+
+def pcs_batch_open(polys, full_log, points, label=b"m2vec", cap=1 << 25):
+    """polys: list of (array, is_ext); points: list of (nv_i, 2) arrays"""
+    arrs = [u64(p[0]).reshape(-1) for p in polys]
+    n = len(arrs)
+    data = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    lens = u64([a.size // (2 if p[1] else 1) for a, p in zip(arrs, polys)])
+    is_ext = np.ascontiguousarray(np.asarray([int(bool(p[1])) for p in polys], dtype=np.int32))
+    pts = np.concatenate([u64(x).reshape(-1) for x in points])
+    out = np.zeros(cap, dtype=np.uint64)
+    ln = C.c_uint64()
+    rc = lib().dpo_pcs_batch_open(C.c_uint32(n), data, ptr(lens), ptr(is_ext), C.c_uint32(full_log), ptr(pts), label, ptr(out),
+                                  C.c_uint64(cap), C.byref(ln))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return out[: ln.value].copy()
