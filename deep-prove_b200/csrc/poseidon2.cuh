@@ -2,7 +2,7 @@
 // Merkle hash shapes built on it.  Reference: ff_ext/src/lib.rs:177-235 (NoAllocPoseidon),
 // poseidon/src/poseidon_hash.rs:17-71 over p3 DuplexChallenger<_,_,8,4> (overwrite-mode absorb,
 // outputs popped from the end of the rate).  Constants: include/dp_poseidon2_constants.h (provenance and
-// pinning status are documented in oracle/gen_poseidon2_constants.py).
+// pinning status are documented in the generator script that emits that header).
 #pragma once
 #include "gl.cuh"
 #include "../../include/dp_poseidon2_constants.h"

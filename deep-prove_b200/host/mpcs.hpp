@@ -43,7 +43,7 @@ struct BasefoldProof {
     std::vector<BatchedQueryResult> batched_queries;    // ::Batched
     std::vector<ExtVec> sumcheck_proof;                 // Option<SumcheckProof<Coefficients>>: 3 coefficients per round
     bool is_trivial = false; std::vector<u64> trivial_proof; bool trivial_is_ext = false;
-    // flat u64 image used by the parity tests (same layout as oracle/basefold.hpp flatten_proof)
+    // flat u64 image used by the parity tests (layout documented in tests/test_oracle_basefold.py parse_flat)
     std::vector<u64> flatten() const {
         std::vector<u64> o;
         auto fe = [&](const Ext &e) { o.push_back(e.c0); o.push_back(e.c1); };
