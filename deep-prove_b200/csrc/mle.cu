@@ -276,6 +276,23 @@ int dp_mle_fix_high(dp_mle *m, const uint64_t *point, uint32_t k) {
     return DP_OK;
 }
 
+// fix_high_variables (mle.rs:529-560): same as above but returns a new MLE and leaves `m` untouched
+int dp_mle_fix_high_new(const dp_mle *m, const uint64_t *point, uint32_t k, dp_mle **outp) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(m && outp && (point || k == 0), DP_ERR_INVALID, "dp_mle_fix_high_new: null argument");
+    DP_CHECK(k <= m->num_vars(), DP_ERR_INVALID, "invalid size of partial point");
+    if (k == 0) return dp_mle_clone(m, outp);
+    gle pt[32]; point_from_host(point, k, pt);
+    dp_mle *r = new dp_mle(); r->len = m->len >> k; r->is_ext = true; r->owned = true;
+    if (int e = dp_dev_alloc(&r->data, r->bytes())) { delete r; return e; }
+    {
+        DpProfScope prof("fix_high(one pass)", m->bytes() + r->bytes());
+        if (int e = dpk_fix_high(m->data, m->is_ext, m->len, pt, k, (gle *)r->data)) return e;
+    }
+    *outp = r;
+    return DP_OK;
+}
+
 int dp_mle_fix_low(const dp_mle *m, const uint64_t *point, uint32_t k, dp_mle **outp) {
     DP_REQUIRE_CTX();
     DP_CHECK(m && outp && (point || k == 0), DP_ERR_INVALID, "dp_mle_fix_low: null argument");

@@ -19,11 +19,12 @@ ABI_SYMBOLS = [
     "dp_init", "dp_shutdown", "dp_device_count", "dp_last_error", "dp_version", "dp_set_stream", "dp_synchronize",
     "dp_kernel_launches", "dp_profile_enable", "dp_profile_reset", "dp_profile_read",
     "dp_mle_upload", "dp_mle_wrap_device", "dp_mle_clone", "dp_mle_download", "dp_mle_info", "dp_mle_device_ptr",
-    "dp_mle_free", "dp_mle_fix_high", "dp_mle_fix_low", "dp_mle_evaluate", "dp_eq_build",
+    "dp_mle_free", "dp_mle_fix_high", "dp_mle_fix_high_new", "dp_mle_fix_low", "dp_mle_evaluate", "dp_eq_build",
     "dp_sc_create", "dp_sc_round", "dp_sc_finish", "dp_sc_destroy", "dp_sc_last_round_bytes", "dp_sc_current_mle",
     "dp_poseidon2_init", "dp_pcs_commit", "dp_pcs_comm_info", "dp_pcs_comm_codeword", "dp_pcs_comm_bh_evals", "dp_pcs_comm_free",
     "dp_pcs_open_begin", "dp_pcs_open_round", "dp_pcs_open_final_message", "dp_pcs_open_query_words", "dp_pcs_open_query",
     "dp_pcs_open_free",
+    "dp_logup_build", "dp_logup_num_vars", "dp_logup_outputs", "dp_logup_layer_mles", "dp_logup_free", "dp_mle_linear_combination",
 ]
 
 
@@ -365,3 +366,52 @@ def pcs_batch_open(mles, full_log, points, label=b"m2vec", cap=1 << 25):
     n = C.c_uint64()
     hcheck(host().dph_pcs_batch_open(hs, len(mles), full_log, _ptr(p), label, _ptr(out), cap, C.byref(n)))
     return out[: n.value].copy()
+
+
+# ---- zkml MLP prover (host mirror of zkml::{Context, Prover}) -----------------------------------------
+class ZkmlContext:
+    """Context::generate for n_layers x [Dense(width x width)+bias -> Requant -> ReLU]: weights, bias and lookup
+    tables uploaded once and committed (setup).  rq: (n_layers, 4) int64 = right_shift, fp_scale,
+    fixed_point_multiplier, intermediate_bit_size."""
+
+    def __init__(self, n_layers, width, weights, bias, rq):
+        _pcs_setup()
+        H = host()
+        H.dph_zkml_context_new.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        H.dph_zkml_context_free.argtypes = [C.c_void_p]
+        H.dph_zkml_prove.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        self.n_layers, self.width = n_layers, width
+        w = np.ascontiguousarray(weights, dtype=np.int64)
+        b = np.ascontiguousarray(bias, dtype=np.int64)
+        r = np.ascontiguousarray(rq, dtype=np.int64)
+        self.h = C.c_void_p()
+        hcheck(H.dph_zkml_context_new(n_layers, width, _ptr(w), _ptr(b), _ptr(r), C.byref(self.h)))
+        self._out = np.zeros(1 << 22, dtype=np.uint64)
+
+    def prove(self, x, label=b"m2vec"):
+        """inference + Prover::prove + flat proof, from a host input vector (end to end)"""
+        x = np.ascontiguousarray(x, dtype=np.int64)
+        n = C.c_uint64()
+        hcheck(host().dph_zkml_prove(self.h, _ptr(x), 0, label, _ptr(self._out), self._out.size, C.byref(n)))
+        return self._out[: n.value].copy()
+
+    def run_inference(self, x):
+        x = np.ascontiguousarray(x, dtype=np.int64)
+        hcheck(host().dph_zkml_prove(self.h, _ptr(x), 1, b"", None, 0, None))
+
+    def prove_trace(self, label=b"m2vec", want_proof=False):
+        """Prover::prove on the stored inference trace (what zkml/src/bin/bench.rs:390-408 times)"""
+        n = C.c_uint64()
+        hcheck(host().dph_zkml_prove(self.h, None, 2, label, _ptr(self._out) if want_proof else None, self._out.size, C.byref(n)))
+        return self._out[: n.value].copy() if want_proof else None
+
+    def free(self):
+        if self.h:
+            host().dph_zkml_context_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -106,3 +106,59 @@ int dph_pcs_batch_open(dp_mle *const *polys, uint32_t n, uint32_t full_log, cons
 }
 
 }  // extern "C"
+
+// ---- zkml MLP prover (host/zkml.hpp) ----
+#include "zkml.hpp"
+#include <chrono>
+namespace {
+struct ZkHandle { dp::zkml::Model model; dp::zkml::Context ctx; std::vector<std::vector<dp::zkml::Element>> trace; std::vector<dp::zkml::Element> trace_input; };
+}
+extern "C" {
+
+// Model = n_layers x [Dense(width x width)+bias -> Requant -> ReLU]; rq = n_layers x {right_shift, fp_scale, fpm, intermediate_bits}.
+// Builds the Context: uploads weights/bias/tables and commits them (CommitmentContext::new) -- setup, not proving.
+int dph_zkml_context_new(uint32_t n_layers, uint32_t width, const int64_t *weights, const int64_t *bias, const int64_t *rq, void **out) {
+    DPH_TRY
+    using namespace dp::zkml;
+    auto *h = new ZkHandle();
+    h->model.input_len = width;
+    for (uint32_t l = 0; l < n_layers; l++) {
+        Node d; d.op = Op::Dense; d.nrows = d.ncols = width;
+        d.weights.assign(weights + (size_t)l * width * width, weights + (size_t)(l + 1) * width * width);
+        d.bias.assign(bias + (size_t)l * width, bias + (size_t)(l + 1) * width);
+        h->model.nodes.push_back(std::move(d));
+        Node r; r.op = Op::Requant; r.rq.right_shift = rq[4 * l]; r.rq.fp_scale = rq[4 * l + 1]; r.rq.fixed_point_multiplier = rq[4 * l + 2]; r.rq.intermediate_bit_size = rq[4 * l + 3];
+        h->model.nodes.push_back(r);
+        Node a; a.op = Op::Relu; h->model.nodes.push_back(a);
+    }
+    h->ctx = Context::generate(h->model);
+    check(dp_synchronize());
+    *out = h;
+    return 0;
+    DPH_CATCH
+}
+void dph_zkml_context_free(void *h) { delete (ZkHandle *)h; }
+
+// mode 0: inference + Prover::prove + flatten (end to end from the host input buffer)
+// mode 1: run inference only and keep the trace in the handle (not proving)
+// mode 2: Prover::prove on the stored trace (what zkml/src/bin/bench.rs times), flatten only if out != NULL
+int dph_zkml_prove(void *handle, const int64_t *input, int mode, const char *label, uint64_t *out, uint64_t cap, uint64_t *out_len) {
+    DPH_TRY
+    using namespace dp::zkml;
+    ZkHandle *h = (ZkHandle *)handle;
+    size_t w = h->model.input_len;
+    if (mode == 0 || mode == 1) { h->trace_input.assign(input, input + w); h->trace = run(h->model, h->trace_input); if (mode == 1) return 0; }
+    BasicTranscript t(label);
+    Prover<BasicTranscript> prover(h->ctx, t);
+    Proof p = prover.prove(h->trace_input, h->trace);
+    if (out) {
+        std::vector<uint64_t> f = p.flatten(h->model.nodes.size());
+        *out_len = f.size();
+        if (f.size() > cap) { g_herr = "dph_zkml_prove: output buffer too small"; return 2; }
+        memcpy(out, f.data(), 8 * f.size());
+    }
+    return 0;
+    DPH_CATCH
+}
+
+}  // extern "C"

@@ -33,6 +33,11 @@ class DeviceMle {
     uint32_t num_vars() const { uint32_t n; check(dp_mle_info(h_.get(), nullptr, nullptr, &n)); return n; }
     Ext evaluate(const ExtVec &point) const { auto f = flatten(point); u64 o[2]; check(dp_mle_evaluate(h_.get(), f.data(), (uint32_t)point.size(), o)); return Ext(o[0], o[1]); }
     void fix_high_variables_in_place(const ExtVec &point) { auto f = flatten(point); check(dp_mle_fix_high(h_.get(), f.data(), (uint32_t)point.size())); }
+    DeviceMle fix_high_variables(const ExtVec &point) const { auto f = flatten(point); dp_mle *o; check(dp_mle_fix_high_new(h_.get(), f.data(), (uint32_t)point.size(), &o)); return DeviceMle(o); }
+    static DeviceMle linear_combination(const std::vector<DeviceMle> &ms, const ExtVec &coefs) {
+        std::vector<dp_mle *> hs; for (auto &m : ms) hs.push_back(m.handle());
+        auto f = flatten(coefs); dp_mle *o; check(dp_mle_linear_combination(hs.data(), f.data(), (uint32_t)hs.size(), &o)); return DeviceMle(o);
+    }
     DeviceMle fix_variables(const ExtVec &point) const { auto f = flatten(point); dp_mle *o; check(dp_mle_fix_low(h_.get(), f.data(), (uint32_t)point.size(), &o)); return DeviceMle(o); }
     DeviceMle clone() const { dp_mle *o; check(dp_mle_clone(h_.get(), &o)); return DeviceMle(o); }
     std::vector<u64> download() const { std::vector<u64> v(len() * (is_ext() ? 2 : 1)); check(dp_mle_download(h_.get(), v.data())); return v; }

@@ -1,0 +1,395 @@
+// Host mirror of the zkml prover for the MLP path (Dense -> Requant -> ReLU chains) over the C ABI.
+//   zkml::{Context::generate, Prover::new/.prove} (zkml/src/iop/context.rs:110-215, iop/prover.rs:401-486),
+//   prove_tables (:110-157), layers/{dense.rs:423-551, requant.rs:208-330,531-680, activation.rs:238-460},
+//   lookup/{context.rs:158-296,464-480,631-781, witness.rs, logup_gkr/prover.rs:24-237},
+//   commit/{context.rs:59-190,290-418, same_poly.rs:88-126}.
+// Orchestration, Fiat-Shamir, claims bookkeeping and the (tiny) quantised witness columns stay on the host as
+// in the reference; every polynomial lives in HBM and every O(n) loop goes through include/deepprove_b200.h.
+#pragma once
+#include "mpcs.hpp"
+#include <unordered_map>
+
+namespace dp {
+namespace zkml {
+
+typedef int64_t Element;                                    // zkml/src/lib.rs:40
+constexpr size_t BIT_LEN = 8;                               // quantization/mod.rs:20-26
+constexpr Element QMIN = -127, QMAX = 127;                  // quantization/mod.rs:28-29
+constexpr Element COLUMN_SEPARATOR = (Element)1 << 32;      // lookup/context.rs:622
+inline size_t ceil_log2(size_t x) { size_t l = 0; while (((size_t)1 << l) < x) l++; return l; }
+
+struct Claim { ExtVec point; Ext eval; };
+
+struct Requant {                                            // layers/requant.rs:52-70
+    size_t right_shift = 0, fp_scale = 0, intermediate_bit_size = 0; Element fixed_point_multiplier = 0;
+    size_t shift() const { return fp_scale + right_shift; }
+    size_t clamping_size() const { return intermediate_bit_size + ceil_log2((size_t)fixed_point_multiplier) - shift(); }
+    Element apply(Element e) const {
+        Element rounding = (Element)1 << (shift() - 1);
+        Element unclamped = (rounding + e * fixed_point_multiplier) >> shift();
+        Element sign = unclamped >= 0 ? 1 : -1, a = unclamped < 0 ? -unclamped : unclamped;
+        return a >= QMAX ? QMAX * sign : unclamped;
+    }
+    Ext recombine_claims(Ext clamping_claim, const ExtVec &shifted) const {   // requant.rs:483-515
+        Ext full = Ext::from_base(canon(1ULL << shift())) * clamping_claim, p2 = Ext::one();
+        for (auto &v : shifted) { full += v * p2; p2 *= Ext::from_base(1ULL << BIT_LEN); }
+        return (full - Ext::from_base(canon(1ULL << (shift() - 1)))) * Ext::from_base(from_i64(fixed_point_multiplier)).inverse();
+    }
+};
+
+enum class Op { Dense, Requant, Relu };
+struct Node { Op op; size_t nrows = 0, ncols = 0; std::vector<Element> weights, bias; Requant rq; };
+struct Model { std::vector<Node> nodes; size_t input_len = 0; };
+
+// TableType with the enum's derive(Ord) order (lookup/context.rs:53-63): Relu < Range < Clamping(size)
+struct TableType {
+    int kind; size_t size;
+    bool operator<(const TableType &o) const { return kind != o.kind ? kind < o.kind : size < o.size; }
+    static TableType relu() { return {0, 0}; }
+    static TableType range() { return {2, 0}; }
+    static TableType clamping(size_t s) { return {3, s}; }
+    size_t multiplicity_poly_vars() const { return kind == 3 ? size : BIT_LEN; }   // :482-493
+};
+inline Element relu(Element e) { return e < 0 ? 0 : e; }
+inline std::vector<u64> to_base(const std::vector<Element> &v) { std::vector<u64> o(v.size()); for (size_t i = 0; i < v.size(); i++) o[i] = from_i64(v[i]); return o; }
+
+// (PCS::CommitmentWithWitness, DenseMultilinearExtension) -- lookup/context.rs:38-41
+struct ProverCommitment { BasefoldCommitmentWithWitness comm; DeviceMle poly; };
+
+struct TableData { std::vector<Element> merged; std::map<Element, u64> table_count; std::vector<DeviceMle> columns; };
+
+struct LogUpProof {
+    std::vector<IOPProof> sumcheck_proofs; std::vector<ExtVec> round_evaluations; std::vector<Claim> output_claims; std::vector<ExtVec> circuit_outputs; bool table = false;
+};
+struct LogUpInput {   // logup_gkr/structs.rs:134-148 with the columns resident in HBM
+    bool table = false; std::vector<DeviceMle> column_evals; DeviceMle multiplicities; Ext constant_challenge, column_separation_challenge; size_t columns_per_instance = 1;
+};
+
+struct LogUpHandle { dp_logup *h = nullptr; ~LogUpHandle() { if (h) dp_logup_free(h); } };
+
+// logup_gkr::prover::batch_prove (prover.rs:24-237)
+template <class T>
+LogUpProof logup_batch_prove(const LogUpInput &in, T &t) {
+    std::vector<std::unique_ptr<LogUpHandle>> circuits;
+    u64 cc[2] = {in.constant_challenge.c0, in.constant_challenge.c1}, sc[2] = {in.column_separation_challenge.c0, in.column_separation_challenge.c1};
+    auto build = [&](size_t from, size_t n, const DeviceMle *mult) {
+        std::vector<dp_mle *> cols; for (size_t k = 0; k < n; k++) cols.push_back(in.column_evals[from + k].handle());
+        auto L = std::make_unique<LogUpHandle>();
+        check(dp_logup_build(cols.data(), (uint32_t)n, mult ? mult->handle() : nullptr, cc, sc, &L->h));
+        circuits.push_back(std::move(L));
+    };
+    if (in.table) build(0, in.column_evals.size(), &in.multiplicities);
+    else for (size_t i = 0; i < in.column_evals.size(); i += in.columns_per_instance) build(i, in.columns_per_instance, nullptr);
+    LogUpProof pr; pr.table = in.table;
+    size_t total_layers = 0;
+    for (auto &c : circuits) {
+        uint32_t nv; check(dp_logup_num_vars(c->h, &nv)); total_layers = std::max<size_t>(total_layers, nv);
+        u64 o[8]; check(dp_logup_outputs(c->h, o));
+        pr.circuit_outputs.push_back({Ext(o[0], o[1]), Ext(o[2], o[3]), Ext(o[4], o[5]), Ext(o[6], o[7])});
+    }
+    t.append_field_element(canon(circuits.size()));
+    for (auto &o : pr.circuit_outputs) t.append_field_element_exts(o);
+    Ext batching = t.get_and_append_challenge("initial_batching"), alpha = t.get_and_append_challenge("initial_alpha"), lambda = t.get_and_append_challenge("initial_lambda");
+    Ext claim = Ext::zero(), ac = Ext::one();
+    for (auto &e : pr.circuit_outputs) { claim += ac * (batching * (e[1] - e[0]) + e[0] + lambda * (batching * (e[3] - e[2]) + e[2])); ac *= alpha; }
+    ExtVec point = {batching};
+    for (size_t v = 1; v <= total_layers; v++) {
+        t.append_field_element_ext(claim);
+        DeviceMle eq = DeviceMle::build_eq_x_r(point);           // compute_betas_eval(&sumcheck_point)
+        VirtualPolynomial vp(v);
+        Ext cur = Ext::one();
+        for (auto &c : circuits) {
+            dp_mle *views[4]; uint32_t n = 0;
+            check(dp_logup_layer_mles(c->h, (uint32_t)v, views, &n));
+            std::vector<DeviceMle> m; for (uint32_t k = 0; k < n; k++) m.push_back(DeviceMle(views[k]));
+            if (n == 4) { vp.add_mle_list({eq, m[0], m[3]}, cur); vp.add_mle_list({eq, m[1], m[2]}, cur); vp.add_mle_list({eq, m[2], m[3]}, cur * lambda); }
+            else { vp.add_mle_list({eq, m[1]}, -cur); vp.add_mle_list({eq, m[0]}, -cur); vp.add_mle_list({eq, m[0], m[1]}, cur * lambda); }
+            cur *= alpha;
+        }
+        auto res = IOPProverState::prove_parallel(std::move(vp), t);
+        point = res.first.point;
+        const ExtVec &fe = res.second.get_mle_final_evaluations();
+        ExtVec evals(fe.begin() + 1, fe.end());
+        batching = t.get_and_append_challenge("logup_batching"); alpha = t.get_and_append_challenge("logup_alpha"); lambda = t.get_and_append_challenge("logup_lambda");
+        point.push_back(batching);
+        pr.sumcheck_proofs.push_back(res.first);
+        Ext acc = Ext::zero(), al = Ext::one();
+        if (v != total_layers || in.table) for (size_t i = 0; i + 3 < evals.size(); i += 4) { const Ext *e = &evals[i]; acc += al * (batching * (e[2] - e[0]) + e[0] + lambda * (batching * (e[1] - e[3]) + e[3])); al *= alpha; }
+        else for (size_t i = 0; i + 1 < evals.size(); i += 2) { const Ext *e = &evals[i]; acc += al * (batching * (e[0] - e[1]) + e[1]); al *= alpha; }   // final_round_claim, Lookup
+        claim = acc;
+        pr.round_evaluations.push_back(evals);
+    }
+    // output claims about the base columns (prover.rs:172-183)
+    if (in.table) pr.output_claims.push_back({point, in.multiplicities.evaluate(point)});
+    for (auto &c : in.column_evals) pr.output_claims.push_back({point, c.evaluate(point)});
+    return pr;
+}
+
+// same_poly::Prover (commit/same_poly.rs:58-126)
+struct SamePolyProof { IOPProof sumcheck; ExtVec evals; Claim extract_claim() const { return {sumcheck.point, evals.at(1)}; } };
+template <class T>
+SamePolyProof same_poly_prove(const DeviceMle &poly, const std::vector<Claim> &claims, T &t) {
+    ExtVec ch; for (size_t i = 0; i < claims.size(); i++) { if (claims[i].point.size() != poly.num_vars()) throw Error(DP_ERR_INVALID, "Invalid claim length"); ch.push_back(t.read_challenge()); }
+    std::vector<DeviceMle> betas; for (auto &c : claims) betas.push_back(DeviceMle::build_eq_x_r(c.point));
+    DeviceMle final_beta = DeviceMle::linear_combination(betas, ch);
+    VirtualPolynomial vp(poly.num_vars());
+    vp.add_mle_list({final_beta, poly}, Ext::one());
+    auto res = IOPProverState::prove_parallel(std::move(vp), t);
+    return {res.first, res.second.get_mle_final_evaluations()};
+}
+
+struct DenseProof { IOPProof sumcheck; Ext bias_eval; ExtVec individual_claims; };
+struct RequantProof { IOPProof io_accumulation; ExtVec accumulation_evals; LogUpProof clamping_lookup, shifted_lookup; std::vector<Digest> commitments; };
+struct ActivationProof { SamePolyProof io_accumulation; LogUpProof lookup; std::vector<Digest> commits; };
+struct TableProof { Digest multiplicity_commit; LogUpProof lookup; };
+struct Proof {   // zkml/src/iop/mod.rs:21-31 + commit::context::ModelOpeningProof
+    std::map<size_t, DenseProof> dense; std::map<size_t, RequantProof> requant; std::map<size_t, ActivationProof> activation;
+    std::vector<TableProof> table_proofs; BasefoldProof batch_proof; std::vector<BasefoldProof> trivial_proofs;
+    std::vector<u64> flatten(size_t n_nodes) const;
+};
+
+// Context (iop/context.rs:38-47): step info + CommitmentContext (weights/bias committed at setup) + lookup tables
+class Context {
+  public:
+    static Context generate(const Model &m) {
+        Context c; c.model = &m;
+        size_t max_len = m.input_len; std::map<TableType, int> tabs;
+        for (auto &n : m.nodes) {
+            if (n.op == Op::Dense) max_len = std::max(max_len, std::max(n.nrows * n.ncols, n.nrows));
+            if (n.op == Op::Requant) { tabs[TableType::range()] = 1; tabs[TableType::clamping(n.rq.clamping_size())] = 1; }
+            if (n.op == Op::Relu) tabs[TableType::relu()] = 1;
+        }
+        for (auto &kv : tabs) max_len = std::max(max_len, (size_t)1 << kv.first.multiplicity_poly_vars());   // context.rs:171-175
+        size_t p2 = 1; while (p2 < max_len) p2 <<= 1;
+        c.pp = Basefold::setup_and_trim(p2);
+        for (size_t id = 0; id < m.nodes.size(); id++) if (m.nodes[id].op == Op::Dense) {   // CommitmentContext::new (commit/context.rs:59-103)
+            for (auto &kv : std::map<std::string, const std::vector<Element> *>{{"DenseBias", &m.nodes[id].bias}, {"DenseWeight", &m.nodes[id].weights}}) {
+                DeviceMle poly = DeviceMle::from_evaluations_vec(to_base(*kv.second));
+                c.model_comms[id][kv.first] = {Basefold::commit(c.pp, poly), poly};
+            }
+        }
+        for (auto &kv : tabs) {   // get_merged_table_column (lookup/context.rs:158-296), resident for every proof
+            TableData td; std::vector<std::vector<u64>> cols;
+            const TableType &tt = kv.first;
+            if (tt.kind == 0) { cols.resize(2); for (Element i = QMIN - 1; i <= QMAX; i++) { Element o = relu(i); td.merged.push_back(i + o * COLUMN_SEPARATOR); cols[0].push_back(from_i64(i)); cols[1].push_back(from_i64(o)); } }
+            else if (tt.kind == 2) { cols.resize(1); for (Element i = 0; i < ((Element)1 << BIT_LEN); i++) { td.merged.push_back(i); cols[0].push_back(from_i64(i)); } }
+            else { cols.resize(2); Element mx = (Element)1 << (tt.size - 1); for (Element i = -mx; i < mx; i++) { Element o = i < QMIN ? QMIN : (i > QMAX ? QMAX : i); td.merged.push_back(i + o * COLUMN_SEPARATOR); cols[0].push_back(from_i64(i)); cols[1].push_back(from_i64(o)); } }
+            for (Element e : td.merged) td.table_count[e]++;
+            for (auto &col : cols) td.columns.push_back(DeviceMle::from_evaluations_vec(col));
+            c.tables[tt] = std::move(td);
+        }
+        return c;
+    }
+    template <class T> void write_to_transcript(T &t) const { for (auto &nk : model_comms) for (auto &pk : nk.second) Basefold::write_commitment(pk.second.comm.root, t); }   // commit/context.rs:181-190
+    const Model *model = nullptr; BasefoldProverParams pp;
+    std::map<size_t, std::map<std::string, ProverCommitment>> model_comms;
+    std::map<TableType, TableData> tables;
+};
+
+struct LogUpWitness { bool table = false; std::vector<ProverCommitment> commits; std::vector<DeviceMle> column_evals; DeviceMle multiplicity_evals; size_t columns_per_instance = 1; TableType tt{0, 0}; };
+
+// quantised inference (model run): outputs[i] = output tensor of node i
+inline std::vector<std::vector<Element>> run(const Model &m, const std::vector<Element> &input) {
+    std::vector<std::vector<Element>> outs; std::vector<Element> cur = input;
+    for (auto &n : m.nodes) {
+        std::vector<Element> o;
+        if (n.op == Op::Dense) { o.resize(n.nrows); for (size_t r = 0; r < n.nrows; r++) { Element a = n.bias[r]; const Element *w = &n.weights[r * n.ncols]; for (size_t c = 0; c < n.ncols; c++) a += w[c] * cur[c]; o[r] = a; } }
+        else if (n.op == Op::Requant) { Element lim = (Element)1 << n.rq.intermediate_bit_size; for (Element e : cur) { if (e > lim || e < -lim) throw Error(DP_ERR_INVALID, "Could not apply requantisation, tensor element had absolute value too large"); o.push_back(n.rq.apply(e)); } }
+        else for (Element e : cur) o.push_back(relu(e));
+        outs.push_back(o); cur = o;
+    }
+    return outs;
+}
+
+// Prover<'a, E, T, PCS> (iop/prover.rs:40-60)
+template <class T>
+class Prover {
+  public:
+    Prover(const Context &ctx, T &transcript) : ctx_(ctx), t_(transcript) {}
+
+    Proof prove(const std::vector<Element> &input) { return prove(input, run(*ctx_.model, input)); }
+    // Prover::prove(full_trace): the inference trace is an INPUT of proving (zkml/src/bin/bench.rs:390-408 times only this)
+    Proof prove(const std::vector<Element> &input, const std::vector<std::vector<Element>> &outs) {
+        const Model &m = *ctx_.model;
+        auto node_input = [&](size_t id) -> const std::vector<Element> & { return id == 0 ? input : outs[id - 1]; };
+        ctx_.write_to_transcript(t_);
+        instantiate_witness_ctx(m, input, outs);
+        // output claim (prover.rs:423-436)
+        const std::vector<Element> &fo = outs.back();
+        Claim last; for (size_t i = 0, nv = ceil_log2(fo.size()); i < nv; i++) last.point.push_back(t_.read_challenge());
+        last.eval = DeviceMle::from_evaluations_vec(to_base(fo)).evaluate(last.point);
+        for (size_t id = m.nodes.size(); id-- > 0;) {
+            const Node &n = m.nodes[id];
+            if (n.op == Op::Dense) last = prove_dense(id, n, last, node_input(id));
+            else if (n.op == Op::Requant) last = prove_requant(id, n, last);
+            else last = prove_activation(id, last, outs[id]);
+        }
+        prove_tables();
+        commit_prove();
+        return std::move(proof_);
+    }
+
+  private:
+    void add_witness_claim(const ProverCommitment &pc, const Claim &c) { (pc.poly.num_vars() <= Basefold::trivial_num_vars() ? trivial_claims_ : claims_).push_back({pc, c}); }   // commit/context.rs:290-310
+    ProverCommitment commit_column(const std::vector<u64> &ev) { DeviceMle p = DeviceMle::from_evaluations_vec(ev); return {Basefold::commit(ctx_.pp, p), p}; }
+
+    // generate_lookup_witnesses (lookup/context.rs:631-756) + initialise_from_table_set (:758-781)
+    void instantiate_witness_ctx(const Model &m, const std::vector<Element> &input, const std::vector<std::vector<Element>> &outs) {
+        auto node_input = [&](size_t id) -> const std::vector<Element> & { return id == 0 ? input : outs[id - 1]; };
+        std::map<TableType, std::unordered_map<Element, u64>> element_count;
+        for (size_t id = 0; id < m.nodes.size(); id++) {
+            const Node &n = m.nodes[id];
+            if (n.op == Op::Requant) {   // requant.rs:208-330
+                size_t shift = n.rq.shift(); Element rc = (Element)1 << (shift - 1), mask = ((Element)1 << shift) - 1;
+                std::vector<Element> cin, cout, shifted;
+                for (Element v : node_input(id)) { Element tmp = v * n.rq.fixed_point_multiplier + rc, cl = tmp >> shift; cin.push_back(cl); cout.push_back(cl < QMIN ? QMIN : (cl > QMAX ? QMAX : cl)); shifted.push_back(tmp & mask); }
+                size_t no_chunks = shift / BIT_LEN; Element rmask = ((Element)1 << BIT_LEN) - 1;
+                std::vector<std::vector<Element>> chunks(no_chunks);
+                for (size_t j = 0; j < no_chunks; j++) for (Element e : shifted) chunks[j].push_back((e >> (j * BIT_LEN)) & rmask);
+                TableType tc = TableType::clamping(n.rq.clamping_size()), tr = TableType::range();
+                for (auto &ch : chunks) for (Element e : ch) element_count[tr][e]++;
+                for (size_t i = 0; i < cin.size(); i++) element_count[tc][cin[i] + cout[i] * COLUMN_SEPARATOR]++;
+                LogUpWitness wc; wc.tt = tc; wc.columns_per_instance = 2;
+                for (auto *v : {&cin, &cout}) { wc.commits.push_back(commit_column(to_base(*v))); wc.column_evals.push_back(wc.commits.back().poly); }
+                LogUpWitness ws; ws.tt = tr; ws.columns_per_instance = 1;
+                for (auto &ch : chunks) { ws.commits.push_back(commit_column(to_base(ch))); ws.column_evals.push_back(ws.commits.back().poly); }
+                lookup_witness_[id] = {wc, ws};
+            } else if (n.op == Op::Relu) {   // activation.rs:238-323
+                TableType tt = TableType::relu(); LogUpWitness w; w.tt = tt; w.columns_per_instance = 2;
+                const auto &a = node_input(id); const auto &b = outs[id];
+                for (size_t i = 0; i < a.size(); i++) element_count[tt][a[i] + COLUMN_SEPARATOR * b[i]]++;
+                for (auto *v : {&a, &b}) { w.commits.push_back(commit_column(to_base(*v))); w.column_evals.push_back(w.commits.back().poly); }
+                lookup_witness_[id] = {w};
+            }
+        }
+        for (auto &kv : element_count) {   // table multiplicities (lookup/context.rs:675-737)
+            const TableData &td = ctx_.tables.at(kv.first);
+            std::vector<u64> mult(td.merged.size());
+            for (size_t i = 0; i < td.merged.size(); i++) {
+                auto it = kv.second.find(td.merged[i]);
+                if (it == kv.second.end()) mult[i] = 0;
+                else { u64 tc = td.table_count.at(td.merged[i]); mult[i] = fmul(canon(it->second), tc != 1 ? finv(canon(tc)) : 1); }
+            }
+            LogUpWitness w; w.table = true; w.tt = kv.first; w.commits.push_back(commit_column(mult)); w.multiplicity_evals = w.commits[0].poly; w.column_evals = td.columns;
+            table_witness_.push_back(w);
+        }
+        constant_challenge_ = t_.get_and_append_challenge("table_constant");
+        for (auto &kv : element_count) challenge_map_[kv.first] = kv.first.kind == 0 ? t_.get_and_append_challenge("Relu") : (kv.first.kind == 3 ? t_.get_and_append_challenge("Clamping") : Ext::one());
+    }
+    LogUpInput get_logup_input(const LogUpWitness &w) const {   // lookup/witness.rs:96-140
+        LogUpInput in; in.table = w.table; in.column_evals = w.column_evals; in.multiplicities = w.multiplicity_evals;
+        in.constant_challenge = constant_challenge_; in.column_separation_challenge = challenge_map_.at(w.tt); in.columns_per_instance = w.columns_per_instance;
+        return in;
+    }
+
+    // Dense::prove_step (layers/dense.rs:423-551)
+    Claim prove_dense(size_t id, const Node &n, const Claim &last_claim, const std::vector<Element> &input) {
+        const auto &comms = ctx_.model_comms.at(id);
+        const DeviceMle &weights = comms.at("DenseWeight").poly, &bias = comms.at("DenseBias").poly;
+        if (ceil_log2(n.nrows) != last_claim.point.size()) throw Error(DP_ERR_INVALID, "something's wrong with the randomness");
+        Ext bias_eval = bias.evaluate(last_claim.point);
+        DeviceMle mat = weights.fix_high_variables(last_claim.point);      // rows are the HIGH variables (dense.rs:471-475)
+        DeviceMle in = DeviceMle::from_evaluations_vec(to_base(input));
+        VirtualPolynomial vp(in.num_vars());
+        vp.add_mle_list({mat, in}, Ext::one());
+        auto res = IOPProverState::prove_parallel(std::move(vp), t_);
+        const ExtVec &fe = res.second.get_mle_final_evaluations();
+        ExtVec wp = res.first.point; wp.insert(wp.end(), last_claim.point.begin(), last_claim.point.end());
+        add_witness_claim(comms.at("DenseBias"), {last_claim.point, bias_eval});   // BTreeMap order of PolyId
+        add_witness_claim(comms.at("DenseWeight"), {wp, fe[0]});
+        proof_.dense[id] = {res.first, bias_eval, fe};
+        return {res.first.point, fe[1]};
+    }
+
+    // Requant::prove_step (layers/requant.rs:531-680)
+    Claim prove_requant(size_t id, const Node &n, const Claim &last_claim) {
+        std::vector<LogUpWitness> ws = lookup_witness_.at(id);
+        if (ws.size() != 2) throw Error(DP_ERR_INVALID, "There should be two lookup witnesses during requantisation");
+        LogUpInput cin = get_logup_input(ws[0]), sin = get_logup_input(ws[1]);
+        LogUpProof cp = logup_batch_prove(cin, t_), sp = logup_batch_prove(sin, t_);
+        size_t nv = cin.column_evals[0].num_vars();
+        DeviceMle cbeta = DeviceMle::build_eq_x_r(cp.output_claims[0].point), lbeta = DeviceMle::build_eq_x_r(last_claim.point), sbeta = DeviceMle::build_eq_x_r(sp.output_claims[0].point);
+        Ext bc = t_.get_and_append_challenge("requant_batching");
+        VirtualPolynomial vp(nv);
+        vp.add_mle_list({cin.column_evals[1], lbeta}, Ext::one());
+        vp.add_mle_list({cin.column_evals[1], cbeta}, bc);
+        Ext comb = bc * bc; vp.add_mle_list({cin.column_evals[0], cbeta}, comb);
+        comb *= bc;
+        for (auto &col : sin.column_evals) { vp.add_mle_list({sbeta, col}, comb); comb *= bc; }
+        auto res = IOPProverState::prove_parallel(std::move(vp), t_);
+        const ExtVec &fe = res.second.get_mle_final_evaluations(); ExtVec point = res.first.point;
+        Ext cout_eval = fe[0], cin_eval = fe[3]; ExtVec sh(fe.begin() + 5, fe.end());
+        Ext combined = n.rq.recombine_claims(cin_eval, sh);
+        RequantProof rp; rp.io_accumulation = res.first; rp.clamping_lookup = cp; rp.shifted_lookup = sp;
+        ExtVec evs = {cin_eval, cout_eval}; evs.insert(evs.end(), sh.begin(), sh.end());
+        std::vector<ProverCommitment> cw = ws[0].commits; cw.insert(cw.end(), ws[1].commits.begin(), ws[1].commits.end());
+        for (size_t i = 0; i < evs.size(); i++) { add_witness_claim(cw[i], {point, evs[i]}); rp.accumulation_evals.push_back(evs[i]); rp.commitments.push_back(cw[i].comm.root); }
+        proof_.requant[id] = rp;
+        return {point, combined};
+    }
+
+    // Activation::prove_step (layers/activation.rs:385-460)
+    Claim prove_activation(size_t id, const Claim &last_claim, const std::vector<Element> &output) {
+        std::vector<LogUpWitness> ws = lookup_witness_.at(id);
+        if (ws.size() != 1) throw Error(DP_ERR_INVALID, "Activation only requires a lookup into one table type");
+        LogUpProof lp = logup_batch_prove(get_logup_input(ws[0]), t_);
+        // the output tensor as an MLE; col_two of the lookup holds the same values (activation.rs:281-283), reuse it
+        SamePolyProof acc = same_poly_prove(ws[0].column_evals[1], {last_claim, lp.output_claims[1]}, t_);
+        (void)output;
+        Claim input_claim = lp.output_claims[0];
+        ActivationProof ap; ap.io_accumulation = acc; ap.lookup = lp;
+        std::vector<Claim> cc = {input_claim, acc.extract_claim()};
+        for (size_t i = 0; i < 2; i++) { add_witness_claim(ws[0].commits[i], cc[i]); ap.commits.push_back(ws[0].commits[i].comm.root); }
+        proof_.activation[id] = ap;
+        return input_claim;
+    }
+
+    // prove_tables (iop/prover.rs:110-157)
+    void prove_tables() {
+        for (auto &w : table_witness_) {
+            LogUpProof tp = logup_batch_prove(get_logup_input(w), t_);
+            add_witness_claim(w.commits[0], tp.output_claims.front());
+            proof_.table_proofs.push_back({w.commits[0].comm.root, tp});   // Relu/Range/Clamping have no committed table columns (lookup/context.rs:495-546)
+        }
+    }
+
+    // CommitmentProver::prove (commit/context.rs:355-418)
+    void commit_prove() {
+        for (auto &c : trivial_claims_) proof_.trivial_proofs.push_back(Basefold::open(ctx_.pp, c.first.poly, c.first.comm, c.second.point, t_));
+        std::vector<DeviceMle> polys; std::vector<BasefoldCommitmentWithWitness> comms; std::vector<ExtVec> points; std::vector<Evaluation> evals;
+        for (size_t i = 0; i < claims_.size(); i++) { polys.push_back(claims_[i].first.poly); comms.push_back(claims_[i].first.comm); points.push_back(claims_[i].second.point); Evaluation e; e.poly = i; e.point = i; e.value = claims_[i].second.eval; evals.push_back(e); }
+        proof_.batch_proof = Basefold::batch_open(ctx_.pp, polys, comms, points, evals, t_);
+    }
+
+    const Context &ctx_; T &t_; Proof proof_;
+    std::map<size_t, std::vector<LogUpWitness>> lookup_witness_; std::vector<LogUpWitness> table_witness_;
+    Ext constant_challenge_; std::map<TableType, Ext> challenge_map_;
+    std::vector<std::pair<ProverCommitment, Claim>> claims_, trivial_claims_;
+};
+
+// flat u64 image for the parity tests (layout documented in tests/test_gpu_zkml.py)
+inline void flat_e(std::vector<u64> &o, const Ext &e) { o.push_back(e.c0); o.push_back(e.c1); }
+inline void flat_iop(std::vector<u64> &o, const IOPProof &p) { o.push_back(p.point.size()); for (auto &e : p.point) flat_e(o, e); o.push_back(p.proofs.size()); for (auto &m : p.proofs) { o.push_back(m.evaluations.size()); for (auto &e : m.evaluations) flat_e(o, e); } }
+inline void flat_logup(std::vector<u64> &o, const LogUpProof &p) {
+    o.push_back(p.sumcheck_proofs.size()); for (auto &s : p.sumcheck_proofs) flat_iop(o, s);
+    o.push_back(p.round_evaluations.size()); for (auto &r : p.round_evaluations) { o.push_back(r.size()); for (auto &e : r) flat_e(o, e); }
+    o.push_back(p.output_claims.size()); for (auto &c : p.output_claims) { o.push_back(c.point.size()); for (auto &e : c.point) flat_e(o, e); flat_e(o, c.eval); }
+    o.push_back(p.circuit_outputs.size()); for (auto &r : p.circuit_outputs) { o.push_back(r.size()); for (auto &e : r) flat_e(o, e); }
+    o.push_back(p.table ? 1 : 0);
+}
+inline std::vector<u64> Proof::flatten(size_t n_nodes) const {
+    std::vector<u64> o;
+    auto fd = [&](const Digest &d) { for (int i = 0; i < 4; i++) o.push_back(d.v[i]); };
+    for (size_t id = 0; id < n_nodes; id++) {
+        if (dense.count(id)) { const auto &d = dense.at(id); o.push_back(100 + id); flat_iop(o, d.sumcheck); flat_e(o, d.bias_eval); o.push_back(d.individual_claims.size()); for (auto &e : d.individual_claims) flat_e(o, e); }
+        if (requant.count(id)) { const auto &r = requant.at(id); o.push_back(200 + id); flat_iop(o, r.io_accumulation); o.push_back(r.accumulation_evals.size()); for (auto &e : r.accumulation_evals) flat_e(o, e); flat_logup(o, r.clamping_lookup); flat_logup(o, r.shifted_lookup); o.push_back(r.commitments.size()); for (auto &d : r.commitments) fd(d); }
+        if (activation.count(id)) { const auto &a = activation.at(id); o.push_back(300 + id); flat_iop(o, a.io_accumulation.sumcheck); o.push_back(a.io_accumulation.evals.size()); for (auto &e : a.io_accumulation.evals) flat_e(o, e); flat_logup(o, a.lookup); o.push_back(a.commits.size()); for (auto &d : a.commits) fd(d); }
+    }
+    o.push_back(table_proofs.size()); for (auto &t : table_proofs) { fd(t.multiplicity_commit); flat_logup(o, t.lookup); }
+    o.push_back(trivial_proofs.size());
+    std::vector<u64> b = batch_proof.flatten(); o.push_back(b.size()); o.insert(o.end(), b.begin(), b.end());
+    return o;
+}
+
+}  // namespace zkml
+}  // namespace dp

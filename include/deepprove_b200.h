@@ -66,6 +66,8 @@ int dp_mle_free(dp_mle *m);
 /* fix_high_variables_in_place (mle.rs:562-603): fixes the TOP k variables at `point` (k x [c0,c1]),
  * i.e. for r in point.rev(): lo[i] += (hi[i]-lo[i])*r.  The MLE becomes Ext with num_vars - k. */
 int dp_mle_fix_high(dp_mle *m, const uint64_t *point, uint32_t k);
+/* fix_high_variables (mle.rs:529-560): non-mutating variant, returns a new Ext MLE. */
+int dp_mle_fix_high_new(const dp_mle *m, const uint64_t *point, uint32_t k, dp_mle **out);
 /* fix_variables (mle.rs:454-484): fixes the LOW k variables (adjacent pairs), returns a new MLE. */
 int dp_mle_fix_low(const dp_mle *m, const uint64_t *point, uint32_t k, dp_mle **out);
 /* evaluate (mle.rs:607-623): point has num_vars elements; out = [c0,c1]. */
@@ -99,6 +101,21 @@ int dp_sc_destroy(dp_sc *s);
 int dp_sc_current_mle(dp_sc *s, uint32_t idx, dp_mle **out_view);
 /* Algorithmic HBM bytes moved by the last dp_sc_round (SURVEY.md 8(d) rules), for roofline reports. */
 uint64_t dp_sc_last_round_bytes(const dp_sc *s);
+
+/* ---- zkml lookup: LogUp-GKR fractional-sum circuit (zkml/src/lookup/logup_gkr/circuit.rs) --------------- */
+typedef struct dp_logup dp_logup;
+/* LogUpCircuit::new_lookup_circuit (multiplicities == NULL; numerators are -1) or new_table_circuit.
+ * columns: Base MLEs of equal power-of-two length; denominators are c + sum_k gamma^k col_k[i]. */
+int dp_logup_build(dp_mle *const *columns, uint32_t n_columns, const dp_mle *multiplicities, const uint64_t constant_challenge[2],
+                   const uint64_t column_separation_challenge[2], dp_logup **out);
+int dp_logup_num_vars(const dp_logup *l, uint32_t *input_layer_num_vars);   /* LogUpCircuit::num_vars */
+int dp_logup_outputs(const dp_logup *l, uint64_t out[8]);                    /* [n0, n1, d0, d1] x [c0,c1] */
+/* LogUpLayer::get_mles of the layer whose halves have `layer_vars` variables: non-owning views
+ * [num_low, num_high, den_low, den_high] (or [den_low, den_high] for the initial lookup layer). */
+int dp_logup_layer_mles(const dp_logup *l, uint32_t layer_vars, dp_mle **out_views, uint32_t *n_views);
+int dp_logup_free(dp_logup *l);
+/* out = sum_k coefs[k] * mles[k] over Ext MLEs of equal length (same_poly.rs:91-110 final_beta). */
+int dp_mle_linear_combination(dp_mle *const *mles, const uint64_t *coefs, uint32_t n, dp_mle **out);
 
 /* ---- mpcs: Basefold over RS code (rate 1/2, 200 queries, basecode 2^7) + Poseidon2 Merkle trees ------ */
 typedef struct dp_pcs_comm dp_pcs_comm;  /* BasefoldCommitmentWithWitness (mpcs/src/basefold/structure.rs:63-72) */

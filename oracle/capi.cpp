@@ -210,3 +210,38 @@ int dpo_pcs_batch_open(u32 n, const u64 *const *data, const u64 *lens, const int
 }
 
 }  // extern "C"
+
+// ---- zkml MLP prover (oracle/zkml.hpp) ----
+#include "zkml.hpp"
+#include <chrono>
+extern "C" {
+// Synthetic MLP (SURVEY.md 8d Cfg 2): context generation (weight commits) + Prover::prove.  Returns the flat proof.
+// out_ms[0] = context (setup) time, out_ms[1] = prove time.
+int dpo_zkml_prove(u32 n_layers, u32 width, u64 seed_model, u64 seed_input, const char *label, u64 *out, u64 cap, u64 *out_len, double *out_ms) {
+    try {
+        Model m = synthetic_mlp(n_layers, width, seed_model);
+        std::vector<Element> input = synthetic_input(width, seed_input);
+        auto t0 = std::chrono::steady_clock::now();
+        ZkContext ctx = zk_context(m);
+        auto t1 = std::chrono::steady_clock::now();
+        Transcript t(label);
+        ModelProof p = zk_prove(ctx, input, t);
+        auto t2 = std::chrono::steady_clock::now();
+        if (out_ms) { out_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count(); out_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count(); }
+        std::vector<u64> f = flatten_model_proof(p, m.nodes.size());
+        *out_len = f.size();
+        if (out) { if (f.size() > cap) { g_err = "dpo_zkml_prove: output buffer too small"; return 2; } memcpy(out, f.data(), 8 * f.size()); }
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// model / input generators exposed so the product's host side gets the SAME synthetic tensors without touching oracle code paths
+void dpo_synthetic_mlp(u32 n_layers, u32 width, u64 seed, int64_t *weights /* n_layers*width*width */, int64_t *bias /* n_layers*width */, int64_t *rq /* n_layers*4 */) {
+    Model m = synthetic_mlp(n_layers, width, seed);
+    size_t l = 0;
+    for (auto &n : m.nodes) {
+        if (n.kind == OP_DENSE) { memcpy(weights + l * width * width, n.weights.data(), 8 * n.weights.size()); memcpy(bias + l * width, n.bias.data(), 8 * n.bias.size()); }
+        if (n.kind == OP_REQUANT) { rq[4 * l] = n.rq.right_shift; rq[4 * l + 1] = n.rq.fp_scale; rq[4 * l + 2] = n.rq.fixed_point_multiplier; rq[4 * l + 3] = n.rq.intermediate_bit_size; l++; }
+    }
+}
+void dpo_synthetic_input(u32 width, u64 seed, int64_t *out) { auto v = synthetic_input(width, seed); memcpy(out, v.data(), 8 * v.size()); }
+}

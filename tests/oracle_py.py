@@ -313,3 +313,29 @@ def pcs_batch_open(polys, full_log, points, label=b"m2vec", cap=1 << 25):
     if rc:
         raise RuntimeError(lib().dpo_last_error().decode())
     return out[: ln.value].copy()
+
+
+# ---- zkml synthetic MLP ----
+def synthetic_mlp(n_layers, width, seed):
+    w = np.zeros(n_layers * width * width, dtype=np.int64)
+    b = np.zeros(n_layers * width, dtype=np.int64)
+    rq = np.zeros(n_layers * 4, dtype=np.int64)
+    lib().dpo_synthetic_mlp(C.c_uint32(n_layers), C.c_uint32(width), C.c_uint64(seed), ptr(w), ptr(b), ptr(rq))
+    return w, b, rq.reshape(n_layers, 4)
+
+
+def synthetic_input(width, seed):
+    x = np.zeros(width, dtype=np.int64)
+    lib().dpo_synthetic_input(C.c_uint32(width), C.c_uint64(seed), ptr(x))
+    return x
+
+
+def zkml_prove(n_layers, width, seed_model, seed_input, label=b"m2vec", cap=1 << 22, want_proof=True):
+    out = np.zeros(cap if want_proof else 1, dtype=np.uint64)
+    n = C.c_uint64()
+    ms = (C.c_double * 2)()
+    rc = lib().dpo_zkml_prove(C.c_uint32(n_layers), C.c_uint32(width), C.c_uint64(seed_model), C.c_uint64(seed_input), label,
+                              ptr(out) if want_proof else None, C.c_uint64(cap), C.byref(n), ms)
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return (out[: n.value].copy() if want_proof else None), (ms[0], ms[1])
