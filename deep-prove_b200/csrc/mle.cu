@@ -163,6 +163,7 @@ int dpk_fix_high(const void *src, bool src_ext, u64 len, const gle *point, u32 k
     gle *w = nullptr;
     if (int e = dp_dev_alloc((void **)&w, sizeof(gle) * J)) return e;
     if (int e = dpk_eq_build(point, k, w)) return e;
+    DpProfScope prof(S < 32 ? "k_fixhigh_dot" : "k_fixhigh_cols", len * (src_ext ? 16 : 8) + S * 16);
     if (S < 32) {
         if (src_ext) k_fixhigh_dot<true><<<(unsigned)S, 256, 0, c.stream>>>(src, w, S, J, out);
         else k_fixhigh_dot<false><<<(unsigned)S, 256, 0, c.stream>>>(src, w, S, J, out);
@@ -285,10 +286,7 @@ int dp_mle_fix_high_new(const dp_mle *m, const uint64_t *point, uint32_t k, dp_m
     gle pt[32]; point_from_host(point, k, pt);
     dp_mle *r = new dp_mle(); r->len = m->len >> k; r->is_ext = true; r->owned = true;
     if (int e = dp_dev_alloc(&r->data, r->bytes())) { delete r; return e; }
-    {
-        DpProfScope prof("fix_high(one pass)", m->bytes() + r->bytes());
-        if (int e = dpk_fix_high(m->data, m->is_ext, m->len, pt, k, (gle *)r->data)) return e;
-    }
+    if (int e = dpk_fix_high(m->data, m->is_ext, m->len, pt, k, (gle *)r->data)) return e;
     *outp = r;
     return DP_OK;
 }

@@ -55,8 +55,9 @@ static inline std::vector<T> rs_encode_t(const std::vector<T> &coeffs, size_t fu
         size_t len = (size_t)1 << lg, half = len >> 1;
         u64 wlen = two_adic_generator(lg);
         std::vector<u64> tw(half); tw[0] = 1; for (size_t j = 1; j < half; j++) tw[j] = f_mul(tw[j - 1], wlen);
-        for (size_t k = 0; k < N; k += len)
-            for (size_t j = 0; j < half; j++) { T t = mulb(a[k + half + j], tw[j]); T u = a[k + j]; a[k + j] = add(u, t); a[k + half + j] = sub(u, t); }
+        par_for(N / 2, 8192, [&](size_t qb, size_t qe) {
+            for (size_t q = qb; q < qe; q++) { size_t k = (q / half) * len, j = q % half; T t = mulb(a[k + half + j], tw[j]); T u = a[k + j]; a[k + j] = add(u, t); a[k + half + j] = sub(u, t); }
+        });
     }
     return a;
 }
@@ -84,15 +85,15 @@ static inline std::vector<std::vector<Digest>> merkelize(const FVec &v) {
     size_t n = v.len(), lg = ceil_log2(n);
     std::vector<std::vector<Digest>> tree;
     std::vector<Digest> h(n >> 1);
-    for (size_t i = 0; i < (n >> 1); i++) {
+    par_for(n >> 1, 8192, [&](size_t ib, size_t ie) { for (size_t i = ib; i < ie; i++) {
         if (v.is_ext) { u64 in[4] = {v.e[2 * i].c0, v.e[2 * i].c1, v.e[2 * i + 1].c0, v.e[2 * i + 1].c1}; h[i] = hash_or_noop(in, 4); }
         else { u64 in[2] = {v.b[2 * i], v.b[2 * i + 1]}; h[i] = hash_or_noop(in, 2); }
-    }
+    } });
     tree.push_back(h);
     for (size_t l = 1; l < lg; l++) {
         const auto &prev = tree[l - 1];
         std::vector<Digest> nx(prev.size() >> 1);
-        for (size_t i = 0; i < nx.size(); i++) nx[i] = compress(prev[2 * i], prev[2 * i + 1]);
+        par_for(nx.size(), 64, [&](size_t ib, size_t ie) { for (size_t i = ib; i < ie; i++) nx[i] = compress(prev[2 * i], prev[2 * i + 1]); });
         tree.push_back(nx);
     }
     return tree;
@@ -140,12 +141,12 @@ static inline std::vector<E> fri_fold(const std::vector<E> &v, size_t full_log, 
     // x0 for consecutive indices: precompute the root powers once (any method gives the same elements)
     u64 g = two_adic_generator(level + 1), shift = f_exp_pow2(GL_GENERATOR, full_log + RS_RATE_LOG - level - 1);
     std::vector<u64> pw((size_t)1 << level); pw[0] = 1; for (size_t i = 1; i < pw.size(); i++) pw[i] = f_mul(pw[i - 1], g);
-    for (size_t i = 0; i < out.size(); i++) {
+    par_for(out.size(), 256, [&](size_t ib, size_t ie) { for (size_t i = ib; i < ie; i++) {
         u64 x0 = f_mul(pw[reverse_bits(i, level)], shift);
         u64 w = f_inv(f_sub(f_neg(x0), x0));
         E a1 = v[2 * i], b1 = v[2 * i + 1];
         out[i] = e_add(a1, e_mul(e_mul(e_sub(r, E::from_base(x0)), e_sub(b1, a1)), E::from_base(w)));
-    }
+    } });
     return out;
 }
 

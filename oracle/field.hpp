@@ -7,9 +7,13 @@
 // Values are kept CANONICAL (< p) at all times; E is AoS [c0, c1] like the reference's Vec<E>.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cstddef>
 #include <vector>
 #include <cassert>
+#include <thread>
+#include <functional>
+#include <algorithm>
 
 namespace dpo {
 
@@ -19,7 +23,13 @@ typedef uint32_t u32;
 
 static const u64 GL_P = 0xFFFFFFFF00000001ULL;
 
-static inline u64 f_reduce128(u128 x) { return (u64)(x % GL_P); }
+// 2^64 = 2^32 - 1 and 2^96 = -1 (mod p): branch-light reduction of a 128-bit product (same value as x % p)
+static inline u64 f_reduce128(u128 x) {
+    u64 lo = (u64)x, hi = (u64)(x >> 64), hh = hi >> 32, hl = hi & 0xFFFFFFFFULL;
+    u64 t0 = lo - hh; if (lo < hh) t0 -= 0xFFFFFFFFULL;
+    u64 t1 = hl * 0xFFFFFFFFULL, r = t0 + t1; if (r < t1) r += 0xFFFFFFFFULL;
+    return r >= GL_P ? r - GL_P : r;
+}
 static inline u64 f_from_u64(u64 x) { return x >= GL_P ? x - GL_P : x; }
 static inline u64 f_add(u64 a, u64 b) { u128 s = (u128)a + b; return (u64)(s >= GL_P ? s - GL_P : s); }
 static inline u64 f_sub(u64 a, u64 b) { return a >= b ? a - b : a + (GL_P - b); }
@@ -67,6 +77,21 @@ static inline E e_pow(E a, u64 e) {
     E r = E::one();
     while (e) { if (e & 1) r = e_mul(r, a); a = e_mul(a, a); e >>= 1; }
     return r;
+}
+
+// par_for: plain std::thread fork-join over [0, n) (no OpenMP in this image).  Threads = DPO_THREADS env or all cores.
+static inline unsigned dpo_threads() {
+    static unsigned n = [] { const char *e = getenv("DPO_THREADS"); unsigned v = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency(); return v ? v : 1u; }();
+    return n;
+}
+template <class F> static inline void par_for(size_t n, size_t min_per_thread, F f) {
+    unsigned T = dpo_threads();
+    if (T <= 1 || n < 2 * min_per_thread) { f((size_t)0, n); return; }
+    size_t chunks = std::min<size_t>(T, n / min_per_thread); if (chunks < 2) { f((size_t)0, n); return; }
+    std::vector<std::thread> th; size_t per = (n + chunks - 1) / chunks;
+    for (size_t c = 1; c < chunks; c++) { size_t b = c * per, e = std::min(n, b + per); if (b < e) th.emplace_back([=] { f(b, e); }); }
+    f((size_t)0, std::min(n, per));
+    for (auto &t : th) t.join();
 }
 
 // splitmix64 -- the synthetic-input generator named in SURVEY.md 8(d) (seeds 1,2,3,...).

@@ -27,9 +27,9 @@ static inline void mle_fix_low_one(MLE &m, E r) {
     size_t half = m.len() >> 1;
     std::vector<E> out(half);
     if (m.is_ext) {
-        for (size_t i = 0; i < half; i++) out[i] = e_add(m.ext[2 * i], e_mul(e_sub(m.ext[2 * i + 1], m.ext[2 * i]), r));
+        par_for(half, 4096, [&](size_t b, size_t e) { for (size_t i = b; i < e; i++) out[i] = e_add(m.ext[2 * i], e_mul(e_sub(m.ext[2 * i + 1], m.ext[2 * i]), r)); });
     } else {
-        for (size_t i = 0; i < half; i++) out[i] = e_add(e_mul_base(r, f_sub(m.base[2 * i + 1], m.base[2 * i])), E::from_base(m.base[2 * i]));
+        par_for(half, 4096, [&](size_t b, size_t e) { for (size_t i = b; i < e; i++) out[i] = e_add(e_mul_base(r, f_sub(m.base[2 * i + 1], m.base[2 * i])), E::from_base(m.base[2 * i])); });
         m.base.clear(); m.base.shrink_to_fit();
     }
     m.ext.swap(out); m.is_ext = true; m.num_vars -= 1;
@@ -48,9 +48,9 @@ static inline void mle_fix_high_one(MLE &m, E r) {
     size_t half = m.len() >> 1;
     std::vector<E> out(half);
     if (m.is_ext) {
-        for (size_t i = 0; i < half; i++) out[i] = e_add(m.ext[i], e_mul(e_sub(m.ext[i + half], m.ext[i]), r));
+        par_for(half, 4096, [&](size_t b, size_t e) { for (size_t i = b; i < e; i++) out[i] = e_add(m.ext[i], e_mul(e_sub(m.ext[i + half], m.ext[i]), r)); });
     } else {
-        for (size_t i = 0; i < half; i++) out[i] = e_add(e_mul_base(r, f_sub(m.base[i + half], m.base[i])), E::from_base(m.base[i]));
+        par_for(half, 4096, [&](size_t b, size_t e) { for (size_t i = b; i < e; i++) out[i] = e_add(e_mul_base(r, f_sub(m.base[i + half], m.base[i])), E::from_base(m.base[i])); });
         m.base.clear(); m.base.shrink_to_fit();
     }
     m.ext.swap(out); m.is_ext = true; m.num_vars -= 1;

@@ -4,6 +4,7 @@
 #include "mle.hpp"
 #include "poseidon.hpp"
 #include <functional>
+#include <atomic>
 
 namespace dpo {
 
@@ -65,16 +66,25 @@ static inline std::vector<E> sumcheck_product_round(const std::vector<const MLE 
         for (auto m : ops) p = e_mul(p, m->get(0));
         for (size_t t = 0; t <= d; t++) acc[t] = p;
     } else {
-        for (size_t b = 0; b + 1 < len; b += 2) {
-            std::vector<E> cur(d), step(d);
-            for (size_t j = 0; j < d; j++) { cur[j] = ops[j]->get(b); step[j] = e_sub(ops[j]->get(b + 1), ops[j]->get(b)); }
-            for (size_t t = 0; t <= d; t++) {
-                E p = E::one();
-                for (size_t j = 0; j < d; j++) p = e_mul(p, cur[j]);
-                acc[t] = e_add(acc[t], p);
-                for (size_t j = 0; j < d; j++) cur[j] = e_add(cur[j], step[j]);
+        size_t npairs = len >> 1;
+        unsigned T = dpo_threads();
+        std::vector<std::vector<E>> part(T, std::vector<E>(d + 1, E::zero()));
+        std::atomic<unsigned> slot{0};
+        par_for(npairs, 2048, [&](size_t pb, size_t pe) {
+            unsigned me = slot.fetch_add(1); std::vector<E> &a = part[me];
+            E cur[5], step[5];
+            for (size_t pi = pb; pi < pe; pi++) {
+                size_t b = 2 * pi;
+                for (size_t j = 0; j < d; j++) { cur[j] = ops[j]->get(b); step[j] = e_sub(ops[j]->get(b + 1), cur[j]); }
+                for (size_t t = 0; t <= d; t++) {
+                    E p = cur[0];
+                    for (size_t j = 1; j < d; j++) p = e_mul(p, cur[j]);
+                    a[t] = e_add(a[t], p);
+                    for (size_t j = 0; j < d; j++) cur[j] = e_add(cur[j], step[j]);
+                }
             }
-        }
+        });
+        for (auto &a : part) for (size_t t = 0; t <= d; t++) acc[t] = e_add(acc[t], a[t]);
     }
     size_t l2 = ceil_log2(len); if (l2 < 1) l2 = 1;
     size_t mult = max_nv - (l2 + round - 1);
