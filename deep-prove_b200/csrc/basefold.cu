@@ -166,6 +166,27 @@ __global__ void k_merkle_up(const u64 *__restrict__ in, u64 n_out, u64 *__restri
         *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(o[2], o[3]);
     }
 }
+// every remaining level of a small (sub)tree in ONE launch: a single block walks the levels with
+// __syncthreads() in between, so a 2^11-leaf witness commitment costs one launch instead of ten
+struct LvlOff { u64 off[36]; };
+template <bool EXT>
+__global__ void __launch_bounds__(256) k_merkle_tail(const void *leaves, u64 n, u32 lg, u32 from_level, u64 *levels, LvlOff lo) {
+    for (u32 l = from_level; l < lg; l++) {
+        u64 nl = n >> (l + 1);
+        u64 *out = levels + 4 * lo.off[l];
+        for (u64 i = threadIdx.x; i < nl; i += blockDim.x) {
+            u64 x[4], y[4], o[4];
+            if (l == 1) { leaf_pair_digest<EXT>(leaves, 2 * i, x); leaf_pair_digest<EXT>(leaves, 2 * i + 1, y); }
+            else {
+                const u64 *in = levels + 4 * lo.off[l - 1] + 8 * i;   // written earlier in this launch: plain loads
+                for (int k = 0; k < 4; k++) { x[k] = in[k]; y[k] = in[4 + k]; }
+            }
+            p2_compress(x, y, o);
+            for (int k = 0; k < 4; k++) out[4 * i + k] = o[k];
+        }
+        __syncthreads();
+    }
+}
 template <bool EXT> __global__ void k_leafpair_root(const void *leaves, u64 *out) { u64 d[4]; leaf_pair_digest<EXT>(leaves, 0, d); for (int i = 0; i < 4; i++) out[i] = d[i]; }
 
 // A Merkle tree over `n` leaves living in HBM: levels >= 1 packed back to back.
@@ -188,17 +209,24 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
         if (ext) k_leafpair_root<true><<<1, 1, 0, c.stream>>>(leaves, t.levels); else k_leafpair_root<false><<<1, 1, 0, c.stream>>>(leaves, t.levels);
         DP_LAUNCHED(); t.root_dev = t.levels;
     } else {
-        u64 n1 = n >> 2;
-        {
-            DpProfScope prof("k_merkle(poseidon2 compress)", n1 * (ext ? 64 : 32) + n1 * 32);
-            if (ext) k_merkle_l1<true><<<dp_grid_for(n1, 128, 8), 128, 0, c.stream>>>(leaves, n1, t.levels);
-            else k_merkle_l1<false><<<dp_grid_for(n1, 128, 8), 128, 0, c.stream>>>(leaves, n1, t.levels);
+        const u64 TAIL = 512;   // levels with <= TAIL digests are finished by one single-block launch
+        u32 l = 1;
+        for (; l < t.lg && (n >> (l + 1)) > TAIL; l++) {
+            u64 nl = n >> (l + 1);
+            DpProfScope prof("k_merkle(poseidon2 compress)", l == 1 ? nl * (ext ? 64 : 32) + nl * 32 : nl * 96);
+            if (l == 1) {
+                if (ext) k_merkle_l1<true><<<dp_grid_for(nl, 128, 8), 128, 0, c.stream>>>(leaves, nl, t.levels);
+                else k_merkle_l1<false><<<dp_grid_for(nl, 128, 8), 128, 0, c.stream>>>(leaves, nl, t.levels);
+            } else k_merkle_up<<<dp_grid_for(nl, 128, 8), 128, 0, c.stream>>>(t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
             DP_LAUNCHED();
         }
-        for (u32 l = 2; l < t.lg; l++) {
-            u64 nl = n >> (l + 1);
-            DpProfScope prof("k_merkle(poseidon2 compress)", nl * 96);
-            k_merkle_up<<<dp_grid_for(nl, 128, 8), 128, 0, c.stream>>>(t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]); DP_LAUNCHED();
+        if (l < t.lg) {
+            LvlOff lo; memset(&lo, 0, sizeof lo);
+            for (u32 k = 1; k < t.lg && k < 36; k++) lo.off[k] = t.lvl_off[k];
+            DpProfScope prof("k_merkle_tail(poseidon2 compress)", (n >> l) * 48);
+            if (ext) k_merkle_tail<true><<<1, 256, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo);
+            else k_merkle_tail<false><<<1, 256, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo);
+            DP_LAUNCHED();
         }
         t.root_dev = t.levels + 4 * t.lvl_off[t.lg - 1];
     }
@@ -312,6 +340,7 @@ int dp_poseidon2_init(const uint64_t *ext_rc /*2x4x8*/, const uint64_t *int_rc /
 }
 
 int dp_pcs_commit(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out) {
+    DP_HOST_TIMED("dp_pcs_commit");
     DP_REQUIRE_CTX();
     DP_CHECK(poly && out, DP_ERR_INVALID, "dp_pcs_commit: null argument");
     u32 nv = poly->num_vars();
@@ -395,6 +424,7 @@ int dp_pcs_comm_free(dp_pcs_comm *cm) {
 // commit_phase / batch_commit_phase up to and including the first sumcheck message
 int dp_pcs_open_begin(const dp_pcs_comm *const *comms, const uint64_t *coeffs, uint32_t n_comms, const uint64_t *point, uint32_t num_vars,
                       dp_pcs_open **out, uint64_t first_msg[6]) {
+    DP_HOST_TIMED("dp_pcs_open_begin");
     DP_REQUIRE_CTX();
     DP_CHECK(comms && n_comms >= 1 && point && out && first_msg, DP_ERR_INVALID, "dp_pcs_open_begin: null argument");
     if (int e = bf_prepare()) return e;
@@ -462,6 +492,7 @@ int dp_pcs_open_begin(const dp_pcs_comm *const *comms, const uint64_t *coeffs, u
 // One commit-phase round (commit_phase.rs:85-171 / :253-352): fold the oracle by `challenge`; unless this is
 // the last round return the next sumcheck message and the root of the folded oracle's tree.
 int dp_pcs_open_round(dp_pcs_open *o, const uint64_t challenge[2], uint64_t next_msg[6], uint64_t root[4], int *is_last) {
+    DP_HOST_TIMED("dp_pcs_open_round");
     DP_REQUIRE_CTX();
     DP_CHECK(o && challenge && is_last, DP_ERR_INVALID, "dp_pcs_open_round: null argument");
     DP_CHECK(o->round < o->num_rounds, DP_ERR_STATE, "dp_pcs_open_round: commit phase already finished");
@@ -550,6 +581,7 @@ uint64_t dp_pcs_open_query_words(const dp_pcs_open *o) {
 // K13 (query_phase.rs:373-474): for every x index, for every commitment then every round oracle:
 // [p0.c0 p0.c1 p1.c0 p1.c1] + Merkle path without leaf sibling or root (merkle_tree.rs:139-152).
 int dp_pcs_open_query(dp_pcs_open *o, const uint64_t *x_indices, uint32_t n, uint64_t *out) {
+    DP_HOST_TIMED("dp_pcs_open_query");
     DP_REQUIRE_CTX();
     DP_CHECK(o && x_indices && out && n > 0, DP_ERR_INVALID, "dp_pcs_open_query: null argument");
     DP_CHECK(o->have_final, DP_ERR_STATE, "dp_pcs_open_query: commit phase not finished");

@@ -42,6 +42,14 @@ struct DpProfScope {
     ~DpProfScope() { dp_prof_end(tok); }
 };
 
+// host-side wall-clock accumulators (DP_HOST_PROF=1): where a round-granular call spends its CPU time
+struct DpHostTimer {
+    const char *name; double t0;
+    explicit DpHostTimer(const char *n);
+    ~DpHostTimer();
+};
+#define DP_HOST_TIMED(name) DpHostTimer dp_host_timer_##__LINE__(name)
+
 // stream-ordered allocation helpers
 int dp_dev_alloc(void **p, size_t bytes);
 int dp_dev_free(void *p);

@@ -1,5 +1,7 @@
 // Context, error reporting and memory-pool plumbing of libdeepprove_b200.so.
 #include "common.cuh"
+#include <map>
+#include <cstdlib>
 
 static thread_local std::string g_err;
 static DpCtx g_ctx;
@@ -30,6 +32,17 @@ int dp_pinned_alloc(void **p, size_t bytes) {
     return DP_OK;
 }
 void dp_pinned_free(void *p) { if (!p) return; for (auto &b : g_pinned) if (b.p == p) { b.used = false; return; } }
+
+#include <chrono>
+static bool g_hostprof = getenv("DP_HOST_PROF") != nullptr;
+static std::map<std::string, std::pair<unsigned long long, double>> g_hostprof_acc;
+static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+DpHostTimer::DpHostTimer(const char *n) : name(n), t0(g_hostprof ? now_us() : 0.0) {}
+DpHostTimer::~DpHostTimer() { if (g_hostprof) { auto &a = g_hostprof_acc[name]; a.first++; a.second += now_us() - t0; } }
+extern "C" void dp_hostprof_dump(void) {
+    for (auto &kv : g_hostprof_acc) fprintf(stderr, "[hostprof] %-32s n=%8llu total=%10.3f ms avg=%8.2f us\n", kv.first.c_str(), kv.second.first, kv.second.second / 1e3, kv.second.second / kv.second.first);
+    g_hostprof_acc.clear();
+}
 
 // ---- per-kernel event timing --------------------------------------------------------------------
 #include <map>

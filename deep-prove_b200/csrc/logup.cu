@@ -36,6 +36,21 @@ __global__ void k_logup_layer(const gle *__restrict__ num, const gle *__restrict
         st_e(oden + i, e_mul(d1, d2));
     }
 }
+// all remaining (small) layers in one single-block launch
+struct LayerPtrs { gle *num[40]; gle *den[40]; };
+__global__ void __launch_bounds__(256) k_logup_tail(LayerPtrs lp, u32 from_layer, u32 n_layers, u64 len0, bool first_is_lookup) {
+    for (u32 k = from_layer; k + 1 < n_layers; k++) {
+        u64 half = len0 >> (k + 1);
+        const gle *num = lp.num[k], *den = lp.den[k];
+        for (u64 i = threadIdx.x; i < half; i += blockDim.x) {
+            gle d1 = den[i], d2 = den[i + half], n;
+            if (k == 0 && first_is_lookup) n = e_neg(e_add(d2, d1));
+            else { gle n1 = num[i], n2 = num[i + half]; n = e_add(e_mul(n1, d2), e_mul(d1, n2)); }
+            lp.num[k + 1][i] = n; lp.den[k + 1][i] = e_mul(d1, d2);
+        }
+        __syncthreads();
+    }
+}
 // out[i] = sum_k coef_k * m_k[i]
 struct LinArg { const gle *m[16]; gle coef[16]; u32 n; };
 __global__ void k_lincomb(LinArg a, u64 len, gle *__restrict__ out) {
@@ -58,6 +73,7 @@ extern "C" {
 // LogUpCircuit::new_lookup_circuit (multiplicities == NULL) / new_table_circuit
 int dp_logup_build(dp_mle *const *columns, uint32_t n_columns, const dp_mle *multiplicities, const uint64_t constant_challenge[2],
                    const uint64_t column_separation_challenge[2], dp_logup **out) {
+    DP_HOST_TIMED("dp_logup_build");
     DP_REQUIRE_CTX();
     DP_CHECK(columns && n_columns >= 1 && n_columns <= 16 && out && constant_challenge && column_separation_challenge, DP_ERR_INVALID, "dp_logup_build: bad argument");
     u64 len = columns[0]->len;
@@ -82,13 +98,20 @@ int dp_logup_build(dp_mle *const *columns, uint32_t n_columns, const dp_mle *mul
     int g = dp_grid_for(len, 256, 8);
     { DpProfScope prof("k_logup_den", len * (8 * n_columns + 16)); k_logup_den<<<g, 256, 0, c.stream>>>(ca, cc, len, L->den[0]); DP_LAUNCHED(); }
     if (L->table) { k_lift_b2e<<<g, 256, 0, c.stream>>>((const u64 *)multiplicities->data, L->num[0], len); DP_LAUNCHED(); }
-    for (u32 k = 0; k + 1 < L->nv; k++) {
+    u32 k = 0;
+    for (; k + 1 < L->nv && (len >> (k + 1)) > 1024; k++) {
         u64 half = len >> (k + 1);
         int gg = dp_grid_for(half, 256, 8);
         DpProfScope prof("k_logup_layer", half * 96);
         if (k == 0 && !L->table) k_logup_layer<true><<<gg, 256, 0, c.stream>>>(nullptr, L->den[0], half, L->num[1], L->den[1]);
         else k_logup_layer<false><<<gg, 256, 0, c.stream>>>(L->num[k], L->den[k], half, L->num[k + 1], L->den[k + 1]);
         DP_LAUNCHED();
+    }
+    if (k + 1 < L->nv) {
+        LayerPtrs lp; memset(&lp, 0, sizeof lp);
+        for (u32 q = 0; q < L->nv && q < 40; q++) { lp.num[q] = L->num[q]; lp.den[q] = L->den[q]; }
+        DpProfScope prof("k_logup_tail", (len >> k) * 96);
+        k_logup_tail<<<1, 256, 0, c.stream>>>(lp, k, L->nv, len, !L->table); DP_LAUNCHED();
     }
     DP_CUDA(cudaGetLastError());
     if (!L->table) L->num[0] = nullptr;

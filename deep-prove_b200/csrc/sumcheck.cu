@@ -275,6 +275,7 @@ extern "C" {
 
 int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *products, uint32_t n_products,
                  uint32_t max_nv, uint32_t max_deg, dp_sc **out) {
+    DP_HOST_TIMED("dp_sc_create");
     DP_REQUIRE_CTX();
     DP_CHECK(mles && products && out && n_mles > 0 && n_products > 0, DP_ERR_INVALID, "dp_sc_create: null/empty argument");
     DP_CHECK(max_nv != 0, DP_ERR_INVALID, "Attempt to prove a constant.");  // prover.rs:590-593
@@ -321,6 +322,7 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
 }
 
 int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
+    DP_HOST_TIMED("dp_sc_round(total)");
     DP_REQUIRE_CTX();
     DP_CHECK(s && out_evals, DP_ERR_INVALID, "dp_sc_round: null argument");
     DP_CHECK(!s->finished && s->round < s->max_nv, DP_ERR_STATE, "Prover is not active");  // prover.rs:636-639
@@ -417,7 +419,7 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
     }
     s->round += 1;
     s->last_bytes = bytes;
-    DP_CUDA(cudaStreamSynchronize(st));
+    { DP_HOST_TIMED("dp_sc_round(sync wait)"); DP_CUDA(cudaStreamSynchronize(st)); }
     // host glue: multiplicity, coefficient, extrapolation, sum over products (prover.rs:694-733)
     gle msg[SC_NACC + 1];
     for (u32 t = 0; t <= s->max_deg; t++) msg[t] = e_zero();
@@ -443,6 +445,7 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
 }
 
 int dp_sc_finish(dp_sc *s, const uint64_t *last_challenge, uint64_t *out_final) {
+    DP_HOST_TIMED("dp_sc_finish");
     DP_REQUIRE_CTX();
     DP_CHECK(s && last_challenge && out_final, DP_ERR_INVALID, "dp_sc_finish: null argument");
     DP_CHECK(!s->finished && s->round == s->max_nv, DP_ERR_STATE, "dp_sc_finish: rounds not complete");
@@ -469,6 +472,7 @@ int dp_sc_finish(dp_sc *s, const uint64_t *last_challenge, uint64_t *out_final) 
 
 int dp_sc_destroy(dp_sc *s) {
     if (!s) return DP_OK;
+    DP_HOST_TIMED("dp_sc_destroy");
     std::lock_guard<std::recursive_mutex> lk(dp_ctx().mu);
     if (dp_ctx().ready) sc_free_all(s);
     delete s;
