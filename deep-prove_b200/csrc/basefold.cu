@@ -166,6 +166,26 @@ __global__ void k_merkle_up(const u64 *__restrict__ in, u64 n_out, u64 *__restri
         *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(o[2], o[3]);
     }
 }
+// 8 lanes per hash (poseidon2.cuh): word w of the leaf-pair digest `pair`
+template <bool EXT> __device__ __forceinline__ u64 leaf_pair_word(const void *leaves, u64 pair, int w) {
+    if (EXT) return ((const u64 *)leaves)[4 * pair + w];
+    return w < 2 ? ((const u64 *)leaves)[2 * pair + w] : 0ULL;
+}
+template <bool EXT, bool FROM_LEAVES>
+__global__ void __launch_bounds__(256) k_merkle_x8(const void *src, u64 n_out, u64 *__restrict__ out) {
+    const int lane8 = threadIdx.x & 7;
+    u64 h = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3, stride = ((u64)gridDim.x * blockDim.x) >> 3;
+    // whole 8-lane groups stay together: the loop bound is uniform inside a group
+    for (; h < n_out; h += stride) {
+        u64 xw = 0, yw = 0;
+        if (lane8 < 4) {
+            if (FROM_LEAVES) { xw = leaf_pair_word<EXT>(src, 2 * h, lane8); yw = leaf_pair_word<EXT>(src, 2 * h + 1, lane8); }
+            else { const u64 *in = (const u64 *)src + 8 * h; xw = in[lane8]; yw = in[4 + lane8]; }
+        }
+        u64 s = p2x8_compress(xw, yw, lane8);
+        if (lane8 < 4) out[4 * h + (3 - lane8)] = s;
+    }
+}
 // every remaining level of a small (sub)tree in ONE launch: a single block walks the levels with
 // __syncthreads() in between, so a 2^11-leaf witness commitment costs one launch instead of ten
 struct LvlOff { u64 off[36]; };
@@ -174,15 +194,18 @@ __global__ void __launch_bounds__(256) k_merkle_tail(const void *leaves, u64 n, 
     for (u32 l = from_level; l < lg; l++) {
         u64 nl = n >> (l + 1);
         u64 *out = levels + 4 * lo.off[l];
-        for (u64 i = threadIdx.x; i < nl; i += blockDim.x) {
-            u64 x[4], y[4], o[4];
-            if (l == 1) { leaf_pair_digest<EXT>(leaves, 2 * i, x); leaf_pair_digest<EXT>(leaves, 2 * i + 1, y); }
-            else {
-                const u64 *in = levels + 4 * lo.off[l - 1] + 8 * i;   // written earlier in this launch: plain loads
-                for (int k = 0; k < 4; k++) { x[k] = in[k]; y[k] = in[4 + k]; }
+        const int lane8 = threadIdx.x & 7;
+        u64 rounds = (nl + (blockDim.x >> 3) - 1) / (blockDim.x >> 3);   // uniform trip count: shuffles need the full warp
+        for (u64 it = 0; it < rounds; it++) {
+            u64 i = it * (blockDim.x >> 3) + (threadIdx.x >> 3);
+            bool live = i < nl;
+            u64 xw = 0, yw = 0;
+            if (live && lane8 < 4) {
+                if (l == 1) { xw = leaf_pair_word<EXT>(leaves, 2 * i, lane8); yw = leaf_pair_word<EXT>(leaves, 2 * i + 1, lane8); }
+                else { const u64 *in = levels + 4 * lo.off[l - 1] + 8 * i; xw = in[lane8]; yw = in[4 + lane8]; }   // plain loads: written earlier in this launch
             }
-            p2_compress(x, y, o);
-            for (int k = 0; k < 4; k++) out[4 * i + k] = o[k];
+            u64 s = p2x8_compress(xw, yw, lane8);
+            if (live && lane8 < 4) out[4 * i + (3 - lane8)] = s;
         }
         __syncthreads();
     }
@@ -213,6 +236,14 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
         u32 l = 1;
         for (; l < t.lg && (n >> (l + 1)) > TAIL; l++) {
             u64 nl = n >> (l + 1);
+            if (nl <= 32768) {   // too few hashes for one thread each: 8 lanes per hash
+                DpProfScope prof("k_merkle_x8(poseidon2 compress)", l == 1 ? nl * (ext ? 64 : 32) + nl * 32 : nl * 96);
+                int g = dp_grid_for(nl * 8, 256, 8);
+                if (l == 1) { if (ext) k_merkle_x8<true, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); else k_merkle_x8<false, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); }
+                else k_merkle_x8<false, false><<<g, 256, 0, c.stream>>>(t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
+                DP_LAUNCHED();
+                continue;
+            }
             DpProfScope prof("k_merkle(poseidon2 compress)", l == 1 ? nl * (ext ? 64 : 32) + nl * 32 : nl * 96);
             if (l == 1) {
                 if (ext) k_merkle_l1<true><<<dp_grid_for(nl, 128, 8), 128, 0, c.stream>>>(leaves, nl, t.levels);
@@ -339,15 +370,14 @@ int dp_poseidon2_init(const uint64_t *ext_rc /*2x4x8*/, const uint64_t *int_rc /
     return DP_OK;
 }
 
-int dp_pcs_commit(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out) {
-    DP_HOST_TIMED("dp_pcs_commit");
-    DP_REQUIRE_CTX();
-    DP_CHECK(poly && out, DP_ERR_INVALID, "dp_pcs_commit: null argument");
+// enqueue every kernel of one commitment on the context's CURRENT stream; the root lands in `root_pinned`
+static int commit_enqueue(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out, u64 *root_pinned) {
     u32 nv = poly->num_vars();
     DP_CHECK(nv <= full_log, DP_ERR_INVALID, "PolynomialTooLarge");                 // basefold.rs:97-99
     DP_CHECK(nv >= 1, DP_ERR_INVALID, "dp_pcs_commit: need at least one variable");
     if (int e = bf_prepare()) return e;
     DpCtx &c = dp_ctx();
+    if (!root_pinned) return dp_fail(DP_ERR_INVALID, "commit_enqueue: no root buffer");
     dp_pcs_comm *cm = new dp_pcs_comm();
     cm->num_vars = nv; cm->full_log = full_log; cm->is_base = !poly->is_ext;
     size_t esz = poly->is_ext ? 16 : 8;
@@ -387,10 +417,56 @@ int dp_pcs_commit(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out) {
         dp_dev_free(coef); dp_dev_free(stab);
     }
     if (int e = tree_build(cm->tree, cm->codeword, poly->is_ext, cm->cw_len)) return e;   // K9
-    DP_CUDA(cudaMemcpyAsync(cm->root, cm->tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
-    DP_CUDA(cudaStreamSynchronize(c.stream));
+    DP_CUDA(cudaMemcpyAsync(root_pinned, cm->tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
     *out = cm;
     return DP_OK;
+}
+
+int dp_pcs_commit(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out) {
+    DP_HOST_TIMED("dp_pcs_commit");
+    DP_REQUIRE_CTX();
+    DP_CHECK(poly && out, DP_ERR_INVALID, "dp_pcs_commit: null argument");
+    u64 *pin = nullptr;
+    if (int e = dp_pinned_alloc((void **)&pin, 32)) return e;
+    int rc = commit_enqueue(poly, full_log, out, pin);
+    if (rc == DP_OK) { DP_CUDA(cudaStreamSynchronize(dp_ctx().stream)); memcpy((*out)->root, pin, 32); }
+    dp_pinned_free(pin);
+    return rc;
+}
+
+// Independent commitments (the reference commits witness columns from rayon workers: activation.rs:293,
+// requant.rs:298/315, lookup/context.rs:677) are enqueued round-robin on a pool of streams so their
+// latency chains (tree depth x Poseidon2 latency) overlap; one synchronisation at the end.
+static std::vector<cudaStream_t> g_pool; static std::vector<cudaEvent_t> g_pool_ev; static cudaEvent_t g_main_ev = nullptr;
+int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_log, dp_pcs_comm **out) {
+    DP_HOST_TIMED("dp_pcs_commit_many");
+    DP_REQUIRE_CTX();
+    DP_CHECK(polys && out && n > 0, DP_ERR_INVALID, "dp_pcs_commit_many: null argument");
+    for (u32 i = 0; i < n; i++) DP_CHECK(polys[i] != nullptr, DP_ERR_INVALID, "dp_pcs_commit_many: null polynomial");
+    if (int e = bf_prepare()) return e;
+    DpCtx &c = dp_ctx();
+    const u32 S = 8;
+    if (g_pool.empty()) {
+        g_pool.resize(S); g_pool_ev.resize(S);
+        for (u32 s = 0; s < S; s++) { DP_CUDA(cudaStreamCreateWithFlags(&g_pool[s], cudaStreamNonBlocking)); DP_CUDA(cudaEventCreateWithFlags(&g_pool_ev[s], cudaEventDisableTiming)); }
+        DP_CUDA(cudaEventCreateWithFlags(&g_main_ev, cudaEventDisableTiming));
+    }
+    u64 *pin = nullptr;
+    if (int e = dp_pinned_alloc((void **)&pin, 32 * (size_t)n)) return e;
+    cudaStream_t main = c.stream;
+    DP_CUDA(cudaEventRecord(g_main_ev, main));
+    u32 used = n < S ? n : S;
+    for (u32 s = 0; s < used; s++) DP_CUDA(cudaStreamWaitEvent(g_pool[s], g_main_ev, 0));
+    int rc = DP_OK;
+    for (u32 i = 0; i < n && rc == DP_OK; i++) { c.stream = g_pool[i % S]; rc = commit_enqueue(polys[i], full_log, &out[i], pin + 4 * i); }
+    c.stream = main;
+    for (u32 s = 0; s < used; s++) { cudaEventRecord(g_pool_ev[s], g_pool[s]); cudaStreamWaitEvent(main, g_pool_ev[s], 0); }
+    if (rc == DP_OK) {
+        DP_CUDA(cudaStreamSynchronize(main));
+        for (u32 i = 0; i < n; i++) memcpy(out[i]->root, pin + 4 * i, 32);
+    }
+    dp_pinned_free(pin);
+    return rc;
 }
 
 int dp_pcs_comm_info(const dp_pcs_comm *cm, uint32_t *num_vars, int *is_base, int *is_trivial, uint64_t root[4]) {

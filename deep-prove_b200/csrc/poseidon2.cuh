@@ -54,6 +54,44 @@ __device__ __forceinline__ void p2_permute(u64 (&s)[8]) {
         p2_mds_light(s);
     }
 }
+// ---- lane-parallel variant: 8 consecutive lanes hold the 8 state words of ONE permutation ----------------
+// Used where a level has too few hashes to fill the GPU with one thread per hash (tree tops, witness-sized
+// trees): the dependent-instruction chain per permutation drops ~3x (every lane does one S-box in the full
+// rounds; the linear layers are warp shuffles inside the 8-lane group).
+__device__ __forceinline__ u64 shfl8(u64 v, int src) { return __shfl_sync(0xffffffffu, v, src, 8); }
+__device__ __forceinline__ u64 shfl8_xor(u64 v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 8); }
+__device__ __forceinline__ u64 p2x8_mds_light(u64 s, int lane8) {
+    int g = lane8 & 4, r = lane8 & 3;
+    u64 a = shfl8(s, g + ((r + 1) & 3)), b = shfl8(s, g + ((r + 2) & 3)), c = shfl8(s, g + ((r + 3) & 3));
+    // row r of circ(2,3,1,1): 2 x_r + 3 x_{r+1} + x_{r+2} + x_{r+3}
+    u64 t = gl_add(gl_add(s, a), gl_add(b, c));
+    u64 o = gl_add(gl_add(t, s), gl_dbl(a));
+    return gl_add(gl_dbl(o), shfl8_xor(o, 4));     // state[i] += out[i] + out[i ^ 4]
+}
+__device__ __forceinline__ u64 p2x8_permute(u64 s, int lane8) {
+    s = p2x8_mds_light(s, lane8);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) { s = p2_pow7(gl_add(s, c_p2_ext[0][r][lane8])); s = p2x8_mds_light(s, lane8); }
+    const u64 dg = c_p2_diag[lane8];
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+        if (lane8 == 0) s = p2_pow7(gl_add(s, c_p2_int[r]));
+        u64 sum = gl_add(s, shfl8_xor(s, 1)); sum = gl_add(sum, shfl8_xor(sum, 2)); sum = gl_add(sum, shfl8_xor(sum, 4));
+        s = gl_add(gl_mul(s, dg), sum);
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) { s = p2_pow7(gl_add(s, c_p2_ext[1][r][lane8])); s = p2x8_mds_light(s, lane8); }
+    return s;
+}
+// lanes 0..3 pass x[lane] / y[lane] (lanes 4..7 pass anything); returns on lane k < 4 the digest word 3 - k
+__device__ __forceinline__ u64 p2x8_compress(u64 xw, u64 yw, int lane8) {
+    u64 s = lane8 < 4 ? xw : 0ULL;
+    s = p2x8_permute(s, lane8);
+    if (lane8 < 4) s = yw;
+    s = p2x8_permute(s, lane8);
+    return s;    // lane k holds state[k]; digest = [s3, s2, s1, s0]
+}
+
 // compress(x, y): absorb x -> permute -> overwrite rate with y -> permute -> [s3, s2, s1, s0]
 __device__ __forceinline__ void p2_compress(const u64 x[4], const u64 y[4], u64 out[4]) {
     u64 s[8] = {x[0], x[1], x[2], x[3], 0, 0, 0, 0};

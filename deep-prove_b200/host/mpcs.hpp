@@ -89,6 +89,13 @@ class Basefold {
         dp_pcs_comm *h; check(dp_pcs_commit(poly.handle(), pp.full_message_size_log, &h));
         return BasefoldCommitmentWithWitness(h);
     }
+    static std::vector<BasefoldCommitmentWithWitness> commit_many(const BasefoldProverParams &pp, const std::vector<DeviceMle> &polys) {
+        std::vector<dp_mle *> hs; for (auto &p : polys) hs.push_back(p.handle());
+        std::vector<dp_pcs_comm *> cs(polys.size(), nullptr);
+        if (!polys.empty()) check(dp_pcs_commit_many(hs.data(), (uint32_t)hs.size(), pp.full_message_size_log, cs.data()));
+        std::vector<BasefoldCommitmentWithWitness> out; for (auto *c : cs) out.push_back(BasefoldCommitmentWithWitness(c));
+        return out;
+    }
     template <class T> static void write_commitment(const Digest &root, T &t) { for (int i = 0; i < 4; i++) t.append_field_element(root.v[i]); }
 
     // Basefold::open (basefold.rs:466-539)

@@ -233,10 +233,15 @@ class Prover {
     void add_witness_claim(const ProverCommitment &pc, const Claim &c) { (pc.poly.num_vars() <= Basefold::trivial_num_vars() ? trivial_claims_ : claims_).push_back({pc, c}); }   // commit/context.rs:290-310
     ProverCommitment commit_column(const std::vector<u64> &ev) { DeviceMle p = DeviceMle::from_evaluations_vec(ev); return {Basefold::commit(ctx_.pp, p), p}; }
 
-    // generate_lookup_witnesses (lookup/context.rs:631-756) + initialise_from_table_set (:758-781)
+    // generate_lookup_witnesses (lookup/context.rs:631-756) + initialise_from_table_set (:758-781).
+    // The reference commits every witness column from rayon workers before any challenge is drawn; here all
+    // columns are gathered first and committed with ONE Basefold::commit_many call (concurrent on the device).
     void instantiate_witness_ctx(const Model &m, const std::vector<Element> &input, const std::vector<std::vector<Element>> &outs) {
         auto node_input = [&](size_t id) -> const std::vector<Element> & { return id == 0 ? input : outs[id - 1]; };
         std::map<TableType, std::unordered_map<Element, u64>> element_count;
+        std::vector<std::vector<u64>> cols;                      // every column to commit, in creation order
+        struct Slot { size_t node; size_t witness; bool table; };  // where commitment k goes
+        std::vector<Slot> slots;
         for (size_t id = 0; id < m.nodes.size(); id++) {
             const Node &n = m.nodes[id];
             if (n.op == Op::Requant) {   // requant.rs:208-330
@@ -250,16 +255,16 @@ class Prover {
                 for (auto &ch : chunks) for (Element e : ch) element_count[tr][e]++;
                 for (size_t i = 0; i < cin.size(); i++) element_count[tc][cin[i] + cout[i] * COLUMN_SEPARATOR]++;
                 LogUpWitness wc; wc.tt = tc; wc.columns_per_instance = 2;
-                for (auto *v : {&cin, &cout}) { wc.commits.push_back(commit_column(to_base(*v))); wc.column_evals.push_back(wc.commits.back().poly); }
                 LogUpWitness ws; ws.tt = tr; ws.columns_per_instance = 1;
-                for (auto &ch : chunks) { ws.commits.push_back(commit_column(to_base(ch))); ws.column_evals.push_back(ws.commits.back().poly); }
                 lookup_witness_[id] = {wc, ws};
+                for (auto *v : {&cin, &cout}) { cols.push_back(to_base(*v)); slots.push_back({id, 0, false}); }
+                for (auto &ch : chunks) { cols.push_back(to_base(ch)); slots.push_back({id, 1, false}); }
             } else if (n.op == Op::Relu) {   // activation.rs:238-323
                 TableType tt = TableType::relu(); LogUpWitness w; w.tt = tt; w.columns_per_instance = 2;
                 const auto &a = node_input(id); const auto &b = outs[id];
                 for (size_t i = 0; i < a.size(); i++) element_count[tt][a[i] + COLUMN_SEPARATOR * b[i]]++;
-                for (auto *v : {&a, &b}) { w.commits.push_back(commit_column(to_base(*v))); w.column_evals.push_back(w.commits.back().poly); }
                 lookup_witness_[id] = {w};
+                for (auto *v : {&a, &b}) { cols.push_back(to_base(*v)); slots.push_back({id, 0, false}); }
             }
         }
         for (auto &kv : element_count) {   // table multiplicities (lookup/context.rs:675-737)
@@ -270,8 +275,16 @@ class Prover {
                 if (it == kv.second.end()) mult[i] = 0;
                 else { u64 tc = td.table_count.at(td.merged[i]); mult[i] = fmul(canon(it->second), tc != 1 ? finv(canon(tc)) : 1); }
             }
-            LogUpWitness w; w.table = true; w.tt = kv.first; w.commits.push_back(commit_column(mult)); w.multiplicity_evals = w.commits[0].poly; w.column_evals = td.columns;
+            LogUpWitness w; w.table = true; w.tt = kv.first; w.column_evals = td.columns;
             table_witness_.push_back(w);
+            cols.push_back(std::move(mult)); slots.push_back({0, table_witness_.size() - 1, true});
+        }
+        std::vector<DeviceMle> polys; for (auto &c : cols) polys.push_back(DeviceMle::from_evaluations_vec(c));
+        std::vector<BasefoldCommitmentWithWitness> comms = Basefold::commit_many(ctx_.pp, polys);
+        for (size_t k = 0; k < slots.size(); k++) {
+            ProverCommitment pc{comms[k], polys[k]};
+            if (slots[k].table) { LogUpWitness &w = table_witness_[slots[k].witness]; w.commits.push_back(pc); w.multiplicity_evals = polys[k]; }
+            else { LogUpWitness &w = lookup_witness_[slots[k].node][slots[k].witness]; w.commits.push_back(pc); w.column_evals.push_back(polys[k]); }
         }
         constant_challenge_ = t_.get_and_append_challenge("table_constant");
         for (auto &kv : element_count) challenge_map_[kv.first] = kv.first.kind == 0 ? t_.get_and_append_challenge("Relu") : (kv.first.kind == 3 ? t_.get_and_append_challenge("Clamping") : Ext::one());

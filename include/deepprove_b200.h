@@ -128,6 +128,9 @@ int dp_poseidon2_init(const uint64_t *ext_rc, const uint64_t *int_rc, const uint
  * (RSCodeProverParameters.full_message_size_log, rs.rs:222-227): it fixes the coset shift.  Polynomials
  * with <= 7 variables get a Merkle tree over their raw evaluations ("TooSmall", basefold.rs:102-104). */
 int dp_pcs_commit(const dp_mle *poly, uint32_t full_message_size_log, dp_pcs_comm **out);
+/* n independent commitments issued concurrently (what the reference does from rayon workers:
+ * activation.rs:293, requant.rs:298/315, lookup/context.rs:677); same results as n dp_pcs_commit calls. */
+int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_message_size_log, dp_pcs_comm **out);
 int dp_pcs_comm_info(const dp_pcs_comm *c, uint32_t *num_vars, int *is_base, int *is_trivial, uint64_t root[4]);
 int dp_pcs_comm_codeword(const dp_pcs_comm *c, dp_mle **out_view);   /* bit-reversed codeword (view) */
 int dp_pcs_comm_bh_evals(const dp_pcs_comm *c, dp_mle **out_view);   /* bit-reversed evaluations (view) */
