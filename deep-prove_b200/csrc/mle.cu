@@ -4,6 +4,7 @@
 // coalesced along the fastest index, lazy (192-bit) accumulation so a dot product costs one modular
 // reduction per output instead of one per term.
 #include "common.cuh"
+#include <algorithm>
 
 struct PointArg { gle r[32]; };
 
@@ -154,6 +155,27 @@ __global__ void k_fixhigh_dot(const void *__restrict__ src, const gle *__restric
         acc = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : e_zero();
         for (int d = 16; d > 0; d >>= 1) acc = e_add(acc, shfl_down_e(acc, d));
         if (threadIdx.x == 0) st_e(out + i, acc);
+    }
+}
+
+// several MLEs of equal size evaluated at ONE point: the eq table is built once, one launch, one copy back
+struct EvalArg { const void *src[16]; u32 ext[16]; };
+__global__ void k_eval_many(EvalArg a, const gle *__restrict__ w, u64 J, gle *__restrict__ out) {
+    const u32 y = blockIdx.x;
+    gle acc = e_zero();
+    for (u64 j = threadIdx.x; j < J; j += blockDim.x) {
+        gle wj = ld_e(w + j);
+        if (a.ext[y]) acc = e_add(acc, e_mul(wj, ld_e((const gle *)a.src[y] + j)));
+        else acc = e_add(acc, e_mul_base(wj, ((const u64 *)a.src[y])[j]));
+    }
+    __shared__ gle sm[32];
+    for (int d = 16; d > 0; d >>= 1) acc = e_add(acc, shfl_down_e(acc, d));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : e_zero();
+        for (int d = 16; d > 0; d >>= 1) acc = e_add(acc, shfl_down_e(acc, d));
+        if (threadIdx.x == 0) st_e(out + y, acc);
     }
 }
 
@@ -340,6 +362,38 @@ int dp_mle_evaluate(const dp_mle *m, const uint64_t *point, uint32_t num_vars, u
     DP_CUDA(cudaMemcpyAsync(out, res, 16, cudaMemcpyDeviceToHost, dp_ctx().stream));
     DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));
     dp_dev_free(res);
+    return DP_OK;
+}
+
+// evaluate (mle.rs:607-623) for n MLEs with the same num_vars at the same point (e.g. the LogUp output claims,
+// logup_gkr/prover.rs:172-183): out = n x [c0,c1]
+int dp_mle_evaluate_many(const dp_mle *const *mles, uint32_t n, const uint64_t *point, uint32_t num_vars, uint64_t *out) {
+    DP_HOST_TIMED("dp_mle_evaluate_many");
+    DP_REQUIRE_CTX();
+    DP_CHECK(mles && out && n > 0 && (point || num_vars == 0), DP_ERR_INVALID, "dp_mle_evaluate_many: null argument");
+    for (u32 i = 0; i < n; i++) DP_CHECK(mles[i] && mles[i]->num_vars() == num_vars, DP_ERR_INVALID, "MLE size does not match the point");
+    if (num_vars == 0 || num_vars > 16) {   // rare shapes: one by one
+        for (u32 i = 0; i < n; i++) if (int e = dp_mle_evaluate(mles[i], point, num_vars, out + 2 * i)) return e;
+        return DP_OK;
+    }
+    gle pt[32]; point_from_host(point, num_vars, pt);
+    u64 J = 1ULL << num_vars;
+    gle *w = nullptr, *res = nullptr, *hres = nullptr;
+    if (int e = dp_dev_alloc((void **)&w, sizeof(gle) * J)) return e;
+    if (int e = dp_dev_alloc((void **)&res, sizeof(gle) * n)) return e;
+    if (int e = dp_pinned_alloc((void **)&hres, sizeof(gle) * n)) return e;
+    if (int e = dpk_eq_build(pt, num_vars, w)) return e;
+    for (u32 base = 0; base < n; base += 16) {
+        EvalArg a; memset(&a, 0, sizeof a);
+        u32 cnt = std::min<u32>(16, n - base);
+        for (u32 i = 0; i < cnt; i++) { a.src[i] = mles[base + i]->data; a.ext[i] = mles[base + i]->is_ext; }
+        k_eval_many<<<cnt, 256, 0, dp_ctx().stream>>>(a, w, J, res + base); DP_LAUNCHED();
+    }
+    DP_CUDA(cudaGetLastError());
+    DP_CUDA(cudaMemcpyAsync(hres, res, sizeof(gle) * n, cudaMemcpyDeviceToHost, dp_ctx().stream));
+    DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));
+    for (u32 i = 0; i < n; i++) { out[2 * i] = hres[i].c0; out[2 * i + 1] = hres[i].c1; }
+    dp_dev_free(w); dp_dev_free(res); dp_pinned_free(hres);
     return DP_OK;
 }
 

@@ -227,6 +227,18 @@ __global__ void k_sc_final(const ScFin *__restrict__ f, u32 n, gle r, gle *__res
     st_e(out + m, v);
 }
 
+// after the LAST round every MLE has <= 2 entries: copy them out with the round message so the closing fold
+// (prover.rs:544-568) needs no further device round trip
+__global__ void k_sc_gather(const ScFin *__restrict__ f, u32 n, gle *__restrict__ out /* 2 per MLE */) {
+    u32 m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    ScFin d = f[m];
+    gle a, b = e_zero();
+    if (d.mode == OPM_E) { const gle *s = (const gle *)d.src; a = ld_e(s); if (d.len > 1) b = ld_e(s + 1); }
+    else { const u64 *s = (const u64 *)d.src; a = e_from_base(s[0]); if (d.len > 1) b = e_from_base(s[1]); }
+    st_e(out + 2 * m, a); st_e(out + 2 * m + 1, b);
+}
+
 // ---------------------------------------------------------------------------------------------------
 struct ScMle {
     const void *cur = nullptr; u64 len = 0; bool is_ext = false;
@@ -242,6 +254,7 @@ struct dp_sc {
     gle *d_partials = nullptr, *d_out = nullptr, *h_out = nullptr;
     u32 *d_counters = nullptr;
     ScFin *d_fin = nullptr, *h_fin = nullptr;
+    gle *h_pairs = nullptr; bool have_pairs = false;
     int gx = 1;
     std::vector<gle> challenges;
     u64 last_bytes = 0;
@@ -267,7 +280,7 @@ static gle sc_extrapolate(const gle *evals, u32 n, u64 at) {
 static int sc_free_all(dp_sc *s) {
     for (auto &m : s->mles) if (m.work) { dp_dev_free(m.work); m.work = nullptr; }
     dp_dev_free(s->d_descs); dp_dev_free(s->d_partials); dp_dev_free(s->d_out); dp_dev_free(s->d_counters); dp_dev_free(s->d_fin);
-    dp_pinned_free(s->h_descs); dp_pinned_free(s->h_out); dp_pinned_free(s->h_fin);
+    dp_pinned_free(s->h_descs); dp_pinned_free(s->h_out); dp_pinned_free(s->h_fin); dp_pinned_free(s->h_pairs);
     return DP_OK;
 }
 
@@ -312,11 +325,12 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
     if ((e = dp_dev_alloc((void **)&s->d_partials, sizeof(gle) * SC_NACC * (size_t)s->gx * n_products))) return e;
     if ((e = dp_dev_alloc((void **)&s->d_out, sizeof(gle) * SC_NACC * n_products))) return e;
     if ((e = dp_dev_alloc((void **)&s->d_counters, sizeof(u32) * n_products))) return e;
-    if ((e = dp_dev_alloc((void **)&s->d_fin, sizeof(ScFin) * n_mles + sizeof(gle) * n_mles))) return e;
+    if ((e = dp_dev_alloc((void **)&s->d_fin, sizeof(ScFin) * n_mles + sizeof(gle) * 2 * n_mles))) return e;
     DP_CUDA(cudaMemsetAsync(s->d_counters, 0, sizeof(u32) * n_products, dp_ctx().stream));
     if ((e = dp_pinned_alloc((void **)&s->h_descs, sizeof(ScProd) * n_products))) return e;
     if ((e = dp_pinned_alloc((void **)&s->h_out, sizeof(gle) * std::max<size_t>(SC_NACC * n_products, n_mles)))) return e;
     if ((e = dp_pinned_alloc((void **)&s->h_fin, sizeof(ScFin) * n_mles))) return e;
+    if ((e = dp_pinned_alloc((void **)&s->h_pairs, sizeof(gle) * 2 * n_mles))) return e;
     *out = s;
     return DP_OK;
 }
@@ -419,6 +433,17 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
     }
     s->round += 1;
     s->last_bytes = bytes;
+    if (s->round == s->max_nv) {   // last round: bring the (<= 2)-entry tables back together with the message
+        bool ok = true;
+        for (u32 i = 0; i < s->n_mles; i++) { const ScMle &m = s->mles[i]; if (m.len > 2) ok = false; s->h_fin[i].src = m.cur; s->h_fin[i].mode = m.is_ext ? OPM_E : OPM_B; s->h_fin[i].len = (u32)m.len; }
+        if (ok) {
+            gle *d_pairs = (gle *)((char *)s->d_fin + sizeof(ScFin) * s->n_mles);
+            DP_CUDA(cudaMemcpyAsync(s->d_fin, s->h_fin, sizeof(ScFin) * s->n_mles, cudaMemcpyHostToDevice, st));
+            k_sc_gather<<<(s->n_mles + 127) / 128, 128, 0, st>>>(s->d_fin, s->n_mles, d_pairs); DP_LAUNCHED();
+            DP_CUDA(cudaMemcpyAsync(s->h_pairs, d_pairs, sizeof(gle) * 2 * s->n_mles, cudaMemcpyDeviceToHost, st));
+            s->have_pairs = true;
+        }
+    }
     { DP_HOST_TIMED("dp_sc_round(sync wait)"); DP_CUDA(cudaStreamSynchronize(st)); }
     // host glue: multiplicity, coefficient, extrapolation, sum over products (prover.rs:694-733)
     gle msg[SC_NACC + 1];
@@ -451,6 +476,15 @@ int dp_sc_finish(dp_sc *s, const uint64_t *last_challenge, uint64_t *out_final) 
     DP_CHECK(!s->finished && s->round == s->max_nv, DP_ERR_STATE, "dp_sc_finish: rounds not complete");
     gle r = e_make(gl_canon(last_challenge[0]), gl_canon(last_challenge[1]));
     s->challenges.push_back(r);
+    if (s->have_pairs) {   // O(#MLEs) host glue on the pairs fetched with the last message
+        for (u32 i = 0; i < s->n_mles; i++) {
+            gle a = s->h_pairs[2 * i], b = s->h_pairs[2 * i + 1];
+            gle v = s->mles[i].len > 1 ? e_add(a, e_mul(e_sub(b, a), r)) : a;
+            out_final[2 * i] = v.c0; out_final[2 * i + 1] = v.c1;
+        }
+        s->finished = true;
+        return DP_OK;
+    }
     for (u32 i = 0; i < s->n_mles; i++) {
         const ScMle &m = s->mles[i];
         // get_mle_final_evaluations asserts len == 1 after the last fix (prover.rs:479-483)

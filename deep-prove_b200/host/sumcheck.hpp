@@ -32,6 +32,13 @@ class DeviceMle {
     bool is_ext() const { int e; check(dp_mle_info(h_.get(), nullptr, &e, nullptr)); return e != 0; }
     uint32_t num_vars() const { uint32_t n; check(dp_mle_info(h_.get(), nullptr, nullptr, &n)); return n; }
     Ext evaluate(const ExtVec &point) const { auto f = flatten(point); u64 o[2]; check(dp_mle_evaluate(h_.get(), f.data(), (uint32_t)point.size(), o)); return Ext(o[0], o[1]); }
+    static ExtVec evaluate_many(const std::vector<DeviceMle> &ms, const ExtVec &point) {
+        std::vector<dp_mle *> hs; for (auto &m : ms) hs.push_back(m.handle());
+        auto f = flatten(point); std::vector<u64> o(2 * ms.size());
+        if (!ms.empty()) check(dp_mle_evaluate_many(hs.data(), (uint32_t)hs.size(), f.data(), (uint32_t)point.size(), o.data()));
+        ExtVec r; for (size_t i = 0; i < ms.size(); i++) r.push_back(Ext(o[2 * i], o[2 * i + 1]));
+        return r;
+    }
     void fix_high_variables_in_place(const ExtVec &point) { auto f = flatten(point); check(dp_mle_fix_high(h_.get(), f.data(), (uint32_t)point.size())); }
     DeviceMle fix_high_variables(const ExtVec &point) const { auto f = flatten(point); dp_mle *o; check(dp_mle_fix_high_new(h_.get(), f.data(), (uint32_t)point.size(), &o)); return DeviceMle(o); }
     static DeviceMle linear_combination(const std::vector<DeviceMle> &ms, const ExtVec &coefs) {

@@ -8,6 +8,9 @@
 #pragma once
 #include "mpcs.hpp"
 #include <unordered_map>
+#include <chrono>
+#include <cstdlib>
+#include <cstdio>
 
 namespace dp {
 namespace zkml {
@@ -120,8 +123,10 @@ LogUpProof logup_batch_prove(const LogUpInput &in, T &t) {
         pr.round_evaluations.push_back(evals);
     }
     // output claims about the base columns (prover.rs:172-183)
-    if (in.table) pr.output_claims.push_back({point, in.multiplicities.evaluate(point)});
-    for (auto &c : in.column_evals) pr.output_claims.push_back({point, c.evaluate(point)});
+    std::vector<DeviceMle> base; if (in.table) base.push_back(in.multiplicities);
+    for (auto &c : in.column_evals) base.push_back(c);
+    ExtVec be = DeviceMle::evaluate_many(base, point);
+    for (auto &e : be) pr.output_claims.push_back({point, e});
     return pr;
 }
 
@@ -212,8 +217,12 @@ class Prover {
     Proof prove(const std::vector<Element> &input, const std::vector<std::vector<Element>> &outs) {
         const Model &m = *ctx_.model;
         auto node_input = [&](size_t id) -> const std::vector<Element> & { return id == 0 ? input : outs[id - 1]; };
+        static const bool prof = getenv("DP_HOST_PROF") != nullptr;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t0 = now();
         ctx_.write_to_transcript(t_);
         instantiate_witness_ctx(m, input, outs);
+        double t1 = now();
         // output claim (prover.rs:423-436)
         const std::vector<Element> &fo = outs.back();
         Claim last; for (size_t i = 0, nv = ceil_log2(fo.size()); i < nv; i++) last.point.push_back(t_.read_challenge());
@@ -224,8 +233,12 @@ class Prover {
             else if (n.op == Op::Requant) last = prove_requant(id, n, last);
             else last = prove_activation(id, last, outs[id]);
         }
+        double t2 = now();
         prove_tables();
+        double t3 = now();
         commit_prove();
+        double t4 = now();
+        if (prof) fprintf(stderr, "[zkml] witness+commits %.2f ms | layers %.2f ms | tables %.2f ms | batch_open %.2f ms | FS permutations %llu\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, (unsigned long long)t_.permutations());
         return std::move(proof_);
     }
 

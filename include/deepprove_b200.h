@@ -72,6 +72,8 @@ int dp_mle_fix_high_new(const dp_mle *m, const uint64_t *point, uint32_t k, dp_m
 int dp_mle_fix_low(const dp_mle *m, const uint64_t *point, uint32_t k, dp_mle **out);
 /* evaluate (mle.rs:607-623): point has num_vars elements; out = [c0,c1]. */
 int dp_mle_evaluate(const dp_mle *m, const uint64_t *point, uint32_t num_vars, uint64_t out[2]);
+/* n MLEs with the same num_vars evaluated at one point (one eq table, one launch): out = n x [c0,c1]. */
+int dp_mle_evaluate_many(const dp_mle *const *mles, uint32_t n, const uint64_t *point, uint32_t num_vars, uint64_t *out);
 /* build_eq_x_r_vec (virtual_poly.rs:414-453) == compute_betas_eval (zkml/src/commit/mod.rs:10-28). */
 int dp_eq_build(const uint64_t *point, uint32_t num_vars, dp_mle **out);
 
