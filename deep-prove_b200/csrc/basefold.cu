@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) k_merkle_x8(const void *src, u64 n_out, u
 // __syncthreads() in between, so a 2^11-leaf witness commitment costs one launch instead of ten
 struct LvlOff { u64 off[36]; };
 template <bool EXT>
-__global__ void __launch_bounds__(1024) k_merkle_tail(const void *leaves, u64 n, u32 lg, u32 from_level, u64 *levels, LvlOff lo) {
+__global__ void __launch_bounds__(256) k_merkle_tail(const void *leaves, u64 n, u32 lg, u32 from_level, u64 *levels, LvlOff lo) {
     for (u32 l = from_level; l < lg; l++) {
         u64 nl = n >> (l + 1);
         u64 *out = levels + 4 * lo.off[l];
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(1024) k_merkle_tail(const void *leaves, u64 n,
         u64 rounds = (nl + (blockDim.x >> 3) - 1) / (blockDim.x >> 3);   // uniform trip count: shuffles need the full warp
         for (u64 it = 0; it < rounds; it++) {
             u64 i = it * (blockDim.x >> 3) + (threadIdx.x >> 3);
+            if (it * (blockDim.x >> 3) + ((threadIdx.x >> 5) << 2) >= nl) continue;   // whole warp idle (warp-uniform): skip the permutations
             bool live = i < nl;
             u64 xw = 0, yw = 0;
             if (live && lane8 < 4) {
@@ -232,7 +233,7 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
         if (ext) k_leafpair_root<true><<<1, 1, 0, c.stream>>>(leaves, t.levels); else k_leafpair_root<false><<<1, 1, 0, c.stream>>>(leaves, t.levels);
         DP_LAUNCHED(); t.root_dev = t.levels;
     } else {
-        const u64 TAIL = 128;   // levels with <= TAIL digests (one 1024-thread pass, 8 lanes per hash) are finished by one single-block launch
+        const u64 TAIL = 32;   // levels with <= TAIL digests (one 1024-thread pass, 8 lanes per hash) are finished by one single-block launch
         u32 l = 1;
         for (; l < t.lg && (n >> (l + 1)) > TAIL; l++) {
             u64 nl = n >> (l + 1);
@@ -255,8 +256,8 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
             LvlOff lo; memset(&lo, 0, sizeof lo);
             for (u32 k = 1; k < t.lg && k < 36; k++) lo.off[k] = t.lvl_off[k];
             DpProfScope prof("k_merkle_tail(poseidon2 compress)", (n >> l) * 48);
-            if (ext) k_merkle_tail<true><<<1, 1024, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo);
-            else k_merkle_tail<false><<<1, 1024, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo);
+            if (ext) k_merkle_tail<true><<<1, 256, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo);
+            else k_merkle_tail<false><<<1, 256, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo);
             DP_LAUNCHED();
         }
         t.root_dev = t.levels + 4 * t.lvl_off[t.lg - 1];

@@ -26,7 +26,7 @@ int dp_pinned_alloc(void **p, size_t bytes) {
     size_t cap = 4096; while (cap < bytes) cap <<= 1;
     for (auto &b : g_pinned) if (!b.used && b.cap == cap) { b.used = true; *p = b.p; return DP_OK; }
     void *q = nullptr;
-    DP_CUDA(cudaHostAlloc(&q, cap, cudaHostAllocDefault));
+    DP_CUDA(cudaHostAlloc(&q, cap, cudaHostAllocMapped));   // device-visible: kernels read descriptors / write results in place
     g_pinned.push_back({q, cap, true});
     *p = q;
     return DP_OK;

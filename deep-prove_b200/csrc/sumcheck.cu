@@ -138,9 +138,18 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
     for (int t = 0; t <= D; t++) acc[t] = a[t];
 }
 
+// completion signal: `out` and `flag` live in mapped pinned host memory, so the round message reaches the host
+// with the kernel's own stores -- no D2H copy node, and the host spins on the flag instead of a stream sync
+__device__ __forceinline__ void sc_signal(u64 seq, u64 *flag, u32 *done) {
+    if (gridDim.y == 1) { __threadfence_system(); *(volatile u64 *)flag = seq; return; }
+    u32 t = atomicAdd(done, 1u);
+    if (t == gridDim.y - 1) { *done = 0; __threadfence_system(); *(volatile u64 *)flag = seq; }
+}
+
 template <int DSEL>   // DSEL = 0: any degree (mixed-degree polynomials); 1..5: every product has this degree
 __global__ void __launch_bounds__(SC_THREADS)
-k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, u32 *__restrict__ counters, gle *__restrict__ out) {
+k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, u32 *__restrict__ counters, gle *__restrict__ out,
+           u64 seq, u64 *flag, u32 *done) {
     __shared__ ScProd pd;
     __shared__ gle wsum[SC_THREADS / 32][SC_NACC];
     __shared__ bool is_last;
@@ -172,10 +181,10 @@ k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, 
     if (threadIdx.x < nacc) {
         gle v = wsum[0][threadIdx.x];
         for (int w = 1; w < SC_THREADS / 32; w++) v = e_add(v, wsum[w][threadIdx.x]);
-        if (gridDim.x == 1) st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, v);   // no cross-block stage
+        if (gridDim.x == 1) { st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, v); __threadfence_system(); }   // no cross-block stage
         else st_e(partials + ((u64)blockIdx.y * gridDim.x + blockIdx.x) * SC_NACC + threadIdx.x, v);
     }
-    if (gridDim.x == 1) return;
+    if (gridDim.x == 1) { __syncthreads(); if (threadIdx.x == 0) sc_signal(seq, flag, done); return; }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -210,8 +219,10 @@ k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, 
             gle w = wsum[0][threadIdx.x];
             for (int k = 1; k < SC_THREADS / 32; k++) w = e_add(w, wsum[k][threadIdx.x]);
             st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, w);
+            __threadfence_system();
         }
-        if (threadIdx.x == 0) counters[blockIdx.y] = 0;
+        __syncthreads();
+        if (threadIdx.x == 0) { counters[blockIdx.y] = 0; sc_signal(seq, flag, done); }
     }
 }
 
@@ -255,6 +266,7 @@ struct dp_sc {
     u32 *d_counters = nullptr;
     ScFin *d_fin = nullptr, *h_fin = nullptr;
     gle *h_pairs = nullptr; bool have_pairs = false;
+    u64 seq = 0; u64 *h_flag = nullptr; u32 *d_done = nullptr;
     int gx = 1;
     std::vector<gle> challenges;
     u64 last_bytes = 0;
@@ -280,6 +292,7 @@ static gle sc_extrapolate(const gle *evals, u32 n, u64 at) {
 static int sc_free_all(dp_sc *s) {
     for (auto &m : s->mles) if (m.work) { dp_dev_free(m.work); m.work = nullptr; }
     dp_dev_free(s->d_descs); dp_dev_free(s->d_partials); dp_dev_free(s->d_out); dp_dev_free(s->d_counters); dp_dev_free(s->d_fin);
+    dp_pinned_free(s->h_flag);
     dp_pinned_free(s->h_descs); dp_pinned_free(s->h_out); dp_pinned_free(s->h_fin); dp_pinned_free(s->h_pairs);
     return DP_OK;
 }
@@ -324,9 +337,12 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
     if ((e = dp_dev_alloc((void **)&s->d_descs, sizeof(ScProd) * n_products))) return e;
     if ((e = dp_dev_alloc((void **)&s->d_partials, sizeof(gle) * SC_NACC * (size_t)s->gx * n_products))) return e;
     if ((e = dp_dev_alloc((void **)&s->d_out, sizeof(gle) * SC_NACC * n_products))) return e;
-    if ((e = dp_dev_alloc((void **)&s->d_counters, sizeof(u32) * n_products))) return e;
+    if ((e = dp_dev_alloc((void **)&s->d_counters, sizeof(u32) * (n_products + 1)))) return e;
+    s->d_done = s->d_counters + n_products;
+    if ((e = dp_pinned_alloc((void **)&s->h_flag, 64))) return e;
+    *s->h_flag = 0;
     if ((e = dp_dev_alloc((void **)&s->d_fin, sizeof(ScFin) * n_mles + sizeof(gle) * 2 * n_mles))) return e;
-    DP_CUDA(cudaMemsetAsync(s->d_counters, 0, sizeof(u32) * n_products, dp_ctx().stream));
+    DP_CUDA(cudaMemsetAsync(s->d_counters, 0, sizeof(u32) * (n_products + 1), dp_ctx().stream));
     if ((e = dp_pinned_alloc((void **)&s->h_descs, sizeof(ScProd) * n_products))) return e;
     if ((e = dp_pinned_alloc((void **)&s->h_out, sizeof(gle) * std::max<size_t>(SC_NACC * n_products, n_mles)))) return e;
     if ((e = dp_pinned_alloc((void **)&s->h_fin, sizeof(ScFin) * n_mles))) return e;
@@ -403,7 +419,7 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
     // grid sized for THIS round: 2 pairs per thread minimum so small rounds run in a single block
     int gx = std::min(s->gx, dp_grid_for(round_pairs <= 256 ? round_pairs : (round_pairs + 1) / 2, SC_THREADS, 4));
     cudaStream_t st = dp_ctx().stream;
-    DP_CUDA(cudaMemcpyAsync(s->d_descs, s->h_descs, sizeof(ScProd) * s->n_products, cudaMemcpyHostToDevice, st));
+    // descriptors are read by the kernel straight from mapped pinned memory (no H2D copy node)
     // MLEs no product references still have to be folded (cannot happen through add_mle_list, kept for safety)
     for (u32 i = 0; i < s->n_mles; i++) if (folds[i] && !written[i]) {
         ScMle &m = s->mles[i];
@@ -412,20 +428,20 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
     dim3 grid((unsigned)gx, s->n_products);
     {
         DpProfScope prof(fold ? "k_sc_round(fold+msg)" : "k_sc_round(msg)", bytes);
+        s->seq++;
         u32 dsel = s->products[0].n_idx;
         for (auto &pr : s->products) if (pr.n_idx != dsel) dsel = 0;
         switch (dsel) {   // one small kernel per uniform degree keeps the instruction footprint low
-        case 1: k_sc_round<1><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
-        case 2: k_sc_round<2><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
-        case 3: k_sc_round<3><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
-        case 4: k_sc_round<4><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
-        case 5: k_sc_round<5><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
-        default: k_sc_round<0><<<grid, SC_THREADS, 0, st>>>(s->d_descs, r, s->d_partials, s->d_counters, s->d_out); break;
+        case 1: k_sc_round<1><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        case 2: k_sc_round<2><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        case 3: k_sc_round<3><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        case 4: k_sc_round<4><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        case 5: k_sc_round<5><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        default: k_sc_round<0><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
         }
         DP_LAUNCHED();
     }
     DP_CUDA(cudaGetLastError());
-    DP_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, sizeof(gle) * SC_NACC * s->n_products, cudaMemcpyDeviceToHost, st));
     // commit the folds to the bookkeeping while the GPU works
     for (u32 i = 0; i < s->n_mles; i++) if (folds[i]) {
         ScMle &m = s->mles[i];
@@ -444,7 +460,15 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
             s->have_pairs = true;
         }
     }
-    { DP_HOST_TIMED("dp_sc_round(sync wait)"); DP_CUDA(cudaStreamSynchronize(st)); }
+    {
+        DP_HOST_TIMED("dp_sc_round(sync wait)");
+        if (s->have_pairs) DP_CUDA(cudaStreamSynchronize(st));      // last round: the gathered pairs follow the kernel
+        else {
+            volatile u64 *f = s->h_flag; u64 spins = 0; bool ok = false;
+            while (!(ok = (*f == s->seq))) { if (++spins > (1ULL << 26)) break; __builtin_ia32_pause(); }
+            if (!ok) { DP_CUDA(cudaStreamSynchronize(st)); DP_CHECK(*f == s->seq, DP_ERR_CUDA, "dp_sc_round: kernel finished without signalling"); }
+        }
+    }
     // host glue: multiplicity, coefficient, extrapolation, sum over products (prover.rs:694-733)
     gle msg[SC_NACC + 1];
     for (u32 t = 0; t <= s->max_deg; t++) msg[t] = e_zero();
