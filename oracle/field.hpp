@@ -23,16 +23,17 @@ typedef uint32_t u32;
 
 static const u64 GL_P = 0xFFFFFFFF00000001ULL;
 
-// 2^64 = 2^32 - 1 and 2^96 = -1 (mod p): branch-light reduction of a 128-bit product (same value as x % p)
+// 2^64 = 2^32 - 1 and 2^96 = -1 (mod p): branch-free reduction of a 128-bit product (same value as x % p)
+static inline u64 f_canon(u64 a) { u64 t = a + 0xFFFFFFFFULL; return t < a ? t : a; }
 static inline u64 f_reduce128(u128 x) {
     u64 lo = (u64)x, hi = (u64)(x >> 64), hh = hi >> 32, hl = hi & 0xFFFFFFFFULL;
-    u64 t0 = lo - hh; if (lo < hh) t0 -= 0xFFFFFFFFULL;
-    u64 t1 = hl * 0xFFFFFFFFULL, r = t0 + t1; if (r < t1) r += 0xFFFFFFFFULL;
-    return r >= GL_P ? r - GL_P : r;
+    u64 t0 = lo - hh; t0 -= ((u64)0 - (u64)(lo < hh)) & 0xFFFFFFFFULL;
+    u64 t1 = (hl << 32) - hl, r = t0 + t1; r += ((u64)0 - (u64)(r < t1)) & 0xFFFFFFFFULL;
+    return f_canon(r);
 }
-static inline u64 f_from_u64(u64 x) { return x >= GL_P ? x - GL_P : x; }
-static inline u64 f_add(u64 a, u64 b) { u128 s = (u128)a + b; return (u64)(s >= GL_P ? s - GL_P : s); }
-static inline u64 f_sub(u64 a, u64 b) { return a >= b ? a - b : a + (GL_P - b); }
+static inline u64 f_from_u64(u64 x) { return f_canon(x); }
+static inline u64 f_add(u64 a, u64 b) { u64 s = a + b; s += ((u64)0 - (u64)(s < a)) & 0xFFFFFFFFULL; return f_canon(s); }
+static inline u64 f_sub(u64 a, u64 b) { u64 d = a - b; return d - (((u64)0 - (u64)(a < b)) & 0xFFFFFFFFULL); }
 static inline u64 f_neg(u64 a) { return a ? GL_P - a : 0; }
 static inline u64 f_mul(u64 a, u64 b) { return f_reduce128((u128)a * b); }
 static inline u64 f_dbl(u64 a) { return f_add(a, a); }
