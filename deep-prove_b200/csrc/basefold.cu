@@ -38,16 +38,22 @@ __device__ __forceinline__ u64 tab_pow(const PowTab &t, u64 e) {
     return gl_mul(gl_mul(t.t0[e & 2047], t.t1[(e >> 11) & 2047]), t.t2[(e >> 22) & 2047]);
 }
 struct BfGlobals { u64 *root_tab = nullptr; bool p2_ready = false; };
-static BfGlobals g_bf;
+static BfGlobals g_bf;          // process-wide, read-only once built (shared by every host thread's context)
+static std::mutex g_bf_mu;
 static int bf_prepare() {
+    if (g_bf.p2_ready && g_bf.root_tab) return DP_OK;
+    std::lock_guard<std::mutex> lk(g_bf_mu);
     if (!g_bf.p2_ready) {
         DP_CUDA(p2_upload_constants((const u64 *)&DP_P2_EXT_RC[0][0][0], (const u64 *)DP_P2_INT_RC, (const u64 *)DP_P2_DIAG));
         g_bf.p2_ready = true;
     }
     if (!g_bf.root_tab) {
-        DP_CUDA(cudaMalloc((void **)&g_bf.root_tab, sizeof(u64) * 3 * 2048));
-        k_pow_table<<<24, 256, 0, dp_ctx().stream>>>(GL_ROOT32, g_bf.root_tab); DP_LAUNCHED();
+        u64 *tab = nullptr;
+        DP_CUDA(cudaMalloc((void **)&tab, sizeof(u64) * 3 * 2048));
+        k_pow_table<<<24, 256, 0, dp_ctx().stream>>>(GL_ROOT32, tab); DP_LAUNCHED();
         DP_CUDA(cudaGetLastError());
+        DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));   // complete before any other thread's stream reads it
+        g_bf.root_tab = tab;
     }
     return DP_OK;
 }
@@ -438,7 +444,7 @@ int dp_pcs_commit(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out) {
 // Independent commitments (the reference commits witness columns from rayon workers: activation.rs:293,
 // requant.rs:298/315, lookup/context.rs:677) are enqueued round-robin on a pool of streams so their
 // latency chains (tree depth x Poseidon2 latency) overlap; one synchronisation at the end.
-static std::vector<cudaStream_t> g_pool; static std::vector<cudaEvent_t> g_pool_ev; static cudaEvent_t g_main_ev = nullptr;
+static thread_local std::vector<cudaStream_t> g_pool; static thread_local std::vector<cudaEvent_t> g_pool_ev; static thread_local cudaEvent_t g_main_ev = nullptr;
 int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_log, dp_pcs_comm **out) {
     DP_HOST_TIMED("dp_pcs_commit_many");
     DP_REQUIRE_CTX();
@@ -446,7 +452,7 @@ int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_log
     for (u32 i = 0; i < n; i++) DP_CHECK(polys[i] != nullptr, DP_ERR_INVALID, "dp_pcs_commit_many: null polynomial");
     if (int e = bf_prepare()) return e;
     DpCtx &c = dp_ctx();
-    const u32 S = 8;
+    const u32 S = 4;
     if (g_pool.empty()) {
         g_pool.resize(S); g_pool_ev.resize(S);
         for (u32 s = 0; s < S; s++) { DP_CUDA(cudaStreamCreateWithFlags(&g_pool[s], cudaStreamNonBlocking)); DP_CUDA(cudaEventCreateWithFlags(&g_pool_ev[s], cudaEventDisableTiming)); }

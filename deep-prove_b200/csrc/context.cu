@@ -2,10 +2,14 @@
 #include "common.cuh"
 #include <map>
 #include <cstdlib>
+#include <atomic>
 
 static thread_local std::string g_err;
-static DpCtx g_ctx;
+// One context PER HOST THREAD (own stream, pinned cache, launch counter): independent proofs run concurrently
+// from several host threads on one GPU and share only read-only device data (model, tables, twiddles).
+static thread_local DpCtx g_ctx;
 DpCtx &dp_ctx() { return g_ctx; }
+static std::atomic<unsigned long long> g_total_launches{0};
 void dp_set_error(const std::string &s) { g_err = s; }
 int dp_fail(int code, const std::string &s) { g_err = s; return code; }
 
@@ -21,7 +25,7 @@ int dp_dev_free(void *p) {
 }
 
 struct PinnedBlk { void *p; size_t cap; bool used; };
-static std::vector<PinnedBlk> g_pinned;
+static thread_local std::vector<PinnedBlk> g_pinned;
 int dp_pinned_alloc(void **p, size_t bytes) {
     size_t cap = 4096; while (cap < bytes) cap <<= 1;
     for (auto &b : g_pinned) if (!b.used && b.cap == cap) { b.used = true; *p = b.p; return DP_OK; }
@@ -35,7 +39,7 @@ void dp_pinned_free(void *p) { if (!p) return; for (auto &b : g_pinned) if (b.p 
 
 #include <chrono>
 static bool g_hostprof = getenv("DP_HOST_PROF") != nullptr;
-static std::map<std::string, std::pair<unsigned long long, double>> g_hostprof_acc;
+static thread_local std::map<std::string, std::pair<unsigned long long, double>> g_hostprof_acc;
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 DpHostTimer::DpHostTimer(const char *n) : name(n), t0(g_hostprof ? now_us() : 0.0) {}
 DpHostTimer::~DpHostTimer() { if (g_hostprof) { auto &a = g_hostprof_acc[name]; a.first++; a.second += now_us() - t0; } }
@@ -48,10 +52,10 @@ extern "C" void dp_hostprof_dump(void) {
 #include <map>
 struct ProfRec { cudaEvent_t a, b; std::string name; u64 bytes; };
 struct ProfStat { u64 count = 0; double ms = 0; u64 bytes = 0; };
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof_pending;
-static std::vector<cudaEvent_t> g_prof_pool;
-static std::map<std::string, ProfStat> g_prof_stats;
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_prof_pending;
+static thread_local std::vector<cudaEvent_t> g_prof_pool;
+static thread_local std::map<std::string, ProfStat> g_prof_stats;
 static cudaEvent_t prof_event() {
     if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -139,6 +143,9 @@ int dp_shutdown(void) {
     cudaStreamSynchronize(g_ctx.stream);
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr; g_ctx.own_stream = false; g_ctx.ready = false;
+    g_total_launches += g_ctx.launches; g_ctx.launches = 0;
+    for (auto &b : g_pinned) cudaFreeHost(b.p);
+    g_pinned.clear();
     return DP_OK;
 }
 
@@ -156,6 +163,7 @@ int dp_synchronize(void) {
     return DP_OK;
 }
 
-uint64_t dp_kernel_launches(void) { return g_ctx.launches; }
+// launches of the calling thread's context + those folded in by threads that have shut down
+uint64_t dp_kernel_launches(void) { return g_ctx.launches + g_total_launches.load(); }
 
 }  // extern "C"

@@ -162,3 +162,35 @@ int dph_zkml_prove(void *handle, const int64_t *input, int mode, const char *lab
 }
 
 }  // extern "C"
+
+// ---- concurrent proving: n_workers host threads, each with its own library context (stream) on `device`, prove
+// the stored trace until n_proofs are done.  The GPU runs the threads' small latency-bound kernels side by side.
+#include <thread>
+#include <atomic>
+extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_workers, uint32_t n_proofs, const char *label, double *out_seconds) {
+    DPH_TRY
+    using namespace dp::zkml;
+    ZkHandle *h = (ZkHandle *)handle;
+    if (h->trace.empty()) throw dp::Error(DP_ERR_STATE, "dph_zkml_prove_concurrent: run inference first (mode 1)");
+    std::atomic<uint32_t> next{0}; std::atomic<int> failed{0}; std::string err; std::mutex emu;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (uint32_t w = 0; w < n_workers; w++) th.emplace_back([&] {
+        try {
+            dp::check(dp_init(device));
+            while (next.fetch_add(1) < n_proofs && !failed.load()) {
+                BasicTranscript t(label);
+                Prover<BasicTranscript> prover(h->ctx, t);
+                Proof p = prover.prove(h->trace_input, h->trace);
+                (void)p;
+            }
+            dp::check(dp_synchronize());
+            dp_shutdown();
+        } catch (const std::exception &e) { failed = 1; std::lock_guard<std::mutex> lk(emu); err = e.what(); }
+    });
+    for (auto &t : th) t.join();
+    if (out_seconds) *out_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (failed.load()) { g_herr = err; return 1; }
+    return 0;
+    DPH_CATCH
+}
