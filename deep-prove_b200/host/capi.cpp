@@ -166,6 +166,7 @@ int dph_zkml_prove(void *handle, const int64_t *input, int mode, const char *lab
 // ---- concurrent proving: n_workers host threads, each with its own library context (stream) on `device`, prove
 // the stored trace until n_proofs are done.  The GPU runs the threads' small latency-bound kernels side by side.
 #include <thread>
+#include <mutex>
 #include <atomic>
 extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_workers, uint32_t n_proofs, const char *label, double *out_seconds) {
     DPH_TRY
