@@ -445,6 +445,11 @@ int dp_pcs_commit(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out) {
 // requant.rs:298/315, lookup/context.rs:677) are enqueued round-robin on a pool of streams so their
 // latency chains (tree depth x Poseidon2 latency) overlap; one synchronisation at the end.
 static thread_local std::vector<cudaStream_t> g_pool; static thread_local std::vector<cudaEvent_t> g_pool_ev; static thread_local cudaEvent_t g_main_ev = nullptr;
+// stream sets are recycled across (short-lived) host threads: creating streams/events is slow and synchronising
+struct StreamSet { std::vector<cudaStream_t> s; std::vector<cudaEvent_t> e; cudaEvent_t main_ev; };
+static std::vector<StreamSet> g_free_sets; static std::mutex g_sets_mu;
+struct StreamSetReturn { ~StreamSetReturn() { if (!g_pool.empty()) { std::lock_guard<std::mutex> lk(g_sets_mu); g_free_sets.push_back({g_pool, g_pool_ev, g_main_ev}); } } };
+static thread_local StreamSetReturn g_set_return;
 int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_log, dp_pcs_comm **out) {
     DP_HOST_TIMED("dp_pcs_commit_many");
     DP_REQUIRE_CTX();
@@ -453,6 +458,11 @@ int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_log
     if (int e = bf_prepare()) return e;
     DpCtx &c = dp_ctx();
     const u32 S = 4;
+    (void)g_set_return;
+    if (g_pool.empty()) {
+        std::lock_guard<std::mutex> lk(g_sets_mu);
+        if (!g_free_sets.empty()) { g_pool = g_free_sets.back().s; g_pool_ev = g_free_sets.back().e; g_main_ev = g_free_sets.back().main_ev; g_free_sets.pop_back(); }
+    }
     if (g_pool.empty()) {
         g_pool.resize(S); g_pool_ev.resize(S);
         for (u32 s = 0; s < S; s++) { DP_CUDA(cudaStreamCreateWithFlags(&g_pool[s], cudaStreamNonBlocking)); DP_CUDA(cudaEventCreateWithFlags(&g_pool_ev[s], cudaEventDisableTiming)); }

@@ -14,6 +14,7 @@ struct DpCtx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaMemPool_t pool = nullptr;       // this thread's stream-ordered pool (no cross-stream reuse dependencies)
     std::recursive_mutex mu;
     unsigned long long launches = 0;
 };

@@ -3,6 +3,7 @@
 #include <map>
 #include <cstdlib>
 #include <atomic>
+#include <mutex>
 
 static thread_local std::string g_err;
 // One context PER HOST THREAD (own stream, pinned cache, launch counter): independent proofs run concurrently
@@ -15,7 +16,8 @@ int dp_fail(int code, const std::string &s) { g_err = s; return code; }
 
 int dp_dev_alloc(void **p, size_t bytes) {
     if (bytes == 0) bytes = 16;
-    DP_CUDA(cudaMallocAsync(p, bytes, dp_ctx().stream));
+    if (dp_ctx().pool) DP_CUDA(cudaMallocFromPoolAsync(p, bytes, dp_ctx().pool, dp_ctx().stream));
+    else DP_CUDA(cudaMallocAsync(p, bytes, dp_ctx().stream));
     return DP_OK;
 }
 int dp_dev_free(void *p) {
@@ -25,9 +27,11 @@ int dp_dev_free(void *p) {
 }
 
 struct PinnedBlk { void *p; size_t cap; bool used; };
-static thread_local std::vector<PinnedBlk> g_pinned;
+static std::vector<PinnedBlk> g_pinned;    // process-wide cache (cudaHostAlloc synchronises the device: never on the hot path)
+static std::mutex g_pinned_mu;
 int dp_pinned_alloc(void **p, size_t bytes) {
     size_t cap = 4096; while (cap < bytes) cap <<= 1;
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
     for (auto &b : g_pinned) if (!b.used && b.cap == cap) { b.used = true; *p = b.p; return DP_OK; }
     void *q = nullptr;
     DP_CUDA(cudaHostAlloc(&q, cap, cudaHostAllocMapped));   // device-visible: kernels read descriptors / write results in place
@@ -35,7 +39,7 @@ int dp_pinned_alloc(void **p, size_t bytes) {
     *p = q;
     return DP_OK;
 }
-void dp_pinned_free(void *p) { if (!p) return; for (auto &b : g_pinned) if (b.p == p) { b.used = false; return; } }
+void dp_pinned_free(void *p) { if (!p) return; std::lock_guard<std::mutex> lk(g_pinned_mu); for (auto &b : g_pinned) if (b.p == p) { b.used = false; return; } }
 
 #include <chrono>
 static bool g_hostprof = getenv("DP_HOST_PROF") != nullptr;
@@ -127,11 +131,16 @@ int dp_init(int device) {
     DP_CUDA(cudaGetDeviceProperties(&prop, device));
     g_ctx.sm_count = prop.multiProcessorCount;
     if (!g_ctx.stream) { DP_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking)); g_ctx.own_stream = true; }
-    // keep freed blocks in the pool: sumcheck rounds allocate/free ping-pong buffers constantly
-    cudaMemPool_t pool;
-    DP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long thresh = ~0ULL;
-    DP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    // keep freed blocks in the pool: sumcheck rounds allocate/free ping-pong buffers constantly.  Each host thread
+    // gets its OWN pool so that reuse never creates a dependency on another thread's stream.
+    if (!g_ctx.pool) {
+        cudaMemPoolProps props; memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned; props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice; props.location.id = device;
+        DP_CUDA(cudaMemPoolCreate(&g_ctx.pool, &props));
+        unsigned long long thresh = ~0ULL;
+        DP_CUDA(cudaMemPoolSetAttribute(g_ctx.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    }
     g_ctx.device = device;
     g_ctx.ready = true;
     return DP_OK;
@@ -144,8 +153,7 @@ int dp_shutdown(void) {
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr; g_ctx.own_stream = false; g_ctx.ready = false;
     g_total_launches += g_ctx.launches; g_ctx.launches = 0;
-    for (auto &b : g_pinned) cudaFreeHost(b.p);
-    g_pinned.clear();
+    if (g_ctx.pool) { cudaMemPoolDestroy(g_ctx.pool); g_ctx.pool = nullptr; }
     return DP_OK;
 }
 
