@@ -168,6 +168,7 @@ int dph_zkml_prove(void *handle, const int64_t *input, int mode, const char *lab
 #include <thread>
 #include <mutex>
 #include <atomic>
+extern "C" void dp_hostprof_dump(void);
 extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_workers, uint32_t n_proofs, const char *label, double *out_seconds) {
     DPH_TRY
     using namespace dp::zkml;
@@ -186,6 +187,7 @@ extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_wo
                 (void)p;
             }
             dp::check(dp_synchronize());
+            if (getenv("DP_HOST_PROF") && next.load() >= n_proofs) { static std::atomic<int> once{0}; if (!once.exchange(1)) dp_hostprof_dump(); }
             dp_shutdown();
         } catch (const std::exception &e) { failed = 1; std::lock_guard<std::mutex> lk(emu); err = e.what(); }
     });
