@@ -202,6 +202,21 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def max_over_ranks(ms, dist, device="cuda"):
+    """device-timed milliseconds -> the slowest rank's value (the job is only done when every rank is)"""
+    if dist is None:
+        return float(ms)
+    import torch
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_value(steps_per_rank, world, ms):
+    """replicas: every rank proves `steps_per_rank` independent proofs; value = all proofs / slowest rank's time"""
+    return steps_per_rank * world / (ms * 1e-3)
+
+
 def cpu_arm(wl, O, steps, warm):
     """time the CPU path (oracle port, all host threads it can use): returns (proofs/s, seconds per step, cores)"""
     cores = O.lib().dpo_num_threads()
@@ -291,11 +306,7 @@ def main():
         barrier()
         ms = sum(a.elapsed_time(b) for a, b in evs)
         launches = dp.lib().dp_kernel_launches() - l0
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches
+        return max_over_ranks(ms, dist), launches
 
     with ClockSampler(local_rank) as clk:
         ms, launches = timed(wl.step_resident, K, max(W, 3))
@@ -335,7 +346,7 @@ def main():
 
     if rank == 0:
         total = K * world
-        v = total / (ms * 1e-3)
+        v = whole_job_value(K, world, ms)
         pub = PUBLISHED.get(args.workload)
         out = {
             "metric": "proofs/sec", "value": v, "unit": "proofs/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),

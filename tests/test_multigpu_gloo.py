@@ -1,0 +1,53 @@
+"""N>1 host logic on CPU (gloo, world_size 2): the replica arm's max-over-ranks timing / whole-job value, and the
+reference arm's "rank 0 alone works and prints, other ranks exit 0" rule (task statement sections 4 and 5)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+import bench
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+ms = 10.0 + 5.0 * rank                       # rank 1 is slower
+agg = bench.max_over_ranks(ms, dist, device="cpu")
+val = bench.whole_job_value(4, world, agg)
+dist.barrier()
+if rank == 0:
+    print(json.dumps({"agg_ms": agg, "value": val, "world": world}))
+dist.destroy_process_group()
+''' % ROOT
+
+
+def _torchrun(args, timeout=300):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613"] + args
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+
+
+def test_replica_timing_is_max_over_ranks(tmp_path):
+    w = tmp_path / "worker.py"
+    w.write_text(WORKER)
+    r = _torchrun([str(w)])
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(line) == 1
+    out = json.loads(line[0])
+    assert out["world"] == 2 and out["agg_ms"] == 15.0           # the slower rank
+    assert abs(out["value"] - 8 / 0.015) < 1e-6                   # 2 ranks x 4 proofs / 15 ms
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    r = _torchrun(["bench.py", "--impl", "reference", "--workload", "sumcheck20", "--gpus", "2", "--steps", "1", "--warmup", "0"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference" and out["n_gpus"] == 2 and out["cpu_baseline"]["kind"] == "port"
+    assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["value"] > 0
