@@ -475,13 +475,14 @@ int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_log
     u32 used = n < S ? n : S;
     for (u32 s = 0; s < used; s++) DP_CUDA(cudaStreamWaitEvent(g_pool[s], g_main_ev, 0));
     int rc = DP_OK;
+    dp_arena_defer(true);    // temporaries released by one commit must not be handed to another stream's commit
     for (u32 i = 0; i < n && rc == DP_OK; i++) { c.stream = g_pool[i % S]; rc = commit_enqueue(polys[i], full_log, &out[i], pin + 4 * i); }
     c.stream = main;
     for (u32 s = 0; s < used; s++) { cudaEventRecord(g_pool_ev[s], g_pool[s]); cudaStreamWaitEvent(main, g_pool_ev[s], 0); }
-    if (rc == DP_OK) {
-        DP_CUDA(cudaStreamSynchronize(main));
-        for (u32 i = 0; i < n; i++) memcpy(out[i]->root, pin + 4 * i, 32);
-    }
+    cudaError_t se = cudaStreamSynchronize(main);
+    dp_arena_defer(false);
+    if (se != cudaSuccess) return dp_fail(DP_ERR_CUDA, std::string("dp_pcs_commit_many: ") + cudaGetErrorString(se));
+    if (rc == DP_OK) for (u32 i = 0; i < n; i++) memcpy(out[i]->root, pin + 4 * i, 32);
     dp_pinned_free(pin);
     return rc;
 }

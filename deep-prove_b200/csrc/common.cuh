@@ -54,6 +54,7 @@ struct DpHostTimer {
 // stream-ordered allocation helpers
 int dp_dev_alloc(void **p, size_t bytes);
 int dp_dev_free(void *p);
+void dp_arena_defer(bool on);   // hold releases back while several streams are in flight (dp_pcs_commit_many)
 // pinned host staging buffers, cached per context (cudaHostAlloc/cudaFreeHost cost ~ms and synchronise)
 int dp_pinned_alloc(void **p, size_t bytes);
 void dp_pinned_free(void *p);

@@ -14,16 +14,52 @@ static std::atomic<unsigned long long> g_total_launches{0};
 void dp_set_error(const std::string &s) { g_err = s; }
 int dp_fail(int code, const std::string &s) { g_err = s; return code; }
 
+// ---- per-thread device arena -------------------------------------------------------------------------
+// A proof makes thousands of short-lived allocations (ping-pong tables, eq tables, partials).  Going to the
+// driver for each one (even cudaMallocAsync) serialises concurrent proving threads on driver locks, so each
+// context sub-allocates from big cudaMalloc'ed slabs with power-of-two size classes on the host.  All work of a
+// context is ordered on its one stream, so a block may be reused as soon as it is released; the only
+// multi-stream section (dp_pcs_commit_many) defers its releases until its streams have been joined.
+#include <unordered_map>
+struct DpArena {
+    struct Slab { char *base; size_t cap, used; };
+    std::vector<Slab> slabs;
+    std::vector<void *> free_list[48];
+    std::unordered_map<void *, unsigned char> cls;
+    std::vector<void *> deferred; bool defer = false;
+    unsigned long long foreign_frees = 0;
+};
+static thread_local DpArena g_arena;
+static constexpr size_t ARENA_SLAB = 256ull << 20;
+void dp_arena_defer(bool on) {
+    g_arena.defer = on;
+    if (!on) { for (void *p : g_arena.deferred) { auto it = g_arena.cls.find(p); if (it != g_arena.cls.end()) g_arena.free_list[it->second].push_back(p); } g_arena.deferred.clear(); }
+}
 int dp_dev_alloc(void **p, size_t bytes) {
-    if (bytes == 0) bytes = 16;
-    if (dp_ctx().pool) DP_CUDA(cudaMallocFromPoolAsync(p, bytes, dp_ctx().pool, dp_ctx().stream));
-    else DP_CUDA(cudaMallocAsync(p, bytes, dp_ctx().stream));
+    if (bytes < 256) bytes = 256;
+    unsigned c = 8; while (((size_t)1 << c) < bytes) c++;
+    DpArena &a = g_arena;
+    if (!a.free_list[c].empty()) { *p = a.free_list[c].back(); a.free_list[c].pop_back(); return DP_OK; }
+    size_t need = (size_t)1 << c;
+    for (auto &s : a.slabs) if (s.cap - s.used >= need) { *p = s.base + s.used; s.used += need; a.cls[*p] = (unsigned char)c; return DP_OK; }
+    size_t cap = need > ARENA_SLAB ? need : ARENA_SLAB;
+    char *base = nullptr;
+    DP_CUDA(cudaMalloc((void **)&base, cap));
+    a.slabs.push_back({base, cap, need});
+    *p = base; a.cls[*p] = (unsigned char)c;
     return DP_OK;
 }
 int dp_dev_free(void *p) {
     if (!p) return DP_OK;
-    DP_CUDA(cudaFreeAsync(p, dp_ctx().stream));
+    DpArena &a = g_arena;
+    auto it = a.cls.find(p);
+    if (it == a.cls.end()) { a.foreign_frees++; return DP_OK; }   // owned by another thread's arena: returned when that arena is torn down
+    if (a.defer) a.deferred.push_back(p); else a.free_list[it->second].push_back(p);
     return DP_OK;
+}
+static void arena_destroy() {
+    for (auto &s : g_arena.slabs) cudaFree(s.base);
+    g_arena = DpArena();
 }
 
 struct PinnedBlk { void *p; size_t cap; bool used; };
@@ -133,14 +169,7 @@ int dp_init(int device) {
     if (!g_ctx.stream) { DP_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking)); g_ctx.own_stream = true; }
     // keep freed blocks in the pool: sumcheck rounds allocate/free ping-pong buffers constantly.  Each host thread
     // gets its OWN pool so that reuse never creates a dependency on another thread's stream.
-    if (!g_ctx.pool) {
-        cudaMemPoolProps props; memset(&props, 0, sizeof props);
-        props.allocType = cudaMemAllocationTypePinned; props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice; props.location.id = device;
-        DP_CUDA(cudaMemPoolCreate(&g_ctx.pool, &props));
-        unsigned long long thresh = ~0ULL;
-        DP_CUDA(cudaMemPoolSetAttribute(g_ctx.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
-    }
+    (void)device;
     g_ctx.device = device;
     g_ctx.ready = true;
     return DP_OK;
@@ -153,7 +182,7 @@ int dp_shutdown(void) {
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr; g_ctx.own_stream = false; g_ctx.ready = false;
     g_total_launches += g_ctx.launches; g_ctx.launches = 0;
-    if (g_ctx.pool) { cudaMemPoolDestroy(g_ctx.pool); g_ctx.pool = nullptr; }
+    arena_destroy();
     return DP_OK;
 }
 

@@ -137,7 +137,8 @@ int dph_zkml_context_new(uint32_t n_layers, uint32_t width, const int64_t *weigh
     return 0;
     DPH_CATCH
 }
-void dph_zkml_context_free(void *h) { delete (ZkHandle *)h; }
+extern "C" void dph_zkml_pool_free(void *handle);
+void dph_zkml_context_free(void *h) { dph_zkml_pool_free(h); delete (ZkHandle *)h; }
 
 // mode 0: inference + Prover::prove + flatten (end to end from the host input buffer)
 // mode 1: run inference only and keep the trace in the handle (not proving)
@@ -163,37 +164,51 @@ int dph_zkml_prove(void *handle, const int64_t *input, int mode, const char *lab
 
 }  // extern "C"
 
-// ---- concurrent proving: n_workers host threads, each with its own library context (stream) on `device`, prove
-// the stored trace until n_proofs are done.  The GPU runs the threads' small latency-bound kernels side by side.
+// ---- concurrent proving: a persistent pool of host threads, each with its own library context (stream + device
+// arena) on `device`, proves the stored trace; the GPU runs the threads' small latency-bound kernels side by side.
 #include <thread>
 #include <mutex>
 #include <atomic>
+#include <condition_variable>
 extern "C" void dp_hostprof_dump(void);
+namespace {
+struct ZkPool {
+    std::vector<std::thread> th; std::mutex mu; std::condition_variable cv, done_cv;
+    ZkHandle *h = nullptr; int device = 0; bool stop = false; uint64_t pending = 0, inflight = 0; std::string label, err; bool failed = false;
+    void worker() {
+        bool inited = false;
+        for (;;) {
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || pending > 0; }); if (stop) break; pending--; inflight++; }
+            try {
+                if (!inited) { dp::check(dp_init(device)); inited = true; }
+                dp::BasicTranscript t(label);
+                dp::zkml::Prover<dp::BasicTranscript> prover(h->ctx, t);
+                dp::zkml::Proof p = prover.prove(h->trace_input, h->trace);
+                (void)p;
+            } catch (const std::exception &e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.what(); }
+            { std::lock_guard<std::mutex> lk(mu); inflight--; if (pending == 0 && inflight == 0) done_cv.notify_all(); }
+        }
+        if (inited) { dp_synchronize(); if (getenv("DP_HOST_PROF")) { static std::atomic<int> once{0}; if (!once.exchange(1)) dp_hostprof_dump(); } dp_shutdown(); }
+    }
+    ~ZkPool() { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all(); for (auto &t : th) t.join(); }
+};
+std::mutex g_pools_mu; std::map<void *, std::unique_ptr<ZkPool>> g_pools;
+}
+extern "C" void dph_zkml_pool_free(void *handle) { std::lock_guard<std::mutex> lk(g_pools_mu); g_pools.erase(handle); }
 extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_workers, uint32_t n_proofs, const char *label, double *out_seconds) {
     DPH_TRY
-    using namespace dp::zkml;
     ZkHandle *h = (ZkHandle *)handle;
     if (h->trace.empty()) throw dp::Error(DP_ERR_STATE, "dph_zkml_prove_concurrent: run inference first (mode 1)");
-    std::atomic<uint32_t> next{0}; std::atomic<int> failed{0}; std::string err; std::mutex emu;
+    ZkPool *pool;
+    { std::lock_guard<std::mutex> lk(g_pools_mu); auto &pp = g_pools[handle]; if (!pp) { pp = std::make_unique<ZkPool>(); pp->h = h; pp->device = device; } pool = pp.get(); }
+    while (pool->th.size() < n_workers) pool->th.emplace_back([pool] { pool->worker(); });
     auto t0 = std::chrono::steady_clock::now();
-    std::vector<std::thread> th;
-    for (uint32_t w = 0; w < n_workers; w++) th.emplace_back([&] {
-        try {
-            dp::check(dp_init(device));
-            while (next.fetch_add(1) < n_proofs && !failed.load()) {
-                BasicTranscript t(label);
-                Prover<BasicTranscript> prover(h->ctx, t);
-                Proof p = prover.prove(h->trace_input, h->trace);
-                (void)p;
-            }
-            dp::check(dp_synchronize());
-            if (getenv("DP_HOST_PROF") && next.load() >= n_proofs) { static std::atomic<int> once{0}; if (!once.exchange(1)) dp_hostprof_dump(); }
-            dp_shutdown();
-        } catch (const std::exception &e) { failed = 1; std::lock_guard<std::mutex> lk(emu); err = e.what(); }
-    });
-    for (auto &t : th) t.join();
+    { std::lock_guard<std::mutex> lk(pool->mu); pool->label = label; pool->failed = false; pool->pending = n_proofs; }
+    // only the first n_workers threads are woken usefully: notify_all, extra threads just compete for the same jobs
+    pool->cv.notify_all();
+    { std::unique_lock<std::mutex> lk(pool->mu); pool->done_cv.wait(lk, [&] { return pool->pending == 0 && pool->inflight == 0; }); }
     if (out_seconds) *out_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (failed.load()) { g_herr = err; return 1; }
+    if (pool->failed) { g_herr = pool->err; return 1; }
     return 0;
     DPH_CATCH
 }
