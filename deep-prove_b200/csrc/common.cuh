@@ -32,7 +32,8 @@ int dp_fail(int code, const std::string &s);
     if (!dp_ctx().ready) return dp_fail(DP_ERR_NO_DEVICE, "dp_init() has not succeeded: no CUDA device context")
 #define DP_CHECK(cond, code, msg) \
     do { if (!(cond)) return dp_fail((code), (msg)); } while (0)
-#define DP_LAUNCHED() (dp_ctx().launches++)
+void dp_count_launch();
+#define DP_LAUNCHED() dp_count_launch()
 
 // optional per-kernel timing with CUDA events on the launch stream (bench.py's roofline leg)
 int dp_prof_begin(const char *name, u64 algorithmic_bytes);   // returns a token (or -1 when disabled)

@@ -11,6 +11,7 @@ static thread_local std::string g_err;
 static thread_local DpCtx g_ctx;
 DpCtx &dp_ctx() { return g_ctx; }
 static std::atomic<unsigned long long> g_total_launches{0};
+void dp_count_launch() { g_total_launches.fetch_add(1, std::memory_order_relaxed); }
 void dp_set_error(const std::string &s) { g_err = s; }
 int dp_fail(int code, const std::string &s) { g_err = s; return code; }
 
@@ -181,7 +182,6 @@ int dp_shutdown(void) {
     cudaStreamSynchronize(g_ctx.stream);
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr; g_ctx.own_stream = false; g_ctx.ready = false;
-    g_total_launches += g_ctx.launches; g_ctx.launches = 0;
     arena_destroy();
     return DP_OK;
 }
@@ -201,6 +201,6 @@ int dp_synchronize(void) {
 }
 
 // launches of the calling thread's context + those folded in by threads that have shut down
-uint64_t dp_kernel_launches(void) { return g_ctx.launches + g_total_launches.load(); }
+uint64_t dp_kernel_launches(void) { return g_total_launches.load(); }   // process-wide, all host threads
 
 }  // extern "C"

@@ -405,12 +405,13 @@ class ZkmlContext:
         hcheck(host().dph_zkml_prove(self.h, None, 2, label, _ptr(self._out) if want_proof else None, self._out.size, C.byref(n)))
         return self._out[: n.value].copy() if want_proof else None
 
-    def prove_concurrent(self, n_workers, n_proofs, device=0, label=b"m2vec"):
-        """n_workers host threads (own stream each) prove the stored trace until n_proofs are done; returns wall seconds"""
+    def prove_concurrent(self, n_workers, n_proofs, device=0, e2e=False, label=b"m2vec"):
+        """n_workers persistent host threads (own stream + device arena each) prove until n_proofs are done; returns wall
+        seconds.  e2e=False: Prover::prove on the stored trace; e2e=True: inference + prove + serialised proof per job."""
         H = host()
-        H.dph_zkml_prove_concurrent.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_double)]
+        H.dph_zkml_prove_concurrent.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p, C.POINTER(C.c_double)]
         sec = C.c_double()
-        hcheck(H.dph_zkml_prove_concurrent(self.h, int(device), int(n_workers), int(n_proofs), label, C.byref(sec)))
+        hcheck(H.dph_zkml_prove_concurrent(self.h, int(device), int(n_workers), int(n_proofs), int(bool(e2e)), label, C.byref(sec)))
         return sec.value
 
     def free(self):

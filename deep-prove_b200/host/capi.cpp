@@ -174,7 +174,7 @@ extern "C" void dp_hostprof_dump(void);
 namespace {
 struct ZkPool {
     std::vector<std::thread> th; std::mutex mu; std::condition_variable cv, done_cv;
-    ZkHandle *h = nullptr; int device = 0; bool stop = false; uint64_t pending = 0, inflight = 0; std::string label, err; bool failed = false;
+    ZkHandle *h = nullptr; int device = 0; bool stop = false; uint64_t pending = 0, inflight = 0; std::string label, err; bool failed = false; bool e2e = false;
     void worker() {
         bool inited = false;
         for (;;) {
@@ -183,8 +183,11 @@ struct ZkPool {
                 if (!inited) { dp::check(dp_init(device)); inited = true; }
                 dp::BasicTranscript t(label);
                 dp::zkml::Prover<dp::BasicTranscript> prover(h->ctx, t);
-                dp::zkml::Proof p = prover.prove(h->trace_input, h->trace);
-                (void)p;
+                if (e2e) {   // from the host input vector: inference, prove, serialised proof in host memory
+                    dp::zkml::Proof p = prover.prove(h->trace_input);
+                    std::vector<uint64_t> bytes = p.flatten(h->model.nodes.size());
+                    if (bytes.empty()) throw dp::Error(DP_ERR_STATE, "empty proof");
+                } else { dp::zkml::Proof p = prover.prove(h->trace_input, h->trace); (void)p; }
             } catch (const std::exception &e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.what(); }
             { std::lock_guard<std::mutex> lk(mu); inflight--; if (pending == 0 && inflight == 0) done_cv.notify_all(); }
         }
@@ -195,7 +198,7 @@ struct ZkPool {
 std::mutex g_pools_mu; std::map<void *, std::unique_ptr<ZkPool>> g_pools;
 }
 extern "C" void dph_zkml_pool_free(void *handle) { std::lock_guard<std::mutex> lk(g_pools_mu); g_pools.erase(handle); }
-extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_workers, uint32_t n_proofs, const char *label, double *out_seconds) {
+extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_workers, uint32_t n_proofs, int e2e, const char *label, double *out_seconds) {
     DPH_TRY
     ZkHandle *h = (ZkHandle *)handle;
     if (h->trace.empty()) throw dp::Error(DP_ERR_STATE, "dph_zkml_prove_concurrent: run inference first (mode 1)");
@@ -203,7 +206,7 @@ extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_wo
     { std::lock_guard<std::mutex> lk(g_pools_mu); auto &pp = g_pools[handle]; if (!pp) { pp = std::make_unique<ZkPool>(); pp->h = h; pp->device = device; } pool = pp.get(); }
     while (pool->th.size() < n_workers) pool->th.emplace_back([pool] { pool->worker(); });
     auto t0 = std::chrono::steady_clock::now();
-    { std::lock_guard<std::mutex> lk(pool->mu); pool->label = label; pool->failed = false; pool->pending = n_proofs; }
+    { std::lock_guard<std::mutex> lk(pool->mu); pool->label = label; pool->failed = false; pool->e2e = e2e != 0; pool->pending = n_proofs; }
     // only the first n_workers threads are woken usefully: notify_all, extra threads just compete for the same jobs
     pool->cv.notify_all();
     { std::unique_lock<std::mutex> lk(pool->mu); pool->done_cv.wait(lk, [&] { return pool->pending == 0 && pool->inflight == 0; }); }
