@@ -320,7 +320,8 @@ def main():
     def timed_many(run, steps, warm):
         """K steps issued as one batch (concurrent proof streams): bracketed by CUDA events recorded on the main stream
         with barrier + synchronize on both sides (the worker streams are drained before the call returns)"""
-        run(min(warm, steps) if warm else 0, local_rank) if warm else None
+        if warm:
+            run(warm, local_rank)
         barrier()
         l0 = dp.lib().dp_kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
