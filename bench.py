@@ -134,6 +134,49 @@ class SumcheckWorkload:
     flush = False
 
 
+class BasefoldWorkload:
+    """BASELINE.json configs[3] on one GPU: Basefold commit + open of one Base polynomial with 2^24 evaluations
+    (splitmix64 mod p), Poseidon2 Merkle, point of 24 E challenges from a fixed seed (SURVEY.md 8d Cfg 4)."""
+    NV = 24
+
+    def __init__(self):
+        self.name = "Basefold commit+open, 2^%d Base evaluations, RS rate 1/2, Poseidon2 Merkle, 200 queries" % self.NV
+        n = 1 << self.NV
+        self.evals = splitmix_f(1, n)
+        self.point = splitmix_f(4, 2 * self.NV).reshape(self.NV, 2)
+        self.h2d = 8 * n
+        self.d2h = None
+        # SURVEY.md 8(d): commit ~64 n, open ~240 n bytes
+        self.alg_bytes = (64 + 240) * n
+
+    def setup_device(self, dp):
+        self.dp = dp
+        self.mle = dp.Mle.upload(self.evals, False)
+        _, flat = dp.pcs_open(self.mle, self.NV, self.point, cap=1 << 23)
+        self.d2h = int(flat.size * 8)
+
+    def step_resident(self, i):
+        self.dp.pcs_open(self.mle, self.NV, self.point, cap=1 << 23)
+
+    def step_e2e(self, i):
+        m = self.dp.Mle.upload(self.evals, False)
+        out = self.dp.pcs_open(m, self.NV, self.point, cap=1 << 23)
+        m.free()
+        return out
+
+    def cpu_step(self, O, i):
+        nv = 20      # bounded sample: 2^20 (1/16 of the workload), scaled below
+        ev = self.evals[: 1 << nv]
+        t0 = time.perf_counter()
+        O.pcs_open(ev, False, nv, self.point[:nv], cap=1 << 23)
+        return (time.perf_counter() - t0) * (1 << (self.NV - nv))
+
+    cpu_sample = "commit+open of the first 2^20 evaluations (1/16 of the workload), time scaled x16"
+    cpu_returns_seconds = True
+    l2_note = "256 MiB L2 flush between steps; the 128 MiB input + 256 MiB codeword + 512 MiB oracle exceed L2 anyway"
+    flush = True
+
+
 def splitmix_raw(seed, n, start=0):
     with np.errstate(over="ignore"):
         i = np.arange(start + 1, start + n + 1, dtype=np.uint64)
@@ -250,13 +293,13 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dense4m", choices=["dense4m", "sumcheck20"])
+    ap.add_argument("--workload", default="dense4m", choices=["dense4m", "sumcheck20", "basefold24"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    wl = DenseWorkload() if args.workload == "dense4m" else SumcheckWorkload()
+    wl = {"dense4m": DenseWorkload, "sumcheck20": SumcheckWorkload, "basefold24": BasefoldWorkload}[args.workload]()
     W = max(args.warmup, 0)
     dtype = "u64 (Goldilocks / GoldilocksExt2 modular integers)"
 
@@ -276,7 +319,7 @@ def main():
         }))
         return
 
-    K = args.steps if args.steps is not None else (96 if args.workload == "dense4m" else 20)
+    K = args.steps if args.steps is not None else {"dense4m": 96, "sumcheck20": 20, "basefold24": 5}[args.workload]
     import torch
     import dpb200 as dp
     if not torch.cuda.is_available() or dp.device_count() <= 0:
@@ -372,7 +415,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_py as O   # cpu_baseline leg: the oracle is the checker/baseline, never the measured product
-        v, sec, cores = cpu_arm(wl, O, 1 if args.workload == "dense4m" else 5, 0)
+        v, sec, cores = cpu_arm(wl, O, 5 if args.workload == "sumcheck20" else 1, 0)
         cpu = {"value": v, "unit": "proofs/s", "cores": cores, "kind": "port",
                "sample": wl.cpu_sample + " (C++ restatement of the reference algorithm, not the Rust reference)"}
 
@@ -381,7 +424,8 @@ def main():
         v = whole_job_value(K, world, ms)
         pub = PUBLISHED.get(args.workload)
         out = {
-            "metric": "proofs/sec", "value": v, "unit": "proofs/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "metric": "proofs/sec" if args.workload != "basefold24" else "commit+open/sec", "value": v, "unit": "proofs/s" if args.workload != "basefold24" else "openings/s",
+            "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (v / pub) if (pub and world == 1) else None,
             "dtype": dtype, "data": "synthetic",
