@@ -424,3 +424,18 @@ class ZkmlContext:
             self.free()
         except Exception:
             pass
+
+
+def sumcheck_prove_batch_polys(T, mles, products, max_nv, label=b"m2vec"):
+    """IOPProverState::prove_batch_polys (devirgo split into T contiguous slices) through the C++ host mirror."""
+    H = host()
+    H.dph_sumcheck_prove_batch_polys.argtypes = [C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(ScProduct), C.c_uint32, C.c_uint32,
+                                                 C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    hs = (C.c_void_p * len(mles))(*[m.h for m in mles])
+    prods = make_products(products)
+    max_deg = max(len(p[1]) for p in products)
+    point = np.zeros((max_nv, 2), dtype=np.uint64)
+    msgs = np.zeros((max_nv, max_deg + 1, 2), dtype=np.uint64)
+    fin = np.zeros((len(mles), 2), dtype=np.uint64)
+    hcheck(H.dph_sumcheck_prove_batch_polys(T, hs, len(mles), prods, len(products), max_nv, label, _ptr(point), _ptr(msgs), _ptr(fin)))
+    return point, msgs, fin

@@ -215,3 +215,31 @@ extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_wo
     return 0;
     DPH_CATCH
 }
+
+// prove_batch_polys over T contiguous slices of the caller's device MLEs (views, no copies)
+extern "C" int dph_sumcheck_prove_batch_polys(uint32_t T, dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *products, uint32_t n_products,
+                                              uint32_t max_nv, const char *label, uint64_t *out_point, uint64_t *out_msgs, uint64_t *out_final) {
+    DPH_TRY
+    uint32_t logT = 0; while ((1u << logT) < T) logT++;
+    std::vector<VirtualPolynomial> polys;
+    for (uint32_t t = 0; t < T; t++) {
+        VirtualPolynomial vp(max_nv - logT);
+        std::vector<DeviceMle> views;
+        for (uint32_t i = 0; i < n_mles; i++) {
+            uint64_t len; int ext; check(dp_mle_info(mles[i], &len, &ext, nullptr));
+            uint64_t sl = len / T;
+            views.push_back(DeviceMle::wrap_device((char *)dp_mle_device_ptr(mles[i]) + (size_t)t * sl * (ext ? 16 : 8), sl, ext));
+        }
+        for (uint32_t p = 0; p < n_products; p++) { std::vector<DeviceMle> l; for (uint32_t j = 0; j < products[p].n_idx; j++) l.push_back(views.at(products[p].idx[j])); vp.add_mle_list(l, Ext(products[p].coef[0], products[p].coef[1])); }
+        polys.push_back(std::move(vp));
+    }
+    BasicTranscript tr(label);
+    auto res = IOPProverState::prove_batch_polys(T, std::move(polys), tr);
+    for (size_t i = 0; i < res.first.point.size(); i++) { out_point[2 * i] = res.first.point[i].c0; out_point[2 * i + 1] = res.first.point[i].c1; }
+    size_t k = 0;
+    for (auto &m : res.first.proofs) for (auto &e : m.evaluations) { out_msgs[2 * k] = e.c0; out_msgs[2 * k + 1] = e.c1; k++; }
+    const ExtVec &fin = res.second.get_mle_final_evaluations();
+    for (size_t i = 0; i < fin.size() && i < n_mles; i++) { out_final[2 * i] = fin[i].c0; out_final[2 * i + 1] = fin[i].c1; }
+    return 0;
+    DPH_CATCH
+}

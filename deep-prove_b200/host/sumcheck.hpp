@@ -129,6 +129,67 @@ class IOPProverState {
         st.poly_ = std::move(poly);
         return {std::move(proof), std::move(st)};
     }
+    // IOPProverState::prove_batch_polys(max_thread_id, polys, transcript) (sumcheck/src/prover.rs:37-321): the devirgo
+    // split with one device sumcheck per slice.  Same proof as prove_parallel on the un-split polynomial.
+    template <class T>
+    static std::pair<IOPProof, IOPProverState> prove_batch_polys(size_t max_thread_id, std::vector<VirtualPolynomial> polys, T &transcript) {
+        if (polys.empty() || polys.size() != max_thread_id || (max_thread_id & (max_thread_id - 1))) throw Error(DP_ERR_INVALID, "prove_batch_polys: polys.len() must equal a power-of-two max_thread_id");
+        size_t nv = polys[0].aux_info.max_num_variables, deg = polys[0].aux_info.max_degree, logT = 0;
+        while (((size_t)1 << logT) < max_thread_id) logT++;
+        for (auto &p : polys) if (p.aux_info.max_num_variables != nv || p.aux_info.max_degree != deg) throw Error(DP_ERR_INVALID, "prove_batch_polys: polys differ in (max_num_variables, max_degree)");
+        IOPProof proof; IOPProverState st;
+        if (nv == 0) return {std::move(proof), std::move(st)};
+        transcript.append_usize(nv + logT);
+        transcript.append_usize(deg);
+        struct H { dp_sc *h = nullptr; ~H() { if (h) dp_sc_destroy(h); } };
+        std::vector<H> hs(polys.size());
+        std::vector<std::vector<dp_mle *>> mh(polys.size());
+        for (size_t t = 0; t < polys.size(); t++) {
+            for (auto &m : polys[t].flattened_ml_extensions) mh[t].push_back(m.handle());
+            check(dp_sc_create(mh[t].data(), (uint32_t)mh[t].size(), polys[t].products.data(), (uint32_t)polys[t].products.size(), (uint32_t)nv, (uint32_t)deg, &hs[t].h));
+        }
+        std::vector<u64> buf(2 * (deg + 1));
+        Ext challenge; bool have = false;
+        for (size_t i = 0; i < nv; i++) {
+            IOPProverMessage msg; msg.evaluations.assign(deg + 1, Ext::zero());
+            u64 c[2] = {challenge.c0, challenge.c1};
+            for (auto &h : hs) { check(dp_sc_round(h.h, have ? c : nullptr, buf.data())); for (size_t k = 0; k <= deg; k++) msg.evaluations[k] += Ext(buf[2 * k], buf[2 * k + 1]); }
+            transcript.append_field_element_exts(msg.evaluations);
+            proof.proofs.push_back(std::move(msg));
+            challenge = transcript.get_and_append_challenge("Internal round"); have = true;
+            st.challenges.push_back(challenge);
+        }
+        size_t n_mles = mh[0].size();
+        std::vector<ExtVec> residual(n_mles);                 // merge_sumcheck_polys (util.rs:215-243)
+        u64 c[2] = {challenge.c0, challenge.c1};
+        for (auto &h : hs) { std::vector<u64> fin(2 * n_mles); check(dp_sc_finish(h.h, c, fin.data())); for (size_t i = 0; i < n_mles; i++) residual[i].push_back(Ext(fin[2 * i], fin[2 * i + 1])); }
+        if (logT == 0) { for (size_t i = 0; i < n_mles; i++) st.finals_.push_back(residual[i][0]); proof.point = st.challenges; return {std::move(proof), std::move(st)}; }
+        VirtualPolynomial merged(logT);
+        std::vector<DeviceMle> mm; for (auto &r : residual) mm.push_back(DeviceMle::from_evaluations_ext_vec(r));
+        for (auto &pr : polys[0].products) { std::vector<DeviceMle> l; for (uint32_t j = 0; j < pr.n_idx; j++) l.push_back(mm[pr.idx[j]]); merged.add_mle_list(l, Ext(pr.coef[0], pr.coef[1])); }
+        merged.aux_info.max_degree = deg;
+        // MLE numbering of `merged` follows first use in the products, as in polys[0]; map back for the final evaluations
+        std::vector<dp_mle *> h2; for (auto &m : merged.flattened_ml_extensions) h2.push_back(m.handle());
+        dp_sc *s2 = nullptr;
+        check(dp_sc_create(h2.data(), (uint32_t)h2.size(), merged.products.data(), (uint32_t)merged.products.size(), (uint32_t)logT, (uint32_t)deg, &s2));
+        H g2; g2.h = s2;
+        have = false;
+        for (size_t i = 0; i < logT; i++) {
+            u64 cc[2] = {challenge.c0, challenge.c1};
+            check(dp_sc_round(s2, have ? cc : nullptr, buf.data()));
+            IOPProverMessage msg; for (size_t k = 0; k <= deg; k++) msg.evaluations.push_back(Ext(buf[2 * k], buf[2 * k + 1]));
+            transcript.append_field_element_exts(msg.evaluations);
+            proof.proofs.push_back(std::move(msg));
+            challenge = transcript.get_and_append_challenge("Internal round"); have = true;
+            st.challenges.push_back(challenge);
+        }
+        u64 cc[2] = {challenge.c0, challenge.c1};
+        std::vector<u64> fin(2 * h2.size()); check(dp_sc_finish(s2, cc, fin.data()));
+        ExtVec f2; for (size_t i = 0; i < h2.size(); i++) f2.push_back(Ext(fin[2 * i], fin[2 * i + 1]));
+        for (size_t i = 0; i < n_mles; i++) { Ext v; for (size_t k = 0; k < h2.size(); k++) if (h2[k] == mm[i].handle()) v = f2[k]; st.finals_.push_back(v); }
+        proof.point = st.challenges;
+        return {std::move(proof), std::move(st)};
+    }
   private:
     dp_sc *sc_ = nullptr;
     ExtVec finals_;

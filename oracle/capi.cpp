@@ -245,3 +245,24 @@ void dpo_synthetic_mlp(u32 n_layers, u32 width, u64 seed, int64_t *weights /* n_
 }
 void dpo_synthetic_input(u32 width, u64 seed, int64_t *out) { auto v = synthetic_input(width, seed); memcpy(out, v.data(), 8 * v.size()); }
 }
+
+// prove_batch_polys: the caller passes the FULL MLEs; they are split into T contiguous slices here
+extern "C" int dpo_sumcheck_prove_batch(u32 T, u32 n_mles, const u64 *const *data, const u64 *lens, const int *is_ext, u32 n_products, const u64 *coefs,
+                                         const u32 *deg, const u32 *idx, u32 max_nv, const char *label, u64 *out_point, u64 *out_msgs, u64 *out_final) {
+    try {
+        u32 logT = (u32)ceil_log2(T);
+        std::vector<VirtualPolynomial> polys;
+        for (u32 t = 0; t < T; t++) {
+            std::vector<const u64 *> d(n_mles); std::vector<u64> l(n_mles);
+            for (u32 i = 0; i < n_mles; i++) { l[i] = lens[i] / T; d[i] = data[i] + (size_t)t * l[i] * (is_ext[i] ? 2 : 1); }
+            polys.push_back(mk_vp(n_mles, d.data(), l.data(), is_ext, n_products, coefs, deg, idx, max_nv - logT));
+        }
+        Transcript t(label);
+        auto res = sumcheck_prove_batch_polys(polys, t);
+        for (size_t i = 0; i < res.first.point.size(); i++) put_e(out_point, i, res.first.point[i]);
+        size_t k = 0;
+        for (auto &m : res.first.proofs) for (E e : m) put_e(out_msgs, k++, e);
+        for (size_t i = 0; i < res.second.size(); i++) put_e(out_final, i, res.second[i]);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}

@@ -189,6 +189,49 @@ static inline std::pair<IOPProof, std::vector<E>> sumcheck_prove(const VirtualPo
     return {proof, st.final_evaluations()};
 }
 
+// IOPProverState::prove_batch_polys (prover.rs:37-321) + merge_sumcheck_polys (util.rs:215-243): the "devirgo"
+// split.  polys[t] is thread t's slice (the top log T variables fixed to t); every round the T messages are summed
+// before Fiat-Shamir; after num_variables rounds the T residual values per MLE form a log T-variable polynomial that
+// is finished with log T ordinary rounds.  Produces the same proof as sumcheck_prove on the un-split polynomial.
+static inline std::pair<IOPProof, std::vector<E>> sumcheck_prove_batch_polys(const std::vector<VirtualPolynomial> &polys, Transcript &t) {
+    size_t T = polys.size();
+    if (T == 0 || (T & (T - 1))) throw std::runtime_error("prove_batch_polys: number of polys must be a power of two");
+    size_t logT = ceil_log2(T), nv = polys[0].max_num_variables, deg = polys[0].max_degree;
+    for (auto &p : polys) if (p.max_num_variables != nv || p.max_degree != deg) throw std::runtime_error("prove_batch_polys: polys differ in (num_variables, degree)");
+    IOPProof proof;
+    if (nv == 0) return {proof, {}};
+    t.append_usize(nv + logT);
+    t.append_usize(deg);
+    std::vector<IOPProverState> st; for (auto &p : polys) st.emplace_back(p);
+    E chal; bool have = false;
+    for (size_t i = 0; i < nv; i++) {
+        std::vector<E> msg(deg + 1, E::zero());
+        for (auto &s : st) { auto m = s.prove_round(have ? &chal : nullptr); for (size_t k = 0; k <= deg; k++) msg[k] = e_add(msg[k], m[k]); }
+        t.append_field_element_exts(msg);
+        proof.proofs.push_back(msg);
+        chal = t.get_and_append_challenge("Internal round"); have = true;
+    }
+    for (auto &s : st) s.finish(chal);
+    std::vector<E> point = st[0].challenges;
+    if (logT == 0) { proof.point = point; return {proof, st[0].final_evaluations()}; }
+    // merge_sumcheck_polys
+    VirtualPolynomial merged(logT); merged.max_degree = deg; merged.products = polys[0].products;
+    size_t n_mles = polys[0].mles.size();
+    for (size_t i = 0; i < n_mles; i++) { std::vector<E> v; for (auto &s : st) v.push_back(s.work[i]->get(0)); merged.mles.push_back(std::make_shared<MLE>(MLE::from_ext(logT, v))); }
+    IOPProverState s2(merged);
+    have = false;
+    for (size_t i = 0; i < logT; i++) {
+        auto msg = s2.prove_round(have ? &chal : nullptr);
+        t.append_field_element_exts(msg);
+        proof.proofs.push_back(msg);
+        chal = t.get_and_append_challenge("Internal round"); have = true;
+    }
+    s2.finish(chal);
+    point.insert(point.end(), s2.challenges.begin(), s2.challenges.end());
+    proof.point = point;
+    return {proof, s2.final_evaluations()};
+}
+
 // interpolate_uni_poly (util.rs:148-199): evaluate the degree-(n-1) poly through (i, p_i) at x
 static inline E interpolate_uni_poly(const std::vector<E> &p, E x) {
     size_t n = p.size();

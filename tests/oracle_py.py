@@ -339,3 +339,17 @@ def zkml_prove(n_layers, width, seed_model, seed_input, label=b"m2vec", cap=1 <<
     if rc:
         raise RuntimeError(lib().dpo_last_error().decode())
     return (out[: n.value].copy() if want_proof else None), (ms[0], ms[1])
+
+
+def sumcheck_prove_batch(T, mles, products, max_nv, label=b"m2vec"):
+    """prove_batch_polys over T contiguous slices of the given full MLEs"""
+    arrs, data, lens, is_ext, coefs, deg, idx = _vp_args(mles, products)
+    max_deg = int(deg.max())
+    point = np.zeros((max_nv, 2), dtype=np.uint64)
+    msgs = np.zeros((max_nv, max_deg + 1, 2), dtype=np.uint64)
+    fin = np.zeros((len(mles), 2), dtype=np.uint64)
+    rc = lib().dpo_sumcheck_prove_batch(C.c_uint32(T), C.c_uint32(len(mles)), data, ptr(lens), ptr(is_ext), C.c_uint32(len(products)),
+                                        ptr(coefs), ptr(deg), ptr(idx), C.c_uint32(max_nv), label, ptr(point), ptr(msgs), ptr(fin))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return point, msgs, fin

@@ -187,3 +187,13 @@ def test_sumcheck_protocol_errors(gpu):
         sc.round(c)
     assert e.value.code == gpu.DP_ERR_STATE and "Prover is not active" in str(e.value)
     sc.finish(c)
+
+
+@pytest.mark.parametrize("nv,shape,T", [(6, [["b", "e"]], 2), (9, [["e", "e", "e"], ["b", "e"]], 4), (12, [["b", "b", "b"]], 8)])
+def test_prove_batch_polys(gpu, nv, shape, T):
+    """a10: devirgo split on device == oracle == prove_parallel on the un-split polynomial"""
+    mles, products = rand_vp(5000 + nv, nv, shape)
+    dm = upload_all(gpu, mles)
+    point, msgs, fin = gpu.sumcheck_prove_batch_polys(T, dm, products, nv)
+    opoint, omsgs, ofin = O.sumcheck_prove(mles, products, nv)
+    assert (point == opoint).all() and (msgs == omsgs).all() and (fin == ofin).all()

@@ -172,3 +172,12 @@ def test_fixed_challenge_rounds_match_transcript_run():
     point, msgs, fin = O.sumcheck_prove(mles, products, 4)
     msgs2, fin2 = O.sumcheck_rounds_fixed(mles, products, 4, point)
     assert (msgs == msgs2).all() and (fin == fin2).all()
+
+
+def test_prove_batch_polys_equals_prove_parallel():
+    """zkml/src/model/mod.rs:987-993 (test_model_sequential): the devirgo split produces the same proof"""
+    for nv, shape, T in [(5, [["b", "e"]], 2), (6, [["e", "e", "e"], ["b", "e"]], 4), (4, [["b", "b", "b"]], 4), (3, [["e"]], 1)]:
+        mles, products = rand_vp(77 + nv, nv, shape)
+        p1, m1, f1 = O.sumcheck_prove(mles, products, nv)
+        p2, m2, f2 = O.sumcheck_prove_batch(T, mles, products, nv)
+        assert (p1 == p2).all() and (m1 == m2).all() and (f1 == f2).all()
