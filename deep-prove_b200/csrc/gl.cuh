@@ -16,6 +16,55 @@ static constexpr u64 GL_P = 0xFFFFFFFF00000001ULL;
 static constexpr u64 GL_EPS = 0xFFFFFFFFULL;  // 2^64 mod p
 
 GL_HD u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
+
+// hi*2^64 + lo  ->  "weak" representative in [0, 2^64) (not necessarily < p)
+__device__ __forceinline__ u64 gl_reduce128_weak(u64 lo, u64 hi) {
+    u64 r;
+    asm("{\n\t.reg .u64 t0, t1, m64;\n\t.reg .u32 hl, hh, m;\n\t"
+        "mov.b64 {hl, hh}, %2;\n\t"
+        "cvt.u64.u32 m64, hh;\n\t"
+        "sub.cc.u64 t0, %1, m64;\n\t"                          // lo - hi_hi          (2^96 == -1)
+        "subc.u32 m, 0, 0;\n\t"
+        "cvt.u64.u32 m64, m;\n\t"
+        "sub.u64 t0, t0, m64;\n\t"                             // borrow: - EPS, cannot underflow
+        "mul.wide.u32 t1, hl, 0xFFFFFFFF;\n\t"                 // hi_lo * (2^32 - 1)   (2^64 == 2^32 - 1)
+        "add.cc.u64 t0, t0, t1;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "cvt.u64.u32 m64, m;\n\t"
+        "add.u64 %0, t0, m64;\n\t}"                            // carry: + EPS, cannot carry again
+        : "=l"(r) : "l"(lo), "l"(hi));
+    return r;
+}
+__device__ __forceinline__ u64 gl_canon_weak(u64 r) {          // [0, 2^64) -> [0, p)
+    u64 t; u32 c;
+    asm("{\n\tadd.cc.u64 %0, %2, 0xFFFFFFFF;\n\taddc.u32 %1, 0, 0;\n\t}" : "=l"(t), "=r"(c) : "l"(r));
+    return c ? t : r;
+}
+#ifdef __CUDA_ARCH__
+// Device fast paths: explicit carry chains (add.cc / addc / sub.cc / subc).  The compiler's lowering of the
+// compare-and-select formulation spends ~2x the instructions, almost all on the half-rate ALU pipe, and the
+// Poseidon2 / Ext-multiply kernels are ALU-bound (ncu: ALU pipe 73 % active, DRAM 0.2 %).
+// After add.cc the carry flag is 0/1 and `subc m, 0, 0` yields 0 - carry (0 or 0xFFFFFFFF == 2^64 mod p);
+// after sub.cc it yields 0 - borrow.
+__device__ __forceinline__ u64 gl_add(u64 a, u64 b) {          // a, b < p  ->  < p
+    u64 s, t; u32 c;
+    asm("{\n\t.reg .u32 c1;\n\t"
+        "add.cc.u64 %0, %3, %4;\n\t"
+        "addc.u32 c1, 0, 0;\n\t"
+        "add.cc.u64 %1, %0, 0xFFFFFFFF;\n\t"                  // s + EPS == s - p (mod 2^64); carries iff s >= p
+        "addc.u32 %2, c1, 0;\n\t}" : "=l"(s), "=l"(t), "=r"(c) : "l"(a), "l"(b));
+    return c ? t : s;                                          // a + b >= p  <=>  either addition carried
+}
+__device__ __forceinline__ u64 gl_sub(u64 a, u64 b) {          // a, b < p  ->  < p
+    u64 d; u32 m;
+    asm("{\n\tsub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;\n\t}" : "=l"(d), "=r"(m) : "l"(a), "l"(b));
+    return d - (u64)m;                                         // borrow: + p == - EPS (mod 2^64)
+}
+__device__ __forceinline__ u64 gl_reduce128(u64 lo, u64 hi) { return gl_canon_weak(gl_reduce128_weak(lo, hi)); }
+__device__ __forceinline__ void gl_mul_wide(u64 a, u64 b, u64 &lo, u64 &hi) { lo = a * b; hi = __umul64hi(a, b); }
+GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0ULL; }
+GL_HD u64 gl_dbl(u64 a) { return gl_add(a, a); }
+#else
 GL_HD u64 gl_add(u64 a, u64 b) {
     u64 s = a + b;
     // a,b < p: on wrap the true sum is s + 2^64, and (s + 2^64) - p == s - p (mod 2^64)
@@ -26,11 +75,7 @@ GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0ULL; }
 GL_HD u64 gl_dbl(u64 a) { return gl_add(a, a); }
 
 GL_HD void gl_mul_wide(u64 a, u64 b, u64 &lo, u64 &hi) {
-#ifdef __CUDA_ARCH__
-    lo = a * b; hi = __umul64hi(a, b);
-#else
     unsigned __int128 t = (unsigned __int128)a * b; lo = (u64)t; hi = (u64)(t >> 64);
-#endif
 }
 // reduce hi*2^64 + lo (any 128-bit value) to canonical form: 2^64 = 2^32 - 1, 2^96 = -1 (mod p)
 GL_HD u64 gl_reduce128(u64 lo, u64 hi) {
@@ -42,6 +87,7 @@ GL_HD u64 gl_reduce128(u64 lo, u64 hi) {
     if (r < t1) r += GL_EPS;                 // carry: 2^64 == EPS (mod p), cannot overflow again
     return r >= GL_P ? r - GL_P : r;
 }
+#endif
 GL_HD u64 gl_mul(u64 a, u64 b) { u64 lo, hi; gl_mul_wide(a, b, lo, hi); return gl_reduce128(lo, hi); }
 GL_HD u64 gl_sqr(u64 a) { return gl_mul(a, a); }
 GL_HD u64 gl_mul7(u64 a) { u64 lo, hi; gl_mul_wide(a, 7ULL, lo, hi); return gl_reduce128(lo, hi); }
@@ -63,6 +109,32 @@ GL_HD bool e_eq(gle a, gle b) { return a.c0 == b.c0 && a.c1 == b.c1; }
 // (a0 + a1 X)(b0 + b1 X) = (a0 b0 + 7 a1 b1) + (a0 b1 + a1 b0) X.
 // The two limbs are each ONE reduction of a <=131-bit sum of raw 128-bit products (fewer reductions
 // than 4 reduced multiplies; same canonical result because the arithmetic is exact).
+#ifdef __CUDA_ARCH__
+// top*2^128 + hi*2^64 + lo with top < 2^31.  2^128 = (2^32-1)^2 = -2^32 (mod p)  =>  subtract top << 32.
+__device__ __forceinline__ u64 gl_reduce160(u64 lo, u64 hi, u32 top) {
+    u64 r = gl_reduce128_weak(lo, hi), d; u32 m;
+    u64 x = (u64)top << 32;
+    asm("{\n\tsub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;\n\t}" : "=l"(d), "=r"(m) : "l"(r), "l"(x));
+    return gl_canon_weak(d - (u64)m);                          // borrow: - EPS; r < x < 2^63 here, so no second borrow
+}
+// (h:l) += a*b as a 160-bit accumulator (l, h, t)
+__device__ __forceinline__ void gl_mac160(u64 &l, u64 &h, u32 &t, u64 a, u64 b) {
+    u64 pl = a * b, ph = __umul64hi(a, b);
+    asm("{\n\tadd.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;\n\t}" : "+l"(l), "+l"(h), "+r"(t) : "l"(pl), "l"(ph));
+}
+__device__ __forceinline__ gle e_mul(gle a, gle b) {
+    // c1 = a0 b1 + a1 b0 : one reduction of the 129-bit sum
+    u64 l = a.c0 * b.c1, h = __umul64hi(a.c0, b.c1); u32 t = 0;
+    gl_mac160(l, h, t, a.c1, b.c0);
+    u64 c1 = gl_reduce160(l, h, t);
+    // c0 = a0 b0 + 7 (a1 b1) : reduce a1 b1 to 64 bits (weak), times 7 is a 67-bit addend
+    u64 w = gl_reduce128_weak(a.c1 * b.c1, __umul64hi(a.c1, b.c1));
+    l = a.c0 * b.c0; h = __umul64hi(a.c0, b.c0); t = 0;
+    gl_mac160(l, h, t, w, 7ULL);
+    u64 c0 = gl_reduce160(l, h, t);
+    return e_make(c0, c1);
+}
+#else
 GL_HD u64 gl_reduce160(u64 lo, u64 hi, u64 top) {  // top*2^128 + hi*2^64 + lo, top < 2^32
     // 2^128 = (2^32-1)^2 mod p = 2^64 - 2^33 + 1 = -2^32 (mod p)  => top*2^128 = -(top << 32)
     u64 r = gl_reduce128(lo, hi);
@@ -84,6 +156,7 @@ GL_HD gle e_mul(gle a, gle b) {
     u64 c0 = gl_reduce160(lo, hi, top);
     return e_make(c0, c1);
 }
+#endif
 GL_HD gle e_mul_base(gle a, u64 b) { return e_make(gl_mul(a.c0, b), gl_mul(a.c1, b)); }
 GL_HD gle e_sqr(gle a) { return e_mul(a, a); }
 GL_HD gle e_inv(gle a) {

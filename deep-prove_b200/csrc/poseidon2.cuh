@@ -18,42 +18,78 @@ static inline cudaError_t p2_upload_constants(const u64 *ext /*64*/, const u64 *
     return cudaMemcpyToSymbol(c_p2_diag, diag, sizeof(u64) * 8);
 }
 
-__device__ __forceinline__ u64 p2_pow7(u64 x) { u64 x2 = gl_sqr(x), x4 = gl_sqr(x2); return gl_mul(gl_mul(x2, x), x4); }
-// p3 MDSMat4 = circ(2,3,1,1) on four lanes
-__device__ __forceinline__ void p2_mat4(u64 &x0, u64 &x1, u64 &x2, u64 &x3) {
-    u64 t01 = gl_add(x0, x1), t23 = gl_add(x2, x3), t = gl_add(t01, t23);
-    u64 a = gl_add(t, x1), b = gl_add(t, x3);
-    u64 n3 = gl_add(b, gl_dbl(x0)), n1 = gl_add(a, gl_dbl(x2));
-    u64 n0 = gl_add(a, t01), n2 = gl_add(b, t23);
-    x0 = n0; x1 = n1; x2 = n2; x3 = n3;
+// ---- "weak" arithmetic: state words live in [0, 2^64) (not reduced below p) between operations ----------------
+// The permutation is ALU-bound, so it is written to minimise instructions: products are reduced to a weak 64-bit
+// value (11 instructions instead of 16 + canonicalisation), the linear layers accumulate in 64+32-bit "wide"
+// sums that are folded once per output, and the internal-layer multiply-add is one 128-bit accumulate + one
+// reduction.  Only the four digest words are canonicalised at the end.  Every step is exact modular arithmetic,
+// so the digests are bit-identical to the canonical formulation.
+struct p2w { u64 lo; u32 hi; };                                                   // value = lo + hi * 2^64
+__device__ __forceinline__ u64 w_mul(u64 a, u64 b) { return gl_reduce128_weak(a * b, __umul64hi(a, b)); }
+__device__ __forceinline__ u64 w_add_canon(u64 a, u64 c) {                        // a weak, c < p  ->  weak
+    u64 r; asm("{\n\t.reg .u32 m;\n\t.reg .u64 m64;\n\tadd.cc.u64 %0, %1, %2;\n\tsubc.u32 m, 0, 0;\n\tcvt.u64.u32 m64, m;\n\tadd.u64 %0, %0, m64;\n\t}" : "=l"(r) : "l"(a), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u64 w_add(u64 a, u64 b) {                              // weak + weak -> weak (two possible wraps)
+    u64 r; asm("{\n\t.reg .u32 m;\n\t.reg .u64 m64;\n\tadd.cc.u64 %0, %1, %2;\n\tsubc.u32 m, 0, 0;\n\tcvt.u64.u32 m64, m;\n\t"
+               "add.cc.u64 %0, %0, m64;\n\tsubc.u32 m, 0, 0;\n\tcvt.u64.u32 m64, m;\n\tadd.u64 %0, %0, m64;\n\t}" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ p2w ww(u64 a) { p2w r; r.lo = a; r.hi = 0; return r; }
+__device__ __forceinline__ p2w ww_add(p2w a, p2w b) { asm("{\n\tadd.cc.u64 %0, %0, %2;\n\taddc.u32 %1, %1, %3;\n\t}" : "+l"(a.lo), "+r"(a.hi) : "l"(b.lo), "r"(b.hi)); return a; }
+__device__ __forceinline__ p2w ww_addu(p2w a, u64 b) { asm("{\n\tadd.cc.u64 %0, %0, %2;\n\taddc.u32 %1, %1, 0;\n\t}" : "+l"(a.lo), "+r"(a.hi) : "l"(b)); return a; }
+__device__ __forceinline__ u64 ww_fold(p2w a) {                                   // hi <= a few dozen: hi * 2^64 == hi * EPS
+    u64 r; asm("{\n\t.reg .u64 t, m64;\n\t.reg .u32 m;\n\tmul.wide.u32 t, %2, 0xFFFFFFFF;\n\tadd.cc.u64 %0, %1, t;\n\tsubc.u32 m, 0, 0;\n\tcvt.u64.u32 m64, m;\n\tadd.u64 %0, %0, m64;\n\t}" : "=l"(r) : "l"(a.lo), "r"(a.hi));
+    return r;
+}
+// a * c + (sum as wide) -> weak, one reduction  (internal layer: s[i] * diag[i] + sum)
+__device__ __forceinline__ u64 w_mul_add(u64 a, u64 c, p2w sum) {
+    u64 lo = a * c, hi = __umul64hi(a, c);
+    asm("{\n\t.reg .u64 h64;\n\tcvt.u64.u32 h64, %3;\n\tadd.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, h64;\n\t}" : "+l"(lo), "+l"(hi) : "l"(sum.lo), "r"(sum.hi));
+    return gl_reduce128_weak(lo, hi);
+}
+__device__ __forceinline__ u64 p2_pow7(u64 x) { u64 x2 = w_mul(x, x), x4 = w_mul(x2, x2); return w_mul(w_mul(x2, x), x4); }
+// p3 MDSMat4 = circ(2,3,1,1) on each half, then state[i] += column sums: out[i] = 2 n[i] + n[i ^ 4]
+__device__ __forceinline__ void p2_mat4w(u64 x0, u64 x1, u64 x2, u64 x3, p2w &n0, p2w &n1, p2w &n2, p2w &n3) {
+    p2w t01 = ww_addu(ww(x0), x1), t23 = ww_addu(ww(x2), x3), all = ww_add(t01, t23);
+    p2w a1 = ww_addu(all, x1), a3 = ww_addu(all, x3);
+    n0 = ww_add(a1, t01);                       // 2x0 + 3x1 + x2 + x3
+    n1 = ww_addu(ww_addu(a1, x2), x2);          // x0 + 2x1 + 3x2 + x3
+    n2 = ww_add(a3, t23);                       // x0 + x1 + 2x2 + 3x3
+    n3 = ww_addu(ww_addu(a3, x0), x0);          // 3x0 + x1 + x2 + 2x3
 }
 __device__ __forceinline__ void p2_mds_light(u64 (&s)[8]) {
-    p2_mat4(s[0], s[1], s[2], s[3]); p2_mat4(s[4], s[5], s[6], s[7]);
+    p2w n[8];
+    p2_mat4w(s[0], s[1], s[2], s[3], n[0], n[1], n[2], n[3]);
+    p2_mat4w(s[4], s[5], s[6], s[7], n[4], n[5], n[6], n[7]);
 #pragma unroll
-    for (int k = 0; k < 4; k++) { u64 c = gl_add(s[k], s[k + 4]); s[k] = gl_add(s[k], c); s[k + 4] = gl_add(s[k + 4], c); }
+    for (int i = 0; i < 8; i++) s[i] = ww_fold(ww_add(ww_add(n[i], n[i]), n[i ^ 4]));
 }
-__device__ __forceinline__ void p2_permute(u64 (&s)[8]) {
+__device__ __forceinline__ void p2_permute(u64 (&s)[8]) {      // weak in, weak out
     p2_mds_light(s);
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = p2_pow7(gl_add(s[i], c_p2_ext[0][r][i]));
+        for (int i = 0; i < 8; i++) s[i] = p2_pow7(w_add_canon(s[i], c_p2_ext[0][r][i]));
         p2_mds_light(s);
     }
 #pragma unroll 1
     for (int r = 0; r < 22; r++) {
-        s[0] = p2_pow7(gl_add(s[0], c_p2_int[r]));
-        u64 sum = gl_add(gl_add(gl_add(s[0], s[1]), gl_add(s[2], s[3])), gl_add(gl_add(s[4], s[5]), gl_add(s[6], s[7])));
+        s[0] = p2_pow7(w_add_canon(s[0], c_p2_int[r]));
+        p2w sum = ww(s[0]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = gl_add(gl_mul(s[i], c_p2_diag[i]), sum);
+        for (int i = 1; i < 8; i++) sum = ww_addu(sum, s[i]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = w_mul_add(s[i], c_p2_diag[i], sum);
     }
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = p2_pow7(gl_add(s[i], c_p2_ext[1][r][i]));
+        for (int i = 0; i < 8; i++) s[i] = p2_pow7(w_add_canon(s[i], c_p2_ext[1][r][i]));
         p2_mds_light(s);
     }
 }
+
 // ---- lane-parallel variant: 8 consecutive lanes hold the 8 state words of ONE permutation ----------------
 // Used where a level has too few hashes to fill the GPU with one thread per hash (tree tops, witness-sized
 // trees): the dependent-instruction chain per permutation drops ~3x (every lane does one S-box in the full
@@ -64,23 +100,24 @@ __device__ __forceinline__ u64 p2x8_mds_light(u64 s, int lane8) {
     int g = lane8 & 4, r = lane8 & 3;
     u64 a = shfl8(s, g + ((r + 1) & 3)), b = shfl8(s, g + ((r + 2) & 3)), c = shfl8(s, g + ((r + 3) & 3));
     // row r of circ(2,3,1,1): 2 x_r + 3 x_{r+1} + x_{r+2} + x_{r+3}
-    u64 t = gl_add(gl_add(s, a), gl_add(b, c));
-    u64 o = gl_add(gl_add(t, s), gl_dbl(a));
-    return gl_add(gl_dbl(o), shfl8_xor(o, 4));     // state[i] += out[i] + out[i ^ 4]
+    p2w o = ww_addu(ww_addu(ww_addu(ww_addu(ww_addu(ww_addu(ww(s), s), a), a), a), b), c);
+    u64 of = ww_fold(o);
+    u64 partner = shfl8_xor(of, 4);
+    return ww_fold(ww_addu(ww_addu(ww(of), of), partner));     // state[i] += out[i] + out[i ^ 4]
 }
 __device__ __forceinline__ u64 p2x8_permute(u64 s, int lane8) {
     s = p2x8_mds_light(s, lane8);
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) { s = p2_pow7(gl_add(s, c_p2_ext[0][r][lane8])); s = p2x8_mds_light(s, lane8); }
+    for (int r = 0; r < 4; r++) { s = p2_pow7(w_add_canon(s, c_p2_ext[0][r][lane8])); s = p2x8_mds_light(s, lane8); }
     const u64 dg = c_p2_diag[lane8];
 #pragma unroll 1
     for (int r = 0; r < 22; r++) {
-        if (lane8 == 0) s = p2_pow7(gl_add(s, c_p2_int[r]));
-        u64 sum = gl_add(s, shfl8_xor(s, 1)); sum = gl_add(sum, shfl8_xor(sum, 2)); sum = gl_add(sum, shfl8_xor(sum, 4));
-        s = gl_add(gl_mul(s, dg), sum);
+        if (lane8 == 0) s = p2_pow7(w_add_canon(s, c_p2_int[r]));
+        u64 sum = w_add(s, shfl8_xor(s, 1)); sum = w_add(sum, shfl8_xor(sum, 2)); sum = w_add(sum, shfl8_xor(sum, 4));
+        s = w_mul_add(s, dg, ww(sum));
     }
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) { s = p2_pow7(gl_add(s, c_p2_ext[1][r][lane8])); s = p2x8_mds_light(s, lane8); }
+    for (int r = 0; r < 4; r++) { s = p2_pow7(w_add_canon(s, c_p2_ext[1][r][lane8])); s = p2x8_mds_light(s, lane8); }
     return s;
 }
 // lanes 0..3 pass x[lane] / y[lane] (lanes 4..7 pass anything); returns on lane k < 4 the digest word 3 - k
@@ -89,7 +126,7 @@ __device__ __forceinline__ u64 p2x8_compress(u64 xw, u64 yw, int lane8) {
     s = p2x8_permute(s, lane8);
     if (lane8 < 4) s = yw;
     s = p2x8_permute(s, lane8);
-    return s;    // lane k holds state[k]; digest = [s3, s2, s1, s0]
+    return gl_canon_weak(s);    // lane k holds state[k]; digest = [s3, s2, s1, s0]
 }
 
 // compress(x, y): absorb x -> permute -> overwrite rate with y -> permute -> [s3, s2, s1, s0]
@@ -98,5 +135,5 @@ __device__ __forceinline__ void p2_compress(const u64 x[4], const u64 y[4], u64 
     p2_permute(s);
     s[0] = y[0]; s[1] = y[1]; s[2] = y[2]; s[3] = y[3];
     p2_permute(s);
-    out[0] = s[3]; out[1] = s[2]; out[2] = s[1]; out[3] = s[0];
+    out[0] = gl_canon_weak(s[3]); out[1] = gl_canon_weak(s[2]); out[2] = gl_canon_weak(s[1]); out[3] = gl_canon_weak(s[0]);
 }
