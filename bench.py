@@ -222,7 +222,8 @@ class DenseWorkload:
         self.ctx.run_inference(self.x)
         dp.lib().dp_synchronize()
 
-    STREAMS = 12    # concurrent independent proofs per GPU (one host thread + CUDA stream + device arena each)
+    STREAMS = 16    # concurrent independent proofs per GPU (one host thread + CUDA stream + device arena each)
+    units_per_step = STREAMS   # one bench step = one batch of STREAMS inference inputs, each proved independently
 
     def step_resident(self, i):
         self.ctx.prove_trace()
@@ -231,16 +232,16 @@ class DenseWorkload:
         return self.ctx.prove(self.x)
 
     def run_resident(self, k, device):
-        self.ctx.prove_concurrent(min(self.STREAMS, k), k, device=device, e2e=False)
+        self.ctx.prove_concurrent(self.STREAMS, k * self.units_per_step, device=device, e2e=False)
 
     def run_e2e(self, k, device):
-        self.ctx.prove_concurrent(min(self.STREAMS, k), k, device=device, e2e=True)
+        self.ctx.prove_concurrent(self.STREAMS, k * self.units_per_step, device=device, e2e=True)
 
     def cpu_step(self, O, i):
         _, ms = O.zkml_prove(self.NL, self.W, self.SEED_MODEL, self.SEED_INPUT, want_proof=False)
         return ms[1] * 1e-3     # Prover::prove only; Context::generate (ms[0]) is setup
 
-    cpu_sample = "1 full proof of the same model and input per step (Context::generate not counted)"
+    cpu_sample = "1 full proof of the same model and input per CPU step, i.e. 1/16 of a GPU step (Context::generate not counted)"
     cpu_returns_seconds = True
     l2_note = ("%d proofs in flight per GPU: aggregate working set (~130 MB of weights/codewords/oracles/trees per proof) "
                "is >> the 126 MB L2; single-stream latency is measured with a 256 MiB L2 flush between proofs" % STREAMS)
@@ -319,7 +320,7 @@ def main():
         }))
         return
 
-    K = args.steps if args.steps is not None else {"dense4m": 96, "sumcheck20": 20, "basefold24": 5}[args.workload]
+    K = args.steps if args.steps is not None else {"dense4m": 6, "sumcheck20": 20, "basefold24": 5}[args.workload]
     import torch
     import dpb200 as dp
     if not torch.cuda.is_available() or dp.device_count() <= 0:
@@ -377,9 +378,9 @@ def main():
     latency_ms = None
     if hasattr(wl, "run_resident"):
         with ClockSampler(local_rank) as clk:
-            ms, launches = timed_many(wl.run_resident, K, max(W, 3) * wl.STREAMS)
+            ms, launches = timed_many(wl.run_resident, K, max(W, 3))
         clocks = clk.summary()
-        ms_e2e, _ = timed_many(wl.run_e2e, K, wl.STREAMS)
+        ms_e2e, _ = timed_many(wl.run_e2e, K, 1)
         lat, _ = timed(wl.step_resident, min(K, 10), 2)     # one proof at a time, L2 flushed between proofs
         latency_ms = lat / min(K, 10)
     else:
@@ -420,8 +421,9 @@ def main():
                "sample": wl.cpu_sample + " (C++ restatement of the reference algorithm, not the Rust reference)"}
 
     if rank == 0:
-        total = K * world
-        v = whole_job_value(K, world, ms)
+        ups = getattr(wl, "units_per_step", 1)
+        total = K * ups * world
+        v = whole_job_value(K * ups, world, ms)
         pub = PUBLISHED.get(args.workload)
         out = {
             "metric": "proofs/sec" if args.workload != "basefold24" else "commit+open/sec", "value": v, "unit": "proofs/s" if args.workload != "basefold24" else "openings/s",
@@ -431,9 +433,10 @@ def main():
             "dtype": dtype, "data": "synthetic",
             "config": {"workload": wl.name, "l2": wl.l2_note,
                        "parallelism": "replicas x%d GPUs (no data-path collective)%s" % (world, (", %d concurrent independent proofs per GPU" % wl.STREAMS) if hasattr(wl, "STREAMS") else ""),
+                       "proofs_per_step": ups,
                        "single_stream_latency_ms": latency_ms,
                        "baseline_note": "vs_baseline divides by 1/2.335 s (reference README: Dense 4M proving time 2335 ms, hardware and exact architecture not stated)"},
-            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": wl.h2d * ups, "d2h_bytes_per_step": wl.d2h * ups},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

@@ -29,9 +29,8 @@ __device__ __forceinline__ u64 gl_reduce128_weak(u64 lo, u64 hi) {
         "sub.u64 t0, t0, m64;\n\t"                             // borrow: - EPS, cannot underflow
         "mul.wide.u32 t1, hl, 0xFFFFFFFF;\n\t"                 // hi_lo * (2^32 - 1)   (2^64 == 2^32 - 1)
         "add.cc.u64 t0, t0, t1;\n\t"
-        "subc.u32 m, 0, 0;\n\t"
-        "cvt.u64.u32 m64, m;\n\t"
-        "add.u64 %0, t0, m64;\n\t}"                            // carry: + EPS, cannot carry again
+        "addc.u32 m, 0, 0;\n\t"                               // NB: subc after add.cc does NOT give -carry (borrow = !carry in hardware)
+        "mad.wide.u32 %0, m, 0xFFFFFFFF, t0;\n\t}"            // carry: + EPS, cannot carry again
         : "=l"(r) : "l"(lo), "l"(hi));
     return r;
 }
@@ -44,8 +43,9 @@ __device__ __forceinline__ u64 gl_canon_weak(u64 r) {          // [0, 2^64) -> [
 // Device fast paths: explicit carry chains (add.cc / addc / sub.cc / subc).  The compiler's lowering of the
 // compare-and-select formulation spends ~2x the instructions, almost all on the half-rate ALU pipe, and the
 // Poseidon2 / Ext-multiply kernels are ALU-bound (ncu: ALU pipe 73 % active, DRAM 0.2 %).
-// After add.cc the carry flag is 0/1 and `subc m, 0, 0` yields 0 - carry (0 or 0xFFFFFFFF == 2^64 mod p);
-// after sub.cc it yields 0 - borrow.
+// After add.cc, `addc c, 0, 0` yields the carry (0/1); after sub.cc, `subc m, 0, 0` yields 0 - borrow
+// (0 or 0xFFFFFFFF == 2^64 mod p).
+// after sub.cc it yields 0 - borrow.  The two flags are NOT interchangeable: use addc after add.cc, subc after sub.cc.
 __device__ __forceinline__ u64 gl_add(u64 a, u64 b) {          // a, b < p  ->  < p
     u64 s, t; u32 c;
     asm("{\n\t.reg .u32 c1;\n\t"

@@ -27,19 +27,19 @@ static inline cudaError_t p2_upload_constants(const u64 *ext /*64*/, const u64 *
 struct p2w { u64 lo; u32 hi; };                                                   // value = lo + hi * 2^64
 __device__ __forceinline__ u64 w_mul(u64 a, u64 b) { return gl_reduce128_weak(a * b, __umul64hi(a, b)); }
 __device__ __forceinline__ u64 w_add_canon(u64 a, u64 c) {                        // a weak, c < p  ->  weak
-    u64 r; asm("{\n\t.reg .u32 m;\n\t.reg .u64 m64;\n\tadd.cc.u64 %0, %1, %2;\n\tsubc.u32 m, 0, 0;\n\tcvt.u64.u32 m64, m;\n\tadd.u64 %0, %0, m64;\n\t}" : "=l"(r) : "l"(a), "l"(c));
+    u64 r; asm("{\n\t.reg .u32 c;\n\t.reg .u64 t;\n\tadd.cc.u64 t, %1, %2;\n\taddc.u32 c, 0, 0;\n\tmad.wide.u32 %0, c, 0xFFFFFFFF, t;\n\t}" : "=l"(r) : "l"(a), "l"(c));
     return r;
 }
 __device__ __forceinline__ u64 w_add(u64 a, u64 b) {                              // weak + weak -> weak (two possible wraps)
-    u64 r; asm("{\n\t.reg .u32 m;\n\t.reg .u64 m64;\n\tadd.cc.u64 %0, %1, %2;\n\tsubc.u32 m, 0, 0;\n\tcvt.u64.u32 m64, m;\n\t"
-               "add.cc.u64 %0, %0, m64;\n\tsubc.u32 m, 0, 0;\n\tcvt.u64.u32 m64, m;\n\tadd.u64 %0, %0, m64;\n\t}" : "=l"(r) : "l"(a), "l"(b));
+    u64 r; asm("{\n\t.reg .u32 c;\n\t.reg .u64 t, e;\n\tadd.cc.u64 t, %1, %2;\n\taddc.u32 c, 0, 0;\n\tmul.wide.u32 e, c, 0xFFFFFFFF;\n\t"
+               "add.cc.u64 t, t, e;\n\taddc.u32 c, 0, 0;\n\tmad.wide.u32 %0, c, 0xFFFFFFFF, t;\n\t}" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
 __device__ __forceinline__ p2w ww(u64 a) { p2w r; r.lo = a; r.hi = 0; return r; }
 __device__ __forceinline__ p2w ww_add(p2w a, p2w b) { asm("{\n\tadd.cc.u64 %0, %0, %2;\n\taddc.u32 %1, %1, %3;\n\t}" : "+l"(a.lo), "+r"(a.hi) : "l"(b.lo), "r"(b.hi)); return a; }
 __device__ __forceinline__ p2w ww_addu(p2w a, u64 b) { asm("{\n\tadd.cc.u64 %0, %0, %2;\n\taddc.u32 %1, %1, 0;\n\t}" : "+l"(a.lo), "+r"(a.hi) : "l"(b)); return a; }
 __device__ __forceinline__ u64 ww_fold(p2w a) {                                   // hi <= a few dozen: hi * 2^64 == hi * EPS
-    u64 r; asm("{\n\t.reg .u64 t, m64;\n\t.reg .u32 m;\n\tmul.wide.u32 t, %2, 0xFFFFFFFF;\n\tadd.cc.u64 %0, %1, t;\n\tsubc.u32 m, 0, 0;\n\tcvt.u64.u32 m64, m;\n\tadd.u64 %0, %0, m64;\n\t}" : "=l"(r) : "l"(a.lo), "r"(a.hi));
+    u64 r; asm("{\n\t.reg .u64 t;\n\t.reg .u32 c;\n\tmul.wide.u32 t, %2, 0xFFFFFFFF;\n\tadd.cc.u64 t, %1, t;\n\taddc.u32 c, 0, 0;\n\tmad.wide.u32 %0, c, 0xFFFFFFFF, t;\n\t}" : "=l"(r) : "l"(a.lo), "r"(a.hi));
     return r;
 }
 // a * c + (sum as wide) -> weak, one reduction  (internal layer: s[i] * diag[i] + sum)
