@@ -1,0 +1,148 @@
+"""One sumcheck proof sharded over ranks (one process per GPU): the devirgo split across GPUs.
+
+Reference: `IOPProverState::prove_batch_polys` (sumcheck/src/prover.rs:37-321) splits a virtual polynomial into
+`max_thread_id` contiguous index ranges (= fixes the top log T variables), lets every thread run the first
+nv - log T rounds on its range, sums the per-thread round messages through channels (prover.rs:150-170) and finishes
+the last log T rounds on the merged residuals (`merge_sumcheck_polys`, util.rs:215-243).  The transcript sees
+nv (total) and the degree, then one summed message per round, so the proof is byte-identical to `prove_parallel`
+on the unsplit polynomial (zkml/src/model/mod.rs:987-993 asserts exactly that).
+
+Here a "thread" is a rank.  Rank g owns elements [g*n/G, (g+1)*n/G) of every MLE, resident on its own GPU; a round is
+one local device launch (dp_sc_round) plus ONE all-gather of (deg+1) Ext values (16*(deg+1) bytes per rank) -- the
+only exchange the path has.  Every rank then adds the G partial messages mod p and runs the same Fiat-Shamir
+transcript, so no challenge broadcast is needed (the sponge is deterministic and ~2 us per permutation on the host).
+After the local rounds the G residual values per MLE are all-gathered and the last log G rounds run replicated.
+
+The exchange is injected (`allgather`) so the same code runs over NCCL (device tensors over NVLink), over gloo
+(CPU tests) or in-process; the per-slice engine is injected as well (product: the CUDA library's dp_sc_*).
+"""
+import numpy as np
+
+P = 0xFFFFFFFF00000001
+
+
+def _sum_mod_p(parts):
+    """parts: [world, k, 2] uint64 canonical -> [k, 2] uint64 (component-wise sum mod p; k is tiny: deg+1 or #MLEs)"""
+    parts = np.asarray(parts, dtype=np.uint64)
+    out = np.zeros(parts.shape[1:], dtype=np.uint64)
+    for idx in np.ndindex(*out.shape):
+        out[idx] = sum(int(parts[(g,) + idx]) for g in range(parts.shape[0])) % P
+    return out
+
+
+class TorchAllGather:
+    """all-gather of a small uint64 array over a torch.distributed process group (NCCL: device tensors; gloo: CPU)."""
+
+    def __init__(self, dist, device=None, group=None):
+        import torch
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+
+    def __call__(self, words):
+        t = self.torch
+        w = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1)
+        send = t.from_numpy(w.view(np.int64)).to(self.device)
+        recv = t.empty(self.world * w.size, dtype=t.int64, device=self.device)
+        self.dist.all_gather_into_tensor(recv, send, group=self.group)
+        return recv.cpu().numpy().view(np.uint64).reshape(self.world, *np.shape(words))
+
+
+def shard_range(n, rank, world):
+    """contiguous index range owned by `rank` (the top log2(world) variables select the rank)"""
+    if world & (world - 1) or n % world:
+        raise ValueError("world size must be a power of two dividing the MLE length")
+    per = n // world
+    return rank * per, (rank + 1) * per
+
+
+def prove_sharded(make_engine, local_mles, products, nv_total, max_deg, rank, world, allgather, transcript):
+    """Distributed `prove_batch_polys` with max_thread_id = world.
+
+    make_engine(mles, products, nv, max_deg) -> object with .round(challenge|None) -> [max_deg+1, 2] and
+    .finish(challenge) -> [n_mles, 2]   (dpb200.Sumcheck over dpb200.Mle handles in the product);
+    local_mles: this rank's slice of every MLE, in the engine's own representation;
+    transcript: .append_msg(bytes) / .append_e(array[k,2]) / .challenge(label) -> [2].
+    Returns (point[nv,2], msgs[nv,max_deg+1,2], final_evals[n_mles,2]) -- identical on every rank.
+    """
+    log_w = world.bit_length() - 1
+    if world != 1 << log_w:
+        raise ValueError("world size must be a power of two")
+    nv_local = nv_total - log_w
+    if nv_local < 1:
+        raise ValueError("prove_sharded: fewer than one local variable per rank")
+    transcript.append_msg(int(nv_total).to_bytes(8, "little"))      # prover.rs:70-71
+    transcript.append_msg(int(max_deg).to_bytes(8, "little"))
+    eng = make_engine(local_mles, products, nv_local, max_deg)
+    point, msgs, ch = [], [], None
+    for _ in range(nv_local):
+        part = eng.round(ch)                                         # local K1/K2 launch
+        msg = _sum_mod_p(allgather(part)) if world > 1 else np.asarray(part, dtype=np.uint64)
+        transcript.append_e(msg)
+        ch = transcript.challenge(b"Internal round")
+        msgs.append(msg); point.append(ch)
+    fin_local = np.asarray(eng.finish(ch), dtype=np.uint64)          # this slice's residual value of every MLE
+    if world == 1:
+        return np.array(point), np.array(msgs), fin_local
+    residual = allgather(fin_local)                                  # [world, n_mles, 2]: merge_sumcheck_polys (util.rs:215-243)
+    n_mles = residual.shape[1]
+    merged = [(np.ascontiguousarray(residual[:, i, :]), True) for i in range(n_mles)]
+    eng2 = make_engine(merged, products, log_w, max_deg)             # last log G rounds, replicated on every rank
+    ch2 = None
+    for _ in range(log_w):
+        msg = np.asarray(eng2.round(ch2), dtype=np.uint64)
+        transcript.append_e(msg)
+        ch2 = transcript.challenge(b"Internal round")
+        msgs.append(msg); point.append(ch2)
+    fin = np.asarray(eng2.finish(ch2), dtype=np.uint64)
+    return np.array(point), np.array(msgs), fin
+
+
+# ---- product engine / transcript (CUDA library + C++ host mirror) -----------------------------------
+class HostTranscript:
+    """BasicTranscript of the C++ host mirror (host/transcript.hpp) -- Poseidon2 duplex sponge on the host CPU."""
+
+    def __init__(self, label=b"m2vec"):
+        import ctypes as C
+        import dpb200 as dp
+        self._C, self._dp = C, dp
+        H = dp.host()
+        H.dph_transcript_new.restype = C.c_void_p
+        H.dph_transcript_new.argtypes = [C.c_char_p]
+        H.dph_transcript_free.argtypes = [C.c_void_p]
+        H.dph_transcript_append_msg.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
+        H.dph_transcript_append_e.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        H.dph_transcript_challenge.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        self.H = H
+        self.h = C.c_void_p(H.dph_transcript_new(label))
+
+    def append_msg(self, m):
+        self.H.dph_transcript_append_msg(self.h, bytes(m), len(m))
+
+    def append_e(self, e):
+        e = np.ascontiguousarray(e, dtype=np.uint64).reshape(-1, 2)
+        self.H.dph_transcript_append_e(self.h, e.ctypes.data, e.shape[0])
+
+    def challenge(self, label):
+        out = np.zeros(2, dtype=np.uint64)
+        self.H.dph_transcript_challenge(self.h, label, out.ctypes.data)
+        return out
+
+    def __del__(self):
+        try:
+            self.H.dph_transcript_free(self.h)
+        except Exception:
+            pass
+
+
+def device_engine(mles, products, nv, max_deg):
+    """per-slice engine on this rank's GPU: mles are dpb200.Mle handles, or (array, is_ext) pairs that get uploaded"""
+    import dpb200 as dp
+    hs = [m if isinstance(m, dp.Mle) else dp.Mle.upload(m[0], m[1]) for m in mles]
+    return dp.Sumcheck(hs, products, nv, max_deg)
+
+
+def prove_sharded_device(local_mles, products, nv_total, rank, world, allgather, label=b"m2vec"):
+    """the product entry: this rank's slices are resident on its GPU (dp_init done by the caller)"""
+    max_deg = max(len(p[1]) for p in products)
+    return prove_sharded(device_engine, local_mles, products, nv_total, max_deg, rank, world, allgather, HostTranscript(label))
