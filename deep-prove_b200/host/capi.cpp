@@ -216,6 +216,44 @@ extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_wo
     DPH_CATCH
 }
 
+// One proof sharded over `world` ranks: `mles` are THIS rank's slices (nv_total - log2(world) variables each).
+// Exchange: shm_region != NULL -> same-node shared-memory mailbox (sizeof = dph_shm_mailbox_bytes(), zero-initialised,
+// mapped by every rank; `*shm_seq` carries the mailbox sequence number across calls); else `cb(user, send, n, recv)`.
+extern "C" uint64_t dph_shm_mailbox_bytes() { return sizeof(ShmMailbox); }
+// one raw all-gather through the mailbox (host-only; used by the CPU tests of the exchange itself)
+extern "C" int dph_shm_allgather(void *shm_region, uint32_t world, uint32_t rank, uint64_t *shm_seq, const uint64_t *send, uint64_t n_words, uint64_t *recv) {
+    DPH_TRY
+    ShmExchange ex(shm_region, world, rank); ex.seq = *shm_seq;
+    ex.allgather((const u64 *)send, n_words, (u64 *)recv);
+    *shm_seq = ex.seq;
+    return 0;
+    DPH_CATCH
+}
+extern "C" int dph_sumcheck_prove_sharded(uint32_t world, uint32_t rank, dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *products, uint32_t n_products,
+                                          uint32_t nv_total, const char *label, void *shm_region, uint64_t *shm_seq, CallbackExchange::Fn cb, void *user,
+                                          uint64_t *out_point, uint64_t *out_msgs, uint64_t *out_final) {
+    DPH_TRY
+    uint32_t logG = 0; while ((1u << logG) < world) logG++;
+    VirtualPolynomial vp(nv_total - logG);
+    std::vector<DeviceMle> views;
+    for (uint32_t i = 0; i < n_mles; i++) {
+        uint64_t len; int ext; check(dp_mle_info(mles[i], &len, &ext, nullptr));
+        views.push_back(DeviceMle::wrap_device(dp_mle_device_ptr(mles[i]), len, ext));
+    }
+    for (uint32_t p = 0; p < n_products; p++) { std::vector<DeviceMle> l; for (uint32_t j = 0; j < products[p].n_idx; j++) l.push_back(views.at(products[p].idx[j])); vp.add_mle_list(l, Ext(products[p].coef[0], products[p].coef[1])); }
+    BasicTranscript tr(label);
+    std::pair<IOPProof, IOPProverState> res;
+    if (shm_region) { ShmExchange ex(shm_region, world, rank); if (shm_seq) ex.seq = *shm_seq; res = IOPProverState::prove_sharded(std::move(vp), nv_total, ex, tr); if (shm_seq) *shm_seq = ex.seq; }
+    else { if (!cb && world > 1) throw Error(DP_ERR_INVALID, "prove_sharded: no exchange given"); CallbackExchange ex(cb, user, world, rank); res = IOPProverState::prove_sharded(std::move(vp), nv_total, ex, tr); }
+    for (size_t i = 0; i < res.first.point.size(); i++) { out_point[2 * i] = res.first.point[i].c0; out_point[2 * i + 1] = res.first.point[i].c1; }
+    size_t k = 0;
+    for (auto &m : res.first.proofs) for (auto &e : m.evaluations) { out_msgs[2 * k] = e.c0; out_msgs[2 * k + 1] = e.c1; k++; }
+    const ExtVec &fin = res.second.get_mle_final_evaluations();
+    for (size_t i = 0; i < fin.size() && i < n_mles; i++) { out_final[2 * i] = fin[i].c0; out_final[2 * i + 1] = fin[i].c1; }
+    return 0;
+    DPH_CATCH
+}
+
 // prove_batch_polys over T contiguous slices of the caller's device MLEs (views, no copies)
 extern "C" int dph_sumcheck_prove_batch_polys(uint32_t T, dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *products, uint32_t n_products,
                                               uint32_t max_nv, const char *label, uint64_t *out_point, uint64_t *out_msgs, uint64_t *out_final) {

@@ -10,6 +10,7 @@
 #include "transcript.hpp"
 #include "../../include/deepprove_b200.h"
 #include <memory>
+#include <algorithm>
 #include <map>
 
 namespace dp {
@@ -50,6 +51,49 @@ class DeviceMle {
     std::vector<u64> download() const { std::vector<u64> v(len() * (is_ext() ? 2 : 1)); check(dp_mle_download(h_.get(), v.data())); return v; }
   private:
     std::shared_ptr<dp_mle> h_;
+};
+
+// Inter-rank exchange used by IOPProverState::prove_sharded: an all-gather of a few u64 words per rank.
+struct Exchange {
+    size_t world = 1, rank = 0;
+    virtual ~Exchange() {}
+    virtual void allgather(const u64 *send, size_t n_words, u64 *recv /* world * n_words, rank-major */) = 0;
+};
+// Same-node exchange through a shared-memory mailbox (all ranks of one box map the same zero-initialised region).
+// The per-round message has to reach the host anyway (Fiat-Shamir runs there), so host-to-host shared memory is the
+// shortest path: ~1 us per exchange instead of a device collective's launch + copy-back.  Slots are double-buffered
+// by sequence parity; a slot is rewritten only two exchanges later, which every reader has passed by then.
+struct ShmMailbox {
+    static constexpr size_t MAX_WORLD = 16, PAYLOAD = 62;
+    struct alignas(64) Slot { volatile u64 seq; u64 n; u64 payload[PAYLOAD]; };
+    Slot slots[MAX_WORLD][2];
+};
+struct ShmExchange : Exchange {
+    ShmMailbox *mb; u64 seq = 0;
+    ShmExchange(void *region, size_t w, size_t r) : mb((ShmMailbox *)region) { world = w; rank = r; if (w > ShmMailbox::MAX_WORLD) throw std::runtime_error("ShmExchange: world too large"); }
+    void allgather(const u64 *send, size_t n, u64 *recv) override {
+        for (size_t off = 0; off < n || off == 0; off += ShmMailbox::PAYLOAD) {
+            size_t m = std::min(n - off, ShmMailbox::PAYLOAD);
+            seq++;
+            ShmMailbox::Slot &mine = mb->slots[rank][seq & 1];
+            for (size_t i = 0; i < m; i++) mine.payload[i] = send[off + i];
+            mine.n = m;
+            __atomic_store_n(&mine.seq, seq, __ATOMIC_RELEASE);
+            for (size_t g = 0; g < world; g++) {
+                ShmMailbox::Slot &sl = mb->slots[g][seq & 1];
+                while (__atomic_load_n(&sl.seq, __ATOMIC_ACQUIRE) != seq) { __builtin_ia32_pause(); }
+                for (size_t i = 0; i < m; i++) recv[g * n + off + i] = sl.payload[i];
+            }
+            if (n == 0) break;
+        }
+    }
+};
+// Exchange through a caller-supplied function (e.g. a torch.distributed all-gather over NCCL or gloo)
+struct CallbackExchange : Exchange {
+    typedef int (*Fn)(void *user, const uint64_t *send, uint64_t n_words, uint64_t *recv);
+    Fn fn; void *user;
+    CallbackExchange(Fn f, void *u, size_t w, size_t r) : fn(f), user(u) { world = w; rank = r; }
+    void allgather(const u64 *send, size_t n, u64 *recv) override { if (fn(user, send, n, recv)) throw std::runtime_error("exchange callback failed"); }
 };
 
 struct VPAuxInfo { size_t max_degree = 0, max_num_variables = 0; };
@@ -164,16 +208,69 @@ class IOPProverState {
         u64 c[2] = {challenge.c0, challenge.c1};
         for (auto &h : hs) { std::vector<u64> fin(2 * n_mles); check(dp_sc_finish(h.h, c, fin.data())); for (size_t i = 0; i < n_mles; i++) residual[i].push_back(Ext(fin[2 * i], fin[2 * i + 1])); }
         if (logT == 0) { for (size_t i = 0; i < n_mles; i++) st.finals_.push_back(residual[i][0]); proof.point = st.challenges; return {std::move(proof), std::move(st)}; }
+        finish_merged(residual, polys[0].products, deg, logT, transcript, proof, st);
+        return {std::move(proof), std::move(st)};
+    }
+
+    // One proof sharded over `ex.world` ranks (one process per GPU): rank g holds the slice [g n/G, (g+1) n/G) of
+    // every MLE as `poly` (nv_total - log G variables).  Same protocol as prove_batch_polys with max_thread_id = G
+    // (prover.rs:37-321): per round ONE all-gather of the (deg+1)-element partial message replaces the reference's
+    // per-thread channels (prover.rs:150-170); every rank adds the partials and runs the same transcript, so no
+    // challenge broadcast exists.  The proof is identical on every rank and to prove_parallel on the unsplit poly.
+    template <class T>
+    static std::pair<IOPProof, IOPProverState> prove_sharded(VirtualPolynomial poly, size_t nv_total, Exchange &ex, T &transcript) {
+        size_t G = ex.world, logG = 0; while (((size_t)1 << logG) < G) logG++;
+        if (G == 0 || (G & (G - 1))) throw Error(DP_ERR_INVALID, "prove_sharded: world size must be a power of two");
+        size_t nv = poly.aux_info.max_num_variables, deg = poly.aux_info.max_degree;
+        if (nv + logG != nv_total || nv == 0) throw Error(DP_ERR_INVALID, "prove_sharded: slice must have nv_total - log2(world) >= 1 variables");
+        IOPProof proof; IOPProverState st;
+        transcript.append_usize(nv_total);
+        transcript.append_usize(deg);
+        struct H { dp_sc *h = nullptr; ~H() { if (h) dp_sc_destroy(h); } } hs;
+        std::vector<dp_mle *> mh; for (auto &m : poly.flattened_ml_extensions) mh.push_back(m.handle());
+        check(dp_sc_create(mh.data(), (uint32_t)mh.size(), poly.products.data(), (uint32_t)poly.products.size(), (uint32_t)nv, (uint32_t)deg, &hs.h));
+        size_t W = 2 * (deg + 1);
+        std::vector<u64> buf(W), all(W * G);
+        Ext challenge; bool have = false;
+        for (size_t i = 0; i < nv; i++) {
+            u64 c[2] = {challenge.c0, challenge.c1};
+            check(dp_sc_round(hs.h, have ? c : nullptr, buf.data()));
+            ex.allgather(buf.data(), W, all.data());
+            IOPProverMessage msg; msg.evaluations.assign(deg + 1, Ext::zero());
+            for (size_t g = 0; g < G; g++) for (size_t k = 0; k <= deg; k++) msg.evaluations[k] += Ext(all[g * W + 2 * k], all[g * W + 2 * k + 1]);
+            transcript.append_field_element_exts(msg.evaluations);
+            proof.proofs.push_back(std::move(msg));
+            challenge = transcript.get_and_append_challenge("Internal round"); have = true;
+            st.challenges.push_back(challenge);
+        }
+        size_t n_mles = mh.size();
+        u64 c[2] = {challenge.c0, challenge.c1};
+        std::vector<u64> fin(2 * n_mles), fall(2 * n_mles * G);
+        check(dp_sc_finish(hs.h, c, fin.data()));
+        if (G == 1) { for (size_t i = 0; i < n_mles; i++) st.finals_.push_back(Ext(fin[2 * i], fin[2 * i + 1])); proof.point = st.challenges; return {std::move(proof), std::move(st)}; }
+        ex.allgather(fin.data(), 2 * n_mles, fall.data());
+        std::vector<ExtVec> residual(n_mles);                 // merge_sumcheck_polys (util.rs:215-243), slice order = rank order
+        for (size_t g = 0; g < G; g++) for (size_t i = 0; i < n_mles; i++) residual[i].push_back(Ext(fall[g * 2 * n_mles + 2 * i], fall[g * 2 * n_mles + 2 * i + 1]));
+        finish_merged(residual, poly.products, deg, logG, transcript, proof, st);   // last log G rounds, replicated on every rank
+        return {std::move(proof), std::move(st)};
+    }
+  private:
+    // stage 2 of the devirgo split: the last log T rounds over the T residual values of every MLE
+    template <class T>
+    static void finish_merged(const std::vector<ExtVec> &residual, const std::vector<dp_sc_product> &products, size_t deg, size_t logT, T &transcript, IOPProof &proof, IOPProverState &st) {
+        size_t n_mles = residual.size();
+        struct H { dp_sc *h = nullptr; ~H() { if (h) dp_sc_destroy(h); } };
+        std::vector<u64> buf(2 * (deg + 1));
+        Ext challenge; bool have = false;
         VirtualPolynomial merged(logT);
         std::vector<DeviceMle> mm; for (auto &r : residual) mm.push_back(DeviceMle::from_evaluations_ext_vec(r));
-        for (auto &pr : polys[0].products) { std::vector<DeviceMle> l; for (uint32_t j = 0; j < pr.n_idx; j++) l.push_back(mm[pr.idx[j]]); merged.add_mle_list(l, Ext(pr.coef[0], pr.coef[1])); }
+        for (auto &pr : products) { std::vector<DeviceMle> l; for (uint32_t j = 0; j < pr.n_idx; j++) l.push_back(mm[pr.idx[j]]); merged.add_mle_list(l, Ext(pr.coef[0], pr.coef[1])); }
         merged.aux_info.max_degree = deg;
-        // MLE numbering of `merged` follows first use in the products, as in polys[0]; map back for the final evaluations
+        // MLE numbering of `merged` follows first use in the products; map back for the final evaluations
         std::vector<dp_mle *> h2; for (auto &m : merged.flattened_ml_extensions) h2.push_back(m.handle());
         dp_sc *s2 = nullptr;
         check(dp_sc_create(h2.data(), (uint32_t)h2.size(), merged.products.data(), (uint32_t)merged.products.size(), (uint32_t)logT, (uint32_t)deg, &s2));
         H g2; g2.h = s2;
-        have = false;
         for (size_t i = 0; i < logT; i++) {
             u64 cc[2] = {challenge.c0, challenge.c1};
             check(dp_sc_round(s2, have ? cc : nullptr, buf.data()));
@@ -188,9 +285,7 @@ class IOPProverState {
         ExtVec f2; for (size_t i = 0; i < h2.size(); i++) f2.push_back(Ext(fin[2 * i], fin[2 * i + 1]));
         for (size_t i = 0; i < n_mles; i++) { Ext v; for (size_t k = 0; k < h2.size(); k++) if (h2[k] == mm[i].handle()) v = f2[k]; st.finals_.push_back(v); }
         proof.point = st.challenges;
-        return {std::move(proof), std::move(st)};
     }
-  private:
     dp_sc *sc_ = nullptr;
     ExtVec finals_;
     VirtualPolynomial poly_;

@@ -146,3 +146,72 @@ def prove_sharded_device(local_mles, products, nv_total, rank, world, allgather,
     """the product entry: this rank's slices are resident on its GPU (dp_init done by the caller)"""
     max_deg = max(len(p[1]) for p in products)
     return prove_sharded(device_engine, local_mles, products, nv_total, max_deg, rank, world, allgather, HostTranscript(label))
+
+
+# ---- native path: the whole sharded proof inside the C++ host mirror, exchange through shared memory -----------
+class ShmMailbox:
+    """Same-node mailbox for IOPProverState::prove_sharded (host/sumcheck.hpp ShmExchange): one zero-initialised POSIX
+    shared-memory region mapped by every rank.  The per-round message must reach the host for Fiat-Shamir anyway, so
+    the ranks exchange it host-to-host (~1 us) instead of through a device collective."""
+
+    def __init__(self, name, rank, world, barrier):
+        import ctypes as C
+        from multiprocessing import shared_memory, resource_tracker
+        import dpb200 as dp
+        H = dp.host()
+        H.dph_shm_mailbox_bytes.restype = C.c_uint64
+        size = int(H.dph_shm_mailbox_bytes())
+        self.rank, self.world = rank, world
+        if rank == 0:
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=size)
+            self.shm.buf[:size] = bytes(size)
+        barrier()
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+            try:
+                resource_tracker.unregister(self.shm._name, "shared_memory")   # rank 0 owns the segment
+            except Exception:
+                pass
+        barrier()
+        self._anchor = C.c_char.from_buffer(self.shm.buf)
+        self.addr = C.addressof(self._anchor)
+        self.seq = C.c_uint64(0)
+
+    def close(self, barrier=None):
+        del self._anchor
+        if barrier is not None:
+            barrier()
+        self.shm.close()
+        if self.rank == 0:
+            self.shm.unlink()
+
+
+def prove_sharded_native(local_mles, products, nv_total, rank, world, mailbox=None, allgather=None, label=b"m2vec"):
+    """IOPProverState::prove_sharded in the C++ host mirror (no Python in the round loop).  Exchange: `mailbox`
+    (ShmMailbox, same node) or `allgather` (callable(words)->[world, n], e.g. TorchAllGather over NCCL)."""
+    import ctypes as C
+    import dpb200 as dp
+    H = dp.host()
+    CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64))
+    H.dph_sumcheck_prove_sharded.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(dp.ScProduct), C.c_uint32, C.c_uint32,
+                                             C.c_char_p, C.c_void_p, C.POINTER(C.c_uint64), CB, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    hs = (C.c_void_p * len(local_mles))(*[m.h for m in local_mles])
+    prods = dp.make_products(products)
+    max_deg = max(len(p[1]) for p in products)
+    point = np.zeros((nv_total, 2), dtype=np.uint64)
+    msgs = np.zeros((nv_total, max_deg + 1, 2), dtype=np.uint64)
+    fin = np.zeros((len(local_mles), 2), dtype=np.uint64)
+
+    def _cb(user, send, n, recv):
+        try:
+            got = allgather(np.ctypeslib.as_array(send, shape=(int(n),)).copy())
+            np.ctypeslib.as_array(recv, shape=(world * int(n),))[:] = np.asarray(got, dtype=np.uint64).reshape(-1)
+            return 0
+        except Exception:
+            return 1
+    cb = CB(_cb) if (mailbox is None and allgather is not None) else C.cast(None, CB)
+    dp.hcheck(H.dph_sumcheck_prove_sharded(world, rank, hs, len(local_mles), prods, len(products), nv_total, label,
+                                           C.c_void_p(mailbox.addr) if mailbox is not None else None,
+                                           C.byref(mailbox.seq) if mailbox is not None else None, cb, None,
+                                           point.ctypes.data, msgs.ctypes.data, fin.ctypes.data))
+    return point, msgs, fin

@@ -45,6 +45,13 @@ local = [dp.Mle.upload((a.reshape(-1, 2)[lo:hi] if e else a[lo:hi]).copy(), e) f
 point, msgs, fin = mg.prove_sharded_device(local, products, nv, rank, world, mg.TorchAllGather(dist))
 ep, em, ef = O.sumcheck_prove(full, products, nv)
 ok = bool((point == ep).all() and (msgs == em).all() and (fin == ef).all())
+# the same proof through the C++ host mirror: shared-memory mailbox, then a torch.distributed callback exchange
+mb = mg.ShmMailbox("dpb200_test_%%d" %% os.getppid(), rank, world, dist.barrier)
+for kw in ({"mailbox": mb}, {"allgather": mg.TorchAllGather(dist)}, {"mailbox": mb}):
+    local = [dp.Mle.upload((a.reshape(-1, 2)[lo:hi] if e else a[lo:hi]).copy(), e) for a, e in full]
+    p2, m2, f2 = mg.prove_sharded_native(local, products, nv, rank, world, **kw)
+    ok = ok and bool((p2 == ep).all() and (m2 == em).all() and (f2 == ef).all())
+mb.close(dist.barrier)
 flags = [None] * world
 dist.all_gather_object(flags, ok)
 if rank == 0:

@@ -103,3 +103,43 @@ def test_sharded_sumcheck_equals_unsplit_proof(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
     assert out == {"ok": True, "world": 2, "rounds": 9}
+
+
+SHM_WORKER = r'''
+import os, sys, json, ctypes as C
+import numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "deep-prove_b200"))
+import torch.distributed as dist
+import dpb200 as dp, multigpu as mg
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+mb = mg.ShmMailbox("dpb200_cpu_%%d" %% os.getppid(), rank, world, dist.barrier)
+H = dp.host()
+H.dph_shm_allgather.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.c_void_p]
+ok = True
+for it in range(2000):
+    n = [8, 1, 62, 63, 200][it %% 5]              # one slot, a full slot, and multi-chunk payloads
+    send = (np.arange(n, dtype=np.uint64) * np.uint64(1000003) + np.uint64(it * 17 + rank)).astype(np.uint64)
+    recv = np.zeros(world * n, dtype=np.uint64)
+    assert H.dph_shm_allgather(C.c_void_p(mb.addr), world, rank, C.byref(mb.seq), send.ctypes.data, n, recv.ctypes.data) == 0
+    for g in range(world):
+        exp = (np.arange(n, dtype=np.uint64) * np.uint64(1000003) + np.uint64(it * 17 + g)).astype(np.uint64)
+        ok = ok and bool((recv[g * n:(g + 1) * n] == exp).all())
+flags = [None] * world
+dist.all_gather_object(flags, ok)
+mb.close(dist.barrier)
+if rank == 0:
+    print(json.dumps({"ok": all(flags), "seq": int(mb.seq.value)}))
+dist.destroy_process_group()
+'''
+
+
+def test_shared_memory_mailbox_allgather(tmp_path):
+    """the same-node exchange used by prove_sharded (host/sumcheck.hpp ShmExchange): 2000 back-to-back all-gathers
+    between two processes, including payloads larger than one slot"""
+    w = tmp_path / "shm.py"
+    w.write_text(SHM_WORKER % {"root": ROOT})
+    r = _torchrun([str(w)])
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert out["ok"] is True and out["seq"] == 400 * (1 + 1 + 1 + 2 + 4)

@@ -32,6 +32,8 @@ def main():
     dist.init_process_group(backend, device_id=torch.device("cuda", local_rank) if backend == "nccl" else None)
     dp.init(local_rank); dp.use_torch_stream()
     ag = mg.TorchAllGather(dist)
+    exch = os.environ.get("DP_EXCHANGE", "shm")     # shm: same-node mailbox (default); nccl: all-gather over NVLink; py: Python round loop + all-gather
+    mb = mg.ShmMailbox("dpb200_devirgo_%d" % os.getppid(), rank, world, dist.barrier) if exch == "shm" else None
     n = 1 << nv
     lo, hi = mg.shard_range(n, rank, world)
     products = [((1, 0), [0, 1, 2])]
@@ -42,7 +44,8 @@ def main():
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = mg.prove_sharded_device(mles, products, nv, rank, world, ag)
+        if exch == "py": out = mg.prove_sharded_device(mles, products, nv, rank, world, ag)
+        else: out = mg.prove_sharded_native(mles, products, nv, rank, world, mailbox=mb, allgather=None if mb is not None else ag)
         e1.record(); torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda" if backend == "nccl" else "cpu")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -65,9 +68,11 @@ def main():
         same = bool((ref[0] == point).all() and (ref[1] == msgs).all() and (ref[2] == fin).all())
     dist.barrier()
     if rank == 0:
-        print(json.dumps({"workload": "sumcheck nv=%d deg=3 3xBase, ONE proof sharded over %d GPUs (devirgo split), %s all-gather per round" % (nv, world, backend),
-                          "n_gpus": world, "sharded_ms": ms, "single_gpu_ms": single_ms, "bit_identical_to_single_gpu_proof": same,
+        print(json.dumps({"workload": "sumcheck nv=%d deg=3 3xBase, ONE proof sharded over %d GPUs (devirgo split), backend %s" % (nv, world, backend),
+                          "n_gpus": world, "exchange": exch, "sharded_ms": ms, "single_gpu_ms": single_ms, "bit_identical_to_single_gpu_proof": same,
                           "rounds": int(msgs.shape[0]), "exchange_bytes_per_round_per_rank": 16 * 4}))
+    if mb is not None:
+        mb.close(dist.barrier)
     dist.destroy_process_group()
 
 
