@@ -213,6 +213,7 @@ int dpo_pcs_batch_open(u32 n, const u64 *const *data, const u64 *lens, const int
 
 // ---- zkml MLP prover (oracle/zkml.hpp) ----
 #include "zkml.hpp"
+#include "conv.hpp"
 #include <chrono>
 extern "C" {
 // Synthetic MLP (SURVEY.md 8d Cfg 2): context generation (weight commits) + Prover::prove.  Returns the flat proof.
@@ -265,4 +266,53 @@ extern "C" int dpo_sumcheck_prove_batch(u32 T, u32 n_mles, const u64 *const *dat
         for (size_t i = 0; i < res.second.size(); i++) put_e(out_final, i, res.second[i]);
         return 0;
     } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+
+// ---- FFT convolution layer (conv.hpp): inference + isolated layer proof on a synthetic layer ----
+extern "C" {
+// synthetic padded layer: filter [kw][kx][real_nw][real_nw], bias [kw], input [kx][n_x][n_x]  (all int64)
+void dpo_synthetic_conv(u32 kw, u32 kx, u32 n_x, u32 real_nw, u32 kw_u, u32 k_u, u32 kx_u, u32 n_x_u, u64 seed_model, u64 seed_input,
+                        int64_t *filter, int64_t *bias, int64_t *input) {
+    ConvLayer f = synthetic_conv(kw, kx, n_x, real_nw, kw_u, k_u, n_x_u, seed_model);
+    memcpy(filter, f.filter.data(), 8 * f.filter.size()); memcpy(bias, f.bias.data(), 8 * f.bias.size());
+    auto x = synthetic_conv_input(kx, n_x, kx_u, n_x_u, seed_input); memcpy(input, x.data(), 8 * x.size());
+}
+// Convolution::op: out_after_bias / out_cleared are [kw][n_x][n_x]
+int dpo_conv_op(u32 kw, u32 kx, u32 n_x, u32 real_nw, const int64_t *filter, const int64_t *bias, const u32 *unpadded_out, const int64_t *input,
+                int64_t *out_after_bias, int64_t *out_cleared) {
+    try {
+        ConvLayer f; f.kw = kw; f.kx = kx; f.nw = n_x; f.real_nw = real_nw; f.filter.assign(filter, filter + (size_t)kw * kx * real_nw * real_nw); f.bias.assign(bias, bias + kw);
+        for (int i = 0; i < 3; i++) f.unpadded_out[i] = unpadded_out[i];
+        std::vector<Element> x(input, input + (size_t)kx * n_x * n_x); ConvData cd;
+        auto cleared = conv_op(f, x, n_x, cd);
+        if (out_after_bias) memcpy(out_after_bias, cd.output_as_element.data(), 8 * cd.output_as_element.size());
+        if (out_cleared) memcpy(out_cleared, cleared.data(), 8 * cleared.size());
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// the layer proof in isolation: output claim = (point drawn from the transcript, MLE(cleared output)(point)) as Prover::prove
+// does for the model output (iop/prover.rs:423-436); flat layout: conv.hpp flatten_conv_proof
+int dpo_conv_prove(u32 kw, u32 kx, u32 n_x, u32 real_nw, const int64_t *filter, const int64_t *bias, const u32 *unpadded_out, const int64_t *input,
+                   const char *label, u64 *out, u64 cap, u64 *out_len) {
+    try {
+        ConvLayer f; f.kw = kw; f.kx = kx; f.nw = n_x; f.real_nw = real_nw; f.filter.assign(filter, filter + (size_t)kw * kx * real_nw * real_nw); f.bias.assign(bias, bias + kw);
+        for (int i = 0; i < 3; i++) f.unpadded_out[i] = unpadded_out[i];
+        std::vector<Element> x(input, input + (size_t)kx * n_x * n_x); ConvData cd;
+        auto cleared = conv_op(f, x, n_x, cd);
+        Transcript t(label);
+        Claim c; c.point = t.sample_vec(ceil_log2(cleared.size()));
+        auto ce = elems_to_ext(cleared); c.eval = mle_evaluate(*ext_mle(ce.data(), ce.size()), c.point);
+        ConvProof pr; Claim in_claim = prove_convolution_step(f, t, c, cd, pr);
+        auto xe = elems_to_ext(x);
+        if (!(mle_evaluate(*ext_mle(xe.data(), xe.size()), in_claim.point) == in_claim.eval)) throw std::runtime_error("conv: returned claim is not an evaluation of the input tensor");
+        std::vector<u64> fl = flatten_conv_proof(pr, in_claim);
+        *out_len = fl.size();
+        if (out) { if (fl.size() > cap) { g_err = "dpo_conv_prove: output buffer too small"; return 2; } memcpy(out, fl.data(), 8 * fl.size()); }
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// tensor.rs:261 fft on [rows][n] Ext values in place (flag 0: FFT, 1: iFFT)
+void dpo_fft_ext(u64 *data, u64 rows, u64 n, int inverse) {
+    for (u64 r = 0; r < rows; r++) { std::vector<E> v(n); for (u64 i = 0; i < n; i++) v[i] = E(data[2 * (r * n + i)], data[2 * (r * n + i) + 1]); fft_ext(v, inverse != 0); for (u64 i = 0; i < n; i++) { data[2 * (r * n + i)] = v[i].c0; data[2 * (r * n + i) + 1] = v[i].c1; } }
+}
 }

@@ -353,3 +353,49 @@ def sumcheck_prove_batch(T, mles, products, max_nv, label=b"m2vec"):
     if rc:
         raise RuntimeError(lib().dpo_last_error().decode())
     return point, msgs, fin
+
+
+# ---- FFT convolution layer (oracle/conv.hpp) ----
+def i64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int64))
+
+
+def synthetic_conv(kw, kx, n_x, real_nw, kw_u, k_u, kx_u, n_x_u, seed_model, seed_input):
+    filt = np.zeros((kw, kx, real_nw, real_nw), dtype=np.int64)
+    bias = np.zeros(kw, dtype=np.int64)
+    x = np.zeros((kx, n_x, n_x), dtype=np.int64)
+    lib().dpo_synthetic_conv(C.c_uint32(kw), C.c_uint32(kx), C.c_uint32(n_x), C.c_uint32(real_nw), C.c_uint32(kw_u), C.c_uint32(k_u), C.c_uint32(kx_u),
+                             C.c_uint32(n_x_u), C.c_uint64(seed_model), C.c_uint64(seed_input), ptr(filt), ptr(bias), ptr(x))
+    unpadded_out = np.asarray([kw_u, n_x_u - k_u + 1, n_x_u - k_u + 1], dtype=np.uint32)
+    return filt, bias, x, unpadded_out
+
+
+def conv_op(filt, bias, unpadded_out, x):
+    kw, kx, rn, _ = filt.shape
+    n_x = x.shape[1]
+    after = np.zeros((kw, n_x, n_x), dtype=np.int64)
+    cleared = np.zeros((kw, n_x, n_x), dtype=np.int64)
+    rc = lib().dpo_conv_op(C.c_uint32(kw), C.c_uint32(kx), C.c_uint32(n_x), C.c_uint32(rn), ptr(i64(filt)), ptr(i64(bias)), ptr(np.ascontiguousarray(unpadded_out, dtype=np.uint32)),
+                           ptr(i64(x)), ptr(after), ptr(cleared))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return after, cleared
+
+
+def conv_prove(filt, bias, unpadded_out, x, label=b"m2vec", cap=1 << 20):
+    kw, kx, rn, _ = filt.shape
+    n_x = x.shape[1]
+    out = np.zeros(cap, dtype=np.uint64)
+    n = C.c_uint64()
+    rc = lib().dpo_conv_prove(C.c_uint32(kw), C.c_uint32(kx), C.c_uint32(n_x), C.c_uint32(rn), ptr(i64(filt)), ptr(i64(bias)), ptr(np.ascontiguousarray(unpadded_out, dtype=np.uint32)),
+                              ptr(i64(x)), label, ptr(out), C.c_uint64(cap), C.byref(n))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return out[:n.value].copy()
+
+
+def fft_ext(rows, inverse=False):
+    a = u64(rows).copy()
+    r, n = a.shape[0], a.shape[1]
+    lib().dpo_fft_ext(ptr(a), C.c_uint64(r), C.c_uint64(n), C.c_int(int(inverse)))
+    return a
