@@ -18,6 +18,7 @@
 //    which IS the stored codeword (basefold.rs:151 bit-reverses the DIT output) -- no final permutation.
 //  * the zero-padded upper half makes the first DIF level a pure copy-and-scale (k_expand).
 #include "common.cuh"
+#include "powtab.cuh"
 #include "poseidon2.cuh"
 #include <algorithm>
 
@@ -26,16 +27,12 @@ static constexpr u32 BF_BASECODE_LOG = 7;
 static constexpr u64 GL_ROOT32 = 1753635133440165772ULL;  // p3 Goldilocks two-adic generator, order 2^32
 
 // ---- root-of-unity / coset power tables: x^e = T0[e & 2047] * T1[(e >> 11) & 2047] * T2[e >> 22] ----
-struct PowTab { const u64 *t0, *t1, *t2; };
 __global__ void k_pow_table(u64 base, u64 *t /* 3 x 2048 */) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= 3 * 2048) return;
     u32 part = k >> 11, idx = k & 2047;
     u64 e = (u64)idx << (11 * part);
     t[k] = gl_pow(base, e);
-}
-__device__ __forceinline__ u64 tab_pow(const PowTab &t, u64 e) {
-    return gl_mul(gl_mul(t.t0[e & 2047], t.t1[(e >> 11) & 2047]), t.t2[(e >> 22) & 2047]);
 }
 struct BfGlobals { u64 *root_tab = nullptr; bool p2_ready = false; };
 static BfGlobals g_bf;          // process-wide, read-only once built (shared by every host thread's context)
@@ -58,6 +55,7 @@ static int bf_prepare() {
     return DP_OK;
 }
 static PowTab root_tab() { PowTab t; t.t0 = g_bf.root_tab; t.t1 = g_bf.root_tab + 2048; t.t2 = g_bf.root_tab + 4096; return t; }
+int dp_root_powtab(PowTab *out) { if (int e = bf_prepare()) return e; *out = root_tab(); return DP_OK; }
 
 // ---- bit reversal (out of place) ----
 template <typename T>

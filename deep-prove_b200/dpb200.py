@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     "dp_pcs_open_begin", "dp_pcs_open_round", "dp_pcs_open_final_message", "dp_pcs_open_query_words", "dp_pcs_open_query",
     "dp_pcs_open_free",
     "dp_logup_build", "dp_logup_num_vars", "dp_logup_outputs", "dp_logup_layer_mles", "dp_logup_free", "dp_mle_linear_combination",
+    "dp_fft_rows", "dp_pad_rows", "dp_conv_prod", "dp_conv_output_elements", "dp_phi_g_init", "dp_phi_level", "dp_mle_repeat",
 ]
 
 
@@ -439,3 +440,22 @@ def sumcheck_prove_batch_polys(T, mles, products, max_nv, label=b"m2vec"):
     fin = np.zeros((len(mles), 2), dtype=np.uint64)
     hcheck(H.dph_sumcheck_prove_batch_polys(T, hs, len(mles), prods, len(products), max_nv, label, _ptr(point), _ptr(msgs), _ptr(fin)))
     return point, msgs, fin
+
+
+# ---- FFT-convolution layer (host/conv.hpp) -------------------------------------------------------------
+def conv_prove(filt, bias, unpadded_out, x, label=b"m2vec", cap=1 << 20, prove=True):
+    """Convolution::op (+ prove_convolution_step when `prove`) on a padded layer: filt [kw, kx, real_nw, real_nw],
+    bias [kw], x [kx, n_x, n_x] (int64).  Returns (after_bias, cleared, flat_proof | None)."""
+    H = host()
+    filt = np.ascontiguousarray(filt, dtype=np.int64); bias = np.ascontiguousarray(bias, dtype=np.int64); x = np.ascontiguousarray(x, dtype=np.int64)
+    kw, kx, rn, _ = filt.shape
+    n_x = x.shape[1]
+    uo = np.ascontiguousarray(unpadded_out, dtype=np.uint32)
+    after = np.zeros((kw, n_x, n_x), dtype=np.int64)
+    cleared = np.zeros((kw, n_x, n_x), dtype=np.int64)
+    out = np.zeros(cap if prove else 1, dtype=np.uint64)
+    n = C.c_uint64()
+    H.dph_conv_prove.argtypes = [C.c_uint32] * 4 + [C.c_void_p] * 4 + [C.c_char_p] + [C.c_void_p] * 3 + [C.c_uint64, C.c_void_p]
+    hcheck(H.dph_conv_prove(kw, kx, n_x, rn, filt.ctypes.data, bias.ctypes.data, uo.ctypes.data, x.ctypes.data, label, after.ctypes.data, cleared.ctypes.data,
+                            out.ctypes.data if prove else None, cap, C.addressof(n) if prove else None))
+    return after, cleared, (out[:n.value].copy() if prove else None)

@@ -109,6 +109,7 @@ int dph_pcs_batch_open(dp_mle *const *polys, uint32_t n, uint32_t full_log, cons
 
 // ---- zkml MLP prover (host/zkml.hpp) ----
 #include "zkml.hpp"
+#include "conv.hpp"
 #include <chrono>
 namespace {
 struct ZkHandle { dp::zkml::Model model; dp::zkml::Context ctx; std::vector<std::vector<dp::zkml::Element>> trace; std::vector<dp::zkml::Element> trace_input; };
@@ -278,6 +279,34 @@ extern "C" int dph_sumcheck_prove_batch_polys(uint32_t T, dp_mle *const *mles, u
     for (auto &m : res.first.proofs) for (auto &e : m.evaluations) { out_msgs[2 * k] = e.c0; out_msgs[2 * k + 1] = e.c1; k++; }
     const ExtVec &fin = res.second.get_mle_final_evaluations();
     for (size_t i = 0; i < fin.size() && i < n_mles; i++) { out_final[2 * i] = fin[i].c0; out_final[2 * i + 1] = fin[i].c1; }
+    return 0;
+    DPH_CATCH
+}
+
+// ---- FFT-convolution layer in isolation (host/conv.hpp): inference + layer proof ----------------------------------
+// The output claim is drawn as Prover::prove draws the model-output claim (iop/prover.rs:423-436): point from the
+// transcript, eval = MLE(cleared output)(point).  Flat layout: host/conv.hpp flatten_conv_proof.
+extern "C" int dph_conv_prove(uint32_t kw, uint32_t kx, uint32_t n_x, uint32_t real_nw, const int64_t *filter, const int64_t *bias, const uint32_t *unpadded_out,
+                              const int64_t *input, const char *label, int64_t *out_after_bias, int64_t *out_cleared, uint64_t *out, uint64_t cap, uint64_t *out_len) {
+    DPH_TRY
+    using namespace dp::zkml;
+    Convolution c; c.kw = kw; c.kx = kx; c.nw = n_x; c.real_nw = real_nw;
+    c.filter.assign(filter, filter + (size_t)kw * kx * real_nw * real_nw); c.bias.assign(bias, bias + kw);
+    for (int i = 0; i < 3; i++) c.unpadded_out[i] = unpadded_out[i];
+    c.load();
+    std::vector<Element> x(input, input + (size_t)kx * n_x * n_x);
+    ConvData pd;
+    std::vector<Element> cleared = c.op(x, pd);
+    if (out_after_bias) memcpy(out_after_bias, pd.output_as_element.data(), 8 * pd.output_as_element.size());
+    if (out_cleared) memcpy(out_cleared, cleared.data(), 8 * cleared.size());
+    if (!out_len) return 0;
+    BasicTranscript t(label);
+    Claim cl; for (size_t i = 0; i < ceil_log2(cleared.size()); i++) cl.point.push_back(t.read_challenge());
+    cl.eval = DeviceMle::from_evaluations_vec(to_base(cleared)).evaluate(cl.point);
+    ConvProof pr; Claim in_claim = c.prove_convolution_step(t, cl, pd, pr);
+    std::vector<u64> fl = flatten_conv_proof(pr, in_claim);
+    *out_len = fl.size();
+    if (out) { if (fl.size() > cap) throw Error(DP_ERR_INVALID, "dph_conv_prove: output buffer too small"); memcpy(out, fl.data(), 8 * fl.size()); }
     return 0;
     DPH_CATCH
 }

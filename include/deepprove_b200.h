@@ -119,6 +119,29 @@ int dp_logup_free(dp_logup *l);
 /* out = sum_k coefs[k] * mles[k] over Ext MLEs of equal length (same_poly.rs:91-110 final_beta). */
 int dp_mle_linear_combination(dp_mle *const *mles, const uint64_t *coefs, uint32_t n, dp_mle **out);
 
+/* ---- FFT-convolution layer (zkml/src/layers/convolution.rs, zkml/src/tensor.rs:220-523, zkml/src/iop/prover.rs:164-399) --
+ * The tensors a convolution proof consumes (FFT of the reversed input, the product tensor, the reduced FFT-matrix rows
+ * W(r, .) with their per-level prefixes) are built on the device next to the sumchecks that read them. */
+/* tensor.rs:261-323 `fft(v, flag)` applied to every row of an Ext MLE viewed as [len >> log_n][2^log_n], in place;
+ * natural order in and out, root = get_root_of_unity(log_n) (tensor.rs:220), inverse includes the 1/n scaling. */
+int dp_fft_rows(dp_mle *m, uint32_t log_n, int inverse);
+/* index_w / index_wf (tensor.rs:236-253, convolution.rs:1535-1550): every source row holds an n_real x n_real block that is
+ * placed top-left in an n x n grid and zero-padded to out_len; the result is Ext, rows * out_len long. */
+int dp_pad_rows(const dp_mle *src, uint64_t rows, uint32_t n_real, uint32_t n, uint64_t out_len, dp_mle **out);
+/* fft_conv accumulation (tensor.rs:489-509): out[i][k] = sum_j x_fft[j][k] * w_fft[i][j][k]; x_fft [kx][row_len], w_fft [kw][kx][row_len]. */
+int dp_conv_prod(const dp_mle *x_fft, const dp_mle *w_fft, uint32_t kw, uint32_t kx, uint64_t row_len, dp_mle **out);
+/* index_u + to_element + add_bias (tensor.rs:255-259,343-361; convolution.rs:152-162): out_host[i][t] =
+ * to_element(out_rows[i][n_x^2 - 1 - t]) + bias[i], out_rows = iFFT(prod) as [kw][2 n_x^2]; bias and out_host are HOST arrays. */
+int dp_conv_output_elements(const dp_mle *out_rows, uint32_t kw, uint32_t n_x, const int64_t *bias, int64_t *out_host);
+/* Prover::phi_g_init (iop/prover.rs:231-289): w_red = W(rx, .) of the FFT (is_fft = 0) or iFFT (is_fft = 1, the reference's
+ * flag value in prove_batch_ifft) matrix scaled by `scale`, length 2^n, plus the n - 1 intermediate tables mid[i] (2^(i+1) values). */
+int dp_phi_g_init(const uint64_t *rx, uint32_t n, const uint64_t scale[2], int is_fft, dp_mle **w_red, dp_mle **mid);
+/* one level of delegate_matrix_evaluation (iop/prover.rs:182-195): out[i] = A + B * omega^(i << shift), omega =
+ * get_root_of_unity(n_total) (its inverse when `inverse`), i < 2^len_log; A, B are Ext scalars the host derives from r1, r2. */
+int dp_phi_level(uint32_t len_log, uint32_t n_total, uint32_t shift, const uint64_t A[2], const uint64_t B[2], int inverse, dp_mle **out);
+/* out = src repeated `times` times back to back (beta_acc, convolution.rs:870). */
+int dp_mle_repeat(const dp_mle *src, uint32_t times, dp_mle **out);
+
 /* ---- mpcs: Basefold over RS code (rate 1/2, 200 queries, basecode 2^7) + Poseidon2 Merkle trees ------ */
 typedef struct dp_pcs_comm dp_pcs_comm;  /* BasefoldCommitmentWithWitness (mpcs/src/basefold/structure.rs:63-72) */
 typedef struct dp_pcs_open dp_pcs_open;  /* prover state of one commit phase (oracles + their trees) */
