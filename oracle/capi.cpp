@@ -213,7 +213,6 @@ int dpo_pcs_batch_open(u32 n, const u64 *const *data, const u64 *lens, const int
 
 // ---- zkml MLP prover (oracle/zkml.hpp) ----
 #include "zkml.hpp"
-#include "conv.hpp"
 #include <chrono>
 extern "C" {
 // Synthetic MLP (SURVEY.md 8d Cfg 2): context generation (weight commits) + Prover::prove.  Returns the flat proof.
@@ -314,5 +313,48 @@ int dpo_conv_prove(u32 kw, u32 kx, u32 n_x, u32 real_nw, const int64_t *filter, 
 // tensor.rs:261 fft on [rows][n] Ext values in place (flag 0: FFT, 1: iFFT)
 void dpo_fft_ext(u64 *data, u64 rows, u64 n, int inverse) {
     for (u64 r = 0; r < rows; r++) { std::vector<E> v(n); for (u64 i = 0; i < n; i++) v[i] = E(data[2 * (r * n + i)], data[2 * (r * n + i) + 1]); fft_ext(v, inverse != 0); for (u64 i = 0; i < n; i++) { data[2 * (r * n + i)] = v[i].c0; data[2 * (r * n + i) + 1] = v[i].c1; } }
+}
+}
+
+// ---- synthetic CNN (conv -> requant -> relu -> maxpool x2, then 3 dense layers): full Prover::prove ----
+extern "C" {
+int dpo_cnn_prove(int small, u64 seed_model, u64 seed_input, const char *label, u64 *out, u64 cap, u64 *out_len, double *out_ms) {
+    try {
+        Model m = synthetic_cnn(small, seed_model);
+        std::vector<Element> input = synthetic_cnn_input(small, seed_input);
+        auto t0 = std::chrono::steady_clock::now();
+        ZkContext ctx = zk_context(m);
+        auto t1 = std::chrono::steady_clock::now();
+        Transcript t(label);
+        ModelProof p = zk_prove(ctx, input, t);
+        auto t2 = std::chrono::steady_clock::now();
+        if (out_ms) { out_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count(); out_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count(); }
+        std::vector<u64> f = flatten_model_proof(p, m.nodes.size());
+        *out_len = f.size();
+        if (out) { if (f.size() > cap) { g_err = "dpo_cnn_prove: output buffer too small"; return 2; } memcpy(out, f.data(), 8 * f.size()); }
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// the model description for the product's host side (same synthetic tensors, no oracle code on the product path):
+// per node: kind, then 8 shape words; weights/bias/filter data are appended to `data` in node order
+int dpo_synthetic_cnn(int small, u64 seed_model, u64 seed_input, int64_t *desc, u64 desc_cap, u64 *desc_len, int64_t *data, u64 data_cap, u64 *data_len, int64_t *input, u64 *input_len) {
+    try {
+        Model m = synthetic_cnn(small, seed_model);
+        std::vector<int64_t> d, w;
+        for (auto &n : m.nodes) {
+            d.push_back(n.kind);
+            if (n.kind == OP_DENSE) { d.insert(d.end(), {(int64_t)n.nrows, (int64_t)n.ncols, 0, 0, 0, 0, 0, 0}); w.insert(w.end(), n.weights.begin(), n.weights.end()); w.insert(w.end(), n.bias.begin(), n.bias.end()); }
+            else if (n.kind == OP_REQUANT) d.insert(d.end(), {(int64_t)n.rq.right_shift, (int64_t)n.rq.fp_scale, (int64_t)n.rq.fixed_point_multiplier, (int64_t)n.rq.intermediate_bit_size, 0, 0, 0, 0});
+            else if (n.kind == OP_CONV) { auto &c = *n.conv; d.insert(d.end(), {(int64_t)c.kw, (int64_t)c.kx, (int64_t)c.nw, (int64_t)c.real_nw, (int64_t)c.unpadded_out[0], (int64_t)c.unpadded_out[1], (int64_t)c.unpadded_out[2], 0}); w.insert(w.end(), c.filter.begin(), c.filter.end()); w.insert(w.end(), c.bias.begin(), c.bias.end()); }
+            else if (n.kind == OP_POOL) d.insert(d.end(), {(int64_t)n.pool_c, (int64_t)n.pool_h, (int64_t)n.pool_w, 0, 0, 0, 0, 0});
+            else d.insert(d.end(), {0, 0, 0, 0, 0, 0, 0, 0});
+        }
+        std::vector<Element> in = synthetic_cnn_input(small, seed_input);
+        *desc_len = d.size(); *data_len = w.size(); *input_len = in.size();
+        if (desc && d.size() <= desc_cap) memcpy(desc, d.data(), 8 * d.size());
+        if (data && w.size() <= data_cap) memcpy(data, w.data(), 8 * w.size());
+        if (input) memcpy(input, in.data(), 8 * in.size());
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
 }

@@ -7,7 +7,7 @@
 //   iop/prover.rs:164-399    delegate_matrix_evaluation, phi_pow_init, phi_g_init, prove_batch_fft, prove_batch_ifft
 // The reference's debug_assert! invariants are kept as hard checks (they are what pins this restatement).
 #pragma once
-#include "zkml.hpp"
+// NOTE: included from the middle of zkml.hpp (needs Claim, Element, ext_mle, sumcheck_prove; zk_prove needs this file)
 
 namespace dpo {
 
@@ -325,29 +325,6 @@ static inline Claim prove_convolution_step(const ConvLayer &f, Transcript &t, co
     Claim fin; fin.point = input_point; fin.point.insert(fin.point.end(), had.first.point.begin() + lrow, had.first.point.end());
     fin.eval = e_mul(fftp.claims[0], v);
     return fin;
-}
-
-static inline void flat_matrix_eval(std::vector<u64> &o, const MatrixEvalProof &m) {
-    o.push_back(m.proofs.size()); for (auto &p : m.proofs) flat_iop(o, p);
-    o.push_back(m.claims.size()); for (auto &c : m.claims) { o.push_back(c.size()); for (E e : c) flat_e(o, e); }
-}
-static inline void flat_evec(std::vector<u64> &o, const std::vector<E> &v) { o.push_back(v.size()); for (E e : v) flat_e(o, e); }
-// field order of ConvProof (convolution.rs:97-121), then the two commitment claims and the returned input claim
-static inline std::vector<u64> flatten_conv_proof(const ConvProof &p, const Claim &input_claim) {
-    std::vector<u64> o;
-    flat_iop(o, p.fft_proof); flat_evec(o, p.fft_claims); flat_iop(o, p.fft_proof_weights); flat_iop(o, p.ifft_proof);
-    o.push_back(p.fft_delegation.proofs.size()); for (auto &q : p.fft_delegation.proofs) flat_iop(o, q);
-    o.push_back(p.fft_delegation_weights.proofs.size()); for (auto &q : p.fft_delegation_weights.proofs) flat_iop(o, q);
-    o.push_back(p.ifft_delegation.proofs.size()); for (auto &q : p.ifft_delegation.proofs) flat_iop(o, q);
-    flat_iop(o, p.hadamard_proof); flat_evec(o, p.ifft_claims); flat_evec(o, p.fft_weight_claims);
-    o.push_back(p.fft_delegation.claims.size()); for (auto &c : p.fft_delegation.claims) flat_evec(o, c);
-    o.push_back(p.fft_delegation_weights.claims.size()); for (auto &c : p.fft_delegation_weights.claims) flat_evec(o, c);
-    o.push_back(p.ifft_delegation.claims.size()); for (auto &c : p.ifft_delegation.claims) flat_evec(o, c);
-    flat_evec(o, p.hadamard_claims); flat_e(o, p.bias_claim); flat_evec(o, p.partial_evals);
-    flat_iop(o, p.clearing_proof.sumcheck); flat_evec(o, p.clearing_proof.individual_claim);
-    flat_evec(o, p.filter_claim.point); flat_e(o, p.filter_claim.eval); flat_evec(o, p.bias_poly_claim.point); flat_e(o, p.bias_poly_claim.eval);
-    flat_evec(o, input_claim.point); flat_e(o, input_claim.eval);
-    return o;
 }
 
 // deterministic synthetic layer + input for tests and golden vectors (NOT from the reference)

@@ -33,11 +33,13 @@ struct RequantParams {                                      // layers/requant.rs
     }
 };
 
-enum OpKind { OP_DENSE = 0, OP_REQUANT = 1, OP_RELU = 2 };
+enum OpKind { OP_DENSE = 0, OP_REQUANT = 1, OP_RELU = 2, OP_CONV = 3, OP_POOL = 4 };
 struct Node {
     OpKind kind; size_t nrows = 0, ncols = 0;
     std::vector<Element> weights, bias;   // Dense, row-major nrows x ncols
     RequantParams rq;
+    std::shared_ptr<struct ConvLayer> conv;                  // OP_CONV (padded layer, conv.hpp)
+    size_t pool_c = 0, pool_h = 0, pool_w = 0;               // OP_POOL: padded input shape [C][H][W], Maxpool2D kernel = stride = 2
 };
 struct Model { std::vector<Node> nodes; size_t input_len = 0; };
 
@@ -101,6 +103,10 @@ struct LogUpProof {
 };
 static std::shared_ptr<MLE> ext_mle(const E *p, size_t n) { auto m = std::make_shared<MLE>(); m->is_ext = true; m->num_vars = ceil_log2(n); m->ext.assign(p, p + n); return m; }
 static std::shared_ptr<MLE> base_mle(const std::vector<u64> &v) { auto m = std::make_shared<MLE>(); m->is_ext = false; m->num_vars = ceil_log2(v.size()); m->base = v; return m; }
+
+}  // namespace dpo
+#include "conv.hpp"   // FFT-convolution layer (uses the definitions above; zk_prove below uses it)
+namespace dpo {
 
 // logup_gkr::prover::batch_prove (prover.rs:24-237)
 static inline LogUpProof logup_batch_prove(const LogUpInput &in, Transcript &t) {
@@ -192,10 +198,12 @@ struct DenseProof { IOPProof sumcheck; E bias_eval; std::vector<E> individual_cl
 struct RequantProof { IOPProof io_accumulation; std::vector<E> accumulation_evals; LogUpProof clamping_lookup, shifted_lookup; std::vector<Digest> commitments; };
 struct ActivationProof { SamePolyProof io_accumulation; LogUpProof lookup; std::vector<Digest> commits; };
 struct TableProof { Digest multiplicity_commit; LogUpProof lookup; };
+struct PoolingProof { IOPProof sumcheck; LogUpProof lookup; std::vector<E> zerocheck_evals; size_t variable_gap = 0; std::vector<Digest> commitments; };   // layers/pooling.rs:60-75
 struct ModelProof {
     std::map<size_t, DenseProof> dense; std::map<size_t, RequantProof> requant; std::map<size_t, ActivationProof> activation;
     std::vector<TableProof> table_proofs;
     BasefoldProof batch_proof; std::vector<BasefoldProof> trivial_proofs;
+    std::map<size_t, ConvProof> conv; std::map<size_t, PoolingProof> pooling;
 };
 
 // Context::generate (iop/context.rs:110-215) for this model family: commits DenseBias / DenseWeight per dense node
@@ -215,23 +223,50 @@ static inline ZkContext zk_context(const Model &m) {
         if (n.kind == OP_DENSE) max_len = std::max(max_len, std::max(n.nrows * n.ncols, n.nrows));
         if (n.kind == OP_REQUANT) { tabs[{TT_RANGE, 0}] = 1; tabs[{TT_CLAMPING, n.rq.clamping_size()}] = 1; }
         if (n.kind == OP_RELU) tabs[{TT_RELU, 0}] = 1;
+        if (n.kind == OP_CONV) max_len = std::max(max_len, std::max(n.conv->filter.size(), n.conv->kw * n.conv->nw * n.conv->nw));
+        if (n.kind == OP_POOL) { tabs[{TT_RANGE, 0}] = 1; max_len = std::max(max_len, n.pool_c * n.pool_h * n.pool_w); }   // pooling.rs:130-170
     }
     for (auto &kv : tabs) { c.tables.push_back(kv.first); size_t mv = kv.first.kind == TT_CLAMPING ? kv.first.size : Q_BIT_LEN; max_len = std::max(max_len, (size_t)1 << mv); }   // context.rs:171-175
     c.full_log = ceil_log2(max_len);
     for (size_t id = 0; id < m.nodes.size(); id++) if (m.nodes[id].kind == OP_DENSE) {
         c.model_comms[id]["DenseBias"] = commit_base(to_base_vec(m.nodes[id].bias), c.full_log);
         c.model_comms[id]["DenseWeight"] = commit_base(to_base_vec(m.nodes[id].weights), c.full_log);
+    } else if (m.nodes[id].kind == OP_CONV) {                 // convolution.rs:532-540 (ConvBias < ConvFilter in the BTreeMap)
+        c.model_comms[id]["ConvBias"] = commit_base(to_base_vec(m.nodes[id].conv->bias), c.full_log);
+        c.model_comms[id]["ConvFilter"] = commit_base(to_base_vec(m.nodes[id].conv->filter), c.full_log);
     }
     return c;
 }
 
 // quantised inference trace (model/mod.rs run): outputs[i] = output of node i
-static inline std::vector<std::vector<Element>> zk_run(const Model &m, const std::vector<Element> &input) {
+// Maxpool2D::op (pooling.rs:667-677, tensor.rs:1335-1384) on a padded [C][H][W] tensor, kernel = stride = 2
+static inline std::vector<Element> maxpool2d(const std::vector<Element> &x, size_t C, size_t H, size_t W) {
+    std::vector<Element> o(C * (H / 2) * (W / 2));
+    for (size_t c = 0; c < C; c++) for (size_t r = 0; r < H / 2; r++) for (size_t cc = 0; cc < W / 2; cc++) {
+        Element mx = x[(c * H + 2 * r) * W + 2 * cc];
+        for (size_t a = 0; a < 2; a++) for (size_t b = 0; b < 2; b++) mx = std::max(mx, x[(c * H + 2 * r + a) * W + 2 * cc + b]);
+        o[(c * (H / 2) + r) * (W / 2) + cc] = mx;
+    }
+    return o;
+}
+// Maxpool2D::compute_polys (pooling.rs:686-771): out - in(2r+dr, 2c+dc) laid out like the output, in the order (dr,dc) = (0,0),(1,0),(0,1),(1,1)
+static inline std::vector<std::vector<Element>> maxpool_diff_polys(const std::vector<Element> &x, const std::vector<Element> &out, size_t C, size_t H, size_t W) {
+    std::vector<std::vector<Element>> d(4, std::vector<Element>(out.size()));
+    static const size_t DR[4] = {0, 1, 0, 1}, DC[4] = {0, 0, 1, 1};
+    for (size_t k = 0; k < 4; k++) for (size_t c = 0; c < C; c++) for (size_t r = 0; r < H / 2; r++) for (size_t cc = 0; cc < W / 2; cc++) {
+        size_t oi = (c * (H / 2) + r) * (W / 2) + cc;
+        d[k][oi] = out[oi] - x[(c * H + 2 * r + DR[k]) * W + 2 * cc + DC[k]];
+    }
+    return d;
+}
+static inline std::vector<std::vector<Element>> zk_run(const Model &m, const std::vector<Element> &input, std::map<size_t, ConvData> *conv_data = nullptr) {
     std::vector<std::vector<Element>> outs; std::vector<Element> cur = input;
     for (auto &n : m.nodes) {
         std::vector<Element> o;
         if (n.kind == OP_DENSE) { o.resize(n.nrows); for (size_t r = 0; r < n.nrows; r++) { Element a = n.bias[r]; for (size_t c = 0; c < n.ncols; c++) a += n.weights[r * n.ncols + c] * cur[c]; o[r] = a; } }
         else if (n.kind == OP_REQUANT) { for (Element e : cur) { Element lim = (Element)1 << n.rq.intermediate_bit_size; if (e > lim || e < -lim) throw std::runtime_error("Could not apply requantisation, tensor element had absolute value too large"); o.push_back(n.rq.apply(e)); } }
+        else if (n.kind == OP_CONV) { ConvData cd; o = conv_op(*n.conv, cur, n.conv->nw, cd); if (conv_data) (*conv_data)[outs.size()] = std::move(cd); }
+        else if (n.kind == OP_POOL) o = maxpool2d(cur, n.pool_c, n.pool_h, n.pool_w);
         else for (Element e : cur) o.push_back(relu(e));
         outs.push_back(o); cur = o;
     }
@@ -243,7 +278,8 @@ struct LogUpWitness { bool table = false; std::vector<std::shared_ptr<WitnessPol
 // Prover::prove (iop/prover.rs:401-486)
 static inline ModelProof zk_prove(const ZkContext &ctx, const std::vector<Element> &input, Transcript &t) {
     const Model &m = *ctx.model; ModelProof proof;
-    std::vector<std::vector<Element>> outs = zk_run(m, input);
+    std::map<size_t, ConvData> conv_data;
+    std::vector<std::vector<Element>> outs = zk_run(m, input, &conv_data);
     auto node_input = [&](size_t id) -> const std::vector<Element> & { return id == 0 ? input : outs[id - 1]; };
     // ctx.write_to_transcript (commit/context.rs:181-190)
     for (auto &nk : ctx.model_comms) for (auto &pk : nk.second) digest_to_transcript(pk.second->comm.root(), t);
@@ -271,6 +307,12 @@ static inline ModelProof zk_prove(const ZkContext &ctx, const std::vector<Elemen
             const auto &a = node_input(id); const auto &b = outs[id];
             for (size_t i = 0; i < a.size(); i++) element_count[tt][a[i] + COLUMN_SEPARATOR * b[i]]++;
             for (auto *v : {&a, &b}) { auto ev = to_base_vec(*v); w.commits.push_back(commit_base(ev, ctx.full_log)); w.column_evals.push_back(ev); }
+            lookup_witness[id] = {w};
+        } else if (n.kind == OP_POOL) {   // pooling.rs:210-271: 4 difference columns looked up in Range; commits = columns + output
+            TableType tr{TT_RANGE, 0}; LogUpWitness w; w.tt = tr; w.columns_per_instance = 1;
+            auto diffs = maxpool_diff_polys(node_input(id), outs[id], n.pool_c, n.pool_h, n.pool_w);
+            for (auto &d : diffs) { for (Element e : d) element_count[tr][e]++; auto ev = to_base_vec(d); w.commits.push_back(commit_base(ev, ctx.full_log)); w.column_evals.push_back(ev); }
+            w.commits.push_back(commit_base(to_base_vec(outs[id]), ctx.full_log));
             lookup_witness[id] = {w};
         }
     }
@@ -338,6 +380,44 @@ static inline ModelProof zk_prove(const ZkContext &ctx, const std::vector<Elemen
             last = {point, combined};
             // the claim handed on must be the requant INPUT evaluated at the point (verify_requant's recombination)
             if (mle_evaluate(*base_mle(to_base_vec(node_input(id))), point) != combined) throw std::runtime_error("requant: recombined claim mismatch");
+        } else if (n.kind == OP_CONV) {   // convolution.rs:609-636 -> prove_convolution_step
+            ConvProof cp; Claim in_claim = prove_convolution_step(*n.conv, t, last, conv_data.at(id), cp);
+            const auto &comms = ctx.model_comms.at(id);                               // add_common_claims: BTreeMap order ConvBias, ConvFilter
+            add_witness_claim(comms.at("ConvBias"), cp.bias_poly_claim);
+            add_witness_claim(comms.at("ConvFilter"), cp.filter_claim);
+            proof.conv[id] = cp;
+            last = in_claim;
+        } else if (n.kind == OP_POOL) {   // pooling.rs:342-519 prove_pooling
+            auto ws = lookup_witness.at(id);
+            LogUpInput in = logup_input(ws[0]);
+            LogUpProof lp = logup_batch_prove(in, t);
+            size_t nv = ceil_log2(outs[id].size());
+            const std::vector<E> &lookup_point = lp.output_claims[0].point;
+            E bc = t.get_and_append_challenge("batch_pooling");
+            auto beta_poly = ext_mle(build_eq_x_r_vec(lookup_point).data(), (size_t)1 << nv);
+            auto last_beta = ext_mle(build_eq_x_r_vec(last.point).data(), (size_t)1 << nv);
+            std::vector<std::shared_ptr<MLE>> diffs; for (auto &col : in.column_evals) diffs.push_back(base_mle(col));
+            VirtualPolynomial vp(nv);
+            { auto all = diffs; all.push_back(beta_poly); vp.add_mle_list(all, E::one()); }
+            E comb = bc; for (auto &d : diffs) { vp.add_mle_list({d, beta_poly}, comb); comb = e_mul(comb, bc); }
+            auto out_mle = base_mle(to_base_vec(outs[id]));
+            vp.add_mle_list({out_mle, last_beta}, comb);
+            auto res = sumcheck_prove(vp, t);
+            const std::vector<E> &fe = res.second; const std::vector<E> &zc_point = res.first.point;
+            size_t ks = 4; E output_eval = fe[ks + 1];
+            PoolingProof pp; pp.sumcheck = res.first; pp.lookup = lp;
+            for (size_t i = 0; i <= ks; i++) { E ev = i < ks ? fe[i] : output_eval; add_witness_claim(ws[0].commits[i], {zc_point, ev}); pp.commitments.push_back(ws[0].commits[i]->comm.root()); pp.zerocheck_evals.push_back(ev); }
+            size_t lw = ceil_log2(n.pool_w);
+            E r1 = t.get_and_append_challenge("input_batching"), r2 = r1;             // `[challenge; 2]`: ONE challenge, copied (pooling.rs:453-456)
+            E m1 = e_sub(E::one(), r1), m2 = e_sub(E::one(), r2);
+            E mult[4] = {e_mul(m1, m2), e_mul(m1, r2), e_mul(r1, m2), e_mul(r1, r2)};
+            E zc_in = E::zero(); for (size_t k = 0; k < ks; k++) zc_in = e_add(zc_in, e_mul(mult[k], e_sub(output_eval, fe[k])));
+            Claim next; next.point.push_back(r1); next.point.insert(next.point.end(), zc_point.begin(), zc_point.begin() + (lw - 1));
+            next.point.push_back(r2); next.point.insert(next.point.end(), zc_point.begin() + (lw - 1), zc_point.end());
+            next.eval = zc_in; pp.variable_gap = lw - 1;
+            if (mle_evaluate(*base_mle(to_base_vec(node_input(id))), next.point) != next.eval) throw std::runtime_error("pooling: input claim mismatch");
+            proof.pooling[id] = pp;
+            last = next;
         } else {   // activation.rs:385-460
             auto ws = lookup_witness.at(id);
             LogUpInput in = logup_input(ws[0]);
@@ -367,6 +447,7 @@ static inline ModelProof zk_prove(const ZkContext &ctx, const std::vector<Elemen
         auto fold = [&](const LogUpProof &p, bool negate) { for (auto &o : p.circuit_outputs) { E n = e_add(e_mul(o[0], o[3]), e_mul(o[1], o[2])), d = e_mul(o[2], o[3]); addf(negate ? e_neg(n) : n, d); } };
         for (auto &kv : proof.requant) { fold(kv.second.clamping_lookup, false); fold(kv.second.shifted_lookup, false); }
         for (auto &kv : proof.activation) fold(kv.second.lookup, false);
+        for (auto &kv : proof.pooling) fold(kv.second.lookup, false);
         for (auto &tp : proof.table_proofs) fold(tp.lookup, false);
         if (!num.is_zero()) throw std::runtime_error("logup: lookup and table fractional sums do not cancel");
     }
@@ -387,12 +468,37 @@ static inline void flat_logup(std::vector<u64> &o, const LogUpProof &p) {
     o.push_back(p.circuit_outputs.size()); for (auto &r : p.circuit_outputs) { o.push_back(r.size()); for (E e : r) flat_e(o, e); }
     o.push_back(p.table ? 1 : 0);
 }
+static inline void flat_matrix_eval(std::vector<u64> &o, const MatrixEvalProof &m) {
+    o.push_back(m.proofs.size()); for (auto &p : m.proofs) flat_iop(o, p);
+    o.push_back(m.claims.size()); for (auto &c : m.claims) { o.push_back(c.size()); for (E e : c) flat_e(o, e); }
+}
+static inline void flat_evec(std::vector<u64> &o, const std::vector<E> &v) { o.push_back(v.size()); for (E e : v) flat_e(o, e); }
+// field order of ConvProof (convolution.rs:97-121), then the two commitment claims and the returned input claim
+static inline std::vector<u64> flatten_conv_proof(const ConvProof &p, const Claim &input_claim) {
+    std::vector<u64> o;
+    flat_iop(o, p.fft_proof); flat_evec(o, p.fft_claims); flat_iop(o, p.fft_proof_weights); flat_iop(o, p.ifft_proof);
+    o.push_back(p.fft_delegation.proofs.size()); for (auto &q : p.fft_delegation.proofs) flat_iop(o, q);
+    o.push_back(p.fft_delegation_weights.proofs.size()); for (auto &q : p.fft_delegation_weights.proofs) flat_iop(o, q);
+    o.push_back(p.ifft_delegation.proofs.size()); for (auto &q : p.ifft_delegation.proofs) flat_iop(o, q);
+    flat_iop(o, p.hadamard_proof); flat_evec(o, p.ifft_claims); flat_evec(o, p.fft_weight_claims);
+    o.push_back(p.fft_delegation.claims.size()); for (auto &c : p.fft_delegation.claims) flat_evec(o, c);
+    o.push_back(p.fft_delegation_weights.claims.size()); for (auto &c : p.fft_delegation_weights.claims) flat_evec(o, c);
+    o.push_back(p.ifft_delegation.claims.size()); for (auto &c : p.ifft_delegation.claims) flat_evec(o, c);
+    flat_evec(o, p.hadamard_claims); flat_e(o, p.bias_claim); flat_evec(o, p.partial_evals);
+    flat_iop(o, p.clearing_proof.sumcheck); flat_evec(o, p.clearing_proof.individual_claim);
+    flat_evec(o, p.filter_claim.point); flat_e(o, p.filter_claim.eval); flat_evec(o, p.bias_poly_claim.point); flat_e(o, p.bias_poly_claim.eval);
+    flat_evec(o, input_claim.point); flat_e(o, input_claim.eval);
+    return o;
+}
+
 static inline std::vector<u64> flatten_model_proof(const ModelProof &p, size_t n_nodes) {
     std::vector<u64> o;
     for (size_t id = 0; id < n_nodes; id++) {
         if (p.dense.count(id)) { const auto &d = p.dense.at(id); o.push_back(100 + id); flat_iop(o, d.sumcheck); flat_e(o, d.bias_eval); o.push_back(d.individual_claims.size()); for (E e : d.individual_claims) flat_e(o, e); }
         if (p.requant.count(id)) { const auto &r = p.requant.at(id); o.push_back(200 + id); flat_iop(o, r.io_accumulation); o.push_back(r.accumulation_evals.size()); for (E e : r.accumulation_evals) flat_e(o, e); flat_logup(o, r.clamping_lookup); flat_logup(o, r.shifted_lookup); o.push_back(r.commitments.size()); for (auto &d : r.commitments) flat_d(o, d); }
         if (p.activation.count(id)) { const auto &a = p.activation.at(id); o.push_back(300 + id); flat_iop(o, a.io_accumulation.sumcheck); o.push_back(a.io_accumulation.evals.size()); for (E e : a.io_accumulation.evals) flat_e(o, e); flat_logup(o, a.lookup); o.push_back(a.commits.size()); for (auto &d : a.commits) flat_d(o, d); }
+        if (p.conv.count(id)) { o.push_back(400 + id); std::vector<u64> c = flatten_conv_proof(p.conv.at(id), Claim()); o.insert(o.end(), c.begin(), c.end()); }
+        if (p.pooling.count(id)) { const auto &q = p.pooling.at(id); o.push_back(500 + id); flat_iop(o, q.sumcheck); flat_logup(o, q.lookup); flat_evec(o, q.zerocheck_evals); o.push_back(q.variable_gap); o.push_back(q.commitments.size()); for (auto &d : q.commitments) flat_d(o, d); }
     }
     o.push_back(p.table_proofs.size()); for (auto &t : p.table_proofs) { flat_d(o, t.multiplicity_commit); flat_logup(o, t.lookup); }
     o.push_back(p.trivial_proofs.size());
@@ -416,6 +522,60 @@ static inline Model synthetic_mlp(size_t n_layers, size_t width, u64 seed) {
         Node a; a.kind = OP_RELU; m.nodes.push_back(a);
     }
     return m;
+}
+static inline RequantParams synthetic_requant(size_t int_part_log, size_t intermediate_bit_size) {
+    RequantParams r; r.intermediate_bit_size = intermediate_bit_size; r.right_shift = int_part_log;
+    r.fp_scale = ((int_part_log + 24 + 7) / 8) * 8 - int_part_log;
+    r.fixed_point_multiplier = (Element)(3 * ((Element)1 << (r.fp_scale - 2)));
+    return r;
+}
+// Synthetic CNN of SURVEY.md 8(d) Cfg 3, defined directly in the padded (power-of-two) domain the prover works in:
+// cifar-cnn.py --num-params 264000 gives c1=12, c2=33, fc1=247, fc2=173 (zkml/assets/scripts/CNN/cifar-cnn.py:175-241):
+//   in [3,32,32] -> conv 5x5 (12) -> requant -> relu -> maxpool -> conv 5x5 (33) -> requant -> relu -> maxpool -> flatten (33*5*5)
+//   -> fc 247 -> requant -> relu -> fc 173 -> requant -> relu -> fc 10.   `scale` = 1 is that model; smaller test models
+//   shrink the image (32 -> 16) and the channel counts.  Padded weights outside the real region are zero.
+struct CnnShape { size_t img, c0, c1, c2, f1, f2, f3, k; };
+static inline CnnShape cnn_shape(int small) { return small ? CnnShape{16, 3, 4, 6, 24, 16, 10, 3} : CnnShape{32, 3, 12, 33, 247, 173, 10, 5}; }
+static inline size_t next_pow2(size_t x) { size_t p = 1; while (p < x) p <<= 1; return p; }
+static inline Model synthetic_cnn(int small, u64 seed) {
+    CnnShape s = cnn_shape(small); Model m; SplitMix64 g(seed);
+    size_t kx_u = s.c0, n_u = s.img, n_p = next_pow2(s.img);
+    m.input_len = next_pow2(s.c0) * n_p * n_p;
+    size_t chans[2] = {s.c1, s.c2};
+    for (int l = 0; l < 2; l++) {
+        size_t kw_u = chans[l], kx = next_pow2(kx_u), kw = next_pow2(kw_u), rn = next_pow2(s.k);
+        Node c; c.kind = OP_CONV; c.conv = std::make_shared<ConvLayer>(synthetic_conv(kw, kx, n_p, rn, kw_u, s.k, n_u, g.next()));
+        for (size_t i = 0; i < kw; i++) for (size_t j = kx_u; j < kx; j++) for (size_t a = 0; a < rn * rn; a++) c.conv->filter[(i * kx + j) * rn * rn + a] = 0;   // padded input channels
+        m.nodes.push_back(c);
+        Node r; r.kind = OP_REQUANT; r.rq = synthetic_requant(ceil_log2(s.k * s.k * kx_u) + 2, 2 * (Q_BIT_LEN - 1) + ceil_log2(s.k * s.k * kx_u + 1)); m.nodes.push_back(r);   // convolution.rs:362-366 output_bitsize
+        Node a; a.kind = OP_RELU; m.nodes.push_back(a);
+        Node p; p.kind = OP_POOL; p.pool_c = kw; p.pool_h = p.pool_w = n_p; m.nodes.push_back(p);
+        kx_u = kw_u; n_u = (n_u - s.k + 1) / 2; n_p /= 2;
+    }
+    size_t in_u_c = s.c2, in_p = next_pow2(s.c2) * n_p * n_p;       // flatten: [C][n_p][n_p] row-major, real region [c2][n_u][n_u]
+    size_t outs_u[3] = {s.f1, s.f2, s.f3}; size_t ncols = in_p;
+    for (int l = 0; l < 3; l++) {
+        Node d; d.kind = OP_DENSE; d.nrows = next_pow2(outs_u[l]); d.ncols = ncols;
+        d.weights.assign(d.nrows * d.ncols, 0); d.bias.assign(d.nrows, 0);
+        for (size_t r = 0; r < outs_u[l]; r++) {
+            for (size_t c = 0; c < d.ncols; c++) {
+                bool real = l == 0 ? ((c / (n_p * n_p)) < in_u_c && ((c / n_p) % n_p) < n_u && (c % n_p) < n_u) : c < outs_u[l - 1];
+                Element w = (Element)(g.next() % 255) - 127; if (real) d.weights[r * d.ncols + c] = w;
+            }
+            d.bias[r] = (Element)(g.next() % 255) - 127;
+        }
+        m.nodes.push_back(d);
+        if (l < 2) {
+            Node r; r.kind = OP_REQUANT; r.rq = synthetic_requant(ceil_log2(d.ncols), 2 * (Q_BIT_LEN - 1) + ceil_log2(d.ncols) + 1); m.nodes.push_back(r);
+            Node a; a.kind = OP_RELU; m.nodes.push_back(a);
+        }
+        ncols = d.nrows;
+    }
+    return m;
+}
+static inline std::vector<Element> synthetic_cnn_input(int small, u64 seed) {
+    CnnShape s = cnn_shape(small); size_t n_p = next_pow2(s.img);
+    return synthetic_conv_input(next_pow2(s.c0), n_p, s.c0, s.img, seed);
 }
 static inline std::vector<Element> synthetic_input(size_t width, u64 seed) { SplitMix64 g(seed); std::vector<Element> v(width); for (auto &x : v) x = (Element)(g.next() % 128); return v; }
 

@@ -399,3 +399,23 @@ def fft_ext(rows, inverse=False):
     r, n = a.shape[0], a.shape[1]
     lib().dpo_fft_ext(ptr(a), C.c_uint64(r), C.c_uint64(n), C.c_int(int(inverse)))
     return a
+
+
+def cnn_prove(small, seed_model, seed_input, label=b"m2vec", cap=1 << 23, want_proof=True):
+    out = np.zeros(cap if want_proof else 1, dtype=np.uint64)
+    n = C.c_uint64()
+    ms = (C.c_double * 2)()
+    rc = lib().dpo_cnn_prove(C.c_int(int(small)), C.c_uint64(seed_model), C.c_uint64(seed_input), label, ptr(out) if want_proof else None, C.c_uint64(cap), C.byref(n), ms)
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return (out[:n.value].copy() if want_proof else None), (ms[0], ms[1])
+
+
+def synthetic_cnn(small, seed_model, seed_input):
+    dl, wl, il = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib().dpo_synthetic_cnn(C.c_int(int(small)), C.c_uint64(seed_model), C.c_uint64(seed_input), None, C.c_uint64(0), C.byref(dl), None, C.c_uint64(0), C.byref(wl), None, C.byref(il))
+    desc = np.zeros(dl.value, dtype=np.int64); data = np.zeros(wl.value, dtype=np.int64); inp = np.zeros(il.value, dtype=np.int64)
+    rc = lib().dpo_synthetic_cnn(C.c_int(int(small)), C.c_uint64(seed_model), C.c_uint64(seed_input), ptr(desc), C.c_uint64(desc.size), C.byref(dl), ptr(data), C.c_uint64(data.size), C.byref(wl), ptr(inp), C.byref(il))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return desc.reshape(-1, 9), data, inp

@@ -48,3 +48,16 @@ def test_conv_layer_proof_invariants_hold(kw, kx, n_x, rn, kw_u, k_u, kx_u, n_x_
     assert flat.size > 100
     assert (flat == O.conv_prove(filt, bias, uo, x)).all()
     assert not (flat == O.conv_prove(filt, bias, uo, x, label=b"other"))[: flat.size // 2].all()
+
+
+def test_small_cnn_full_proof_passes_every_invariant():
+    """conv -> requant -> relu -> maxpool (x2) -> 3 dense layers, full Prover::prove on the CPU checker: the conv
+    invariants, the pooling input-claim identity (pooling.rs:453-490), requant recombination, the LogUp fractional-sum
+    cancellation across lookups and tables, the model-input claim and Basefold's batch sanity checks all hold."""
+    flat, _ = O.cnn_prove(1, 3, 4)
+    assert flat.size > 10000
+    again, _ = O.cnn_prove(1, 3, 4)
+    assert (flat == again).all()
+    desc, data, inp = O.synthetic_cnn(1, 3, 4)
+    kinds = list(desc[:, 0])
+    assert kinds == [3, 1, 2, 4, 3, 1, 2, 4, 0, 1, 2, 0, 1, 2, 0]
