@@ -427,6 +427,23 @@ class ZkmlContext:
             pass
 
 
+class ModelContext(ZkmlContext):
+    """Context::generate for a general layer list (Dense / Requant / ReLU / Convolution / Maxpool2D), see
+    dph_model_context_new: desc (n_nodes, 9) int64, data = weights in node order, input_len = padded input length."""
+
+    def __init__(self, desc, data, input_len):
+        _pcs_setup()
+        H = host()
+        H.dph_model_context_new.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        H.dph_zkml_context_free.argtypes = [C.c_void_p]
+        H.dph_zkml_prove.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        d = np.ascontiguousarray(desc, dtype=np.int64).reshape(-1, 9)
+        w = np.ascontiguousarray(data, dtype=np.int64)
+        self.h = C.c_void_p()
+        hcheck(H.dph_model_context_new(_ptr(d), d.shape[0], _ptr(w), int(input_len), C.byref(self.h)))
+        self._out = np.zeros(1 << 23, dtype=np.uint64)
+
+
 def sumcheck_prove_batch_polys(T, mles, products, max_nv, label=b"m2vec"):
     """IOPProverState::prove_batch_polys (devirgo split into T contiguous slices) through the C++ host mirror."""
     H = host()

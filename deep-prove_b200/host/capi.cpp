@@ -109,10 +109,9 @@ int dph_pcs_batch_open(dp_mle *const *polys, uint32_t n, uint32_t full_log, cons
 
 // ---- zkml MLP prover (host/zkml.hpp) ----
 #include "zkml.hpp"
-#include "conv.hpp"
 #include <chrono>
 namespace {
-struct ZkHandle { dp::zkml::Model model; dp::zkml::Context ctx; std::vector<std::vector<dp::zkml::Element>> trace; std::vector<dp::zkml::Element> trace_input; };
+struct ZkHandle { dp::zkml::Model model; dp::zkml::Context ctx; std::vector<std::vector<dp::zkml::Element>> trace; std::vector<dp::zkml::Element> trace_input; std::map<size_t, dp::zkml::ConvData> trace_conv; };
 }
 extern "C" {
 
@@ -149,10 +148,10 @@ int dph_zkml_prove(void *handle, const int64_t *input, int mode, const char *lab
     using namespace dp::zkml;
     ZkHandle *h = (ZkHandle *)handle;
     size_t w = h->model.input_len;
-    if (mode == 0 || mode == 1) { h->trace_input.assign(input, input + w); h->trace = run(h->model, h->trace_input); if (mode == 1) return 0; }
+    if (mode == 0 || mode == 1) { h->trace_input.assign(input, input + w); h->trace_conv.clear(); h->trace = run(h->ctx, h->trace_input, &h->trace_conv); if (mode == 1) return 0; }
     BasicTranscript t(label);
     Prover<BasicTranscript> prover(h->ctx, t);
-    Proof p = prover.prove(h->trace_input, h->trace);
+    Proof p = prover.prove(h->trace_input, h->trace, &h->trace_conv);
     if (out) {
         std::vector<uint64_t> f = p.flatten(h->model.nodes.size());
         *out_len = f.size();
@@ -188,7 +187,7 @@ struct ZkPool {
                     dp::zkml::Proof p = prover.prove(h->trace_input);
                     std::vector<uint64_t> bytes = p.flatten(h->model.nodes.size());
                     if (bytes.empty()) throw dp::Error(DP_ERR_STATE, "empty proof");
-                } else { dp::zkml::Proof p = prover.prove(h->trace_input, h->trace); (void)p; }
+                } else { dp::zkml::Proof p = prover.prove(h->trace_input, h->trace, &h->trace_conv); (void)p; }
             } catch (const std::exception &e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.what(); }
             { std::lock_guard<std::mutex> lk(mu); inflight--; if (pending == 0 && inflight == 0) done_cv.notify_all(); }
         }
@@ -307,6 +306,36 @@ extern "C" int dph_conv_prove(uint32_t kw, uint32_t kx, uint32_t n_x, uint32_t r
     std::vector<u64> fl = flatten_conv_proof(pr, in_claim);
     *out_len = fl.size();
     if (out) { if (fl.size() > cap) throw Error(DP_ERR_INVALID, "dph_conv_prove: output buffer too small"); memcpy(out, fl.data(), 8 * fl.size()); }
+    return 0;
+    DPH_CATCH
+}
+
+// General model builder: `desc` holds 9 int64 per node {kind, 8 shape words} and `data` the weights in node order
+// (kind 0 Dense {nrows, ncols}: weights then bias; 1 Requant {right_shift, fp_scale, multiplier, intermediate_bits};
+//  2 ReLU; 3 Conv {kw, kx, nw, real_nw, unpadded_out[3]}: filter then bias; 4 Maxpool {C, H, W}).  Same handle type as
+// dph_zkml_context_new: dph_zkml_prove / dph_zkml_prove_concurrent / dph_zkml_context_free apply.
+extern "C" int dph_model_context_new(const int64_t *desc, uint32_t n_nodes, const int64_t *data, uint64_t input_len, void **out) {
+    DPH_TRY
+    using namespace dp::zkml;
+    auto *h = new ZkHandle();
+    h->model.input_len = input_len;
+    const int64_t *w = data;
+    for (uint32_t i = 0; i < n_nodes; i++) {
+        const int64_t *d = desc + 9 * (size_t)i; Node n;
+        switch (d[0]) {
+        case 0: n.op = Op::Dense; n.nrows = d[1]; n.ncols = d[2]; n.weights.assign(w, w + n.nrows * n.ncols); w += n.nrows * n.ncols; n.bias.assign(w, w + n.nrows); w += n.nrows; break;
+        case 1: n.op = Op::Requant; n.rq.right_shift = d[1]; n.rq.fp_scale = d[2]; n.rq.fixed_point_multiplier = d[3]; n.rq.intermediate_bit_size = d[4]; break;
+        case 2: n.op = Op::Relu; break;
+        case 3: { n.op = Op::Conv; n.kw = d[1]; n.kx = d[2]; n.nw = d[3]; n.real_nw = d[4]; for (int k = 0; k < 3; k++) n.unpadded_out[k] = d[5 + k];
+                  size_t fl = n.kw * n.kx * n.real_nw * n.real_nw; n.weights.assign(w, w + fl); w += fl; n.bias.assign(w, w + n.kw); w += n.kw; break; }
+        case 4: n.op = Op::Pool; n.pool_c = d[1]; n.pool_h = d[2]; n.pool_w = d[3]; break;
+        default: delete h; throw Error(DP_ERR_INVALID, "dph_model_context_new: unknown node kind");
+        }
+        h->model.nodes.push_back(std::move(n));
+    }
+    h->ctx = Context::generate(h->model);
+    check(dp_synchronize());
+    *out = h;
     return 0;
     DPH_CATCH
 }

@@ -3,10 +3,10 @@
 //   :368-458, :697-1077), hadamard::prove (layers/hadamard.rs:83-126), Prover::{prove_batch_fft, prove_batch_ifft,
 //   delegate_matrix_evaluation} (iop/prover.rs:164-212,295-399), Tensor::fft_conv (tensor.rs:458-523).
 // Same structure and names as the reference; every tensor lives in HBM (include/deepprove_b200.h), the host keeps the
-// transcript, the O(log n) scalars and the claims.  sumchecks fold their operands in place on the device, so operands
-// that are needed again are produced fresh (fix_high_variables / pad_rows / repeat return new tensors).
+// transcript, the O(log n) scalars and the claims.  dp_sc_* borrows its operands and never modifies them, so resident
+// tensors (filters, the inference trace) are shared by any number of proofs.
 #pragma once
-#include "zkml.hpp"
+// included from the middle of zkml.hpp (needs Claim, Element, to_base; Prover below needs this file)
 
 namespace dp {
 namespace zkml {
@@ -156,7 +156,7 @@ struct Convolution {
     }
     // Convolution::prove_convolution_step (convolution.rs:697-1077)
     template <class T>
-    Claim prove_convolution_step(T &t, const Claim &last_claim_in, ConvData &pd, ConvProof &out) const {
+    Claim prove_convolution_step(T &t, const Claim &last_claim_in, const ConvData &pd, ConvProof &out) const {
         size_t lfs = ceil_log2(filter_size()), lkw = ceil_log2(kw), lrow = ceil_log2(row_len());
         out.clearing_proof = hadamard_prove(t, last_claim_in, pd.output_as_element, clearing_tensor());
         Claim last_claim{out.clearing_proof.sumcheck.point, out.clearing_proof.individual_claim[0]};
@@ -207,25 +207,6 @@ struct Convolution {
         return fin;
     }
 };
-
-inline void flat_evec(std::vector<u64> &o, const ExtVec &v) { o.push_back(v.size()); for (auto &e : v) flat_e(o, e); }
-// same layout as the CPU checker's flattening: ConvProof field order (convolution.rs:97-121), the two commitment claims, the input claim
-inline std::vector<u64> flatten_conv_proof(const ConvProof &p, const Claim &input_claim) {
-    std::vector<u64> o;
-    flat_iop(o, p.fft_proof); flat_evec(o, p.fft_claims); flat_iop(o, p.fft_proof_weights); flat_iop(o, p.ifft_proof);
-    o.push_back(p.fft_delegation.proofs.size()); for (auto &q : p.fft_delegation.proofs) flat_iop(o, q);
-    o.push_back(p.fft_delegation_weights.proofs.size()); for (auto &q : p.fft_delegation_weights.proofs) flat_iop(o, q);
-    o.push_back(p.ifft_delegation.proofs.size()); for (auto &q : p.ifft_delegation.proofs) flat_iop(o, q);
-    flat_iop(o, p.hadamard_proof); flat_evec(o, p.ifft_claims); flat_evec(o, p.fft_weight_claims);
-    o.push_back(p.fft_delegation.claims.size()); for (auto &c : p.fft_delegation.claims) flat_evec(o, c);
-    o.push_back(p.fft_delegation_weights.claims.size()); for (auto &c : p.fft_delegation_weights.claims) flat_evec(o, c);
-    o.push_back(p.ifft_delegation.claims.size()); for (auto &c : p.ifft_delegation.claims) flat_evec(o, c);
-    flat_evec(o, p.hadamard_claims); flat_e(o, p.bias_claim); flat_evec(o, p.partial_evals);
-    flat_iop(o, p.clearing_proof.sumcheck); flat_evec(o, p.clearing_proof.individual_claim);
-    flat_evec(o, p.filter_claim.point); flat_e(o, p.filter_claim.eval); flat_evec(o, p.bias_poly_claim.point); flat_e(o, p.bias_poly_claim.eval);
-    flat_evec(o, input_claim.point); flat_e(o, input_claim.eval);
-    return o;
-}
 
 }  // namespace zkml
 }  // namespace dp

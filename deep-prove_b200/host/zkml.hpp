@@ -40,8 +40,12 @@ struct Requant {                                            // layers/requant.rs
     }
 };
 
-enum class Op { Dense, Requant, Relu };
-struct Node { Op op; size_t nrows = 0, ncols = 0; std::vector<Element> weights, bias; Requant rq; };
+enum class Op { Dense, Requant, Relu, Conv, Pool };
+struct Node {
+    Op op; size_t nrows = 0, ncols = 0; std::vector<Element> weights, bias; Requant rq;
+    size_t kw = 0, kx = 0, nw = 0, real_nw = 0, unpadded_out[3] = {0, 0, 0};     // Conv: padded layer, `weights` = filter [kw][kx][real_nw][real_nw], `bias` [kw]
+    size_t pool_c = 0, pool_h = 0, pool_w = 0;                                   // Pool: padded input shape [C][H][W] (Maxpool2D, kernel = stride = 2)
+};
 struct Model { std::vector<Node> nodes; size_t input_len = 0; };
 
 // TableType with the enum's derive(Ord) order (lookup/context.rs:53-63): Relu < Range < Clamping(size)
@@ -143,12 +147,20 @@ SamePolyProof same_poly_prove(const DeviceMle &poly, const std::vector<Claim> &c
     return {res.first, res.second.get_mle_final_evaluations()};
 }
 
+}  // namespace zkml
+}  // namespace dp
+#include "conv.hpp"   // FFT-convolution layer (uses the definitions above; the Prover below uses it)
+namespace dp {
+namespace zkml {
+
 struct DenseProof { IOPProof sumcheck; Ext bias_eval; ExtVec individual_claims; };
+struct PoolingProof { IOPProof sumcheck; LogUpProof lookup; ExtVec zerocheck_evals; size_t variable_gap = 0; std::vector<Digest> commitments; };   // layers/pooling.rs:60-75
 struct RequantProof { IOPProof io_accumulation; ExtVec accumulation_evals; LogUpProof clamping_lookup, shifted_lookup; std::vector<Digest> commitments; };
 struct ActivationProof { SamePolyProof io_accumulation; LogUpProof lookup; std::vector<Digest> commits; };
 struct TableProof { Digest multiplicity_commit; LogUpProof lookup; };
 struct Proof {   // zkml/src/iop/mod.rs:21-31 + commit::context::ModelOpeningProof
     std::map<size_t, DenseProof> dense; std::map<size_t, RequantProof> requant; std::map<size_t, ActivationProof> activation;
+    std::map<size_t, ConvProof> conv; std::map<size_t, PoolingProof> pooling;
     std::vector<TableProof> table_proofs; BasefoldProof batch_proof; std::vector<BasefoldProof> trivial_proofs;
     std::vector<u64> flatten(size_t n_nodes) const;
 };
@@ -163,6 +175,8 @@ class Context {
             if (n.op == Op::Dense) max_len = std::max(max_len, std::max(n.nrows * n.ncols, n.nrows));
             if (n.op == Op::Requant) { tabs[TableType::range()] = 1; tabs[TableType::clamping(n.rq.clamping_size())] = 1; }
             if (n.op == Op::Relu) tabs[TableType::relu()] = 1;
+            if (n.op == Op::Conv) max_len = std::max(max_len, std::max(n.weights.size(), n.kw * n.nw * n.nw));
+            if (n.op == Op::Pool) { tabs[TableType::range()] = 1; max_len = std::max(max_len, n.pool_c * n.pool_h * n.pool_w); }   // pooling.rs:130-170
         }
         for (auto &kv : tabs) max_len = std::max(max_len, (size_t)1 << kv.first.multiplicity_poly_vars());   // context.rs:171-175
         size_t p2 = 1; while (p2 < max_len) p2 <<= 1;
@@ -172,6 +186,15 @@ class Context {
                 DeviceMle poly = DeviceMle::from_evaluations_vec(to_base(*kv.second));
                 c.model_comms[id][kv.first] = {Basefold::commit(c.pp, poly), poly};
             }
+        } else if (m.nodes[id].op == Op::Conv) {   // convolution.rs:532-540: ConvBias, ConvFilter (BTreeMap order)
+            const Node &n = m.nodes[id];
+            Convolution cv; cv.kw = n.kw; cv.kx = n.kx; cv.nw = n.nw; cv.real_nw = n.real_nw; cv.filter = n.weights; cv.bias = n.bias;
+            for (int i = 0; i < 3; i++) cv.unpadded_out[i] = n.unpadded_out[i];
+            cv.load();
+            DeviceMle bias_poly = DeviceMle::from_evaluations_vec(to_base(n.bias));
+            c.model_comms[id]["ConvBias"] = {Basefold::commit(c.pp, bias_poly), bias_poly};
+            c.model_comms[id]["ConvFilter"] = {Basefold::commit(c.pp, cv.filter_mle), cv.filter_mle};
+            c.convs[id] = std::move(cv);
         }
         for (auto &kv : tabs) {   // get_merged_table_column (lookup/context.rs:158-296), resident for every proof
             TableData td; std::vector<std::vector<u64>> cols;
@@ -189,22 +212,39 @@ class Context {
     const Model *model = nullptr; BasefoldProverParams pp;
     std::map<size_t, std::map<std::string, ProverCommitment>> model_comms;
     std::map<TableType, TableData> tables;
+    std::map<size_t, Convolution> convs;                      // resident conv layers (weights, FFT'd filters)
 };
 
 struct LogUpWitness { bool table = false; std::vector<ProverCommitment> commits; std::vector<DeviceMle> column_evals; DeviceMle multiplicity_evals; size_t columns_per_instance = 1; TableType tt{0, 0}; };
 
 // quantised inference (model run): outputs[i] = output tensor of node i
-inline std::vector<std::vector<Element>> run(const Model &m, const std::vector<Element> &input) {
+// Maxpool2D::op (pooling.rs:667-677) on a padded [C][H][W] tensor
+inline std::vector<Element> maxpool2d(const std::vector<Element> &x, size_t C, size_t H, size_t W) {
+    std::vector<Element> o(C * (H / 2) * (W / 2));
+    for (size_t c = 0; c < C; c++) for (size_t r = 0; r < H / 2; r++) for (size_t cc = 0; cc < W / 2; cc++) {
+        Element mx = x[(c * H + 2 * r) * W + 2 * cc];
+        for (size_t a = 0; a < 2; a++) for (size_t b = 0; b < 2; b++) mx = std::max(mx, x[(c * H + 2 * r + a) * W + 2 * cc + b]);
+        o[(c * (H / 2) + r) * (W / 2) + cc] = mx;
+    }
+    return o;
+}
+inline std::vector<std::vector<Element>> run(const Model &m, const std::vector<Element> &input, const Context *ctx = nullptr, std::map<size_t, ConvData> *conv_data = nullptr) {
     std::vector<std::vector<Element>> outs; std::vector<Element> cur = input;
     for (auto &n : m.nodes) {
         std::vector<Element> o;
         if (n.op == Op::Dense) { o.resize(n.nrows); for (size_t r = 0; r < n.nrows; r++) { Element a = n.bias[r]; const Element *w = &n.weights[r * n.ncols]; for (size_t c = 0; c < n.ncols; c++) a += w[c] * cur[c]; o[r] = a; } }
         else if (n.op == Op::Requant) { Element lim = (Element)1 << n.rq.intermediate_bit_size; for (Element e : cur) { if (e > lim || e < -lim) throw Error(DP_ERR_INVALID, "Could not apply requantisation, tensor element had absolute value too large"); o.push_back(n.rq.apply(e)); } }
-        else for (Element e : cur) o.push_back(relu(e));
+        else if (n.op == Op::Relu) for (Element e : cur) o.push_back(relu(e));
+        else if (n.op == Op::Pool) o = maxpool2d(cur, n.pool_c, n.pool_h, n.pool_w);
+        else {
+            if (!ctx || !conv_data) throw Error(DP_ERR_INVALID, "run: a convolution needs the Context (resident FFT'd filters)");
+            ConvData cd; o = ctx->convs.at(outs.size()).op(cur, cd); (*conv_data)[outs.size()] = std::move(cd);
+        }
         outs.push_back(o); cur = o;
     }
     return outs;
 }
+inline std::vector<std::vector<Element>> run(const Context &ctx, const std::vector<Element> &input, std::map<size_t, ConvData> *conv_data) { return run(*ctx.model, input, &ctx, conv_data); }
 
 // Prover<'a, E, T, PCS> (iop/prover.rs:40-60)
 template <class T>
@@ -212,9 +252,9 @@ class Prover {
   public:
     Prover(const Context &ctx, T &transcript) : ctx_(ctx), t_(transcript) {}
 
-    Proof prove(const std::vector<Element> &input) { return prove(input, run(*ctx_.model, input)); }
+    Proof prove(const std::vector<Element> &input) { std::map<size_t, ConvData> cd; auto outs = run(ctx_, input, &cd); return prove(input, outs, &cd); }
     // Prover::prove(full_trace): the inference trace is an INPUT of proving (zkml/src/bin/bench.rs:390-408 times only this)
-    Proof prove(const std::vector<Element> &input, const std::vector<std::vector<Element>> &outs) {
+    Proof prove(const std::vector<Element> &input, const std::vector<std::vector<Element>> &outs, const std::map<size_t, ConvData> *conv_data = nullptr) {
         const Model &m = *ctx_.model;
         auto node_input = [&](size_t id) -> const std::vector<Element> & { return id == 0 ? input : outs[id - 1]; };
         static const bool prof = getenv("DP_HOST_PROF") != nullptr;
@@ -231,7 +271,12 @@ class Prover {
             const Node &n = m.nodes[id];
             if (n.op == Op::Dense) last = prove_dense(id, n, last, node_input(id));
             else if (n.op == Op::Requant) last = prove_requant(id, n, last);
-            else last = prove_activation(id, last, outs[id]);
+            else if (n.op == Op::Relu) last = prove_activation(id, last, outs[id]);
+            else if (n.op == Op::Pool) last = prove_pooling(id, n, last);
+            else {
+                if (!conv_data || !conv_data->count(id)) throw Error(DP_ERR_INVALID, "prove: no convolution proving data in the trace");
+                last = prove_convolution(id, last, conv_data->at(id));
+            }
         }
         double t2 = now();
         prove_tables();
@@ -253,7 +298,7 @@ class Prover {
         auto node_input = [&](size_t id) -> const std::vector<Element> & { return id == 0 ? input : outs[id - 1]; };
         std::map<TableType, std::unordered_map<Element, u64>> element_count;
         std::vector<std::vector<u64>> cols;                      // every column to commit, in creation order
-        struct Slot { size_t node; size_t witness; bool table; };  // where commitment k goes
+        struct Slot { size_t node; size_t witness; bool table; bool column = true; };  // where commitment k goes (column: also a lookup column)
         std::vector<Slot> slots;
         for (size_t id = 0; id < m.nodes.size(); id++) {
             const Node &n = m.nodes[id];
@@ -278,6 +323,19 @@ class Prover {
                 for (size_t i = 0; i < a.size(); i++) element_count[tt][a[i] + COLUMN_SEPARATOR * b[i]]++;
                 lookup_witness_[id] = {w};
                 for (auto *v : {&a, &b}) { cols.push_back(to_base(*v)); slots.push_back({id, 0, false}); }
+            } else if (n.op == Op::Pool) {   // pooling.rs:210-271 + compute_polys (:686-771): out - in(2r+dr, 2c+dc), (dr,dc) = (0,0),(1,0),(0,1),(1,1)
+                TableType tr = TableType::range(); LogUpWitness w; w.tt = tr; w.columns_per_instance = 1;
+                const auto &x = node_input(id); const auto &out = outs[id];
+                size_t C = n.pool_c, H = n.pool_h, W = n.pool_w;
+                static const size_t DR[4] = {0, 1, 0, 1}, DC[4] = {0, 0, 1, 1};
+                lookup_witness_[id] = {w};
+                for (size_t k = 0; k < 4; k++) {
+                    std::vector<Element> d(out.size());
+                    for (size_t c = 0; c < C; c++) for (size_t r = 0; r < H / 2; r++) for (size_t cc = 0; cc < W / 2; cc++) { size_t oi = (c * (H / 2) + r) * (W / 2) + cc; d[oi] = out[oi] - x[(c * H + 2 * r + DR[k]) * W + 2 * cc + DC[k]]; }
+                    for (Element e : d) element_count[tr][e]++;
+                    cols.push_back(to_base(d)); slots.push_back({id, 0, false});
+                }
+                cols.push_back(to_base(out)); slots.push_back({id, 0, false, false});   // the output poly: committed, not a lookup column
             }
         }
         for (auto &kv : element_count) {   // table multiplicities (lookup/context.rs:675-737)
@@ -297,7 +355,7 @@ class Prover {
         for (size_t k = 0; k < slots.size(); k++) {
             ProverCommitment pc{comms[k], polys[k]};
             if (slots[k].table) { LogUpWitness &w = table_witness_[slots[k].witness]; w.commits.push_back(pc); w.multiplicity_evals = polys[k]; }
-            else { LogUpWitness &w = lookup_witness_[slots[k].node][slots[k].witness]; w.commits.push_back(pc); w.column_evals.push_back(polys[k]); }
+            else { LogUpWitness &w = lookup_witness_[slots[k].node][slots[k].witness]; w.commits.push_back(pc); if (slots[k].column) w.column_evals.push_back(polys[k]); }
         }
         constant_challenge_ = t_.get_and_append_challenge("table_constant");
         for (auto &kv : element_count) challenge_map_[kv.first] = kv.first.kind == 0 ? t_.get_and_append_challenge("Relu") : (kv.first.kind == 3 ? t_.get_and_append_challenge("Clamping") : Ext::one());
@@ -370,6 +428,48 @@ class Prover {
         return input_claim;
     }
 
+    // Convolution::prove (convolution.rs:609-636) -> prove_convolution_step, then add_common_claims (:1003-1010)
+    Claim prove_convolution(size_t id, const Claim &last_claim, const ConvData &pd) {
+        ConvProof cp; Claim in_claim = ctx_.convs.at(id).prove_convolution_step(t_, last_claim, pd, cp);
+        const auto &comms = ctx_.model_comms.at(id);
+        add_witness_claim(comms.at("ConvBias"), cp.bias_poly_claim);                  // BTreeMap order of PolyId
+        add_witness_claim(comms.at("ConvFilter"), cp.filter_claim);
+        proof_.conv[id] = cp;
+        return in_claim;
+    }
+    // Pooling::prove_pooling (layers/pooling.rs:342-519)
+    Claim prove_pooling(size_t id, const Node &n, const Claim &last_claim) {
+        std::vector<LogUpWitness> ws = lookup_witness_.at(id);
+        if (ws.size() != 1) throw Error(DP_ERR_INVALID, "Pooling only requires a lookup into one table type");
+        LogUpInput in = get_logup_input(ws[0]);
+        LogUpProof lp = logup_batch_prove(in, t_);
+        const ExtVec &lookup_point = lp.output_claims[0].point;
+        size_t nv = lookup_point.size(), ks = 4;
+        Ext bc = t_.get_and_append_challenge("batch_pooling");
+        DeviceMle beta_poly = DeviceMle::build_eq_x_r(lookup_point), last_beta = DeviceMle::build_eq_x_r(last_claim.point);
+        std::vector<DeviceMle> diffs = in.column_evals;
+        VirtualPolynomial vp(nv);
+        { std::vector<DeviceMle> all = diffs; all.push_back(beta_poly); vp.add_mle_list(all, Ext::one()); }   // zerocheck: prod_k (out - in_k) = 0
+        Ext comb = bc; for (auto &d : diffs) { vp.add_mle_list({d, beta_poly}, comb); comb *= bc; }
+        DeviceMle out_mle = ws[0].commits[ks].poly;
+        vp.add_mle_list({out_mle, last_beta}, comb);
+        auto res = IOPProverState::prove_parallel(std::move(vp), t_);
+        const ExtVec &fe = res.second.get_mle_final_evaluations(); const ExtVec &zc = res.first.point;
+        Ext output_eval = fe[ks + 1];
+        PoolingProof pp; pp.sumcheck = res.first; pp.lookup = lp;
+        for (size_t i = 0; i <= ks; i++) { Ext ev = i < ks ? fe[i] : output_eval; add_witness_claim(ws[0].commits[i], {zc, ev}); pp.commitments.push_back(ws[0].commits[i].comm.root); pp.zerocheck_evals.push_back(ev); }
+        size_t lw = ceil_log2(n.pool_w);
+        Ext r1 = t_.get_and_append_challenge("input_batching"), r2 = r1;            // `[challenge; 2]` is ONE challenge, copied (pooling.rs:453-456)
+        Ext m1 = Ext::one() - r1, m2 = Ext::one() - r2;
+        Ext mult[4] = {m1 * m2, m1 * r2, r1 * m2, r1 * r2};
+        Ext zc_in = Ext::zero(); for (size_t k = 0; k < ks; k++) zc_in += mult[k] * (output_eval - fe[k]);
+        Claim next; next.point.push_back(r1); next.point.insert(next.point.end(), zc.begin(), zc.begin() + (lw - 1));
+        next.point.push_back(r2); next.point.insert(next.point.end(), zc.begin() + (lw - 1), zc.end());
+        next.eval = zc_in; pp.variable_gap = lw - 1;
+        proof_.pooling[id] = pp;
+        return next;
+    }
+
     // prove_tables (iop/prover.rs:110-157)
     void prove_tables() {
         for (auto &w : table_witness_) {
@@ -403,6 +503,25 @@ inline void flat_logup(std::vector<u64> &o, const LogUpProof &p) {
     o.push_back(p.circuit_outputs.size()); for (auto &r : p.circuit_outputs) { o.push_back(r.size()); for (auto &e : r) flat_e(o, e); }
     o.push_back(p.table ? 1 : 0);
 }
+inline void flat_evec(std::vector<u64> &o, const ExtVec &v) { o.push_back(v.size()); for (auto &e : v) flat_e(o, e); }
+// same layout as the CPU checker's flattening: ConvProof field order (convolution.rs:97-121), the two commitment claims, the input claim
+inline std::vector<u64> flatten_conv_proof(const ConvProof &p, const Claim &input_claim) {
+    std::vector<u64> o;
+    flat_iop(o, p.fft_proof); flat_evec(o, p.fft_claims); flat_iop(o, p.fft_proof_weights); flat_iop(o, p.ifft_proof);
+    o.push_back(p.fft_delegation.proofs.size()); for (auto &q : p.fft_delegation.proofs) flat_iop(o, q);
+    o.push_back(p.fft_delegation_weights.proofs.size()); for (auto &q : p.fft_delegation_weights.proofs) flat_iop(o, q);
+    o.push_back(p.ifft_delegation.proofs.size()); for (auto &q : p.ifft_delegation.proofs) flat_iop(o, q);
+    flat_iop(o, p.hadamard_proof); flat_evec(o, p.ifft_claims); flat_evec(o, p.fft_weight_claims);
+    o.push_back(p.fft_delegation.claims.size()); for (auto &c : p.fft_delegation.claims) flat_evec(o, c);
+    o.push_back(p.fft_delegation_weights.claims.size()); for (auto &c : p.fft_delegation_weights.claims) flat_evec(o, c);
+    o.push_back(p.ifft_delegation.claims.size()); for (auto &c : p.ifft_delegation.claims) flat_evec(o, c);
+    flat_evec(o, p.hadamard_claims); flat_e(o, p.bias_claim); flat_evec(o, p.partial_evals);
+    flat_iop(o, p.clearing_proof.sumcheck); flat_evec(o, p.clearing_proof.individual_claim);
+    flat_evec(o, p.filter_claim.point); flat_e(o, p.filter_claim.eval); flat_evec(o, p.bias_poly_claim.point); flat_e(o, p.bias_poly_claim.eval);
+    flat_evec(o, input_claim.point); flat_e(o, input_claim.eval);
+    return o;
+}
+
 inline std::vector<u64> Proof::flatten(size_t n_nodes) const {
     std::vector<u64> o;
     auto fd = [&](const Digest &d) { for (int i = 0; i < 4; i++) o.push_back(d.v[i]); };
@@ -410,6 +529,8 @@ inline std::vector<u64> Proof::flatten(size_t n_nodes) const {
         if (dense.count(id)) { const auto &d = dense.at(id); o.push_back(100 + id); flat_iop(o, d.sumcheck); flat_e(o, d.bias_eval); o.push_back(d.individual_claims.size()); for (auto &e : d.individual_claims) flat_e(o, e); }
         if (requant.count(id)) { const auto &r = requant.at(id); o.push_back(200 + id); flat_iop(o, r.io_accumulation); o.push_back(r.accumulation_evals.size()); for (auto &e : r.accumulation_evals) flat_e(o, e); flat_logup(o, r.clamping_lookup); flat_logup(o, r.shifted_lookup); o.push_back(r.commitments.size()); for (auto &d : r.commitments) fd(d); }
         if (activation.count(id)) { const auto &a = activation.at(id); o.push_back(300 + id); flat_iop(o, a.io_accumulation.sumcheck); o.push_back(a.io_accumulation.evals.size()); for (auto &e : a.io_accumulation.evals) flat_e(o, e); flat_logup(o, a.lookup); o.push_back(a.commits.size()); for (auto &d : a.commits) fd(d); }
+        if (conv.count(id)) { o.push_back(400 + id); std::vector<u64> c = flatten_conv_proof(conv.at(id), Claim()); o.insert(o.end(), c.begin(), c.end()); }
+        if (pooling.count(id)) { const auto &q = pooling.at(id); o.push_back(500 + id); flat_iop(o, q.sumcheck); flat_logup(o, q.lookup); flat_evec(o, q.zerocheck_evals); o.push_back(q.variable_gap); o.push_back(q.commitments.size()); for (auto &d : q.commitments) fd(d); }
     }
     o.push_back(table_proofs.size()); for (auto &t : table_proofs) { fd(t.multiplicity_commit); flat_logup(o, t.lookup); }
     o.push_back(trivial_proofs.size());

@@ -1,0 +1,26 @@
+"""Full zkml proof of a CNN (conv -> requant -> relu -> maxpool, twice, then three dense layers) on the device against
+the CPU checker: identical flat proof (every layer proof, table proofs and the batched Basefold opening).  The large
+case is SURVEY.md 8(d) Cfg 3, CNN-264k in its padded form."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("small", [1, 0])
+def test_cnn_full_proof(gpu, small):
+    desc, data, x = O.synthetic_cnn(small, 3, 4)
+    ctx = gpu.ModelContext(desc, data, x.size)
+    got = ctx.prove(x)
+    exp, _ = O.cnn_prove(small, 3, 4)
+    assert got.shape == exp.shape
+    if not (got == exp).all():
+        first = int(np.argmax(got != exp))
+        raise AssertionError("first difference at word %d of %d" % (first, exp.size))
+    # a stored trace can be proved again (resident tensors are borrowed, never modified)
+    ctx.run_inference(x)
+    assert (ctx.prove_trace(want_proof=True) == exp).all()
+    assert (ctx.prove_trace(want_proof=True) == exp).all()
+    ctx.free()

@@ -40,7 +40,7 @@ def main():
     slices = [splitmix_f(s, hi - lo, skip=lo) for s in (1, 2, 3)]
 
     def sharded():
-        mles = [dp.Mle.upload(a, False) for a in slices]      # the prover consumes its inputs (in-place folds)
+        mles = [dp.Mle.upload(a, False) for a in slices]
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
