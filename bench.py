@@ -248,6 +248,55 @@ class DenseWorkload:
     flush = True
 
 
+class CnnWorkload:
+    """CNN-264k (SURVEY.md 8(d) Cfg 3) in its padded form: conv5x5 -> requant -> relu -> maxpool (x2) -> fc x3 on a
+    3x32x32 input; the arrays come from deep-prove_b200/models.py and both arms prove the identical model and input."""
+    STREAMS = 16
+    units_per_step = STREAMS
+
+    def __init__(self):
+        sys.path.insert(0, os.path.join(ROOT, "deep-prove_b200"))
+        import models
+        self.desc, self.data, self.x, self.n_params = models.cnn(seed=1)
+        self.name = ("CNN-264k: conv5x5(12) -> requant -> relu -> maxpool -> conv5x5(33) -> requant -> relu -> maxpool -> fc 247 -> fc 173 -> fc 10 "
+                     "on 3x32x32 (%d parameters, padded to powers of two), BIT_LEN 8, full zkml Prover::prove" % self.n_params)
+        # big streaming parts of one proof: fix_high over the fc1 matrix (2^20 Base) + Basefold batch_open over the 2^20-sized commitments
+        n = 1 << 20
+        self.alg_bytes = 8 * n + (16 * n + 8 * n) + 240 * n
+        self.h2d = None
+        self.d2h = None
+
+    def setup_device(self, dp):
+        self.dp = dp
+        self.ctx = dp.ModelContext(self.desc, self.data, self.x.size)
+        proof = self.ctx.prove(self.x)
+        self.d2h = int(proof.size * 8)
+        self.h2d = int(8 * self.x.size + 8 * 600_000)     # input + the witness columns uploaded per proof (requant/relu/pool columns)
+        self.ctx.run_inference(self.x)
+        dp.lib().dp_synchronize()
+
+    def step_resident(self, i):
+        self.ctx.prove_trace()
+
+    def step_e2e(self, i):
+        return self.ctx.prove(self.x)
+
+    def run_resident(self, k, device):
+        self.ctx.prove_concurrent(self.STREAMS, k * self.units_per_step, device=device, e2e=False)
+
+    def run_e2e(self, k, device):
+        self.ctx.prove_concurrent(self.STREAMS, k * self.units_per_step, device=device, e2e=True)
+
+    def cpu_step(self, O, i):
+        _, ms = O.model_prove(self.desc, self.data, self.x, want_proof=False)
+        return ms[1] * 1e-3
+
+    cpu_sample = "1 full proof of the same model and input per CPU step, i.e. 1/16 of a GPU step (Context::generate not counted)"
+    cpu_returns_seconds = True
+    l2_note = ("%d proofs in flight per GPU (aggregate working set >> the 126 MB L2); single-stream latency is measured with a 256 MiB L2 flush between proofs" % STREAMS)
+    flush = True
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -285,7 +334,7 @@ def cpu_arm(wl, O, steps, warm):
 
 
 # "Dense 4M proving time 2335 ms" (README.md:18; hardware and exact architecture NOT stated)
-PUBLISHED = {"dense4m": 1.0 / 2.335}
+PUBLISHED = {"dense4m": 1.0 / 2.335, "cnn264k": 1.0 / 1.242}   # and "CNN 264k ... proving time 1242 ms" (README.md:17)
 
 
 def main():
@@ -294,13 +343,13 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dense4m", choices=["dense4m", "sumcheck20", "basefold24"])
+    ap.add_argument("--workload", default="dense4m", choices=["dense4m", "cnn264k", "sumcheck20", "basefold24"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    wl = {"dense4m": DenseWorkload, "sumcheck20": SumcheckWorkload, "basefold24": BasefoldWorkload}[args.workload]()
+    wl = {"dense4m": DenseWorkload, "cnn264k": CnnWorkload, "sumcheck20": SumcheckWorkload, "basefold24": BasefoldWorkload}[args.workload]()
     W = max(args.warmup, 0)
     dtype = "u64 (Goldilocks / GoldilocksExt2 modular integers)"
 
@@ -320,7 +369,7 @@ def main():
         }))
         return
 
-    K = args.steps if args.steps is not None else {"dense4m": 6, "sumcheck20": 20, "basefold24": 5}[args.workload]
+    K = args.steps if args.steps is not None else {"dense4m": 6, "cnn264k": 6, "sumcheck20": 20, "basefold24": 5}[args.workload]
     import torch
     import dpb200 as dp
     if not torch.cuda.is_available() or dp.device_count() <= 0:
@@ -435,7 +484,7 @@ def main():
                        "parallelism": "replicas x%d GPUs (no data-path collective)%s" % (world, (", %d concurrent independent proofs per GPU" % wl.STREAMS) if hasattr(wl, "STREAMS") else ""),
                        "proofs_per_step": ups,
                        "single_stream_latency_ms": latency_ms,
-                       "baseline_note": "vs_baseline divides by 1/2.335 s (reference README: Dense 4M proving time 2335 ms, hardware and exact architecture not stated)"},
+                       "baseline_note": "vs_baseline divides by the reference README's proving time (Dense 4M 2335 ms / CNN 264k 1242 ms; hardware and exact architecture not stated)"},
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": wl.h2d * ups, "d2h_bytes_per_step": wl.d2h * ups},
             "gpu_launches": int(launches),
             "clocks": clocks,

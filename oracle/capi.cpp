@@ -358,3 +358,37 @@ int dpo_synthetic_cnn(int small, u64 seed_model, u64 seed_input, int64_t *desc, 
     } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
 }
+
+// Prover::prove of a model given as the layer descriptor the product's model builder takes (deep-prove_b200/models.py):
+// 9 int64 per node {kind, 8 shape words}, weights in node order.
+extern "C" int dpo_model_prove(const int64_t *desc, u32 n_nodes, const int64_t *data, const int64_t *input, u64 input_len, const char *label,
+                               u64 *out, u64 cap, u64 *out_len, double *out_ms) {
+    try {
+        Model m; m.input_len = input_len; const int64_t *w = data;
+        for (u32 i = 0; i < n_nodes; i++) {
+            const int64_t *d = desc + 9 * (size_t)i; Node n;
+            switch (d[0]) {
+            case 0: n.kind = OP_DENSE; n.nrows = d[1]; n.ncols = d[2]; n.weights.assign(w, w + n.nrows * n.ncols); w += n.nrows * n.ncols; n.bias.assign(w, w + n.nrows); w += n.nrows; break;
+            case 1: n.kind = OP_REQUANT; n.rq.right_shift = d[1]; n.rq.fp_scale = d[2]; n.rq.fixed_point_multiplier = d[3]; n.rq.intermediate_bit_size = d[4]; break;
+            case 2: n.kind = OP_RELU; break;
+            case 3: { n.kind = OP_CONV; auto c = std::make_shared<ConvLayer>(); c->kw = d[1]; c->kx = d[2]; c->nw = d[3]; c->real_nw = d[4]; for (int k = 0; k < 3; k++) c->unpadded_out[k] = d[5 + k];
+                      size_t fl = c->kw * c->kx * c->real_nw * c->real_nw; c->filter.assign(w, w + fl); w += fl; c->bias.assign(w, w + c->kw); w += c->kw; n.conv = c; break; }
+            case 4: n.kind = OP_POOL; n.pool_c = d[1]; n.pool_h = d[2]; n.pool_w = d[3]; break;
+            default: throw std::runtime_error("dpo_model_prove: unknown node kind");
+            }
+            m.nodes.push_back(n);
+        }
+        std::vector<Element> in(input, input + input_len);
+        auto t0 = std::chrono::steady_clock::now();
+        ZkContext ctx = zk_context(m);
+        auto t1 = std::chrono::steady_clock::now();
+        Transcript t(label);
+        ModelProof p = zk_prove(ctx, in, t);
+        auto t2 = std::chrono::steady_clock::now();
+        if (out_ms) { out_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count(); out_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count(); }
+        std::vector<u64> f = flatten_model_proof(p, m.nodes.size());
+        if (out_len) *out_len = f.size();
+        if (out) { if (f.size() > cap) { g_err = "dpo_model_prove: output buffer too small"; return 2; } memcpy(out, f.data(), 8 * f.size()); }
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}

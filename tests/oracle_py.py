@@ -419,3 +419,14 @@ def synthetic_cnn(small, seed_model, seed_input):
     if rc:
         raise RuntimeError(lib().dpo_last_error().decode())
     return desc.reshape(-1, 9), data, inp
+
+
+def model_prove(desc, data, x, label=b"m2vec", cap=1 << 23, want_proof=True):
+    """Prover::prove of a model given as a layer descriptor (deep-prove_b200/models.py); returns (flat | None, (ctx_ms, prove_ms))"""
+    d = i64(desc).reshape(-1, 9); w = i64(data); xi = i64(x)
+    out = np.zeros(cap if want_proof else 1, dtype=np.uint64)
+    n = C.c_uint64(); ms = (C.c_double * 2)()
+    rc = lib().dpo_model_prove(ptr(d), C.c_uint32(d.shape[0]), ptr(w), ptr(xi), C.c_uint64(xi.size), label, ptr(out) if want_proof else None, C.c_uint64(cap), C.byref(n), ms)
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return (out[:n.value].copy() if want_proof else None), (ms[0], ms[1])

@@ -24,3 +24,17 @@ def test_cnn_full_proof(gpu, small):
     assert (ctx.prove_trace(want_proof=True) == exp).all()
     assert (ctx.prove_trace(want_proof=True) == exp).all()
     ctx.free()
+
+
+def test_cnn264k_from_descriptor(gpu):
+    """the bench's CNN-264k arrays (deep-prove_b200/models.py) through both arms"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deep-prove_b200"))
+    import models
+    desc, data, x, n_params = models.cnn(seed=7)
+    assert 250_000 < n_params < 270_000
+    ctx = gpu.ModelContext(desc, data, x.size)
+    got = ctx.prove(x)
+    exp, _ = O.model_prove(desc, data, x)
+    assert got.shape == exp.shape and (got == exp).all()
+    ctx.free()
