@@ -226,6 +226,123 @@ k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, 
     }
 }
 
+
+// ---- resident tail: every remaining round of a small sumcheck in ONE single-block launch -------------------
+// Once the tables are small (<= SC_TAIL_PAIRS pairs) a round is pure latency: launch + two-stage reduction + the
+// host's Fiat-Shamir.  The tail kernel stays resident instead: it writes each round message to mapped host memory,
+// raises the flag, and polls a mapped mailbox for the next challenge (one thread, one PCIe read in flight), so a
+// round costs the block-local work + two PCIe hops + the host sponge -- no launch, no cross-block stage.
+// The per-round bookkeeping the host does for k_sc_round (operand order, fold destinations, ping-pong buffers) is
+// replayed by thread 0 in shared memory.  The kernel cannot hang: the poll gives up after SC_TAIL_TIMEOUT cycles or
+// when the host posts the abort value.  Opt-in per handle (dp_sc_set_resident_tail): the caller promises not to
+// wait on other work in the same stream between rounds.
+static constexpr u32 SC_TAIL_MAXM = 96, SC_TAIL_MAXP = 48;
+static constexpr u64 SC_TAIL_PAIRS = 2048;
+static constexpr long long SC_TAIL_TIMEOUT = 6000000000LL;   // ~3 s at 1.9 GHz
+static constexpr u64 SC_TAIL_ABORT = ~0ULL, SC_TAIL_FAILED = ~0ULL - 1;
+struct TMle { const void *cur; gle *work; u64 len, len0; u32 is_ext, where; };
+struct TProd { u32 n_idx; u32 idx[5]; };
+struct ScTail { u32 n_mles, n_products, n_rounds, first_has_challenge; TMle m[SC_TAIL_MAXM]; TProd p[SC_TAIL_MAXP]; };
+
+template <int DSEL>
+__global__ void __launch_bounds__(SC_THREADS)
+k_sc_tail(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pairs /* mapped */, volatile u64 *flag /* mapped */,
+          volatile u64 *chal /* mapped: [seq, c0, c1] */, u64 seq0) {
+    __shared__ TMle sm[SC_TAIL_MAXM];
+    __shared__ TProd sp[SC_TAIL_MAXP];
+    __shared__ gle *sdst[SC_TAIL_MAXM];
+    __shared__ unsigned char sfold[SC_TAIL_MAXM], swritten[SC_TAIL_MAXM];
+    __shared__ ScProd pd;
+    __shared__ gle wsum[SC_THREADS / 32][SC_NACC];
+    __shared__ gle s_r;
+    __shared__ u32 s_status;
+    const u32 nm = cfg->n_mles, np = cfg->n_products, nr = cfg->n_rounds;
+    for (u32 i = threadIdx.x; i < nm; i += blockDim.x) sm[i] = cfg->m[i];
+    for (u32 i = threadIdx.x; i < np; i += blockDim.x) sp[i] = cfg->p[i];
+    if (threadIdx.x == 0) { s_r = r0; s_status = 0; }
+    __syncthreads();
+    for (u32 k = 0; k < nr; k++) {
+        const u64 seq = seq0 + k;
+        if (k > 0) {   // wait for the host's challenge for this round
+            if (threadIdx.x == 0) {
+                long long t0 = clock64(); u64 v;
+                while ((v = chal[0]) != seq) {
+                    if (v == SC_TAIL_ABORT) { s_status = 1; break; }
+                    if (clock64() - t0 > SC_TAIL_TIMEOUT) { s_status = 2; break; }
+                }
+                if (!s_status) { __threadfence_system(); s_r = e_make(chal[1], chal[2]); }
+            }
+            __syncthreads();
+            if (s_status) { if (threadIdx.x == 0 && s_status == 2) { __threadfence_system(); *flag = SC_TAIL_FAILED; } return; }
+        }
+        const bool fold = (k > 0) || cfg->first_has_challenge;
+        const gle r = s_r;
+        for (u32 i = threadIdx.x; i < nm; i += blockDim.x) {
+            bool f = fold && sm[i].len > 1;
+            sfold[i] = f; swritten[i] = 0;
+            sdst[i] = f ? ((sm[i].where == 1) ? sm[i].work + (sm[i].len0 >> 1) : sm[i].work) : nullptr;
+        }
+        __syncthreads();
+        for (u32 p = 0; p < np; p++) {
+            if (threadIdx.x == 0) {   // same descriptor the host builds for k_sc_round
+                const TProd &pr = sp[p];
+                u32 order[5], c = 0;
+                for (u32 j = 0; j < pr.n_idx; j++) { u32 mi = pr.idx[j]; if (sm[mi].is_ext || sfold[mi]) order[c++] = j; }
+                for (u32 j = 0; j < pr.n_idx; j++) { u32 mi = pr.idx[j]; if (!(sm[mi].is_ext || sfold[mi])) order[c++] = j; }
+                bool allbase = true; u64 newlen = 0;
+                for (u32 jj = 0; jj < pr.n_idx; jj++) {
+                    u32 mi = pr.idx[order[jj]]; const TMle &m = sm[mi]; ScOp &op = pd.op[jj];
+                    op.src = m.cur; op.dst = nullptr;
+                    if (sfold[mi]) { op.mode = m.is_ext ? OPM_EF : OPM_BF; if (!swritten[mi]) { op.dst = sdst[mi]; swritten[mi] = 1; } newlen = m.len >> 1; allbase = false; }
+                    else { op.mode = m.is_ext ? OPM_E : OPM_B; newlen = m.len; if (m.is_ext) allbase = false; }
+                }
+                pd.d = pr.n_idx; pd.allbase = allbase; pd.konst = newlen == 1; pd.npairs = newlen >> 1;
+            }
+            __syncthreads();
+            gle acc[SC_NACC];
+#pragma unroll
+            for (int t = 0; t < SC_NACC; t++) acc[t] = e_zero();
+            if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL>(pd, r, acc);
+            else switch (pd.d) {
+            case 1: sc_body<1>(pd, r, acc); break;
+            case 2: sc_body<2>(pd, r, acc); break;
+            case 3: sc_body<3>(pd, r, acc); break;
+            case 4: sc_body<4>(pd, r, acc); break;
+            default: sc_body<5>(pd, r, acc); break;
+            }
+            const int nacc = pd.d + 1;
+            for (int t = 0; t < nacc; t++) {
+                gle v = acc[t];
+                for (int d = 16; d > 0; d >>= 1) v = e_add(v, shfl_down_e(v, d));
+                if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x < nacc) {
+                gle v = wsum[0][threadIdx.x];
+                for (int w = 1; w < SC_THREADS / 32; w++) v = e_add(v, wsum[w][threadIdx.x]);
+                st_e(out + (u64)p * SC_NACC + threadIdx.x, v);
+            }
+            __syncthreads();   // folded tables of this product are complete before a later product reads them as plain operands
+        }
+        for (u32 i = threadIdx.x; i < nm; i += blockDim.x) if (sfold[i]) {
+            TMle &m = sm[i];
+            m.cur = sdst[i]; m.where = (sdst[i] == m.work) ? 1 : 2; m.len >>= 1; m.is_ext = 1;
+        }
+        __syncthreads();
+        if (k == nr - 1) {   // last round: hand the (<= 2)-entry tables over with the message (k_sc_gather's job)
+            for (u32 i = threadIdx.x; i < nm; i += blockDim.x) {
+                const TMle &m = sm[i]; gle a, b;
+                if (m.is_ext) { a = ld_e((const gle *)m.cur); b = m.len > 1 ? ld_e((const gle *)m.cur + 1) : a; }
+                else { a = e_from_base(*(const u64 *)m.cur); b = m.len > 1 ? e_from_base(*((const u64 *)m.cur + 1)) : a; }
+                st_e(pairs + 2 * i, a); st_e(pairs + 2 * i + 1, b);
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) { *flag = seq; }
+    }
+}
+
 struct ScFin { const void *src; u32 mode; u32 len; };
 __global__ void k_sc_final(const ScFin *__restrict__ f, u32 n, gle r, gle *__restrict__ out) {
     u32 m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,6 +385,8 @@ struct dp_sc {
     gle *h_pairs = nullptr; bool have_pairs = false;
     u64 seq = 0; u64 *h_flag = nullptr; u32 *d_done = nullptr;
     int gx = 1;
+    bool tail_enabled = false, tail_active = false; u32 tail_last_round = 0;
+    ScTail *h_tail = nullptr; u64 *h_chal = nullptr;
     std::vector<gle> challenges;
     u64 last_bytes = 0;
 };
@@ -294,7 +413,95 @@ static int sc_free_all(dp_sc *s) {
     dp_dev_free(s->d_descs); dp_dev_free(s->d_partials); dp_dev_free(s->d_out); dp_dev_free(s->d_counters); dp_dev_free(s->d_fin);
     dp_pinned_free(s->h_flag);
     dp_pinned_free(s->h_descs); dp_pinned_free(s->h_out); dp_pinned_free(s->h_fin); dp_pinned_free(s->h_pairs);
+    dp_pinned_free(s->h_tail); dp_pinned_free(s->h_chal);
     return DP_OK;
+}
+
+// host glue: multiplicity, coefficient, extrapolation, sum over products (prover.rs:694-733)
+static int sc_glue(dp_sc *s, uint64_t *out_evals) {
+    gle msg[SC_NACC + 1];
+    for (u32 t = 0; t <= s->max_deg; t++) msg[t] = e_zero();
+    for (u32 p = 0; p < s->n_products; p++) {
+        const dp_sc_product &pr = s->products[p];
+        u32 d = pr.n_idx;
+        gle sum[16];
+        u64 len = s->mles[pr.idx[0]].len;
+        u32 l2 = std::max<u32>(ceil_log2_u64(len), 1);
+        int mult = (int)s->max_nv - (int)(l2 + s->round - 1);  // sumcheck_macro/src/lib.rs:242
+        DP_CHECK(mult >= 0, DP_ERR_INVALID, "dp_sc_round: negative num_vars multiplicity");
+        gle coef = e_make(pr.coef[0], pr.coef[1]);
+        for (u32 t = 0; t <= d; t++) {
+            gle v = s->h_out[p * SC_NACC + t];
+            if (mult > 0) v = e_mul_base(v, gl_canon(1ULL << mult));
+            sum[t] = e_mul(v, coef);
+        }
+        for (u32 i = 0; i < s->max_deg - d; i++) sum[d + 1 + i] = sc_extrapolate(sum, d + 1, d + 1 + i);
+        for (u32 t = 0; t <= s->max_deg; t++) msg[t] = e_add(msg[t], sum[t]);
+    }
+    for (u32 t = 0; t <= s->max_deg; t++) { out_evals[2 * t] = msg[t].c0; out_evals[2 * t + 1] = msg[t].c1; }
+    return DP_OK;
+}
+
+
+// ---- resident tail, host side ----
+static bool sc_tail_eligible(const dp_sc *s, bool fold) {
+    if (!s->tail_enabled || s->n_mles > SC_TAIL_MAXM || s->n_products > SC_TAIL_MAXP || s->max_nv - s->round < 2) return false;
+    std::vector<char> used(s->n_mles, 0);
+    for (auto &pr : s->products) for (u32 j = 0; j < pr.n_idx; j++) used[pr.idx[j]] = 1;
+    for (u32 i = 0; i < s->n_mles; i++) {
+        const ScMle &m = s->mles[i];
+        if (!used[i] && m.len > 1) return false;
+        u64 nl = (fold && m.len > 1) ? m.len >> 1 : m.len;
+        if ((nl >> 1) > SC_TAIL_PAIRS) return false;
+    }
+    return true;
+}
+// one round served by the resident kernel (started here on its first round)
+static int sc_tail_round(dp_sc *s, gle r, bool fold, uint64_t *out_evals) {
+    cudaStream_t st = dp_ctx().stream;
+    s->seq++;
+    if (!s->tail_active) {
+        int e = 0;
+        if (!s->h_tail && (e = dp_pinned_alloc((void **)&s->h_tail, sizeof(ScTail)))) return e;
+        if (!s->h_chal && (e = dp_pinned_alloc((void **)&s->h_chal, 64))) return e;
+        ScTail &t = *s->h_tail;
+        t.n_mles = s->n_mles; t.n_products = s->n_products; t.n_rounds = s->max_nv - s->round; t.first_has_challenge = fold ? 1 : 0;
+        for (u32 i = 0; i < s->n_mles; i++) {
+            ScMle &m = s->mles[i];
+            if (m.len > 1 && !m.work) { if ((e = dp_dev_alloc((void **)&m.work, sizeof(gle) * ((m.len0 >> 1) + (m.len0 >> 2) + 1)))) return e; }
+            t.m[i].cur = m.cur; t.m[i].work = m.work; t.m[i].len = m.len; t.m[i].len0 = m.len0; t.m[i].is_ext = m.is_ext; t.m[i].where = (u32)m.where;
+        }
+        for (u32 p = 0; p < s->n_products; p++) { t.p[p].n_idx = s->products[p].n_idx; for (u32 j = 0; j < 5; j++) t.p[p].idx[j] = s->products[p].idx[j]; }
+        s->h_chal[0] = 0;
+        u32 dsel = s->products[0].n_idx;
+        for (auto &pr : s->products) if (pr.n_idx != dsel) dsel = 0;
+        DpProfScope prof("k_sc_tail(resident rounds; time includes the host's Fiat-Shamir between rounds)", 0);
+        switch (dsel) {
+        case 1: k_sc_tail<1><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
+        case 2: k_sc_tail<2><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
+        case 3: k_sc_tail<3><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
+        case 4: k_sc_tail<4><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
+        case 5: k_sc_tail<5><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
+        default: k_sc_tail<0><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
+        }
+        DP_LAUNCHED();
+        DP_CUDA(cudaGetLastError());
+        s->tail_active = true;
+    } else {   // post the challenge: value first, then the sequence number the kernel polls
+        s->h_chal[1] = r.c0; s->h_chal[2] = r.c1;
+        __atomic_store_n(&s->h_chal[0], s->seq, __ATOMIC_RELEASE);
+    }
+    if (fold) for (auto &m : s->mles) if (m.len > 1) { m.len >>= 1; m.is_ext = true; m.cur = nullptr; m.where = 3; }   // the tables now live in the kernel's bookkeeping
+    s->round += 1;
+    s->last_bytes = 0;
+    {
+        DP_HOST_TIMED("dp_sc_round(sync wait)");
+        volatile u64 *f = s->h_flag; u64 spins = 0; bool ok = false;
+        while (!(ok = (*f == s->seq))) { if (*f == SC_TAIL_FAILED) break; if (++spins > (1ULL << 30)) break; __builtin_ia32_pause(); }
+        if (!ok) { s->h_chal[0] = SC_TAIL_ABORT; cudaStreamSynchronize(st); DP_CHECK(false, DP_ERR_CUDA, "dp_sc_round: resident tail kernel timed out waiting for a challenge (other work queued in the same stream?)"); }
+    }
+    if (s->round == s->max_nv) s->have_pairs = true;   // written to mapped memory before the flag
+    return sc_glue(s, out_evals);
 }
 
 extern "C" {
@@ -368,6 +575,7 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
         if (s->challenges.size() == 1)
             for (auto &m : s->mles) DP_CHECK(m.len > 1, DP_ERR_INVALID, "calling sumcheck on constant");  // prover.rs:667-669
     }
+    if (s->tail_active || sc_tail_eligible(s, fold)) return sc_tail_round(s, r, fold, out_evals);
     // plan this round's folds: every MLE with >= 1 variable halves (prover.rs:659-684)
     std::vector<gle *> dst(s->n_mles, nullptr);
     std::vector<char> folds(s->n_mles, 0), written(s->n_mles, 0);
@@ -469,28 +677,7 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
             if (!ok) { DP_CUDA(cudaStreamSynchronize(st)); DP_CHECK(*f == s->seq, DP_ERR_CUDA, "dp_sc_round: kernel finished without signalling"); }
         }
     }
-    // host glue: multiplicity, coefficient, extrapolation, sum over products (prover.rs:694-733)
-    gle msg[SC_NACC + 1];
-    for (u32 t = 0; t <= s->max_deg; t++) msg[t] = e_zero();
-    for (u32 p = 0; p < s->n_products; p++) {
-        const dp_sc_product &pr = s->products[p];
-        u32 d = pr.n_idx;
-        gle sum[16];
-        u64 len = s->mles[pr.idx[0]].len;
-        u32 l2 = std::max<u32>(ceil_log2_u64(len), 1);
-        int mult = (int)s->max_nv - (int)(l2 + s->round - 1);  // sumcheck_macro/src/lib.rs:242
-        DP_CHECK(mult >= 0, DP_ERR_INVALID, "dp_sc_round: negative num_vars multiplicity");
-        gle coef = e_make(pr.coef[0], pr.coef[1]);
-        for (u32 t = 0; t <= d; t++) {
-            gle v = s->h_out[p * SC_NACC + t];
-            if (mult > 0) v = e_mul_base(v, gl_canon(1ULL << mult));
-            sum[t] = e_mul(v, coef);
-        }
-        for (u32 i = 0; i < s->max_deg - d; i++) sum[d + 1 + i] = sc_extrapolate(sum, d + 1, d + 1 + i);
-        for (u32 t = 0; t <= s->max_deg; t++) msg[t] = e_add(msg[t], sum[t]);
-    }
-    for (u32 t = 0; t <= s->max_deg; t++) { out_evals[2 * t] = msg[t].c0; out_evals[2 * t + 1] = msg[t].c1; }
-    return DP_OK;
+    return sc_glue(s, out_evals);
 }
 
 int dp_sc_finish(dp_sc *s, const uint64_t *last_challenge, uint64_t *out_final) {
@@ -532,17 +719,29 @@ int dp_sc_destroy(dp_sc *s) {
     if (!s) return DP_OK;
     DP_HOST_TIMED("dp_sc_destroy");
     std::lock_guard<std::recursive_mutex> lk(dp_ctx().mu);
-    if (dp_ctx().ready) sc_free_all(s);
+    if (dp_ctx().ready) {
+        if (s->tail_active && s->round < s->max_nv) { s->h_chal[0] = SC_TAIL_ABORT; cudaStreamSynchronize(dp_ctx().stream); }   // release the waiting kernel
+        sc_free_all(s);
+    }
     delete s;
     return DP_OK;
 }
 
 uint64_t dp_sc_last_round_bytes(const dp_sc *s) { return s ? s->last_bytes : 0; }
 
+int dp_sc_set_resident_tail(dp_sc *s, int enable) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(s && !s->tail_active, DP_ERR_STATE, "dp_sc_set_resident_tail: null handle or tail already running");
+    static const bool off = getenv("DP_SC_NO_TAIL") != nullptr;
+    s->tail_enabled = enable != 0 && !off;
+    return DP_OK;
+}
+
 int dp_sc_current_mle(dp_sc *s, uint32_t idx, dp_mle **out) {
     DP_REQUIRE_CTX();
     DP_CHECK(s && out && idx < s->n_mles, DP_ERR_INVALID, "dp_sc_current_mle: bad argument");
     const ScMle &m = s->mles[idx];
+    DP_CHECK(!s->tail_active, DP_ERR_STATE, "dp_sc_current_mle: tables are owned by the resident tail kernel");
     dp_mle *v = new dp_mle();
     v->data = const_cast<void *>(m.cur); v->len = m.len; v->is_ext = m.is_ext; v->owned = false;
     *out = v;

@@ -145,6 +145,7 @@ class Basefold {
         dp_sc *sc = nullptr;
         check(dp_sc_create(hs.data(), (uint32_t)hs.size(), vp.products.data(), (uint32_t)vp.products.size(), num_vars, 2, &sc));
         std::shared_ptr<dp_sc> guard(sc, [](dp_sc *p) { dp_sc_destroy(p); });
+        check(dp_sc_set_resident_tail(sc, 1));
         Ext sum = target, ch; bool have = false; ExtVec challenges;
         const u64 inv2 = 0x7FFFFFFF80000001ULL;
         for (uint32_t round = 0; round < num_vars; round++) {

@@ -153,6 +153,7 @@ class IOPProverState {
         std::vector<dp_mle *> hs;
         for (auto &m : poly.flattened_ml_extensions) hs.push_back(m.handle());
         check(dp_sc_create(hs.data(), (uint32_t)hs.size(), poly.products.data(), (uint32_t)poly.products.size(), (uint32_t)nv, (uint32_t)deg, &st.sc_));
+        check(dp_sc_set_resident_tail(st.sc_, 1));   // this loop only runs the transcript between rounds: small rounds stay resident on the device
         std::vector<u64> buf(2 * (deg + 1));
         Ext challenge; bool have = false;
         for (size_t i = 0; i < nv; i++) {

@@ -94,6 +94,13 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
  * previous round's challenge [c0,c1] afterwards.  out_evals receives (max_degree+1) x [c0,c1]:
  * the round polynomial at 0..max_degree, products already scaled, extrapolated and summed. */
 int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals);
+/* Opt in to the resident tail: once every table has <= 2048 pairs, ALL remaining rounds are served by one single-block
+ * kernel that stays on the device, posts each round message to mapped host memory and polls a mapped mailbox for the next
+ * challenge (no launch and no cross-block reduction per round).  Contract: between consecutive dp_sc_round calls on this
+ * handle the calling thread must not WAIT on other work submitted to the same stream (it would queue behind the
+ * resident kernel).  The kernel gives up by itself after ~3 s without a challenge and dp_sc_round reports the error;
+ * dp_sc_destroy releases it.  Results are identical with and without it.  Env DP_SC_NO_TAIL=1 disables it globally. */
+int dp_sc_set_resident_tail(dp_sc *s, int enable);
 /* Tail of prove_parallel (prover.rs:544-568) + get_mle_final_evaluations (:474-490): fixes the last
  * challenge and writes n_mles x [c0,c1]. */
 int dp_sc_finish(dp_sc *s, const uint64_t *last_challenge, uint64_t *out_final_evals);
