@@ -71,8 +71,7 @@ template <int N> __device__ __forceinline__ void acc_add_dyn_e(gle (&a)[N], int 
 }
 
 template <int D>
-__device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC]) {
-    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+__device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC], const u64 tid, const u64 stride) {
     if (pd.konst) {
         if (tid == 0) {
             gle p = sc_load_const(pd.op[0], r);
@@ -162,13 +161,14 @@ k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, 
     gle acc[SC_NACC];
 #pragma unroll
     for (int t = 0; t < SC_NACC; t++) acc[t] = e_zero();
-    if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL>(pd, r, acc);
+    const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (u64)gridDim.x * blockDim.x;
+    if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL>(pd, r, acc, gtid, gstride);
     else switch (pd.d) {
-    case 1: sc_body<1>(pd, r, acc); break;
-    case 2: sc_body<2>(pd, r, acc); break;
-    case 3: sc_body<3>(pd, r, acc); break;
-    case 4: sc_body<4>(pd, r, acc); break;
-    default: sc_body<5>(pd, r, acc); break;
+    case 1: sc_body<1>(pd, r, acc, gtid, gstride); break;
+    case 2: sc_body<2>(pd, r, acc, gtid, gstride); break;
+    case 3: sc_body<3>(pd, r, acc, gtid, gstride); break;
+    case 4: sc_body<4>(pd, r, acc, gtid, gstride); break;
+    default: sc_body<5>(pd, r, acc, gtid, gstride); break;
     }
     const int nacc = pd.d + 1;
     // warp shuffle reduction, then across warps through shared memory
@@ -228,7 +228,7 @@ k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, 
 
 
 // ---- resident tail: every remaining round of a small sumcheck in ONE single-block launch -------------------
-// Once the tables are small (<= SC_TAIL_PAIRS pairs) a round is pure latency: launch + two-stage reduction + the
+// Once the tables are small (<= SC_TAIL_PAIRS pairs, i.e. the last 8 rounds) a round is pure latency: launch + two-stage reduction + the
 // host's Fiat-Shamir.  The tail kernel stays resident instead: it writes each round message to mapped host memory,
 // raises the flag, and polls a mapped mailbox for the next challenge (one thread, one PCIe read in flight), so a
 // round costs the block-local work + two PCIe hops + the host sponge -- no launch, no cross-block stage.
@@ -237,7 +237,7 @@ k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, 
 // when the host posts the abort value.  Opt-in per handle (dp_sc_set_resident_tail): the caller promises not to
 // wait on other work in the same stream between rounds.
 static constexpr u32 SC_TAIL_MAXM = 96, SC_TAIL_MAXP = 48;
-static constexpr u64 SC_TAIL_PAIRS = 2048;
+static constexpr u64 SC_TAIL_PAIRS = 128;
 static constexpr long long SC_TAIL_TIMEOUT = 6000000000LL;   // ~3 s at 1.9 GHz
 static constexpr u64 SC_TAIL_ABORT = ~0ULL, SC_TAIL_FAILED = ~0ULL - 1;
 struct TMle { const void *cur; gle *work; u64 len, len0; u32 is_ext, where; };
@@ -250,16 +250,19 @@ k_sc_tail(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pa
           volatile u64 *chal /* mapped: [seq, c0, c1] */, u64 seq0) {
     __shared__ TMle sm[SC_TAIL_MAXM];
     __shared__ TProd sp[SC_TAIL_MAXP];
+    __shared__ ScProd spd[SC_TAIL_MAXP];
     __shared__ gle *sdst[SC_TAIL_MAXM];
-    __shared__ unsigned char sfold[SC_TAIL_MAXM], swritten[SC_TAIL_MAXM];
-    __shared__ ScProd pd;
-    __shared__ gle wsum[SC_THREADS / 32][SC_NACC];
+    __shared__ unsigned char sfold[SC_TAIL_MAXM], swriter[SC_TAIL_MAXM];
     __shared__ gle s_r;
     __shared__ u32 s_status;
     const u32 nm = cfg->n_mles, np = cfg->n_products, nr = cfg->n_rounds;
-    for (u32 i = threadIdx.x; i < nm; i += blockDim.x) sm[i] = cfg->m[i];
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (u32 i = threadIdx.x; i < nm; i += blockDim.x) { sm[i] = cfg->m[i]; swriter[i] = 0xff; }
     for (u32 i = threadIdx.x; i < np; i += blockDim.x) sp[i] = cfg->p[i];
     if (threadIdx.x == 0) { s_r = r0; s_status = 0; }
+    __syncthreads();
+    // the product that writes an MLE's folded table is the first one referencing it (the host's `written` rule); static
+    if (threadIdx.x == 0) for (u32 p = 0; p < np; p++) for (u32 j = 0; j < sp[p].n_idx; j++) { u32 mi = sp[p].idx[j]; if (swriter[mi] == 0xff) swriter[mi] = (unsigned char)p; }
     __syncthreads();
     for (u32 k = 0; k < nr; k++) {
         const u64 seq = seq0 + k;
@@ -279,51 +282,50 @@ k_sc_tail(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pa
         const gle r = s_r;
         for (u32 i = threadIdx.x; i < nm; i += blockDim.x) {
             bool f = fold && sm[i].len > 1;
-            sfold[i] = f; swritten[i] = 0;
+            sfold[i] = f;
             sdst[i] = f ? ((sm[i].where == 1) ? sm[i].work + (sm[i].len0 >> 1) : sm[i].work) : nullptr;
         }
         __syncthreads();
-        for (u32 p = 0; p < np; p++) {
-            if (threadIdx.x == 0) {   // same descriptor the host builds for k_sc_round
-                const TProd &pr = sp[p];
-                u32 order[5], c = 0;
-                for (u32 j = 0; j < pr.n_idx; j++) { u32 mi = pr.idx[j]; if (sm[mi].is_ext || sfold[mi]) order[c++] = j; }
-                for (u32 j = 0; j < pr.n_idx; j++) { u32 mi = pr.idx[j]; if (!(sm[mi].is_ext || sfold[mi])) order[c++] = j; }
-                bool allbase = true; u64 newlen = 0;
-                for (u32 jj = 0; jj < pr.n_idx; jj++) {
-                    u32 mi = pr.idx[order[jj]]; const TMle &m = sm[mi]; ScOp &op = pd.op[jj];
-                    op.src = m.cur; op.dst = nullptr;
-                    if (sfold[mi]) { op.mode = m.is_ext ? OPM_EF : OPM_BF; if (!swritten[mi]) { op.dst = sdst[mi]; swritten[mi] = 1; } newlen = m.len >> 1; allbase = false; }
-                    else { op.mode = m.is_ext ? OPM_E : OPM_B; newlen = m.len; if (m.is_ext) allbase = false; }
-                }
-                pd.d = pr.n_idx; pd.allbase = allbase; pd.konst = newlen == 1; pd.npairs = newlen >> 1;
+        for (u32 p = threadIdx.x; p < np; p += blockDim.x) {   // the descriptor the host builds for k_sc_round, one thread per product
+            const TProd &pr = sp[p]; ScProd &pd = spd[p];
+            u32 order[5], c = 0;
+            for (u32 j = 0; j < pr.n_idx; j++) { u32 mi = pr.idx[j]; if (sm[mi].is_ext || sfold[mi]) order[c++] = j; }
+            for (u32 j = 0; j < pr.n_idx; j++) { u32 mi = pr.idx[j]; if (!(sm[mi].is_ext || sfold[mi])) order[c++] = j; }
+            bool allbase = true, wrote[5] = {false, false, false, false, false}; u64 newlen = 0;
+            for (u32 jj = 0; jj < pr.n_idx; jj++) {
+                u32 mi = pr.idx[order[jj]]; const TMle &m = sm[mi]; ScOp &op = pd.op[jj];
+                op.src = m.cur; op.dst = nullptr;
+                if (sfold[mi]) {
+                    op.mode = m.is_ext ? OPM_EF : OPM_BF;
+                    bool dup = false; for (u32 q = 0; q < jj; q++) if (wrote[q] && pr.idx[order[q]] == mi) dup = true;
+                    if (swriter[mi] == p && !dup) { op.dst = sdst[mi]; wrote[jj] = true; }
+                    newlen = m.len >> 1; allbase = false;
+                } else { op.mode = m.is_ext ? OPM_E : OPM_B; newlen = m.len; if (m.is_ext) allbase = false; }
             }
-            __syncthreads();
+            pd.d = pr.n_idx; pd.allbase = allbase; pd.konst = newlen == 1; pd.npairs = newlen >> 1;
+        }
+        __syncthreads();
+        for (u32 p = warp; p < np; p += nwarps) {   // one warp per product: tables have <= SC_TAIL_PAIRS pairs here
+            const ScProd &pd = spd[p];
             gle acc[SC_NACC];
 #pragma unroll
             for (int t = 0; t < SC_NACC; t++) acc[t] = e_zero();
-            if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL>(pd, r, acc);
+            if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL>(pd, r, acc, lane, 32);
             else switch (pd.d) {
-            case 1: sc_body<1>(pd, r, acc); break;
-            case 2: sc_body<2>(pd, r, acc); break;
-            case 3: sc_body<3>(pd, r, acc); break;
-            case 4: sc_body<4>(pd, r, acc); break;
-            default: sc_body<5>(pd, r, acc); break;
+            case 1: sc_body<1>(pd, r, acc, lane, 32); break;
+            case 2: sc_body<2>(pd, r, acc, lane, 32); break;
+            case 3: sc_body<3>(pd, r, acc, lane, 32); break;
+            case 4: sc_body<4>(pd, r, acc, lane, 32); break;
+            default: sc_body<5>(pd, r, acc, lane, 32); break;
             }
             const int nacc = pd.d + 1;
             for (int t = 0; t < nacc; t++) {
                 gle v = acc[t];
                 for (int d = 16; d > 0; d >>= 1) v = e_add(v, shfl_down_e(v, d));
-                if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = v;
+                if (lane == 0) st_e(out + (u64)p * SC_NACC + t, v);
             }
-            __syncthreads();
-            if (threadIdx.x < nacc) {
-                gle v = wsum[0][threadIdx.x];
-                for (int w = 1; w < SC_THREADS / 32; w++) v = e_add(v, wsum[w][threadIdx.x]);
-                st_e(out + (u64)p * SC_NACC + threadIdx.x, v);
-            }
-            __syncthreads();   // folded tables of this product are complete before a later product reads them as plain operands
         }
+        __syncthreads();
         for (u32 i = threadIdx.x; i < nm; i += blockDim.x) if (sfold[i]) {
             TMle &m = sm[i];
             m.cur = sdst[i]; m.where = (sdst[i] == m.work) ? 1 : 2; m.len >>= 1; m.is_ext = 1;

@@ -94,7 +94,7 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
  * previous round's challenge [c0,c1] afterwards.  out_evals receives (max_degree+1) x [c0,c1]:
  * the round polynomial at 0..max_degree, products already scaled, extrapolated and summed. */
 int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals);
-/* Opt in to the resident tail: once every table has <= 2048 pairs, ALL remaining rounds are served by one single-block
+/* Opt in to the resident tail: once every table has <= 128 pairs (the last 8 rounds), ALL remaining rounds are served by one single-block
  * kernel that stays on the device, posts each round message to mapped host memory and polls a mapped mailbox for the next
  * challenge (no launch and no cross-block reduction per round).  Contract: between consecutive dp_sc_round calls on this
  * handle the calling thread must not WAIT on other work submitted to the same stream (it would queue behind the
