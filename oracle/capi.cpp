@@ -392,3 +392,33 @@ extern "C" int dpo_model_prove(const int64_t *desc, u32 n_nodes, const int64_t *
         return 0;
     } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
+
+// ---- Basefold verifier (verify.hpp) on a flat proof image (from this library or from the device) ----
+#include "verify.hpp"
+extern "C" {
+// Basefold::verify: 0 = accepted; 1 = rejected (dpo_last_error says why)
+int dpo_pcs_verify(const u64 *flat, u64 n, const u64 *root, u32 num_vars, int is_base, u32 full_log, const u64 *point, const u64 *eval, const char *label) {
+    try {
+        BasefoldProof pr = unflatten_proof(flat, n);
+        PureCommitment c; for (int i = 0; i < 4; i++) c.root.v[i] = root[i]; c.num_vars = num_vars; c.is_base = is_base != 0;
+        Transcript t(label);
+        basefold_verify(full_log, c, mk_point(point, num_vars), E(eval[0], eval[1]), pr, t);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+// Basefold::batch_verify with Evaluation::new(i, i, evals[i]); points concatenated (poly i has num_vars[i] elements)
+int dpo_pcs_batch_verify(const u64 *flat, u64 n, u32 n_polys, const u64 *roots, const u32 *num_vars, const int *is_base, u32 full_log, const u64 *points, const u64 *evals, const char *label) {
+    try {
+        BasefoldProof pr = unflatten_proof(flat, n);
+        std::vector<PureCommitment> comms; std::vector<std::vector<E>> pts; std::vector<Evaluation> ev; size_t o = 0;
+        for (u32 i = 0; i < n_polys; i++) {
+            PureCommitment c; for (int k = 0; k < 4; k++) c.root.v[k] = roots[4 * i + k]; c.num_vars = num_vars[i]; c.is_base = is_base[i] != 0; comms.push_back(c);
+            pts.push_back(mk_point(points + 2 * o, num_vars[i])); o += num_vars[i];
+            ev.push_back({i, i, E(evals[2 * i], evals[2 * i + 1])});
+        }
+        Transcript t(label);
+        basefold_batch_verify(full_log, comms, pts, ev, pr, t);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+}

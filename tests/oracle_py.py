@@ -430,3 +430,17 @@ def model_prove(desc, data, x, label=b"m2vec", cap=1 << 23, want_proof=True):
     if rc:
         raise RuntimeError(lib().dpo_last_error().decode())
     return (out[:n.value].copy() if want_proof else None), (ms[0], ms[1])
+
+
+def pcs_verify(flat, root, num_vars, is_base, full_log, point, eval_, label=b"m2vec"):
+    """Basefold::verify on a flat proof image; returns None when accepted, else the rejection reason"""
+    f = u64(flat); r = u64(root); pt = u64(point).reshape(-1); ev = u64(eval_).reshape(-1)
+    rc = lib().dpo_pcs_verify(ptr(f), C.c_uint64(f.size), ptr(r), C.c_uint32(num_vars), C.c_int(int(is_base)), C.c_uint32(full_log), ptr(pt), ptr(ev), label)
+    return None if rc == 0 else lib().dpo_last_error().decode()
+
+
+def pcs_batch_verify(flat, roots, num_vars, is_base, full_log, points, evals, label=b"m2vec"):
+    f = u64(flat); r = u64(roots).reshape(-1); nv = np.ascontiguousarray(num_vars, dtype=np.uint32); ib = np.ascontiguousarray(is_base, dtype=np.int32)
+    pt = u64(np.concatenate([u64(p).reshape(-1) for p in points])); ev = u64(evals).reshape(-1)
+    rc = lib().dpo_pcs_batch_verify(ptr(f), C.c_uint64(f.size), C.c_uint32(len(nv)), ptr(r), ptr(nv), ptr(ib), C.c_uint32(full_log), ptr(pt), ptr(ev), label)
+    return None if rc == 0 else lib().dpo_last_error().decode()

@@ -46,6 +46,7 @@ def test_open(gpu, nv, full_log, ext):
             assert a[k] == b[k], k
         assert a["single"] == b["single"], "queries"
     assert (got == exp).all()
+    assert O.pcs_verify(got, root, nv, not ext, full_log, pt, O.evaluate(ev, ext, pt)) is None   # Basefold::verify accepts (basefold.rs:863-962)
 
 
 @pytest.mark.parametrize("shape,full_log", [([(10, False)], 10), ([(10, False), (8, False), (9, True)], 10), ([(9, False), (12, False), (12, True), (8, False)], 13),
@@ -63,6 +64,10 @@ def test_batch_open(gpu, shape, full_log):
             assert a[k] == b[k], k
         assert a["batched"] == b["batched"], "queries"
     assert (got == exp).all()
+    # the device's proof is accepted by the restated Basefold::batch_verify (basefold.rs:964-1098)
+    roots = np.array([O.pcs_commit(p, e, full_log, want_codeword=False)[0] for p, e in polys])
+    evals = np.array([O.evaluate(p, e, pt) for (p, e), pt in zip(polys, pts)])
+    assert O.pcs_batch_verify(got, roots, [nv for nv, _ in shape], [not e for _, e in shape], full_log, pts, evals) is None
 
 
 def test_open_full_size_properties(gpu):
@@ -78,6 +83,7 @@ def test_open_full_size_properties(gpu):
     root, flat = gpu.pcs_open(m, full_log, pt)
     pr = parse_flat(flat)
     assert len(pr["sumcheck_messages"]) == nv - 7 and len(pr["roots"]) == nv - 8 and len(pr["single"]) == 200
+    assert O.pcs_verify(flat, root, nv, True, full_log, pt, O.evaluate(ev, False, pt)) is None   # the verifier needs no 2^20-sized work
     m0 = pr["sumcheck_messages"][0]
     s = O.pe_add(O.pe_add(O.pe_add((m0[0], m0[1]), (m0[0], m0[1])), (m0[2], m0[3])), (m0[4], m0[5]))
     assert s == tuple(int(x) for x in m.evaluate(pt))

@@ -1,0 +1,39 @@
+"""commit -> open -> verify accepts (the reference's own test, mpcs/src/basefold.rs:1239-1331), with the verifier restated
+from basefold.rs:863-1098 and query_phase.rs:141-283,915-975,1116-1236; tampered proofs / wrong claims are rejected."""
+import numpy as np
+import pytest
+
+import oracle_py as O
+
+
+@pytest.mark.parametrize("nv,full_log,ext", [(8, 8, False), (9, 11, False), (10, 10, True), (12, 13, False), (5, 8, False)])
+def test_open_verifies(nv, full_log, ext):
+    ev = O.splitmix_e(500 + nv, 1 << nv) if ext else O.splitmix_f(500 + nv, 1 << nv)
+    pt = O.splitmix_e(600 + nv, nv)
+    root, _, _ = O.pcs_commit(ev, ext, full_log)
+    value = O.evaluate(ev, ext, pt)
+    if nv > 7:
+        flat = O.pcs_open(ev, ext, full_log, pt)
+        assert O.pcs_verify(flat, root, nv, not ext, full_log, pt, value) is None
+        bad = value.copy(); bad[0] ^= np.uint64(1)
+        assert "p0(0) + p0(1)" in O.pcs_verify(flat, root, nv, not ext, full_log, pt, bad)
+        tam = flat.copy(); tam[flat.size // 2] ^= np.uint64(1)          # somewhere in the query openings
+        assert O.pcs_verify(tam, root, nv, not ext, full_log, pt, value) is not None
+        other_root = root.copy(); other_root[0] ^= np.uint64(1)
+        assert "merkle" in O.pcs_verify(flat, other_root, nv, not ext, full_log, pt, value)
+        assert O.pcs_verify(flat, root, nv, not ext, full_log, pt, value, label=b"other") is not None   # different transcript
+
+
+@pytest.mark.parametrize("shape,full_log", [([(10, False)], 10), ([(10, False), (8, False), (9, True)], 10), ([(9, False), (12, False), (12, True), (8, False)], 13)])
+def test_batch_open_verifies(shape, full_log):
+    polys = [(O.splitmix_e(700 + i, 1 << nv) if ext else O.splitmix_f(700 + i, 1 << nv), ext) for i, (nv, ext) in enumerate(shape)]
+    points = [O.splitmix_e(800 + i, nv) for i, (nv, _) in enumerate(shape)]
+    flat = O.pcs_batch_open(polys, full_log, points)
+    roots = [O.pcs_commit(p, e, full_log, want_codeword=False)[0] for p, e in polys]
+    evals = np.array([O.evaluate(p, e, pt) for (p, e), pt in zip(polys, points)])
+    nvs = [nv for nv, _ in shape]; isb = [not e for _, e in shape]
+    assert O.pcs_batch_verify(flat, np.array(roots), nvs, isb, full_log, points, evals) is None
+    bad = evals.copy(); bad[-1, 1] ^= np.uint64(1)
+    assert "classic sumcheck" in O.pcs_batch_verify(flat, np.array(roots), nvs, isb, full_log, points, bad)
+    tam = flat.copy(); tam[-3] ^= np.uint64(1)
+    assert O.pcs_batch_verify(tam, np.array(roots), nvs, isb, full_log, points, evals) is not None
