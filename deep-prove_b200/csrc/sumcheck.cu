@@ -541,7 +541,7 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
     }
     s->products.assign(products, products + n_products);
     for (auto &pr : s->products) { pr.coef[0] = gl_canon(pr.coef[0]); pr.coef[1] = gl_canon(pr.coef[1]); }
-    s->gx = dp_grid_for(max_pairs, SC_THREADS, 4);
+    s->gx = dp_grid_for(max_pairs, SC_THREADS, 6);   // upper bound of any round's grid (partials buffer)
     int e = 0;
     if ((e = dp_dev_alloc((void **)&s->d_descs, sizeof(ScProd) * n_products))) return e;
     if ((e = dp_dev_alloc((void **)&s->d_partials, sizeof(gle) * SC_NACC * (size_t)s->gx * n_products))) return e;
@@ -627,7 +627,10 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
         round_pairs = std::max<u64>(round_pairs, d.npairs);
     }
     // grid sized for THIS round: 2 pairs per thread minimum so small rounds run in a single block
-    int gx = std::min(s->gx, dp_grid_for(round_pairs <= 256 ? round_pairs : (round_pairs + 1) / 2, SC_THREADS, 4));
+    // large rounds are latency-bound on HBM (ncu r01b: 21 % warps active at 2 pairs/thread and <= 4 CTAs/SM): one pair per
+    // thread and up to 6 CTAs per SM put more loads in flight; small rounds keep 2 pairs per thread so they fit one block
+    int gx = round_pairs > 8192 ? dp_grid_for(round_pairs, SC_THREADS, 6)
+                                : std::min(s->gx, dp_grid_for(round_pairs <= 256 ? round_pairs : (round_pairs + 1) / 2, SC_THREADS, 4));
     cudaStream_t st = dp_ctx().stream;
     // descriptors are read by the kernel straight from mapped pinned memory (no H2D copy node)
     // MLEs no product references still have to be folded (cannot happen through add_mle_list, kept for safety)
