@@ -147,13 +147,16 @@ __device__ __forceinline__ void sc_signal(u64 seq, u64 *flag, u32 *done) {
 
 template <int DSEL>   // DSEL = 0: any degree (mixed-degree polynomials); 1..5: every product has this degree
 __global__ void __launch_bounds__(SC_THREADS)
-k_sc_round(const ScProd *__restrict__ descs, gle r, gle *__restrict__ partials, u32 *__restrict__ counters, gle *__restrict__ out,
-           u64 seq, u64 *flag, u32 *done) {
+k_sc_round(const ScProd *__restrict__ descs, const __grid_constant__ ScProd desc0, gle r, gle *__restrict__ partials, u32 *__restrict__ counters,
+           gle *__restrict__ out, u64 seq, u64 *flag, u32 *done) {
     __shared__ ScProd pd;
     __shared__ gle wsum[SC_THREADS / 32][SC_NACC];
     __shared__ bool is_last;
     {
-        const u64 *s = (const u64 *)(descs + blockIdx.y);
+        // single-product polynomials carry their descriptor in the kernel parameters; otherwise `descs` is mapped host
+        // memory for small grids (no copy node) and a device copy for large ones (hundreds of CTAs each fetching 216 B
+        // over PCIe was the dominant cost of large rounds: ncu r01b showed 44 % of stall cycles at this barrier)
+        const u64 *s = descs ? (const u64 *)(descs + blockIdx.y) : (const u64 *)&desc0;
         u64 *d = (u64 *)&pd;
         for (int k = threadIdx.x; k < (int)(sizeof(ScProd) / 8); k += blockDim.x) d[k] = s[k];
     }
@@ -642,15 +645,18 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
     {
         DpProfScope prof(fold ? "k_sc_round(fold+msg)" : "k_sc_round(msg)", bytes);
         s->seq++;
+        const ScProd *descs_arg = s->h_descs;                 // mapped pinned memory: no copy node on the latency path
+        if (s->n_products == 1) descs_arg = nullptr;          // descriptor travels in the kernel parameters
+        else if ((u64)gx * s->n_products > 32) { DP_CUDA(cudaMemcpyAsync(s->d_descs, s->h_descs, sizeof(ScProd) * s->n_products, cudaMemcpyHostToDevice, st)); descs_arg = s->d_descs; }
         u32 dsel = s->products[0].n_idx;
         for (auto &pr : s->products) if (pr.n_idx != dsel) dsel = 0;
         switch (dsel) {   // one small kernel per uniform degree keeps the instruction footprint low
-        case 1: k_sc_round<1><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
-        case 2: k_sc_round<2><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
-        case 3: k_sc_round<3><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
-        case 4: k_sc_round<4><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
-        case 5: k_sc_round<5><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
-        default: k_sc_round<0><<<grid, SC_THREADS, 0, st>>>(s->h_descs, r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        case 1: k_sc_round<1><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        case 2: k_sc_round<2><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        case 3: k_sc_round<3><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        case 4: k_sc_round<4><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        case 5: k_sc_round<5><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        default: k_sc_round<0><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
         }
         DP_LAUNCHED();
     }
