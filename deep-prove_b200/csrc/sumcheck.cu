@@ -70,7 +70,7 @@ template <int N> __device__ __forceinline__ void acc_add_dyn_e(gle (&a)[N], int 
     for (int k = 0; k < N; k++) if (k == t) a[k] = e_add(a[k], p);
 }
 
-template <int D>
+template <int D, bool BIG = false>
 __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC], const u64 tid, const u64 stride) {
     if (pd.konst) {
         if (tid == 0) {
@@ -87,6 +87,31 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
         u64 a[D + 1];
 #pragma unroll
         for (int t = 0; t <= D; t++) a[t] = 0;
+        if (BIG) {
+            // large rounds: two pairs in flight per thread (2 D independent 16-byte loads, two independent multiply
+            // chains) and the evaluation points fully unrolled -- the small-round body below trades that for footprint
+            for (u64 i = tid; i < pd.npairs; i += 2 * stride) {
+                const u64 i2 = i + stride; const bool two = i2 < pd.npairs;
+                u64 c0[D], s0[D], c1[D], s1[D];
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    ulonglong2 v = ld_b2((const u64 *)pd.op[j].src + 2 * i);
+                    ulonglong2 w = two ? ld_b2((const u64 *)pd.op[j].src + 2 * i2) : make_ulonglong2(0, 0);
+                    c0[j] = v.x; s0[j] = gl_sub(v.y, v.x); c1[j] = w.x; s1[j] = gl_sub(w.y, w.x);
+                }
+#pragma unroll
+                for (int t = 0; t <= D; t++) {
+                    u64 p = c0[0], q = c1[0];
+#pragma unroll
+                    for (int j = 1; j < D; j++) { p = gl_mul(p, c0[j]); q = gl_mul(q, c1[j]); }
+                    a[t] = gl_add(a[t], gl_add(p, q));
+                    if (t < D) {
+#pragma unroll
+                        for (int j = 0; j < D; j++) { c0[j] = gl_add(c0[j], s0[j]); c1[j] = gl_add(c1[j], s1[j]); }
+                    }
+                }
+            }
+        } else
         for (u64 i = tid; i < pd.npairs; i += stride) {
             u64 cur[D], st[D];
 #pragma unroll
@@ -113,6 +138,33 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
     gle a[D + 1];
 #pragma unroll
     for (int t = 0; t <= D; t++) a[t] = e_zero();
+    if (BIG) {
+        for (u64 i = tid; i < pd.npairs; i += 2 * stride) {
+            const u64 i2 = i + stride; const bool two = i2 < pd.npairs;
+            gle c0[D], s0[D], c1[D], s1[D];
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                gle lo, hi, lo2 = e_zero(), hi2 = e_zero();
+                sc_load_pair(pd.op[j], i, r, lo, hi);
+                if (two) sc_load_pair(pd.op[j], i2, r, lo2, hi2);
+                c0[j] = lo; s0[j] = e_sub(hi, lo); c1[j] = lo2; s1[j] = e_sub(hi2, lo2);
+            }
+#pragma unroll
+            for (int t = 0; t <= D; t++) {
+                gle p = c0[0], q = c1[0];
+#pragma unroll
+                for (int j = 1; j < D; j++) {
+                    if (pd.op[j].mode == OPM_B) { p = e_mul_base(p, c0[j].c0); q = e_mul_base(q, c1[j].c0); }
+                    else { p = e_mul(p, c0[j]); q = e_mul(q, c1[j]); }
+                }
+                a[t] = e_add(a[t], e_add(p, q));
+                if (t < D) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) { c0[j] = e_add(c0[j], s0[j]); c1[j] = e_add(c1[j], s1[j]); }
+                }
+            }
+        }
+    } else
     for (u64 i = tid; i < pd.npairs; i += stride) {
         gle cur[D], st[D];
 #pragma unroll
@@ -145,7 +197,7 @@ __device__ __forceinline__ void sc_signal(u64 seq, u64 *flag, u32 *done) {
     if (t == gridDim.y - 1) { *done = 0; __threadfence_system(); *(volatile u64 *)flag = seq; }
 }
 
-template <int DSEL>   // DSEL = 0: any degree (mixed-degree polynomials); 1..5: every product has this degree
+template <int DSEL, bool BIG = false>   // DSEL = 0: any degree (mixed-degree polynomials); 1..5: every product has this degree; BIG: large-round body
 __global__ void __launch_bounds__(SC_THREADS)
 k_sc_round(const ScProd *__restrict__ descs, const __grid_constant__ ScProd desc0, gle r, gle *__restrict__ partials, u32 *__restrict__ counters,
            gle *__restrict__ out, u64 seq, u64 *flag, u32 *done) {
@@ -165,7 +217,7 @@ k_sc_round(const ScProd *__restrict__ descs, const __grid_constant__ ScProd desc
 #pragma unroll
     for (int t = 0; t < SC_NACC; t++) acc[t] = e_zero();
     const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (u64)gridDim.x * blockDim.x;
-    if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL>(pd, r, acc, gtid, gstride);
+    if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL, BIG>(pd, r, acc, gtid, gstride);
     else switch (pd.d) {
     case 1: sc_body<1>(pd, r, acc, gtid, gstride); break;
     case 2: sc_body<2>(pd, r, acc, gtid, gstride); break;
@@ -630,9 +682,9 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
         round_pairs = std::max<u64>(round_pairs, d.npairs);
     }
     // grid sized for THIS round: 2 pairs per thread minimum so small rounds run in a single block
-    // large rounds are latency-bound on HBM (ncu r01b: 21 % warps active at 2 pairs/thread and <= 4 CTAs/SM): one pair per
-    // thread and up to 6 CTAs per SM put more loads in flight; small rounds keep 2 pairs per thread so they fit one block
-    int gx = round_pairs > 8192 ? dp_grid_for(round_pairs, SC_THREADS, 6)
+    // large rounds: ~4 pairs per thread (two in flight at a time, see sc_body<D, BIG>) amortise the per-thread reduction;
+    // small rounds keep 2 pairs per thread so they fit one block
+    int gx = round_pairs > 8192 ? dp_grid_for((round_pairs + 3) / 4, SC_THREADS, 6)
                                 : std::min(s->gx, dp_grid_for(round_pairs <= 256 ? round_pairs : (round_pairs + 1) / 2, SC_THREADS, 4));
     cudaStream_t st = dp_ctx().stream;
     // descriptors are read by the kernel straight from mapped pinned memory (no H2D copy node)
@@ -650,6 +702,10 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
         else if ((u64)gx * s->n_products > 32) { DP_CUDA(cudaMemcpyAsync(s->d_descs, s->h_descs, sizeof(ScProd) * s->n_products, cudaMemcpyHostToDevice, st)); descs_arg = s->d_descs; }
         u32 dsel = s->products[0].n_idx;
         for (auto &pr : s->products) if (pr.n_idx != dsel) dsel = 0;
+        const bool big = round_pairs > 8192 && (dsel == 2 || dsel == 3);
+        if (big && dsel == 2) k_sc_round<2, true><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done);
+        else if (big) k_sc_round<3, true><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done);
+        else
         switch (dsel) {   // one small kernel per uniform degree keeps the instruction footprint low
         case 1: k_sc_round<1><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
         case 2: k_sc_round<2><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
