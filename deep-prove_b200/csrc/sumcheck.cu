@@ -684,7 +684,7 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
     // grid sized for THIS round: 2 pairs per thread minimum so small rounds run in a single block
     // large rounds: ~4 pairs per thread (two in flight at a time, see sc_body<D, BIG>) amortise the per-thread reduction;
     // small rounds keep 2 pairs per thread so they fit one block
-    int gx = round_pairs > 8192 ? dp_grid_for((round_pairs + 3) / 4, SC_THREADS, 6)
+    int gx = round_pairs > 8192 ? dp_grid_for(round_pairs, SC_THREADS, 6)
                                 : std::min(s->gx, dp_grid_for(round_pairs <= 256 ? round_pairs : (round_pairs + 1) / 2, SC_THREADS, 4));
     cudaStream_t st = dp_ctx().stream;
     // descriptors are read by the kernel straight from mapped pinned memory (no H2D copy node)
@@ -702,7 +702,8 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
         else if ((u64)gx * s->n_products > 32) { DP_CUDA(cudaMemcpyAsync(s->d_descs, s->h_descs, sizeof(ScProd) * s->n_products, cudaMemcpyHostToDevice, st)); descs_arg = s->d_descs; }
         u32 dsel = s->products[0].n_idx;
         for (auto &pr : s->products) if (pr.n_idx != dsel) dsel = 0;
-        const bool big = round_pairs > 8192 && (dsel == 2 || dsel == 3);
+        bool big = round_pairs > 8192 && (dsel == 2 || dsel == 3);
+        for (u32 p = 0; p < s->n_products; p++) if (!s->h_descs[p].allbase) big = false;   // measured: the two-in-flight body only pays off for the all-Base first round (122 regs on the Ext path)
         if (big && dsel == 2) k_sc_round<2, true><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done);
         else if (big) k_sc_round<3, true><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done);
         else
