@@ -142,6 +142,44 @@ __global__ void k_expand(const T *__restrict__ c, T *__restrict__ out, u32 lg_m,
     }
 }
 
+
+// ---- small polynomials: bit reversal, hypercube interpolation, zero-pad + coset scale, and the whole DIF NTT in ONE block ----
+// (k_bitrev -> k_tile_pass<T,0> -> k_expand -> k_tile_pass<T,1> on a codeword that fits in shared memory: a 2^10 witness column
+//  costs one launch instead of six; same butterflies, same twiddles, same order -> identical codeword)
+template <typename T>
+__global__ void __launch_bounds__(512) k_encode_small(const T *__restrict__ in, T *__restrict__ bh, T *__restrict__ cw, u32 nv, u64 shift, PowTab tab) {
+    extern __shared__ unsigned char smem_raw[];
+    T *sm = reinterpret_cast<T *>(smem_raw);
+    __shared__ u64 sq[16];                                  // shift^(2^k)
+    const u32 m = 1u << nv, n_log = nv + 1, N = 2u << nv;
+    if (threadIdx.x == 0) { u64 x = shift; for (u32 k = 0; k < nv; k++) { sq[k] = x; x = gl_sqr(x); } }
+    for (u32 j = threadIdx.x; j < m; j += blockDim.x) { T v = in[__brev(j) >> (32 - nv)]; bh[j] = v; sm[j] = v; }
+    __syncthreads();
+    for (u32 l = 0; l < nv; l++) {                          // interpolate_over_boolean_hypercube on the bit-reversed evaluations
+        const u32 half = m >> (l + 1);
+        for (u32 q = threadIdx.x; q < (m >> 1); q += blockDim.x) { u32 i0 = (q / half) * 2 * half + (q % half); sm[i0 + half] = t_sub(sm[i0 + half], sm[i0]); }
+        __syncthreads();
+    }
+    for (u32 j = threadIdx.x; j < m; j += blockDim.x) {    // k_expand: x = c[j] shift^j ; out[j] = x ; out[j+m] = x w_N^j  (first DIF level of the zero-padded input)
+        u64 sp = 1; for (u32 k = 0; k < nv; k++) if (j >> k & 1) sp = gl_mul(sp, sq[k]);
+        T x = t_mulb(sm[j], sp);
+        sm[j] = x; sm[j + m] = t_mulb(x, tab_pow(tab, (u64)j << (32 - n_log)));
+    }
+    __syncthreads();
+    for (u32 l = 1; l < n_log; l++) {                       // remaining DIF levels
+        const u32 half = N >> (l + 1);
+        for (u32 q = threadIdx.x; q < (N >> 1); q += blockDim.x) {
+            u32 i0 = (q / half) * 2 * half + (q % half), i1 = i0 + half;
+            u64 e = (u64)(i0 & (half - 1)) << l;
+            u64 w = tab_pow(tab, e << (32 - n_log));
+            T u = sm[i0], v = sm[i1];
+            sm[i0] = t_add(u, v); sm[i1] = t_mulb(t_sub(u, v), w);
+        }
+        __syncthreads();
+    }
+    for (u32 k = threadIdx.x; k < N; k += blockDim.x) cw[k] = sm[k];
+}
+
 // ---- K9 Merkle ----
 template <bool EXT> __device__ __forceinline__ void leaf_pair_digest(const void *leaves, u64 pair, u64 d[4]) {
     if (EXT) { const gle *l = (const gle *)leaves + 2 * pair; gle a = ld_e(l), b = ld_e(l + 1); d[0] = a.c0; d[1] = a.c1; d[2] = b.c0; d[3] = b.c1; }
@@ -215,6 +253,34 @@ __global__ void __launch_bounds__(256) k_merkle_tail(const void *leaves, u64 n, 
         __syncthreads();
     }
 }
+// several consecutive levels of a medium tree in ONE launch: every block owns 2^(nlev-1) hashes of the first level and
+// walks its subtree upwards (8 lanes per hash, __syncthreads between levels), writing every level it passes.
+// A 2^11-leaf witness tree costs 2 launches (this + the tail) instead of 6: the level-by-level latency chain is the same,
+// the launches (the scarce resource when 16 proofs are in flight) are not.
+template <bool EXT, bool FROM_LEAVES>
+__global__ void __launch_bounds__(256) k_merkle_multi(const void *src, u32 first_level, u32 nlev, u64 nl_first, u64 *levels, LvlOff lo) {
+    const int lane8 = threadIdx.x & 7; const u32 grp = threadIdx.x >> 3, ngrp = blockDim.x >> 3;
+    const u64 h0 = 1ULL << (nlev - 1);                         // hashes of the first level owned by this block
+    for (u32 k = 0; k < nlev; k++) {
+        const u32 l = first_level + k;
+        const u64 cnt = h0 >> k, base = (u64)blockIdx.x * cnt; // this block's hashes at level l
+        u64 *out = levels + 4 * lo.off[l];
+        const u64 rounds = (cnt + ngrp - 1) / ngrp;
+        for (u64 it = 0; it < rounds; it++) {
+            if (it * ngrp + ((threadIdx.x >> 5) << 2) >= cnt) continue;   // whole warp idle (warp-uniform)
+            const u64 j = it * ngrp + grp; const bool live = j < cnt; const u64 i = base + j;
+            u64 xw = 0, yw = 0;
+            if (live && lane8 < 4) {
+                if (k == 0 && FROM_LEAVES) { xw = leaf_pair_word<EXT>(src, 2 * i, lane8); yw = leaf_pair_word<EXT>(src, 2 * i + 1, lane8); }
+                else { const u64 *in = (k == 0 ? (const u64 *)src : levels + 4 * lo.off[l - 1]) + 8 * i; xw = in[lane8]; yw = in[4 + lane8]; }
+            }
+            u64 sres = p2x8_compress(xw, yw, lane8);
+            if (live && lane8 < 4) out[4 * i + (3 - lane8)] = sres;
+        }
+        __syncthreads();
+    }
+    (void)nl_first;
+}
 template <bool EXT> __global__ void k_leafpair_root(const void *leaves, u64 *out) { u64 d[4]; leaf_pair_digest<EXT>(leaves, 0, d); for (int i = 0; i < 4; i++) out[i] = d[i]; }
 
 // A Merkle tree over `n` leaves living in HBM: levels >= 1 packed back to back.
@@ -239,8 +305,22 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
     } else {
         const u64 TAIL = 32;   // levels with <= TAIL digests (one 1024-thread pass, 8 lanes per hash) are finished by one single-block launch
         u32 l = 1;
+        LvlOff lo_all; memset(&lo_all, 0, sizeof lo_all);
+        for (u32 k = 1; k < t.lg && k < 36; k++) lo_all.off[k] = t.lvl_off[k];
         for (; l < t.lg && (n >> (l + 1)) > TAIL; l++) {
             u64 nl = n >> (l + 1);
+            u32 a = 0; while ((1ULL << a) < nl) a++;
+            if (nl <= 32768 && a >= 8 && t.lg < 36) {   // medium level: this and the next nlev-1 levels in one launch
+                u32 nlev = std::min<u32>(7, a - 5);
+                DpProfScope prof("k_merkle_multi(poseidon2 compress)", (l == 1 ? nl * (ext ? 64 : 32) : nl * 64) + 2 * nl * 32);
+                unsigned g = (unsigned)(nl >> (nlev - 1));
+                const void *src = l == 1 ? leaves : (const void *)(t.levels + 4 * t.lvl_off[l - 1]);
+                if (l == 1) { if (ext) k_merkle_multi<true, true><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all); else k_merkle_multi<false, true><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all); }
+                else k_merkle_multi<false, false><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all);
+                DP_LAUNCHED();
+                l += nlev - 1;
+                continue;
+            }
             if (nl <= 32768) {   // too few hashes for one thread each: 8 lanes per hash
                 DpProfScope prof("k_merkle_x8(poseidon2 compress)", l == 1 ? nl * (ext ? 64 : 32) + nl * 32 : nl * 96);
                 int g = dp_grid_for(nl * 8, 256, 8);
@@ -395,11 +475,23 @@ static int commit_enqueue(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **o
     } else {
         u64 N = m << BF_RATE_LOG; u32 n_log = nv + BF_RATE_LOG;
         cm->cw_len = N;
+        if (int e = dp_dev_alloc(&cm->codeword, esz * N)) return e;
+        // coset shift: shift = 7^(2^(full_log - lg m))  (rs.rs:481-488)
+        u64 shift = 7; for (u32 i = 0; i < full_log - nv; i++) shift = gl_sqr(shift);
+        if (esz * N <= 64 * 1024 && nv <= 15) {   // the whole codeword fits in one block's shared memory: one launch
+            size_t smem = esz * N;
+            DpProfScope p("k_encode_small(bitrev+moebius+expand+ntt)", esz * m * 2 + esz * N);
+            if (poly->is_ext) {
+                if (smem > 48 * 1024) DP_CUDA(cudaFuncSetAttribute(k_encode_small<gle>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_encode_small<gle><<<1, 512, smem, c.stream>>>((const gle *)poly->data, (gle *)cm->bh_evals, (gle *)cm->codeword, nv, shift, root_tab());
+            } else {
+                if (smem > 48 * 1024) DP_CUDA(cudaFuncSetAttribute(k_encode_small<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_encode_small<u64><<<1, 512, smem, c.stream>>>((const u64 *)poly->data, (u64 *)cm->bh_evals, (u64 *)cm->codeword, nv, shift, root_tab());
+            }
+            DP_LAUNCHED(); DP_CUDA(cudaGetLastError());
+        } else {
         void *coef = nullptr;
         if (int e = dp_dev_alloc(&coef, esz * m)) return e;
-        if (int e = dp_dev_alloc(&cm->codeword, esz * N)) return e;
-        // coset shift table: shift = 7^(2^(full_log - lg m))  (rs.rs:481-488)
-        u64 shift = 7; for (u32 i = 0; i < full_log - nv; i++) shift = gl_sqr(shift);
         u64 *stab = nullptr;
         if (int e = dp_dev_alloc((void **)&stab, sizeof(u64) * 3 * 2048)) return e;
         k_pow_table<<<24, 256, 0, c.stream>>>(shift, stab); DP_LAUNCHED();
@@ -420,6 +512,7 @@ static int commit_enqueue(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **o
         }
         DP_CUDA(cudaGetLastError());
         dp_dev_free(coef); dp_dev_free(stab);
+        }
     }
     if (int e = tree_build(cm->tree, cm->codeword, poly->is_ext, cm->cw_len)) return e;   // K9
     DP_CUDA(cudaMemcpyAsync(root_pinned, cm->tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
