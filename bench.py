@@ -15,6 +15,8 @@ A "step" is one pass of the hot path over one batch of synthetic input.  Workloa
 `--impl reference` times the CPU path (the oracle port -- the reference itself is Rust with un-vendored
 dependencies and cannot be built in this image) on the same config.
 """
+import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before torch/CUDA initialise: 16 proof streams + commit pools need more than 8 hardware queues
 import argparse
 import json
 import os

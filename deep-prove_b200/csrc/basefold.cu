@@ -548,7 +548,7 @@ int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_log
     for (u32 i = 0; i < n; i++) DP_CHECK(polys[i] != nullptr, DP_ERR_INVALID, "dp_pcs_commit_many: null polynomial");
     if (int e = bf_prepare()) return e;
     DpCtx &c = dp_ctx();
-    const u32 S = 4;
+    static const u32 S = [] { const char *e = getenv("DP_COMMIT_STREAMS"); int v = e ? atoi(e) : 4; return (u32)(v < 1 ? 1 : (v > 8 ? 8 : v)); }();   // streams per host thread for independent commits
     (void)g_set_return;
     if (g_pool.empty()) {
         std::lock_guard<std::mutex> lk(g_sets_mu);

@@ -158,6 +158,10 @@ int dp_device_count(void) {
 }
 
 int dp_init(int device) {
+    // many small kernels from many streams: the default of 8 hardware work queues makes unrelated streams wait on each
+    // other (a resident tail kernel in a shared queue stalls its neighbours); 32 is the hardware maximum.  Only effective
+    // if CUDA is not initialised yet in this process -- hosts that initialise CUDA first should export it themselves.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
     int n = dp_device_count();
     if (n <= 0) return dp_fail(DP_ERR_NO_DEVICE, "no CUDA device visible: deepprove_b200 has no CPU fallback");

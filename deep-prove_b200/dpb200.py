@@ -29,6 +29,10 @@ ABI_SYMBOLS = [
 ]
 
 
+# must be in the environment before CUDA initialises (see dp_init): 32 hardware work queues instead of 8
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 class DpError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("deepprove_b200 error %d: %s" % (code, msg))

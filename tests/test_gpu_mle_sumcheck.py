@@ -197,3 +197,28 @@ def test_prove_batch_polys(gpu, nv, shape, T):
     point, msgs, fin = gpu.sumcheck_prove_batch_polys(T, dm, products, nv)
     opoint, omsgs, ofin = O.sumcheck_prove(mles, products, nv)
     assert (point == opoint).all() and (msgs == omsgs).all() and (fin == ofin).all()
+
+
+def test_resident_tail_is_released_when_the_prover_is_dropped(gpu):
+    """the resident tail kernel (dp_sc_set_resident_tail) waits for challenges on the device; dropping the handle in the
+    middle of a proof must release it (abort word) instead of leaving a spinning kernel behind, and the library must keep
+    working afterwards.  Also: with and without the tail the round messages are identical."""
+    import ctypes as C
+    nv = 9
+    mles = [(O.splitmix_f(71, 1 << nv), False), (O.splitmix_e(72, 1 << nv), True)]
+    products = [((2, 3), [0, 1]), ((1, 0), [1, 1, 0])]
+    ch = O.splitmix_e(73, nv)
+    exp_msgs, exp_fin = O.sumcheck_rounds_fixed(mles, products, nv, ch)
+    for tail in (0, 1):
+        sc = gpu.Sumcheck([gpu.Mle.upload(a, e) for a, e in mles], products, nv, 3)
+        gpu.check(gpu.lib().dp_sc_set_resident_tail(sc.h, tail))
+        got = [sc.round(None)] + [sc.round(ch[i - 1]) for i in range(1, nv)]
+        assert (np.array(got) == exp_msgs).all()
+        assert (sc.finish(ch[nv - 1]) == exp_fin).all()
+        sc.destroy()
+    sc = gpu.Sumcheck([gpu.Mle.upload(a, e) for a, e in mles], products, nv, 3)
+    gpu.check(gpu.lib().dp_sc_set_resident_tail(sc.h, 1))
+    sc.round(None); sc.round(ch[0]); sc.round(ch[1])      # tables are <= 128 pairs from round 2 on: the tail kernel is now waiting
+    sc.destroy()                                           # must post the abort word and return
+    m = gpu.Mle.upload(mles[0][0], False)
+    assert (m.evaluate(ch) == O.evaluate(mles[0][0], False, ch)).all()   # the stream is usable again
