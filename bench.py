@@ -299,6 +299,24 @@ class CnnWorkload:
     flush = True
 
 
+def pin_to_gpu_numa_node(torch, local_rank):
+    """Every round trip of the prover crosses PCIe twice (mapped-memory message, challenge mailbox): keep this rank's
+    host threads on the CPUs local to its GPU (sysfs local_cpulist of the GPU's PCI function).  Best effort."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -385,6 +403,7 @@ def main():
     if not torch.cuda.is_available() or dp.device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    pin_to_gpu_numa_node(torch, local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist

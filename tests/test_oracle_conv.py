@@ -61,3 +61,19 @@ def test_small_cnn_full_proof_passes_every_invariant():
     desc, data, inp = O.synthetic_cnn(1, 3, 4)
     kinds = list(desc[:, 0])
     assert kinds == [3, 1, 2, 4, 3, 1, 2, 4, 0, 1, 2, 0, 1, 2, 0]
+
+
+def test_numpy_model_descriptor_proves_on_the_checker():
+    """deep-prove_b200/models.py (the arrays bench.py feeds to both arms): the small CNN proves and passes every invariant;
+    the CNN-264k descriptor has the reference script's layer sizes (cifar-cnn.py:175-241 with --num-params 264000)"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deep-prove_b200"))
+    import models
+    desc, data, x, n = models.cnn_small(seed=3)
+    flat, _ = O.model_prove(desc, data, x)
+    assert flat.size > 10000 and (flat == O.model_prove(desc, data, x)[0]).all()
+    d, w, xin, n_params = models.cnn(seed=1)
+    assert [int(k) for k in d[:, 0]] == [3, 1, 2, 4, 3, 1, 2, 4, 0, 1, 2, 0, 1, 2, 0]
+    assert tuple(d[0, 1:8]) == (16, 4, 32, 8, 12, 28, 28) and tuple(d[4, 1:8]) == (64, 16, 16, 8, 33, 10, 10)
+    assert tuple(d[8, 1:3]) == (256, 4096) and tuple(d[11, 1:3]) == (256, 256) and tuple(d[14, 1:3]) == (16, 256)
+    assert n_params == 12 * (75 + 1) + 33 * (12 * 25 + 1) + 247 * (825 + 1) + 173 * (247 + 1) + 10 * (173 + 1)
