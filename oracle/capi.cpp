@@ -422,3 +422,22 @@ int dpo_pcs_batch_verify(const u64 *flat, u64 n, u32 n_polys, const u64 *roots, 
     } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
 }
+
+// ---- model verifier (zk_verify.hpp): prove on the checker, then verify on a FRESH transcript as deep-prove's verifier would ----
+#include "zk_verify.hpp"
+extern "C" int dpo_zkml_prove_verify(u32 n_layers, u32 width, u64 seed_model, u64 seed_input, const char *label, int tamper) {
+    try {
+        Model m = synthetic_mlp(n_layers, width, seed_model);
+        std::vector<Element> input = synthetic_input(width, seed_input);
+        ZkContext ctx = zk_context(m);
+        Transcript tp(label);
+        ModelProof p = zk_prove(ctx, input, tp);
+        std::vector<Element> output = zk_run(m, input).back();
+        if (tamper == 1) output[0] += 1;                                          // wrong public output
+        if (tamper == 2) p.dense.begin()->second.individual_claims[1].c0 ^= 1;    // a forged claim
+        if (tamper == 3) p.table_proofs[0].lookup.circuit_outputs[0][0].c0 ^= 1;  // a forged lookup fraction
+        Transcript tv(label);
+        zk_verify(ctx, input, output, p, tv);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}

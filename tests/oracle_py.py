@@ -444,3 +444,9 @@ def pcs_batch_verify(flat, roots, num_vars, is_base, full_log, points, evals, la
     pt = u64(np.concatenate([u64(p).reshape(-1) for p in points])); ev = u64(evals).reshape(-1)
     rc = lib().dpo_pcs_batch_verify(ptr(f), C.c_uint64(f.size), C.c_uint32(len(nv)), ptr(r), ptr(nv), ptr(ib), C.c_uint32(full_log), ptr(pt), ptr(ev), label)
     return None if rc == 0 else lib().dpo_last_error().decode()
+
+
+def zkml_prove_verify(n_layers, width, seed_model, seed_input, label=b"m2vec", tamper=0):
+    """prove on the checker, verify on a fresh transcript with the restated model verifier; None = accepted, else the reason"""
+    rc = lib().dpo_zkml_prove_verify(C.c_uint32(n_layers), C.c_uint32(width), C.c_uint64(seed_model), C.c_uint64(seed_input), label, C.c_int(tamper))
+    return None if rc == 0 else lib().dpo_last_error().decode()

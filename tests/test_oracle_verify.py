@@ -37,3 +37,14 @@ def test_batch_open_verifies(shape, full_log):
     assert "classic sumcheck" in O.pcs_batch_verify(flat, np.array(roots), nvs, isb, full_log, points, bad)
     tam = flat.copy(); tam[-3] ^= np.uint64(1)
     assert O.pcs_batch_verify(tam, np.array(roots), nvs, isb, full_log, points, evals) is not None
+
+
+@pytest.mark.parametrize("nl,w", [(2, 64), (1, 256), (3, 128)])
+def test_model_proof_is_accepted_by_the_restated_verifier(nl, w):
+    """Verifier::verify (zkml/src/iop/verifier.rs:72-296) restated in oracle/zk_verify.hpp re-derives every challenge on its
+    own transcript: acceptance pins the prover restatement's Fiat-Shamir order and claim chaining (dense, requant, relu,
+    table proofs, commitment openings), which device-vs-checker equality alone cannot; forged proofs are rejected."""
+    assert O.zkml_prove_verify(nl, w, 5, 6) is None
+    assert O.zkml_prove_verify(nl, w, 5, 6, tamper=1) is not None      # wrong public output
+    assert "dense" in O.zkml_prove_verify(nl, w, 5, 6, tamper=2)        # forged claim
+    assert O.zkml_prove_verify(nl, w, 5, 6, tamper=3) is not None      # forged lookup fraction
