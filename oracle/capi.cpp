@@ -441,3 +441,34 @@ extern "C" int dpo_zkml_prove_verify(u32 n_layers, u32 width, u64 seed_model, u6
         return 0;
     } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
+
+// prove + verify for a model given as a layer descriptor (same format as dpo_model_prove)
+extern "C" int dpo_model_prove_verify(const int64_t *desc, u32 n_nodes, const int64_t *data, const int64_t *input, u64 input_len, const char *label, int tamper) {
+    try {
+        Model m; m.input_len = input_len; const int64_t *w = data;
+        for (u32 i = 0; i < n_nodes; i++) {
+            const int64_t *d = desc + 9 * (size_t)i; Node n;
+            switch (d[0]) {
+            case 0: n.kind = OP_DENSE; n.nrows = d[1]; n.ncols = d[2]; n.weights.assign(w, w + n.nrows * n.ncols); w += n.nrows * n.ncols; n.bias.assign(w, w + n.nrows); w += n.nrows; break;
+            case 1: n.kind = OP_REQUANT; n.rq.right_shift = d[1]; n.rq.fp_scale = d[2]; n.rq.fixed_point_multiplier = d[3]; n.rq.intermediate_bit_size = d[4]; break;
+            case 2: n.kind = OP_RELU; break;
+            case 3: { n.kind = OP_CONV; auto c = std::make_shared<ConvLayer>(); c->kw = d[1]; c->kx = d[2]; c->nw = d[3]; c->real_nw = d[4]; for (int k = 0; k < 3; k++) c->unpadded_out[k] = d[5 + k];
+                      size_t fl = c->kw * c->kx * c->real_nw * c->real_nw; c->filter.assign(w, w + fl); w += fl; c->bias.assign(w, w + c->kw); w += c->kw; n.conv = c; break; }
+            case 4: n.kind = OP_POOL; n.pool_c = d[1]; n.pool_h = d[2]; n.pool_w = d[3]; break;
+            default: throw std::runtime_error("dpo_model_prove_verify: unknown node kind");
+            }
+            m.nodes.push_back(n);
+        }
+        std::vector<Element> in(input, input + input_len);
+        ZkContext ctx = zk_context(m);
+        Transcript tp(label);
+        ModelProof p = zk_prove(ctx, in, tp);
+        std::vector<Element> output = zk_run(m, in).back();
+        if (tamper == 1) output[0] += 1;
+        if (tamper == 2 && !p.conv.empty()) p.conv.begin()->second.partial_evals[0].c0 ^= 1;
+        if (tamper == 3 && !p.pooling.empty()) p.pooling.begin()->second.zerocheck_evals[1].c1 ^= 1;
+        Transcript tv(label);
+        zk_verify(ctx, in, output, p, tv);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}

@@ -98,6 +98,85 @@ static inline std::vector<E> evaluate_table_columns(const TableType &tt, const s
     return {first, mle_evaluate(*base_mle(col), point)};
 }
 
+
+// pow_two_omegas / phi_eval (layers/convolution.rs:1450-1482)
+static inline std::vector<E> pow_two_omegas(size_t n, bool is_fft) {
+    std::vector<E> pows(n - 1); E rou = get_root_of_unity(n); if (is_fft) rou = e_inv(rou);
+    pows[0] = rou; for (size_t i = 1; i + 1 < n; i++) pows[i] = e_mul(pows[i - 1], pows[i - 1]);
+    return pows;
+}
+static inline E phi_eval(const std::vector<E> &r, E rand1, E rand2, const std::vector<E> &exponents, bool first_iter) {
+    E ev = E::one(), one = E::one();
+    for (size_t i = 0; i < r.size(); i++) ev = e_mul(ev, e_add(e_sub(one, r[i]), e_mul(r[i], exponents[exponents.size() - r.size() + i])));
+    if (first_iter) return e_mul(e_sub(one, rand2), e_add(e_sub(one, rand1), e_mul(rand1, ev)));
+    return e_add(e_sub(one, rand1), e_mul(e_mul(e_sub(one, e_mul(E::from_u64(2), rand2)), rand1), ev));
+}
+// ConvCtx::verify_fft_delegation (convolution.rs:1090-1141)
+static inline void verify_fft_delegation(Transcript &t, E claim, const ConvProof &proof, const MatrixEvalProof &del, std::vector<E> prev_r, size_t lfs) {
+    size_t iter = del.proofs.size();
+    std::vector<E> exponents = pow_two_omegas(iter + 1, false);
+    for (size_t i = 0; i < iter; i++) {
+        sumcheck_verify(claim, del.proofs[i], lfs - i, 3, t);
+        zk_ensure(eq_eval(del.proofs[i].point, std::vector<E>(prev_r.begin(), prev_r.begin() + del.proofs[i].point.size())) == del.claims[i][0], "Error in identity evaluation fft delegation");
+        zk_ensure(phi_eval(del.proofs[i].point, proof.hadamard_proof.point[i], prev_r.back(), exponents, i == 0) == del.claims[i][1], "Error in phi computation fft delegation");
+        claim = del.claims[i][2]; prev_r = del.proofs[i].point;
+    }
+    E one = E::one();
+    zk_ensure(claim == e_add(e_mul(e_sub(one, e_mul(E::from_u64(2), proof.hadamard_proof.point[iter])), prev_r[0]), e_sub(one, prev_r[0])), "Error in final FFT delegation step");
+}
+// hadamard::verify (layers/hadamard.rs:128-159)
+static inline Claim hadamard_verify(Transcript &t, const HadamardProof &proof, const Claim &out_claim, E expected_v2_eval) {
+    SumCheckSubClaim sub = sumcheck_verify(out_claim.eval, proof.sumcheck, out_claim.point.size(), 3, t);
+    E beta_eval = eq_eval(out_claim.point, proof.sumcheck.point);
+    zk_ensure(expected_v2_eval == proof.individual_claim[1], "Hadamard verification failed for v2 eval");
+    zk_ensure(e_mul(e_mul(beta_eval, proof.individual_claim[0]), proof.individual_claim[1]) == sub.expected_evaluation, "Hadamard verification failed for product eval");
+    return {proof.sumcheck.point, proof.individual_claim[0]};
+}
+// ConvCtx::verify_convolution (convolution.rs:1143-1375); returns the claim on the layer input, fills the two commitment claims
+static inline Claim verify_convolution(const ConvLayer &f, Transcript &t, const Claim &last_claim_in, const ConvProof &proof, Claim &filter_claim, Claim &bias_claim) {
+    size_t lfs = ceil_log2(f.filter_size()), lrow = lfs + 1, lkx = ceil_log2(f.kx);
+    size_t padded[3] = {f.kw, f.nw, f.nw};
+    std::vector<Element> clearing = new_clearing_tensor(f.unpadded_out, padded);
+    E expected_v2 = mle_evaluate(*base_mle(to_base_vec(clearing)), proof.clearing_proof.sumcheck.point);
+    Claim last_claim = hadamard_verify(t, proof.clearing_proof, last_claim_in, expected_v2);
+    E conv_claim = e_sub(last_claim.eval, proof.bias_claim);
+    sumcheck_verify(conv_claim, proof.ifft_proof, lrow, 2, t);
+    zk_ensure(proof.ifft_delegation.proofs.size() == lfs, "Inconsistency in iFFT delegation proofs/aux size");
+    size_t iter = lfs; E claim = proof.ifft_claims[1], one = E::one();
+    std::vector<E> exponents = pow_two_omegas(iter + 1, true), prev_r = proof.ifft_proof.point;
+    for (size_t i = 0; i < iter; i++) {
+        const IOPProof &dp = proof.ifft_delegation.proofs[i];
+        sumcheck_verify(claim, dp, lfs - i, 3, t);
+        zk_ensure(eq_eval(dp.point, std::vector<E>(prev_r.begin(), prev_r.begin() + dp.point.size())) == proof.ifft_delegation.claims[i][0], "Error in identity evaluation ifft delegation");
+        zk_ensure(phi_eval(dp.point, e_sub(one, last_claim.point[i]), prev_r.back(), exponents, false) == proof.ifft_delegation.claims[i][1], "Error in phi computation ifft delegation");
+        prev_r = dp.point; claim = proof.ifft_delegation.claims[i][2];
+    }
+    E scale = e_inv(E::from_u64((u64)1 << (iter + 1)));
+    zk_ensure(claim == e_add(e_mul(scale, prev_r[0]), e_mul(scale, e_sub(one, prev_r[0]))), "Error in final iFFT delegation step");
+    sumcheck_verify(proof.ifft_claims[0], proof.hadamard_proof, lrow + lkx, 3, t);
+    zk_ensure(proof.hadamard_claims[2] == eq_eval(proof.ifft_proof.point, std::vector<E>(proof.hadamard_proof.point.begin(), proof.hadamard_proof.point.begin() + proof.ifft_proof.point.size())), "Error in Beta evaluation");
+    sumcheck_verify(proof.hadamard_claims[1], proof.fft_proof, lrow, 2, t);
+    zk_ensure(proof.fft_delegation.proofs.size() == lfs, "Inconsistency in FFT delegation proofs/aux size");
+    verify_fft_delegation(t, proof.fft_claims[1], proof, proof.fft_delegation, proof.fft_proof.point, lfs);
+    sumcheck_verify(proof.hadamard_claims[0], proof.fft_proof_weights, lrow, 2, t);
+    verify_fft_delegation(t, proof.fft_weight_claims[1], proof, proof.fft_delegation_weights, proof.fft_proof_weights.point, lfs);
+    std::vector<E> wp = proof.fft_proof_weights.point; E v = e_inv(e_sub(one, wp.back())); wp.pop_back();
+    std::vector<E> eqt = build_eq_x_r_vec(wp);                                  // identity_eval(to_bits(i nw + j), weights_point) for all (i, j)
+    E yw = E::zero();
+    for (size_t i = 0; i < f.real_nw; i++) for (size_t j = 0; j < f.real_nw; j++) yw = e_add(yw, e_mul(proof.partial_evals[i * f.real_nw + j], eqt[i * f.nw + j]));
+    zk_ensure(e_mul(proof.fft_weight_claims[0], v) == yw, "Error in padded_fft evaluation claim");
+    std::vector<E> weights_rand = t.sample_vec(ceil_log2(f.real_nw * f.real_nw));
+    std::vector<E> point = proof.hadamard_proof.point; point.insert(point.end(), last_claim.point.begin() + lfs, last_claim.point.end());
+    bias_claim = Claim{std::vector<E>(last_claim.point.begin() + proof.ifft_delegation.proofs.size(), last_claim.point.end()), proof.bias_claim};
+    std::vector<E> fp = weights_rand; fp.insert(fp.end(), point.begin() + lrow, point.end());
+    filter_claim = Claim{fp, mle_evaluate(*ext_mle(proof.partial_evals.data(), proof.partial_evals.size()), weights_rand)};
+    std::vector<E> ip = proof.fft_proof.point; E vv = e_inv(e_sub(one, ip.back())); ip.pop_back();
+    for (auto &x : ip) x = e_sub(one, x);
+    Claim out; out.point = ip; out.point.insert(out.point.end(), proof.hadamard_proof.point.begin() + lrow, proof.hadamard_proof.point.end());
+    out.eval = e_mul(proof.fft_claims[0], vv);
+    return out;
+}
+// PoolingCtx::verify_pooling (layers/pooling.rs:525-650); the commitment claims are appended to `cv`
 struct VerifierCommitClaim { PureCommitment comm; Claim claim; };
 struct CommitmentVerifier {
     std::vector<VerifierCommitClaim> claims, trivial_claims;
@@ -187,7 +266,42 @@ static inline void zk_verify(const ZkContext &ctx, const std::vector<Element> &i
             cv.add_witness_claim(pure_of(p.commits[0], vc.claims[0].point.size()), vc.claims[0]);
             cv.add_witness_claim(pure_of(p.commits[1], new_out.point.size()), new_out);
             last = vc.claims[0];
-        } else throw ZkVerifyError("zk_verify: convolution / pooling verification is not restated yet");
+        } else if (n.kind == OP_CONV) {                                              // ConvCtx::verify -> verify_convolution
+            zk_ensure(proof.conv.count(id), "no convolution proof for node " + std::to_string(id));
+            Claim fc, bcl; Claim in_claim = verify_convolution(*n.conv, t, last, proof.conv.at(id), fc, bcl);
+            const auto &comms = ctx.model_comms.at(id);                               // add_common_claims: ConvBias, ConvFilter (BTreeMap order)
+            cv.add_witness_claim(pure_of(comms.at("ConvBias")->comm.root(), comms.at("ConvBias")->comm.num_vars), bcl);
+            cv.add_witness_claim(pure_of(comms.at("ConvFilter")->comm.root(), comms.at("ConvFilter")->comm.num_vars), fc);
+            used_model[id] = true;
+            last = in_claim;
+        } else if (n.kind == OP_POOL) {                                              // verify_pooling (pooling.rs:525-650)
+            zk_ensure(proof.pooling.count(id), "no pooling proof for node " + std::to_string(id));
+            const PoolingProof &p = proof.pooling.at(id);
+            LogUpVerifierClaim vc = verify_logup_proof(p.lookup, 4, constant_challenge, E::one(), t);
+            E bc = t.get_and_append_challenge("batch_pooling");
+            E init = E::zero(), comb = bc;
+            for (auto &c : vc.claims) { init = e_add(init, e_mul(c.eval, comb)); comb = e_mul(comb, bc); }
+            init = e_add(init, e_mul(comb, last.eval));
+            size_t nv = vc.point().size();
+            SumCheckSubClaim sub = sumcheck_verify(init, p.sumcheck, nv, 5, t);
+            const std::vector<E> &zc = sub.point;
+            E beta_eval = eq_eval(vc.point(), zc), lcb = eq_eval(last.point, zc);
+            size_t ks = p.zerocheck_evals.size() - 1;
+            E prod = beta_eval, sum = E::zero(), ch = bc;
+            for (size_t k = 0; k < ks; k++) { prod = e_mul(prod, p.zerocheck_evals[k]); sum = e_add(sum, e_mul(ch, p.zerocheck_evals[k])); ch = e_mul(ch, bc); }
+            E output_eval = p.zerocheck_evals[ks];
+            E expected = e_add(e_add(prod, e_mul(sum, beta_eval)), e_mul(e_mul(output_eval, lcb), ch));
+            zk_ensure(expected == sub.expected_evaluation, "Expected pooling zerocheck claim did not equal the verifier claim");
+            zk_ensure(p.commitments.size() == p.zerocheck_evals.size(), "pooling: commitments / evaluations mismatch");
+            for (size_t k = 0; k < p.zerocheck_evals.size(); k++) cv.add_witness_claim(pure_of(p.commitments[k], zc.size()), {zc, p.zerocheck_evals[k]});
+            E r1 = t.get_and_append_challenge("input_batching"), r2 = r1;             // `[challenge; 2]`
+            E m1 = e_sub(E::one(), r1), m2 = e_sub(E::one(), r2);
+            E mult[4] = {e_mul(m1, m2), e_mul(m1, r2), e_mul(r1, m2), e_mul(r1, r2)};
+            Claim next; next.point.push_back(r1); next.point.insert(next.point.end(), zc.begin(), zc.begin() + p.variable_gap);
+            next.point.push_back(r2); next.point.insert(next.point.end(), zc.begin() + p.variable_gap, zc.end());
+            next.eval = E::zero(); for (size_t k = 0; k < ks; k++) next.eval = e_add(next.eval, e_mul(e_sub(output_eval, p.zerocheck_evals[k]), mult[k]));
+            last = next;
+        } else throw ZkVerifyError("zk_verify: unknown node kind");
     }
     // table proofs, zipped with the context's table order (verifier.rs:215-240, verify_table :320-383)
     zk_ensure(proof.table_proofs.size() == ctx.tables.size(), "number of table proofs != number of tables");

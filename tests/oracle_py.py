@@ -450,3 +450,9 @@ def zkml_prove_verify(n_layers, width, seed_model, seed_input, label=b"m2vec", t
     """prove on the checker, verify on a fresh transcript with the restated model verifier; None = accepted, else the reason"""
     rc = lib().dpo_zkml_prove_verify(C.c_uint32(n_layers), C.c_uint32(width), C.c_uint64(seed_model), C.c_uint64(seed_input), label, C.c_int(tamper))
     return None if rc == 0 else lib().dpo_last_error().decode()
+
+
+def model_prove_verify(desc, data, x, label=b"m2vec", tamper=0):
+    d = i64(desc).reshape(-1, 9); w = i64(data); xi = i64(x)
+    rc = lib().dpo_model_prove_verify(ptr(d), C.c_uint32(d.shape[0]), ptr(w), ptr(xi), C.c_uint64(xi.size), label, C.c_int(tamper))
+    return None if rc == 0 else lib().dpo_last_error().decode()

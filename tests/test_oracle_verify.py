@@ -48,3 +48,18 @@ def test_model_proof_is_accepted_by_the_restated_verifier(nl, w):
     assert O.zkml_prove_verify(nl, w, 5, 6, tamper=1) is not None      # wrong public output
     assert "dense" in O.zkml_prove_verify(nl, w, 5, 6, tamper=2)        # forged claim
     assert O.zkml_prove_verify(nl, w, 5, 6, tamper=3) is not None      # forged lookup fraction
+
+
+@pytest.mark.parametrize("which", ["small", "cnn264k"])
+def test_cnn_proof_is_accepted_by_the_restated_verifier(which):
+    """the CNN path through the restated verifier: hadamard::verify, ConvCtx::verify_convolution + verify_fft_delegation
+    (convolution.rs:1090-1375), PoolingCtx::verify_pooling (pooling.rs:525-650) on top of the MLP pieces"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deep-prove_b200"))
+    import models
+    desc, data, x, _ = models.cnn_small(seed=3) if which == "small" else models.cnn(seed=1)
+    assert O.model_prove_verify(desc, data, x) is None
+    if which == "small":
+        assert O.model_prove_verify(desc, data, x, tamper=1) is not None
+        assert "padded_fft" in O.model_prove_verify(desc, data, x, tamper=2)
+        assert "pooling" in O.model_prove_verify(desc, data, x, tamper=3)
