@@ -234,10 +234,10 @@ class DenseWorkload:
         return self.ctx.prove(self.x)
 
     def run_resident(self, k, device):
-        self.ctx.prove_concurrent(self.STREAMS, k * self.units_per_step, device=device, e2e=False)
+        self.ctx.prove_concurrent(host_workers(self.STREAMS), k * self.units_per_step, device=device, e2e=False)
 
     def run_e2e(self, k, device):
-        self.ctx.prove_concurrent(self.STREAMS, k * self.units_per_step, device=device, e2e=True)
+        self.ctx.prove_concurrent(host_workers(self.STREAMS), k * self.units_per_step, device=device, e2e=True)
 
     def cpu_step(self, O, i):
         _, ms = O.zkml_prove(self.NL, self.W, self.SEED_MODEL, self.SEED_INPUT, want_proof=False)
@@ -284,10 +284,10 @@ class CnnWorkload:
         return self.ctx.prove(self.x)
 
     def run_resident(self, k, device):
-        self.ctx.prove_concurrent(self.STREAMS, k * self.units_per_step, device=device, e2e=False)
+        self.ctx.prove_concurrent(host_workers(self.STREAMS), k * self.units_per_step, device=device, e2e=False)
 
     def run_e2e(self, k, device):
-        self.ctx.prove_concurrent(self.STREAMS, k * self.units_per_step, device=device, e2e=True)
+        self.ctx.prove_concurrent(host_workers(self.STREAMS), k * self.units_per_step, device=device, e2e=True)
 
     def cpu_step(self, O, i):
         _, ms = O.model_prove(self.desc, self.data, self.x, want_proof=False)
@@ -297,6 +297,16 @@ class CnnWorkload:
     cpu_returns_seconds = True
     l2_note = ("%d proofs in flight per GPU (aggregate working set >> the 126 MB L2); single-stream latency is measured with a 256 MiB L2 flush between proofs" % STREAMS)
     flush = True
+
+
+def host_workers(streams):
+    """host threads per GPU: every in-flight proof has a thread that hashes and spin-waits, so never oversubscribe the box
+    (8 ranks x 16 threads would take all 128 hardware threads of the measurement host and starve everything else)"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cpus = os.cpu_count() or 16
+    if world * (streams + 2) <= cpus:
+        return streams
+    return max(4, cpus // world - 4)
 
 
 def pin_to_gpu_numa_node(torch, local_rank):
@@ -517,7 +527,7 @@ def main():
             "vs_baseline": (v / pub) if (pub and world == 1) else None,
             "dtype": dtype, "data": "synthetic",
             "config": {"workload": wl.name, "l2": wl.l2_note,
-                       "parallelism": "replicas x%d GPUs (no data-path collective)%s" % (world, (", %d concurrent independent proofs per GPU" % wl.STREAMS) if hasattr(wl, "STREAMS") else ""),
+                       "parallelism": "replicas x%d GPUs (no data-path collective)%s" % (world, (", %d concurrent independent proofs per GPU" % host_workers(wl.STREAMS)) if hasattr(wl, "STREAMS") else ""),
                        "proofs_per_step": ups,
                        "single_stream_latency_ms": latency_ms,
                        "baseline_note": "vs_baseline divides by the reference README's proving time (Dense 4M 2335 ms / CNN 264k 1242 ms; hardware and exact architecture not stated)"},
