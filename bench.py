@@ -56,7 +56,10 @@ class ClockSampler:
         self.proc = None
 
     def __enter__(self):
-        # ONE long-running nvidia-smi (-lms 200) for the whole timed region, as in the profiling recipe
+        # ONE long-running nvidia-smi (-lms 200) for the whole timed region, as in the profiling recipe; rank 0 only (its
+        # line is the one printed, and N pollers taking driver locks perturb a launch-heavy workload)
+        if int(os.environ.get("RANK", "0")) != 0:
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
