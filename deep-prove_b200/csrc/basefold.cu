@@ -330,10 +330,13 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
                 continue;
             }
             DpProfScope prof("k_merkle(poseidon2 compress)", l == 1 ? nl * (ext ? 64 : 32) + nl * 32 : nl * 96);
+            const unsigned mgrid = (unsigned)std::min<u64>((nl + 127) / 128, 1u << 22);
             if (l == 1) {
-                if (ext) k_merkle_l1<true><<<dp_grid_for(nl, 128, 8), 128, 0, c.stream>>>(leaves, nl, t.levels);
-                else k_merkle_l1<false><<<dp_grid_for(nl, 128, 8), 128, 0, c.stream>>>(leaves, nl, t.levels);
-            } else k_merkle_up<<<dp_grid_for(nl, 128, 8), 128, 0, c.stream>>>(t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
+                // one hash per thread, many SHORT blocks (no persistent grid-stride blocks): with 16 proofs in flight the block
+                // scheduler can interleave other streams' latency-critical single-block kernels every few microseconds
+                if (ext) k_merkle_l1<true><<<mgrid, 128, 0, c.stream>>>(leaves, nl, t.levels);
+                else k_merkle_l1<false><<<mgrid, 128, 0, c.stream>>>(leaves, nl, t.levels);
+            } else k_merkle_up<<<mgrid, 128, 0, c.stream>>>(t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
             DP_LAUNCHED();
         }
         if (l < t.lg) {
