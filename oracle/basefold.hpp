@@ -400,4 +400,88 @@ static inline std::vector<u64> flatten_proof(const BasefoldProof &p) {
     return o;
 }
 
+
+// ---- batch_commit / simple_batch_open: several same-size polynomials under ONE Merkle tree, opened at ONE point ----
+// (Basefold::batch_commit basefold.rs:356-452, merkelize with batch leaves merkle_tree.rs:261-330 + hash_two_leaves_batch_*
+//  util/hash.rs:30-41, simple_batch_open basefold.rs:777-861, simple_batch_commit_phase commit_phase.rs:363-510,
+//  simple_batch_prover_query_phase query_phase.rs:104-138,474-534)
+static inline Digest hash_batch_leaf(const std::vector<FVec> &vals, size_t idx) {
+    std::vector<u64> in;
+    for (auto &v : vals) { if (v.is_ext) { in.push_back(v.e[idx].c0); in.push_back(v.e[idx].c1); } else in.push_back(v.b[idx]); }
+    return hash_or_noop(in.data(), in.size());                 // hash_bases / hash_elems: m-to-1 (no-op pad when <= 4 base elements)
+}
+static inline std::vector<std::vector<Digest>> merkelize_batch(const std::vector<FVec> &vals) {
+    if (vals.size() == 1) return merkelize(vals[0]);
+    size_t n = vals[0].len(), lg = ceil_log2(n);
+    std::vector<std::vector<Digest>> tree;
+    std::vector<Digest> h(n >> 1);
+    par_for(n >> 1, 2048, [&](size_t ib, size_t ie) { for (size_t i = ib; i < ie; i++) h[i] = compress(hash_batch_leaf(vals, 2 * i), hash_batch_leaf(vals, 2 * i + 1)); });
+    tree.push_back(h);
+    for (size_t l = 1; l < lg; l++) {
+        const auto &prev = tree[l - 1]; std::vector<Digest> nx(prev.size() >> 1);
+        par_for(nx.size(), 64, [&](size_t ib, size_t ie) { for (size_t i = ib; i < ie; i++) nx[i] = compress(prev[2 * i], prev[2 * i + 1]); });
+        tree.push_back(nx);
+    }
+    return tree;
+}
+struct BatchCommitment {                                        // BasefoldCommitmentWithWitness with num_polys > 1
+    std::vector<std::vector<Digest>> inner; std::vector<FVec> leaves, bh_evals;   // leaves = bit-reversed codewords (raw evals when trivial)
+    size_t num_vars = 0, num_polys = 0; bool is_base = true, trivial = false;
+    Digest root() const { return inner.back()[0]; }
+    size_t codeword_size() const { return leaves[0].len(); }
+    std::vector<Digest> path(size_t leaf_index) const { std::vector<Digest> p; for (size_t l = 0; l + 1 < inner.size(); l++) p.push_back(inner[l][(leaf_index >> (l + 1)) ^ 1]); return p; }
+};
+static inline BatchCommitment basefold_batch_commit(const std::vector<FVec> &polys, size_t full_log) {
+    if (polys.empty()) throw std::runtime_error("cannot batch commit to zero polynomials");
+    BatchCommitment c; c.num_polys = polys.size(); c.num_vars = ceil_log2(polys[0].len()); c.is_base = !polys[0].is_ext;
+    for (auto &p : polys) if (ceil_log2(p.len()) != c.num_vars || p.is_ext != polys[0].is_ext) throw std::runtime_error("cannot batch commit to polynomials with different number of variables");
+    for (auto &p : polys) { Commitment one = basefold_commit(p, full_log); c.trivial = one.trivial; c.leaves.push_back(one.codeword_tree.leaves); c.bh_evals.push_back(one.bh_evals); }
+    c.inner = merkelize_batch(c.leaves);
+    return c;
+}
+struct SimpleBatchQueryResult { size_t x_index, index; bool is_base; std::vector<E> left, right; std::vector<Digest> path; std::vector<QueryOpening> oracle; };
+struct SimpleBatchProof { CommitPhaseProof commit_phase; std::vector<SimpleBatchQueryResult> queries; bool trivial = false; std::vector<FVec> trivial_evals; };
+// simple_batch_commit_phase: the single-polynomial commit phase on  sum_i coeff_i codeword_i  /  sum_i coeff_i bh_evals_i
+static inline SimpleBatchProof basefold_simple_batch_open(size_t full_log, const BatchCommitment &comm, const std::vector<E> &point, const std::vector<E> &evals, Transcript &t) {
+    SimpleBatchProof pr;
+    if (comm.trivial) { pr.trivial = true; pr.trivial_evals = comm.bh_evals; return pr; }
+    if (comm.num_polys != evals.size() || point.size() != comm.num_vars) throw std::runtime_error("simple_batch_open: shape mismatch");
+    size_t bsl = ceil_log2(evals.size());
+    std::vector<E> tt; for (size_t i = 0; i < bsl; i++) tt.push_back(t.get_and_append_challenge("batch coeffs"));
+    std::vector<E> eq_xt = build_eq_x_r_vec(tt); eq_xt.resize(evals.size());
+    // a synthetic single commitment carrying the batched codeword / evaluations drives the unchanged commit phase
+    Commitment batched; batched.num_vars = comm.num_vars; batched.is_base = false;
+    std::vector<E> cw(comm.codeword_size(), E::zero()), ev((size_t)1 << comm.num_vars, E::zero());
+    for (size_t k = 0; k < comm.num_polys; k++) {
+        for (size_t i = 0; i < cw.size(); i++) cw[i] = e_add(cw[i], e_mul(comm.leaves[k].get(i), eq_xt[k]));
+        for (size_t i = 0; i < ev.size(); i++) ev[i] = e_add(ev[i], e_mul(comm.bh_evals[k].get(i), eq_xt[k]));
+    }
+    batched.codeword_tree.leaves = ext_fvec(cw); batched.bh_evals = ext_fvec(ev);
+    std::vector<MerkleTree> trees;
+    pr.commit_phase = commit_phase(full_log, point, batched, t, comm.num_vars, comm.num_vars - RS_BASECODE_MSG_SIZE_LOG, trees);
+    for (size_t x : query_indices(t, RS_NUM_QUERIES, comm.codeword_size())) {
+        SimpleBatchQueryResult q; q.x_index = x; size_t p1 = x | 1, p0 = p1 - 1; q.index = p0; q.is_base = comm.is_base;
+        for (auto &l : comm.leaves) { q.left.push_back(l.get(p0)); q.right.push_back(l.get(p1)); }
+        q.path = comm.path(p0);
+        size_t index = x >> 1;
+        for (auto &tr : trees) { q.oracle.push_back(open_pair(tr, index)); index >>= 1; }
+        pr.queries.push_back(q);
+    }
+    return pr;
+}
+static inline std::vector<u64> flatten_simple_batch_proof(const SimpleBatchProof &p) {
+    std::vector<u64> o;
+    o.push_back(p.commit_phase.sumcheck_messages.size()); for (auto &m : p.commit_phase.sumcheck_messages) for (E e : m) flat_e(o, e);
+    o.push_back(p.commit_phase.roots.size()); for (auto &d : p.commit_phase.roots) flat_d(o, d);
+    o.push_back(p.commit_phase.final_message.size()); for (E e : p.commit_phase.final_message) flat_e(o, e);
+    o.push_back(p.queries.size());
+    for (auto &q : p.queries) {
+        o.push_back(q.x_index); o.push_back(q.index); o.push_back(q.is_base ? 1 : 0); o.push_back(q.left.size());
+        for (size_t k = 0; k < q.left.size(); k++) { if (q.is_base) { o.push_back(q.left[k].c0); o.push_back(q.right[k].c0); } else { flat_e(o, q.left[k]); flat_e(o, q.right[k]); } }
+        o.push_back(q.path.size()); for (auto &d : q.path) flat_d(o, d);
+        o.push_back(q.oracle.size()); for (auto &x : q.oracle) flat_q(o, x);
+    }
+    return o;
+}
+
 }  // namespace dpo

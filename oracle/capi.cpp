@@ -472,3 +472,38 @@ extern "C" int dpo_model_prove_verify(const int64_t *desc, u32 n_nodes, const in
         return 0;
     } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
+
+// ---- batch_commit + simple_batch_open (+ verify) ----
+extern "C" {
+// polys: n_polys arrays of len elements (same size, same field); returns root and, optionally, the flat proof of
+// simple_batch_open at `point` with evals = each polynomial's evaluation there (computed here)
+int dpo_pcs_simple_batch(u32 n_polys, const u64 *const *data, u64 len, int is_ext, u32 full_log, const u64 *point, const char *label,
+                         u64 *out_root, u64 *out_evals, u64 *out, u64 cap, u64 *out_len) {
+    try {
+        std::vector<FVec> polys; for (u32 i = 0; i < n_polys; i++) polys.push_back(mk_fvec(data[i], len, is_ext));
+        BatchCommitment c = basefold_batch_commit(polys, full_log);
+        for (int i = 0; i < 4; i++) out_root[i] = c.root().v[i];
+        if (!point) return 0;
+        std::vector<E> pt = mk_point(point, (u32)c.num_vars), evals;
+        for (auto &p : polys) { MLE m; m.is_ext = p.is_ext; m.num_vars = c.num_vars; m.base = p.b; m.ext = p.e; evals.push_back(mle_evaluate(m, pt)); }
+        for (u32 i = 0; i < n_polys; i++) { out_evals[2 * i] = evals[i].c0; out_evals[2 * i + 1] = evals[i].c1; }
+        Transcript t(label);
+        SimpleBatchProof p = basefold_simple_batch_open(full_log, c, pt, evals, t);
+        std::vector<u64> f = flatten_simple_batch_proof(p);
+        *out_len = f.size();
+        if (f.size() > cap) { g_err = "dpo_pcs_simple_batch: output buffer too small"; return 2; }
+        memcpy(out, f.data(), 8 * f.size());
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+int dpo_pcs_simple_batch_verify(const u64 *flat, u64 n, const u64 *root, u32 num_vars, int is_base, u32 n_polys, u32 full_log, const u64 *point, const u64 *evals, const char *label) {
+    try {
+        SimpleBatchProof pr = unflatten_simple_batch_proof(flat, n);
+        PureCommitment c; for (int i = 0; i < 4; i++) c.root.v[i] = root[i]; c.num_vars = num_vars; c.is_base = is_base != 0;
+        std::vector<E> ev; for (u32 i = 0; i < n_polys; i++) ev.push_back(E(evals[2 * i], evals[2 * i + 1]));
+        Transcript t(label);
+        basefold_simple_batch_verify(full_log, c, n_polys, mk_point(point, num_vars), ev, pr, t);
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}
+}

@@ -188,4 +188,80 @@ static inline BasefoldProof unflatten_proof(const u64 *p, size_t n) {
     return pr;
 }
 
+
+// Basefold::simple_batch_verify (basefold.rs:1100-1202) + simple_batch_verifier_query_phase (query_phase.rs:285-372) +
+// SimpleBatchSingleQueryResultWithMerklePath::check (:1468-1535) + authenticate_batch_leaves_root (merkle path of batch leaves)
+static inline SimpleBatchProof unflatten_simple_batch_proof(const u64 *p, size_t n) {
+    size_t k = 0;
+    auto u = [&]() -> u64 { if (k >= n) throw VerifyError("flat proof truncated"); return p[k++]; };
+    auto e = [&]() { u64 a = u(), b = u(); return E(a, b); };
+    auto d = [&]() { Digest x; for (int i = 0; i < 4; i++) x.v[i] = u(); return x; };
+    auto q = [&]() { QueryOpening o; o.index = u(); o.is_base = u() != 0; if (o.is_base) { o.p0 = E::from_base(u()); o.p1 = E::from_base(u()); } else { o.p0 = e(); o.p1 = e(); } size_t np = u(); for (size_t i = 0; i < np; i++) o.path.push_back(d()); return o; };
+    SimpleBatchProof pr;
+    size_t nm = u(); for (size_t i = 0; i < nm; i++) { std::vector<E> m; for (int j = 0; j < 3; j++) m.push_back(e()); pr.commit_phase.sumcheck_messages.push_back(m); }
+    size_t nr = u(); for (size_t i = 0; i < nr; i++) pr.commit_phase.roots.push_back(d());
+    size_t nf = u(); for (size_t i = 0; i < nf; i++) pr.commit_phase.final_message.push_back(e());
+    size_t nq = u();
+    for (size_t i = 0; i < nq; i++) {
+        SimpleBatchQueryResult r; r.x_index = u(); r.index = u(); r.is_base = u() != 0; size_t m = u();
+        for (size_t j = 0; j < m; j++) { if (r.is_base) { r.left.push_back(E::from_base(u())); r.right.push_back(E::from_base(u())); } else { r.left.push_back(e()); r.right.push_back(e()); } }
+        size_t np = u(); for (size_t j = 0; j < np; j++) r.path.push_back(d());
+        size_t no = u(); for (size_t j = 0; j < no; j++) r.oracle.push_back(q());
+        pr.queries.push_back(r);
+    }
+    if (k != n) throw VerifyError("flat proof has trailing words");
+    return pr;
+}
+static inline void basefold_simple_batch_verify(size_t full_log, const PureCommitment &comm, size_t num_polys, const std::vector<E> &point, const std::vector<E> &evals, const SimpleBatchProof &proof, Transcript &t) {
+    if (evals.size() != num_polys) throw VerifyError("number of evaluations != number of committed polynomials");
+    if (proof.trivial) { if (!(merkelize_batch(proof.trivial_evals).back()[0] == comm.root)) throw VerifyError("MerkleRootMismatch"); return; }
+    size_t num_vars = point.size();
+    if (num_vars != comm.num_vars || num_vars < RS_BASECODE_MSG_SIZE_LOG) throw VerifyError("point length != commitment num_vars");
+    size_t num_rounds = num_vars - RS_BASECODE_MSG_SIZE_LOG;
+    size_t bsl = ceil_log2(evals.size());
+    std::vector<E> tt; for (size_t i = 0; i < bsl; i++) tt.push_back(t.get_and_append_challenge("batch coeffs"));
+    std::vector<E> eq_xt = build_eq_x_r_vec(tt); eq_xt.resize(evals.size());
+    std::vector<E> fc; std::vector<size_t> queries;
+    replay_commit_phase(proof.commit_phase, num_rounds, (size_t)1 << (num_vars + RS_RATE_LOG), t, fc, queries);
+    std::vector<E> rev(fc.rbegin(), fc.rend());
+    E coeff = eq_xy_eval(std::vector<E>(point.end() - fc.size(), point.end()), rev);
+    std::vector<E> eq = build_eq_x_r_vec(std::vector<E>(point.begin(), point.end() - fc.size()));
+    for (auto &e : eq) e = e_mul(e, coeff);
+    std::vector<E> final_codeword = final_codeword_of(proof.commit_phase.final_message, full_log, true);
+    if (proof.queries.size() != queries.size()) throw VerifyError("wrong number of query results");
+    for (size_t qi = 0; qi < queries.size(); qi++) {
+        const SimpleBatchQueryResult &q = proof.queries[qi]; size_t index = queries[qi];
+        if (q.x_index != index || q.left.size() != num_polys || q.right.size() != num_polys || q.is_base != comm.is_base) throw VerifyError("query result does not match the commitment / transcript");
+        if (q.oracle.size() + 1 != num_rounds) throw VerifyError("wrong number of oracle openings");
+        for (size_t i = 0; i < q.oracle.size(); i++) check_merkle_path(q.oracle[i], proof.commit_phase.roots[i], "oracle");
+        {   // authenticate_batch_leaves_root: compress(hash(left values), hash(right values)) then up the path
+            std::vector<u64> a, b;
+            for (size_t k = 0; k < num_polys; k++) { if (q.is_base) { a.push_back(q.left[k].c0); b.push_back(q.right[k].c0); } else { a.push_back(q.left[k].c0); a.push_back(q.left[k].c1); b.push_back(q.right[k].c0); b.push_back(q.right[k].c1); } }
+            Digest cur = num_polys == 1 ? (q.is_base ? hash_or_noop(std::vector<u64>{a[0], b[0]}.data(), 2) : hash_or_noop(std::vector<u64>{a[0], a[1], b[0], b[1]}.data(), 4))
+                                        : compress(hash_or_noop(a.data(), a.size()), hash_or_noop(b.data(), b.size()));
+            size_t idx = q.index >> 1;
+            for (const Digest &sib : q.path) { cur = (idx & 1) ? compress(sib, cur) : compress(cur, sib); idx >>= 1; }
+            if (!(cur == comm.root)) throw VerifyError("merkle path does not authenticate: batch commitment");
+        }
+        E left = E::zero(), right = E::zero();                   // leaves.batch(batch_coeffs)
+        for (size_t k = 0; k < num_polys; k++) { left = e_add(left, e_mul(q.left[k], eq_xt[k])); right = e_add(right, e_mul(q.right[k], eq_xt[k])); }
+        size_t right_index = index | 1, left_index = right_index - 1;
+        if (q.index != left_index) throw VerifyError("commitment opening at the wrong index");
+        for (size_t i = 0; i < num_rounds; i++) {
+            u64 x0, w; folding_coeffs(full_log, num_vars + RS_RATE_LOG - i - 1, left_index >> 1, x0, w);
+            E res = interpolate2_weights(E::from_base(x0), left, E::from_base(f_neg(x0)), right, E::from_base(w), fc[i]);
+            size_t next_index = right_index >> 1; E next;
+            if (i + 1 < num_rounds) {
+                right_index = next_index | 1; left_index = right_index - 1;
+                if (q.oracle[i].index != left_index) throw VerifyError("oracle opening at the wrong index");
+                left = q.oracle[i].p0; right = q.oracle[i].p1;
+                next = (next_index & 1) == 0 ? left : right;
+            } else next = final_codeword[next_index];
+            if (!(res == next)) throw VerifyError("simple-batch fold consistency failed at round " + std::to_string(i));
+        }
+    }
+    E claimed = E::zero(); for (size_t k = 0; k < evals.size(); k++) claimed = e_add(claimed, e_mul(eq_xt[k], evals[k]));   // inner_product(batch_coeffs, evals)
+    final_sumcheck_checks(proof.commit_phase, fc, eq, claimed);
+}
+
 }  // namespace dpo

@@ -456,3 +456,24 @@ def model_prove_verify(desc, data, x, label=b"m2vec", tamper=0):
     d = i64(desc).reshape(-1, 9); w = i64(data); xi = i64(x)
     rc = lib().dpo_model_prove_verify(ptr(d), C.c_uint32(d.shape[0]), ptr(w), ptr(xi), C.c_uint64(xi.size), label, C.c_int(tamper))
     return None if rc == 0 else lib().dpo_last_error().decode()
+
+
+def pcs_simple_batch(polys, is_ext, full_log, point=None, label=b"m2vec", cap=1 << 24):
+    """batch_commit of same-size polynomials (+ simple_batch_open at `point`): returns (root, evals | None, flat | None)"""
+    arrs = [u64(p).reshape(-1) for p in polys]
+    n = len(arrs); ln = arrs[0].size // (2 if is_ext else 1)
+    data = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    root = np.zeros(4, dtype=np.uint64); evals = np.zeros((n, 2), dtype=np.uint64)
+    out = np.zeros(cap if point is not None else 1, dtype=np.uint64); ol = C.c_uint64()
+    pt = u64(point).reshape(-1) if point is not None else None
+    rc = lib().dpo_pcs_simple_batch(C.c_uint32(n), data, C.c_uint64(ln), C.c_int(int(is_ext)), C.c_uint32(full_log), ptr(pt) if pt is not None else None, label,
+                                    ptr(root), ptr(evals), ptr(out), C.c_uint64(cap), C.byref(ol))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return root, (evals if point is not None else None), (out[:ol.value].copy() if point is not None else None)
+
+
+def pcs_simple_batch_verify(flat, root, num_vars, is_base, n_polys, full_log, point, evals, label=b"m2vec"):
+    f = u64(flat); r = u64(root); pt = u64(point).reshape(-1); ev = u64(evals).reshape(-1)
+    rc = lib().dpo_pcs_simple_batch_verify(ptr(f), C.c_uint64(f.size), ptr(r), C.c_uint32(num_vars), C.c_int(int(is_base)), C.c_uint32(n_polys), C.c_uint32(full_log), ptr(pt), ptr(ev), label)
+    return None if rc == 0 else lib().dpo_last_error().decode()

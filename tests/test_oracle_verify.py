@@ -63,3 +63,20 @@ def test_cnn_proof_is_accepted_by_the_restated_verifier(which):
         assert O.model_prove_verify(desc, data, x, tamper=1) is not None
         assert "padded_fft" in O.model_prove_verify(desc, data, x, tamper=2)
         assert "pooling" in O.model_prove_verify(desc, data, x, tamper=3)
+
+
+@pytest.mark.parametrize("n_polys,nv,full_log,ext", [(3, 9, 10, False), (5, 10, 10, False), (2, 9, 9, True), (1, 9, 9, False), (4, 8, 12, False)])
+def test_batch_commit_simple_batch_open_verifies(n_polys, nv, full_log, ext):
+    """batch_commit -> simple_batch_open -> simple_batch_verify accepts (the reference's batch_commit_open_verify,
+    mpcs/src/basefold.rs:1300-1331); one polynomial under batch_commit has the plain commitment's root"""
+    polys = [O.splitmix_e(900 + i, 1 << nv) if ext else O.splitmix_f(900 + i, 1 << nv) for i in range(n_polys)]
+    pt = O.splitmix_e(950, nv)
+    root, evals, flat = O.pcs_simple_batch(polys, ext, full_log, pt)
+    assert all((evals[i] == O.evaluate(polys[i], ext, pt)).all() for i in range(n_polys))
+    if n_polys == 1:
+        assert (root == O.pcs_commit(polys[0], ext, full_log, want_codeword=False)[0]).all()
+    assert O.pcs_simple_batch_verify(flat, root, nv, not ext, n_polys, full_log, pt, evals) is None
+    bad = evals.copy(); bad[0, 0] ^= np.uint64(1)
+    assert O.pcs_simple_batch_verify(flat, root, nv, not ext, n_polys, full_log, pt, bad) is not None
+    tam = flat.copy(); tam[flat.size // 2] ^= np.uint64(1)
+    assert O.pcs_simple_batch_verify(tam, root, nv, not ext, n_polys, full_log, pt, evals) is not None
