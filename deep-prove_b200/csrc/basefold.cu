@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256) k_merkle_x8(const void *src, u64 n_out, u
 // __syncthreads() in between, so a 2^11-leaf witness commitment costs one launch instead of ten
 struct LvlOff { u64 off[36]; };
 template <bool EXT>
-__global__ void __launch_bounds__(256) k_merkle_tail(const void *leaves, u64 n, u32 lg, u32 from_level, u64 *levels, LvlOff lo) {
+__global__ void __launch_bounds__(256) k_merkle_tail(const void *leaves, u64 n, u32 lg, u32 from_level, u64 *levels, LvlOff lo, const u64 *lvl0) {
     for (u32 l = from_level; l < lg; l++) {
         u64 nl = n >> (l + 1);
         u64 *out = levels + 4 * lo.off[l];
@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(256) k_merkle_tail(const void *leaves, u64 n, 
             bool live = i < nl;
             u64 xw = 0, yw = 0;
             if (live && lane8 < 4) {
-                if (l == 1) { xw = leaf_pair_word<EXT>(leaves, 2 * i, lane8); yw = leaf_pair_word<EXT>(leaves, 2 * i + 1, lane8); }
-                else { const u64 *in = levels + 4 * lo.off[l - 1] + 8 * i; xw = in[lane8]; yw = in[4 + lane8]; }   // plain loads: written earlier in this launch
+                if (l == 1 && !lvl0) { xw = leaf_pair_word<EXT>(leaves, 2 * i, lane8); yw = leaf_pair_word<EXT>(leaves, 2 * i + 1, lane8); }
+                else { const u64 *in = (l == 1 ? lvl0 : levels + 4 * lo.off[l - 1]) + 8 * i; xw = in[lane8]; yw = in[4 + lane8]; }   // plain loads: written earlier in this launch
             }
             u64 s = p2x8_compress(xw, yw, lane8);
             if (live && lane8 < 4) out[4 * i + (3 - lane8)] = s;
@@ -281,6 +281,23 @@ __global__ void __launch_bounds__(256) k_merkle_multi(const void *src, u32 first
     }
     (void)nl_first;
 }
+
+// batch_commit leaf level (merkle_tree.rs:286-312, util/hash.rs:30-41): digest_i = compress(hash(values of all m polynomials at
+// index 2i), hash(... at 2i+1)), hash = hash_or_noop over the base-field limbs
+struct BatchPtrs { const void *p[64]; };
+template <bool EXT>
+__global__ void k_merkle_batch_l0(BatchPtrs bp, u32 m, u64 n_out, u64 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    u64 x[4], y[4], o[4];
+    const int n = EXT ? 2 * (int)m : (int)m;
+    auto ga = [&](int k) -> u64 { return EXT ? ((const u64 *)bp.p[k >> 1])[2 * (2 * i) + (k & 1)] : ((const u64 *)bp.p[k])[2 * i]; };
+    auto gb = [&](int k) -> u64 { return EXT ? ((const u64 *)bp.p[k >> 1])[2 * (2 * i + 1) + (k & 1)] : ((const u64 *)bp.p[k])[2 * i + 1]; };
+    p2_hash_or_noop(ga, n, x); p2_hash_or_noop(gb, n, y);
+    p2_compress(x, y, o);
+    *reinterpret_cast<ulonglong2 *>(out + 4 * i) = make_ulonglong2(o[0], o[1]);
+    *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(o[2], o[3]);
+}
 template <bool EXT> __global__ void k_leafpair_root(const void *leaves, u64 *out) { u64 d[4]; leaf_pair_digest<EXT>(leaves, 0, d); for (int i = 0; i < 4; i++) out[i] = d[i]; }
 
 // A Merkle tree over `n` leaves living in HBM: levels >= 1 packed back to back.
@@ -290,16 +307,21 @@ struct DevTree {
     std::vector<u64> lvl_off;         // lvl_off[l] for l = 1..lg-1
     u64 *root_dev = nullptr;          // 4 limbs
     bool own_leaves = false;
+    const u64 *level0 = nullptr;      // batch trees only: stored digests of the leaf pairs (single-polynomial trees recompute them)
+    bool own_levels = true;           // false for the per-polynomial views of a batch commitment
 };
-static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
+// `lvl0` != NULL: a batch tree -- the digests of the leaf pairs are given (k_merkle_batch_l0) instead of being packed from `leaves`
+static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n, const u64 *lvl0 = nullptr) {
     DpCtx &c = dp_ctx();
+    t.level0 = lvl0;
     t.leaves = leaves; t.ext = ext; t.n = n; t.lg = 0; while ((1ULL << t.lg) < n) t.lg++;
     DP_CHECK(t.lg >= 1, DP_ERR_INVALID, "merkle tree needs at least two leaves");
     t.lvl_off.assign(t.lg + 1, 0);
     u64 total = 0;
     for (u32 l = 1; l < t.lg; l++) { t.lvl_off[l] = total; total += n >> (l + 1); }
     if (int e = dp_dev_alloc((void **)&t.levels, sizeof(u64) * 4 * (total + 1))) return e;
-    if (t.lg == 1) {
+    if (t.lg == 1 && lvl0) { t.root_dev = const_cast<u64 *>(lvl0); }
+    else if (t.lg == 1) {
         if (ext) k_leafpair_root<true><<<1, 1, 0, c.stream>>>(leaves, t.levels); else k_leafpair_root<false><<<1, 1, 0, c.stream>>>(leaves, t.levels);
         DP_LAUNCHED(); t.root_dev = t.levels;
     } else {
@@ -314,8 +336,8 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
                 u32 nlev = std::min<u32>(7, a - 5);
                 DpProfScope prof("k_merkle_multi(poseidon2 compress)", (l == 1 ? nl * (ext ? 64 : 32) : nl * 64) + 2 * nl * 32);
                 unsigned g = (unsigned)(nl >> (nlev - 1));
-                const void *src = l == 1 ? leaves : (const void *)(t.levels + 4 * t.lvl_off[l - 1]);
-                if (l == 1) { if (ext) k_merkle_multi<true, true><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all); else k_merkle_multi<false, true><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all); }
+                const void *src = l == 1 ? (lvl0 ? (const void *)lvl0 : leaves) : (const void *)(t.levels + 4 * t.lvl_off[l - 1]);
+                if (l == 1 && !lvl0) { if (ext) k_merkle_multi<true, true><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all); else k_merkle_multi<false, true><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all); }
                 else k_merkle_multi<false, false><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all);
                 DP_LAUNCHED();
                 l += nlev - 1;
@@ -324,27 +346,27 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
             if (nl <= 32768) {   // too few hashes for one thread each: 8 lanes per hash
                 DpProfScope prof("k_merkle_x8(poseidon2 compress)", l == 1 ? nl * (ext ? 64 : 32) + nl * 32 : nl * 96);
                 int g = dp_grid_for(nl * 8, 256, 8);
-                if (l == 1) { if (ext) k_merkle_x8<true, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); else k_merkle_x8<false, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); }
-                else k_merkle_x8<false, false><<<g, 256, 0, c.stream>>>(t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
+                if (l == 1 && !lvl0) { if (ext) k_merkle_x8<true, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); else k_merkle_x8<false, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); }
+                else k_merkle_x8<false, false><<<g, 256, 0, c.stream>>>(l == 1 ? lvl0 : t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
                 DP_LAUNCHED();
                 continue;
             }
             DpProfScope prof("k_merkle(poseidon2 compress)", l == 1 ? nl * (ext ? 64 : 32) + nl * 32 : nl * 96);
             const unsigned mgrid = (unsigned)std::min<u64>((nl + 127) / 128, 1u << 22);
-            if (l == 1) {
+            if (l == 1 && !lvl0) {
                 // one hash per thread, many SHORT blocks (no persistent grid-stride blocks): with 16 proofs in flight the block
                 // scheduler can interleave other streams' latency-critical single-block kernels every few microseconds
                 if (ext) k_merkle_l1<true><<<mgrid, 128, 0, c.stream>>>(leaves, nl, t.levels);
                 else k_merkle_l1<false><<<mgrid, 128, 0, c.stream>>>(leaves, nl, t.levels);
-            } else k_merkle_up<<<mgrid, 128, 0, c.stream>>>(t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
+            } else k_merkle_up<<<mgrid, 128, 0, c.stream>>>(l == 1 ? lvl0 : t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
             DP_LAUNCHED();
         }
         if (l < t.lg) {
             LvlOff lo; memset(&lo, 0, sizeof lo);
             for (u32 k = 1; k < t.lg && k < 36; k++) lo.off[k] = t.lvl_off[k];
             DpProfScope prof("k_merkle_tail(poseidon2 compress)", (n >> l) * 48);
-            if (ext) k_merkle_tail<true><<<1, 256, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo);
-            else k_merkle_tail<false><<<1, 256, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo);
+            if (ext) k_merkle_tail<true><<<1, 256, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo, lvl0);
+            else k_merkle_tail<false><<<1, 256, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo, lvl0);
             DP_LAUNCHED();
         }
         t.root_dev = t.levels + 4 * t.lvl_off[t.lg - 1];
@@ -352,7 +374,7 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n) {
     DP_CUDA(cudaGetLastError());
     return DP_OK;
 }
-static void tree_free(DevTree &t) { dp_dev_free(t.levels); t.levels = nullptr; if (t.own_leaves) dp_dev_free(const_cast<void *>(t.leaves)); t.leaves = nullptr; }
+static void tree_free(DevTree &t) { if (t.own_levels) dp_dev_free(t.levels); t.levels = nullptr; if (t.own_leaves) dp_dev_free(const_cast<void *>(t.leaves)); t.leaves = nullptr; }
 
 // ---- K10 FRI fold (commit_phase.rs:511-526, rs.rs:377-410, arithmetic.rs:120-132) ----
 // out[i] = y0 + (r - x0) * (y1 - y0) * w,  x0 = w_{2^(level+1)}^{rev(i, level)} * gamma_lvl,  w = -1/(2 x0)
@@ -385,7 +407,7 @@ __global__ void k_lift(const u64 *__restrict__ src, gle *__restrict__ out, u64 n
 }
 
 // ---- K13 query gather: per (query, tree): [p0.c0 p0.c1 p1.c0 p1.c1][path digests x (lg-1)] ----
-struct QTree { const void *leaves; const u64 *levels; u64 off[34]; u32 lg; u32 ext; u32 shift; u32 pad; };
+struct QTree { const void *leaves; const u64 *levels; const u64 *level0; u64 off[34]; u32 lg; u32 ext; u32 shift; u32 pad; };
 __global__ void k_query_gather(const QTree *__restrict__ trees, u32 n_trees, const u64 *__restrict__ xs, const u64 *__restrict__ out_off, u64 per_query, u64 *__restrict__ out) {
     u32 q = blockIdx.x, ti = blockIdx.y;
     QTree t = trees[ti];
@@ -400,7 +422,8 @@ __global__ void k_query_gather(const QTree *__restrict__ trees, u32 n_trees, con
         if (k + 1 < t.lg) {   // path entry k = inner[k][(p0 >> (k+1)) ^ 1]
             u64 node = (p0 >> (k + 1)) ^ 1;
             u64 *d = o + 4 + 4 * k;
-            if (k == 0) {
+            if (k == 0 && t.level0) { const u64 *sd = t.level0 + 4 * node; d[0] = sd[0]; d[1] = sd[1]; d[2] = sd[2]; d[3] = sd[3]; }
+            else if (k == 0) {
                 if (t.ext) { const gle *l = (const gle *)t.leaves + 2 * node; gle a = ld_e(l), b = ld_e(l + 1); d[0] = a.c0; d[1] = a.c1; d[2] = b.c0; d[3] = b.c1; }
                 else { const u64 *l = (const u64 *)t.leaves + 2 * node; d[0] = l[0]; d[1] = l[1]; d[2] = 0; d[3] = 0; }
             } else {
@@ -419,6 +442,8 @@ struct dp_pcs_comm {
     u64 cw_len = 0;
     DevTree tree;
     u64 root[4] = {0, 0, 0, 0};
+    std::vector<dp_pcs_comm *> parts;   // batch_commit: one (encode-only) commitment per polynomial; their trees are views of `tree`
+    u64 *level0 = nullptr;              // batch_commit: digests of the leaf pairs
 };
 
 struct OpenRound { gle *oracle = nullptr; u64 len = 0; DevTree tree; };
@@ -459,13 +484,13 @@ int dp_poseidon2_init(const uint64_t *ext_rc /*2x4x8*/, const uint64_t *int_rc /
 }
 
 // enqueue every kernel of one commitment on the context's CURRENT stream; the root lands in `root_pinned`
-static int commit_enqueue(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out, u64 *root_pinned) {
+static int commit_enqueue(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out, u64 *root_pinned, bool with_tree = true) {
     u32 nv = poly->num_vars();
     DP_CHECK(nv <= full_log, DP_ERR_INVALID, "PolynomialTooLarge");                 // basefold.rs:97-99
     DP_CHECK(nv >= 1, DP_ERR_INVALID, "dp_pcs_commit: need at least one variable");
     if (int e = bf_prepare()) return e;
     DpCtx &c = dp_ctx();
-    if (!root_pinned) return dp_fail(DP_ERR_INVALID, "commit_enqueue: no root buffer");
+    if (!root_pinned && with_tree) return dp_fail(DP_ERR_INVALID, "commit_enqueue: no root buffer");
     dp_pcs_comm *cm = new dp_pcs_comm();
     cm->num_vars = nv; cm->full_log = full_log; cm->is_base = !poly->is_ext;
     size_t esz = poly->is_ext ? 16 : 8;
@@ -517,8 +542,10 @@ static int commit_enqueue(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **o
         dp_dev_free(coef); dp_dev_free(stab);
         }
     }
-    if (int e = tree_build(cm->tree, cm->codeword, poly->is_ext, cm->cw_len)) return e;   // K9
-    DP_CUDA(cudaMemcpyAsync(root_pinned, cm->tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
+    if (with_tree) {
+        if (int e = tree_build(cm->tree, cm->codeword, poly->is_ext, cm->cw_len)) return e;   // K9
+        DP_CUDA(cudaMemcpyAsync(root_pinned, cm->tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
+    }
     *out = cm;
     return DP_OK;
 }
@@ -533,6 +560,58 @@ int dp_pcs_commit(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out) {
     if (rc == DP_OK) { DP_CUDA(cudaStreamSynchronize(dp_ctx().stream)); memcpy((*out)->root, pin, 32); }
     dp_pinned_free(pin);
     return rc;
+}
+
+
+// Basefold::batch_commit (basefold.rs:356-452): n polynomials of the same size and field under ONE Merkle tree whose leaves
+// are the batches of values (merkle_tree.rs:68-74,286-312).  Encoding is the per-polynomial pipeline; the leaf level hashes
+// all polynomials' values at an index pair; the levels above are the ordinary tree.
+int dp_pcs_batch_commit(const dp_mle *const *polys, uint32_t n, uint32_t full_log, dp_pcs_comm **out) {
+    DP_HOST_TIMED("dp_pcs_batch_commit");
+    DP_REQUIRE_CTX();
+    DP_CHECK(polys && out && n >= 1, DP_ERR_INVALID, "cannot batch commit to zero polynomials");      // basefold.rs:367-371
+    DP_CHECK(n <= 64, DP_ERR_UNSUPPORTED, "dp_pcs_batch_commit: at most 64 polynomials per batch");
+    for (u32 i = 0; i < n; i++) DP_CHECK(polys[i] && polys[i]->len == polys[0]->len && polys[i]->is_ext == polys[0]->is_ext, DP_ERR_INVALID,
+                                         "cannot batch commit to polynomials with different number of variables");   // :379-386
+    if (int e = bf_prepare()) return e;
+    DpCtx &c = dp_ctx();
+    dp_pcs_comm *b = new dp_pcs_comm();
+    b->num_vars = polys[0]->num_vars(); b->full_log = full_log; b->is_base = !polys[0]->is_ext;
+    BatchPtrs bp; memset(&bp, 0, sizeof bp);
+    for (u32 i = 0; i < n; i++) {
+        dp_pcs_comm *part = nullptr;
+        if (int e = commit_enqueue(polys[i], full_log, &part, nullptr, false)) { dp_pcs_comm_free(b); return e; }
+        b->parts.push_back(part); bp.p[i] = part->codeword;
+    }
+    b->trivial = b->parts[0]->trivial; b->cw_len = b->parts[0]->cw_len;
+    u64 N = b->cw_len, n0 = N >> 1;
+    if (int e = dp_dev_alloc((void **)&b->level0, 32 * n0)) { dp_pcs_comm_free(b); return e; }
+    {
+        DpProfScope prof("k_merkle_batch_l0(poseidon2 sponge + compress)", (u64)n * N * (b->is_base ? 8 : 16) + 32 * n0);
+        unsigned g = (unsigned)((n0 + 127) / 128);
+        if (b->is_base) k_merkle_batch_l0<false><<<g, 128, 0, c.stream>>>(bp, n, n0, b->level0); else k_merkle_batch_l0<true><<<g, 128, 0, c.stream>>>(bp, n, n0, b->level0);
+        DP_LAUNCHED();
+    }
+    if (int e = tree_build(b->tree, b->parts[0]->codeword, !b->is_base, N, b->level0)) { dp_pcs_comm_free(b); return e; }
+    for (auto *part : b->parts) {   // per-polynomial views: own leaves, the batch tree's digests
+        DevTree &t = part->tree; t = b->tree; t.leaves = part->codeword; t.own_levels = false; t.own_leaves = false;
+    }
+    u64 *pin = nullptr;
+    if (int e = dp_pinned_alloc((void **)&pin, 32)) { dp_pcs_comm_free(b); return e; }
+    DP_CUDA(cudaMemcpyAsync(pin, b->tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
+    DP_CUDA(cudaStreamSynchronize(c.stream));
+    memcpy(b->root, pin, 32); for (auto *part : b->parts) memcpy(part->root, pin, 32);
+    dp_pinned_free(pin);
+    *out = b;
+    return DP_OK;
+}
+// number of polynomials under a commitment (1 for dp_pcs_commit) and the i-th per-polynomial view of a batch commitment
+// (borrowed: valid until the batch commitment is freed) -- the handles dp_pcs_open_begin / dp_pcs_open_query take
+uint32_t dp_pcs_comm_num_polys(const dp_pcs_comm *cm) { return cm ? (cm->parts.empty() ? 1u : (uint32_t)cm->parts.size()) : 0u; }
+int dp_pcs_comm_part(const dp_pcs_comm *cm, uint32_t i, const dp_pcs_comm **out) {
+    DP_CHECK(cm && out && i < cm->parts.size(), DP_ERR_INVALID, "dp_pcs_comm_part: not a batch commitment or index out of range");
+    *out = cm->parts[i];
+    return DP_OK;
 }
 
 // Independent commitments (the reference commits witness columns from rayon workers: activation.rs:293,
@@ -604,7 +683,8 @@ int dp_pcs_comm_bh_evals(const dp_pcs_comm *cm, dp_mle **view) {
 int dp_pcs_comm_free(dp_pcs_comm *cm) {
     if (!cm) return DP_OK;
     std::lock_guard<std::recursive_mutex> lk(dp_ctx().mu);
-    if (dp_ctx().ready) { tree_free(cm->tree); if (!cm->trivial) dp_dev_free(cm->codeword); dp_dev_free(cm->bh_evals); }
+    if (dp_ctx().ready) { tree_free(cm->tree); if (!cm->trivial) dp_dev_free(cm->codeword); dp_dev_free(cm->bh_evals); dp_dev_free(cm->level0); }
+    for (auto *p : cm->parts) dp_pcs_comm_free(p);
     delete cm;
     return DP_OK;
 }
@@ -779,7 +859,7 @@ int dp_pcs_open_query(dp_pcs_open *o, const uint64_t *x_indices, uint32_t n, uin
     u32 lgN = o->num_vars + BF_RATE_LOG; u64 w = 0; u32 k = 0;
     auto fill = [&](const DevTree &t, u32 shift) {
         QTree &q = qt[k]; memset(&q, 0, sizeof q);
-        q.leaves = t.leaves; q.levels = t.levels; q.lg = t.lg; q.ext = t.ext; q.shift = shift;
+        q.leaves = t.leaves; q.levels = t.levels; q.level0 = t.level0; q.lg = t.lg; q.ext = t.ext; q.shift = shift;
         for (u32 l = 1; l < t.lg && l < 34; l++) q.off[l] = t.lvl_off[l];
         off[k] = w; w += 4 + 4 * (u64)(t.lg - 1); k++;
     };

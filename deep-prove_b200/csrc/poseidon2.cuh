@@ -137,3 +137,18 @@ __device__ __forceinline__ void p2_compress(const u64 x[4], const u64 y[4], u64 
     p2_permute(s);
     out[0] = gl_canon_weak(s[3]); out[1] = gl_canon_weak(s[2]); out[2] = gl_canon_weak(s[1]); out[3] = gl_canon_weak(s[0]);
 }
+
+// PoseidonHash::hash_or_noop (poseidon/src/poseidon_hash.rs:22-28) for n elements fetched through `get(i)`:
+// n <= 4: zero-padded copy, no permutation; else the duplex sponge (rate 4, overwrite-mode absorb, a trailing partial
+// block overwrites only its own words) and the digest is popped from the end of the rate: [s3, s2, s1, s0].
+template <class F>
+__device__ __forceinline__ void p2_hash_or_noop(F get, int n, u64 out[4]) {
+    if (n <= 4) { for (int i = 0; i < 4; i++) out[i] = i < n ? get(i) : 0ULL; return; }
+    u64 s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i + k < n) s[k] = get(i + k);
+        p2_permute(s);
+    }
+    out[0] = gl_canon_weak(s[3]); out[1] = gl_canon_weak(s[2]); out[2] = gl_canon_weak(s[1]); out[3] = gl_canon_weak(s[0]);
+}

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "dp_mle_upload", "dp_mle_wrap_device", "dp_mle_clone", "dp_mle_download", "dp_mle_info", "dp_mle_device_ptr",
     "dp_mle_free", "dp_mle_fix_high", "dp_mle_fix_high_new", "dp_mle_fix_low", "dp_mle_evaluate", "dp_mle_evaluate_many", "dp_eq_build",
     "dp_sc_create", "dp_sc_round", "dp_sc_finish", "dp_sc_destroy", "dp_sc_last_round_bytes", "dp_sc_current_mle", "dp_sc_set_resident_tail",
-    "dp_poseidon2_init", "dp_pcs_commit", "dp_pcs_commit_many", "dp_pcs_comm_info", "dp_pcs_comm_codeword", "dp_pcs_comm_bh_evals", "dp_pcs_comm_free",
+    "dp_poseidon2_init", "dp_pcs_commit", "dp_pcs_commit_many", "dp_pcs_batch_commit", "dp_pcs_comm_num_polys", "dp_pcs_comm_part", "dp_pcs_comm_info", "dp_pcs_comm_codeword", "dp_pcs_comm_bh_evals", "dp_pcs_comm_free",
     "dp_pcs_open_begin", "dp_pcs_open_round", "dp_pcs_open_final_message", "dp_pcs_open_query_words", "dp_pcs_open_query",
     "dp_pcs_open_free",
     "dp_logup_build", "dp_logup_num_vars", "dp_logup_outputs", "dp_logup_layer_mles", "dp_logup_free", "dp_mle_linear_combination",
@@ -371,6 +371,23 @@ def pcs_batch_open(mles, full_log, points, label=b"m2vec", cap=1 << 25):
     n = C.c_uint64()
     hcheck(host().dph_pcs_batch_open(hs, len(mles), full_log, _ptr(p), label, _ptr(out), cap, C.byref(n)))
     return out[: n.value].copy()
+
+
+def pcs_simple_batch(mles, full_log, point=None, evals=None, label=b"m2vec", cap=1 << 24):
+    """Basefold::batch_commit of same-size device MLEs (+ simple_batch_open at `point` with the claimed `evals`): (root, flat | None)"""
+    _pcs_setup()
+    H = host()
+    H.dph_pcs_simple_batch.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    hs = (C.c_void_p * len(mles))(*[m.h for m in mles])
+    root = np.zeros(4, dtype=np.uint64)
+    n = C.c_uint64()
+    if point is None:
+        hcheck(H.dph_pcs_simple_batch(hs, len(mles), full_log, None, 0, None, label, root.ctypes.data, None, 0, C.byref(n)))
+        return root, None
+    pt = _u64(point).reshape(-1); ev = _u64(evals).reshape(-1)
+    out = np.zeros(cap, dtype=np.uint64)
+    hcheck(H.dph_pcs_simple_batch(hs, len(mles), full_log, pt.ctypes.data, pt.size // 2, ev.ctypes.data, label, root.ctypes.data, out.ctypes.data, cap, C.byref(n)))
+    return root, out[: n.value].copy()
 
 
 # ---- zkml MLP prover (host mirror of zkml::{Context, Prover}) -----------------------------------------

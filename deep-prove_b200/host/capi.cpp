@@ -339,3 +339,25 @@ extern "C" int dph_model_context_new(const int64_t *desc, uint32_t n_nodes, cons
     return 0;
     DPH_CATCH
 }
+
+// batch_commit (+ simple_batch_open at `point` when given): polys are caller-owned device MLEs of equal size / field
+extern "C" int dph_pcs_simple_batch(dp_mle *const *polys, uint32_t n, uint32_t full_log, const uint64_t *point, uint32_t nv, const uint64_t *evals, const char *label,
+                                    uint64_t *out_root, uint64_t *out, uint64_t cap, uint64_t *out_len) {
+    DPH_TRY
+    BasefoldProverParams pp; pp.full_message_size_log = full_log;
+    std::vector<DeviceMle> ps;
+    for (uint32_t i = 0; i < n; i++) { uint64_t len; int ext; check(dp_mle_info(polys[i], &len, &ext, nullptr)); ps.push_back(DeviceMle::wrap_device(dp_mle_device_ptr(polys[i]), len, ext)); }
+    BasefoldCommitmentWithWitness comm = Basefold::batch_commit(pp, ps);
+    memcpy(out_root, comm.root.v, 32);
+    if (!point) return 0;
+    ExtVec pt, ev; for (uint32_t i = 0; i < nv; i++) pt.push_back(Ext(point[2 * i], point[2 * i + 1]));
+    for (uint32_t i = 0; i < n; i++) ev.push_back(Ext(evals[2 * i], evals[2 * i + 1]));
+    BasicTranscript t(label);
+    SimpleBatchProof sp = Basefold::simple_batch_open(pp, comm, pt, ev, t);
+    std::vector<uint64_t> f = sp.flatten();
+    *out_len = f.size();
+    if (f.size() > cap) throw Error(DP_ERR_INVALID, "dph_pcs_simple_batch: output buffer too small");
+    memcpy(out, f.data(), 8 * f.size());
+    return 0;
+    DPH_CATCH
+}

@@ -25,6 +25,7 @@ class BasefoldCommitmentWithWitness {
     }
     dp_pcs_comm *handle() const { return h_.get(); }
     uint32_t num_vars = 0; bool is_base = true, trivial = false; Digest root;
+    uint32_t num_polys() const { return dp_pcs_comm_num_polys(h_.get()); }
     u64 codeword_size() const { return trivial ? (1ULL << num_vars) : (1ULL << (num_vars + RS_RATE_LOG)); }
   private:
     std::shared_ptr<dp_pcs_comm> h_;
@@ -61,6 +62,30 @@ struct BasefoldProof {
         for (auto &q : single_queries) { o.push_back(q.x_index); fq(q.commitment_query); o.push_back(q.oracle_query.size()); for (auto &x : q.oracle_query) fq(x); }
         o.push_back(batched_queries.size());
         for (auto &q : batched_queries) { o.push_back(q.x_index); o.push_back(q.oracle_query.size()); for (auto &x : q.oracle_query) fq(x); o.push_back(q.commitments_query.size()); for (auto &x : q.commitments_query) fq(x); }
+        return o;
+    }
+};
+
+// ProofQueriesResultWithMerklePath::SimpleBatched (query_phase.rs:1420-1560): every committed polynomial's leaf pair + ONE path
+struct SimpleBatchQueryResult { u64 x_index = 0, index = 0; bool is_base = false; ExtVec left, right; std::vector<Digest> merkle_path; std::vector<CodewordQuery> oracle_query; };
+struct SimpleBatchProof {
+    std::vector<ExtVec> sumcheck_messages; std::vector<Digest> roots; ExtVec final_message; std::vector<SimpleBatchQueryResult> queries;
+    bool is_trivial = false;
+    std::vector<u64> flatten() const {   // same image as the CPU checker's flatten_simple_batch_proof
+        std::vector<u64> o;
+        auto fe = [&](const Ext &e) { o.push_back(e.c0); o.push_back(e.c1); };
+        auto fd = [&](const Digest &d) { for (int i = 0; i < 4; i++) o.push_back(d.v[i]); };
+        o.push_back(sumcheck_messages.size()); for (auto &m : sumcheck_messages) for (auto &e : m) fe(e);
+        o.push_back(roots.size()); for (auto &d : roots) fd(d);
+        o.push_back(final_message.size()); for (auto &e : final_message) fe(e);
+        o.push_back(queries.size());
+        for (auto &q : queries) {
+            o.push_back(q.x_index); o.push_back(q.index); o.push_back(q.is_base ? 1 : 0); o.push_back(q.left.size());
+            for (size_t k = 0; k < q.left.size(); k++) { if (q.is_base) { o.push_back(q.left[k].c0); o.push_back(q.right[k].c0); } else { fe(q.left[k]); fe(q.right[k]); } }
+            o.push_back(q.merkle_path.size()); for (auto &d : q.merkle_path) fd(d);
+            o.push_back(q.oracle_query.size());
+            for (auto &x : q.oracle_query) { o.push_back(x.index); o.push_back(x.is_base ? 1 : 0); if (x.is_base) { o.push_back(x.p0.c0); o.push_back(x.p1.c0); } else { fe(x.p0); fe(x.p1); } o.push_back(x.merkle_path.size()); for (auto &d : x.merkle_path) fd(d); }
+        }
         return o;
     }
 };
@@ -172,6 +197,39 @@ class Basefold {
         for (auto &c : comms) { cs.push_back(c.handle()); cw.push_back(c.codeword_size()); isb.push_back(c.is_base); }
         run_commit_phase(cs.data(), &coeffs, (uint32_t)cs.size(), challenges, num_vars, transcript, pr, /*batch=*/true, cw, isb);
         return pr;
+    }
+
+    // Basefold::batch_commit (basefold.rs:356-452)
+    static BasefoldCommitmentWithWitness batch_commit(const BasefoldProverParams &pp, const std::vector<DeviceMle> &polys) {
+        std::vector<dp_mle *> hs; for (auto &p : polys) hs.push_back(p.handle());
+        dp_pcs_comm *h; check(dp_pcs_batch_commit(hs.data(), (uint32_t)hs.size(), pp.full_message_size_log, &h));
+        return BasefoldCommitmentWithWitness(h);
+    }
+    // Basefold::simple_batch_open (basefold.rs:777-861): all polynomials of one batch commitment at ONE point.  The commit phase is
+    // the batch commit phase over the per-polynomial views with coefficients eq(t) (simple_batch_commit_phase, commit_phase.rs:363-510)
+    template <class T>
+    static SimpleBatchProof simple_batch_open(const BasefoldProverParams &pp, const BasefoldCommitmentWithWitness &comm, const ExtVec &point, const ExtVec &evals, T &transcript) {
+        (void)pp;
+        SimpleBatchProof sp;
+        if (comm.trivial) { sp.is_trivial = true; return sp; }                       // Proof::trivial(bh_evals): the caller holds the evaluations
+        uint32_t n = comm.num_polys();
+        if (n != evals.size() || point.size() != comm.num_vars) throw Error(DP_ERR_INVALID, "simple_batch_open: one evaluation per committed polynomial at a num_vars-long point");
+        size_t bsl = 0; while ((1ULL << bsl) < evals.size()) bsl++;
+        ExtVec t; for (size_t i = 0; i < bsl; i++) t.push_back(transcript.get_and_append_challenge("batch coeffs"));
+        ExtVec eq_xt = build_eq_x_r_vec_host(t); eq_xt.resize(evals.size());
+        std::vector<dp_pcs_comm *> cs; std::vector<u64> cw; std::vector<bool> isb;
+        for (uint32_t i = 0; i < n; i++) { const dp_pcs_comm *part; check(dp_pcs_comm_part(comm.handle(), i, &part)); cs.push_back(const_cast<dp_pcs_comm *>(part)); cw.push_back(comm.codeword_size()); isb.push_back(comm.is_base); }
+        BasefoldProof pr;
+        run_commit_phase(cs.data(), &eq_xt, n, point, comm.num_vars, transcript, pr, /*batch=*/true, cw, isb);
+        sp.sumcheck_messages = pr.sumcheck_messages; sp.roots = pr.roots; sp.final_message = pr.final_message;
+        for (auto &b : pr.batched_queries) {
+            SimpleBatchQueryResult q; q.x_index = b.x_index; q.index = b.commitments_query[0].index; q.is_base = comm.is_base;
+            for (auto &c : b.commitments_query) { q.left.push_back(c.p0); q.right.push_back(c.p1); }
+            q.merkle_path = b.commitments_query[0].merkle_path;                        // one tree: every view authenticates with the same path
+            q.oracle_query = b.oracle_query;
+            sp.queries.push_back(q);
+        }
+        return sp;
     }
 
   private:

@@ -163,6 +163,14 @@ int dp_pcs_commit(const dp_mle *poly, uint32_t full_message_size_log, dp_pcs_com
 /* n independent commitments issued concurrently (what the reference does from rayon workers:
  * activation.rs:293, requant.rs:298/315, lookup/context.rs:677); same results as n dp_pcs_commit calls. */
 int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_message_size_log, dp_pcs_comm **out);
+/* Basefold::batch_commit (mpcs/src/basefold.rs:356-452): n polynomials of equal size and field type under ONE Merkle tree with
+ * batch leaves (merkle_tree.rs:68-74,286-312; hash_two_leaves_batch_*, util/hash.rs:30-41).  dp_pcs_comm_info gives the root.
+ * dp_pcs_comm_part(i) is a borrowed per-polynomial view (own codeword, the batch tree's digests): simple_batch_open
+ * (basefold.rs:777-861) is dp_pcs_open_begin over the n views with coeffs = eq(t)[0..n] followed by the usual rounds, and
+ * dp_pcs_open_query returns for view i its leaf pair and the (shared) batch path -- see host/mpcs.hpp::simple_batch_open. */
+int dp_pcs_batch_commit(const dp_mle *const *polys, uint32_t n, uint32_t full_log, dp_pcs_comm **out);
+uint32_t dp_pcs_comm_num_polys(const dp_pcs_comm *c);
+int dp_pcs_comm_part(const dp_pcs_comm *c, uint32_t i, const dp_pcs_comm **out);
 int dp_pcs_comm_info(const dp_pcs_comm *c, uint32_t *num_vars, int *is_base, int *is_trivial, uint64_t root[4]);
 int dp_pcs_comm_codeword(const dp_pcs_comm *c, dp_mle **out_view);   /* bit-reversed codeword (view) */
 int dp_pcs_comm_bh_evals(const dp_pcs_comm *c, dp_mle **out_view);   /* bit-reversed evaluations (view) */

@@ -91,3 +91,20 @@ def test_open_full_size_properties(gpu):
         assert authenticate(qr["commitment"], [int(x) for x in root], True)
         for k, oq in enumerate(qr["oracle"]):
             assert authenticate(oq, pr["roots"][k], False)
+
+
+@pytest.mark.parametrize("n_polys,nv,full_log,ext", [(3, 9, 10, False), (5, 10, 10, False), (2, 9, 9, True), (1, 9, 9, False), (4, 8, 12, False), (6, 13, 13, False), (3, 16, 16, False), (3, 5, 8, False)])
+def test_batch_commit_and_simple_batch_open(gpu, n_polys, nv, full_log, ext):
+    """Basefold::batch_commit (one tree with batch leaves) and simple_batch_open (basefold.rs:356-452,777-861): root and whole
+    proof identical to the CPU checker's, and accepted by the restated simple_batch_verify"""
+    polys = [rnd_poly(900 + i, nv, ext) for i in range(n_polys)]
+    pt = O.splitmix_e(950, nv)
+    if nv <= 7:   # trivial commitment: only the root (the opening is the evaluations themselves)
+        root, _ = gpu.pcs_simple_batch([gpu.Mle.upload(p, ext) for p in polys], full_log)
+        assert (root == O.pcs_simple_batch(polys, ext, full_log)[0]).all()
+        return
+    eroot, evals, exp = O.pcs_simple_batch(polys, ext, full_log, pt)
+    root, got = gpu.pcs_simple_batch([gpu.Mle.upload(p, ext) for p in polys], full_log, pt, evals)
+    assert (root == eroot).all()
+    assert got.shape == exp.shape and (got == exp).all()
+    assert O.pcs_simple_batch_verify(got, root, nv, not ext, n_polys, full_log, pt, evals) is None
