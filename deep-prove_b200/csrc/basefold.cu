@@ -577,6 +577,18 @@ int dp_pcs_batch_commit(const dp_mle *const *polys, uint32_t n, uint32_t full_lo
     DpCtx &c = dp_ctx();
     dp_pcs_comm *b = new dp_pcs_comm();
     b->num_vars = polys[0]->num_vars(); b->full_log = full_log; b->is_base = !polys[0]->is_ext;
+    if (n == 1) {   // merkelize with one value vector is the plain tree (merkle_tree.rs:274-285): the batch is a view of an ordinary commitment
+        dp_pcs_comm *part = nullptr; u64 *pin1 = nullptr;
+        if (int e = dp_pinned_alloc((void **)&pin1, 32)) { dp_pcs_comm_free(b); return e; }
+        int rc = commit_enqueue(polys[0], full_log, &part, pin1, true);
+        if (rc == DP_OK) { cudaStreamSynchronize(c.stream); memcpy(part->root, pin1, 32); memcpy(b->root, pin1, 32); }
+        dp_pinned_free(pin1);
+        if (rc != DP_OK) { dp_pcs_comm_free(b); return rc; }
+        b->parts.push_back(part); b->trivial = part->trivial; b->cw_len = part->cw_len;
+        b->tree = part->tree; b->tree.own_levels = false; b->tree.own_leaves = false;
+        *out = b;
+        return DP_OK;
+    }
     BatchPtrs bp; memset(&bp, 0, sizeof bp);
     for (u32 i = 0; i < n; i++) {
         dp_pcs_comm *part = nullptr;
