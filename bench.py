@@ -507,6 +507,9 @@ def main():
                 "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "launches": cnt, "avg_us": 1e3 * tot_ms / max(cnt, 1), "alg_bytes_per_launch": tot_bytes / max(cnt, 1),
                 "share_of_kernel_time": tot_ms / all_ms if all_ms > 0 else None,
+                # context for a latency-bound dominant kernel: the kernels that actually stream, by algorithmic bytes
+                "streaming_kernels": {k: {"GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 1), "frac": round(v[2] / (v[1] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4), "ms": round(v[1], 4)}
+                                      for k, v in sorted(prof.items(), key=lambda kv: -kv[1][2])[:3] if v[1] > 0},
                 "all_kernels": {k: {"launches": v[0], "ms": round(v[1], 4), "GBps": round(v[2] / (v[1] * 1e-3) / 1e9, 2) if v[1] > 0 else 0.0}
                                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
 
