@@ -373,6 +373,22 @@ def pcs_batch_open(mles, full_log, points, label=b"m2vec", cap=1 << 25):
     return out[: n.value].copy()
 
 
+def pcs_batch_open_evals(mles, full_log, points, eval_poly, eval_point, label=b"m2vec", cap=1 << 25):
+    """commit each polynomial, then Basefold::batch_open with an explicit evaluation list (several polynomials may share a point)"""
+    _pcs_setup()
+    H = host()
+    H.dph_pcs_batch_open_evals.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p,
+                                           C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    hs = (C.c_void_p * len(mles))(*[m.h for m in mles])
+    p = np.concatenate([_u64(x).reshape(-1) for x in points])
+    pnv = np.ascontiguousarray([_u64(x).reshape(-1, 2).shape[0] for x in points], dtype=np.uint32)
+    ep = np.ascontiguousarray(eval_poly, dtype=np.uint32); eq = np.ascontiguousarray(eval_point, dtype=np.uint32)
+    out = np.zeros(cap, dtype=np.uint64)
+    n = C.c_uint64()
+    hcheck(H.dph_pcs_batch_open_evals(hs, len(mles), full_log, p.ctypes.data, pnv.ctypes.data, len(pnv), ep.ctypes.data, eq.ctypes.data, len(ep), label, out.ctypes.data, cap, C.byref(n)))
+    return out[: n.value].copy()
+
+
 def pcs_simple_batch(mles, full_log, point=None, evals=None, label=b"m2vec", cap=1 << 24):
     """Basefold::batch_commit of same-size device MLEs (+ simple_batch_open at `point` with the claimed `evals`): (root, flat | None)"""
     _pcs_setup()

@@ -361,3 +361,24 @@ extern "C" int dph_pcs_simple_batch(dp_mle *const *polys, uint32_t n, uint32_t f
     return 0;
     DPH_CATCH
 }
+
+// batch_open with an explicit evaluation list: `points` = n_points points concatenated (point k has point_nv[k] elements),
+// evaluation j claims polys[eval_poly[j]] at points[eval_point[j]] (the value is computed here)
+extern "C" int dph_pcs_batch_open_evals(dp_mle *const *polys, uint32_t n, uint32_t full_log, const uint64_t *points, const uint32_t *point_nv, uint32_t n_points,
+                                        const uint32_t *eval_poly, const uint32_t *eval_point, uint32_t n_evals, const char *label, uint64_t *out, uint64_t cap, uint64_t *out_len) {
+    DPH_TRY
+    BasefoldProverParams pp; pp.full_message_size_log = full_log;
+    std::vector<DeviceMle> ms; std::vector<BasefoldCommitmentWithWitness> comms; std::vector<ExtVec> pts; std::vector<Evaluation> evals;
+    for (uint32_t i = 0; i < n; i++) { uint64_t len; int ext; check(dp_mle_info(polys[i], &len, &ext, nullptr)); ms.push_back(DeviceMle::wrap_device(dp_mle_device_ptr(polys[i]), len, ext)); comms.push_back(Basefold::commit(pp, ms.back())); }
+    size_t o = 0;
+    for (uint32_t k = 0; k < n_points; k++) { ExtVec pt; for (uint32_t j = 0; j < point_nv[k]; j++) pt.push_back(Ext(points[2 * (o + j)], points[2 * (o + j) + 1])); o += point_nv[k]; pts.push_back(pt); }
+    for (uint32_t j = 0; j < n_evals; j++) { Evaluation ev; ev.poly = eval_poly[j]; ev.point = eval_point[j]; ev.value = ms.at(ev.poly).evaluate(pts.at(ev.point)); evals.push_back(ev); }
+    BasicTranscript t(label);
+    BasefoldProof pr = Basefold::batch_open(pp, ms, comms, pts, evals, t);
+    std::vector<uint64_t> f = pr.flatten();
+    *out_len = f.size();
+    if (f.size() > cap) throw Error(DP_ERR_INVALID, "dph_pcs_batch_open_evals: output buffer too small");
+    memcpy(out, f.data(), 8 * f.size());
+    return 0;
+    DPH_CATCH
+}

@@ -150,22 +150,22 @@ class Basefold {
         ExtVec eq_xt = build_eq_x_r_vec_host(t);
         Ext target = Ext::zero();
         for (size_t i = 0; i < evals.size(); i++) target += evals[i].value * Ext::from_base(canon(1ULL << (num_vars - points[evals[i].point].size()))) * eq_xt[i];
-        // merged polynomials: the reference keeps (scalar, Borrowed(poly)) while a point has one polynomial
-        // (basefold.rs:617-623) -- the only case zkml produces (Evaluation::new(i, i, _), commit/context.rs:378).
-        std::vector<int> owner(points.size(), -1); std::vector<Ext> scalar(points.size());
-        for (size_t i = 0; i < evals.size(); i++) {
-            if (owner[evals[i].point] != -1) throw Error(DP_ERR_UNSUPPORTED, "batch_open: several polynomials opened at one point index (merge on device not implemented)");
-            owner[evals[i].point] = (int)evals[i].poly; scalar[evals[i].point] = eq_xt[i];
-        }
+        // merged polynomials (basefold.rs:617-640): the reference forms sum_i eq_xt[i] * poly_i per point.  The sumcheck message
+        // is linear in the polynomial, so one product (eq(point_k), poly_i) with coefficient eq_xt[i] PER EVALUATION gives the
+        // identical messages without materialising the merge; the point's eq table is shared (folded once) by all its products.
         // ClassicSumCheck<CoefficientsProver>::prove (sum_check/classic.rs:230-285, classic/coeff.rs:196-345):
-        // sum_k scalar_k * eq(x, y_k) * poly_k(x), LSB-first, 3 coefficients per round with c1 from the running sum
+        // LSB-first, 3 coefficients per round with c1 from the running sum
         VirtualPolynomial vp(num_vars);
         std::vector<DeviceMle> eqs;
-        for (size_t k = 0; k < points.size(); k++) {
-            if (owner[k] < 0) throw Error(DP_ERR_INVALID, "batch_open: point without evaluation");
-            eqs.push_back(DeviceMle::build_eq_x_r(points[k]));
-            vp.add_mle_list({eqs.back(), polys[owner[k]]}, scalar[k]);
+        for (size_t k = 0; k < points.size(); k++) eqs.push_back(DeviceMle::build_eq_x_r(points[k]));
+        std::vector<bool> used(points.size(), false);
+        for (size_t i = 0; i < evals.size(); i++) {
+            if (evals[i].point >= points.size() || evals[i].poly >= polys.size()) throw Error(DP_ERR_INVALID, "batch_open: evaluation refers to a missing polynomial / point");
+            if (polys[evals[i].poly].num_vars() != points[evals[i].point].size()) throw Error(DP_ERR_INVALID, "batch_open: point length != polynomial num_vars");   // basefold.rs:575-580
+            vp.add_mle_list({eqs[evals[i].point], polys[evals[i].poly]}, eq_xt[i]);
+            used[evals[i].point] = true;
         }
+        for (bool u : used) if (!u) throw Error(DP_ERR_INVALID, "batch_open: point without evaluation");
         std::vector<dp_mle *> hs; for (auto &m : vp.flattened_ml_extensions) hs.push_back(m.handle());
         dp_sc *sc = nullptr;
         check(dp_sc_create(hs.data(), (uint32_t)hs.size(), vp.products.data(), (uint32_t)vp.products.size(), num_vars, 2, &sc));

@@ -507,3 +507,31 @@ int dpo_pcs_simple_batch_verify(const u64 *flat, u64 n, const u64 *root, u32 num
     } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
 }
+
+// batch_open / batch_verify with an explicit evaluation list (several polynomials may share a point)
+extern "C" int dpo_pcs_batch_open_evals(u32 n, const u64 *const *data, const u64 *lens, const int *is_ext, u32 full_log, const u64 *points, const u32 *point_nv, u32 n_points,
+                                        const u32 *eval_poly, const u32 *eval_point, u32 n_evals, const char *label, u64 *out_roots, u64 *out_values, u64 *out, u64 cap, u64 *out_len, int verify) {
+    try {
+        std::vector<FVec> polys; std::vector<Commitment> comms; std::vector<std::vector<E>> pts; std::vector<Evaluation> evals;
+        for (u32 i = 0; i < n; i++) { polys.push_back(mk_fvec(data[i], lens[i], is_ext[i])); comms.push_back(basefold_commit(polys.back(), full_log)); for (int k = 0; k < 4; k++) out_roots[4 * i + k] = comms.back().root().v[k]; }
+        size_t o = 0;
+        for (u32 k = 0; k < n_points; k++) { pts.push_back(mk_point(points + 2 * o, point_nv[k])); o += point_nv[k]; }
+        for (u32 j = 0; j < n_evals; j++) {
+            const FVec &p = polys.at(eval_poly[j]); MLE m; m.is_ext = p.is_ext; m.num_vars = ceil_log2(p.len()); m.base = p.b; m.ext = p.e;
+            E v = mle_evaluate(m, pts.at(eval_point[j])); evals.push_back({eval_poly[j], eval_point[j], v}); out_values[2 * j] = v.c0; out_values[2 * j + 1] = v.c1;
+        }
+        std::vector<const Commitment *> cp; for (auto &c : comms) cp.push_back(&c);
+        Transcript t(label);
+        BasefoldProof p = basefold_batch_open(full_log, polys, cp, pts, evals, t);
+        if (verify) {
+            std::vector<PureCommitment> pcs; for (auto &c : comms) { PureCommitment q; q.root = c.root(); q.num_vars = c.num_vars; q.is_base = c.is_base; pcs.push_back(q); }
+            Transcript tv(label);
+            basefold_batch_verify(full_log, pcs, pts, evals, p, tv);
+        }
+        std::vector<u64> f = flatten_proof(p);
+        *out_len = f.size();
+        if (f.size() > cap) { g_err = "dpo_pcs_batch_open_evals: output buffer too small"; return 2; }
+        memcpy(out, f.data(), 8 * f.size());
+        return 0;
+    } catch (std::exception &e) { g_err = e.what(); return 1; }
+}

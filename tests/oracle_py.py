@@ -477,3 +477,22 @@ def pcs_simple_batch_verify(flat, root, num_vars, is_base, n_polys, full_log, po
     f = u64(flat); r = u64(root); pt = u64(point).reshape(-1); ev = u64(evals).reshape(-1)
     rc = lib().dpo_pcs_simple_batch_verify(ptr(f), C.c_uint64(f.size), ptr(r), C.c_uint32(num_vars), C.c_int(int(is_base)), C.c_uint32(n_polys), C.c_uint32(full_log), ptr(pt), ptr(ev), label)
     return None if rc == 0 else lib().dpo_last_error().decode()
+
+
+def pcs_batch_open_evals(polys, full_log, points, eval_poly, eval_point, label=b"m2vec", cap=1 << 25, verify=True):
+    """batch_open with an explicit (poly, point) evaluation list, verified by the restated batch_verify when `verify`"""
+    arrs = [u64(p[0]).reshape(-1) for p in polys]
+    n = len(arrs)
+    data = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    lens = u64([a.size // (2 if p[1] else 1) for a, p in zip(arrs, polys)])
+    ie = np.ascontiguousarray(np.asarray([int(bool(p[1])) for p in polys], dtype=np.int32))
+    pts = u64(np.concatenate([u64(x).reshape(-1) for x in points]))
+    pnv = np.ascontiguousarray([u64(x).reshape(-1, 2).shape[0] for x in points], dtype=np.uint32)
+    ep = np.ascontiguousarray(eval_poly, dtype=np.uint32); eq = np.ascontiguousarray(eval_point, dtype=np.uint32)
+    roots = np.zeros((n, 4), dtype=np.uint64); vals = np.zeros((len(ep), 2), dtype=np.uint64)
+    out = np.zeros(cap, dtype=np.uint64); ol = C.c_uint64()
+    rc = lib().dpo_pcs_batch_open_evals(C.c_uint32(n), data, ptr(lens), ptr(ie), C.c_uint32(full_log), ptr(pts), ptr(pnv), C.c_uint32(len(pnv)), ptr(ep), ptr(eq), C.c_uint32(len(ep)),
+                                        label, ptr(roots), ptr(vals), ptr(out), C.c_uint64(cap), C.byref(ol), C.c_int(int(verify)))
+    if rc:
+        raise RuntimeError(lib().dpo_last_error().decode())
+    return out[:ol.value].copy(), roots, vals

@@ -108,3 +108,15 @@ def test_batch_commit_and_simple_batch_open(gpu, n_polys, nv, full_log, ext):
     assert (root == eroot).all()
     assert got.shape == exp.shape and (got == exp).all()
     assert O.pcs_simple_batch_verify(got, root, nv, not ext, n_polys, full_log, pt, evals) is None
+
+
+def test_batch_open_with_shared_points(gpu):
+    """batch_open where two polynomials share a point and one polynomial is opened at two points (the merged-polynomial case of
+    basefold.rs:617-640): the device adds one sumcheck product per evaluation instead of merging; identical proof"""
+    shape = [(10, False), (10, False), (9, True), (10, False)]
+    polys = [(rnd_poly(1000 + i, nv, ext), ext) for i, (nv, ext) in enumerate(shape)]
+    points = [O.splitmix_e(1100, 10), O.splitmix_e(1101, 9), O.splitmix_e(1102, 10)]
+    eval_poly, eval_point = [0, 1, 2, 3, 0], [0, 0, 1, 2, 2]
+    exp, _, _ = O.pcs_batch_open_evals(polys, 11, points, eval_poly, eval_point)
+    got = gpu.pcs_batch_open_evals([gpu.Mle.upload(a, e) for a, e in polys], 11, points, eval_poly, eval_point)
+    assert got.shape == exp.shape and (got == exp).all()

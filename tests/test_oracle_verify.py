@@ -80,3 +80,14 @@ def test_batch_commit_simple_batch_open_verifies(n_polys, nv, full_log, ext):
     assert O.pcs_simple_batch_verify(flat, root, nv, not ext, n_polys, full_log, pt, bad) is not None
     tam = flat.copy(); tam[flat.size // 2] ^= np.uint64(1)
     assert O.pcs_simple_batch_verify(tam, root, nv, not ext, n_polys, full_log, pt, evals) is not None
+
+
+def test_batch_open_with_shared_points_verifies():
+    """several polynomials opened at the same point (basefold.rs:617-640 merges them) and one polynomial at two points: the
+    restated batch_verify accepts"""
+    shape = [(10, False), (10, False), (9, True), (10, False)]
+    polys = [(O.splitmix_e(1000 + i, 1 << nv) if ext else O.splitmix_f(1000 + i, 1 << nv), ext) for i, (nv, ext) in enumerate(shape)]
+    points = [O.splitmix_e(1100, 10), O.splitmix_e(1101, 9), O.splitmix_e(1102, 10)]
+    eval_poly, eval_point = [0, 1, 2, 3, 0], [0, 0, 1, 2, 2]
+    flat, roots, vals = O.pcs_batch_open_evals(polys, 11, points, eval_poly, eval_point)   # raises unless batch_verify accepts
+    assert flat.size > 1000
