@@ -15,6 +15,7 @@
 // O(deg^2) glue (2^k multiplicity, coefficient, barycentric extrapolation -- prover.rs:713-724,
 // util.rs:101-136) runs on the host inside dp_sc_round, exactly where the reference has it.
 #include "common.cuh"
+#include <mutex>
 #include <algorithm>
 
 enum : u32 { OPM_B = 0, OPM_E = 1, OPM_BF = 2, OPM_EF = 3 };
@@ -500,6 +501,34 @@ static int sc_glue(dp_sc *s, uint64_t *out_evals) {
 }
 
 
+
+// Can a resident kernel talk to the host while it runs?  Not under tools that serialise launches (Nsight Compute blocks the
+// launching thread until the profiled kernel has finished, so the kernel would wait for a challenge its host cannot post).
+// Checked once per process: known injection environments are refused outright, otherwise a one-thread probe kernel waits
+// (<= ~50 ms) for a word the host posts right after the launch call returns.
+__global__ void k_tail_probe(volatile u64 *mailbox, volatile u64 *result, long long limit_cycles) {
+    long long t0 = clock64(); u64 ok = 2;
+    while (clock64() - t0 < limit_cycles) { if (mailbox[0] == 1) { ok = 1; break; } }
+    __threadfence_system();
+    result[0] = ok;
+}
+static bool sc_tail_supported() {
+    static std::once_flag once; static bool supported = false;
+    std::call_once(once, [] {
+        if (getenv("DP_SC_NO_TAIL") || getenv("CUDA_INJECTION64_PATH") || getenv("CUDA_INJECTION32_PATH") || getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") ||
+            getenv("NV_NSIGHT_INJECTION_PORT_BASE") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return;
+        u64 *pin = nullptr;
+        if (dp_pinned_alloc((void **)&pin, 128) != DP_OK) return;
+        pin[0] = 0; pin[8] = 0;
+        cudaStream_t st = dp_ctx().stream;
+        k_tail_probe<<<1, 1, 0, st>>>(pin, pin + 8, 100000000LL); dp_count_launch();
+        __atomic_store_n(&pin[0], (u64)1, __ATOMIC_RELEASE);          // reached at once unless the launch call itself waits for the kernel
+        if (cudaStreamSynchronize(st) == cudaSuccess) supported = (pin[8] == 1);
+        dp_pinned_free(pin);
+    });
+    return supported;
+}
+
 // ---- resident tail, host side ----
 static bool sc_tail_eligible(const dp_sc *s, bool fold) {
     if (!s->tail_enabled || s->n_mles > SC_TAIL_MAXM || s->n_products > SC_TAIL_MAXP || s->max_nv - s->round < 2) return false;
@@ -800,8 +829,7 @@ uint64_t dp_sc_last_round_bytes(const dp_sc *s) { return s ? s->last_bytes : 0; 
 int dp_sc_set_resident_tail(dp_sc *s, int enable) {
     DP_REQUIRE_CTX();
     DP_CHECK(s && !s->tail_active, DP_ERR_STATE, "dp_sc_set_resident_tail: null handle or tail already running");
-    static const bool off = getenv("DP_SC_NO_TAIL") != nullptr;
-    s->tail_enabled = enable != 0 && !off;
+    s->tail_enabled = enable != 0 && sc_tail_supported();
     return DP_OK;
 }
 

@@ -99,7 +99,9 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals);
  * challenge (no launch and no cross-block reduction per round).  Contract: between consecutive dp_sc_round calls on this
  * handle the calling thread must not WAIT on other work submitted to the same stream (it would queue behind the
  * resident kernel).  The kernel gives up by itself after ~3 s without a challenge and dp_sc_round reports the error;
- * dp_sc_destroy releases it.  Results are identical with and without it.  Env DP_SC_NO_TAIL=1 disables it globally. */
+ * dp_sc_destroy releases it.  Results are identical with and without it.  Env DP_SC_NO_TAIL=1 disables it globally, and it
+ * disables itself under tools that serialise kernel launches (Nsight Compute, compute-sanitizer): a one-time probe checks
+ * that a running kernel can see a word the host posts after the launch call returned. */
 int dp_sc_set_resident_tail(dp_sc *s, int enable);
 /* Tail of prove_parallel (prover.rs:544-568) + get_mle_final_evaluations (:474-490): fixes the last
  * challenge and writes n_mles x [c0,c1]. */
