@@ -24,10 +24,10 @@ dist.destroy_process_group()
 ''' % ROOT
 
 
-def _torchrun(args, timeout=300):
+def _torchrun(args, timeout=300, nproc=2):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29613"] + args
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", str(29613 + nproc)] + args
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
 
 
@@ -94,15 +94,19 @@ dist.destroy_process_group()
 '''
 
 
-def test_sharded_sumcheck_equals_unsplit_proof(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_sumcheck_equals_unsplit_proof(tmp_path, world):
     """devirgo split across ranks (multigpu.prove_sharded) == prove_parallel on the unsplit polynomial, on every rank
     (the identity zkml/src/model/mod.rs:987-993 asserts); exchange over gloo, slices evaluated by the CPU checker"""
     w = tmp_path / "sharded.py"
     w.write_text(SHARDED_WORKER % {"root": ROOT})
-    r = _torchrun([str(w)])
+    r = _torchrun([str(w)], nproc=world)
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
-    assert out == {"ok": True, "world": 2, "rounds": 9}
+    assert out == {"ok": True, "world": world, "rounds": 9}
 
 
 SHM_WORKER = r'''
