@@ -495,7 +495,8 @@ def main():
         # the resident tail kernel spans many rounds and its event time includes the host's Fiat-Shamir between them:
         # it is reported separately and is not a candidate for the dominant kernel
         tail = {k: v for k, v in prof.items() if k.startswith("k_sc_tail")}
-        prof = {k: v for k, v in prof.items() if not k.startswith("k_sc_tail")}
+        rest = {k: v for k, v in prof.items() if not k.startswith("k_sc_tail")}
+        prof = rest if rest else prof           # a workload made of resident rounds only: fall back to the tail itself
         name = max(prof, key=lambda k: prof[k][1])
         cnt, tot_ms, tot_bytes = prof[name]
         ach = tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
