@@ -12,6 +12,22 @@ extern "C" {
 const char *dph_last_error() { return g_herr.c_str(); }
 
 void dph_poseidon2_permute(uint64_t *state) { Poseidon2::permute(state); }
+// fast (weak-form) permutation against the canonical formulation on n seeded states, every third one drawn from edge values;
+// returns the number of mismatching or non-canonical output words (0 expected)
+uint64_t dph_poseidon2_selfcheck(uint64_t n, uint64_t seed) {
+    auto sm = [&]() { uint64_t z = (seed += 0x9E3779B97F4A7C15ULL); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31); };
+    const uint64_t edge[] = {0, 1, 2, P - 1, P - 2, EPS, EPS + 1, 1ULL << 32, 1ULL << 63, (P - 1) / 2, 0xFFFFFFFEFFFFFFFFULL, 7};
+    const int ne = sizeof(edge) / 8; uint64_t bad = 0, a[8], b[8], ca[8] = {0}, cb[8] = {0};
+    for (uint64_t it = 0; it < n; it++) {
+        for (int i = 0; i < 8; i++) a[i] = b[i] = (it % 3 == 0) ? edge[sm() % ne] : canon(sm());
+        Poseidon2::permute(a); Poseidon2::permute_canonical(b);
+        for (int i = 0; i < 8; i++) if (a[i] != b[i] || a[i] >= P) bad++;
+        ca[it & 3] = cb[it & 3] = canon(sm());                       // and a chained (sponge-like) sequence
+        Poseidon2::permute(ca); Poseidon2::permute_canonical(cb);
+        for (int i = 0; i < 8; i++) if (ca[i] != cb[i]) bad++;
+    }
+    return bad;
+}
 
 void *dph_transcript_new(const char *label) { return new BasicTranscript(label); }
 void dph_transcript_free(void *t) { delete (BasicTranscript *)t; }

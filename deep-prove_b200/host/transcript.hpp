@@ -12,21 +12,61 @@ namespace dp {
 
 class Poseidon2 {
   public:
+    // The sponge sits on the critical path between device rounds (~3400 permutations per Dense-4M proof), so the permutation
+    // is written like the device one (csrc/poseidon2.cuh): state words stay "weak" (any u64, not reduced below p), products
+    // are reduced 128 -> 64 bits without canonicalising, the linear layers accumulate in 128 bits and fold once per output,
+    // the internal layer's s[i] * diag[i] + sum is ONE reduction.  Exact modular arithmetic throughout; canonical in, canonical out.
     static void permute(u64 s[8]) {
         linear_ext(s);
-        for (int r = 0; r < 4; r++) { for (int i = 0; i < 8; i++) s[i] = pow7(fadd(s[i], DP_P2_EXT_RC[0][r][i])); linear_ext(s); }
+        for (int r = 0; r < 4; r++) { for (int i = 0; i < 8; i++) s[i] = pow7(wadd(s[i], DP_P2_EXT_RC[0][r][i])); linear_ext(s); }
         for (int r = 0; r < 22; r++) {
-            s[0] = pow7(fadd(s[0], DP_P2_INT_RC[r]));
+            s[0] = pow7(wadd(s[0], DP_P2_INT_RC[r]));
+            u128 tot = 0;
+            for (int i = 0; i < 8; i++) tot += s[i];                                        // < 2^67
+            for (int i = 0; i < 8; i++) s[i] = wred((u128)s[i] * DP_P2_DIAG[i] + tot);      // < 2^128 - 2^96 + 2^67: no overflow
+        }
+        for (int r = 0; r < 4; r++) { for (int i = 0; i < 8; i++) s[i] = pow7(wadd(s[i], DP_P2_EXT_RC[1][r][i])); linear_ext(s); }
+        for (int i = 0; i < 8; i++) s[i] = canon(s[i]);
+    }
+    // the straightforward canonical formulation (kept as the cross-check of the fast path, tests/test_hash_transcript.py)
+    static void permute_canonical(u64 s[8]) {
+        linear_ext_c(s);
+        for (int r = 0; r < 4; r++) { for (int i = 0; i < 8; i++) s[i] = pow7_c(fadd(s[i], DP_P2_EXT_RC[0][r][i])); linear_ext_c(s); }
+        for (int r = 0; r < 22; r++) {
+            s[0] = pow7_c(fadd(s[0], DP_P2_INT_RC[r]));
             u64 tot = 0;
             for (int i = 0; i < 8; i++) tot = fadd(tot, s[i]);
             for (int i = 0; i < 8; i++) s[i] = fadd(fmul(s[i], DP_P2_DIAG[i]), tot);
         }
-        for (int r = 0; r < 4; r++) { for (int i = 0; i < 8; i++) s[i] = pow7(fadd(s[i], DP_P2_EXT_RC[1][r][i])); linear_ext(s); }
+        for (int r = 0; r < 4; r++) { for (int i = 0; i < 8; i++) s[i] = pow7_c(fadd(s[i], DP_P2_EXT_RC[1][r][i])); linear_ext_c(s); }
     }
   private:
-    static u64 pow7(u64 x) { u64 a = fmul(x, x), b = fmul(a, a); return fmul(fmul(a, x), b); }
-    // circ(2,3,1,1) on each half, then add the column sums (p3 MDSMat4 + mds_light_permutation)
+    // hi * 2^64 + lo -> some representative in [0, 2^64): 2^64 = 2^32 - 1, 2^96 = -1 (mod p); branch-free
+    static u64 wred(u128 x) {
+        u64 lo = (u64)x, hi = (u64)(x >> 64), hh = hi >> 32, hl = hi & EPS;
+        u64 t0 = lo - hh; t0 -= ((u64)0 - (u64)(lo < hh)) & EPS;
+        u64 t1 = (hl << 32) - hl;
+        u64 r = t0 + t1; r += ((u64)0 - (u64)(r < t1)) & EPS;
+        return r;
+    }
+    static u64 wmul(u64 a, u64 b) { return wred((u128)a * b); }
+    static u64 wadd(u64 a, u64 c) { u64 r = a + c; r += ((u64)0 - (u64)(r < a)) & EPS; return r; }   // a weak, c < p: at most one wrap, then + EPS cannot wrap again
+    static u64 pow7(u64 x) { u64 a = wmul(x, x), b = wmul(a, a); return wmul(wmul(a, x), b); }
+    // circ(2,3,1,1) on each half, then add the column sums (p3 MDSMat4 + mds_light_permutation): out[i] = 2 n[i] + n[i ^ 4], n < 7 * 2^64
     static void linear_ext(u64 *s) {
+        u128 n[8];
+        for (int h = 0; h < 8; h += 4) {
+            const u64 *x = s + h;
+            u128 a = (u128)x[0] + x[1], b = (u128)x[2] + x[3], all = a + b;
+            n[h + 0] = all + x[1] + a;                 // 2 x0 + 3 x1 + x2 + x3
+            n[h + 1] = all + x[1] + x[2] + x[2];       // x0 + 2 x1 + 3 x2 + x3
+            n[h + 2] = all + x[3] + b;                 // x0 + x1 + 2 x2 + 3 x3
+            n[h + 3] = all + x[3] + x[0] + x[0];       // 3 x0 + x1 + x2 + 2 x3
+        }
+        for (int i = 0; i < 8; i++) s[i] = wred(n[i] + n[i] + n[i ^ 4]);
+    }
+    static u64 pow7_c(u64 x) { u64 a = fmul(x, x), b = fmul(a, a); return fmul(fmul(a, x), b); }
+    static void linear_ext_c(u64 *s) {
         for (int h = 0; h < 8; h += 4) {
             u64 *x = s + h;
             u64 a = fadd(x[0], x[1]), b = fadd(x[2], x[3]), all = fadd(a, b);

@@ -535,3 +535,16 @@ extern "C" int dpo_pcs_batch_open_evals(u32 n, const u64 *const *data, const u64
         return 0;
     } catch (std::exception &e) { g_err = e.what(); return 1; }
 }
+
+// fast permutation vs the plain restatement on n seeded states (edge values every third state): number of mismatching words
+extern "C" u64 dpo_poseidon2_selfcheck(u64 n, u64 seed) {
+    SplitMix64 g(seed);
+    const u64 edge[] = {0, 1, 2, GL_P - 1, GL_P - 2, 0xFFFFFFFFULL, 0x100000000ULL, 1ULL << 63, (GL_P - 1) / 2, 0xFFFFFFFEFFFFFFFFULL, 7};
+    const int ne = sizeof(edge) / 8; u64 bad = 0, a[8], b[8];
+    for (u64 it = 0; it < n; it++) {
+        for (int i = 0; i < 8; i++) a[i] = b[i] = (it % 3 == 0) ? edge[g.next() % ne] : g.next_f();
+        poseidon2_permute(a); poseidon2_permute_plain(b);
+        for (int i = 0; i < 8; i++) if (a[i] != b[i] || a[i] >= GL_P) bad++;
+    }
+    return bad;
+}

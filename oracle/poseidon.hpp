@@ -38,7 +38,7 @@ static inline u64 p2_sbox(u64 x) { u64 x2 = f_mul(x, x), x3 = f_mul(x2, x), x4 =
 // NoAllocPoseidon::permute_mut (ff_ext/src/lib.rs:222-228):
 //   external_initial (mds_light, then 4x [add rc, x^7, mds_light]); 22x internal [s0 += rc; s0 ^= 7;
 //   s[i] = s[i]*diag[i] + sum]; external_terminal (4x [add rc, x^7, mds_light]).
-static inline void poseidon2_permute(u64 s[8]) {
+static inline void poseidon2_permute_plain(u64 s[8]) {
     p2_mds_light(s);
     for (int r = 0; r < 4; r++) {
         for (int i = 0; i < 8; i++) s[i] = p2_sbox(f_add(s[i], DP_P2_EXT_RC[0][r][i]));
@@ -54,6 +54,41 @@ static inline void poseidon2_permute(u64 s[8]) {
         for (int i = 0; i < 8; i++) s[i] = p2_sbox(f_add(s[i], DP_P2_EXT_RC[1][r][i]));
         p2_mds_light(s);
     }
+}
+
+// Same permutation, written for speed (the Merkle trees of the CPU baseline are ~all permutations): state words stay "weak"
+// (any u64), products are reduced 128 -> 64 bits without canonicalising, linear layers accumulate in 128 bits, the internal
+// layer's s[i] * diag[i] + sum is one reduction.  Exact arithmetic: canonical in, canonical out, identical to the plain form
+// above (dpo_poseidon2_selfcheck compares them; the golden vectors pin both).
+static inline u64 p2w_red(u128 x) {
+    u64 lo = (u64)x, hi = (u64)(x >> 64), hh = hi >> 32, hl = hi & 0xFFFFFFFFULL;
+    u64 t0 = lo - hh; t0 -= ((u64)0 - (u64)(lo < hh)) & 0xFFFFFFFFULL;
+    u64 t1 = (hl << 32) - hl;
+    u64 r = t0 + t1; r += ((u64)0 - (u64)(r < t1)) & 0xFFFFFFFFULL;
+    return r;
+}
+static inline u64 p2w_mul(u64 a, u64 b) { return p2w_red((u128)a * b); }
+static inline u64 p2w_add(u64 a, u64 c) { u64 r = a + c; r += ((u64)0 - (u64)(r < a)) & 0xFFFFFFFFULL; return r; }
+static inline u64 p2w_sbox(u64 x) { u64 a = p2w_mul(x, x), b = p2w_mul(a, a); return p2w_mul(p2w_mul(a, x), b); }
+static inline void p2w_mds_light(u64 *s) {
+    u128 n[8];
+    for (int h = 0; h < 8; h += 4) {
+        const u64 *x = s + h;
+        u128 a = (u128)x[0] + x[1], b = (u128)x[2] + x[3], all = a + b;
+        n[h + 0] = all + x[1] + a; n[h + 1] = all + x[1] + x[2] + x[2]; n[h + 2] = all + x[3] + b; n[h + 3] = all + x[3] + x[0] + x[0];
+    }
+    for (int i = 0; i < 8; i++) s[i] = p2w_red(n[i] + n[i] + n[i ^ 4]);
+}
+static inline void poseidon2_permute(u64 s[8]) {
+    p2w_mds_light(s);
+    for (int r = 0; r < 4; r++) { for (int i = 0; i < 8; i++) s[i] = p2w_sbox(p2w_add(s[i], DP_P2_EXT_RC[0][r][i])); p2w_mds_light(s); }
+    for (int r = 0; r < 22; r++) {
+        s[0] = p2w_sbox(p2w_add(s[0], DP_P2_INT_RC[r]));
+        u128 tot = 0; for (int i = 0; i < 8; i++) tot += s[i];
+        for (int i = 0; i < 8; i++) s[i] = p2w_red((u128)s[i] * DP_P2_DIAG[i] + tot);
+    }
+    for (int r = 0; r < 4; r++) { for (int i = 0; i < 8; i++) s[i] = p2w_sbox(p2w_add(s[i], DP_P2_EXT_RC[1][r][i])); p2w_mds_light(s); }
+    for (int i = 0; i < 8; i++) s[i] = f_canon(s[i]);
 }
 
 // DuplexChallenger<F, P, 8, 4>  (poseidon/src/challenger.rs:14-20; p3-challenger duplex_challenger.rs)

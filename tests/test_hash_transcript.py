@@ -90,3 +90,22 @@ def test_host_transcript_equals_oracle_transcript():
         assert (c1 == out).all()
         assert int(c1[0]) < O.P and int(c1[1]) < O.P
     h.dph_transcript_free(th)
+
+
+def test_fast_host_permutation_equals_the_canonical_formulation():
+    """the weak-form host permutation (host/transcript.hpp) against the plain canonical one on 300k seeded states incl. edge
+    values (0, 1, p-1, 2^32-1, 2^32, 2^63, ...) and a chained sponge-like sequence: identical, canonical outputs"""
+    import ctypes as C
+    import dpb200 as dp
+    H = dp.host()
+    H.dph_poseidon2_selfcheck.restype = C.c_uint64
+    H.dph_poseidon2_selfcheck.argtypes = [C.c_uint64, C.c_uint64]
+    assert H.dph_poseidon2_selfcheck(300000, 12345) == 0
+
+
+def test_fast_checker_permutation_equals_the_plain_restatement():
+    """oracle/poseidon.hpp: the speed-oriented permutation used by the CPU baseline against the line-by-line restatement"""
+    L = O.lib()
+    L.dpo_poseidon2_selfcheck.restype = C.c_uint64
+    L.dpo_poseidon2_selfcheck.argtypes = [C.c_uint64, C.c_uint64]
+    assert L.dpo_poseidon2_selfcheck(300000, 777) == 0
