@@ -16,7 +16,7 @@ HOST_HDRS := $(wildcard $(PKG)/host/*.hpp) include/deepprove_b200.h
 ORC_SRCS  := $(wildcard oracle/*.cpp)
 ORC_HDRS  := $(wildcard oracle/*.hpp) include/dp_poseidon2_constants.h
 
-all: product host oracle
+all: product host oracle tools
 
 product: $(PKG)/libdeepprove_b200.so
 host: $(PKG)/libdeepprove_host.so
@@ -35,7 +35,12 @@ $(PKG)/libdeepprove_host.so: $(HOST_SRCS) $(HOST_HDRS) $(PKG)/libdeepprove_b200.
 oracle/libdp_oracle.so: $(ORC_SRCS) $(ORC_HDRS)
 	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -fPIC -shared -Wall -o $@ $(ORC_SRCS) -lpthread
 
-clean:
-	rm -rf build $(PKG)/*.so oracle/*.so
+# device-vs-host self test of the field primitives and Poseidon2 (run by tests/test_gpu_baseline_size.py on the GPU box)
+tools: $(PKG)/gl_selftest_bin
+$(PKG)/gl_selftest_bin: tools/gl_selftest.cu $(CU_HDRS) $(HOST_HDRS)
+	$(NVCC) $(ARCH) -O2 -std=c++17 -Iinclude -o $@ tools/gl_selftest.cu
 
-.PHONY: all product host oracle clean
+clean:
+	rm -rf build $(PKG)/*.so oracle/*.so $(PKG)/gl_selftest_bin
+
+.PHONY: all product host oracle tools clean

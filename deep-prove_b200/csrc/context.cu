@@ -28,18 +28,43 @@ struct DpArena {
     std::vector<void *> free_list[48];
     std::unordered_map<void *, unsigned char> cls;
     std::vector<void *> deferred; bool defer = false;
+    // blocks of THIS arena released by other host threads (e.g. a handle created on one proving thread and destroyed on
+    // another): parked here under the registry lock and folded back into the free lists by the owner's next allocation
+    std::vector<void *> returned; std::atomic<unsigned> n_returned{0};
     unsigned long long foreign_frees = 0;
+    ~DpArena();
 };
+// process-wide slab registry: which arena owns an address (only consulted on the rare foreign free and on teardown)
+struct SlabReg { char *base; size_t cap; DpArena *owner; };
+static std::vector<SlabReg> g_slab_reg;
+static std::mutex g_slab_mu;
 static thread_local DpArena g_arena;
 static constexpr size_t ARENA_SLAB = 256ull << 20;
+static void arena_release_slabs(DpArena &a) {
+    {
+        std::lock_guard<std::mutex> lk(g_slab_mu);
+        for (size_t i = 0; i < g_slab_reg.size();) { if (g_slab_reg[i].owner == &a) { g_slab_reg[i] = g_slab_reg.back(); g_slab_reg.pop_back(); } else i++; }
+        a.returned.clear(); a.n_returned = 0;
+    }
+    for (auto &s : a.slabs) cudaFree(s.base);    // after the runtime has shut down this is a harmless error
+    a.slabs.clear();
+}
+// a host thread that exits without dp_shutdown() must not leak its >= 256 MB slabs
+DpArena::~DpArena() { arena_release_slabs(*this); }
 void dp_arena_defer(bool on) {
     g_arena.defer = on;
     if (!on) { for (void *p : g_arena.deferred) { auto it = g_arena.cls.find(p); if (it != g_arena.cls.end()) g_arena.free_list[it->second].push_back(p); } g_arena.deferred.clear(); }
+}
+static void arena_drain_returned(DpArena &a) {
+    std::lock_guard<std::mutex> lk(g_slab_mu);
+    for (void *p : a.returned) { auto it = a.cls.find(p); if (it != a.cls.end()) a.free_list[it->second].push_back(p); }
+    a.returned.clear(); a.n_returned = 0;
 }
 int dp_dev_alloc(void **p, size_t bytes) {
     if (bytes < 256) bytes = 256;
     unsigned c = 8; while (((size_t)1 << c) < bytes) c++;
     DpArena &a = g_arena;
+    if (a.free_list[c].empty() && a.n_returned.load(std::memory_order_acquire)) arena_drain_returned(a);
     if (!a.free_list[c].empty()) { *p = a.free_list[c].back(); a.free_list[c].pop_back(); return DP_OK; }
     size_t need = (size_t)1 << c;
     for (auto &s : a.slabs) if (s.cap - s.used >= need) { *p = s.base + s.used; s.used += need; a.cls[*p] = (unsigned char)c; return DP_OK; }
@@ -47,6 +72,7 @@ int dp_dev_alloc(void **p, size_t bytes) {
     char *base = nullptr;
     DP_CUDA(cudaMalloc((void **)&base, cap));
     a.slabs.push_back({base, cap, need});
+    { std::lock_guard<std::mutex> lk(g_slab_mu); g_slab_reg.push_back({base, cap, &a}); }
     *p = base; a.cls[*p] = (unsigned char)c;
     return DP_OK;
 }
@@ -54,13 +80,22 @@ int dp_dev_free(void *p) {
     if (!p) return DP_OK;
     DpArena &a = g_arena;
     auto it = a.cls.find(p);
-    if (it == a.cls.end()) { a.foreign_frees++; return DP_OK; }   // owned by another thread's arena: returned when that arena is torn down
+    if (it == a.cls.end()) {
+        // owned by another thread's arena: hand it back to its owner.  The owner's stream knows nothing about the work this
+        // thread queued on the block, so that work is drained first (foreign frees are rare: cross-thread handle teardown).
+        a.foreign_frees++;
+        if (g_ctx.ready && g_ctx.stream) cudaStreamSynchronize(g_ctx.stream);
+        std::lock_guard<std::mutex> lk(g_slab_mu);
+        for (auto &r : g_slab_reg) if ((char *)p >= r.base && (char *)p < r.base + r.cap) { r.owner->returned.push_back(p); r.owner->n_returned.fetch_add(1, std::memory_order_release); break; }
+        return DP_OK;
+    }
     if (a.defer) a.deferred.push_back(p); else a.free_list[it->second].push_back(p);
     return DP_OK;
 }
 static void arena_destroy() {
-    for (auto &s : g_arena.slabs) cudaFree(s.base);
-    g_arena = DpArena();
+    arena_release_slabs(g_arena);
+    for (auto &f : g_arena.free_list) f.clear();
+    g_arena.cls.clear(); g_arena.deferred.clear(); g_arena.defer = false;
 }
 
 struct PinnedBlk { void *p; size_t cap; bool used; };
@@ -168,6 +203,8 @@ int dp_init(int device) {
     if (device < 0 || device >= n) return dp_fail(DP_ERR_INVALID, "dp_init: device index out of range");
     DP_CUDA(cudaSetDevice(device));
     if (g_ctx.ready && g_ctx.device == device) return DP_OK;
+    // the stream and the arena of this thread's context belong to the device it was initialised on
+    if (g_ctx.ready) { cudaSetDevice(g_ctx.device); return dp_fail(DP_ERR_STATE, "dp_init: this thread's context is bound to another device; call dp_shutdown() first"); }
     cudaDeviceProp prop;
     DP_CUDA(cudaGetDeviceProperties(&prop, device));
     g_ctx.sm_count = prop.multiProcessorCount;

@@ -599,6 +599,7 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
     DP_CHECK(mles && products && out && n_mles > 0 && n_products > 0, DP_ERR_INVALID, "dp_sc_create: null/empty argument");
     DP_CHECK(max_nv != 0, DP_ERR_INVALID, "Attempt to prove a constant.");  // prover.rs:590-593
     DP_CHECK(max_nv <= 40, DP_ERR_INVALID, "dp_sc_create: max_num_variables too large");
+    for (u32 i = 0; i < n_mles; i++) DP_CHECK(mles[i] != nullptr, DP_ERR_INVALID, "dp_sc_create: null MLE");   // every entry is dereferenced below, referenced by a product or not
     u32 seen_deg = 0;
     for (u32 p = 0; p < n_products; p++) {
         const dp_sc_product &pr = products[p];
@@ -626,20 +627,25 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
     s->products.assign(products, products + n_products);
     for (auto &pr : s->products) { pr.coef[0] = gl_canon(pr.coef[0]); pr.coef[1] = gl_canon(pr.coef[1]); }
     s->gx = dp_grid_for(max_pairs, SC_THREADS, 6);   // upper bound of any round's grid (partials buffer)
-    int e = 0;
-    if ((e = dp_dev_alloc((void **)&s->d_descs, sizeof(ScProd) * n_products))) return e;
-    if ((e = dp_dev_alloc((void **)&s->d_partials, sizeof(gle) * SC_NACC * (size_t)s->gx * n_products))) return e;
-    if ((e = dp_dev_alloc((void **)&s->d_out, sizeof(gle) * SC_NACC * n_products))) return e;
-    if ((e = dp_dev_alloc((void **)&s->d_counters, sizeof(u32) * (n_products + 1)))) return e;
-    s->d_done = s->d_counters + n_products;
-    if ((e = dp_pinned_alloc((void **)&s->h_flag, 64))) return e;
-    *s->h_flag = 0;
-    if ((e = dp_dev_alloc((void **)&s->d_fin, sizeof(ScFin) * n_mles + sizeof(gle) * 2 * n_mles))) return e;
-    DP_CUDA(cudaMemsetAsync(s->d_counters, 0, sizeof(u32) * (n_products + 1), dp_ctx().stream));
-    if ((e = dp_pinned_alloc((void **)&s->h_descs, sizeof(ScProd) * n_products))) return e;
-    if ((e = dp_pinned_alloc((void **)&s->h_out, sizeof(gle) * std::max<size_t>(SC_NACC * n_products, n_mles)))) return e;
-    if ((e = dp_pinned_alloc((void **)&s->h_fin, sizeof(ScFin) * n_mles))) return e;
-    if ((e = dp_pinned_alloc((void **)&s->h_pairs, sizeof(gle) * 2 * n_mles))) return e;
+    // any failure below releases what was already allocated (dp_sc_destroy tolerates the partially built handle)
+    auto build = [&]() -> int {
+        int e = 0;
+        if ((e = dp_dev_alloc((void **)&s->d_descs, sizeof(ScProd) * n_products))) return e;
+        if ((e = dp_dev_alloc((void **)&s->d_partials, sizeof(gle) * SC_NACC * (size_t)s->gx * n_products))) return e;
+        if ((e = dp_dev_alloc((void **)&s->d_out, sizeof(gle) * SC_NACC * n_products))) return e;
+        if ((e = dp_dev_alloc((void **)&s->d_counters, sizeof(u32) * (n_products + 1)))) return e;
+        s->d_done = s->d_counters + n_products;
+        if ((e = dp_pinned_alloc((void **)&s->h_flag, 64))) return e;
+        *s->h_flag = 0;
+        if ((e = dp_dev_alloc((void **)&s->d_fin, sizeof(ScFin) * n_mles + sizeof(gle) * 2 * n_mles))) return e;
+        DP_CUDA(cudaMemsetAsync(s->d_counters, 0, sizeof(u32) * (n_products + 1), dp_ctx().stream));
+        if ((e = dp_pinned_alloc((void **)&s->h_descs, sizeof(ScProd) * n_products))) return e;
+        if ((e = dp_pinned_alloc((void **)&s->h_out, sizeof(gle) * std::max<size_t>(SC_NACC * n_products, n_mles)))) return e;
+        if ((e = dp_pinned_alloc((void **)&s->h_fin, sizeof(ScFin) * n_mles))) return e;
+        if ((e = dp_pinned_alloc((void **)&s->h_pairs, sizeof(gle) * 2 * n_mles))) return e;
+        return DP_OK;
+    };
+    if (int e = build()) { sc_free_all(s); delete s; return e; }
     *out = s;
     return DP_OK;
 }

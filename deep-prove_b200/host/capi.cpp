@@ -36,6 +36,21 @@ void dph_transcript_append_msg(void *t, const uint8_t *m, uint64_t n) { ((BasicT
 void dph_transcript_append_e(void *t, const uint64_t *e, uint64_t n) { for (uint64_t i = 0; i < n; i++) ((BasicTranscript *)t)->append_field_element_ext(Ext(e[2 * i], e[2 * i + 1])); }
 void dph_transcript_challenge(void *t, const char *label, uint64_t *out) { Ext c = ((BasicTranscript *)t)->get_and_append_challenge(label); out[0] = c.c0; out[1] = c.c1; }
 
+// VirtualPolynomial numbers MLEs by FIRST USE in the products (virtual_poly.rs:168-177), and get_mle_final_evaluations()
+// returns them in that order; the C entry points below report final evaluations in the CALLER's `mles` order instead.
+// remap[i] = position of caller MLE i in first-use order, UINT32_MAX when no product references it (its slot is zeroed).
+static std::vector<uint32_t> first_use_remap(const dp_sc_product *products, uint32_t n_products, uint32_t n_mles) {
+    std::vector<uint32_t> remap(n_mles, UINT32_MAX); uint32_t next = 0;
+    for (uint32_t p = 0; p < n_products; p++) for (uint32_t j = 0; j < products[p].n_idx; j++) { uint32_t i = products[p].idx[j]; if (i < n_mles && remap[i] == UINT32_MAX) remap[i] = next++; }
+    return remap;
+}
+static void write_finals(const ExtVec &fin, const std::vector<uint32_t> &remap, uint64_t *out_final) {
+    for (size_t i = 0; i < remap.size(); i++) {
+        Ext v = (remap[i] != UINT32_MAX && remap[i] < fin.size()) ? fin[remap[i]] : Ext::zero();
+        out_final[2 * i] = v.c0; out_final[2 * i + 1] = v.c1;
+    }
+}
+
 // IOPProverState::prove_parallel over device MLE handles with BasicTranscript::new(label) (or an
 // existing transcript when `transcript` is non-null).  out_msgs: nv x (max_deg+1) x E.
 int dph_sumcheck_prove_parallel(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *products, uint32_t n_products,
@@ -54,9 +69,7 @@ int dph_sumcheck_prove_parallel(dp_mle *const *mles, uint32_t n_mles, const dp_s
         for (uint32_t j = 0; j < products[p].n_idx; j++) l.push_back(views.at(products[p].idx[j]));
         vp.add_mle_list(l, Ext(products[p].coef[0], products[p].coef[1]));
     }
-    std::vector<uint32_t> remap(n_mles, UINT32_MAX);
-    for (size_t k = 0; k < vp.flattened_ml_extensions.size(); k++)
-        for (uint32_t i = 0; i < n_mles; i++) if (vp.flattened_ml_extensions[k].handle() == views[i].handle()) remap[i] = (uint32_t)k;
+    std::vector<uint32_t> remap = first_use_remap(products, n_products, n_mles);
     BasicTranscript local(label ? label : "");
     BasicTranscript &t = transcript ? *(BasicTranscript *)transcript : local;
     auto res = IOPProverState::prove_parallel(std::move(vp), t);
@@ -66,7 +79,7 @@ int dph_sumcheck_prove_parallel(dp_mle *const *mles, uint32_t n_mles, const dp_s
     size_t k = 0;
     for (auto &m : res.first.proofs) for (auto &e : m.evaluations) { out_msgs[2 * k] = e.c0; out_msgs[2 * k + 1] = e.c1; k++; }
     const ExtVec &fin = res.second.get_mle_final_evaluations();
-    for (uint32_t i = 0; i < n_mles; i++) if (remap[i] != UINT32_MAX && remap[i] < fin.size()) { out_final[2 * i] = fin[remap[i]].c0; out_final[2 * i + 1] = fin[remap[i]].c1; }
+    write_finals(fin, remap, out_final);
     return 0;
     DPH_CATCH
 }
@@ -259,13 +272,18 @@ extern "C" int dph_sumcheck_prove_sharded(uint32_t world, uint32_t rank, dp_mle 
     for (uint32_t p = 0; p < n_products; p++) { std::vector<DeviceMle> l; for (uint32_t j = 0; j < products[p].n_idx; j++) l.push_back(views.at(products[p].idx[j])); vp.add_mle_list(l, Ext(products[p].coef[0], products[p].coef[1])); }
     BasicTranscript tr(label);
     std::pair<IOPProof, IOPProverState> res;
-    if (shm_region) { ShmExchange ex(shm_region, world, rank); if (shm_seq) ex.seq = *shm_seq; res = IOPProverState::prove_sharded(std::move(vp), nv_total, ex, tr); if (shm_seq) *shm_seq = ex.seq; }
+    if (shm_region) {
+        ShmExchange ex(shm_region, world, rank); if (shm_seq) ex.seq = *shm_seq;
+        try { res = IOPProverState::prove_sharded(std::move(vp), nv_total, ex, tr); }
+        catch (...) { ex.poison(); if (shm_seq) *shm_seq = ex.seq; throw; }   // peers fail fast instead of spinning on this rank's slot
+        if (shm_seq) *shm_seq = ex.seq;
+    }
     else { if (!cb && world > 1) throw Error(DP_ERR_INVALID, "prove_sharded: no exchange given"); CallbackExchange ex(cb, user, world, rank); res = IOPProverState::prove_sharded(std::move(vp), nv_total, ex, tr); }
     for (size_t i = 0; i < res.first.point.size(); i++) { out_point[2 * i] = res.first.point[i].c0; out_point[2 * i + 1] = res.first.point[i].c1; }
     size_t k = 0;
     for (auto &m : res.first.proofs) for (auto &e : m.evaluations) { out_msgs[2 * k] = e.c0; out_msgs[2 * k + 1] = e.c1; k++; }
     const ExtVec &fin = res.second.get_mle_final_evaluations();
-    for (size_t i = 0; i < fin.size() && i < n_mles; i++) { out_final[2 * i] = fin[i].c0; out_final[2 * i + 1] = fin[i].c1; }
+    write_finals(fin, first_use_remap(products, n_products, n_mles), out_final);
     return 0;
     DPH_CATCH
 }
@@ -293,7 +311,7 @@ extern "C" int dph_sumcheck_prove_batch_polys(uint32_t T, dp_mle *const *mles, u
     size_t k = 0;
     for (auto &m : res.first.proofs) for (auto &e : m.evaluations) { out_msgs[2 * k] = e.c0; out_msgs[2 * k + 1] = e.c1; k++; }
     const ExtVec &fin = res.second.get_mle_final_evaluations();
-    for (size_t i = 0; i < fin.size() && i < n_mles; i++) { out_final[2 * i] = fin[i].c0; out_final[2 * i + 1] = fin[i].c1; }
+    write_finals(fin, first_use_remap(products, n_products, n_mles), out_final);
     return 0;
     DPH_CATCH
 }

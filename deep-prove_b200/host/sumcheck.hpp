@@ -12,6 +12,7 @@
 #include <memory>
 #include <algorithm>
 #include <map>
+#include <chrono>
 
 namespace dp {
 
@@ -70,18 +71,29 @@ struct ShmMailbox {
 };
 struct ShmExchange : Exchange {
     ShmMailbox *mb; u64 seq = 0;
+    static constexpr u64 POISON = ~0ULL; static constexpr int TIMEOUT_S = 60;
+    // called by a rank that is abandoning the proof (exception path): wakes every peer with an error instead of a hang
+    void poison() { for (int b = 0; b < 2; b++) __atomic_store_n(&mb->slots[rank][b].seq, POISON, __ATOMIC_RELEASE); }
     ShmExchange(void *region, size_t w, size_t r) : mb((ShmMailbox *)region) { world = w; rank = r; if (w > ShmMailbox::MAX_WORLD) throw std::runtime_error("ShmExchange: world too large"); }
     void allgather(const u64 *send, size_t n, u64 *recv) override {
         for (size_t off = 0; off < n || off == 0; off += ShmMailbox::PAYLOAD) {
             size_t m = std::min(n - off, ShmMailbox::PAYLOAD);
             seq++;
+            const auto t_start = std::chrono::steady_clock::now();
             ShmMailbox::Slot &mine = mb->slots[rank][seq & 1];
             for (size_t i = 0; i < m; i++) mine.payload[i] = send[off + i];
             mine.n = m;
             __atomic_store_n(&mine.seq, seq, __ATOMIC_RELEASE);
             for (size_t g = 0; g < world; g++) {
                 ShmMailbox::Slot &sl = mb->slots[g][seq & 1];
-                while (__atomic_load_n(&sl.seq, __ATOMIC_ACQUIRE) != seq) { __builtin_ia32_pause(); }
+                // bounded: a rank that died or threw mid-proof must not hang its peers forever (a failing rank posts POISON)
+                for (u64 spins = 0;; spins++) {
+                    u64 v = __atomic_load_n(&sl.seq, __ATOMIC_ACQUIRE);
+                    if (v == seq) break;
+                    if (v == POISON) throw std::runtime_error("ShmExchange: a peer rank aborted the exchange");
+                    if ((spins & 0xFFFF) == 0xFFFF && std::chrono::steady_clock::now() - t_start > std::chrono::seconds(TIMEOUT_S)) throw std::runtime_error("ShmExchange: timed out waiting for a peer rank");
+                    __builtin_ia32_pause();
+                }
                 for (size_t i = 0; i < m; i++) recv[g * n + off + i] = sl.payload[i];
             }
             if (n == 0) break;
@@ -93,7 +105,10 @@ struct CallbackExchange : Exchange {
     typedef int (*Fn)(void *user, const uint64_t *send, uint64_t n_words, uint64_t *recv);
     Fn fn; void *user;
     CallbackExchange(Fn f, void *u, size_t w, size_t r) : fn(f), user(u) { world = w; rank = r; }
-    void allgather(const u64 *send, size_t n, u64 *recv) override { if (fn(user, send, n, recv)) throw std::runtime_error("exchange callback failed"); }
+    void allgather(const u64 *send, size_t n, u64 *recv) override {
+        if (!fn) { if (world != 1) throw std::runtime_error("exchange callback missing"); for (size_t i = 0; i < n; i++) recv[i] = send[i]; return; }   // a world of one needs no exchange
+        if (fn(user, send, n, recv)) throw std::runtime_error("exchange callback failed");
+    }
 };
 
 struct VPAuxInfo { size_t max_degree = 0, max_num_variables = 0; };

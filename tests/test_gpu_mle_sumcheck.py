@@ -222,3 +222,26 @@ def test_resident_tail_is_released_when_the_prover_is_dropped(gpu):
     sc.destroy()                                           # must post the abort word and return
     m = gpu.Mle.upload(mles[0][0], False)
     assert (m.evaluate(ch) == O.evaluate(mles[0][0], False, ch)).all()   # the stream is usable again
+
+
+def test_final_evaluations_follow_caller_order(gpu):
+    """round-1 advisor finding: VirtualPolynomial numbers MLEs by first use (virtual_poly.rs:168-177); the C entry points must report
+    final evaluations in the CALLER's order even when the first product references [2, 0] and MLE 1 is referenced by nobody
+    (its slot is zero: it is not part of the VirtualPolynomial).  prove_parallel, prove_batch_polys and prove_sharded agree."""
+    import multigpu as mg
+    nv = 8
+    mles = [(O.splitmix_f(1, 1 << nv), False), (O.splitmix_e(2, 1 << nv), True), (O.splitmix_f(3, 1 << nv), False), (O.splitmix_f(4, 1 << nv), False)]
+    products = [((1, 0), [2, 0]), ((2, 1), [0, 3, 2])]
+    ep, em, ef = O.sumcheck_prove(mles, products, nv)
+    exp_fin = ef.copy(); exp_fin[1] = 0
+    for name, run in (("parallel", lambda dm: gpu.sumcheck_prove_parallel(dm, products, nv)),
+                      ("batch", lambda dm: gpu.sumcheck_prove_batch_polys(4, dm, products, nv)),
+                      ("sharded-native", lambda dm: mg.prove_sharded_native(dm, products, nv, 0, 1, allgather=lambda w: w[None, :])),
+                      ("sharded-python", lambda dm: mg.prove_sharded_device(dm, products, nv, 0, 1, None))):
+        point, msgs, fin = run(upload_all(gpu, mles))
+        assert (np.asarray(point) == ep).all() and (np.asarray(msgs) == em).all(), name
+        fin = np.asarray(fin)
+        for i in (0, 2, 3):
+            assert (fin[i] == exp_fin[i]).all(), (name, i)
+        if name != "sharded-python":      # the Python path folds every MLE it is given, referenced or not
+            assert (fin[1] == 0).all(), name
