@@ -21,6 +21,8 @@
 #include "powtab.cuh"
 #include "poseidon2.cuh"
 #include <algorithm>
+#include <atomic>
+#include <map>
 
 static constexpr u32 BF_RATE_LOG = 1;            // RSCodeDefaultSpec (rs.rs:192-214)
 static constexpr u32 BF_BASECODE_LOG = 7;
@@ -228,58 +230,64 @@ __global__ void __launch_bounds__(256) k_merkle_x8(const void *src, u64 n_out, u
         if (lane8 < 4) out[4 * h + (3 - lane8)] = s;
     }
 }
-// every remaining level of a small (sub)tree in ONE launch: a single block walks the levels with
-// __syncthreads() in between, so a 2^11-leaf witness commitment costs one launch instead of ten
+// Every remaining level of a tree whose current level has <= MK_SMALL hashes, in ONE launch (8 lanes per hash).  Each block owns
+// MK_SUB hashes of the first level -- one pass of its 32 lane groups -- and walks that subtree up to its root with a block barrier
+// per level; the last block to finish (ticket) folds the <= 64 subtree roots the same way.  Every level is a single pass, so the
+// tree costs depth x (one compress latency) and ONE launch instead of a launch per level (or a multi-level launch + a tail launch).
 struct LvlOff { u64 off[36]; };
-template <bool EXT>
-__global__ void __launch_bounds__(256) k_merkle_tail(const void *leaves, u64 n, u32 lg, u32 from_level, u64 *levels, LvlOff lo, const u64 *lvl0) {
-    for (u32 l = from_level; l < lg; l++) {
-        u64 nl = n >> (l + 1);
-        u64 *out = levels + 4 * lo.off[l];
-        const int lane8 = threadIdx.x & 7;
-        u64 rounds = (nl + (blockDim.x >> 3) - 1) / (blockDim.x >> 3);   // uniform trip count: shuffles need the full warp
-        for (u64 it = 0; it < rounds; it++) {
-            u64 i = it * (blockDim.x >> 3) + (threadIdx.x >> 3);
-            if (it * (blockDim.x >> 3) + ((threadIdx.x >> 5) << 2) >= nl) continue;   // whole warp idle (warp-uniform): skip the permutations
-            bool live = i < nl;
-            u64 xw = 0, yw = 0;
-            if (live && lane8 < 4) {
-                if (l == 1 && !lvl0) { xw = leaf_pair_word<EXT>(leaves, 2 * i, lane8); yw = leaf_pair_word<EXT>(leaves, 2 * i + 1, lane8); }
-                else { const u64 *in = (l == 1 ? lvl0 : levels + 4 * lo.off[l - 1]) + 8 * i; xw = in[lane8]; yw = in[4 + lane8]; }   // plain loads: written earlier in this launch
-            }
-            u64 s = p2x8_compress(xw, yw, lane8);
-            if (live && lane8 < 4) out[4 * i + (3 - lane8)] = s;
-        }
-        __syncthreads();
-    }
-}
-// several consecutive levels of a medium tree in ONE launch: every block owns 2^(nlev-1) hashes of the first level and
-// walks its subtree upwards (8 lanes per hash, __syncthreads between levels), writing every level it passes.
-// A 2^11-leaf witness tree costs 2 launches (this + the tail) instead of 6: the level-by-level latency chain is the same,
-// the launches (the scarce resource when 16 proofs are in flight) are not.
+static constexpr u32 MK_SUB = 32;
+static constexpr u64 MK_SMALL = 2048;
 template <bool EXT, bool FROM_LEAVES>
-__global__ void __launch_bounds__(256) k_merkle_multi(const void *src, u32 first_level, u32 nlev, u64 nl_first, u64 *levels, LvlOff lo) {
-    const int lane8 = threadIdx.x & 7; const u32 grp = threadIdx.x >> 3, ngrp = blockDim.x >> 3;
-    const u64 h0 = 1ULL << (nlev - 1);                         // hashes of the first level owned by this block
-    for (u32 k = 0; k < nlev; k++) {
-        const u32 l = first_level + k;
-        const u64 cnt = h0 >> k, base = (u64)blockIdx.x * cnt; // this block's hashes at level l
+__global__ void __launch_bounds__(256) k_merkle_small(const void *src, u32 first_level, u32 lg, u64 nl_first, u64 *levels, LvlOff lo, u32 *ticket) {
+    const int lane8 = threadIdx.x & 7; const u32 grp = threadIdx.x >> 3;
+    const u32 sub = (u32)(nl_first < MK_SUB ? nl_first : MK_SUB);
+    u32 l = first_level;
+    for (u32 k = 0; (sub >> k) >= 1 && l < lg; k++, l++) {
+        const u32 cnt = sub >> k; const u64 base = (u64)blockIdx.x * cnt;
         u64 *out = levels + 4 * lo.off[l];
-        const u64 rounds = (cnt + ngrp - 1) / ngrp;
-        for (u64 it = 0; it < rounds; it++) {
-            if (it * ngrp + ((threadIdx.x >> 5) << 2) >= cnt) continue;   // whole warp idle (warp-uniform)
-            const u64 j = it * ngrp + grp; const bool live = j < cnt; const u64 i = base + j;
+        if ((grp & ~3u) < cnt) {                       // warp-uniform (a warp holds 4 lane groups): idle warps skip the permutations
+            const bool live = grp < cnt; const u64 i = base + grp;
             u64 xw = 0, yw = 0;
             if (live && lane8 < 4) {
                 if (k == 0 && FROM_LEAVES) { xw = leaf_pair_word<EXT>(src, 2 * i, lane8); yw = leaf_pair_word<EXT>(src, 2 * i + 1, lane8); }
                 else { const u64 *in = (k == 0 ? (const u64 *)src : levels + 4 * lo.off[l - 1]) + 8 * i; xw = in[lane8]; yw = in[4 + lane8]; }
             }
-            u64 sres = p2x8_compress(xw, yw, lane8);
+            const u64 sres = p2x8_compress(xw, yw, lane8);
             if (live && lane8 < 4) out[4 * i + (3 - lane8)] = sres;
         }
         __syncthreads();
     }
-    (void)nl_first;
+    if (gridDim.x == 1) return;
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) { const u32 t = atomicAdd(ticket, 1u); last = (t == gridDim.x - 1); if (last) *ticket = 0; }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (u32 cnt = gridDim.x >> 1; cnt >= 1 && l < lg; cnt >>= 1, l++) {
+        u64 *out = levels + 4 * lo.off[l];
+        const u64 *in0 = levels + 4 * lo.off[l - 1];
+        for (u32 b = 0; b < cnt; b += 32) {
+            if (b + (grp & ~3u) >= cnt) continue;
+            const u32 j = b + grp; const bool live = j < cnt;
+            u64 xw = 0, yw = 0;
+            if (live && lane8 < 4) { xw = __ldcg(in0 + 8 * (u64)j + lane8); yw = __ldcg(in0 + 8 * (u64)j + 4 + lane8); }   // written by other blocks / an earlier pass
+            const u64 sres = p2x8_compress(xw, yw, lane8);
+            if (live && lane8 < 4) out[4 * (u64)j + (3 - lane8)] = sres;
+        }
+        __syncthreads();
+    }
+}
+// process-wide pool of zeroed ticket counters (each k_merkle_small launch takes the next one and leaves it zero again)
+static u32 *g_mk_tickets = nullptr; static std::atomic<u32> g_mk_next{0}; static constexpr u32 MK_TICKETS = 4096;
+static int mk_ticket(u32 **out) {
+    if (!g_mk_tickets) {
+        std::lock_guard<std::mutex> lk(g_bf_mu);
+        if (!g_mk_tickets) { u32 *p = nullptr; DP_CUDA(cudaMalloc((void **)&p, sizeof(u32) * MK_TICKETS)); DP_CUDA(cudaMemset(p, 0, sizeof(u32) * MK_TICKETS)); g_mk_tickets = p; }
+    }
+    *out = g_mk_tickets + (g_mk_next.fetch_add(1, std::memory_order_relaxed) % MK_TICKETS);
+    return DP_OK;
 }
 
 // batch_commit leaf level (merkle_tree.rs:286-312, util/hash.rs:30-41): digest_i = compress(hash(values of all m polynomials at
@@ -325,48 +333,39 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n, const u64
         if (ext) k_leafpair_root<true><<<1, 1, 0, c.stream>>>(leaves, t.levels); else k_leafpair_root<false><<<1, 1, 0, c.stream>>>(leaves, t.levels);
         DP_LAUNCHED(); t.root_dev = t.levels;
     } else {
-        const u64 TAIL = 32;   // levels with <= TAIL digests (one 1024-thread pass, 8 lanes per hash) are finished by one single-block launch
         u32 l = 1;
         LvlOff lo_all; memset(&lo_all, 0, sizeof lo_all);
         for (u32 k = 1; k < t.lg && k < 36; k++) lo_all.off[k] = t.lvl_off[k];
-        for (; l < t.lg && (n >> (l + 1)) > TAIL; l++) {
-            u64 nl = n >> (l + 1);
-            u32 a = 0; while ((1ULL << a) < nl) a++;
-            if (nl <= 32768 && a >= 8 && t.lg < 36) {   // medium level: this and the next nlev-1 levels in one launch
-                u32 nlev = std::min<u32>(7, a - 5);
-                DpProfScope prof("k_merkle_multi(poseidon2 compress)", (l == 1 ? nl * (ext ? 64 : 32) : nl * 64) + 2 * nl * 32);
-                unsigned g = (unsigned)(nl >> (nlev - 1));
+        for (; l < t.lg; l++) {
+            const u64 nl = n >> (l + 1);
+            const bool from_leaves = (l == 1 && !lvl0);
+            const u64 in_bytes = from_leaves ? nl * (ext ? 64 : 32) : nl * 64;
+            if (nl <= MK_SMALL && t.lg < 36) {   // this and every remaining level in one launch
+                DpProfScope prof("k_merkle_small(poseidon2 compress, all remaining levels)", in_bytes + (2 * nl - 1) * 32 * 2, 2 * (2 * nl - 1));
+                const unsigned g = (unsigned)((nl + MK_SUB - 1) / MK_SUB);
+                u32 *ticket = nullptr; if (int e = mk_ticket(&ticket)) return e;
                 const void *src = l == 1 ? (lvl0 ? (const void *)lvl0 : leaves) : (const void *)(t.levels + 4 * t.lvl_off[l - 1]);
-                if (l == 1 && !lvl0) { if (ext) k_merkle_multi<true, true><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all); else k_merkle_multi<false, true><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all); }
-                else k_merkle_multi<false, false><<<g, 256, 0, c.stream>>>(src, l, nlev, nl, t.levels, lo_all);
+                if (from_leaves) { if (ext) k_merkle_small<true, true><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket); else k_merkle_small<false, true><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket); }
+                else k_merkle_small<false, false><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket);
                 DP_LAUNCHED();
-                l += nlev - 1;
-                continue;
+                break;
             }
-            if (nl <= 32768) {   // too few hashes for one thread each: 8 lanes per hash
-                DpProfScope prof("k_merkle_x8(poseidon2 compress)", l == 1 ? nl * (ext ? 64 : 32) + nl * 32 : nl * 96);
+            if (nl <= 32768) {   // too few hashes for one thread each: 8 lanes per hash, one level per launch across the whole GPU
+                DpProfScope prof("k_merkle_x8(poseidon2 compress)", in_bytes + nl * 32, 2 * nl);
                 int g = dp_grid_for(nl * 8, 256, 8);
-                if (l == 1 && !lvl0) { if (ext) k_merkle_x8<true, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); else k_merkle_x8<false, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); }
+                if (from_leaves) { if (ext) k_merkle_x8<true, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); else k_merkle_x8<false, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); }
                 else k_merkle_x8<false, false><<<g, 256, 0, c.stream>>>(l == 1 ? lvl0 : t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
                 DP_LAUNCHED();
                 continue;
             }
-            DpProfScope prof("k_merkle(poseidon2 compress)", l == 1 ? nl * (ext ? 64 : 32) + nl * 32 : nl * 96);
+            DpProfScope prof("k_merkle(poseidon2 compress)", in_bytes + nl * 32, 2 * nl);
             const unsigned mgrid = (unsigned)std::min<u64>((nl + 127) / 128, 1u << 22);
-            if (l == 1 && !lvl0) {
+            if (from_leaves) {
                 // one hash per thread, many SHORT blocks (no persistent grid-stride blocks): with 16 proofs in flight the block
                 // scheduler can interleave other streams' latency-critical single-block kernels every few microseconds
                 if (ext) k_merkle_l1<true><<<mgrid, 128, 0, c.stream>>>(leaves, nl, t.levels);
                 else k_merkle_l1<false><<<mgrid, 128, 0, c.stream>>>(leaves, nl, t.levels);
             } else k_merkle_up<<<mgrid, 128, 0, c.stream>>>(l == 1 ? lvl0 : t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
-            DP_LAUNCHED();
-        }
-        if (l < t.lg) {
-            LvlOff lo; memset(&lo, 0, sizeof lo);
-            for (u32 k = 1; k < t.lg && k < 36; k++) lo.off[k] = t.lvl_off[k];
-            DpProfScope prof("k_merkle_tail(poseidon2 compress)", (n >> l) * 48);
-            if (ext) k_merkle_tail<true><<<1, 256, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo, lvl0);
-            else k_merkle_tail<false><<<1, 256, 0, c.stream>>>(leaves, n, t.lg, l, t.levels, lo, lvl0);
             DP_LAUNCHED();
         }
         t.root_dev = t.levels + 4 * t.lvl_off[t.lg - 1];
@@ -520,9 +519,21 @@ static int commit_enqueue(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **o
         } else {
         void *coef = nullptr;
         if (int e = dp_dev_alloc(&coef, esz * m)) return e;
-        u64 *stab = nullptr;
-        if (int e = dp_dev_alloc((void **)&stab, sizeof(u64) * 3 * 2048)) return e;
-        k_pow_table<<<24, 256, 0, c.stream>>>(shift, stab); DP_LAUNCHED();
+        // powers of the coset shift: one table per (full_log - nv), built once per process and kept (read-only afterwards)
+        const u64 *stab = nullptr;
+        {
+            static std::map<u64, const u64 *> shift_tabs;
+            std::lock_guard<std::mutex> lk(g_bf_mu);
+            auto it = shift_tabs.find(shift);
+            if (it == shift_tabs.end()) {
+                u64 *nt = nullptr;
+                DP_CUDA(cudaMalloc((void **)&nt, sizeof(u64) * 3 * 2048));
+                k_pow_table<<<24, 256, 0, c.stream>>>(shift, nt); DP_LAUNCHED();
+                DP_CUDA(cudaStreamSynchronize(c.stream));       // other host threads' streams may read it as soon as the map holds it
+                it = shift_tabs.emplace(shift, nt).first;
+            }
+            stab = it->second;
+        }
         PowTab st; st.t0 = stab; st.t1 = stab + 2048; st.t2 = stab + 4096;
         int g = dp_grid_for(m, 256, 8);
         if (poly->is_ext) {
@@ -539,7 +550,7 @@ static int commit_enqueue(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **o
             if (int e = run_levels<u64, 1>((u64 *)cm->codeword, n_log, 1, n_log)) return e;
         }
         DP_CUDA(cudaGetLastError());
-        dp_dev_free(coef); dp_dev_free(stab);
+        dp_dev_free(coef);
         }
     }
     if (with_tree) {

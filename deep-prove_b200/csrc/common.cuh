@@ -36,11 +36,11 @@ void dp_count_launch();
 #define DP_LAUNCHED() dp_count_launch()
 
 // optional per-kernel timing with CUDA events on the launch stream (bench.py's roofline leg)
-int dp_prof_begin(const char *name, u64 algorithmic_bytes);   // returns a token (or -1 when disabled)
+int dp_prof_begin(const char *name, u64 algorithmic_bytes, u64 units = 0);   // returns a token (or -1 when disabled); units: permutations / field ops
 void dp_prof_end(int token);
 struct DpProfScope {
     int tok;
-    DpProfScope(const char *name, u64 bytes) : tok(dp_prof_begin(name, bytes)) {}
+    DpProfScope(const char *name, u64 bytes, u64 units = 0) : tok(dp_prof_begin(name, bytes, units)) {}
     ~DpProfScope() { dp_prof_end(tok); }
 };
 

@@ -125,31 +125,36 @@ extern "C" void dp_hostprof_dump(void) {
 }
 
 // ---- per-kernel event timing --------------------------------------------------------------------
+// Process-wide switch and statistics, thread-local event lists: every proving thread brackets its launches with events
+// on ITS stream and folds the elapsed times into the shared table (dp_profile_flush at the end of a proof, or any
+// dp_profile_* call), so a batch of concurrent proofs yields the per-kernel breakdown of the concurrent region itself.
 #include <map>
-struct ProfRec { cudaEvent_t a, b; std::string name; u64 bytes; };
-struct ProfStat { u64 count = 0; double ms = 0; u64 bytes = 0; };
-static thread_local bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; std::string name; u64 bytes, units; };
+struct ProfStat { u64 count = 0; double ms = 0; u64 bytes = 0, units = 0; };
+static std::atomic<bool> g_prof_on{false};
 static thread_local std::vector<ProfRec> g_prof_pending;
 static thread_local std::vector<cudaEvent_t> g_prof_pool;
-static thread_local std::map<std::string, ProfStat> g_prof_stats;
+static std::map<std::string, ProfStat> g_prof_stats;
+static std::mutex g_prof_mu;
 static cudaEvent_t prof_event() {
     if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
-int dp_prof_begin(const char *name, u64 bytes) {
-    if (!g_prof_on) return -1;
-    ProfRec r; r.a = prof_event(); r.b = prof_event(); r.name = name; r.bytes = bytes;
+int dp_prof_begin(const char *name, u64 bytes, u64 units) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return -1;
+    ProfRec r; r.a = prof_event(); r.b = prof_event(); r.name = name; r.bytes = bytes; r.units = units;
     cudaEventRecord(r.a, g_ctx.stream);
     g_prof_pending.push_back(r);
     return (int)g_prof_pending.size() - 1;
 }
-void dp_prof_end(int tok) { if (tok >= 0) cudaEventRecord(g_prof_pending[tok].b, g_ctx.stream); }
+void dp_prof_end(int tok) { if (tok >= 0 && tok < (int)g_prof_pending.size()) cudaEventRecord(g_prof_pending[tok].b, g_ctx.stream); }
 static void prof_resolve() {
     if (g_prof_pending.empty()) return;
     cudaStreamSynchronize(g_ctx.stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto &r : g_prof_pending) {
         float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
-        ProfStat &s = g_prof_stats[r.name]; s.count++; s.ms += ms; s.bytes += r.bytes;
+        ProfStat &s = g_prof_stats[r.name]; s.count++; s.ms += ms; s.bytes += r.bytes; s.units += r.units;
         g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
     }
     g_prof_pending.clear();
@@ -160,28 +165,40 @@ extern "C" {
 int dp_profile_enable(int on) {
     std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
     prof_resolve();
-    g_prof_on = on != 0;
+    g_prof_on.store(on != 0);
+    return DP_OK;
+}
+int dp_profile_flush(void) {   // fold this thread's pending events into the process-wide table (cheap no-op when idle)
+    if (g_prof_pending.empty()) return DP_OK;
+    std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
+    prof_resolve();
     return DP_OK;
 }
 int dp_profile_reset(void) {
     std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
-    prof_resolve(); g_prof_stats.clear();
+    prof_resolve();
+    std::lock_guard<std::mutex> lk2(g_prof_mu);
+    g_prof_stats.clear();
     return DP_OK;
 }
-// Writes up to `cap` entries; returns the number of distinct kernel names seen.
-int dp_profile_read(char (*names)[64], uint64_t *counts, double *total_ms, uint64_t *bytes, int cap) {
+// Writes up to `cap` entries; returns the number of distinct kernel names seen.  `units` (may be NULL) = the kernel's own
+// work unit summed over launches: Poseidon2 permutations for the Merkle kernels, field operations for the sumcheck rounds.
+int dp_profile_read_ex(char (*names)[64], uint64_t *counts, double *total_ms, uint64_t *bytes, uint64_t *units, int cap) {
     std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
     prof_resolve();
+    std::lock_guard<std::mutex> lk2(g_prof_mu);
     int i = 0;
     for (auto &kv : g_prof_stats) {
         if (i < cap) {
             snprintf(names[i], 64, "%s", kv.first.c_str());
             counts[i] = kv.second.count; total_ms[i] = kv.second.ms; bytes[i] = kv.second.bytes;
+            if (units) units[i] = kv.second.units;
         }
         i++;
     }
     return i;
 }
+int dp_profile_read(char (*names)[64], uint64_t *counts, double *total_ms, uint64_t *bytes, int cap) { return dp_profile_read_ex(names, counts, total_ms, bytes, nullptr, cap); }
 
 const char *dp_last_error(void) { return g_err.c_str(); }
 const char *dp_version(void) { return "deepprove_b200 0.1 (sm_100a)"; }

@@ -61,6 +61,7 @@ __device__ __forceinline__ u64 gl_sub(u64 a, u64 b) {          // a, b < p  ->  
     return d - (u64)m;                                         // borrow: + p == - EPS (mod 2^64)
 }
 __device__ __forceinline__ u64 gl_reduce128(u64 lo, u64 hi) { return gl_canon_weak(gl_reduce128_weak(lo, hi)); }
+__device__ __forceinline__ u64 gl_mul_weak(u64 a, u64 b) { return gl_reduce128_weak(a * b, __umul64hi(a, b)); }   // any u64 inputs -> [0, 2^64)
 __device__ __forceinline__ void gl_mul_wide(u64 a, u64 b, u64 &lo, u64 &hi) { lo = a * b; hi = __umul64hi(a, b); }
 GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0ULL; }
 GL_HD u64 gl_dbl(u64 a) { return gl_add(a, a); }

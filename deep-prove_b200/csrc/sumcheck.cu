@@ -26,38 +26,47 @@ static constexpr int SC_THREADS = 256;
 
 __device__ __forceinline__ gle fold_b(u64 a, u64 b, gle r) { return e_add(e_mul_base(r, gl_sub(b, a)), e_from_base(a)); }
 __device__ __forceinline__ gle fold_e(gle a, gle b, gle r) { return e_add(a, e_mul(e_sub(b, a), r)); }
+// CG: L1-bypassing loads (ld.global.cg) -- the resident cluster kernel reads tables other CTAs of the cluster wrote a round earlier
+template <bool CG> __device__ __forceinline__ gle ldx_e(const gle *p) {
+    if (CG) { ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p)); return e_make(v.x, v.y); }
+    return ld_e(p);
+}
+template <bool CG> __device__ __forceinline__ ulonglong2 ldx_b2(const u64 *p) { return CG ? __ldcg(reinterpret_cast<const ulonglong2 *>(p)) : ld_b2(p); }
+template <bool CG> __device__ __forceinline__ u64 ldx_b(const u64 *p) { return CG ? __ldcg(p) : *p; }
 
+template <bool CG = false>
 __device__ __forceinline__ void sc_load_pair(const ScOp &op, u64 i, gle r, gle &lo, gle &hi) {
     switch (op.mode) {
     case OPM_B: {
-        ulonglong2 v = ld_b2((const u64 *)op.src + 2 * i);
+        ulonglong2 v = ldx_b2<CG>((const u64 *)op.src + 2 * i);
         lo = e_from_base(v.x); hi = e_from_base(v.y);
     } break;
     case OPM_E: {
         const gle *s = (const gle *)op.src + 2 * i;
-        lo = ld_e(s); hi = ld_e(s + 1);
+        lo = ldx_e<CG>(s); hi = ldx_e<CG>(s + 1);
     } break;
     case OPM_BF: {
         const u64 *s = (const u64 *)op.src + 4 * i;
-        ulonglong2 v0 = ld_b2(s), v1 = ld_b2(s + 2);
+        ulonglong2 v0 = ldx_b2<CG>(s), v1 = ldx_b2<CG>(s + 2);
         lo = fold_b(v0.x, v0.y, r); hi = fold_b(v1.x, v1.y, r);
         if (op.dst) { st_e(op.dst + 2 * i, lo); st_e(op.dst + 2 * i + 1, hi); }
     } break;
     default: {
         const gle *s = (const gle *)op.src + 4 * i;
-        gle f0 = ld_e(s), f1 = ld_e(s + 1), f2 = ld_e(s + 2), f3 = ld_e(s + 3);
+        gle f0 = ldx_e<CG>(s), f1 = ldx_e<CG>(s + 1), f2 = ldx_e<CG>(s + 2), f3 = ldx_e<CG>(s + 3);
         lo = fold_e(f0, f1, r); hi = fold_e(f2, f3, r);
         if (op.dst) { st_e(op.dst + 2 * i, lo); st_e(op.dst + 2 * i + 1, hi); }
     } break;
     }
 }
 // length-1 operands (sumcheck_macro/src/lib.rs:236-241): value at every evaluation point
+template <bool CG = false>
 __device__ __forceinline__ gle sc_load_const(const ScOp &op, gle r) {
     switch (op.mode) {
-    case OPM_B: return e_from_base(*(const u64 *)op.src);
-    case OPM_E: return ld_e((const gle *)op.src);
-    case OPM_BF: { ulonglong2 v = ld_b2((const u64 *)op.src); gle x = fold_b(v.x, v.y, r); if (op.dst) st_e(op.dst, x); return x; }
-    default: { const gle *s = (const gle *)op.src; gle x = fold_e(ld_e(s), ld_e(s + 1), r); if (op.dst) st_e(op.dst, x); return x; }
+    case OPM_B: return e_from_base(ldx_b<CG>((const u64 *)op.src));
+    case OPM_E: return ldx_e<CG>((const gle *)op.src);
+    case OPM_BF: { ulonglong2 v = ldx_b2<CG>((const u64 *)op.src); gle x = fold_b(v.x, v.y, r); if (op.dst) st_e(op.dst, x); return x; }
+    default: { const gle *s = (const gle *)op.src; gle x = fold_e(ldx_e<CG>(s), ldx_e<CG>(s + 1), r); if (op.dst) st_e(op.dst, x); return x; }
     }
 }
 
@@ -71,13 +80,15 @@ template <int N> __device__ __forceinline__ void acc_add_dyn_e(gle (&a)[N], int 
     for (int k = 0; k < N; k++) if (k == t) a[k] = e_add(a[k], p);
 }
 
-template <int D, bool BIG = false>
+// General body: any mix of operand modes, decided at run time per operand (mixed Base/Ext products, shared MLEs, constants).
+// The uniform-mode rounds that carry the bandwidth (all operands Base / all folding) take the lean kernels below instead.
+template <int D, bool CG = false>
 __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC], const u64 tid, const u64 stride) {
     if (pd.konst) {
         if (tid == 0) {
-            gle p = sc_load_const(pd.op[0], r);
+            gle p = sc_load_const<CG>(pd.op[0], r);
 #pragma unroll
-            for (int j = 1; j < D; j++) p = e_mul(p, sc_load_const(pd.op[j], r));
+            for (int j = 1; j < D; j++) p = e_mul(p, sc_load_const<CG>(pd.op[j], r));
 #pragma unroll
             for (int t = 0; t <= D; t++) acc[t] = p;
         }
@@ -88,36 +99,11 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
         u64 a[D + 1];
 #pragma unroll
         for (int t = 0; t <= D; t++) a[t] = 0;
-        if (BIG) {
-            // large rounds: two pairs in flight per thread (2 D independent 16-byte loads, two independent multiply
-            // chains) and the evaluation points fully unrolled -- the small-round body below trades that for footprint
-            for (u64 i = tid; i < pd.npairs; i += 2 * stride) {
-                const u64 i2 = i + stride; const bool two = i2 < pd.npairs;
-                u64 c0[D], s0[D], c1[D], s1[D];
-#pragma unroll
-                for (int j = 0; j < D; j++) {
-                    ulonglong2 v = ld_b2((const u64 *)pd.op[j].src + 2 * i);
-                    ulonglong2 w = two ? ld_b2((const u64 *)pd.op[j].src + 2 * i2) : make_ulonglong2(0, 0);
-                    c0[j] = v.x; s0[j] = gl_sub(v.y, v.x); c1[j] = w.x; s1[j] = gl_sub(w.y, w.x);
-                }
-#pragma unroll
-                for (int t = 0; t <= D; t++) {
-                    u64 p = c0[0], q = c1[0];
-#pragma unroll
-                    for (int j = 1; j < D; j++) { p = gl_mul(p, c0[j]); q = gl_mul(q, c1[j]); }
-                    a[t] = gl_add(a[t], gl_add(p, q));
-                    if (t < D) {
-#pragma unroll
-                        for (int j = 0; j < D; j++) { c0[j] = gl_add(c0[j], s0[j]); c1[j] = gl_add(c1[j], s1[j]); }
-                    }
-                }
-            }
-        } else
         for (u64 i = tid; i < pd.npairs; i += stride) {
             u64 cur[D], st[D];
 #pragma unroll
             for (int j = 0; j < D; j++) {
-                ulonglong2 v = ld_b2((const u64 *)pd.op[j].src + 2 * i);
+                ulonglong2 v = ldx_b2<CG>((const u64 *)pd.op[j].src + 2 * i);
                 cur[j] = v.x; st[j] = gl_sub(v.y, v.x);
             }
 #pragma unroll 1
@@ -139,39 +125,12 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
     gle a[D + 1];
 #pragma unroll
     for (int t = 0; t <= D; t++) a[t] = e_zero();
-    if (BIG) {
-        for (u64 i = tid; i < pd.npairs; i += 2 * stride) {
-            const u64 i2 = i + stride; const bool two = i2 < pd.npairs;
-            gle c0[D], s0[D], c1[D], s1[D];
-#pragma unroll
-            for (int j = 0; j < D; j++) {
-                gle lo, hi, lo2 = e_zero(), hi2 = e_zero();
-                sc_load_pair(pd.op[j], i, r, lo, hi);
-                if (two) sc_load_pair(pd.op[j], i2, r, lo2, hi2);
-                c0[j] = lo; s0[j] = e_sub(hi, lo); c1[j] = lo2; s1[j] = e_sub(hi2, lo2);
-            }
-#pragma unroll
-            for (int t = 0; t <= D; t++) {
-                gle p = c0[0], q = c1[0];
-#pragma unroll
-                for (int j = 1; j < D; j++) {
-                    if (pd.op[j].mode == OPM_B) { p = e_mul_base(p, c0[j].c0); q = e_mul_base(q, c1[j].c0); }
-                    else { p = e_mul(p, c0[j]); q = e_mul(q, c1[j]); }
-                }
-                a[t] = e_add(a[t], e_add(p, q));
-                if (t < D) {
-#pragma unroll
-                    for (int j = 0; j < D; j++) { c0[j] = e_add(c0[j], s0[j]); c1[j] = e_add(c1[j], s1[j]); }
-                }
-            }
-        }
-    } else
     for (u64 i = tid; i < pd.npairs; i += stride) {
         gle cur[D], st[D];
 #pragma unroll
         for (int j = 0; j < D; j++) {
             gle lo, hi;
-            sc_load_pair(pd.op[j], i, r, lo, hi);
+            sc_load_pair<CG>(pd.op[j], i, r, lo, hi);
             cur[j] = lo; st[j] = e_sub(hi, lo);
         }
 #pragma unroll 1
@@ -191,20 +150,80 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
 }
 
 // completion signal: `out` and `flag` live in mapped pinned host memory, so the round message reaches the host
-// with the kernel's own stores -- no D2H copy node, and the host spins on the flag instead of a stream sync
+// with the kernel's own stores -- no D2H copy node, and the host spins on the flag instead of a stream sync.
+// Called by ONE thread after a block barrier that follows the message stores of its block mates: its system-scope fence
+// orders those stores (observed through the barrier) before the flag.
 __device__ __forceinline__ void sc_signal(u64 seq, u64 *flag, u32 *done) {
     if (gridDim.y == 1) { __threadfence_system(); *(volatile u64 *)flag = seq; return; }
+    __threadfence_system();
     u32 t = atomicAdd(done, 1u);
     if (t == gridDim.y - 1) { *done = 0; __threadfence_system(); *(volatile u64 *)flag = seq; }
 }
 
-template <int DSEL, bool BIG = false>   // DSEL = 0: any degree (mixed-degree polynomials); 1..5: every product has this degree; BIG: large-round body
+// Block + grid reduction of the per-thread accumulators of one product (blockIdx.y) and hand-over to the host:
+// registers -> warp shuffles -> shared memory -> one partial per block; the last block to finish (ticket) adds the block
+// partials.  Field addition is exact, so the summation order is free and the message is bit-identical to the reference's fold.
+template <int BLOCK>
+__device__ __forceinline__ void sc_epilogue(const gle (&acc)[SC_NACC], const int nacc, gle *__restrict__ partials, u32 *__restrict__ counters,
+                                            gle *__restrict__ out, u64 seq, u64 *flag, u32 *done) {
+    __shared__ gle wsum[BLOCK / 32][SC_NACC];
+    __shared__ bool is_last;
+    for (int t = 0; t < nacc; t++) {
+        gle v = acc[t];
+        for (int d = 16; d > 0; d >>= 1) v = e_add(v, shfl_down_e(v, d));
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nacc) {
+        gle v = wsum[0][threadIdx.x];
+        for (int w = 1; w < BLOCK / 32; w++) v = e_add(v, wsum[w][threadIdx.x]);
+        if (gridDim.x == 1) st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, v);   // no cross-block stage
+        else st_e(partials + ((u64)blockIdx.y * gridDim.x + blockIdx.x) * SC_NACC + threadIdx.x, v);
+    }
+    if (gridDim.x == 1) { __syncthreads(); if (threadIdx.x == 0) sc_signal(seq, flag, done); return; }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 ticket = atomicAdd(counters + blockIdx.y, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last block of this product: all threads sum the block partials (independent L2 loads in flight), then the same
+    // shuffle + shared-memory tree as above
+    gle v[SC_NACC];
+#pragma unroll
+    for (int t = 0; t < SC_NACC; t++) v[t] = e_zero();
+    for (u32 x = threadIdx.x; x < gridDim.x; x += BLOCK) {
+        const gle *pp = partials + ((u64)blockIdx.y * gridDim.x + x) * SC_NACC;
+#pragma unroll
+        for (int t = 0; t < SC_NACC; t++) if (t < nacc) {
+            ulonglong2 q = __ldcg(reinterpret_cast<const ulonglong2 *>(pp + t));
+            v[t] = e_add(v[t], e_make(q.x, q.y));
+        }
+    }
+    __syncthreads();
+    for (int t = 0; t < nacc; t++) {
+        gle w = v[t];
+        for (int d = 16; d > 0; d >>= 1) w = e_add(w, shfl_down_e(w, d));
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < nacc) {
+        gle w = wsum[0][threadIdx.x];
+        for (int k = 1; k < BLOCK / 32; k++) w = e_add(w, wsum[k][threadIdx.x]);
+        st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, w);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { counters[blockIdx.y] = 0; sc_signal(seq, flag, done); }
+}
+
+template <int DSEL>   // DSEL = 0: any degree (mixed-degree polynomials); 1..5: every product has this degree
 __global__ void __launch_bounds__(SC_THREADS)
 k_sc_round(const ScProd *__restrict__ descs, const __grid_constant__ ScProd desc0, gle r, gle *__restrict__ partials, u32 *__restrict__ counters,
            gle *__restrict__ out, u64 seq, u64 *flag, u32 *done) {
     __shared__ ScProd pd;
-    __shared__ gle wsum[SC_THREADS / 32][SC_NACC];
-    __shared__ bool is_last;
     {
         // single-product polynomials carry their descriptor in the kernel parameters; otherwise `descs` is mapped host
         // memory for small grids (no copy node) and a device copy for large ones (hundreds of CTAs each fetching 216 B
@@ -218,7 +237,7 @@ k_sc_round(const ScProd *__restrict__ descs, const __grid_constant__ ScProd desc
 #pragma unroll
     for (int t = 0; t < SC_NACC; t++) acc[t] = e_zero();
     const u64 gtid = (u64)blockIdx.x * blockDim.x + threadIdx.x, gstride = (u64)gridDim.x * blockDim.x;
-    if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL, BIG>(pd, r, acc, gtid, gstride);
+    if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL>(pd, r, acc, gtid, gstride);
     else switch (pd.d) {
     case 1: sc_body<1>(pd, r, acc, gtid, gstride); break;
     case 2: sc_body<2>(pd, r, acc, gtid, gstride); break;
@@ -226,116 +245,195 @@ k_sc_round(const ScProd *__restrict__ descs, const __grid_constant__ ScProd desc
     case 4: sc_body<4>(pd, r, acc, gtid, gstride); break;
     default: sc_body<5>(pd, r, acc, gtid, gstride); break;
     }
-    const int nacc = pd.d + 1;
-    // warp shuffle reduction, then across warps through shared memory
-    for (int t = 0; t < nacc; t++) {
-        gle v = acc[t];
-        for (int d = 16; d > 0; d >>= 1) v = e_add(v, shfl_down_e(v, d));
-        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < nacc) {
-        gle v = wsum[0][threadIdx.x];
-        for (int w = 1; w < SC_THREADS / 32; w++) v = e_add(v, wsum[w][threadIdx.x]);
-        if (gridDim.x == 1) { st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, v); __threadfence_system(); }   // no cross-block stage
-        else st_e(partials + ((u64)blockIdx.y * gridDim.x + blockIdx.x) * SC_NACC + threadIdx.x, v);
-    }
-    if (gridDim.x == 1) { __syncthreads(); if (threadIdx.x == 0) sc_signal(seq, flag, done); return; }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u32 ticket = atomicAdd(counters + blockIdx.y, 1u);
-        is_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // last block of this product: all 256 threads sum the block partials (independent L2 loads in
-    // flight), then the same shuffle + shared-memory tree as above
+    sc_epilogue<SC_THREADS>(acc, (int)pd.d + 1, partials, counters, out, seq, flag, done);
+}
+
+// ---- lean kernels for the rounds that move the bytes ---------------------------------------------------------------------
+// Every operand of every product is in the SAME storage mode this round (all Base: the first round of a Base polynomial; all
+// folding Base->Ext: its second round; all folding Ext->Ext: every later round; all Ext: the first round of an Ext polynomial)
+// and every product has the same degree D in {2, 3}.  The mode and the degree are compile-time, so the body is a straight line
+// of loads and multiply chains (no per-operand switch, 64-118 registers instead of 122 for everything), the products of the
+// last multiplication are accumulated UNREDUCED in 192-bit (Base) / 2 x 160-bit (Ext) sums and reduced once per thread and
+// evaluation point, and the block shape follows the measurements in tools/kbench.cu: Base rounds 256 threads x 2 pairs in
+// flight (HBM-bound: 1.9 TB/s at nu = 20), folding rounds 128 threads x 1 pair (issue-bound: 122 instructions per E x E).
+struct acc192 { u64 lo, hi; u32 top; };                     // lo + hi 2^64 + top 2^128
+__device__ __forceinline__ void acc_mac(acc192 &a, u64 x, u64 y) {
+    u64 pl = x * y, ph = __umul64hi(x, y);
+    asm("{\n\tadd.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;\n\t}" : "+l"(a.lo), "+l"(a.hi), "+r"(a.top) : "l"(pl), "l"(ph));
+}
+__device__ __forceinline__ u64 acc_reduce(const acc192 &a) { return gl_reduce160(a.lo, a.hi, a.top); }
+struct eacc { acc192 c0, c1; };
+__device__ __forceinline__ void eacc_mac(eacc &a, gle x, gle y) {   // a += x * y   (c1 = x0 y1 + x1 y0; c0 = x0 y0 + 7 w, w = weak(x1 y1))
+    acc_mac(a.c1, x.c0, y.c1); acc_mac(a.c1, x.c1, y.c0);
+    u64 w = gl_reduce128_weak(x.c1 * y.c1, __umul64hi(x.c1, y.c1));
+    acc_mac(a.c0, x.c0, y.c0); acc_mac(a.c0, w, 7ULL);
+}
+template <int MODE> struct ScLeanShape { static constexpr int BLOCK = MODE == OPM_B ? 256 : 128, MINB = 4, PPT = MODE == OPM_B ? 2 : 1; };
+
+template <int D, int MODE>
+__global__ void __launch_bounds__(ScLeanShape<MODE>::BLOCK, ScLeanShape<MODE>::MINB)
+k_sc_lean(const ScProd *__restrict__ descs, const __grid_constant__ ScProd desc0, gle r, gle *__restrict__ partials, u32 *__restrict__ counters,
+          gle *__restrict__ out, u64 seq, u64 *flag, u32 *done) {
+    constexpr int BLOCK = ScLeanShape<MODE>::BLOCK, PPT = ScLeanShape<MODE>::PPT;
+    __shared__ ScProd pd;
     {
-        gle v[SC_NACC];
+        const u64 *s = descs ? (const u64 *)(descs + blockIdx.y) : (const u64 *)&desc0;
+        u64 *d = (u64 *)&pd;
+        for (int k = threadIdx.x; k < (int)(sizeof(ScProd) / 8); k += BLOCK) d[k] = s[k];
+    }
+    __syncthreads();
+    const u64 npairs = pd.npairs, T = (u64)gridDim.x * BLOCK;
+    gle acc[SC_NACC];
 #pragma unroll
-        for (int t = 0; t < SC_NACC; t++) v[t] = e_zero();
-        for (u32 x = threadIdx.x; x < gridDim.x; x += blockDim.x) {
-            const gle *pp = partials + ((u64)blockIdx.y * gridDim.x + x) * SC_NACC;
+    for (int t = 0; t < SC_NACC; t++) acc[t] = e_zero();
+    if (MODE == OPM_B) {
+        acc192 a[D + 1];
 #pragma unroll
-            for (int t = 0; t < SC_NACC; t++) if (t < nacc) {
-                ulonglong2 q = __ldcg(reinterpret_cast<const ulonglong2 *>(pp + t));
-                v[t] = e_add(v[t], e_make(q.x, q.y));
+        for (int t = 0; t <= D; t++) { a[t].lo = 0; a[t].hi = 0; a[t].top = 0; }
+        const u64 *src[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) src[j] = (const u64 *)pd.op[j].src;
+        for (u64 i0 = (u64)blockIdx.x * BLOCK + threadIdx.x; i0 < npairs; i0 += PPT * T) {
+            ulonglong2 v[PPT][D];
+#pragma unroll
+            for (int p = 0; p < PPT; p++) {
+                u64 i = i0 + p * T; const bool ok = i < npairs; if (!ok) i = i0;
+#pragma unroll
+                for (int j = 0; j < D; j++) v[p][j] = ld_b2(src[j] + 2 * i);
+                if (!ok) v[p][0] = make_ulonglong2(0, 0);          // a zero factor contributes nothing at every point
+            }
+#pragma unroll
+            for (int p = 0; p < PPT; p++) {
+                u64 c[D], s[D];
+#pragma unroll
+                for (int j = 0; j < D; j++) { c[j] = v[p][j].x; s[j] = gl_sub(v[p][j].y, v[p][j].x); }
+#pragma unroll
+                for (int t = 0; t <= D; t++) {
+                    u64 q = c[0];
+#pragma unroll
+                    for (int j = 1; j < D - 1; j++) q = gl_mul_weak(q, c[j]);
+                    acc_mac(a[t], q, c[D - 1]);
+                    if (t < D) {
+#pragma unroll
+                        for (int j = 0; j < D; j++) c[j] = gl_add(c[j], s[j]);
+                    }
+                }
             }
         }
-        __syncthreads();
-        for (int t = 0; t < nacc; t++) {
-            gle w = v[t];
-            for (int d = 16; d > 0; d >>= 1) w = e_add(w, shfl_down_e(w, d));
-            if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = w;
+#pragma unroll
+        for (int t = 0; t <= D; t++) acc[t] = e_from_base(acc_reduce(a[t]));
+    } else {
+        eacc a[D + 1];
+#pragma unroll
+        for (int t = 0; t <= D; t++) { a[t].c0 = {0, 0, 0}; a[t].c1 = {0, 0, 0}; }
+        for (u64 i = (u64)blockIdx.x * BLOCK + threadIdx.x; i < npairs; i += T) {
+            gle c[D], s[D];
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                gle lo, hi;
+                if (MODE == OPM_BF) {
+                    const u64 *q = (const u64 *)pd.op[j].src + 4 * i;
+                    ulonglong2 v0 = ld_b2(q), v1 = ld_b2(q + 2);
+                    lo = fold_b(v0.x, v0.y, r); hi = fold_b(v1.x, v1.y, r);
+                    if (pd.op[j].dst) { st_e(pd.op[j].dst + 2 * i, lo); st_e(pd.op[j].dst + 2 * i + 1, hi); }
+                } else if (MODE == OPM_EF) {
+                    const gle *q = (const gle *)pd.op[j].src + 4 * i;
+                    gle f0 = ld_e(q), f1 = ld_e(q + 1), f2 = ld_e(q + 2), f3 = ld_e(q + 3);
+                    lo = fold_e(f0, f1, r); hi = fold_e(f2, f3, r);
+                    if (pd.op[j].dst) { st_e(pd.op[j].dst + 2 * i, lo); st_e(pd.op[j].dst + 2 * i + 1, hi); }
+                } else {
+                    const gle *q = (const gle *)pd.op[j].src + 2 * i;
+                    lo = ld_e(q); hi = ld_e(q + 1);
+                }
+                c[j] = lo; s[j] = e_sub(hi, lo);
+            }
+#pragma unroll
+            for (int t = 0; t <= D; t++) {
+                gle q = c[0];
+#pragma unroll
+                for (int j = 1; j < D - 1; j++) q = e_mul(q, c[j]);
+                eacc_mac(a[t], q, c[D - 1]);
+                if (t < D) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) c[j] = e_add(c[j], s[j]);
+                }
+            }
         }
-        __syncthreads();
-        if (threadIdx.x < nacc) {
-            gle w = wsum[0][threadIdx.x];
-            for (int k = 1; k < SC_THREADS / 32; k++) w = e_add(w, wsum[k][threadIdx.x]);
-            st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, w);
-            __threadfence_system();
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { counters[blockIdx.y] = 0; sc_signal(seq, flag, done); }
+#pragma unroll
+        for (int t = 0; t <= D; t++) acc[t] = e_make(acc_reduce(a[t].c0), acc_reduce(a[t].c1));
     }
+    sc_epilogue<BLOCK>(acc, D + 1, partials, counters, out, seq, flag, done);
 }
 
 
-// ---- resident tail: every remaining round of a small sumcheck in ONE single-block launch -------------------
-// Once the tables are small (<= SC_TAIL_PAIRS pairs, i.e. the last 8 rounds) a round is pure latency: launch + two-stage reduction + the
-// host's Fiat-Shamir.  The tail kernel stays resident instead: it writes each round message to mapped host memory,
-// raises the flag, and polls a mapped mailbox for the next challenge (one thread, one PCIe read in flight), so a
-// round costs the block-local work + two PCIe hops + the host sponge -- no launch, no cross-block stage.
-// The per-round bookkeeping the host does for k_sc_round (operand order, fold destinations, ping-pong buffers) is
-// replayed by thread 0 in shared memory.  The kernel cannot hang: the poll gives up after SC_TAIL_TIMEOUT cycles or
-// when the host posts the abort value.  Opt-in per handle (dp_sc_set_resident_tail): the caller promises not to
-// wait on other work in the same stream between rounds.
-static constexpr u32 SC_TAIL_MAXM = 96, SC_TAIL_MAXP = 48;
-static constexpr u64 SC_TAIL_PAIRS = 128;
-static constexpr long long SC_TAIL_TIMEOUT = 6000000000LL;   // ~3 s at 1.9 GHz
+// ---- resident rounds: every remaining round of a small sumcheck in ONE launch of a thread-block CLUSTER --------------------
+// Once the tables are small a round is pure latency: launch + two-stage reduction + the host's Fiat-Shamir.  This kernel stays
+// resident instead: up to 8 CTAs (one cluster: co-scheduled by the hardware, hardware barrier between them) split the pairs of
+// every product by warp, the warp partials meet in a small global scratch, CTA 0 adds them, writes the round message to mapped
+// host memory, raises the flag and polls a mapped mailbox for the next challenge (one thread, one PCIe read in flight); the
+// challenge reaches the other CTAs through the cluster barrier.  A round costs the compute of its widest product spread over
+// <= 2048 threads + two cluster barriers (~0.2 us each) + two PCIe hops + the host sponge -- no launch, no cross-block ticket
+// stage, no cold instruction cache.  The folded tables ping-pong in HBM/L2 (the cluster barrier orders the stores; readers use
+// L1-bypassing loads).  The per-round bookkeeping the host does for k_sc_round (operand order, fold destinations, ping-pong
+// buffers) is replayed identically by every CTA in shared memory.  The kernel cannot hang: the poll gives up after
+// SC_RES_TIMEOUT cycles or when the host posts the abort value, and the other CTAs only ever wait on the cluster barrier.
+// Opt-in per handle (dp_sc_set_resident_tail): the caller promises not to wait on other work in the same stream between rounds.
+static constexpr u32 SC_RES_MAXM = 96, SC_RES_MAXP = 48, SC_RES_MAXCTA = 8;
+static constexpr u64 SC_RES_WORK = 16384;                    // resident once sum over products of (pairs this round) <= this
+static constexpr long long SC_RES_TIMEOUT = 6000000000LL;   // ~3 s at 1.9 GHz
 static constexpr u64 SC_TAIL_ABORT = ~0ULL, SC_TAIL_FAILED = ~0ULL - 1;
 struct TMle { const void *cur; gle *work; u64 len, len0; u32 is_ext, where; };
 struct TProd { u32 n_idx; u32 idx[5]; };
-struct ScTail { u32 n_mles, n_products, n_rounds, first_has_challenge; TMle m[SC_TAIL_MAXM]; TProd p[SC_TAIL_MAXP]; };
+struct ScTail { u32 n_mles, n_products, n_rounds, first_has_challenge; TMle m[SC_RES_MAXM]; TProd p[SC_RES_MAXP]; };
+
+__device__ __forceinline__ u32 cl_rank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ u32 cl_size() { u32 r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// all threads of all CTAs of the cluster; release/acquire at cluster scope (global stores before it are visible after it)
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 template <int DSEL>
 __global__ void __launch_bounds__(SC_THREADS)
-k_sc_tail(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pairs /* mapped */, volatile u64 *flag /* mapped */,
-          volatile u64 *chal /* mapped: [seq, c0, c1] */, u64 seq0) {
-    __shared__ TMle sm[SC_TAIL_MAXM];
-    __shared__ TProd sp[SC_TAIL_MAXP];
-    __shared__ ScProd spd[SC_TAIL_MAXP];
-    __shared__ gle *sdst[SC_TAIL_MAXM];
-    __shared__ unsigned char sfold[SC_TAIL_MAXM], swriter[SC_TAIL_MAXM];
-    __shared__ gle s_r;
-    __shared__ u32 s_status;
+k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pairs /* mapped */, volatile u64 *flag /* mapped */,
+         volatile u64 *chal /* mapped: [seq, c0, c1] */, u64 seq0, gle *xpart /* device: warp partials */, u64 *xctl /* device: [status, c0, c1] */) {
+    __shared__ TMle sm[SC_RES_MAXM];
+    __shared__ TProd sp[SC_RES_MAXP];
+    __shared__ ScProd spd[SC_RES_MAXP];
+    __shared__ gle *sdst[SC_RES_MAXM];
+    __shared__ unsigned char sfold[SC_RES_MAXM], swriter[SC_RES_MAXM];
     const u32 nm = cfg->n_mles, np = cfg->n_products, nr = cfg->n_rounds;
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = SC_THREADS / 32;
+    const u32 rank = cl_rank(), ncta = cl_size();
+    const u32 W = ncta * nwarps, gw = rank * nwarps + warp;              // warps of the cluster, this warp's index
+    // pairs of a product are split over G warps (G a power of two, np * G <= W); with more products than warps a warp takes several
+    u32 G = 1; while (np * (G << 1) <= W) G <<= 1;
     for (u32 i = threadIdx.x; i < nm; i += blockDim.x) { sm[i] = cfg->m[i]; swriter[i] = 0xff; }
     for (u32 i = threadIdx.x; i < np; i += blockDim.x) sp[i] = cfg->p[i];
-    if (threadIdx.x == 0) { s_r = r0; s_status = 0; }
     __syncthreads();
     // the product that writes an MLE's folded table is the first one referencing it (the host's `written` rule); static
     if (threadIdx.x == 0) for (u32 p = 0; p < np; p++) for (u32 j = 0; j < sp[p].n_idx; j++) { u32 mi = sp[p].idx[j]; if (swriter[mi] == 0xff) swriter[mi] = (unsigned char)p; }
     __syncthreads();
+    gle r = r0;
     for (u32 k = 0; k < nr; k++) {
         const u64 seq = seq0 + k;
         if (k > 0) {   // wait for the host's challenge for this round
-            if (threadIdx.x == 0) {
-                long long t0 = clock64(); u64 v;
+            if (rank == 0 && threadIdx.x == 0) {
+                long long t0 = clock64(); u64 v, status = 0;
                 while ((v = chal[0]) != seq) {
-                    if (v == SC_TAIL_ABORT) { s_status = 1; break; }
-                    if (clock64() - t0 > SC_TAIL_TIMEOUT) { s_status = 2; break; }
+                    if (v == SC_TAIL_ABORT) { status = 1; break; }
+                    if (clock64() - t0 > SC_RES_TIMEOUT) { status = 2; break; }
                 }
-                if (!s_status) { __threadfence_system(); s_r = e_make(chal[1], chal[2]); }
+                u64 c0 = 0, c1 = 0;
+                if (!status) { __threadfence_system(); c0 = chal[1]; c1 = chal[2]; }
+                __stcg(xctl + 1, c0); __stcg(xctl + 2, c1); __stcg(xctl, status);
             }
-            __syncthreads();
-            if (s_status) { if (threadIdx.x == 0 && s_status == 2) { __threadfence_system(); *flag = SC_TAIL_FAILED; } return; }
+            cl_sync();
+            const u64 status = __ldcg(xctl);
+            if (status) { if (rank == 0 && threadIdx.x == 0 && status == 2) { __threadfence_system(); *flag = SC_TAIL_FAILED; } return; }   // uniform over the cluster
+            r = e_make(__ldcg(xctl + 1), __ldcg(xctl + 2));
         }
         const bool fold = (k > 0) || cfg->first_has_challenge;
-        const gle r = s_r;
         for (u32 i = threadIdx.x; i < nm; i += blockDim.x) {
             bool f = fold && sm[i].len > 1;
             sfold[i] = f;
@@ -361,43 +459,55 @@ k_sc_tail(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pa
             pd.d = pr.n_idx; pd.allbase = allbase; pd.konst = newlen == 1; pd.npairs = newlen >> 1;
         }
         __syncthreads();
-        for (u32 p = warp; p < np; p += nwarps) {   // one warp per product: tables have <= SC_TAIL_PAIRS pairs here
+        // work: slot (p, s) = sub-slice s of product p's pairs; warp gw owns slots gw, gw + W, ...
+        for (u32 slot = gw; slot < np * G; slot += W) {
+            const u32 p = slot / G, s = slot % G;
             const ScProd &pd = spd[p];
             gle acc[SC_NACC];
 #pragma unroll
             for (int t = 0; t < SC_NACC; t++) acc[t] = e_zero();
-            if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL>(pd, r, acc, lane, 32);
+            const u64 first = (u64)s * 32 + lane, stride = (u64)G * 32;
+            if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL, true>(pd, r, acc, first, stride);
             else switch (pd.d) {
-            case 1: sc_body<1>(pd, r, acc, lane, 32); break;
-            case 2: sc_body<2>(pd, r, acc, lane, 32); break;
-            case 3: sc_body<3>(pd, r, acc, lane, 32); break;
-            case 4: sc_body<4>(pd, r, acc, lane, 32); break;
-            default: sc_body<5>(pd, r, acc, lane, 32); break;
+            case 1: sc_body<1, true>(pd, r, acc, first, stride); break;
+            case 2: sc_body<2, true>(pd, r, acc, first, stride); break;
+            case 3: sc_body<3, true>(pd, r, acc, first, stride); break;
+            case 4: sc_body<4, true>(pd, r, acc, first, stride); break;
+            default: sc_body<5, true>(pd, r, acc, first, stride); break;
             }
             const int nacc = pd.d + 1;
             for (int t = 0; t < nacc; t++) {
                 gle v = acc[t];
                 for (int d = 16; d > 0; d >>= 1) v = e_add(v, shfl_down_e(v, d));
-                if (lane == 0) st_e(out + (u64)p * SC_NACC + t, v);
+                if (lane == 0) __stcg(reinterpret_cast<ulonglong2 *>(xpart + (u64)slot * SC_NACC + t), make_ulonglong2(v.c0, v.c1));
             }
         }
-        __syncthreads();
+        cl_sync();                                             // warp partials and folded tables of every CTA are visible
         for (u32 i = threadIdx.x; i < nm; i += blockDim.x) if (sfold[i]) {
             TMle &m = sm[i];
             m.cur = sdst[i]; m.where = (sdst[i] == m.work) ? 1 : 2; m.len >>= 1; m.is_ext = 1;
         }
         __syncthreads();
-        if (k == nr - 1) {   // last round: hand the (<= 2)-entry tables over with the message (k_sc_gather's job)
-            for (u32 i = threadIdx.x; i < nm; i += blockDim.x) {
-                const TMle &m = sm[i]; gle a, b;
-                if (m.is_ext) { a = ld_e((const gle *)m.cur); b = m.len > 1 ? ld_e((const gle *)m.cur + 1) : a; }
-                else { a = e_from_base(*(const u64 *)m.cur); b = m.len > 1 ? e_from_base(*((const u64 *)m.cur + 1)) : a; }
-                st_e(pairs + 2 * i, a); st_e(pairs + 2 * i + 1, b);
+        if (rank == 0) {
+            for (u32 x = threadIdx.x; x < np * SC_NACC; x += blockDim.x) {
+                const u32 p = x / SC_NACC, t = x % SC_NACC;
+                if (t > spd[p].d) continue;
+                gle v = e_zero();
+                for (u32 s = 0; s < G; s++) { ulonglong2 q = __ldcg(reinterpret_cast<const ulonglong2 *>(xpart + ((u64)p * G + s) * SC_NACC + t)); v = e_add(v, e_make(q.x, q.y)); }
+                st_e(out + (u64)p * SC_NACC + t, v);
             }
+            if (k == nr - 1) {   // last round: hand the (<= 2)-entry tables over with the message (k_sc_gather's job)
+                for (u32 i = threadIdx.x; i < nm; i += blockDim.x) {
+                    const TMle &m = sm[i]; gle a, b;
+                    if (m.is_ext) { a = ldx_e<true>((const gle *)m.cur); b = m.len > 1 ? ldx_e<true>((const gle *)m.cur + 1) : a; }
+                    else { a = e_from_base(ldx_b<true>((const u64 *)m.cur)); b = m.len > 1 ? e_from_base(ldx_b<true>((const u64 *)m.cur + 1)) : a; }
+                    st_e(pairs + 2 * i, a); st_e(pairs + 2 * i + 1, b);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { __threadfence_system(); *flag = seq; }
         }
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) { *flag = seq; }
+        // CTAs other than 0 run ahead to the next cluster barrier; xpart is not rewritten before it (the work phase follows it)
     }
 }
 
@@ -445,6 +555,8 @@ struct dp_sc {
     int gx = 1;
     bool tail_enabled = false, tail_active = false; u32 tail_last_round = 0;
     ScTail *h_tail = nullptr; u64 *h_chal = nullptr;
+    gle *d_xpart = nullptr; u64 *d_xctl = nullptr;        // resident cluster kernel: warp partials, [status, c0, c1]
+    u64 last_ops = 0;
     std::vector<gle> challenges;
     u64 last_bytes = 0;
 };
@@ -469,6 +581,7 @@ static gle sc_extrapolate(const gle *evals, u32 n, u64 at) {
 static int sc_free_all(dp_sc *s) {
     for (auto &m : s->mles) if (m.work) { dp_dev_free(m.work); m.work = nullptr; }
     dp_dev_free(s->d_descs); dp_dev_free(s->d_partials); dp_dev_free(s->d_out); dp_dev_free(s->d_counters); dp_dev_free(s->d_fin);
+    dp_dev_free(s->d_xpart); dp_dev_free(s->d_xctl);
     dp_pinned_free(s->h_flag);
     dp_pinned_free(s->h_descs); dp_pinned_free(s->h_out); dp_pinned_free(s->h_fin); dp_pinned_free(s->h_pairs);
     dp_pinned_free(s->h_tail); dp_pinned_free(s->h_chal);
@@ -529,18 +642,28 @@ static bool sc_tail_supported() {
     return supported;
 }
 
-// ---- resident tail, host side ----
+// ---- resident rounds, host side ----
+// total pair-items of the round that would start the resident kernel (every product's pairs after this round's fold)
+static u64 sc_round_work(const dp_sc *s, bool fold) {
+    u64 work = 0;
+    for (auto &pr : s->products) { const ScMle &m = s->mles[pr.idx[0]]; u64 nl = (fold && m.len > 1) ? m.len >> 1 : m.len; work += std::max<u64>(nl >> 1, 1); }
+    return work;
+}
 static bool sc_tail_eligible(const dp_sc *s, bool fold) {
-    if (!s->tail_enabled || s->n_mles > SC_TAIL_MAXM || s->n_products > SC_TAIL_MAXP || s->max_nv - s->round < 2) return false;
+    if (!s->tail_enabled || s->n_mles > SC_RES_MAXM || s->n_products > SC_RES_MAXP || s->max_nv - s->round < 2) return false;
     std::vector<char> used(s->n_mles, 0);
     for (auto &pr : s->products) for (u32 j = 0; j < pr.n_idx; j++) used[pr.idx[j]] = 1;
-    for (u32 i = 0; i < s->n_mles; i++) {
-        const ScMle &m = s->mles[i];
-        if (!used[i] && m.len > 1) return false;
-        u64 nl = (fold && m.len > 1) ? m.len >> 1 : m.len;
-        if ((nl >> 1) > SC_TAIL_PAIRS) return false;
-    }
-    return true;
+    for (u32 i = 0; i < s->n_mles; i++) if (!used[i] && s->mles[i].len > 1) return false;
+    return sc_round_work(s, fold) <= SC_RES_WORK;
+}
+template <int DSEL>
+static cudaError_t sc_res_launch(u32 ncta, cudaStream_t st, const ScTail *cfg, gle r, gle *out, gle *pairs, u64 *flag, u64 *chal, u64 seq, gle *xpart, u64 *xctl) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(ncta); lc.blockDim = dim3(SC_THREADS); lc.dynamicSmemBytes = 0; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, k_sc_res<DSEL>, cfg, r, out, pairs, (volatile u64 *)flag, (volatile u64 *)chal, seq, xpart, xctl);
 }
 // one round served by the resident kernel (started here on its first round)
 static int sc_tail_round(dp_sc *s, gle r, bool fold, uint64_t *out_evals) {
@@ -559,18 +682,26 @@ static int sc_tail_round(dp_sc *s, gle r, bool fold, uint64_t *out_evals) {
         }
         for (u32 p = 0; p < s->n_products; p++) { t.p[p].n_idx = s->products[p].n_idx; for (u32 j = 0; j < 5; j++) t.p[p].idx[j] = s->products[p].idx[j]; }
         s->h_chal[0] = 0;
+        // cluster size by the first resident round's work: ~512 pair-items per CTA, a power of two <= 8 (portable cluster size)
+        const u64 work = sc_round_work(s, fold);
+        u32 ncta = 1; while (ncta < SC_RES_MAXCTA && (u64)ncta * 512 < work) ncta <<= 1;
+        const u32 slots = std::max<u32>(ncta * (SC_THREADS / 32), s->n_products);
+        if (!s->d_xpart && (e = dp_dev_alloc((void **)&s->d_xpart, sizeof(gle) * SC_NACC * slots))) return e;
+        if (!s->d_xctl && (e = dp_dev_alloc((void **)&s->d_xctl, 64))) return e;
         u32 dsel = s->products[0].n_idx;
         for (auto &pr : s->products) if (pr.n_idx != dsel) dsel = 0;
-        DpProfScope prof("k_sc_tail(resident rounds; time includes the host's Fiat-Shamir between rounds)", 0);
+        DpProfScope prof("k_sc_res(resident cluster rounds; time includes the host's Fiat-Shamir between rounds)", 0);
+        cudaError_t ce;
         switch (dsel) {
-        case 1: k_sc_tail<1><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
-        case 2: k_sc_tail<2><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
-        case 3: k_sc_tail<3><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
-        case 4: k_sc_tail<4><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
-        case 5: k_sc_tail<5><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
-        default: k_sc_tail<0><<<1, SC_THREADS, 0, st>>>(s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq); break;
+        case 1: ce = sc_res_launch<1>(ncta, st, s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq, s->d_xpart, s->d_xctl); break;
+        case 2: ce = sc_res_launch<2>(ncta, st, s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq, s->d_xpart, s->d_xctl); break;
+        case 3: ce = sc_res_launch<3>(ncta, st, s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq, s->d_xpart, s->d_xctl); break;
+        case 4: ce = sc_res_launch<4>(ncta, st, s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq, s->d_xpart, s->d_xctl); break;
+        case 5: ce = sc_res_launch<5>(ncta, st, s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq, s->d_xpart, s->d_xctl); break;
+        default: ce = sc_res_launch<0>(ncta, st, s->h_tail, r, s->h_out, s->h_pairs, s->h_flag, s->h_chal, s->seq, s->d_xpart, s->d_xctl); break;
         }
         DP_LAUNCHED();
+        DP_CUDA(ce);
         DP_CUDA(cudaGetLastError());
         s->tail_active = true;
     } else {   // post the challenge: value first, then the sequence number the kernel polls
@@ -584,7 +715,7 @@ static int sc_tail_round(dp_sc *s, gle r, bool fold, uint64_t *out_evals) {
         DP_HOST_TIMED("dp_sc_round(sync wait)");
         volatile u64 *f = s->h_flag; u64 spins = 0; bool ok = false;
         while (!(ok = (*f == s->seq))) { if (*f == SC_TAIL_FAILED) break; if (++spins > (1ULL << 30)) break; __builtin_ia32_pause(); }
-        if (!ok) { s->h_chal[0] = SC_TAIL_ABORT; cudaStreamSynchronize(st); DP_CHECK(false, DP_ERR_CUDA, "dp_sc_round: resident tail kernel timed out waiting for a challenge (other work queued in the same stream?)"); }
+        if (!ok) { s->h_chal[0] = SC_TAIL_ABORT; cudaStreamSynchronize(st); DP_CHECK(false, DP_ERR_CUDA, "dp_sc_round: resident kernel timed out waiting for a challenge (other work queued in the same stream?)"); }
     }
     if (s->round == s->max_nv) s->have_pairs = true;   // written to mapped memory before the flag
     return sc_glue(s, out_evals);
@@ -626,7 +757,7 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
     }
     s->products.assign(products, products + n_products);
     for (auto &pr : s->products) { pr.coef[0] = gl_canon(pr.coef[0]); pr.coef[1] = gl_canon(pr.coef[1]); }
-    s->gx = dp_grid_for(max_pairs, SC_THREADS, 6);   // upper bound of any round's grid (partials buffer)
+    s->gx = (int)std::min<u64>((max_pairs + 127) / 128 + 1, (u64)dp_ctx().sm_count * 16);   // upper bound of any round's grid (partials buffer): lean folding rounds use 128-thread blocks, one pair per thread
     // any failure below releases what was already allocated (dp_sc_destroy tolerates the partially built handle)
     auto build = [&]() -> int {
         int e = 0;
@@ -716,13 +847,31 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
         d.npairs = newlen >> 1;
         round_pairs = std::max<u64>(round_pairs, d.npairs);
     }
-    // grid sized for THIS round: 2 pairs per thread minimum so small rounds run in a single block
-    // large rounds: ~4 pairs per thread (two in flight at a time, see sc_body<D, BIG>) amortise the per-thread reduction;
-    // small rounds keep 2 pairs per thread so they fit one block
-    int gx = round_pairs > 8192 ? dp_grid_for(round_pairs, SC_THREADS, 6)
-                                : std::min(s->gx, dp_grid_for(round_pairs <= 256 ? round_pairs : (round_pairs + 1) / 2, SC_THREADS, 4));
+    // uniform rounds take the lean kernels: every operand of every product in the same mode, one degree in {2, 3}, no constants
+    u32 dsel = s->products[0].n_idx;
+    for (auto &pr : s->products) if (pr.n_idx != dsel) dsel = 0;
+    int lean_mode = -1;
+    if ((dsel == 2 || dsel == 3) && round_pairs > 2048) {
+        lean_mode = (int)s->h_descs[0].op[0].mode;
+        for (u32 p = 0; p < s->n_products && lean_mode >= 0; p++) {
+            const ScProd &d = s->h_descs[p];
+            if (d.konst) lean_mode = -1;
+            for (u32 j = 0; j < d.d && lean_mode >= 0; j++) if ((int)d.op[j].mode != lean_mode) lean_mode = -1;
+        }
+    }
+    // field operations of this round in the operand field: (d-1)(d+1) mul + (5d+4) add per pair, + (1 mul + 2 add) for
+    // each of the 2 elements a folding operand contributes to a pair
+    u64 ops = 0;
+    for (u32 p = 0; p < s->n_products; p++) { const ScProd &d = s->h_descs[p]; u64 nf = 0; for (u32 j = 0; j < d.d; j++) if (d.op[j].mode >= OPM_BF) nf++; ops += d.npairs * ((u64)(d.d - 1) * (d.d + 1) + 5 * d.d + 4 + 6 * nf); }
+    s->last_ops = ops;
+    // grid sized for THIS round.  lean: Base rounds 256 threads x 2 pairs in flight, folding rounds 128 threads x 1 pair (tools/kbench.cu);
+    // general kernel: 2 pairs per thread minimum so small rounds run in a single block
+    int gx;
+    if (lean_mode == (int)OPM_B) gx = (int)std::min<u64>((round_pairs + 511) / 512, (u64)dp_ctx().sm_count * 4);
+    else if (lean_mode >= 0) gx = (int)std::min<u64>((round_pairs + 127) / 128, (u64)s->gx);
+    else gx = round_pairs > 8192 ? std::min(s->gx, dp_grid_for(round_pairs, SC_THREADS, 6))
+                                 : std::min(s->gx, dp_grid_for(round_pairs <= 256 ? round_pairs : (round_pairs + 1) / 2, SC_THREADS, 4));
     cudaStream_t st = dp_ctx().stream;
-    // descriptors are read by the kernel straight from mapped pinned memory (no H2D copy node)
     // MLEs no product references still have to be folded (cannot happen through add_mle_list, kept for safety)
     for (u32 i = 0; i < s->n_mles; i++) if (folds[i] && !written[i]) {
         ScMle &m = s->mles[i];
@@ -730,26 +879,32 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
     }
     dim3 grid((unsigned)gx, s->n_products);
     {
-        DpProfScope prof(fold ? "k_sc_round(fold+msg)" : "k_sc_round(msg)", bytes);
+        DpProfScope prof(lean_mode == (int)OPM_B ? "k_sc_lean(msg, Base)" : lean_mode == (int)OPM_E ? "k_sc_lean(msg, Ext)" : lean_mode == (int)OPM_BF ? "k_sc_lean(fold Base->Ext + msg)"
+                         : lean_mode == (int)OPM_EF ? "k_sc_lean(fold Ext + msg)" : fold ? "k_sc_round(fold+msg)" : "k_sc_round(msg)", bytes, ops);
         s->seq++;
         const ScProd *descs_arg = s->h_descs;                 // mapped pinned memory: no copy node on the latency path
         if (s->n_products == 1) descs_arg = nullptr;          // descriptor travels in the kernel parameters
         else if ((u64)gx * s->n_products > 32) { DP_CUDA(cudaMemcpyAsync(s->d_descs, s->h_descs, sizeof(ScProd) * s->n_products, cudaMemcpyHostToDevice, st)); descs_arg = s->d_descs; }
-        u32 dsel = s->products[0].n_idx;
-        for (auto &pr : s->products) if (pr.n_idx != dsel) dsel = 0;
-        bool big = round_pairs > 8192 && (dsel == 2 || dsel == 3);
-        for (u32 p = 0; p < s->n_products; p++) if (!s->h_descs[p].allbase) big = false;   // measured: the two-in-flight body only pays off for the all-Base first round (122 regs on the Ext path)
-        if (big && dsel == 2) k_sc_round<2, true><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done);
-        else if (big) k_sc_round<3, true><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done);
-        else
+#define SC_ARGS descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done
+#define SC_LEAN(D, M) k_sc_lean<D, M><<<grid, ScLeanShape<M>::BLOCK, 0, st>>>(SC_ARGS)
+        if (lean_mode >= 0) {
+            switch (lean_mode * 4 + (int)dsel) {
+            case OPM_B * 4 + 2: SC_LEAN(2, OPM_B); break;   case OPM_B * 4 + 3: SC_LEAN(3, OPM_B); break;
+            case OPM_E * 4 + 2: SC_LEAN(2, OPM_E); break;   case OPM_E * 4 + 3: SC_LEAN(3, OPM_E); break;
+            case OPM_BF * 4 + 2: SC_LEAN(2, OPM_BF); break; case OPM_BF * 4 + 3: SC_LEAN(3, OPM_BF); break;
+            case OPM_EF * 4 + 2: SC_LEAN(2, OPM_EF); break; default: SC_LEAN(3, OPM_EF); break;
+            }
+        } else
         switch (dsel) {   // one small kernel per uniform degree keeps the instruction footprint low
-        case 1: k_sc_round<1><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
-        case 2: k_sc_round<2><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
-        case 3: k_sc_round<3><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
-        case 4: k_sc_round<4><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
-        case 5: k_sc_round<5><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
-        default: k_sc_round<0><<<grid, SC_THREADS, 0, st>>>(descs_arg, s->h_descs[0], r, s->d_partials, s->d_counters, s->h_out, s->seq, s->h_flag, s->d_done); break;
+        case 1: k_sc_round<1><<<grid, SC_THREADS, 0, st>>>(SC_ARGS); break;
+        case 2: k_sc_round<2><<<grid, SC_THREADS, 0, st>>>(SC_ARGS); break;
+        case 3: k_sc_round<3><<<grid, SC_THREADS, 0, st>>>(SC_ARGS); break;
+        case 4: k_sc_round<4><<<grid, SC_THREADS, 0, st>>>(SC_ARGS); break;
+        case 5: k_sc_round<5><<<grid, SC_THREADS, 0, st>>>(SC_ARGS); break;
+        default: k_sc_round<0><<<grid, SC_THREADS, 0, st>>>(SC_ARGS); break;
         }
+#undef SC_LEAN
+#undef SC_ARGS
         DP_LAUNCHED();
     }
     DP_CUDA(cudaGetLastError());

@@ -218,6 +218,7 @@ struct ZkPool {
                     if (bytes.empty()) throw dp::Error(DP_ERR_STATE, "empty proof");
                 } else { dp::zkml::Proof p = prover.prove(h->trace_input, h->trace, &h->trace_conv); (void)p; }
             } catch (const std::exception &e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.what(); }
+            dp_profile_flush();   // per-kernel timing of the concurrent region (no-op unless dp_profile_enable(1))
             { std::lock_guard<std::mutex> lk(mu); inflight--; if (pending == 0 && inflight == 0) done_cv.notify_all(); }
         }
         if (inited) { dp_synchronize(); if (getenv("DP_HOST_PROF")) { static std::atomic<int> once{0}; if (!once.exchange(1)) dp_hostprof_dump(); } dp_shutdown(); }

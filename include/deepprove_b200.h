@@ -52,6 +52,11 @@ uint64_t dp_kernel_launches(void);       /* number of kernels this library launc
 int dp_profile_enable(int on);
 int dp_profile_reset(void);
 int dp_profile_read(char (*names)[64], uint64_t *counts, double *total_ms, uint64_t *bytes, int cap);
+/* the same plus each kernel's own work unit summed over launches (Poseidon2 permutations for the Merkle kernels, field
+ * operations for the sumcheck rounds; 0 elsewhere).  The table is process-wide: proving threads fold their launches in with
+ * dp_profile_flush(), so a batch of concurrent proofs is profiled as it runs. */
+int dp_profile_read_ex(char (*names)[64], uint64_t *counts, double *total_ms, uint64_t *bytes, uint64_t *units, int cap);
+int dp_profile_flush(void);
 
 /* ---- multilinear_extensions ------------------------------------------------------------------ */
 /* DenseMultilinearExtension::from_evaluations_vec / _ext_vec (mle.rs:183-260): copy host -> HBM. */

@@ -20,7 +20,9 @@ static thread_local std::string g_err;
 extern "C" {
 
 const char *dpo_last_error() { return g_err.c_str(); }
-int dpo_num_threads() { return (int)std::thread::hardware_concurrency(); }
+int dpo_num_threads() { return (int)std::thread::hardware_concurrency(); }   // hardware threads of the host
+int dpo_get_threads() { return (int)dpo_threads(); }                           // threads a par_for may use right now
+void dpo_set_threads(int n) { dpo_threads_var().store(n > 0 ? (unsigned)n : 1u); }
 
 // ---- field (vectorised, for the device-arithmetic tests) ----
 void dpo_f_binop(int op, const u64 *a, const u64 *b, u64 n, u64 *out) {

@@ -12,6 +12,7 @@
 #include <vector>
 #include <cassert>
 #include <thread>
+#include <atomic>
 #include <functional>
 #include <algorithm>
 
@@ -80,11 +81,13 @@ static inline E e_pow(E a, u64 e) {
     return r;
 }
 
-// par_for: plain std::thread fork-join over [0, n) (no OpenMP in this image).  Threads = DPO_THREADS env or all cores.
-static inline unsigned dpo_threads() {
-    static unsigned n = [] { const char *e = getenv("DPO_THREADS"); unsigned v = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency(); return v ? v : 1u; }();
+// par_for: plain std::thread fork-join over [0, n) (no OpenMP in this image).  Threads = DPO_THREADS env or all hardware
+// threads; dpo_set_threads() changes it at run time (bench.py's throughput mode: k concurrent proofs x T/k threads each).
+inline std::atomic<unsigned> &dpo_threads_var() {
+    static std::atomic<unsigned> n{[] { const char *e = getenv("DPO_THREADS"); unsigned v = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency(); return v ? v : 1u; }()};
     return n;
 }
+static inline unsigned dpo_threads() { return dpo_threads_var().load(std::memory_order_relaxed); }
 template <class F> static inline void par_for(size_t n, size_t min_per_thread, F f) {
     unsigned T = dpo_threads();
     if (T <= 1 || n < 2 * min_per_thread) { f((size_t)0, n); return; }
