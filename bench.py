@@ -602,7 +602,7 @@ def run_gpu_workload(env, wl, K, W, full):
     if rows:
         # the resident tail spans many rounds and its event time includes the host's Fiat-Shamir between them: listed, but never
         # the "dominant kernel"
-        cand = {k: r for k, r in rows.items() if not k.startswith("k_sc_tail") and not k.startswith("k_sc_prove")} or rows
+        cand = {k: r for k, r in rows.items() if not k.startswith("k_sc_res")} or rows
         name = max(cand, key=lambda k: cand[k]["ms"])
         r = rows[name]
         all_ms = sum(x["ms"] for x in cand.values())

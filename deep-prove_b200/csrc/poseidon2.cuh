@@ -65,28 +65,27 @@ __device__ __forceinline__ void p2_mds_light(u64 (&s)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; i++) s[i] = ww_fold(ww_add(ww_add(n[i], n[i]), n[i ^ 4]));
 }
+// One loop over the 30 rounds with a warp-uniform branch between the two round shapes: ONE copy of the external-round body
+// (8 S-boxes + linear layer, ~900 instructions) instead of two, so the whole permutation is ~1.3 k instructions of code.  The
+// level kernels were stalled on instruction fetch more than on anything else (ncu r02b: no_instruction 3.7 stall cycles per
+// issued instruction with the ~4 k-instruction version: two permutations x three round loops inlined back to back).
 __device__ __forceinline__ void p2_permute(u64 (&s)[8]) {      // weak in, weak out
     p2_mds_light(s);
 #pragma unroll 1
-    for (int r = 0; r < 4; r++) {
+    for (int r = 0; r < 30; r++) {
+        if (r < 4 || r >= 26) {
+            const u64 *rc = r < 4 ? c_p2_ext[0][r] : c_p2_ext[1][r - 26];
 #pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = p2_pow7(w_add_canon(s[i], c_p2_ext[0][r][i]));
-        p2_mds_light(s);
-    }
-#pragma unroll 1
-    for (int r = 0; r < 22; r++) {
-        s[0] = p2_pow7(w_add_canon(s[0], c_p2_int[r]));
-        p2w sum = ww(s[0]);
+            for (int i = 0; i < 8; i++) s[i] = p2_pow7(w_add_canon(s[i], rc[i]));
+            p2_mds_light(s);
+        } else {
+            s[0] = p2_pow7(w_add_canon(s[0], c_p2_int[r - 4]));
+            p2w sum = ww(s[0]);
 #pragma unroll
-        for (int i = 1; i < 8; i++) sum = ww_addu(sum, s[i]);
+            for (int i = 1; i < 8; i++) sum = ww_addu(sum, s[i]);
 #pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = w_mul_add(s[i], c_p2_diag[i], sum);
-    }
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[i] = p2_pow7(w_add_canon(s[i], c_p2_ext[1][r][i]));
-        p2_mds_light(s);
+            for (int i = 0; i < 8; i++) s[i] = w_mul_add(s[i], c_p2_diag[i], sum);
+        }
     }
 }
 
@@ -140,12 +139,14 @@ __device__ __forceinline__ u64 p2x8_compress(u64 xw, u64 yw, int lane8) {
     return gl_canon_weak(s);    // lane k holds state[k]; digest = [s3, s2, s1, s0]
 }
 
-// compress(x, y): absorb x -> permute -> overwrite rate with y -> permute -> [s3, s2, s1, s0]
+// compress(x, y): absorb x -> permute -> overwrite rate with y -> permute -> [s3, s2, s1, s0]  (one copy of the permutation: see above)
 __device__ __forceinline__ void p2_compress(const u64 x[4], const u64 y[4], u64 out[4]) {
     u64 s[8] = {x[0], x[1], x[2], x[3], 0, 0, 0, 0};
-    p2_permute(s);
-    s[0] = y[0]; s[1] = y[1]; s[2] = y[2]; s[3] = y[3];
-    p2_permute(s);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        if (half) { s[0] = y[0]; s[1] = y[1]; s[2] = y[2]; s[3] = y[3]; }
+        p2_permute(s);
+    }
     out[0] = gl_canon_weak(s[3]); out[1] = gl_canon_weak(s[2]); out[2] = gl_canon_weak(s[1]); out[3] = gl_canon_weak(s[0]);
 }
 

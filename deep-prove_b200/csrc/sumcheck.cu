@@ -70,6 +70,34 @@ __device__ __forceinline__ gle sc_load_const(const ScOp &op, gle r) {
     }
 }
 
+// Out-of-line copies for the latency-bound kernels (general rounds, resident rounds).  Their cost is instruction FETCH, not issue:
+// with every E x E (122 instructions) and every operand's 4-way mode switch inlined, k_sc_res<3> was 6.9 k instructions (110 KB) and
+// k_sc_round<3> 5.5 k -- more than the SM's instruction cache holds -- so a round of a few hundred pairs spent most of its ~15 us
+// refetching its own code from L2.  One shared copy of each costs a call (~20 cycles) per use and keeps the round loop resident.
+__device__ __noinline__ gle e_mul_ni(gle a, gle b) { return e_mul(a, b); }
+struct gle2 { gle lo, hi; };
+template <bool CG>
+__device__ __noinline__ gle2 sc_load_pair_ni(const ScOp *op, u64 i, gle r) {
+    gle2 o;
+    switch (op->mode) {
+    case OPM_B: { ulonglong2 v = ldx_b2<CG>((const u64 *)op->src + 2 * i); o.lo = e_from_base(v.x); o.hi = e_from_base(v.y); } break;
+    case OPM_E: { const gle *s = (const gle *)op->src + 2 * i; o.lo = ldx_e<CG>(s); o.hi = ldx_e<CG>(s + 1); } break;
+    case OPM_BF: {
+        const u64 *s = (const u64 *)op->src + 4 * i;
+        ulonglong2 v0 = ldx_b2<CG>(s), v1 = ldx_b2<CG>(s + 2);
+        o.lo = fold_b(v0.x, v0.y, r); o.hi = fold_b(v1.x, v1.y, r);
+        if (op->dst) { st_e(op->dst + 2 * i, o.lo); st_e(op->dst + 2 * i + 1, o.hi); }
+    } break;
+    default: {
+        const gle *s = (const gle *)op->src + 4 * i;
+        gle f0 = ldx_e<CG>(s), f1 = ldx_e<CG>(s + 1), f2 = ldx_e<CG>(s + 2), f3 = ldx_e<CG>(s + 3);
+        o.lo = e_add(f0, e_mul_ni(e_sub(f1, f0), r)); o.hi = e_add(f2, e_mul_ni(e_sub(f3, f2), r));
+        if (op->dst) { st_e(op->dst + 2 * i, o.lo); st_e(op->dst + 2 * i + 1, o.hi); }
+    } break;
+    }
+    return o;
+}
+
 // a[t] += p with a runtime t but register-resident a[] (predicated select, no local memory)
 template <int N> __device__ __forceinline__ void acc_add_dyn(u64 (&a)[N], int t, u64 p) {
 #pragma unroll
@@ -88,7 +116,7 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
         if (tid == 0) {
             gle p = sc_load_const<CG>(pd.op[0], r);
 #pragma unroll
-            for (int j = 1; j < D; j++) p = e_mul(p, sc_load_const<CG>(pd.op[j], r));
+            for (int j = 1; j < D; j++) p = e_mul_ni(p, sc_load_const<CG>(pd.op[j], r));
 #pragma unroll
             for (int t = 0; t <= D; t++) acc[t] = p;
         }
@@ -129,15 +157,14 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
         gle cur[D], st[D];
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            gle lo, hi;
-            sc_load_pair<CG>(pd.op[j], i, r, lo, hi);
-            cur[j] = lo; st[j] = e_sub(hi, lo);
+            const gle2 v = sc_load_pair_ni<CG>(&pd.op[j], i, r);
+            cur[j] = v.lo; st[j] = e_sub(v.hi, v.lo);
         }
 #pragma unroll 1
         for (int t = 0; t <= D; t++) {
             gle p = cur[0];
 #pragma unroll
-            for (int j = 1; j < D; j++) p = (pd.op[j].mode == OPM_B) ? e_mul_base(p, cur[j].c0) : e_mul(p, cur[j]);
+            for (int j = 1; j < D; j++) p = (pd.op[j].mode == OPM_B) ? e_mul_base(p, cur[j].c0) : e_mul_ni(p, cur[j]);
             acc_add_dyn_e<D + 1>(a, t, p);
             if (t < D) {
 #pragma unroll
@@ -163,24 +190,39 @@ __device__ __forceinline__ void sc_signal(u64 seq, u64 *flag, u32 *done) {
 // Block + grid reduction of the per-thread accumulators of one product (blockIdx.y) and hand-over to the host:
 // registers -> warp shuffles -> shared memory -> one partial per block; the last block to finish (ticket) adds the block
 // partials.  Field addition is exact, so the summation order is free and the message is bit-identical to the reference's fold.
+// The sums are LAZY: canonical limbs are added as plain 96-bit integers (add.cc / addc: 2 instructions and one carry of latency per
+// step instead of a 9-instruction modular add) and reduced once per stage -- the reduction tree is the serial part of every round.
+struct wsum96 { u64 lo; u32 hi; };
+__device__ __forceinline__ void ws_add(wsum96 &a, u64 lo, u32 hi) { asm("{\n\tadd.cc.u64 %0, %0, %2;\n\taddc.u32 %1, %1, %3;\n\t}" : "+l"(a.lo), "+r"(a.hi) : "l"(lo), "r"(hi)); }
+__device__ __forceinline__ u64 ws_reduce(const wsum96 &a) { return gl_reduce128(a.lo, (u64)a.hi); }
+__device__ __forceinline__ void ws_warp_reduce(wsum96 &a) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { u64 l = __shfl_down_sync(0xffffffffu, a.lo, d); u32 h = __shfl_down_sync(0xffffffffu, a.hi, d); ws_add(a, l, h); }
+}
 template <int BLOCK>
 __device__ __forceinline__ void sc_epilogue(const gle (&acc)[SC_NACC], const int nacc, gle *__restrict__ partials, u32 *__restrict__ counters,
                                             gle *__restrict__ out, u64 seq, u64 *flag, u32 *done) {
-    __shared__ gle wsum[BLOCK / 32][SC_NACC];
+    __shared__ u64 wlo[BLOCK / 32][SC_NACC][2];
+    __shared__ u32 whi[BLOCK / 32][SC_NACC][2];
     __shared__ bool is_last;
-    for (int t = 0; t < nacc; t++) {
-        gle v = acc[t];
-        for (int d = 16; d > 0; d >>= 1) v = e_add(v, shfl_down_e(v, d));
-        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = v;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < SC_NACC; t++) if (t < nacc) {
+        wsum96 v0 = {acc[t].c0, 0}, v1 = {acc[t].c1, 0};
+        ws_warp_reduce(v0); ws_warp_reduce(v1);
+        if (lane == 0) { wlo[warp][t][0] = v0.lo; whi[warp][t][0] = v0.hi; wlo[warp][t][1] = v1.lo; whi[warp][t][1] = v1.hi; }
     }
     __syncthreads();
-    if (threadIdx.x < nacc) {
-        gle v = wsum[0][threadIdx.x];
-        for (int w = 1; w < BLOCK / 32; w++) v = e_add(v, wsum[w][threadIdx.x]);
-        if (gridDim.x == 1) st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, v);   // no cross-block stage
-        else st_e(partials + ((u64)blockIdx.y * gridDim.x + blockIdx.x) * SC_NACC + threadIdx.x, v);
+    if (threadIdx.x < 2 * nacc) {                     // thread (t, limb) adds the warps' sums and reduces once
+        const u32 t = threadIdx.x >> 1, limb = threadIdx.x & 1;
+        wsum96 v = {0, 0};
+#pragma unroll
+        for (int w = 0; w < BLOCK / 32; w++) ws_add(v, wlo[w][t][limb], whi[w][t][limb]);
+        const u64 r = ws_reduce(v);
+        u64 *dst = gridDim.x == 1 ? (u64 *)(out + (u64)blockIdx.y * SC_NACC + t) : (u64 *)(partials + ((u64)blockIdx.y * gridDim.x + blockIdx.x) * SC_NACC + t);
+        dst[limb] = r;
     }
-    if (gridDim.x == 1) { __syncthreads(); if (threadIdx.x == 0) sc_signal(seq, flag, done); return; }
+    if (gridDim.x == 1) { __syncthreads(); if (threadIdx.x == 0) sc_signal(seq, flag, done); return; }   // no cross-block stage
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -190,30 +232,31 @@ __device__ __forceinline__ void sc_epilogue(const gle (&acc)[SC_NACC], const int
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // last block of this product: all threads sum the block partials (independent L2 loads in flight), then the same
-    // shuffle + shared-memory tree as above
-    gle v[SC_NACC];
+    // last block of this product: all threads add the block partials (independent L2 loads in flight), then the same tree
+    wsum96 v[SC_NACC][2];
 #pragma unroll
-    for (int t = 0; t < SC_NACC; t++) v[t] = e_zero();
+    for (int t = 0; t < SC_NACC; t++) { v[t][0] = {0, 0}; v[t][1] = {0, 0}; }
     for (u32 x = threadIdx.x; x < gridDim.x; x += BLOCK) {
         const gle *pp = partials + ((u64)blockIdx.y * gridDim.x + x) * SC_NACC;
 #pragma unroll
         for (int t = 0; t < SC_NACC; t++) if (t < nacc) {
             ulonglong2 q = __ldcg(reinterpret_cast<const ulonglong2 *>(pp + t));
-            v[t] = e_add(v[t], e_make(q.x, q.y));
+            ws_add(v[t][0], q.x, 0); ws_add(v[t][1], q.y, 0);
         }
     }
     __syncthreads();
-    for (int t = 0; t < nacc; t++) {
-        gle w = v[t];
-        for (int d = 16; d > 0; d >>= 1) w = e_add(w, shfl_down_e(w, d));
-        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][t] = w;
+#pragma unroll
+    for (int t = 0; t < SC_NACC; t++) if (t < nacc) {
+        ws_warp_reduce(v[t][0]); ws_warp_reduce(v[t][1]);
+        if (lane == 0) { wlo[warp][t][0] = v[t][0].lo; whi[warp][t][0] = v[t][0].hi; wlo[warp][t][1] = v[t][1].lo; whi[warp][t][1] = v[t][1].hi; }
     }
     __syncthreads();
-    if (threadIdx.x < nacc) {
-        gle w = wsum[0][threadIdx.x];
-        for (int k = 1; k < BLOCK / 32; k++) w = e_add(w, wsum[k][threadIdx.x]);
-        st_e(out + (u64)blockIdx.y * SC_NACC + threadIdx.x, w);
+    if (threadIdx.x < 2 * nacc) {
+        const u32 t = threadIdx.x >> 1, limb = threadIdx.x & 1;
+        wsum96 w = {0, 0};
+#pragma unroll
+        for (int k = 0; k < BLOCK / 32; k++) ws_add(w, wlo[k][t][limb], whi[k][t][limb]);
+        ((u64 *)(out + (u64)blockIdx.y * SC_NACC + t))[limb] = ws_reduce(w);
     }
     __syncthreads();
     if (threadIdx.x == 0) { counters[blockIdx.y] = 0; sc_signal(seq, flag, done); }
@@ -245,7 +288,7 @@ k_sc_round(const ScProd *__restrict__ descs, const __grid_constant__ ScProd desc
     case 4: sc_body<4>(pd, r, acc, gtid, gstride); break;
     default: sc_body<5>(pd, r, acc, gtid, gstride); break;
     }
-    sc_epilogue<SC_THREADS>(acc, (int)pd.d + 1, partials, counters, out, seq, flag, done);
+    sc_epilogue<SC_THREADS>(acc, DSEL != 0 ? DSEL + 1 : (int)pd.d + 1, partials, counters, out, seq, flag, done);
 }
 
 // ---- lean kernels for the rounds that move the bytes ---------------------------------------------------------------------
@@ -475,11 +518,12 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
             case 4: sc_body<4, true>(pd, r, acc, first, stride); break;
             default: sc_body<5, true>(pd, r, acc, first, stride); break;
             }
-            const int nacc = pd.d + 1;
-            for (int t = 0; t < nacc; t++) {
-                gle v = acc[t];
-                for (int d = 16; d > 0; d >>= 1) v = e_add(v, shfl_down_e(v, d));
-                if (lane == 0) __stcg(reinterpret_cast<ulonglong2 *>(xpart + (u64)slot * SC_NACC + t), make_ulonglong2(v.c0, v.c1));
+            const int nacc = DSEL != 0 ? DSEL + 1 : (int)pd.d + 1;
+#pragma unroll
+            for (int t = 0; t < SC_NACC; t++) if (t < nacc) {     // lazy 96-bit warp sums, one reduction per limb (see sc_epilogue)
+                wsum96 v0 = {acc[t].c0, 0}, v1 = {acc[t].c1, 0};
+                ws_warp_reduce(v0); ws_warp_reduce(v1);
+                if (lane == 0) __stcg(reinterpret_cast<ulonglong2 *>(xpart + (u64)slot * SC_NACC + t), make_ulonglong2(ws_reduce(v0), ws_reduce(v1)));
             }
         }
         cl_sync();                                             // warp partials and folded tables of every CTA are visible

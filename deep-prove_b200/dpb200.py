@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     "dp_pcs_open_begin", "dp_pcs_open_round", "dp_pcs_open_final_message", "dp_pcs_open_query_words", "dp_pcs_open_query",
     "dp_pcs_open_free",
     "dp_logup_build", "dp_logup_num_vars", "dp_logup_outputs", "dp_logup_layer_mles", "dp_logup_free", "dp_mle_linear_combination",
+    "dp_wit_begin", "dp_wit_dense", "dp_wit_requant", "dp_wit_relu", "dp_wit_pool", "dp_wit_finish", "dp_wit_free",
     "dp_fft_rows", "dp_pad_rows", "dp_conv_prod", "dp_conv_output_elements", "dp_phi_g_init", "dp_phi_level", "dp_mle_repeat",
 ]
 
@@ -200,6 +201,55 @@ class Mle:
     def free(self):
         if self.h:
             lib().dp_mle_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Witness:
+    """dp_wit_*: quantised inference ops and lookup-witness columns on the device (one object per proof)."""
+
+    def __init__(self, tables):
+        """tables: list of (kind, size) -- kind 0 Relu, 2 Range, 3 Clamping(size)"""
+        self.n = len(tables)
+        k = (C.c_uint32 * self.n)(*[int(t[0]) for t in tables]); z = (C.c_uint32 * self.n)(*[int(t[1]) for t in tables])
+        self.h = C.c_void_p()
+        check(lib().dp_wit_begin(self.n, k, z, C.byref(self.h)))
+
+    @staticmethod
+    def dense(w, bias, x, nrows, ncols):
+        h = C.c_void_p()
+        check(lib().dp_wit_dense(w.h, bias.h, x.h, int(nrows), int(ncols), C.byref(h)))
+        return Mle(h.value)
+
+    def requant(self, x, shift, fpm, intermediate_bits, clamp_table, range_table):
+        nc = 2 + shift // 8
+        cols = (C.c_void_p * nc)()
+        check(lib().dp_wit_requant(self.h, x.h, int(shift), C.c_int64(int(fpm)), int(intermediate_bits), int(clamp_table), int(range_table), cols, nc))
+        return [Mle(c) for c in cols]
+
+    def relu(self, x, relu_table):
+        h = C.c_void_p()
+        check(lib().dp_wit_relu(self.h, x.h, int(relu_table), C.byref(h)))
+        return Mle(h.value)
+
+    def pool(self, x, c, hh, w, range_table):
+        cols = (C.c_void_p * 5)()
+        check(lib().dp_wit_pool(self.h, x.h, int(c), int(hh), int(w), int(range_table), cols))
+        return [Mle(v) for v in cols]
+
+    def finish(self):
+        mu = (C.c_void_p * self.n)(); bits = C.c_uint32()
+        check(lib().dp_wit_finish(self.h, mu, C.byref(bits)))
+        return [Mle(v) for v in mu], bits.value
+
+    def free(self):
+        if self.h:
+            lib().dp_wit_free(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

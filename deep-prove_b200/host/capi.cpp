@@ -140,7 +140,7 @@ int dph_pcs_batch_open(dp_mle *const *polys, uint32_t n, uint32_t full_log, cons
 #include "zkml.hpp"
 #include <chrono>
 namespace {
-struct ZkHandle { dp::zkml::Model model; dp::zkml::Context ctx; std::vector<std::vector<dp::zkml::Element>> trace; std::vector<dp::zkml::Element> trace_input; std::map<size_t, dp::zkml::ConvData> trace_conv; };
+struct ZkHandle { dp::zkml::Model model; dp::zkml::Context ctx; dp::zkml::DeviceTrace trace; std::vector<dp::zkml::Element> trace_input; };   // the stored trace lives in HBM
 }
 extern "C" {
 
@@ -177,10 +177,10 @@ int dph_zkml_prove(void *handle, const int64_t *input, int mode, const char *lab
     using namespace dp::zkml;
     ZkHandle *h = (ZkHandle *)handle;
     size_t w = h->model.input_len;
-    if (mode == 0 || mode == 1) { h->trace_input.assign(input, input + w); h->trace_conv.clear(); h->trace = run(h->ctx, h->trace_input, &h->trace_conv); if (mode == 1) return 0; }
+    if (mode == 0 || mode == 1) { h->trace_input.assign(input, input + w); h->trace = run_device(h->ctx, h->trace_input); check(dp_synchronize()); if (mode == 1) return 0; }
     BasicTranscript t(label);
     Prover<BasicTranscript> prover(h->ctx, t);
-    Proof p = prover.prove(h->trace_input, h->trace, &h->trace_conv);
+    Proof p = prover.prove(h->trace);
     if (out) {
         std::vector<uint64_t> f = p.flatten(h->model.nodes.size());
         *out_len = f.size();
@@ -216,7 +216,7 @@ struct ZkPool {
                     dp::zkml::Proof p = prover.prove(h->trace_input);
                     std::vector<uint64_t> bytes = p.flatten(h->model.nodes.size());
                     if (bytes.empty()) throw dp::Error(DP_ERR_STATE, "empty proof");
-                } else { dp::zkml::Proof p = prover.prove(h->trace_input, h->trace, &h->trace_conv); (void)p; }
+                } else { dp::zkml::Proof p = prover.prove(h->trace); (void)p; }
             } catch (const std::exception &e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.what(); }
             dp_profile_flush();   // per-kernel timing of the concurrent region (no-op unless dp_profile_enable(1))
             { std::lock_guard<std::mutex> lk(mu); inflight--; if (pending == 0 && inflight == 0) done_cv.notify_all(); }
@@ -231,7 +231,7 @@ extern "C" void dph_zkml_pool_free(void *handle) { std::lock_guard<std::mutex> l
 extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_workers, uint32_t n_proofs, int e2e, const char *label, double *out_seconds) {
     DPH_TRY
     ZkHandle *h = (ZkHandle *)handle;
-    if (h->trace.empty()) throw dp::Error(DP_ERR_STATE, "dph_zkml_prove_concurrent: run inference first (mode 1)");
+    if (!h->trace.valid()) throw dp::Error(DP_ERR_STATE, "dph_zkml_prove_concurrent: run inference first (mode 1)");
     ZkPool *pool;
     { std::lock_guard<std::mutex> lk(g_pools_mu); auto &pp = g_pools[handle]; if (!pp) { pp = std::make_unique<ZkPool>(); pp->h = h; pp->device = device; } pool = pp.get(); }
     while (pool->th.size() < n_workers) pool->th.emplace_back([pool] { pool->worker(); });

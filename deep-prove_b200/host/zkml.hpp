@@ -246,32 +246,94 @@ inline std::vector<std::vector<Element>> run(const Model &m, const std::vector<E
 }
 inline std::vector<std::vector<Element>> run(const Context &ctx, const std::vector<Element> &input, std::map<size_t, ConvData> *conv_data) { return run(*ctx.model, input, &ctx, conv_data); }
 
+// The inference trace ON THE DEVICE: every tensor is a Base MLE of canonical field elements of signed integers (Tensor::to_field),
+// so a trace tensor doubles as a lookup column.  Built by run_device (quantised inference on the device: only the model input
+// crosses PCIe) or by uploading a host trace once (upload_trace); read-only afterwards, shared by concurrent provers.
+struct DeviceTrace { DeviceMle input; std::vector<DeviceMle> outs; std::map<size_t, ConvData> conv; bool valid() const { return input.valid(); } };
+struct WitHandle { dp_wit *w = nullptr; ~WitHandle() { if (w) dp_wit_free(w); } };
+// the tables of a Context in TableType order (the reference's BTreeMap order) as the dp_wit_begin arguments
+inline void wit_tables(const Context &ctx, std::vector<uint32_t> &kinds, std::vector<uint32_t> &sizes, std::map<TableType, uint32_t> &index) {
+    for (auto &kv : ctx.tables) { index[kv.first] = (uint32_t)kinds.size(); kinds.push_back((uint32_t)kv.first.kind); sizes.push_back((uint32_t)kv.first.size); }
+}
+inline DeviceMle wit_own(dp_mle *h) { return DeviceMle(h); }
+inline std::vector<DeviceMle> wit_requant(dp_wit *w, const DeviceMle &x, const Requant &rq, const std::map<TableType, uint32_t> &ti) {
+    size_t nc = 2 + rq.shift() / BIT_LEN; std::vector<dp_mle *> raw(nc, nullptr);
+    check(dp_wit_requant(w, x.handle(), (uint32_t)rq.shift(), rq.fixed_point_multiplier, (uint32_t)rq.intermediate_bit_size,
+                         ti.at(TableType::clamping(rq.clamping_size())), ti.at(TableType::range()), raw.data(), (uint32_t)nc));
+    std::vector<DeviceMle> cols; for (dp_mle *h : raw) cols.push_back(wit_own(h));
+    return cols;
+}
+inline std::vector<DeviceMle> wit_pool(dp_wit *w, const DeviceMle &x, const Node &n, const std::map<TableType, uint32_t> &ti) {
+    dp_mle *raw[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    check(dp_wit_pool(w, x.handle(), (uint32_t)n.pool_c, (uint32_t)n.pool_h, (uint32_t)n.pool_w, ti.at(TableType::range()), raw));
+    std::vector<DeviceMle> cols; for (dp_mle *h : raw) cols.push_back(wit_own(h));
+    return cols;
+}
+inline void wit_check(uint32_t bits) {
+    if (bits & 1) throw Error(DP_ERR_INVALID, "Could not apply requantisation, tensor element had absolute value too large");
+    if (bits) throw Error(DP_ERR_INVALID, "lookup witness: a value is not in its table (clamping / relu / pooling range)");
+}
+inline std::vector<Element> to_elements(const DeviceMle &m) { std::vector<u64> f = m.download(); std::vector<Element> o(f.size()); for (size_t i = 0; i < f.size(); i++) o[i] = f[i] > (P >> 1) ? -(Element)(P - f[i]) : (Element)f[i]; return o; }
+// Model::run on the device (Dense / Requant / Relu / Maxpool2D kernels of csrc/witness.cu; the FFT convolution keeps its
+// host-vector interface: its input comes down and its output goes back up once per convolution node)
+inline DeviceTrace run_device(const Context &ctx, const std::vector<Element> &input) {
+    const Model &m = *ctx.model;
+    DeviceTrace tr; tr.input = DeviceMle::from_evaluations_vec(to_base(input));
+    std::vector<uint32_t> kinds, sizes; std::map<TableType, uint32_t> ti; wit_tables(ctx, kinds, sizes, ti);
+    WitHandle wh; if (!kinds.empty()) check(dp_wit_begin((uint32_t)kinds.size(), kinds.data(), sizes.data(), &wh.w));
+    DeviceMle cur = tr.input;
+    for (size_t id = 0; id < m.nodes.size(); id++) {
+        const Node &n = m.nodes[id]; DeviceMle o;
+        if (n.op == Op::Dense) { const auto &c = ctx.model_comms.at(id); dp_mle *h; check(dp_wit_dense(c.at("DenseWeight").poly.handle(), c.at("DenseBias").poly.handle(), cur.handle(), (uint32_t)n.nrows, (uint32_t)n.ncols, &h)); o = wit_own(h); }
+        else if (n.op == Op::Requant) o = wit_requant(wh.w, cur, n.rq, ti)[1];
+        else if (n.op == Op::Relu) { dp_mle *h; check(dp_wit_relu(wh.w, cur.handle(), ti.at(TableType::relu()), &h)); o = wit_own(h); }
+        else if (n.op == Op::Pool) o = wit_pool(wh.w, cur, n, ti)[4];
+        else { ConvData cd; std::vector<Element> out = ctx.convs.at(id).op(to_elements(cur), cd); tr.conv[id] = std::move(cd); o = DeviceMle::from_evaluations_vec(to_base(out)); }
+        tr.outs.push_back(o); cur = o;
+    }
+    if (wh.w) { std::vector<dp_mle *> mu(kinds.size(), nullptr); uint32_t bits = 0; check(dp_wit_finish(wh.w, mu.data(), &bits)); for (dp_mle *h : mu) wit_own(h); wit_check(bits); }
+    return tr;
+}
+inline DeviceTrace upload_trace(const std::vector<Element> &input, const std::vector<std::vector<Element>> &outs, const std::map<size_t, ConvData> *conv_data) {
+    DeviceTrace tr; tr.input = DeviceMle::from_evaluations_vec(to_base(input));
+    for (auto &o : outs) tr.outs.push_back(DeviceMle::from_evaluations_vec(to_base(o)));
+    if (conv_data) tr.conv = *conv_data;
+    return tr;
+}
+
 // Prover<'a, E, T, PCS> (iop/prover.rs:40-60)
 template <class T>
 class Prover {
   public:
     Prover(const Context &ctx, T &transcript) : ctx_(ctx), t_(transcript) {}
 
-    Proof prove(const std::vector<Element> &input) { std::map<size_t, ConvData> cd; auto outs = run(ctx_, input, &cd); return prove(input, outs, &cd); }
-    // Prover::prove(full_trace): the inference trace is an INPUT of proving (zkml/src/bin/bench.rs:390-408 times only this)
+    // end to end from the host input vector: inference on the device, then prove
+    Proof prove(const std::vector<Element> &input) { DeviceTrace tr = run_device(ctx_, input); return prove(tr); }
+    // a host trace (the reference's InferenceTrace): uploaded once, tensor by tensor
     Proof prove(const std::vector<Element> &input, const std::vector<std::vector<Element>> &outs, const std::map<size_t, ConvData> *conv_data = nullptr) {
+        DeviceTrace tr = upload_trace(input, outs, conv_data); return prove(tr);
+    }
+    // Prover::prove(full_trace): the inference trace is an INPUT of proving (zkml/src/bin/bench.rs:390-408 times only this)
+    Proof prove(const DeviceTrace &tr) {
         const Model &m = *ctx_.model;
-        auto node_input = [&](size_t id) -> const std::vector<Element> & { return id == 0 ? input : outs[id - 1]; };
+        if (tr.outs.size() != m.nodes.size()) throw Error(DP_ERR_INVALID, "prove: the trace does not match the model");
+        const std::map<size_t, ConvData> *conv_data = &tr.conv;
+        auto node_input = [&](size_t id) -> const DeviceMle & { return id == 0 ? tr.input : tr.outs[id - 1]; };
         static const bool prof = getenv("DP_HOST_PROF") != nullptr;
         auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         double t0 = now();
         ctx_.write_to_transcript(t_);
-        instantiate_witness_ctx(m, input, outs);
+        instantiate_witness_ctx(m, tr);
         double t1 = now();
         // output claim (prover.rs:423-436)
-        const std::vector<Element> &fo = outs.back();
-        Claim last; for (size_t i = 0, nv = ceil_log2(fo.size()); i < nv; i++) last.point.push_back(t_.read_challenge());
-        last.eval = DeviceMle::from_evaluations_vec(to_base(fo)).evaluate(last.point);
+        const DeviceMle &fo = tr.outs.back();
+        Claim last; for (size_t i = 0, nv = fo.num_vars(); i < nv; i++) last.point.push_back(t_.read_challenge());
+        last.eval = fo.evaluate(last.point);
         for (size_t id = m.nodes.size(); id-- > 0;) {
             const Node &n = m.nodes[id];
             if (n.op == Op::Dense) last = prove_dense(id, n, last, node_input(id));
             else if (n.op == Op::Requant) last = prove_requant(id, n, last);
-            else if (n.op == Op::Relu) last = prove_activation(id, last, outs[id]);
+            else if (n.op == Op::Relu) last = prove_activation(id, last);
             else if (n.op == Op::Pool) last = prove_pooling(id, n, last);
             else {
                 if (!conv_data || !conv_data->count(id)) throw Error(DP_ERR_INVALID, "prove: no convolution proving data in the trace");
@@ -294,63 +356,52 @@ class Prover {
     // generate_lookup_witnesses (lookup/context.rs:631-756) + initialise_from_table_set (:758-781).
     // The reference commits every witness column from rayon workers before any challenge is drawn; here all
     // columns are gathered first and committed with ONE Basefold::commit_many call (concurrent on the device).
-    void instantiate_witness_ctx(const Model &m, const std::vector<Element> &input, const std::vector<std::vector<Element>> &outs) {
-        auto node_input = [&](size_t id) -> const std::vector<Element> & { return id == 0 ? input : outs[id - 1]; };
-        std::map<TableType, std::unordered_map<Element, u64>> element_count;
-        std::vector<std::vector<u64>> cols;                      // every column to commit, in creation order
+    void instantiate_witness_ctx(const Model &m, const DeviceTrace &tr) {
+        auto node_input = [&](size_t id) -> const DeviceMle & { return id == 0 ? tr.input : tr.outs[id - 1]; };
+        std::vector<DeviceMle> polys;                            // every column to commit, in creation order (all device-resident)
         struct Slot { size_t node; size_t witness; bool table; bool column = true; };  // where commitment k goes (column: also a lookup column)
         std::vector<Slot> slots;
+        std::vector<uint32_t> kinds, sizes; std::map<TableType, uint32_t> ti; wit_tables(ctx_, kinds, sizes, ti);
+        WitHandle wh; if (!kinds.empty()) check(dp_wit_begin((uint32_t)kinds.size(), kinds.data(), sizes.data(), &wh.w));
+        std::map<TableType, bool> used;
         for (size_t id = 0; id < m.nodes.size(); id++) {
             const Node &n = m.nodes[id];
-            if (n.op == Op::Requant) {   // requant.rs:208-330
-                size_t shift = n.rq.shift(); Element rc = (Element)1 << (shift - 1), mask = ((Element)1 << shift) - 1;
-                std::vector<Element> cin, cout, shifted;
-                for (Element v : node_input(id)) { Element tmp = v * n.rq.fixed_point_multiplier + rc, cl = tmp >> shift; cin.push_back(cl); cout.push_back(cl < QMIN ? QMIN : (cl > QMAX ? QMAX : cl)); shifted.push_back(tmp & mask); }
-                size_t no_chunks = shift / BIT_LEN; Element rmask = ((Element)1 << BIT_LEN) - 1;
-                std::vector<std::vector<Element>> chunks(no_chunks);
-                for (size_t j = 0; j < no_chunks; j++) for (Element e : shifted) chunks[j].push_back((e >> (j * BIT_LEN)) & rmask);
-                TableType tc = TableType::clamping(n.rq.clamping_size()), tr = TableType::range();
-                for (auto &ch : chunks) for (Element e : ch) element_count[tr][e]++;
-                for (size_t i = 0; i < cin.size(); i++) element_count[tc][cin[i] + cout[i] * COLUMN_SEPARATOR]++;
+            if (n.op == Op::Requant) {   // requant.rs:208-330: clamping (input, output) columns + the byte chunks of the shifted-out bits
+                TableType tc = TableType::clamping(n.rq.clamping_size()), trg = TableType::range();
+                used[tc] = used[trg] = true;
+                std::vector<DeviceMle> c = wit_requant(wh.w, node_input(id), n.rq, ti);
                 LogUpWitness wc; wc.tt = tc; wc.columns_per_instance = 2;
-                LogUpWitness ws; ws.tt = tr; ws.columns_per_instance = 1;
+                LogUpWitness ws; ws.tt = trg; ws.columns_per_instance = 1;
                 lookup_witness_[id] = {wc, ws};
-                for (auto *v : {&cin, &cout}) { cols.push_back(to_base(*v)); slots.push_back({id, 0, false}); }
-                for (auto &ch : chunks) { cols.push_back(to_base(ch)); slots.push_back({id, 1, false}); }
-            } else if (n.op == Op::Relu) {   // activation.rs:238-323
-                TableType tt = TableType::relu(); LogUpWitness w; w.tt = tt; w.columns_per_instance = 2;
-                const auto &a = node_input(id); const auto &b = outs[id];
-                for (size_t i = 0; i < a.size(); i++) element_count[tt][a[i] + COLUMN_SEPARATOR * b[i]]++;
+                for (size_t k = 0; k < c.size(); k++) { polys.push_back(c[k]); slots.push_back({id, k < 2 ? (size_t)0 : (size_t)1, false}); }
+            } else if (n.op == Op::Relu) {   // activation.rs:238-323: the node's input and output tensors ARE the two columns
+                TableType tt = TableType::relu(); LogUpWitness w; w.tt = tt; w.columns_per_instance = 2; used[tt] = true;
+                dp_mle *h; check(dp_wit_relu(wh.w, node_input(id).handle(), ti.at(tt), &h)); DeviceMle out = wit_own(h);
                 lookup_witness_[id] = {w};
-                for (auto *v : {&a, &b}) { cols.push_back(to_base(*v)); slots.push_back({id, 0, false}); }
-            } else if (n.op == Op::Pool) {   // pooling.rs:210-271 + compute_polys (:686-771): out - in(2r+dr, 2c+dc), (dr,dc) = (0,0),(1,0),(0,1),(1,1)
-                TableType tr = TableType::range(); LogUpWitness w; w.tt = tr; w.columns_per_instance = 1;
-                const auto &x = node_input(id); const auto &out = outs[id];
-                size_t C = n.pool_c, H = n.pool_h, W = n.pool_w;
-                static const size_t DR[4] = {0, 1, 0, 1}, DC[4] = {0, 0, 1, 1};
+                polys.push_back(node_input(id)); slots.push_back({id, 0, false});
+                polys.push_back(out); slots.push_back({id, 0, false});
+            } else if (n.op == Op::Pool) {   // pooling.rs:210-271 + compute_polys (:686-771)
+                TableType trg = TableType::range(); LogUpWitness w; w.tt = trg; w.columns_per_instance = 1; used[trg] = true;
+                std::vector<DeviceMle> c = wit_pool(wh.w, node_input(id), n, ti);
                 lookup_witness_[id] = {w};
-                for (size_t k = 0; k < 4; k++) {
-                    std::vector<Element> d(out.size());
-                    for (size_t c = 0; c < C; c++) for (size_t r = 0; r < H / 2; r++) for (size_t cc = 0; cc < W / 2; cc++) { size_t oi = (c * (H / 2) + r) * (W / 2) + cc; d[oi] = out[oi] - x[(c * H + 2 * r + DR[k]) * W + 2 * cc + DC[k]]; }
-                    for (Element e : d) element_count[tr][e]++;
-                    cols.push_back(to_base(d)); slots.push_back({id, 0, false});
-                }
-                cols.push_back(to_base(out)); slots.push_back({id, 0, false, false});   // the output poly: committed, not a lookup column
+                for (size_t k = 0; k < 4; k++) { polys.push_back(c[k]); slots.push_back({id, 0, false}); }
+                polys.push_back(c[4]); slots.push_back({id, 0, false, false});   // the output poly: committed, not a lookup column
             }
         }
-        for (auto &kv : element_count) {   // table multiplicities (lookup/context.rs:675-737)
-            const TableData &td = ctx_.tables.at(kv.first);
-            std::vector<u64> mult(td.merged.size());
-            for (size_t i = 0; i < td.merged.size(); i++) {
-                auto it = kv.second.find(td.merged[i]);
-                if (it == kv.second.end()) mult[i] = 0;
-                else { u64 tc = td.table_count.at(td.merged[i]); mult[i] = fmul(canon(it->second), tc != 1 ? finv(canon(tc)) : 1); }
+        std::vector<TableType> table_order;
+        if (wh.w) {   // table multiplicities (lookup/context.rs:675-737): histograms the node kernels filled, every table row distinct
+            std::vector<dp_mle *> mu(kinds.size(), nullptr); uint32_t bits = 0;
+            check(dp_wit_finish(wh.w, mu.data(), &bits));
+            std::vector<DeviceMle> mults; for (dp_mle *h : mu) mults.push_back(wit_own(h));
+            wit_check(bits);
+            for (auto &kv : ctx_.tables) {
+                if (!used.count(kv.first)) continue;
+                for (auto &tc : kv.second.table_count) if (tc.second != 1) throw Error(DP_ERR_UNSUPPORTED, "device multiplicities need distinct table rows");
+                LogUpWitness w; w.table = true; w.tt = kv.first; w.column_evals = kv.second.columns;
+                table_witness_.push_back(w); table_order.push_back(kv.first);
+                polys.push_back(mults[ti.at(kv.first)]); slots.push_back({0, table_witness_.size() - 1, true});
             }
-            LogUpWitness w; w.table = true; w.tt = kv.first; w.column_evals = td.columns;
-            table_witness_.push_back(w);
-            cols.push_back(std::move(mult)); slots.push_back({0, table_witness_.size() - 1, true});
         }
-        std::vector<DeviceMle> polys; for (auto &c : cols) polys.push_back(DeviceMle::from_evaluations_vec(c));
         std::vector<BasefoldCommitmentWithWitness> comms = Basefold::commit_many(ctx_.pp, polys);
         for (size_t k = 0; k < slots.size(); k++) {
             ProverCommitment pc{comms[k], polys[k]};
@@ -358,7 +409,7 @@ class Prover {
             else { LogUpWitness &w = lookup_witness_[slots[k].node][slots[k].witness]; w.commits.push_back(pc); if (slots[k].column) w.column_evals.push_back(polys[k]); }
         }
         constant_challenge_ = t_.get_and_append_challenge("table_constant");
-        for (auto &kv : element_count) challenge_map_[kv.first] = kv.first.kind == 0 ? t_.get_and_append_challenge("Relu") : (kv.first.kind == 3 ? t_.get_and_append_challenge("Clamping") : Ext::one());
+        for (auto &tt : table_order) challenge_map_[tt] = tt.kind == 0 ? t_.get_and_append_challenge("Relu") : (tt.kind == 3 ? t_.get_and_append_challenge("Clamping") : Ext::one());
     }
     LogUpInput get_logup_input(const LogUpWitness &w) const {   // lookup/witness.rs:96-140
         LogUpInput in; in.table = w.table; in.column_evals = w.column_evals; in.multiplicities = w.multiplicity_evals;
@@ -367,13 +418,13 @@ class Prover {
     }
 
     // Dense::prove_step (layers/dense.rs:423-551)
-    Claim prove_dense(size_t id, const Node &n, const Claim &last_claim, const std::vector<Element> &input) {
+    Claim prove_dense(size_t id, const Node &n, const Claim &last_claim, const DeviceMle &input) {
         const auto &comms = ctx_.model_comms.at(id);
         const DeviceMle &weights = comms.at("DenseWeight").poly, &bias = comms.at("DenseBias").poly;
         if (ceil_log2(n.nrows) != last_claim.point.size()) throw Error(DP_ERR_INVALID, "something's wrong with the randomness");
         Ext bias_eval = bias.evaluate(last_claim.point);
         DeviceMle mat = weights.fix_high_variables(last_claim.point);      // rows are the HIGH variables (dense.rs:471-475)
-        DeviceMle in = DeviceMle::from_evaluations_vec(to_base(input));
+        const DeviceMle &in = input;                                        // the trace tensor itself (a sumcheck borrows its inputs)
         VirtualPolynomial vp(in.num_vars());
         vp.add_mle_list({mat, in}, Ext::one());
         auto res = IOPProverState::prove_parallel(std::move(vp), t_);
@@ -413,13 +464,12 @@ class Prover {
     }
 
     // Activation::prove_step (layers/activation.rs:385-460)
-    Claim prove_activation(size_t id, const Claim &last_claim, const std::vector<Element> &output) {
+    Claim prove_activation(size_t id, const Claim &last_claim) {
         std::vector<LogUpWitness> ws = lookup_witness_.at(id);
         if (ws.size() != 1) throw Error(DP_ERR_INVALID, "Activation only requires a lookup into one table type");
         LogUpProof lp = logup_batch_prove(get_logup_input(ws[0]), t_);
         // the output tensor as an MLE; col_two of the lookup holds the same values (activation.rs:281-283), reuse it
         SamePolyProof acc = same_poly_prove(ws[0].column_evals[1], {last_claim, lp.output_claims[1]}, t_);
-        (void)output;
         Claim input_claim = lp.output_claims[0];
         ActivationProof ap; ap.io_accumulation = acc; ap.lookup = lp;
         std::vector<Claim> cc = {input_claim, acc.extract_claim()};

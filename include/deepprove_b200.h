@@ -201,6 +201,27 @@ uint64_t dp_pcs_open_query_words(const dp_pcs_open *o);
 int dp_pcs_open_query(dp_pcs_open *o, const uint64_t *x_indices, uint32_t n, uint64_t *out);
 int dp_pcs_open_free(dp_pcs_open *o);
 
+/* ---- quantised inference + lookup-witness generation on the device ---------------------------------
+ * Replaces the host loops of Dense::op (zkml/src/layers/dense.rs), Requant::op / gen_lookup_witness
+ * (layers/requant.rs:208-330), Activation::gen_lookup_witness (layers/activation.rs:238-323), Maxpool2D::op + compute_polys
+ * (layers/pooling.rs:210-271,667-771) and the multiplicity counting of generate_lookup_witnesses (lookup/context.rs:675-737).
+ * Tensors are Base MLEs of canonical field elements of signed integers (exactly Tensor<Element>::to_field), so a trace
+ * tensor is itself a witness column.  One dp_wit per proof holds the tables' multiplicity histograms; the node calls add
+ * their lookups to them.  Table types as in lookup/context.rs:53-63: kind 0 Relu, 2 Range, 3 Clamping(size). */
+typedef struct dp_wit dp_wit;
+int dp_wit_begin(uint32_t n_tables, const uint32_t *kinds, const uint32_t *sizes, dp_wit **out);
+int dp_wit_dense(const dp_mle *weights /* [nrows][ncols] */, const dp_mle *bias, const dp_mle *x, uint32_t nrows, uint32_t ncols, dp_mle **out);
+/* cols[0] clamping input, cols[1] clamping output (= the node's output tensor), cols[2 ..] the shift / BIT_LEN byte chunks */
+int dp_wit_requant(dp_wit *w, const dp_mle *x, uint32_t shift, int64_t fixed_point_multiplier, uint32_t intermediate_bit_size,
+                   uint32_t clamp_table, uint32_t range_table, dp_mle **cols, uint32_t n_cols);
+int dp_wit_relu(dp_wit *w, const dp_mle *x, uint32_t relu_table, dp_mle **out);
+/* cols[0..3] = out - in(2r+dr, 2c+dc) for (dr,dc) = (0,0),(1,0),(0,1),(1,1); cols[4] = the pooled output [C][H/2][W/2] */
+int dp_wit_pool(dp_wit *w, const dp_mle *x, uint32_t C, uint32_t H, uint32_t W, uint32_t range_table, dp_mle **cols);
+/* multiplicity polynomial of every table (dp_wit_begin order).  error_bits != 0: a value fell outside its table (1 requant
+ * input too large, 2 clamping, 4 relu, 8 pooling) -- the reference panics there. */
+int dp_wit_finish(dp_wit *w, dp_mle **mults, uint32_t *error_bits);
+int dp_wit_free(dp_wit *w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <chrono>
 #include "../deep-prove_b200/csrc/poseidon2.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
@@ -394,6 +395,31 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_sce3(const gle *__restrict__ f0
     if (threadIdx.x < 4) { gle v = ws[0][threadIdx.x]; for (int w = 1; w < BLOCK / 32; w++) v = e_add(v, ws[w][threadIdx.x]); partials[4 * blockIdx.x + threadIdx.x] = v; }
 }
 
+// ---- host <-> resident-kernel round trip (the per-round floor of the resident sumcheck kernel) ----
+__device__ __forceinline__ u64 ld_relaxed_sys(const u64 *p) { u64 v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p) { u64 v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed_sys(u64 *p, u64 v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+// variant bits: 1 poll with ld.relaxed.sys (else volatile), 2 flag with st.release.sys (else __threadfence_system + volatile store),
+// 4 dirty 64 KB of device memory before signalling (as a folding round does), 8 no fence at all (PCIe posted-write order only)
+__global__ void k_pingpong(u64 *mailbox, u64 *flag, u64 *out_mapped, u64 *scratch, int n, int variant) {
+    for (int k = 1; k <= n; k++) {
+        if (threadIdx.x == 0) {
+            if (variant & 1) { while (ld_relaxed_sys(mailbox) != (u64)k) {} } else { while (*(volatile u64 *)mailbox != (u64)k) {} }
+        }
+        __syncthreads();
+        if (variant & 4) for (int i = threadIdx.x; i < 8192; i += blockDim.x) scratch[i] = k + i;
+        if (threadIdx.x < 8) out_mapped[threadIdx.x] = (u64)k + threadIdx.x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (variant & 8) st_relaxed_sys(flag, (u64)k);
+            else if (variant & 2) st_release_sys(flag, (u64)k);
+            else { __threadfence_system(); *(volatile u64 *)flag = (u64)k; }
+        }
+    }
+}
+__global__ void k_tiny(u64 *flag, u64 *out_mapped, u64 k) { if (threadIdx.x < 8) out_mapped[threadIdx.x] = k + threadIdx.x; __syncthreads(); if (threadIdx.x == 0) { __threadfence_system(); *(volatile u64 *)flag = k; } }
+
 // sum of the block partials on the host (field addition is exact: any order gives the same element)
 static void host_sum_f(const u64 *d, int blocks, u64 out[4]) {
     std::vector<u64> h(4 * blocks); cudaMemcpy(h.data(), d, 32 * blocks, cudaMemcpyDeviceToHost);
@@ -511,6 +537,34 @@ int main(int argc, char **argv) {
 #define RUN_E(PPT, BLOCK, MINB, LAZY, GRID) rep2("fold-e PPT=" #PPT " block=" #BLOCK " minb=" #MINB " lazy=" #LAZY " grid=" #GRID, GRID, \
             timed([&] { k_sce3<PPT, BLOCK, MINB, LAZY><<<GRID, BLOCK>>>(g[0], g[1], g[2], r, g2[0], g2[1], g2[2], npairs / 4, parte); }), 37.75, refe3, g2[1], g2sum)
         RUN_E(1, 256, 1, false, 512); RUN_E(1, 256, 1, true, 512); RUN_E(1, 256, 3, true, 512); RUN_E(1, 128, 4, true, 1024); RUN_E(1, 128, 6, true, 1024); RUN_E(2, 128, 4, true, 512); RUN_E(1, 64, 8, true, 2048);
+    }
+    if (want("pp")) {
+        u64 *pin; CK(cudaHostAlloc((void **)&pin, 4096 * 3, cudaHostAllocMapped));
+        volatile u64 *mailbox = pin, *flag = pin + 512, *outm = pin + 1024;
+        u64 *scratch; CK(cudaMalloc(&scratch, 8192 * 8));
+        const int N = 2000;
+        printf("[pp] host <-> resident kernel round trip, %d iterations (host: store mailbox, spin on flag)\n", N);
+        for (int variant : {0, 1, 2, 3, 4, 6, 8, 9, 12}) {
+            mailbox[0] = 0; flag[0] = 0;
+            k_pingpong<<<1, 256>>>((u64 *)mailbox, (u64 *)flag, (u64 *)outm, scratch, N, variant);
+            auto t0 = std::chrono::steady_clock::now();
+            for (int k = 1; k <= N; k++) {
+                __atomic_store_n(&mailbox[0], (u64)k, __ATOMIC_RELEASE);
+                while (__atomic_load_n(&flag[0], __ATOMIC_ACQUIRE) != (u64)k) {}
+            }
+            double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+            CK(cudaDeviceSynchronize());
+            printf("  variant %2d (%s poll, %s%s): %6.2f us per round trip (payload word0 %llu)\n", variant, (variant & 1) ? "ld.relaxed.sys" : "volatile", (variant & 8) ? "st.relaxed.sys, no fence" : (variant & 2) ? "st.release.sys" : "membar.sys + volatile st",
+                   (variant & 4) ? ", 64 KB device writes first" : "", us / N, (unsigned long long)outm[0]);
+        }
+        {   // reference: one tiny launch per round
+            flag[0] = 0;
+            auto t0 = std::chrono::steady_clock::now();
+            for (int k = 1; k <= N; k++) { k_tiny<<<1, 256>>>((u64 *)flag, (u64 *)outm, (u64)k); while (__atomic_load_n(&flag[0], __ATOMIC_ACQUIRE) != (u64)k) {} }
+            double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+            CK(cudaDeviceSynchronize());
+            printf("  one launch per round (tiny kernel + membar.sys + flag): %6.2f us per round\n", us / N);
+        }
     }
     printf("done (%s)\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
