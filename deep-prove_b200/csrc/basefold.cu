@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "powtab.cuh"
 #include "poseidon2.cuh"
+#include "blake3.cuh"
 #include <algorithm>
 #include <atomic>
 #include <map>
@@ -308,6 +309,65 @@ __global__ void k_merkle_batch_l0(BatchPtrs bp, u32 m, u64 n_out, u64 *__restric
 }
 template <bool EXT> __global__ void k_leafpair_root(const void *leaves, u64 *out) { u64 d[4]; leaf_pair_digest<EXT>(leaves, 0, d); for (int i = 0; i < 4; i++) out[i] = d[i]; }
 
+// ---- the `blake` MerkleHasher (mpcs/src/util/hash.rs:79-95): leaf pair -> BLAKE3(LE bytes), inner node -> BLAKE3(left || right) ----
+// Selected process-wide with dp_set_merkle_hasher (the reference selects at compile time: feature `blake`, mpcs/src/lib.rs:339-342).
+static std::atomic<int> g_hasher{0};          // 0 Poseidon2 (default), 1 BLAKE3
+static inline bool blake_on() { return g_hasher.load(std::memory_order_relaxed) == 1; }
+template <bool EXT> __device__ __forceinline__ void b3_leaf_pair(const void *leaves, u64 pair, u64 d[4]) {
+    u64 w[4];
+    if (EXT) { const gle *l = (const gle *)leaves + 2 * pair; gle a = ld_e(l), b = ld_e(l + 1); w[0] = a.c0; w[1] = a.c1; w[2] = b.c0; w[3] = b.c1; b3::hash_words(w, 4, d); }
+    else { ulonglong2 v = ld_b2((const u64 *)leaves + 2 * pair); w[0] = v.x; w[1] = v.y; b3::hash_words(w, 2, d); }
+}
+// level 0 (hash_two_leaves) of a single-polynomial tree: one digest per leaf pair.  Stored (unlike the Poseidon variant, whose
+// level 0 is a zero-padded copy of the pair and is recomputed on demand).
+template <bool EXT> __global__ void k_b3_leaves(const void *__restrict__ leaves, u64 n_out, u64 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    u64 d[4]; b3_leaf_pair<EXT>(leaves, i, d);
+    *reinterpret_cast<ulonglong2 *>(out + 4 * i) = make_ulonglong2(d[0], d[1]); *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(d[2], d[3]);
+}
+__global__ void k_b3_up(const u64 *__restrict__ in, u64 n_out, u64 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    u64 w[8];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) { ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(in + 8 * i + k); w[k] = v.x; w[k + 1] = v.y; }
+    u64 d[4]; b3::hash_words(w, 8, d);
+    *reinterpret_cast<ulonglong2 *>(out + 4 * i) = make_ulonglong2(d[0], d[1]); *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(d[2], d[3]);
+}
+// every remaining level (<= 1024 hashes at the first one) in one single-block launch
+__global__ void __launch_bounds__(1024) k_b3_tail(const u64 *__restrict__ in0, u32 first_level, u32 lg, u64 nl_first, u64 *levels, LvlOff lo) {
+    const u64 *in = in0; u64 nl = nl_first;
+    for (u32 l = first_level; l < lg; l++, nl >>= 1) {
+        u64 *out = levels + 4 * lo.off[l];
+        if (threadIdx.x < nl) {
+            u64 w[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) w[k] = in[8 * (u64)threadIdx.x + k];
+            u64 d[4]; b3::hash_words(w, 8, d);
+#pragma unroll
+            for (int k = 0; k < 4; k++) out[4 * (u64)threadIdx.x + k] = d[k];
+        }
+        __syncthreads();
+        in = out;
+    }
+}
+
+// batch_commit leaf level under BLAKE3: digest_i = H( H(values of all polynomials at 2i) || H(... at 2i+1) )  (hash_two_leaves_batch_*)
+template <bool EXT>
+__global__ void k_b3_batch_l0(BatchPtrs bp, u32 m, u64 n_out, u64 *__restrict__ out) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const int n = EXT ? 2 * (int)m : (int)m;
+    auto ga = [&](int k) -> u64 { return EXT ? ((const u64 *)bp.p[k >> 1])[2 * (2 * i) + (k & 1)] : ((const u64 *)bp.p[k])[2 * i]; };
+    auto gb = [&](int k) -> u64 { return EXT ? ((const u64 *)bp.p[k >> 1])[2 * (2 * i + 1) + (k & 1)] : ((const u64 *)bp.p[k])[2 * i + 1]; };
+    u64 w[8], d[4];
+    b3::hash_stream(ga, n, w); b3::hash_stream(gb, n, w + 4);
+    b3::hash_words(w, 8, d);
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[4 * i + k] = d[k];
+}
+
 // A Merkle tree over `n` leaves living in HBM: levels >= 1 packed back to back.
 struct DevTree {
     const void *leaves = nullptr; bool ext = false; u64 n = 0; u32 lg = 0;
@@ -317,6 +377,7 @@ struct DevTree {
     bool own_leaves = false;
     const u64 *level0 = nullptr;      // batch trees only: stored digests of the leaf pairs (single-polynomial trees recompute them)
     bool own_levels = true;           // false for the per-polynomial views of a batch commitment
+    bool own_level0 = false;          // BLAKE3 trees of one polynomial store their leaf-pair digests (Poseidon2 recomputes them: zero-padded copies)
 };
 // `lvl0` != NULL: a batch tree -- the digests of the leaf pairs are given (k_merkle_batch_l0) instead of being packed from `leaves`
 static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n, const u64 *lvl0 = nullptr) {
@@ -328,6 +389,30 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n, const u64
     u64 total = 0;
     for (u32 l = 1; l < t.lg; l++) { t.lvl_off[l] = total; total += n >> (l + 1); }
     if (int e = dp_dev_alloc((void **)&t.levels, sizeof(u64) * 4 * (total + 1))) return e;
+    if (blake_on()) {
+        const u64 *l0 = lvl0;
+        if (!l0) {
+            u64 *own = nullptr; if (int e = dp_dev_alloc((void **)&own, sizeof(u64) * 4 * (n >> 1))) return e;
+            DpProfScope prof("k_b3_leaves(blake3)", n * (ext ? 16 : 8) + (n >> 1) * 32);
+            const unsigned g = (unsigned)(((n >> 1) + 255) / 256);
+            if (ext) k_b3_leaves<true><<<g, 256, 0, c.stream>>>(leaves, n >> 1, own); else k_b3_leaves<false><<<g, 256, 0, c.stream>>>(leaves, n >> 1, own);
+            DP_LAUNCHED();
+            t.level0 = l0 = own; t.own_level0 = true;
+        }
+        if (t.lg == 1) { t.root_dev = const_cast<u64 *>(l0); DP_CUDA(cudaGetLastError()); return DP_OK; }
+        LvlOff lo_all; memset(&lo_all, 0, sizeof lo_all);
+        for (u32 k = 1; k < t.lg && k < 36; k++) lo_all.off[k] = t.lvl_off[k];
+        for (u32 l = 1; l < t.lg; l++) {
+            const u64 nl = n >> (l + 1);
+            const u64 *in = l == 1 ? l0 : t.levels + 4 * t.lvl_off[l - 1];
+            if (nl <= 1024 && t.lg < 36) { DpProfScope prof("k_b3_tail(blake3)", nl * 96); k_b3_tail<<<1, 1024, 0, c.stream>>>(in, l, t.lg, nl, t.levels, lo_all); DP_LAUNCHED(); break; }
+            DpProfScope prof("k_b3_up(blake3)", nl * 96);
+            k_b3_up<<<(unsigned)((nl + 255) / 256), 256, 0, c.stream>>>(in, nl, t.levels + 4 * t.lvl_off[l]); DP_LAUNCHED();
+        }
+        t.root_dev = t.levels + 4 * t.lvl_off[t.lg - 1];
+        DP_CUDA(cudaGetLastError());
+        return DP_OK;
+    }
     if (t.lg == 1 && lvl0) { t.root_dev = const_cast<u64 *>(lvl0); }
     else if (t.lg == 1) {
         if (ext) k_leafpair_root<true><<<1, 1, 0, c.stream>>>(leaves, t.levels); else k_leafpair_root<false><<<1, 1, 0, c.stream>>>(leaves, t.levels);
@@ -373,7 +458,7 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n, const u64
     DP_CUDA(cudaGetLastError());
     return DP_OK;
 }
-static void tree_free(DevTree &t) { if (t.own_levels) dp_dev_free(t.levels); t.levels = nullptr; if (t.own_leaves) dp_dev_free(const_cast<void *>(t.leaves)); t.leaves = nullptr; }
+static void tree_free(DevTree &t) { if (t.own_levels) dp_dev_free(t.levels); t.levels = nullptr; if (t.own_level0) { dp_dev_free(const_cast<u64 *>(t.level0)); t.level0 = nullptr; t.own_level0 = false; } if (t.own_leaves) dp_dev_free(const_cast<void *>(t.leaves)); t.leaves = nullptr; }
 
 // ---- K10 FRI fold (commit_phase.rs:511-526, rs.rs:377-410, arithmetic.rs:120-132) ----
 // out[i] = y0 + (r - x0) * (y1 - y0) * w,  x0 = w_{2^(level+1)}^{rev(i, level)} * gamma_lvl,  w = -1/(2 x0)
@@ -468,6 +553,13 @@ static void msg_to_coeffs(const uint64_t *ev /* p(0),p(1),p(2) */, uint64_t *out
 }
 
 extern "C" {
+
+int dp_set_merkle_hasher(int kind) {
+    DP_CHECK(kind == 0 || kind == 1, DP_ERR_INVALID, "dp_set_merkle_hasher: 0 = Poseidon2 (PoseidonHasher), 1 = BLAKE3 (BlakeHasher)");
+    g_hasher.store(kind);
+    return DP_OK;
+}
+int dp_get_merkle_hasher(void) { return g_hasher.load(); }
 
 int dp_poseidon2_init(const uint64_t *ext_rc /*2x4x8*/, const uint64_t *int_rc /*22*/, const uint64_t *diag /*8*/) {
     DP_REQUIRE_CTX();
@@ -612,7 +704,11 @@ int dp_pcs_batch_commit(const dp_mle *const *polys, uint32_t n, uint32_t full_lo
     {
         DpProfScope prof("k_merkle_batch_l0(poseidon2 sponge + compress)", (u64)n * N * (b->is_base ? 8 : 16) + 32 * n0);
         unsigned g = (unsigned)((n0 + 127) / 128);
-        if (b->is_base) k_merkle_batch_l0<false><<<g, 128, 0, c.stream>>>(bp, n, n0, b->level0); else k_merkle_batch_l0<true><<<g, 128, 0, c.stream>>>(bp, n, n0, b->level0);
+        if (blake_on()) {
+            DP_CHECK((b->is_base ? n : 2 * n) <= 128, DP_ERR_UNSUPPORTED, "dp_pcs_batch_commit: BLAKE3 batch leaves are limited to one 1024-byte chunk (128 base / 64 extension polynomials)");
+            if (b->is_base) k_b3_batch_l0<false><<<g, 128, 0, c.stream>>>(bp, n, n0, b->level0); else k_b3_batch_l0<true><<<g, 128, 0, c.stream>>>(bp, n, n0, b->level0);
+        }
+        else if (b->is_base) k_merkle_batch_l0<false><<<g, 128, 0, c.stream>>>(bp, n, n0, b->level0); else k_merkle_batch_l0<true><<<g, 128, 0, c.stream>>>(bp, n, n0, b->level0);
         DP_LAUNCHED();
     }
     if (int e = tree_build(b->tree, b->parts[0]->codeword, !b->is_base, N, b->level0)) { dp_pcs_comm_free(b); return e; }

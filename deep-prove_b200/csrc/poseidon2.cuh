@@ -110,21 +110,15 @@ __device__ __forceinline__ u64 p2x8_permute(u64 s, int lane8) {
     s = p2x8_mds_light(s, lane8);
 #pragma unroll 1
     for (int r = 0; r < 4; r++) { s = p2_pow7(w_add_canon(s, c_p2_ext[0][r][lane8])); s = p2x8_mds_light(s, lane8); }
-    // Internal rounds.  Only word 0 goes through the S-box, so the dependent chain of round r+1 starts from lane 0's value alone.
-    // R = sum of words 1..7 is kept on every lane and refreshed AFTER the state update: its three shuffle+add steps are issued
-    // ahead of the next S-box and complete in its shadow (the next round needs R only after its own pow7), instead of sitting
-    // between the S-box and the multiply-add as an 8-lane all-reduce did (~30 % of the round's latency).
+    // Internal rounds: S-box on lane 0, then an 8-lane all-reduce, then the multiply-add.  (A variant that keeps the sum of words 1..7
+    // on every lane and refreshes it in the shadow of the next S-box was measured SLOWER on B200 -- 21.96 vs 20.20 us per compress,
+    // tools/kbench.cu `lat` -- the extra shuffles it issues ahead of the S-box cost more than the all-reduce latency they hide.)
     const u64 dg = c_p2_diag[lane8];
-    u64 R = p2x8_allsum(lane8 == 0 ? 0ULL : s);
-    u64 rc = c_p2_int[0];
 #pragma unroll 1
     for (int r = 0; r < 22; r++) {
-        const u64 rc_next = c_p2_int[r < 21 ? r + 1 : 21];      // constant for the next round: off the dependent chain
-        if (lane8 == 0) s = p2_pow7(w_add_canon(s, rc));
-        const u64 t0 = shfl8(s, 0);                             // word 0 after the S-box
-        s = w_mul_add(s, dg, ww(w_add(t0, R)));                 // s[i] * diag[i] + (s0' + R)
-        R = p2x8_allsum(lane8 == 0 ? 0ULL : s);
-        rc = rc_next;
+        if (lane8 == 0) s = p2_pow7(w_add_canon(s, c_p2_int[r]));
+        const u64 sum = p2x8_allsum(s);
+        s = w_mul_add(s, dg, ww(sum));
     }
 #pragma unroll 1
     for (int r = 0; r < 4; r++) { s = p2_pow7(w_add_canon(s, c_p2_ext[1][r][lane8])); s = p2x8_mds_light(s, lane8); }

@@ -427,7 +427,7 @@ static constexpr long long SC_RES_TIMEOUT = 6000000000LL;   // ~3 s at 1.9 GHz
 static constexpr u64 SC_TAIL_ABORT = ~0ULL, SC_TAIL_FAILED = ~0ULL - 1;
 struct TMle { const void *cur; gle *work; u64 len, len0; u32 is_ext, where; };
 struct TProd { u32 n_idx; u32 idx[5]; };
-struct ScTail { u32 n_mles, n_products, n_rounds, first_has_challenge; TMle m[SC_RES_MAXM]; TProd p[SC_RES_MAXP]; };
+struct ScTail { u32 n_mles, n_products, n_rounds, first_has_challenge; long long *dbg; TMle m[SC_RES_MAXM]; TProd p[SC_RES_MAXP]; };   // dbg: optional per-round phase clocks (DP_SC_RES_DEBUG)
 
 __device__ __forceinline__ u32 cl_rank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ u32 cl_size() { u32 r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
@@ -458,8 +458,11 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
     if (threadIdx.x == 0) for (u32 p = 0; p < np; p++) for (u32 j = 0; j < sp[p].n_idx; j++) { u32 mi = sp[p].idx[j]; if (swriter[mi] == 0xff) swriter[mi] = (unsigned char)p; }
     __syncthreads();
     gle r = r0;
+    long long *const dbg = cfg->dbg;
+#define RES_MARK(ph) do { if (dbg && rank == 0 && threadIdx.x == 0) dbg[k * 8 + (ph)] = clock64(); } while (0)
     for (u32 k = 0; k < nr; k++) {
         const u64 seq = seq0 + k;
+        RES_MARK(0);
         if (k > 0) {   // wait for the host's challenge for this round
             if (rank == 0 && threadIdx.x == 0) {
                 long long t0 = clock64(); u64 v, status = 0;
@@ -476,6 +479,7 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
             if (status) { if (rank == 0 && threadIdx.x == 0 && status == 2) { __threadfence_system(); *flag = SC_TAIL_FAILED; } return; }   // uniform over the cluster
             r = e_make(__ldcg(xctl + 1), __ldcg(xctl + 2));
         }
+        RES_MARK(1);
         const bool fold = (k > 0) || cfg->first_has_challenge;
         for (u32 i = threadIdx.x; i < nm; i += blockDim.x) {
             bool f = fold && sm[i].len > 1;
@@ -502,6 +506,7 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
             pd.d = pr.n_idx; pd.allbase = allbase; pd.konst = newlen == 1; pd.npairs = newlen >> 1;
         }
         __syncthreads();
+        RES_MARK(2);
         // work: slot (p, s) = sub-slice s of product p's pairs; warp gw owns slots gw, gw + W, ...
         for (u32 slot = gw; slot < np * G; slot += W) {
             const u32 p = slot / G, s = slot % G;
@@ -526,7 +531,9 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
                 if (lane == 0) __stcg(reinterpret_cast<ulonglong2 *>(xpart + (u64)slot * SC_NACC + t), make_ulonglong2(ws_reduce(v0), ws_reduce(v1)));
             }
         }
+        RES_MARK(3);
         cl_sync();                                             // warp partials and folded tables of every CTA are visible
+        RES_MARK(4);
         for (u32 i = threadIdx.x; i < nm; i += blockDim.x) if (sfold[i]) {
             TMle &m = sm[i];
             m.cur = sdst[i]; m.where = (sdst[i] == m.work) ? 1 : 2; m.len >>= 1; m.is_ext = 1;
@@ -549,7 +556,9 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
                 }
             }
             __syncthreads();
+            RES_MARK(5);
             if (threadIdx.x == 0) { __threadfence_system(); *flag = seq; }
+            RES_MARK(6);
         }
         // CTAs other than 0 run ahead to the next cluster barrier; xpart is not rewritten before it (the work phase follows it)
     }
@@ -600,6 +609,7 @@ struct dp_sc {
     bool tail_enabled = false, tail_active = false; u32 tail_last_round = 0;
     ScTail *h_tail = nullptr; u64 *h_chal = nullptr;
     gle *d_xpart = nullptr; u64 *d_xctl = nullptr;        // resident cluster kernel: warp partials, [status, c0, c1]
+    long long *h_dbg = nullptr; u32 dbg_rounds = 0;
     u64 last_ops = 0;
     std::vector<gle> challenges;
     u64 last_bytes = 0;
@@ -628,6 +638,15 @@ static int sc_free_all(dp_sc *s) {
     dp_dev_free(s->d_xpart); dp_dev_free(s->d_xctl);
     dp_pinned_free(s->h_flag);
     dp_pinned_free(s->h_descs); dp_pinned_free(s->h_out); dp_pinned_free(s->h_fin); dp_pinned_free(s->h_pairs);
+    if (s->h_dbg) {   // DP_SC_RES_DEBUG: device clocks of CTA 0 / thread 0 per round: wait-for-challenge | broadcast | descriptors | work | cluster barrier | sum+store | fence+flag
+        cudaStreamSynchronize(dp_ctx().stream);
+        for (u32 k = 0; k < s->dbg_rounds && k < 64; k++) {
+            const long long *d = s->h_dbg + 8 * k;
+            fprintf(stderr, "[sc_res] round %2u cycles: wait %6lld bcast %5lld desc %5lld work %6lld clsync %5lld sum %5lld signal %5lld | total-excl-wait %6lld\n", k,
+                    d[1] - d[0], 0LL, d[2] - d[1], d[3] - d[2], d[4] - d[3], d[5] - d[4], d[6] - d[5], d[6] - d[1]);
+        }
+        dp_pinned_free(s->h_dbg);
+    }
     dp_pinned_free(s->h_tail); dp_pinned_free(s->h_chal);
     return DP_OK;
 }
@@ -726,6 +745,8 @@ static int sc_tail_round(dp_sc *s, gle r, bool fold, uint64_t *out_evals) {
         }
         for (u32 p = 0; p < s->n_products; p++) { t.p[p].n_idx = s->products[p].n_idx; for (u32 j = 0; j < 5; j++) t.p[p].idx[j] = s->products[p].idx[j]; }
         s->h_chal[0] = 0;
+        t.dbg = nullptr;
+        if (getenv("DP_SC_RES_DEBUG")) { if (!s->h_dbg && (e = dp_pinned_alloc((void **)&s->h_dbg, sizeof(long long) * 8 * 64))) return e; memset(s->h_dbg, 0, sizeof(long long) * 8 * 64); t.dbg = s->h_dbg; s->dbg_rounds = t.n_rounds; }
         // cluster size by the first resident round's work: ~512 pair-items per CTA, a power of two <= 8 (portable cluster size)
         const u64 work = sc_round_work(s, fold);
         u32 ncta = 1; while (ncta < SC_RES_MAXCTA && (u64)ncta * 512 < work) ncta <<= 1;

@@ -29,12 +29,15 @@ uint64_t dph_poseidon2_selfcheck(uint64_t n, uint64_t seed) {
     return bad;
 }
 
-void *dph_transcript_new(const char *label) { return new BasicTranscript(label); }
-void dph_transcript_free(void *t) { delete (BasicTranscript *)t; }
-void dph_transcript_append_f(void *t, const uint64_t *f, uint64_t n) { for (uint64_t i = 0; i < n; i++) ((BasicTranscript *)t)->append_field_element(f[i]); }
-void dph_transcript_append_msg(void *t, const uint8_t *m, uint64_t n) { ((BasicTranscript *)t)->append_message(m, n); }
-void dph_transcript_append_e(void *t, const uint64_t *e, uint64_t n) { for (uint64_t i = 0; i < n; i++) ((BasicTranscript *)t)->append_field_element_ext(Ext(e[2 * i], e[2 * i + 1])); }
-void dph_transcript_challenge(void *t, const char *label, uint64_t *out) { Ext c = ((BasicTranscript *)t)->get_and_append_challenge(label); out[0] = c.c0; out[1] = c.c1; }
+// Hasher pair of everything proved from now on: 0 = PoseidonHasher + BasicTranscript (default), 1 = BlakeHasher + BlakeTranscript
+// (the reference's cargo feature `blake`: mpcs/src/lib.rs:339-342, zkml/src/bin/bench.rs:29-44).  Process-wide; set it between proofs.
+int dph_set_hasher(int kind) { if (kind != 0 && kind != 1) { g_herr = "dph_set_hasher: 0 or 1"; return 1; } if (dp_set_merkle_hasher(kind) != DP_OK) { g_herr = dp_last_error(); return 1; } dp::hasher_mode() = kind; return 0; }
+void *dph_transcript_new(const char *label) { return new DynTranscript(label); }
+void dph_transcript_free(void *t) { delete (DynTranscript *)t; }
+void dph_transcript_append_f(void *t, const uint64_t *f, uint64_t n) { for (uint64_t i = 0; i < n; i++) ((DynTranscript *)t)->append_field_element(f[i]); }
+void dph_transcript_append_msg(void *t, const uint8_t *m, uint64_t n) { ((DynTranscript *)t)->append_message(m, n); }
+void dph_transcript_append_e(void *t, const uint64_t *e, uint64_t n) { for (uint64_t i = 0; i < n; i++) ((DynTranscript *)t)->append_field_element_ext(Ext(e[2 * i], e[2 * i + 1])); }
+void dph_transcript_challenge(void *t, const char *label, uint64_t *out) { Ext c = ((DynTranscript *)t)->get_and_append_challenge(label); out[0] = c.c0; out[1] = c.c1; }
 
 // VirtualPolynomial numbers MLEs by FIRST USE in the products (virtual_poly.rs:168-177), and get_mle_final_evaluations()
 // returns them in that order; the C entry points below report final evaluations in the CALLER's `mles` order instead.
@@ -51,7 +54,7 @@ static void write_finals(const ExtVec &fin, const std::vector<uint32_t> &remap, 
     }
 }
 
-// IOPProverState::prove_parallel over device MLE handles with BasicTranscript::new(label) (or an
+// IOPProverState::prove_parallel over device MLE handles with DynTranscript::new(label) (or an
 // existing transcript when `transcript` is non-null).  out_msgs: nv x (max_deg+1) x E.
 int dph_sumcheck_prove_parallel(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *products, uint32_t n_products,
                                 uint32_t max_nv, const char *label, void *transcript, uint64_t *out_point, uint64_t *out_msgs,
@@ -70,8 +73,8 @@ int dph_sumcheck_prove_parallel(dp_mle *const *mles, uint32_t n_mles, const dp_s
         vp.add_mle_list(l, Ext(products[p].coef[0], products[p].coef[1]));
     }
     std::vector<uint32_t> remap = first_use_remap(products, n_products, n_mles);
-    BasicTranscript local(label ? label : "");
-    BasicTranscript &t = transcript ? *(BasicTranscript *)transcript : local;
+    DynTranscript local(label ? label : "");
+    DynTranscript &t = transcript ? *(DynTranscript *)transcript : local;
     auto res = IOPProverState::prove_parallel(std::move(vp), t);
     size_t deg = res.first.proofs.empty() ? 0 : res.first.proofs[0].evaluations.size() - 1;
     *out_max_deg = (uint32_t)deg;
@@ -99,7 +102,7 @@ int dph_pcs_open(dp_mle *poly, uint32_t full_log, const uint64_t *point, const c
     auto comm = Basefold::commit(pp, m);
     if (out_root) memcpy(out_root, comm.root.v, 32);
     ExtVec pt; for (uint32_t i = 0; i < nv; i++) pt.push_back(Ext(point[2 * i], point[2 * i + 1]));
-    BasicTranscript t(label);
+    DynTranscript t(label);
     BasefoldProof pr = Basefold::open(pp, m, comm, pt, t);
     std::vector<uint64_t> f = pr.flatten();
     *out_len = f.size();
@@ -124,7 +127,7 @@ int dph_pcs_batch_open(dp_mle *const *polys, uint32_t n, uint32_t full_log, cons
         Evaluation ev; ev.poly = i; ev.point = i; ev.value = ms.back().evaluate(pt);
         evals.push_back(ev);
     }
-    BasicTranscript t(label);
+    DynTranscript t(label);
     BasefoldProof pr = Basefold::batch_open(pp, ms, comms, pts, evals, t);
     std::vector<uint64_t> f = pr.flatten();
     *out_len = f.size();
@@ -178,8 +181,8 @@ int dph_zkml_prove(void *handle, const int64_t *input, int mode, const char *lab
     ZkHandle *h = (ZkHandle *)handle;
     size_t w = h->model.input_len;
     if (mode == 0 || mode == 1) { h->trace_input.assign(input, input + w); h->trace = run_device(h->ctx, h->trace_input); check(dp_synchronize()); if (mode == 1) return 0; }
-    BasicTranscript t(label);
-    Prover<BasicTranscript> prover(h->ctx, t);
+    DynTranscript t(label);
+    Prover<DynTranscript> prover(h->ctx, t);
     Proof p = prover.prove(h->trace);
     if (out) {
         std::vector<uint64_t> f = p.flatten(h->model.nodes.size());
@@ -210,8 +213,8 @@ struct ZkPool {
             { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || pending > 0; }); if (stop) break; pending--; inflight++; }
             try {
                 if (!inited) { dp::check(dp_init(device)); inited = true; }
-                dp::BasicTranscript t(label);
-                dp::zkml::Prover<dp::BasicTranscript> prover(h->ctx, t);
+                dp::DynTranscript t(label);
+                dp::zkml::Prover<dp::DynTranscript> prover(h->ctx, t);
                 if (e2e) {   // from the host input vector: inference, prove, serialised proof in host memory
                     dp::zkml::Proof p = prover.prove(h->trace_input);
                     std::vector<uint64_t> bytes = p.flatten(h->model.nodes.size());
@@ -271,7 +274,7 @@ extern "C" int dph_sumcheck_prove_sharded(uint32_t world, uint32_t rank, dp_mle 
         views.push_back(DeviceMle::wrap_device(dp_mle_device_ptr(mles[i]), len, ext));
     }
     for (uint32_t p = 0; p < n_products; p++) { std::vector<DeviceMle> l; for (uint32_t j = 0; j < products[p].n_idx; j++) l.push_back(views.at(products[p].idx[j])); vp.add_mle_list(l, Ext(products[p].coef[0], products[p].coef[1])); }
-    BasicTranscript tr(label);
+    DynTranscript tr(label);
     std::pair<IOPProof, IOPProverState> res;
     if (shm_region) {
         ShmExchange ex(shm_region, world, rank); if (shm_seq) ex.seq = *shm_seq;
@@ -306,7 +309,7 @@ extern "C" int dph_sumcheck_prove_batch_polys(uint32_t T, dp_mle *const *mles, u
         for (uint32_t p = 0; p < n_products; p++) { std::vector<DeviceMle> l; for (uint32_t j = 0; j < products[p].n_idx; j++) l.push_back(views.at(products[p].idx[j])); vp.add_mle_list(l, Ext(products[p].coef[0], products[p].coef[1])); }
         polys.push_back(std::move(vp));
     }
-    BasicTranscript tr(label);
+    DynTranscript tr(label);
     auto res = IOPProverState::prove_batch_polys(T, std::move(polys), tr);
     for (size_t i = 0; i < res.first.point.size(); i++) { out_point[2 * i] = res.first.point[i].c0; out_point[2 * i + 1] = res.first.point[i].c1; }
     size_t k = 0;
@@ -334,7 +337,7 @@ extern "C" int dph_conv_prove(uint32_t kw, uint32_t kx, uint32_t n_x, uint32_t r
     if (out_after_bias) memcpy(out_after_bias, pd.output_as_element.data(), 8 * pd.output_as_element.size());
     if (out_cleared) memcpy(out_cleared, cleared.data(), 8 * cleared.size());
     if (!out_len) return 0;
-    BasicTranscript t(label);
+    DynTranscript t(label);
     Claim cl; for (size_t i = 0; i < ceil_log2(cleared.size()); i++) cl.point.push_back(t.read_challenge());
     cl.eval = DeviceMle::from_evaluations_vec(to_base(cleared)).evaluate(cl.point);
     ConvProof pr; Claim in_claim = c.prove_convolution_step(t, cl, pd, pr);
@@ -387,7 +390,7 @@ extern "C" int dph_pcs_simple_batch(dp_mle *const *polys, uint32_t n, uint32_t f
     if (!point) return 0;
     ExtVec pt, ev; for (uint32_t i = 0; i < nv; i++) pt.push_back(Ext(point[2 * i], point[2 * i + 1]));
     for (uint32_t i = 0; i < n; i++) ev.push_back(Ext(evals[2 * i], evals[2 * i + 1]));
-    BasicTranscript t(label);
+    DynTranscript t(label);
     SimpleBatchProof sp = Basefold::simple_batch_open(pp, comm, pt, ev, t);
     std::vector<uint64_t> f = sp.flatten();
     *out_len = f.size();
@@ -408,7 +411,7 @@ extern "C" int dph_pcs_batch_open_evals(dp_mle *const *polys, uint32_t n, uint32
     size_t o = 0;
     for (uint32_t k = 0; k < n_points; k++) { ExtVec pt; for (uint32_t j = 0; j < point_nv[k]; j++) pt.push_back(Ext(points[2 * (o + j)], points[2 * (o + j) + 1])); o += point_nv[k]; pts.push_back(pt); }
     for (uint32_t j = 0; j < n_evals; j++) { Evaluation ev; ev.poly = eval_poly[j]; ev.point = eval_point[j]; ev.value = ms.at(ev.poly).evaluate(pts.at(ev.point)); evals.push_back(ev); }
-    BasicTranscript t(label);
+    DynTranscript t(label);
     BasefoldProof pr = Basefold::batch_open(pp, ms, comms, pts, evals, t);
     std::vector<uint64_t> f = pr.flatten();
     *out_len = f.size();

@@ -125,4 +125,57 @@ class BasicTranscript {
     Sponge sp_;
 };
 
+// BlakeTranscript (transcript/src/blake.rs), the transcript of the reference's `blake` feature (zkml/src/bin/bench.rs:29-44): one running
+// BLAKE3 hasher.  Through trait Transcript<E> (transcript/src/lib.rs:22-93) a base element is absorbed as update("field_element") +
+// update(BigUint::to_bytes_le of the canonical value: no trailing zero bytes, [0] for zero); an extension element as
+// update("field_element_ext") + update(bytes(c0) || bytes(c1)); a message goes through the trait default (8-byte chunks -> field
+// elements -> one append each); a challenge is update("challenge") + 16 bytes of finalize_xof read as two little-endian u64, retried
+// until both are canonical (ff_ext/src/lib.rs:29-41,246-254).  BLAKE3 itself: include/dp_blake3.h (pinned against the Python package).
+}  // namespace dp
+#include "../../include/dp_blake3.h"
+namespace dp {
+class BlakeTranscript {
+  public:
+    explicit BlakeTranscript(const std::string &label) { h_.update(label.data(), label.size()); }   // BlakeTranscript::new: raw label bytes
+    void append_field_element(u64 f) { uint8_t b[8]; size_t n = le(canon(f), b); h_.update("field_element", 13); h_.update(b, n); }
+    void append_field_elements(const std::vector<u64> &f) { for (u64 x : f) append_field_element(x); }
+    void append_message(const uint8_t *m, size_t n) { for (size_t i = 0; i < n; i += 8) { u64 v = 0; memcpy(&v, m + i, n - i < 8 ? n - i : 8); append_field_element(v); } }
+    void append_message(const std::string &s) { append_message((const uint8_t *)s.data(), s.size()); }
+    void append_usize(u64 v) { append_field_element(v); }
+    void append_field_element_ext(const Ext &e) { uint8_t b[16]; size_t n0 = le(canon(e.c0), b), n1 = le(canon(e.c1), b + n0); h_.update("field_element_ext", 17); h_.update(b, n0 + n1); }
+    void append_field_element_exts(const ExtVec &v) { for (auto &e : v) append_field_element_ext(e); }
+    Ext read_challenge() {
+        for (;;) {
+            h_.update("challenge", 9); nfin_++;
+            uint8_t o[16]; h_.finalize(o, 16);
+            u64 a, b; memcpy(&a, o, 8); memcpy(&b, o + 8, 8);
+            if (a < P && b < P) return Ext(a, b);
+        }
+    }
+    Ext get_and_append_challenge(const std::string &label) { append_message(label); return read_challenge(); }
+    u64 permutations() const { return nfin_; }    // statistics: finalisations
+  private:
+    static size_t le(u64 c, uint8_t b[8]) { size_t n = 0; for (int k = 0; k < 8; k++) { b[k] = (uint8_t)(c >> (8 * k)); if (b[k]) n = k + 1; } return n ? n : 1; }
+    dpb3::Hasher h_; u64 nfin_ = 0;
+};
+
+// The transcript the C entry points of the host library build: BasicTranscript, or BlakeTranscript after dph_set_hasher(1)
+inline int &hasher_mode() { static int m = 0; return m; }
+class DynTranscript {
+  public:
+    explicit DynTranscript(const std::string &label) : blake_(hasher_mode() == 1), b_(blake_ ? std::string() : label), k_(blake_ ? label : std::string()) {}
+    void append_field_element(u64 f) { blake_ ? k_.append_field_element(f) : b_.append_field_element(f); }
+    void append_field_elements(const std::vector<u64> &f) { for (u64 x : f) append_field_element(x); }
+    void append_message(const uint8_t *m, size_t n) { blake_ ? k_.append_message(m, n) : b_.append_message(m, n); }
+    void append_message(const std::string &s) { append_message((const uint8_t *)s.data(), s.size()); }
+    void append_usize(u64 v) { blake_ ? k_.append_usize(v) : b_.append_usize(v); }
+    void append_field_element_ext(const Ext &e) { blake_ ? k_.append_field_element_ext(e) : b_.append_field_element_ext(e); }
+    void append_field_element_exts(const ExtVec &v) { for (auto &e : v) append_field_element_ext(e); }
+    Ext read_challenge() { return blake_ ? k_.read_challenge() : b_.read_challenge(); }
+    Ext get_and_append_challenge(const std::string &label) { append_message(label); return read_challenge(); }
+    u64 permutations() const { return blake_ ? k_.permutations() : b_.permutations(); }
+  private:
+    bool blake_; BasicTranscript b_; BlakeTranscript k_;
+};
+
 }  // namespace dp

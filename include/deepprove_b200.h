@@ -160,6 +160,11 @@ int dp_mle_repeat(const dp_mle *src, uint32_t times, dp_mle **out);
 typedef struct dp_pcs_comm dp_pcs_comm;  /* BasefoldCommitmentWithWitness (mpcs/src/basefold/structure.rs:63-72) */
 typedef struct dp_pcs_open dp_pcs_open;  /* prover state of one commit phase (oracles + their trees) */
 
+/* MerkleHasher of every commitment built from now on (process-wide): 0 = PoseidonHasher (default), 1 = BlakeHasher
+ * (mpcs/src/util/hash.rs:44-98; the reference selects with the cargo feature `blake`, mpcs/src/lib.rs:339-342).  Digests are
+ * 4 x u64 in both cases (BLAKE3: the 32 digest bytes as little-endian words).  Do not mix hashers within one proof. */
+int dp_set_merkle_hasher(int kind);
+int dp_get_merkle_hasher(void);
 /* Optional: replace the built-in Poseidon2 constants (HL Goldilocks width-8 instance) with the ones the
  * Rust host reads from p3-goldilocks: ext_rc[2][4][8], int_rc[22], diag[8]  (ff_ext/src/lib.rs:179-194). */
 int dp_poseidon2_init(const uint64_t *ext_rc, const uint64_t *int_rc, const uint64_t *diag);

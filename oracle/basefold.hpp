@@ -166,6 +166,8 @@ static inline std::vector<E> parallel_pi(const std::vector<E> &evals, const std:
 
 struct CommitPhaseProof { std::vector<std::vector<E>> sumcheck_messages; std::vector<Digest> roots; std::vector<E> final_message; };
 
+// PoseidonHasher: the four digest elements; BlakeHasher: append_message(32 digest bytes) (mpcs/src/util/hash.rs:57-62, 96-98) -- the trait's
+// append_message turns them into four field elements too (each 8-byte word taken modulo p), so one line serves both
 static inline void digest_to_transcript(const Digest &d, Transcript &t) { for (int i = 0; i < 4; i++) t.append_field_element(d.v[i]); }
 static inline FVec ext_fvec(const std::vector<E> &v) { FVec f; f.is_ext = true; f.e = v; return f; }
 

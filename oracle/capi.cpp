@@ -56,6 +56,20 @@ int dpo_evaluate(const u64 *evals, u64 len, int is_ext, const u64 *point, u32 nv
 void dpo_build_eq(const u64 *point, u32 nv, u64 *out) { auto v = build_eq_x_r_vec(mk_point(point, nv)); for (size_t i = 0; i < v.size(); i++) put_e(out, i, v[i]); }
 void dpo_eq_eval(const u64 *x, const u64 *y, u32 n, u64 *out) { put_e(out, 0, eq_eval(mk_point(x, n), mk_point(y, n))); }
 
+// ---- hasher selection + BLAKE3 (include/dp_blake3.h) ----
+void dpo_set_hash_mode(int m) { hash_mode_var().store(m == 1 ? 1 : 0); }      // 0 Poseidon2 + BasicTranscript, 1 BLAKE3 + BlakeTranscript
+int dpo_get_hash_mode() { return hash_mode_var().load(); }
+// hash `n` bytes fed in pieces of `piece` bytes (0 = all at once); when `mid` > 0 a finalize is taken after `mid` bytes first (the
+// running hasher must not be disturbed by it); `out_len` bytes of extendable output
+void dpo_blake3(const uint8_t *data, u64 n, u64 piece, u64 mid, uint8_t *out, u64 out_len) {
+    dpb3::Hasher h; u64 off = 0; uint8_t tmp[64];
+    if (piece == 0) piece = n ? n : 1;
+    while (off < n) { u64 take = std::min<u64>(piece, n - off); if (mid > off && mid < off + take) take = mid - off; h.update(data + off, take); off += take; if (off == mid) h.finalize(tmp, 64); }
+    h.finalize(out, out_len);
+}
+void dpo_hash_bases(const u64 *in, u64 n, u64 *out) { Digest d = hash_or_noop(in, n); memcpy(out, d.v, 32); }
+void dpo_hash_two_digests(const u64 *a, const u64 *b, u64 *out) { Digest x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Digest d = compress(x, y); memcpy(out, d.v, 32); }
+
 // ---- Poseidon2 / challenger / transcript ----
 void dpo_poseidon2_permute(u64 *state) { poseidon2_permute(state); }
 void dpo_hash_or_noop(const u64 *in, u64 n, u64 *out) { Digest d = hash_or_noop(in, n); memcpy(out, d.v, 32); }

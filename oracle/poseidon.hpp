@@ -10,6 +10,8 @@
 #pragma once
 #include "field.hpp"
 #include "../include/dp_poseidon2_constants.h"
+#include "../include/dp_blake3.h"
+#include <atomic>
 #include <array>
 #include <cstring>
 
@@ -121,8 +123,22 @@ struct Digest {
     bool operator==(const Digest &o) const { return memcmp(v, o.v, sizeof v) == 0; }
 };
 
+// Which MerkleHasher / Transcript pair the checker runs (the reference picks at compile time: feature `blake`, mpcs/src/lib.rs:339-342,
+// zkml/src/bin/bench.rs:29-44).  0 = PoseidonHasher + BasicTranscript (default), 1 = BlakeHasher + BlakeTranscript.  The blake pair is
+// fully determined by the reference sources + standard BLAKE3, i.e. it is the PINNED variant of every digest, challenge and proof byte.
+inline std::atomic<int> &hash_mode_var() { static std::atomic<int> m{0}; return m; }
+static inline bool blake_mode() { return hash_mode_var().load(std::memory_order_relaxed) == 1; }
+// BlakeHasher::hash_bases (mpcs/src/util/hash.rs:83-89): BLAKE3 over the canonical little-endian u64 bytes of the elements
+static inline Digest blake_hash_bases(const u64 *in, size_t n) {
+    dpb3::Hasher h;
+    for (size_t i = 0; i < n; i++) { u64 c = f_canon(in[i]); uint8_t b[8]; for (int k = 0; k < 8; k++) b[k] = (uint8_t)(c >> (8 * k)); h.update(b, 8); }
+    uint8_t o[32]; h.finalize(o, 32);
+    Digest d; memcpy(d.v, o, 32);          // the 32 digest bytes, carried as four little-endian words
+    return d;
+}
 // PoseidonHash::hash_or_noop (poseidon_hash.rs:22-28): <= 4 elements -> zero-padded copy, no permutation
 static inline Digest hash_or_noop(const u64 *in, size_t n) {
+    if (blake_mode()) return blake_hash_bases(in, n);
     Digest d;
     if (n <= 4) {
         for (size_t i = 0; i < 4; i++) d.v[i] = i < n ? in[i] : 0;
@@ -135,6 +151,10 @@ static inline Digest hash_or_noop(const u64 *in, size_t n) {
 }
 // compress (poseidon_hash.rs:66-71): observe x(4) -> permute, observe y(4) -> permute, sample 4
 static inline Digest compress(const Digest &x, const Digest &y) {
+    if (blake_mode()) {   // BlakeHasher::hash_two_digests (hash.rs:90-95): BLAKE3(a.bytes || b.bytes)
+        uint8_t in[64], o[32]; memcpy(in, x.v, 32); memcpy(in + 32, y.v, 32); dpb3::hash(in, 64, o);
+        Digest d; memcpy(d.v, o, 32); return d;
+    }
     Challenger c;
     for (int i = 0; i < 4; i++) c.observe(x.v[i]);
     for (int i = 0; i < 4; i++) c.observe(y.v[i]);
@@ -155,18 +175,44 @@ static inline std::vector<u64> bytes_to_field_elements(const uint8_t *b, size_t 
     return out;
 }
 
-// BasicTranscript (transcript/src/basic.rs) over trait Transcript (transcript/src/lib.rs:22-93)
+// BasicTranscript (transcript/src/basic.rs) over trait Transcript (transcript/src/lib.rs:22-93); in blake mode BlakeTranscript
+// (transcript/src/blake.rs): one running BLAKE3 hasher; a base element is absorbed as update("field_element") + update(LE bytes of the
+// canonical value WITHOUT trailing zero bytes -- BigUint::to_bytes_le, [0] for zero); an extension element as
+// update("field_element_ext") + update(bytes(c0) || bytes(c1)); a message goes through the trait default (lib.rs:42-45: 8-byte chunks
+// -> field elements -> append_field_elements); a challenge is update("challenge") + 16 bytes of finalize_xof, parsed as two LE u64,
+// retried until both are canonical (ff_ext/src/lib.rs:29-41, 246-254).
 struct Transcript {
     Challenger ch;
-    Transcript() {}
-    explicit Transcript(const char *label) { append_message((const uint8_t *)label, strlen(label)); }
-    void append_field_element(u64 f) { ch.observe(f); }
-    void append_field_elements(const u64 *f, size_t n) { for (size_t i = 0; i < n; i++) ch.observe(f[i]); }
-    void append_message(const uint8_t *m, size_t n) { for (u64 f : bytes_to_field_elements(m, n)) ch.observe(f); }
+    dpb3::Hasher bh; bool blake = false;
+    Transcript() : blake(blake_mode()) {}
+    explicit Transcript(const char *label) : blake(blake_mode()) {
+        if (blake) bh.update(label, strlen(label));                       // BlakeTranscript::new(label): raw label bytes
+        else append_message((const uint8_t *)label, strlen(label));
+    }
+    static size_t biguint_le(u64 c, uint8_t b[8]) { size_t n = 0; for (int k = 0; k < 8; k++) { b[k] = (uint8_t)(c >> (8 * k)); if (b[k]) n = k + 1; } return n ? n : 1; }
+    void append_field_element(u64 f) {
+        if (!blake) { ch.observe(f); return; }
+        uint8_t b[8]; size_t n = biguint_le(f_canon(f), b);
+        bh.update("field_element", 13); bh.update(b, n);
+    }
+    void append_field_elements(const u64 *f, size_t n) { for (size_t i = 0; i < n; i++) append_field_element(f[i]); }
+    void append_message(const uint8_t *m, size_t n) { for (u64 f : bytes_to_field_elements(m, n)) append_field_element(f); }
     void append_usize(u64 v) { append_message((const uint8_t *)&v, 8); }  // usize.to_le_bytes()
-    void append_field_element_ext(E e) { ch.observe(e.c0); ch.observe(e.c1); }
+    void append_field_element_ext(E e) {
+        if (!blake) { ch.observe(e.c0); ch.observe(e.c1); return; }
+        uint8_t b[16]; size_t n0 = biguint_le(f_canon(e.c0), b), n1 = biguint_le(f_canon(e.c1), b + n0);
+        bh.update("field_element_ext", 17); bh.update(b, n0 + n1);
+    }
     void append_field_element_exts(const std::vector<E> &v) { for (E e : v) append_field_element_ext(e); }
-    E read_challenge() { u64 a = ch.sample(); u64 b = ch.sample(); return E(a, b); }
+    E read_challenge() {
+        if (!blake) { u64 a = ch.sample(); u64 b = ch.sample(); return E(a, b); }
+        for (;;) {
+            bh.update("challenge", 9);
+            uint8_t o[16]; bh.finalize(o, 16);
+            u64 a, b; memcpy(&a, o, 8); memcpy(&b, o + 8, 8);
+            if (a < GL_P && b < GL_P) return E(a, b);
+        }
+    }
     E get_and_append_challenge(const char *label) { append_message((const uint8_t *)label, strlen(label)); return read_challenge(); }
     std::vector<E> sample_vec(size_t n) { std::vector<E> v; for (size_t i = 0; i < n; i++) v.push_back(read_challenge()); return v; }
 };

@@ -37,6 +37,11 @@ def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def set_hash_mode(kind):
+    """0 = Poseidon2 + BasicTranscript (default), 1 = BLAKE3 + BlakeTranscript (the reference's `blake` feature); process-wide"""
+    lib().dpo_set_hash_mode(int(kind))
+
+
 def splitmix_f(seed, n):
     out = np.empty(n, dtype=np.uint64)
     lib().dpo_splitmix_f(C.c_uint64(seed), C.c_uint64(n), ptr(out))
@@ -150,6 +155,11 @@ class Transcript:
     def challenge(self, label):
         out = np.zeros(2, dtype=np.uint64)
         lib().dpo_transcript_challenge(self.h, label, ptr(out))
+        return out
+
+    def read_challenge(self):
+        out = np.zeros(2, dtype=np.uint64)
+        lib().dpo_transcript_read_challenge(self.h, ptr(out))
         return out
 
     def __del__(self):

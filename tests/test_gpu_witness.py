@@ -34,7 +34,7 @@ def test_requant_columns_and_multiplicities(gpu, n, width):
     fp = ((lw + 24 + 7) // 8) * 8 - lw
     shift, fpm, ibits = lw + fp, 3 << (fp - 2), 2 * 7 + lw + 1
     csize = ibits + (fpm - 1).bit_length() - shift      # Requant::clamping_size
-    x = rng.integers(-(1 << ibits), (1 << ibits) + 1, size=n)
+    x = rng.integers(-(1 << (ibits - 1)), (1 << (ibits - 1)) + 1, size=n)     # the clamping table covers |cin| < 2^(csize-1): |x| <= 2^(ibits-1) stays inside (0.375 * 2^csize)
     tmp = x * fpm + (1 << (shift - 1)); cl = tmp >> shift; co = np.clip(cl, QMIN, QMAX); sh = tmp & ((1 << shift) - 1)
     chunks = [(sh >> (8 * j)) & 255 for j in range(shift // 8)]
     wit = gpu.Witness([(2, 0), (3, csize)])
@@ -53,7 +53,11 @@ def test_requant_rejects_out_of_range_inputs(gpu):
     wit = gpu.Witness([(2, 0), (3, 10)])
     wit.requant(gpu.Mle.upload(to_field(np.array([1 << 40, 0, 0, 0])), False), 16, 3 << 6, 20, 1, 0)
     _, bits = wit.finish()
-    assert bits & 1
+    assert bits & 1          # "Could not apply requantisation, tensor element had absolute value too large"
+    wit = gpu.Witness([(2, 0), (3, 10)])
+    wit.requant(gpu.Mle.upload(to_field(np.array([1 << 19, 0, 0, 0])), False), 16, 3 << 6, 20, 1, 0)   # in range for the op, outside the clamping table
+    _, bits = wit.finish()
+    assert bits == 2
 
 
 def test_relu_and_pool(gpu):
