@@ -89,6 +89,57 @@ __device__ __forceinline__ void p2_permute(u64 (&s)[8]) {      // weak in, weak 
     }
 }
 
+// Latency-optimised formulation for the tree tops (one thread per hash, few hashes): the only serial dependency of the internal
+// rounds is the S-box lane, x' = (d0 + 1) y + R with y = (x + c)^7 and R = the sum of the other seven words, so the chain per round
+// is three multiplications deep -- [t^2 | u = (d0+1) t] -> [t^4 | u t^2] -> (u t^2) t^4 + R -- instead of five (S-box, then the
+// multiply-add); y itself and the seven multiply-adds of the other words sit in the shadow of the next round's chain.  Two extra
+// multiplications per round, exact arithmetic, same digest.
+__device__ __forceinline__ u64 w_mul_addu(u64 a, u64 b, u64 c) {                  // a * b + c -> weak (a, b, c any u64)
+    u64 lo = a * b, hi = __umul64hi(a, b);
+    asm("{\n\tadd.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, 0;\n\t}" : "+l"(lo), "+l"(hi) : "l"(c));
+    return gl_reduce128_weak(lo, hi);
+}
+__device__ __forceinline__ void p2_permute_lat(u64 (&s)[8]) {  // weak in, weak out
+    p2_mds_light(s);
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = p2_pow7(w_add_canon(s[i], c_p2_ext[0][r][i]));
+        p2_mds_light(s);
+    }
+    const u64 d0p1 = c_p2_diag[0] + 1;                          // diag is canonical (< p), so this fits; weak is fine for w_mul
+    p2w R = ww(s[1]);
+#pragma unroll
+    for (int i = 2; i < 8; i++) R = ww_addu(R, s[i]);
+#pragma unroll 2
+    for (int r = 0; r < 22; r++) {
+        const u64 t = w_add_canon(s[0], c_p2_int[r]);
+        const u64 t2 = w_mul(t, t), u = w_mul(t, d0p1);
+        const u64 t4 = w_mul(t2, t2), u3 = w_mul(u, t2), t3 = w_mul(t, t2);
+        s[0] = w_mul_addu(u3, t4, ww_fold(R));
+        const p2w sum = ww_addu(R, w_mul(t3, t4));
+        p2w nr; nr.lo = 0; nr.hi = 0;
+#pragma unroll
+        for (int i = 1; i < 8; i++) { s[i] = w_mul_add(s[i], c_p2_diag[i], sum); nr = ww_addu(nr, s[i]); }
+        R = nr;
+    }
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = p2_pow7(w_add_canon(s[i], c_p2_ext[1][r][i]));
+        p2_mds_light(s);
+    }
+}
+__device__ __forceinline__ void p2_compress_lat(const u64 x[4], const u64 y[4], u64 out[4]) {
+    u64 s[8] = {x[0], x[1], x[2], x[3], 0, 0, 0, 0};
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        if (half) { s[0] = y[0]; s[1] = y[1]; s[2] = y[2]; s[3] = y[3]; }
+        p2_permute_lat(s);
+    }
+    out[0] = gl_canon_weak(s[3]); out[1] = gl_canon_weak(s[2]); out[2] = gl_canon_weak(s[1]); out[3] = gl_canon_weak(s[0]);
+}
+
 // ---- lane-parallel variant: 8 consecutive lanes hold the 8 state words of ONE permutation ----------------
 // Used where a level has too few hashes to fill the GPU with one thread per hash (tree tops, witness-sized
 // trees): the dependent-instruction chain per permutation drops ~3x (every lane does one S-box in the full

@@ -23,6 +23,12 @@ __global__ void k_perm(const u64 *in, u64 *out, int n) {
     p2_permute(s);
     for (int k = 0; k < 8; k++) out[8 * i + k] = gl_canon_weak(s[k]);
 }
+__global__ void k_perm_lat(const u64 *in, u64 *out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n) return;
+    u64 s[8]; for (int k = 0; k < 8; k++) s[k] = in[8 * i + k];
+    p2_permute_lat(s);
+    for (int k = 0; k < 8; k++) out[8 * i + k] = gl_canon_weak(s[k]);
+}
 __global__ void k_perm8(const u64 *in, u64 *out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x; int h = i >> 3, l = i & 7; if (h >= n) return;
     u64 s = p2x8_permute(in[8 * h + l], l);
@@ -54,16 +60,19 @@ int main() {
     // permutation
     std::vector<u64> in(8 * n), pe(8 * n), p8(8 * n);
     for (auto &v : in) v = gl_canon(sm(st));
+    for (int i = 0; i < 64; i++) for (int k = 0; k < 8; k++) in[8 * i + k] = ((i >> (k % 6)) & 1) ? GL_P - 1 - (u64)(i & 3) : (u64)(i & 7);   // extreme canonical words
     u64 *din, *dp; cudaMalloc(&din, n * 64); cudaMalloc(&dp, n * 64);
     cudaMemcpy(din, in.data(), n * 64, cudaMemcpyHostToDevice);
     k_perm<<<n / 128, 128>>>(din, dp, n); cudaMemcpy(pe.data(), dp, n * 64, cudaMemcpyDeviceToHost);
     k_perm8<<<n * 8 / 128, 128>>>(din, dp, n); cudaMemcpy(p8.data(), dp, n * 64, cudaMemcpyDeviceToHost);
-    int b1 = 0, b8 = 0;
+    std::vector<u64> pl(8 * n);
+    k_perm_lat<<<n / 128, 128>>>(din, dp, n); cudaMemcpy(pl.data(), dp, n * 64, cudaMemcpyDeviceToHost);
+    int b1 = 0, b8 = 0, bl = 0;
     for (int i = 0; i < n; i++) {
         uint64_t s[8]; for (int k = 0; k < 8; k++) s[k] = in[8 * i + k];
         dp::Poseidon2::permute(s);
-        for (int k = 0; k < 8; k++) { if (pe[8 * i + k] != s[k]) b1++; if (p8[8 * i + k] != s[k]) b8++; }
+        for (int k = 0; k < 8; k++) { if (pe[8 * i + k] != s[k]) b1++; if (p8[8 * i + k] != s[k]) b8++; if (pl[8 * i + k] != s[k]) bl++; }
     }
-    printf("permute bad=%d  permute_x8 bad=%d  (cuda: %s)\n", b1, b8, cudaGetErrorString(cudaDeviceSynchronize()));
+    printf("permute bad=%d  permute_x8 bad=%d  permute_lat bad=%d  (cuda: %s)\n", b1, b8, bl, cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }

@@ -8,6 +8,8 @@
 #include <string>
 #include <algorithm>
 #include <chrono>
+#include <thread>
+#include <atomic>
 #include "../deep-prove_b200/csrc/poseidon2.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
@@ -133,6 +135,12 @@ __global__ void k_chain_lib(u64 *io, int len) {
     u64 x[4], y[4], o[4];
     for (int k = 0; k < 4; k++) { x[k] = io[8 * threadIdx.x + k]; y[k] = io[8 * threadIdx.x + 4 + k]; }
     for (int it = 0; it < len; it++) { p2_compress(x, y, o); for (int k = 0; k < 4; k++) x[k] = o[k]; }
+    for (int k = 0; k < 4; k++) io[8 * threadIdx.x + k] = x[k];
+}
+__global__ void k_chain_latopt(u64 *io, int len) {
+    u64 x[4], y[4], o[4];
+    for (int k = 0; k < 4; k++) { x[k] = io[8 * threadIdx.x + k]; y[k] = io[8 * threadIdx.x + 4 + k]; }
+    for (int it = 0; it < len; it++) { p2_compress_lat(x, y, o); for (int k = 0; k < 4; k++) x[k] = o[k]; }
     for (int k = 0; k < 4; k++) io[8 * threadIdx.x + k] = x[k];
 }
 __global__ void k_chain_x8(u64 *io, int len) {   // 8 lanes per hash: hash h = thread / 8
@@ -478,6 +486,7 @@ int main(int argc, char **argv) {
         // NB: time_ms re-runs the chain on its own output; the digest printed is from the first clean run
         for (int th : {32, 64, 128, 256}) {
             run("thread-per-hash lib p2_compress", [&](int t) { k_chain_lib<<<1, t>>>(io, LEN); }, th, th);
+            run("thread-per-hash lat-opt (3-deep internal rounds)", [&](int t) { k_chain_latopt<<<1, t>>>(io, LEN); }, th, th);
             run("thread-per-hash v UI=1", [&](int t) { k_chain_tph<1><<<1, t>>>(io, LEN); }, th, th);
             run("thread-per-hash v UI=2", [&](int t) { k_chain_tph<2><<<1, t>>>(io, LEN); }, th, th);
             run("thread-per-hash v UI=11", [&](int t) { k_chain_tph<11><<<1, t>>>(io, LEN); }, th, th);
@@ -564,6 +573,46 @@ int main(int argc, char **argv) {
             double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
             CK(cudaDeviceSynchronize());
             printf("  one launch per round (tiny kernel + membar.sys + flag): %6.2f us per round\n", us / N);
+        }
+    }
+    if (want("launch")) {
+        // How many kernel launches per second does one process sustain from T host threads, each on its own stream?  (a) fire and
+        // forget: T threads x N tiny launches, one sync at the end; (b) round trips: launch, spin on the flag the kernel raises
+        // (the prover's per-round pattern); (c) like (a) with a burst of 4 launches between flag waits (the prover's mix).
+        printf("[launch] tiny-kernel launches from T threads on T streams (one process, one context)\n");
+        for (int T : {1, 2, 4, 8, 16, 24, 32}) {
+            const int N = 20000 / (T > 4 ? 2 : 1);
+            std::vector<cudaStream_t> st(T); std::vector<u64 *> pins(T);
+            for (int t = 0; t < T; t++) { CK(cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking)); CK(cudaHostAlloc((void **)&pins[t], 4096, cudaHostAllocMapped)); pins[t][0] = 0; }
+            for (int mode = 0; mode < 3; mode++) {
+                std::atomic<int> go{0};
+                std::vector<std::thread> th;
+                std::vector<double> call_us(T, 0.0);
+                for (int t = 0; t < T; t++) th.emplace_back([&, t] {
+                    cudaSetDevice(0);
+                    volatile u64 *flag = pins[t]; u64 *outm = pins[t] + 64;
+                    while (!go.load()) {}
+                    double acc = 0;
+                    for (int k = 1; k <= N; k++) {
+                        auto c0 = std::chrono::steady_clock::now();
+                        k_tiny<<<1, 256, 0, st[t]>>>((u64 *)flag, outm, (u64)k + (u64)mode * 1000000);
+                        if (mode == 2) for (int q = 0; q < 3; q++) k_tiny<<<1, 256, 0, st[t]>>>((u64 *)flag, outm, (u64)k + (u64)mode * 1000000);
+                        acc += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - c0).count();
+                        if (mode >= 1) while (__atomic_load_n(&flag[0], __ATOMIC_ACQUIRE) != (u64)k + (u64)mode * 1000000) {}
+                    }
+                    cudaStreamSynchronize(st[t]);
+                    call_us[t] = acc / N;
+                });
+                auto t0 = std::chrono::steady_clock::now();
+                go.store(1);
+                for (auto &x : th) x.join();
+                double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                double per = 0; for (double v : call_us) per += v; per /= T;
+                const double launches = (double)T * N * (mode == 2 ? 4 : 1);
+                printf("  T=%2d %-28s %8.1f k launches/s   %6.2f us per loop iteration per thread, %5.2f us inside the launch call(s)\n", T,
+                       mode == 0 ? "fire-and-forget" : mode == 1 ? "launch + spin on flag" : "4 launches + spin on flag", launches / sec / 1e3, 1e6 * sec / N, per);
+            }
+            for (int t = 0; t < T; t++) { cudaStreamDestroy(st[t]); cudaFreeHost(pins[t]); }
         }
     }
     printf("done (%s)\n", cudaGetErrorString(cudaDeviceSynchronize()));
