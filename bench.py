@@ -266,7 +266,7 @@ class DenseWorkload:
         self.ctx.run_inference(self.x)
         dp.lib().dp_synchronize()
 
-    STREAMS = 16    # concurrent independent proofs per GPU (one host thread + CUDA stream + device arena each)
+    STREAMS = 48    # concurrent independent proofs per GPU (one host thread + CUDA stream + device arena each)
     units_per_step = STREAMS   # one bench step = one batch of STREAMS inference inputs, each proved independently
 
     def step_resident(self, i):
@@ -303,7 +303,7 @@ class CnnWorkload:
     3x32x32 input; the arrays come from deep-prove_b200/models.py and both arms prove the identical model and input."""
     key = "cnn264k"
     metric, unit = "proofs/sec", "proofs/s"
-    STREAMS = 16
+    STREAMS = 48
     units_per_step = STREAMS
     cpu_frac = 1.0
 
@@ -360,14 +360,29 @@ class CnnWorkload:
 WORKLOADS = {"dense4m": DenseWorkload, "cnn264k": CnnWorkload, "sumcheck20": SumcheckWorkload, "basefold24": BasefoldWorkload}
 
 
+def cpu_budget():
+    """CPUs this rank may use: the process's affinity mask and the cgroup CPU quota (the 1-GPU measurement boxes report 128 logical
+    CPUs but run the container under cpu.max = 16 CPUs: a spinning thread per proof in flight is throttled beyond that),
+    divided among the ranks of this node"""
+    try:
+        cpus = float(len(os.sched_getaffinity(0)))
+    except Exception:
+        cpus = float(os.cpu_count() or 16)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            cpus = min(cpus, float(quota) / float(period))
+    except Exception:
+        pass
+    world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    return max(2.0, cpus / max(world, 1))
+
+
 def host_workers(streams):
-    """host threads per GPU: every in-flight proof has a thread that hashes and waits for its rounds, so never oversubscribe the
-    box (8 ranks x 16 threads would take all 128 hardware threads of the measurement host and starve everything else)"""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    cpus = os.cpu_count() or 16
-    if world * (streams + 2) <= cpus:
-        return streams
-    return max(4, cpus // world - 4)
+    """independent proofs in flight per GPU = proving threads.  They wait for the device through the library's blocking mode
+    (dp_set_wait_mode(1): sleeping threads, one poller), so the count is set by what keeps the GPU busy (`streams`), capped at
+    three threads per CPU of this rank's budget."""
+    return int(max(4, min(streams, 3 * cpu_budget())))
 
 
 def pin_to_gpu_numa_node(torch, local_rank):
@@ -558,12 +573,15 @@ def run_gpu_workload(env, wl, K, W, full):
     latency_ms = None
     clk = ClockSampler(local_rank)
     if batched:
+        dp.set_wait_mode(1)      # many proofs in flight: proving threads sleep on the library's poller instead of spinning
         with clk:
             ms, launches = timed_many(wl.run_resident, K, W)
         ms_e2e, _ = timed_many(wl.run_e2e, K, 1)
         if full:
+            dp.set_wait_mode(0)  # one proof at a time: the single proving thread spins (lowest latency)
             lat, _ = timed(wl.step_resident, min(K, 10), 2)     # one proof at a time, L2 flushed between proofs
             latency_ms = lat / min(K, 10)
+            dp.set_wait_mode(1)
     else:
         with clk:
             ms, launches = timed(wl.step_resident, K, W)
@@ -583,6 +601,7 @@ def run_gpu_workload(env, wl, K, W, full):
     torch.cuda.synchronize()
     prof = dp.profile_read(with_units=True)
     dp.profile_enable(False)
+    dp.set_wait_mode(0)
     rows, alu_ceiling = kernel_table(prof, peaks, clocks.get("sm_mhz"), env["sm_count"])
 
     ups = getattr(wl, "units_per_step", 1)

@@ -52,7 +52,7 @@ static int bf_prepare() {
         DP_CUDA(cudaMalloc((void **)&tab, sizeof(u64) * 3 * 2048));
         k_pow_table<<<24, 256, 0, dp_ctx().stream>>>(GL_ROOT32, tab); DP_LAUNCHED();
         DP_CUDA(cudaGetLastError());
-        DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));   // complete before any other thread's stream reads it
+        DP_CUDA(dp_stream_sync(dp_ctx().stream));   // complete before any other thread's stream reads it
         g_bf.root_tab = tab;
     }
     return DP_OK;
@@ -211,6 +211,22 @@ __global__ void k_merkle_up(const u64 *__restrict__ in, u64 n_out, u64 *__restri
         *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(o[2], o[3]);
     }
 }
+template <bool EXT, bool FROM_LEAVES>
+__global__ void __launch_bounds__(64) k_merkle_mid(const void *__restrict__ src, u64 n_out, u64 *__restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    u64 x[4], y[4], o[4];
+    if (FROM_LEAVES) { leaf_pair_digest<EXT>(src, 2 * i, x); leaf_pair_digest<EXT>(src, 2 * i + 1, y); }
+    else {
+        const u64 *in = (const u64 *)src;
+        ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(in + 8 * i), b = *reinterpret_cast<const ulonglong2 *>(in + 8 * i + 2);
+        ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(in + 8 * i + 4), d = *reinterpret_cast<const ulonglong2 *>(in + 8 * i + 6);
+        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; y[0] = c.x; y[1] = c.y; y[2] = d.x; y[3] = d.y;
+    }
+    p2_compress_lat(x, y, o);
+    *reinterpret_cast<ulonglong2 *>(out + 4 * i) = make_ulonglong2(o[0], o[1]);
+    *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(o[2], o[3]);
+}
 // 8 lanes per hash (poseidon2.cuh): word w of the leaf-pair digest `pair`
 template <bool EXT> __device__ __forceinline__ u64 leaf_pair_word(const void *leaves, u64 pair, int w) {
     if (EXT) return ((const u64 *)leaves)[4 * pair + w];
@@ -231,34 +247,62 @@ __global__ void __launch_bounds__(256) k_merkle_x8(const void *src, u64 n_out, u
         if (lane8 < 4) out[4 * h + (3 - lane8)] = s;
     }
 }
-// Every remaining level of a tree whose current level has <= MK_SMALL hashes, in ONE launch (8 lanes per hash).  Each block owns
-// MK_SUB hashes of the first level -- one pass of its 32 lane groups -- and walks that subtree up to its root with a block barrier
-// per level; the last block to finish (ticket) folds the <= 64 subtree roots the same way.  Every level is a single pass, so the
-// tree costs depth x (one compress latency) and ONE launch instead of a launch per level (or a multi-level launch + a tail launch).
+// Every remaining level of a tree whose current level has <= MK_SMALL hashes, in ONE launch.  Each block owns MK_SUB hashes of the
+// first level and walks that subtree up to its root with a block barrier per level; the last block to finish (ticket) folds the
+// <= 8 subtree roots.  A level with >= 64 hashes per block runs one THREAD per hash (latency-optimised permutation): the same
+// ~40 us per level as a single-warp chain costs anyway, at 1/5 of the issue slots of the lane-parallel form -- with dozens of proofs
+// in flight these small trees were as much GPU work as all the wide Merkle levels together (8 lanes x ~4.5 k instructions per
+// permutation against 12.8 k for one thread).  Levels with <= 32 hashes per block use 8 lanes per hash (shorter dependent chain,
+// ~27 us per level); 88 % of a 2048-hash tree's permutations are in the thread-per-hash levels.
 struct LvlOff { u64 off[36]; };
-static constexpr u32 MK_SUB = 32;
+static constexpr u32 MK_SUB = 256;
 static constexpr u64 MK_SMALL = 2048;
+// `rt`: optional hand-over of the root to the host with the kernel's own stores (mapped pinned memory): root words, then a system
+// fence, then the sequence number the host waits for -- no D2H copy node and no separate signal launch per tree.
+struct RootOut { u64 *root_host; u64 *flag; u64 seq; };
+__device__ __forceinline__ void mk_publish_root(const RootOut &rt, const u64 *root_dev) {   // one thread, after the barrier that follows the root's stores
+    if (!rt.root_host) return;
+#pragma unroll
+    for (int k = 0; k < 4; k++) rt.root_host[k] = __ldcg(root_dev + k);
+    if (rt.flag) { __threadfence_system(); *(volatile u64 *)rt.flag = rt.seq; }
+}
 template <bool EXT, bool FROM_LEAVES>
-__global__ void __launch_bounds__(256) k_merkle_small(const void *src, u32 first_level, u32 lg, u64 nl_first, u64 *levels, LvlOff lo, u32 *ticket) {
+__global__ void __launch_bounds__(256) k_merkle_small(const void *src, u32 first_level, u32 lg, u64 nl_first, u64 *levels, LvlOff lo, u32 *ticket, RootOut rt) {
     const int lane8 = threadIdx.x & 7; const u32 grp = threadIdx.x >> 3;
     const u32 sub = (u32)(nl_first < MK_SUB ? nl_first : MK_SUB);
     u32 l = first_level;
     for (u32 k = 0; (sub >> k) >= 1 && l < lg; k++, l++) {
         const u32 cnt = sub >> k; const u64 base = (u64)blockIdx.x * cnt;
         u64 *out = levels + 4 * lo.off[l];
-        if ((grp & ~3u) < cnt) {                       // warp-uniform (a warp holds 4 lane groups): idle warps skip the permutations
+        const u64 *prev = k == 0 ? (const u64 *)src : levels + 4 * lo.off[l - 1];
+        if (cnt >= 64) {                                   // one thread per hash
+            if (threadIdx.x < cnt) {
+                const u64 i = base + threadIdx.x;
+                u64 x[4], y[4], o[4];
+                if (k == 0 && FROM_LEAVES) { leaf_pair_digest<EXT>(src, 2 * i, x); leaf_pair_digest<EXT>(src, 2 * i + 1, y); }
+                else {
+                    const u64 *in = prev + 8 * i;
+                    ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(in), b = *reinterpret_cast<const ulonglong2 *>(in + 2);
+                    ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(in + 4), d = *reinterpret_cast<const ulonglong2 *>(in + 6);
+                    x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; y[0] = c.x; y[1] = c.y; y[2] = d.x; y[3] = d.y;
+                }
+                p2_compress_lat(x, y, o);
+                *reinterpret_cast<ulonglong2 *>(out + 4 * i) = make_ulonglong2(o[0], o[1]);
+                *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(o[2], o[3]);
+            }
+        } else if ((grp & ~3u) < cnt) {                    // 8 lanes per hash; warp-uniform (a warp holds 4 lane groups): idle warps skip the permutations
             const bool live = grp < cnt; const u64 i = base + grp;
             u64 xw = 0, yw = 0;
             if (live && lane8 < 4) {
                 if (k == 0 && FROM_LEAVES) { xw = leaf_pair_word<EXT>(src, 2 * i, lane8); yw = leaf_pair_word<EXT>(src, 2 * i + 1, lane8); }
-                else { const u64 *in = (k == 0 ? (const u64 *)src : levels + 4 * lo.off[l - 1]) + 8 * i; xw = in[lane8]; yw = in[4 + lane8]; }
+                else { const u64 *in = prev + 8 * i; xw = in[lane8]; yw = in[4 + lane8]; }
             }
             const u64 sres = p2x8_compress(xw, yw, lane8);
             if (live && lane8 < 4) out[4 * i + (3 - lane8)] = sres;
         }
         __syncthreads();
     }
-    if (gridDim.x == 1) return;
+    if (gridDim.x == 1) { if (threadIdx.x == 0) mk_publish_root(rt, levels + 4 * lo.off[lg - 1]); return; }
     __shared__ bool last;
     __threadfence();
     __syncthreads();
@@ -279,6 +323,7 @@ __global__ void __launch_bounds__(256) k_merkle_small(const void *src, u32 first
         }
         __syncthreads();
     }
+    if (threadIdx.x == 0) mk_publish_root(rt, levels + 4 * lo.off[lg - 1]);
 }
 // process-wide pool of zeroed ticket counters (each k_merkle_small launch takes the next one and leaves it zero again)
 static u32 *g_mk_tickets = nullptr; static std::atomic<u32> g_mk_next{0}; static constexpr u32 MK_TICKETS = 4096;
@@ -380,7 +425,10 @@ struct DevTree {
     bool own_level0 = false;          // BLAKE3 trees of one polynomial store their leaf-pair digests (Poseidon2 recomputes them: zero-padded copies)
 };
 // `lvl0` != NULL: a batch tree -- the digests of the leaf pairs are given (k_merkle_batch_l0) instead of being packed from `leaves`
-static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n, const u64 *lvl0 = nullptr) {
+// `rt` (optional): the launch that produces the root also stores it (and then rt->flag = rt->seq) in mapped host memory; *rt_done
+// tells the caller whether that happened (single-level and BLAKE3 trees do not: the caller copies the root as before)
+static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n, const u64 *lvl0 = nullptr, const RootOut *rt = nullptr, bool *rt_done = nullptr) {
+    if (rt_done) *rt_done = false;
     DpCtx &c = dp_ctx();
     t.level0 = lvl0;
     t.leaves = leaves; t.ext = ext; t.n = n; t.lg = 0; while ((1ULL << t.lg) < n) t.lg++;
@@ -430,16 +478,22 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n, const u64
                 const unsigned g = (unsigned)((nl + MK_SUB - 1) / MK_SUB);
                 u32 *ticket = nullptr; if (int e = mk_ticket(&ticket)) return e;
                 const void *src = l == 1 ? (lvl0 ? (const void *)lvl0 : leaves) : (const void *)(t.levels + 4 * t.lvl_off[l - 1]);
-                if (from_leaves) { if (ext) k_merkle_small<true, true><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket); else k_merkle_small<false, true><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket); }
-                else k_merkle_small<false, false><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket);
+                RootOut ro = rt ? *rt : RootOut{nullptr, nullptr, 0};
+                if (from_leaves) { if (ext) k_merkle_small<true, true><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket, ro); else k_merkle_small<false, true><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket, ro); }
+                else k_merkle_small<false, false><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket, ro);
                 DP_LAUNCHED();
+                if (rt && rt_done) *rt_done = true;
                 break;
             }
-            if (nl <= 32768) {   // too few hashes for one thread each: 8 lanes per hash, one level per launch across the whole GPU
-                DpProfScope prof("k_merkle_x8(poseidon2 compress)", in_bytes + nl * 32, 2 * nl);
-                int g = dp_grid_for(nl * 8, 256, 8);
-                if (from_leaves) { if (ext) k_merkle_x8<true, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); else k_merkle_x8<false, true><<<g, 256, 0, c.stream>>>(leaves, nl, t.levels); }
-                else k_merkle_x8<false, false><<<g, 256, 0, c.stream>>>(l == 1 ? lvl0 : t.levels + 4 * t.lvl_off[l - 1], nl, t.levels + 4 * t.lvl_off[l]);
+            if (nl <= 32768) {
+                // Mid levels (2 k .. 32 k hashes): one thread per hash in 64-thread blocks, with the latency-optimised permutation.  A
+                // level is one wave of single-warp chains either way (46 us per compress per warp, 39 us in this formulation vs 52 us
+                // for the 8-lanes-per-hash kernel used before), but it now holds 1/8 of the thread slots and issues ~1/5 of the
+                // instructions, so the mid levels of many proofs' trees overlap instead of queueing behind each other.
+                DpProfScope prof("k_merkle_mid(poseidon2 compress, thread per hash)", in_bytes + nl * 32, 2 * nl);
+                const unsigned g = (unsigned)((nl + 63) / 64);
+                if (from_leaves) { if (ext) k_merkle_mid<true, true><<<g, 64, 0, c.stream>>>(leaves, nl, t.levels); else k_merkle_mid<false, true><<<g, 64, 0, c.stream>>>(leaves, nl, t.levels); }
+                else k_merkle_mid<false, false><<<g, 64, 0, c.stream>>>(l == 1 ? (const void *)lvl0 : (const void *)(t.levels + 4 * t.lvl_off[l - 1]), nl, t.levels + 4 * t.lvl_off[l]);
                 DP_LAUNCHED();
                 continue;
             }
@@ -476,14 +530,63 @@ __global__ void k_fri_fold(const gle *__restrict__ in, gle *__restrict__ out, u3
     }
 }
 
-// ---- K12 batch prelude: acc[i] (+)= coef * src[i >> rep_log]  (src Base or Ext) ----
-template <bool EXT, bool INIT>
-__global__ void k_axpy_bcast(gle *__restrict__ acc, const void *__restrict__ src, u64 n, u32 rep_log, gle coef) {
+// ---- K12 batch prelude (commit_phase.rs:205-236,271-282): out[i] = (base[i]) + sum_k coef_k * src_k[i >> rep_k] ----
+// ONE pass for all sources: the reference (and the first version here) adds one polynomial at a time, i.e. a read-modify-write of
+// the whole running oracle per commitment -- 47 passes over a 16 MB table in a Dense-4M opening.  Each thread owns one output
+// element, walks the source table (kernel parameters, <= LC_MAX entries per launch) and accumulates the raw 128-bit products in
+// 192-bit sums that are reduced once (field addition is exact, so the order is free and the element is identical).
+struct bacc192 { u64 lo, hi; u32 top; };
+__device__ __forceinline__ void bacc_mac(bacc192 &a, u64 x, u64 y) {
+    u64 pl = x * y, ph = __umul64hi(x, y);
+    asm("{\n\tadd.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;\n\t}" : "+l"(a.lo), "+l"(a.hi), "+r"(a.top) : "l"(pl), "l"(ph));
+}
+static constexpr u32 LC_MAX = 96;
+struct LcSrc { const void *p; u64 c0, c1; u32 ext, rep_log; };
+struct LcArgs { LcSrc s[LC_MAX]; u32 n; u32 pad; };
+template <bool HAS_BASE>
+__global__ void __launch_bounds__(256) k_lincomb_bcast(gle *__restrict__ out, const gle *__restrict__ base, const __grid_constant__ LcArgs a, u64 n) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        gle v = EXT ? e_mul(ld_e((const gle *)src + (i >> rep_log)), coef) : e_mul_base(coef, ((const u64 *)src)[i >> rep_log]);
-        st_e(acc + i, INIT ? v : e_add(ld_e(acc + i), v));
+        bacc192 s0 = {0, 0, 0}, s1 = {0, 0, 0};
+        for (u32 k = 0; k < a.n; k++) {
+            const LcSrc &q = a.s[k];
+            const u64 j = i >> q.rep_log;
+            if (q.ext) {   // (c0 + c1 X)(x0 + x1 X) = c0 x0 + 7 c1 x1 + (c0 x1 + c1 x0) X
+                const gle x = ld_e((const gle *)q.p + j);
+                bacc_mac(s1, q.c0, x.c1); bacc_mac(s1, q.c1, x.c0);
+                bacc_mac(s0, q.c0, x.c0); bacc_mac(s0, gl_reduce128_weak(q.c1 * x.c1, __umul64hi(q.c1, x.c1)), 7ULL);
+            } else {
+                const u64 x = ((const u64 *)q.p)[j];
+                bacc_mac(s0, q.c0, x); bacc_mac(s1, q.c1, x);
+            }
+        }
+        gle v = e_make(gl_reduce160(s0.lo, s0.hi, s0.top), gl_reduce160(s1.lo, s1.hi, s1.top));
+        if (HAS_BASE) v = e_add(v, ld_e(base + i));
+        st_e(out + i, v);
     }
+}
+struct LcTerm { const void *p; gle coef; bool ext; u32 rep_log; };
+// out = (base ? base : 0) + sum terms; out may alias base.  Zero terms and no base: out = 0.
+static int lincomb_bcast(gle *out, const gle *base, const std::vector<LcTerm> &terms, u64 n) {
+    DpCtx &c = dp_ctx();
+    if (terms.empty()) {
+        if (!base) DP_CUDA(cudaMemsetAsync(out, 0, sizeof(gle) * n, c.stream));
+        else if (base != out) DP_CUDA(cudaMemcpyAsync(out, base, sizeof(gle) * n, cudaMemcpyDeviceToDevice, c.stream));
+        return DP_OK;
+    }
+    const int g = dp_grid_for(n, 256, 8);
+    for (size_t o = 0; o < terms.size(); o += LC_MAX) {
+        LcArgs a; memset(&a, 0, sizeof a);
+        a.n = (u32)std::min<size_t>(LC_MAX, terms.size() - o);
+        u64 src_bytes = 0;
+        for (u32 k = 0; k < a.n; k++) { const LcTerm &t = terms[o + k]; a.s[k].p = t.p; a.s[k].c0 = t.coef.c0; a.s[k].c1 = t.coef.c1; a.s[k].ext = t.ext ? 1 : 0; a.s[k].rep_log = t.rep_log; src_bytes += (n >> t.rep_log) * (t.ext ? 16 : 8); }
+        const gle *b = o == 0 ? base : out;
+        DpProfScope p("k_lincomb_bcast", src_bytes + n * (b ? 32 : 16));
+        if (b) k_lincomb_bcast<true><<<g, 256, 0, c.stream>>>(out, b, a, n); else k_lincomb_bcast<false><<<g, 256, 0, c.stream>>>(out, nullptr, a, n);
+        DP_LAUNCHED();
+    }
+    DP_CUDA(cudaGetLastError());
+    return DP_OK;
 }
 __global__ void k_lift(const u64 *__restrict__ src, gle *__restrict__ out, u64 n) {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
@@ -542,6 +645,7 @@ struct dp_pcs_open {
     dp_sc *sc = nullptr;
     gle final_msg[1 << BF_BASECODE_LOG]; bool have_final = false;
     gle *scratch_sum_evals = nullptr;
+    u64 *h_root = nullptr; u64 root_seq = 0;     // mapped pinned: [0..3] root of the round's tree, [8] completion word
 };
 
 static void msg_to_coeffs(const uint64_t *ev /* p(0),p(1),p(2) */, uint64_t *out /* c0,c1,c2 */) {
@@ -568,7 +672,7 @@ int dp_poseidon2_init(const uint64_t *ext_rc /*2x4x8*/, const uint64_t *int_rc /
     for (int i = 0; i < 64; i++) a[i] = gl_canon(ext_rc[i]);
     for (int i = 0; i < 22; i++) b[i] = gl_canon(int_rc[i]);
     for (int i = 0; i < 8; i++) d[i] = gl_canon(diag[i]);
-    DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));
+    DP_CUDA(dp_stream_sync(dp_ctx().stream));
     DP_CUDA(p2_upload_constants(a, b, d));
     g_bf.p2_ready = true;
     return DP_OK;
@@ -621,7 +725,7 @@ static int commit_enqueue(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **o
                 u64 *nt = nullptr;
                 DP_CUDA(cudaMalloc((void **)&nt, sizeof(u64) * 3 * 2048));
                 k_pow_table<<<24, 256, 0, c.stream>>>(shift, nt); DP_LAUNCHED();
-                DP_CUDA(cudaStreamSynchronize(c.stream));       // other host threads' streams may read it as soon as the map holds it
+                DP_CUDA(dp_stream_sync(c.stream));       // other host threads' streams may read it as soon as the map holds it
                 it = shift_tabs.emplace(shift, nt).first;
             }
             stab = it->second;
@@ -646,8 +750,9 @@ static int commit_enqueue(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **o
         }
     }
     if (with_tree) {
-        if (int e = tree_build(cm->tree, cm->codeword, poly->is_ext, cm->cw_len)) return e;   // K9
-        DP_CUDA(cudaMemcpyAsync(root_pinned, cm->tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
+        RootOut ro{root_pinned, nullptr, 0}; bool published = false;
+        if (int e = tree_build(cm->tree, cm->codeword, poly->is_ext, cm->cw_len, nullptr, &ro, &published)) return e;   // K9
+        if (!published) DP_CUDA(cudaMemcpyAsync(root_pinned, cm->tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
     }
     *out = cm;
     return DP_OK;
@@ -660,7 +765,7 @@ int dp_pcs_commit(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out) {
     u64 *pin = nullptr;
     if (int e = dp_pinned_alloc((void **)&pin, 32)) return e;
     int rc = commit_enqueue(poly, full_log, out, pin);
-    if (rc == DP_OK) { DP_CUDA(cudaStreamSynchronize(dp_ctx().stream)); memcpy((*out)->root, pin, 32); }
+    if (rc == DP_OK) { DP_CUDA(dp_stream_sync(dp_ctx().stream)); memcpy((*out)->root, pin, 32); }
     dp_pinned_free(pin);
     return rc;
 }
@@ -684,7 +789,7 @@ int dp_pcs_batch_commit(const dp_mle *const *polys, uint32_t n, uint32_t full_lo
         dp_pcs_comm *part = nullptr; u64 *pin1 = nullptr;
         if (int e = dp_pinned_alloc((void **)&pin1, 32)) { dp_pcs_comm_free(b); return e; }
         int rc = commit_enqueue(polys[0], full_log, &part, pin1, true);
-        if (rc == DP_OK) { cudaStreamSynchronize(c.stream); memcpy(part->root, pin1, 32); memcpy(b->root, pin1, 32); }
+        if (rc == DP_OK) { dp_stream_sync(c.stream); memcpy(part->root, pin1, 32); memcpy(b->root, pin1, 32); }
         dp_pinned_free(pin1);
         if (rc != DP_OK) { dp_pcs_comm_free(b); return rc; }
         b->parts.push_back(part); b->trivial = part->trivial; b->cw_len = part->cw_len;
@@ -718,7 +823,7 @@ int dp_pcs_batch_commit(const dp_mle *const *polys, uint32_t n, uint32_t full_lo
     u64 *pin = nullptr;
     if (int e = dp_pinned_alloc((void **)&pin, 32)) { dp_pcs_comm_free(b); return e; }
     DP_CUDA(cudaMemcpyAsync(pin, b->tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
-    DP_CUDA(cudaStreamSynchronize(c.stream));
+    DP_CUDA(dp_stream_sync(c.stream));
     memcpy(b->root, pin, 32); for (auto *part : b->parts) memcpy(part->root, pin, 32);
     dp_pinned_free(pin);
     *out = b;
@@ -771,7 +876,7 @@ int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_log
     for (u32 i = 0; i < n && rc == DP_OK; i++) { c.stream = g_pool[i % S]; rc = commit_enqueue(polys[i], full_log, &out[i], pin + 4 * i); }
     c.stream = main;
     for (u32 s = 0; s < used; s++) { cudaEventRecord(g_pool_ev[s], g_pool[s]); cudaStreamWaitEvent(main, g_pool_ev[s], 0); }
-    cudaError_t se = cudaStreamSynchronize(main);
+    cudaError_t se = dp_stream_sync(main);
     dp_arena_defer(false);
     if (se != cudaSuccess) return dp_fail(DP_ERR_CUDA, std::string("dp_pcs_commit_many: ") + cudaGetErrorString(se));
     if (rc == DP_OK) for (u32 i = 0; i < n; i++) memcpy(out[i]->root, pin + 4 * i, 32);
@@ -838,23 +943,17 @@ int dp_pcs_open_begin(const dp_pcs_comm *const *comms, const uint64_t *coeffs, u
         ev->data = cm->bh_evals; ev->is_ext = !cm->is_base;     // running_evals = bh_evals (commit_phase.rs:50)
     } else {
         // running_oracle = sum of coeff * codeword over the full-size commitments (commit_phase.rs:205-223)
-        bool init = true;
-        for (u32 i = 0; i < n_comms; i++) if (comms[i]->cw_len == N) {
-            int g = dp_grid_for(N, 256, 8);
-            DpProfScope p("k_axpy_bcast", N * 40);
-            if (comms[i]->is_base) { if (init) k_axpy_bcast<false, true><<<g, 256, 0, c.stream>>>(o->oracle0, comms[i]->codeword, N, 0, o->coeffs[i]); else k_axpy_bcast<false, false><<<g, 256, 0, c.stream>>>(o->oracle0, comms[i]->codeword, N, 0, o->coeffs[i]); }
-            else { if (init) k_axpy_bcast<true, true><<<g, 256, 0, c.stream>>>(o->oracle0, comms[i]->codeword, N, 0, o->coeffs[i]); else k_axpy_bcast<true, false><<<g, 256, 0, c.stream>>>(o->oracle0, comms[i]->codeword, N, 0, o->coeffs[i]); }
-            DP_LAUNCHED(); init = false;
+        {
+            std::vector<LcTerm> terms;
+            for (u32 i = 0; i < n_comms; i++) if (comms[i]->cw_len == N) terms.push_back({comms[i]->codeword, o->coeffs[i], !comms[i]->is_base, 0});
+            if (int e = lincomb_bcast(o->oracle0, nullptr, terms, N)) return e;
         }
-        if (init) DP_CUDA(cudaMemsetAsync(o->oracle0, 0, sizeof(gle) * N, c.stream));
         // sum_of_all_evals_for_sumcheck: smaller polynomials are broadcast over chunks (commit_phase.rs:225-236)
         if (int e = dp_dev_alloc((void **)&o->scratch_sum_evals, sizeof(gle) * M)) return e;
-        for (u32 i = 0; i < n_comms; i++) {
-            u32 rep = num_vars - comms[i]->num_vars; int g = dp_grid_for(M, 256, 8);
-            DpProfScope p("k_axpy_bcast", M * 40);
-            if (comms[i]->is_base) { if (i == 0) k_axpy_bcast<false, true><<<g, 256, 0, c.stream>>>(o->scratch_sum_evals, comms[i]->bh_evals, M, rep, o->coeffs[i]); else k_axpy_bcast<false, false><<<g, 256, 0, c.stream>>>(o->scratch_sum_evals, comms[i]->bh_evals, M, rep, o->coeffs[i]); }
-            else { if (i == 0) k_axpy_bcast<true, true><<<g, 256, 0, c.stream>>>(o->scratch_sum_evals, comms[i]->bh_evals, M, rep, o->coeffs[i]); else k_axpy_bcast<true, false><<<g, 256, 0, c.stream>>>(o->scratch_sum_evals, comms[i]->bh_evals, M, rep, o->coeffs[i]); }
-            DP_LAUNCHED();
+        {
+            std::vector<LcTerm> terms;
+            for (u32 i = 0; i < n_comms; i++) terms.push_back({comms[i]->bh_evals, o->coeffs[i], !comms[i]->is_base, num_vars - comms[i]->num_vars});
+            if (int e = lincomb_bcast(o->scratch_sum_evals, nullptr, terms, M)) return e;
         }
         ev->data = o->scratch_sum_evals; ev->is_ext = true;
     }
@@ -894,13 +993,9 @@ int dp_pcs_open_round(dp_pcs_open *o, const uint64_t challenge[2], uint64_t next
         if (any) {
             gle *merged = nullptr;
             if (int e = dp_dev_alloc((void **)&merged, sizeof(gle) * len)) return e;
-            DP_CUDA(cudaMemcpyAsync(merged, o->oracle0, sizeof(gle) * len, cudaMemcpyDeviceToDevice, c.stream));
-            for (size_t k = 0; k < o->comms.size(); k++) if (o->comms[k]->cw_len == len) {
-                int g = dp_grid_for(len, 256, 8);
-                if (o->comms[k]->is_base) k_axpy_bcast<false, false><<<g, 256, 0, c.stream>>>(merged, o->comms[k]->codeword, len, 0, o->coeffs[k]);
-                else k_axpy_bcast<true, false><<<g, 256, 0, c.stream>>>(merged, o->comms[k]->codeword, len, 0, o->coeffs[k]);
-                DP_LAUNCHED();
-            }
+            std::vector<LcTerm> terms;
+            for (size_t k = 0; k < o->comms.size(); k++) if (o->comms[k]->cw_len == len) terms.push_back({o->comms[k]->codeword, o->coeffs[k], !o->comms[k]->is_base, 0});
+            if (int e = lincomb_bcast(merged, o->oracle0, terms, len)) return e;
             o->oracle0 = merged; o->oracle0_owned = true;   // the previous buffer stays owned by rounds.back()
         }
     }
@@ -926,9 +1021,13 @@ int dp_pcs_open_round(dp_pcs_open *o, const uint64_t challenge[2], uint64_t next
         if (int e = dp_sc_round(o->sc, ch, ev3)) return e;       // sum_check_challenge_round
         msg_to_coeffs(ev3, next_msg);
         OpenRound rd; rd.oracle = folded; rd.len = len >> 1;
-        if (int e = tree_build(rd.tree, folded, true, rd.len)) return e;   // compute_inner_ext
-        DP_CUDA(cudaMemcpyAsync(root, rd.tree.root_dev, 32, cudaMemcpyDeviceToHost, c.stream));
-        DP_CUDA(cudaStreamSynchronize(c.stream));
+        if (!o->h_root) { void *hp = nullptr; if (int e = dp_pinned_alloc(&hp, 128)) return e; o->h_root = (u64 *)hp; o->h_root[8] = 0; o->root_seq = 0; }
+        RootOut ro{o->h_root, o->h_root + 8, ++o->root_seq}; bool published = false;
+        if (int e = tree_build(rd.tree, folded, true, rd.len, nullptr, &ro, &published)) return e;   // compute_inner_ext
+        if (published) {   // the tree's last launch stores the root and then the sequence number in mapped memory
+            if (dp_wait_flag(o->h_root + 8, o->root_seq, false, 0, 30.0) != o->root_seq) { DP_CUDA(dp_stream_sync(c.stream)); DP_CHECK(o->h_root[8] == o->root_seq, DP_ERR_CUDA, "dp_pcs_open_round: tree kernel finished without publishing its root"); }
+            memcpy(root, o->h_root, 32);
+        } else if (int e = dp_d2h(root, rd.tree.root_dev, 32, c.stream)) return e;
         o->rounds.push_back(rd);
         *is_last = 0;
     } else {
@@ -938,8 +1037,7 @@ int dp_pcs_open_round(dp_pcs_open *o, const uint64_t challenge[2], uint64_t next
         if (int e = dp_sc_current_mle(o->sc, 1, &view)) return e;
         DP_CHECK(view->len == (1ULL << BF_BASECODE_LOG) && view->is_ext, DP_ERR_STATE, "dp_pcs_open_round: unexpected final message size");
         gle tmp[1 << BF_BASECODE_LOG];
-        DP_CUDA(cudaMemcpyAsync(tmp, view->data, sizeof tmp, cudaMemcpyDeviceToHost, c.stream));
-        DP_CUDA(cudaStreamSynchronize(c.stream));
+        if (int e = dp_d2h(tmp, view->data, sizeof tmp, c.stream)) return e;
         dp_mle_free(view);
         for (u32 k = 0; k < (1u << BF_BASECODE_LOG); k++) { u32 j = 0; for (u32 b = 0; b < BF_BASECODE_LOG; b++) if (k >> b & 1) j |= 1u << (BF_BASECODE_LOG - 1 - b); o->final_msg[j] = tmp[k]; }
         o->have_final = true;
@@ -992,11 +1090,10 @@ int dp_pcs_open_query(dp_pcs_open *o, const uint64_t *x_indices, uint32_t n, uin
     DP_CUDA(cudaMemcpyAsync(dq, qt.data(), sizeof(QTree) * nt, cudaMemcpyHostToDevice, c.stream));
     DP_CUDA(cudaMemcpyAsync(doff, off.data(), 8 * nt, cudaMemcpyHostToDevice, c.stream));
     DP_CUDA(cudaMemcpyAsync(dx, x_indices, 8 * (size_t)n, cudaMemcpyHostToDevice, c.stream));
-    DP_CUDA(cudaStreamSynchronize(c.stream));   // qt/off are stack-owned host buffers
+    DP_CUDA(dp_stream_sync(c.stream));   // qt/off are stack-owned host buffers
     k_query_gather<<<dim3(n, nt), 32, 0, c.stream>>>(dq, nt, dx, doff, w, dout); DP_LAUNCHED();
     DP_CUDA(cudaGetLastError());
-    DP_CUDA(cudaMemcpyAsync(out, dout, 8 * w * n, cudaMemcpyDeviceToHost, c.stream));
-    DP_CUDA(cudaStreamSynchronize(c.stream));
+    if (int e = dp_d2h(out, dout, 8 * w * n, c.stream)) return e;
     dp_dev_free(dq); dp_dev_free(doff); dp_dev_free(dx); dp_dev_free(dout);
     return DP_OK;
 }
@@ -1011,6 +1108,8 @@ int dp_pcs_open_free(dp_pcs_open *o) {
         if (!oracle_in_rounds) dp_dev_free(o->oracle0);
         dp_dev_free(o->scratch_sum_evals);
     }
+    if (o->h_root && o->h_root[8] != o->root_seq && dp_ctx().ready) dp_stream_sync(dp_ctx().stream);   // a tree kernel still owns the pinned block
+    dp_pinned_free(o->h_root);
     if (o->eq) dp_mle_free(o->eq);
     if (o->evals) dp_mle_free(o->evals);
     delete o;

@@ -114,6 +114,156 @@ int dp_pinned_alloc(void **p, size_t bytes) {
 void dp_pinned_free(void *p) { if (!p) return; std::lock_guard<std::mutex> lk(g_pinned_mu); for (auto &b : g_pinned) if (b.p == p) { b.used = false; return; } }
 
 #include <chrono>
+// ---- waiting without burning a core (see common.cuh) -------------------------------------------------------------------
+#include <thread>
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#include <time.h>
+static std::atomic<int> g_wait_mode{-1};
+int dp_wait_mode() {
+    int m = g_wait_mode.load(std::memory_order_relaxed);
+    if (m < 0) { const char *e = getenv("DP_WAIT_MODE"); m = (e && (e[0] == '1' || e[0] == 'b' || e[0] == 'B')) ? DP_WAIT_BLOCK : DP_WAIT_SPIN; g_wait_mode.store(m); }
+    return m;
+}
+static long futex_call(std::atomic<u32> *addr, int op, u32 val, const struct timespec *ts) { return syscall(SYS_futex, (u32 *)addr, op, val, ts, nullptr, 0); }
+struct WaitSlot {
+    std::atomic<u32> state{0};                 // 0 idle, 1 armed (the poller watches it), 2 fired
+    volatile u64 *flag = nullptr; u64 want = 0, fail = 0; bool has_fail = false;
+    u64 seen = 0;
+    std::atomic<u32> wake{0};                  // futex word the owner sleeps on
+    char pad[64];
+};
+static constexpr u32 WAIT_SLOTS = 1024;
+static WaitSlot g_wslots[WAIT_SLOTS];
+static std::atomic<u32> g_wslots_used{0}, g_armed{0}, g_poller_gen{0};
+static std::once_flag g_poller_once;
+static void poller_main() {
+    for (;;) {
+        if (g_armed.load(std::memory_order_acquire) == 0) {       // nothing to watch: sleep until a waiter arms a slot
+            const u32 gen = g_poller_gen.load(std::memory_order_acquire);
+            if (g_armed.load(std::memory_order_acquire) == 0) { struct timespec ts = {0, 2000000}; futex_call(&g_poller_gen, FUTEX_WAIT_PRIVATE, gen, &ts); }
+            continue;
+        }
+        const u32 n = std::min<u32>(g_wslots_used.load(std::memory_order_acquire), WAIT_SLOTS);
+        for (u32 i = 0; i < n; i++) {
+            WaitSlot &w = g_wslots[i];
+            if (w.state.load(std::memory_order_acquire) != 1) continue;
+            const u64 v = *w.flag;
+            if (v == w.want || (w.has_fail && v == w.fail)) {
+                w.seen = v;
+                g_armed.fetch_sub(1, std::memory_order_acq_rel);
+                w.state.store(2, std::memory_order_release);
+                w.wake.store(1, std::memory_order_release);
+                futex_call(&w.wake, FUTEX_WAKE_PRIVATE, 1, nullptr);
+            }
+        }
+        __builtin_ia32_pause();
+    }
+}
+u64 dp_wait_flag(volatile u64 *flag, u64 want, bool has_fail, u64 fail, double timeout_s) {
+    // a result that is already there (or lands within a microsecond) never pays for a sleep
+    for (int k = 0; k < 64; k++) { const u64 v = *flag; if (v == want || (has_fail && v == fail)) return v; __builtin_ia32_pause(); }
+    const auto t_start = std::chrono::steady_clock::now();
+    if (dp_wait_mode() == DP_WAIT_SPIN) {
+        for (u64 spins = 1;; spins++) {
+            const u64 v = *flag; if (v == want || (has_fail && v == fail)) return v;
+            if ((spins & 0xFFFF) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > timeout_s) return DP_WAIT_TIMEOUT;
+            __builtin_ia32_pause();
+        }
+    }
+    // BLOCK mode: a bounded number of waiters may still spin for a short while (lowest latency for the proofs that are in
+    // their round-trip-bound phases) -- never more than about half of the CPUs this process may use.
+    {
+        static const int spin_limit = [] {
+            if (const char *e = getenv("DP_WAIT_SPINNERS")) return atoi(e);
+            double cpus = (double)std::thread::hardware_concurrency();
+            if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) { char q[64]; double per = 0; if (fscanf(f, "%63s %lf", q, &per) == 2 && strcmp(q, "max") != 0 && per > 0) cpus = std::min(cpus, atof(q) / per); fclose(f); }
+            return std::max(0, (int)(cpus / 2) - 1);
+        }();
+        static std::atomic<int> spinners{0};
+        if (spin_limit > 0 && spinners.fetch_add(1, std::memory_order_acq_rel) < spin_limit) {
+            u64 seen = DP_WAIT_TIMEOUT; bool got = false;
+            for (u64 spins = 1;; spins++) {
+                const u64 v = *flag; if (v == want || (has_fail && v == fail)) { seen = v; got = true; break; }
+                if ((spins & 0x3FF) == 0 && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 60e-6) break;
+                __builtin_ia32_pause();
+            }
+            spinners.fetch_sub(1, std::memory_order_acq_rel);
+            if (got) return seen;
+        } else spinners.fetch_sub(1, std::memory_order_acq_rel);
+    }
+    static thread_local int my_slot = -1;
+    if (my_slot < 0) {
+        const u32 idx = g_wslots_used.fetch_add(1, std::memory_order_acq_rel);
+        if (idx >= WAIT_SLOTS) { g_wslots_used.store(WAIT_SLOTS); my_slot = -2; } else my_slot = (int)idx;
+    }
+    if (my_slot == -2) {   // more waiting threads than slots (never in practice): sleep-poll
+        for (;;) {
+            const u64 v = *flag; if (v == want || (has_fail && v == fail)) return v;
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > timeout_s) return DP_WAIT_TIMEOUT;
+            struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr);
+        }
+    }
+    std::call_once(g_poller_once, [] { std::thread(poller_main).detach(); });
+    WaitSlot &w = g_wslots[my_slot];
+    w.flag = flag; w.want = want; w.fail = fail; w.has_fail = has_fail; w.wake.store(0, std::memory_order_relaxed);
+    const u32 armed_before = g_armed.fetch_add(1, std::memory_order_acq_rel);
+    w.state.store(1, std::memory_order_release);
+    if (armed_before == 0) { g_poller_gen.fetch_add(1, std::memory_order_acq_rel); futex_call(&g_poller_gen, FUTEX_WAKE_PRIVATE, 1, nullptr); }
+    for (;;) {
+        if (w.wake.load(std::memory_order_acquire) == 0) { struct timespec ts = {0, 5000000}; futex_call(&w.wake, FUTEX_WAIT_PRIVATE, 0, &ts); }
+        if (w.state.load(std::memory_order_acquire) == 2) { const u64 v = w.seen; w.state.store(0, std::memory_order_release); return v; }
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > timeout_s) {
+            // withdraw the slot; if the poller fires it at this very moment the result is simply taken
+            u32 one = 1;
+            if (w.state.compare_exchange_strong(one, 0, std::memory_order_acq_rel)) { g_armed.fetch_sub(1, std::memory_order_acq_rel); return DP_WAIT_TIMEOUT; }
+        }
+    }
+}
+__global__ void k_signal(u64 *flag, u64 seq) { __threadfence_system(); *(volatile u64 *)flag = seq; }
+cudaError_t dp_stream_sync(cudaStream_t st) {
+    if (dp_wait_mode() == DP_WAIT_SPIN) return cudaStreamSynchronize(st);
+    DpCtx &c = g_ctx;
+    if (!c.sync_flag) { void *p = nullptr; if (dp_pinned_alloc(&p, 64) != DP_OK) return cudaErrorMemoryAllocation; c.sync_flag = (u64 *)p; *c.sync_flag = 0; c.sync_seq = 0; }
+    const u64 seq = ++c.sync_seq;
+    k_signal<<<1, 1, 0, st>>>(c.sync_flag, seq); dp_count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (dp_wait_flag(c.sync_flag, seq, false, 0, 30.0) != seq) return cudaStreamSynchronize(st);   // timeout: let the runtime report what happened
+    return cudaSuccess;
+}
+
+DpD2H::DpD2H(cudaStream_t s, size_t reserve_bytes) : st(s) { cap = reserve_bytes < 64 ? 64 : reserve_bytes; if (dp_pinned_alloc(&pin, cap) != DP_OK) { pin = nullptr; cap = 0; } }
+DpD2H::~DpD2H() { dp_pinned_free(pin); }
+int DpD2H::add(void *host_dst, const void *dev_src, size_t bytes) {
+    if (!pin || used + bytes > cap) return dp_fail(DP_ERR_CUDA, "DpD2H: staging buffer too small or not allocated");
+    DP_CUDA(cudaMemcpyAsync((char *)pin + used, dev_src, bytes, cudaMemcpyDeviceToHost, st));
+    pieces.push_back({host_dst, used, bytes});
+    used += (bytes + 15) & ~(size_t)15;
+    return DP_OK;
+}
+int DpD2H::finish() {
+    DP_CUDA(dp_stream_sync(st));
+    for (auto &p : pieces) memcpy(p.dst, (char *)pin + p.off, p.bytes);
+    pieces.clear(); used = 0;
+    return DP_OK;
+}
+int dp_d2h(void *host_dst, const void *dev_src, size_t bytes, cudaStream_t st) {
+    DpD2H x(st, bytes);
+    if (int e = x.add(host_dst, dev_src, bytes)) return e;
+    return x.finish();
+}
+
+int dp_zero_block_get(void **p) {
+    DpCtx &c = g_ctx;
+    if (!c.zero_blocks.empty()) { *p = c.zero_blocks.back(); c.zero_blocks.pop_back(); return DP_OK; }
+    if (int e = dp_dev_alloc(p, 256)) return e;
+    DP_CUDA(cudaMemsetAsync(*p, 0, 256, c.stream));
+    return DP_OK;
+}
+void dp_zero_block_put(void *p) { if (p) g_ctx.zero_blocks.push_back(p); }
+
 static bool g_hostprof = getenv("DP_HOST_PROF") != nullptr;
 static thread_local std::map<std::string, std::pair<unsigned long long, double>> g_hostprof_acc;
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -161,6 +311,13 @@ static void prof_resolve() {
 }
 
 extern "C" {
+
+int dp_set_wait_mode(int mode) {
+    if (mode != DP_WAIT_SPIN && mode != DP_WAIT_BLOCK) return dp_fail(DP_ERR_INVALID, "dp_set_wait_mode: 0 = spin, 1 = block on the poller thread");
+    g_wait_mode.store(mode);
+    return DP_OK;
+}
+int dp_get_wait_mode(void) { return dp_wait_mode(); }
 
 int dp_profile_enable(int on) {
     std::lock_guard<std::recursive_mutex> lk(g_ctx.mu);
@@ -240,6 +397,8 @@ int dp_shutdown(void) {
     cudaStreamSynchronize(g_ctx.stream);
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.stream);
     g_ctx.stream = nullptr; g_ctx.own_stream = false; g_ctx.ready = false;
+    if (g_ctx.sync_flag) { dp_pinned_free(g_ctx.sync_flag); g_ctx.sync_flag = nullptr; }
+    g_ctx.zero_blocks.clear();     // they live in the arena that is released below
     arena_destroy();
     return DP_OK;
 }

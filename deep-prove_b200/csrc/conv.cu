@@ -117,10 +117,9 @@ extern "C" int dp_conv_output_elements(const dp_mle *out_rows, uint32_t kw, uint
     DP_CUDA(cudaMemcpyAsync(db, bias, 8 * (size_t)kw, cudaMemcpyHostToDevice, st));
     k_conv_out_elems<<<dp_grid_for(nx2 * kw, 256, 8), 256, 0, st>>>((const gle *)out_rows->data, kw, (u32)nx2, db, d); DP_LAUNCHED();
     DP_CUDA(cudaGetLastError());
-    DP_CUDA(cudaMemcpyAsync(out_host, d, 8 * nx2 * kw, cudaMemcpyDeviceToHost, st));
-    DP_CUDA(cudaStreamSynchronize(st));
+    const int rc = dp_d2h(out_host, d, 8 * nx2 * kw, st);
     dp_dev_free(d); dp_dev_free(db);
-    return DP_OK;
+    return rc;
 }
 
 // ---- phi_g_init (iop/prover.rs:231-289): the FFT / iFFT matrix row W(rx, .) and its per-level prefixes, one launch ----

@@ -38,7 +38,8 @@ __global__ void k_logup_layer(const gle *__restrict__ num, const gle *__restrict
 }
 // all remaining (small) layers in one single-block launch
 struct LayerPtrs { gle *num[40]; gle *den[40]; };
-__global__ void __launch_bounds__(256) k_logup_tail(LayerPtrs lp, u32 from_layer, u32 n_layers, u64 len0, bool first_is_lookup) {
+// `out_host` (mapped pinned, 9 words): the circuit's outputs [n0, n1, d0, d1] and then the completion word, stored by the kernel itself
+__global__ void __launch_bounds__(256) k_logup_tail(LayerPtrs lp, u32 from_layer, u32 n_layers, u64 len0, bool first_is_lookup, u64 *out_host, u64 seq) {
     for (u32 k = from_layer; k + 1 < n_layers; k++) {
         u64 half = len0 >> (k + 1);
         const gle *num = lp.num[k], *den = lp.den[k];
@@ -49,6 +50,13 @@ __global__ void __launch_bounds__(256) k_logup_tail(LayerPtrs lp, u32 from_layer
             lp.num[k + 1][i] = n; lp.den[k + 1][i] = e_mul(d1, d2);
         }
         __syncthreads();
+    }
+    if (out_host && threadIdx.x == 0) {
+        const gle *num = lp.num[n_layers - 1], *den = lp.den[n_layers - 1];
+        const gle a = num[0], b = num[1], c = den[0], d = den[1];
+        out_host[0] = a.c0; out_host[1] = a.c1; out_host[2] = b.c0; out_host[3] = b.c1; out_host[4] = c.c0; out_host[5] = c.c1; out_host[6] = d.c0; out_host[7] = d.c1;
+        __threadfence_system();
+        *(volatile u64 *)(out_host + 8) = seq;
     }
 }
 // out[i] = sum_k coef_k * m_k[i]
@@ -66,6 +74,7 @@ struct dp_logup {
     bool table = false; u32 nv = 0;            // layer 0 has 2^nv entries
     std::vector<gle *> num, den;               // per layer; num[0] == nullptr for a lookup circuit
     gle *block = nullptr;
+    u64 *h_out = nullptr;                      // mapped pinned: outputs + completion word written by k_logup_tail
 };
 
 extern "C" {
@@ -111,7 +120,9 @@ int dp_logup_build(dp_mle *const *columns, uint32_t n_columns, const dp_mle *mul
         LayerPtrs lp; memset(&lp, 0, sizeof lp);
         for (u32 q = 0; q < L->nv && q < 40; q++) { lp.num[q] = L->num[q]; lp.den[q] = L->den[q]; }
         DpProfScope prof("k_logup_tail", (len >> k) * 96);
-        k_logup_tail<<<1, 256, 0, c.stream>>>(lp, k, L->nv, len, !L->table); DP_LAUNCHED();
+        void *hp = nullptr;
+        if (L->nv - 1 > k && dp_pinned_alloc(&hp, 128) == DP_OK) { L->h_out = (u64 *)hp; L->h_out[8] = 0; }
+        k_logup_tail<<<1, 256, 0, c.stream>>>(lp, k, L->nv, len, !L->table, L->h_out, 1); DP_LAUNCHED();
     }
     DP_CUDA(cudaGetLastError());
     if (!L->table) L->num[0] = nullptr;
@@ -131,10 +142,15 @@ int dp_logup_outputs(const dp_logup *L, uint64_t out[8]) {
     DP_CHECK(L && out, DP_ERR_INVALID, "dp_logup_outputs: null");
     u32 last = L->nv - 1;
     DP_CHECK(L->num[last] != nullptr, DP_ERR_INVALID, "dp_logup_outputs: circuit too small");
-    DP_CUDA(cudaMemcpyAsync(out, L->num[last], 32, cudaMemcpyDeviceToHost, dp_ctx().stream));
-    DP_CUDA(cudaMemcpyAsync(out + 4, L->den[last], 32, cudaMemcpyDeviceToHost, dp_ctx().stream));
-    DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));
-    return DP_OK;
+    if (L->h_out) {   // stored by the tail kernel itself
+        if (dp_wait_flag(L->h_out + 8, 1, false, 0, 30.0) != 1) { DP_CUDA(dp_stream_sync(dp_ctx().stream)); DP_CHECK(L->h_out[8] == 1, DP_ERR_CUDA, "dp_logup_outputs: the tail kernel did not publish the outputs"); }
+        memcpy(out, L->h_out, 64);
+        return DP_OK;
+    }
+    DpD2H x(dp_ctx().stream, 64);
+    if (int e = x.add(out, L->num[last], 32)) return e;
+    if (int e = x.add(out + 4, L->den[last], 32)) return e;
+    return x.finish();
 }
 
 // LogUpLayer::get_mles (circuit.rs:137-180) of the layer whose halves have `layer_vars` variables:
@@ -156,7 +172,11 @@ int dp_logup_layer_mles(const dp_logup *L, uint32_t layer_vars, dp_mle **out_vie
 int dp_logup_free(dp_logup *L) {
     if (!L) return DP_OK;
     std::lock_guard<std::recursive_mutex> lk(dp_ctx().mu);
-    if (dp_ctx().ready) dp_dev_free(L->block);
+    if (dp_ctx().ready) {
+        if (L->h_out && L->h_out[8] != 1) dp_stream_sync(dp_ctx().stream);   // the tail kernel still owns the pinned block
+        dp_dev_free(L->block);
+    }
+    dp_pinned_free(L->h_out);
     delete L;
     return DP_OK;
 }

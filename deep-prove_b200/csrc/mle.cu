@@ -263,9 +263,7 @@ int dp_mle_clone(const dp_mle *src, dp_mle **out) {
 int dp_mle_download(const dp_mle *m, uint64_t *out_evals) {
     DP_REQUIRE_CTX();
     DP_CHECK(m && out_evals, DP_ERR_INVALID, "dp_mle_download: null argument");
-    DP_CUDA(cudaMemcpyAsync(out_evals, m->data, m->bytes(), cudaMemcpyDeviceToHost, dp_ctx().stream));
-    DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));
-    return DP_OK;
+    return dp_d2h(out_evals, m->data, m->bytes(), dp_ctx().stream);
 }
 
 int dp_mle_info(const dp_mle *m, uint64_t *len, int *is_ext, uint32_t *num_vars) {
@@ -359,10 +357,9 @@ int dp_mle_evaluate(const dp_mle *m, const uint64_t *point, uint32_t num_vars, u
             dp_dev_free(mid);
         }
     }
-    DP_CUDA(cudaMemcpyAsync(out, res, 16, cudaMemcpyDeviceToHost, dp_ctx().stream));
-    DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));
+    const int rc = dp_d2h(out, res, 16, dp_ctx().stream);
     dp_dev_free(res);
-    return DP_OK;
+    return rc;
 }
 
 // evaluate (mle.rs:607-623) for n MLEs with the same num_vars at the same point (e.g. the LogUp output claims,
@@ -391,7 +388,7 @@ int dp_mle_evaluate_many(const dp_mle *const *mles, uint32_t n, const uint64_t *
     }
     DP_CUDA(cudaGetLastError());
     DP_CUDA(cudaMemcpyAsync(hres, res, sizeof(gle) * n, cudaMemcpyDeviceToHost, dp_ctx().stream));
-    DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));
+    DP_CUDA(dp_stream_sync(dp_ctx().stream));
     for (u32 i = 0; i < n; i++) { out[2 * i] = hres[i].c0; out[2 * i + 1] = hres[i].c1; }
     dp_dev_free(w); dp_dev_free(res); dp_pinned_free(hres);
     return DP_OK;

@@ -601,7 +601,7 @@ struct dp_sc {
     std::vector<dp_sc_product> products;
     ScProd *d_descs = nullptr, *h_descs = nullptr;
     gle *d_partials = nullptr, *d_out = nullptr, *h_out = nullptr;
-    u32 *d_counters = nullptr;
+    u32 *d_counters = nullptr; bool counters_pooled = false, round_in_flight = false;
     ScFin *d_fin = nullptr, *h_fin = nullptr;
     gle *h_pairs = nullptr; bool have_pairs = false;
     u64 seq = 0; u64 *h_flag = nullptr; u32 *d_done = nullptr;
@@ -634,12 +634,13 @@ static gle sc_extrapolate(const gle *evals, u32 n, u64 at) {
 
 static int sc_free_all(dp_sc *s) {
     for (auto &m : s->mles) if (m.work) { dp_dev_free(m.work); m.work = nullptr; }
-    dp_dev_free(s->d_descs); dp_dev_free(s->d_partials); dp_dev_free(s->d_out); dp_dev_free(s->d_counters); dp_dev_free(s->d_fin);
+    dp_dev_free(s->d_descs); dp_dev_free(s->d_partials); dp_dev_free(s->d_out); dp_dev_free(s->d_fin);
+    if (s->counters_pooled && !s->round_in_flight) dp_zero_block_put(s->d_counters); else dp_dev_free(s->d_counters);   // a round that never signalled may have left tickets behind
     dp_dev_free(s->d_xpart); dp_dev_free(s->d_xctl);
     dp_pinned_free(s->h_flag);
     dp_pinned_free(s->h_descs); dp_pinned_free(s->h_out); dp_pinned_free(s->h_fin); dp_pinned_free(s->h_pairs);
     if (s->h_dbg) {   // DP_SC_RES_DEBUG: device clocks of CTA 0 / thread 0 per round: wait-for-challenge | broadcast | descriptors | work | cluster barrier | sum+store | fence+flag
-        cudaStreamSynchronize(dp_ctx().stream);
+        dp_stream_sync(dp_ctx().stream);
         for (u32 k = 0; k < s->dbg_rounds && k < 64; k++) {
             const long long *d = s->h_dbg + 8 * k;
             fprintf(stderr, "[sc_res] round %2u cycles: wait %6lld bcast %5lld desc %5lld work %6lld clsync %5lld sum %5lld signal %5lld | total-excl-wait %6lld\n", k,
@@ -699,7 +700,7 @@ static bool sc_tail_supported() {
         cudaStream_t st = dp_ctx().stream;
         k_tail_probe<<<1, 1, 0, st>>>(pin, pin + 8, 100000000LL); dp_count_launch();
         __atomic_store_n(&pin[0], (u64)1, __ATOMIC_RELEASE);          // reached at once unless the launch call itself waits for the kernel
-        if (cudaStreamSynchronize(st) == cudaSuccess) supported = (pin[8] == 1);
+        if (dp_stream_sync(st) == cudaSuccess) supported = (pin[8] == 1);
         dp_pinned_free(pin);
     });
     return supported;
@@ -778,9 +779,8 @@ static int sc_tail_round(dp_sc *s, gle r, bool fold, uint64_t *out_evals) {
     s->last_bytes = 0;
     {
         DP_HOST_TIMED("dp_sc_round(sync wait)");
-        volatile u64 *f = s->h_flag; u64 spins = 0; bool ok = false;
-        while (!(ok = (*f == s->seq))) { if (*f == SC_TAIL_FAILED) break; if (++spins > (1ULL << 30)) break; __builtin_ia32_pause(); }
-        if (!ok) { s->h_chal[0] = SC_TAIL_ABORT; cudaStreamSynchronize(st); DP_CHECK(false, DP_ERR_CUDA, "dp_sc_round: resident kernel timed out waiting for a challenge (other work queued in the same stream?)"); }
+        const bool ok = dp_wait_flag(s->h_flag, s->seq, true, SC_TAIL_FAILED, 8.0) == s->seq;
+        if (!ok) { s->h_chal[0] = SC_TAIL_ABORT; dp_stream_sync(st); DP_CHECK(false, DP_ERR_CUDA, "dp_sc_round: resident kernel timed out waiting for a challenge (other work queued in the same stream?)"); }
     }
     if (s->round == s->max_nv) s->have_pairs = true;   // written to mapped memory before the flag
     return sc_glue(s, out_evals);
@@ -829,12 +829,12 @@ int dp_sc_create(dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *prod
         if ((e = dp_dev_alloc((void **)&s->d_descs, sizeof(ScProd) * n_products))) return e;
         if ((e = dp_dev_alloc((void **)&s->d_partials, sizeof(gle) * SC_NACC * (size_t)s->gx * n_products))) return e;
         if ((e = dp_dev_alloc((void **)&s->d_out, sizeof(gle) * SC_NACC * n_products))) return e;
-        if ((e = dp_dev_alloc((void **)&s->d_counters, sizeof(u32) * (n_products + 1)))) return e;
+        if (sizeof(u32) * (n_products + 1) <= 256) { if ((e = dp_zero_block_get((void **)&s->d_counters))) return e; s->counters_pooled = true; }
+        else { if ((e = dp_dev_alloc((void **)&s->d_counters, sizeof(u32) * (n_products + 1)))) return e; DP_CUDA(cudaMemsetAsync(s->d_counters, 0, sizeof(u32) * (n_products + 1), dp_ctx().stream)); }
         s->d_done = s->d_counters + n_products;
         if ((e = dp_pinned_alloc((void **)&s->h_flag, 64))) return e;
         *s->h_flag = 0;
         if ((e = dp_dev_alloc((void **)&s->d_fin, sizeof(ScFin) * n_mles + sizeof(gle) * 2 * n_mles))) return e;
-        DP_CUDA(cudaMemsetAsync(s->d_counters, 0, sizeof(u32) * (n_products + 1), dp_ctx().stream));
         if ((e = dp_pinned_alloc((void **)&s->h_descs, sizeof(ScProd) * n_products))) return e;
         if ((e = dp_pinned_alloc((void **)&s->h_out, sizeof(gle) * std::max<size_t>(SC_NACC * n_products, n_mles)))) return e;
         if ((e = dp_pinned_alloc((void **)&s->h_fin, sizeof(ScFin) * n_mles))) return e;
@@ -946,7 +946,7 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
     {
         DpProfScope prof(lean_mode == (int)OPM_B ? "k_sc_lean(msg, Base)" : lean_mode == (int)OPM_E ? "k_sc_lean(msg, Ext)" : lean_mode == (int)OPM_BF ? "k_sc_lean(fold Base->Ext + msg)"
                          : lean_mode == (int)OPM_EF ? "k_sc_lean(fold Ext + msg)" : fold ? "k_sc_round(fold+msg)" : "k_sc_round(msg)", bytes, ops);
-        s->seq++;
+        s->seq++; s->round_in_flight = true;
         const ScProd *descs_arg = s->h_descs;                 // mapped pinned memory: no copy node on the latency path
         if (s->n_products == 1) descs_arg = nullptr;          // descriptor travels in the kernel parameters
         else if ((u64)gx * s->n_products > 32) { DP_CUDA(cudaMemcpyAsync(s->d_descs, s->h_descs, sizeof(ScProd) * s->n_products, cudaMemcpyHostToDevice, st)); descs_arg = s->d_descs; }
@@ -993,11 +993,12 @@ int dp_sc_round(dp_sc *s, const uint64_t *challenge, uint64_t *out_evals) {
     }
     {
         DP_HOST_TIMED("dp_sc_round(sync wait)");
-        if (s->have_pairs) DP_CUDA(cudaStreamSynchronize(st));      // last round: the gathered pairs follow the kernel
+        if (s->have_pairs) { DP_CUDA(dp_stream_sync(st)); s->round_in_flight = false; }      // last round: the gathered pairs follow the kernel
         else {
-            volatile u64 *f = s->h_flag; u64 spins = 0; bool ok = false;
-            while (!(ok = (*f == s->seq))) { if (++spins > (1ULL << 26)) break; __builtin_ia32_pause(); }
-            if (!ok) { DP_CUDA(cudaStreamSynchronize(st)); DP_CHECK(*f == s->seq, DP_ERR_CUDA, "dp_sc_round: kernel finished without signalling"); }
+            volatile u64 *f = s->h_flag;
+            const bool ok = dp_wait_flag(f, s->seq, false, 0, 2.0) == s->seq;
+            if (ok) s->round_in_flight = false;
+            if (!ok) { DP_CUDA(dp_stream_sync(st)); DP_CHECK(*f == s->seq, DP_ERR_CUDA, "dp_sc_round: kernel finished without signalling"); s->round_in_flight = false; }
         }
     }
     return sc_glue(s, out_evals);
@@ -1032,7 +1033,7 @@ int dp_sc_finish(dp_sc *s, const uint64_t *last_challenge, uint64_t *out_final) 
     k_sc_final<<<(s->n_mles + 127) / 128, 128, 0, st>>>(s->d_fin, s->n_mles, r, d_vals); DP_LAUNCHED();
     DP_CUDA(cudaGetLastError());
     DP_CUDA(cudaMemcpyAsync(s->h_out, d_vals, sizeof(gle) * s->n_mles, cudaMemcpyDeviceToHost, st));
-    DP_CUDA(cudaStreamSynchronize(st));
+    DP_CUDA(dp_stream_sync(st));
     for (u32 i = 0; i < s->n_mles; i++) { out_final[2 * i] = s->h_out[i].c0; out_final[2 * i + 1] = s->h_out[i].c1; }
     s->finished = true;
     return DP_OK;
@@ -1043,7 +1044,7 @@ int dp_sc_destroy(dp_sc *s) {
     DP_HOST_TIMED("dp_sc_destroy");
     std::lock_guard<std::recursive_mutex> lk(dp_ctx().mu);
     if (dp_ctx().ready) {
-        if (s->tail_active && s->round < s->max_nv) { s->h_chal[0] = SC_TAIL_ABORT; cudaStreamSynchronize(dp_ctx().stream); }   // release the waiting kernel
+        if (s->tail_active && s->round < s->max_nv) { s->h_chal[0] = SC_TAIL_ABORT; dp_stream_sync(dp_ctx().stream); }   // release the waiting kernel
         sc_free_all(s);
     }
     delete s;

@@ -196,7 +196,7 @@ int dp_wit_finish(dp_wit *w, dp_mle **mults, uint32_t *error_bits) {
     cudaStream_t st = dp_ctx().stream;
     k_wit_mult<<<(unsigned)((w->off[w->n_tables] + 255) / 256), 256, 0, st>>>(w->counts, o); DP_LAUNCHED();
     DP_CUDA(cudaMemcpyAsync(w->err_pinned, w->counts + w->off[w->n_tables], 4, cudaMemcpyDeviceToHost, st));
-    DP_CUDA(cudaStreamSynchronize(st));
+    DP_CUDA(dp_stream_sync(st));
     *error_bits = *w->err_pinned;
     return DP_OK;
 }

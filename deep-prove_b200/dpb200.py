@@ -117,6 +117,12 @@ def init(device=0):
     check(lib().dp_init(int(device)))
 
 
+def set_wait_mode(mode):
+    """0 = every proving thread spins on its completion word (lowest latency); 1 = threads sleep and ONE poller thread of the
+    library wakes them (many more proofs than CPUs in flight)"""
+    check(lib().dp_set_wait_mode(int(mode)))
+
+
 def device_count():
     return lib().dp_device_count()
 

@@ -207,12 +207,22 @@ namespace {
 struct ZkPool {
     std::vector<std::thread> th; std::mutex mu; std::condition_variable cv, done_cv;
     ZkHandle *h = nullptr; int device = 0; bool stop = false; uint64_t pending = 0, inflight = 0; std::string label, err; bool failed = false; bool e2e = false;
-    void worker() {
-        bool inited = false;
+    // Identical proofs started together stay in lockstep: all of them sit in the latency-bound layer sumchecks (GPU nearly idle)
+    // and then all of them queue their GPU-filling opening kernels behind each other (CUPTI timeline, profiles/r02k).  So the
+    // workers of one call start `stagger_s` apart (one proof duration spread over the workers; the duration is an average over the
+    // proofs this pool has already run -- the first call of a pool is not staggered): latency-bound and GPU-bound phases of
+    // different proofs then overlap.  The ramp-up and ramp-down this costs are inside the caller's timed region.
+    uint32_t active = 0; uint64_t call_gen = 0; double stagger_s = 0.0, avg_proof_s = 0.0; uint64_t n_timed = 0;
+    void worker(uint32_t idx) {
+        bool inited = false; uint64_t seen_gen = 0;
         for (;;) {
-            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || pending > 0; }); if (stop) break; pending--; inflight++; }
+            uint64_t gen; double delay = 0.0;
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || (pending > 0 && idx < active); }); if (stop) break; pending--; inflight++; gen = call_gen; if (gen != seen_gen) { seen_gen = gen; delay = stagger_s * idx; } }
             try {
+                const bool first_ever = !inited;     // grows this thread's device arena: not a representative duration
                 if (!inited) { dp::check(dp_init(device)); inited = true; }
+                if (delay > 0.0) std::this_thread::sleep_for(std::chrono::duration<double>(delay));
+                auto t0 = std::chrono::steady_clock::now();
                 dp::DynTranscript t(label);
                 dp::zkml::Prover<dp::DynTranscript> prover(h->ctx, t);
                 if (e2e) {   // from the host input vector: inference, prove, serialised proof in host memory
@@ -220,6 +230,8 @@ struct ZkPool {
                     std::vector<uint64_t> bytes = p.flatten(h->model.nodes.size());
                     if (bytes.empty()) throw dp::Error(DP_ERR_STATE, "empty proof");
                 } else { dp::zkml::Proof p = prover.prove(h->trace); (void)p; }
+                const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (!first_ever) { std::lock_guard<std::mutex> lk(mu); n_timed++; avg_proof_s += (sec - avg_proof_s) / (double)std::min<uint64_t>(n_timed, 64); }
             } catch (const std::exception &e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.what(); }
             dp_profile_flush();   // per-kernel timing of the concurrent region (no-op unless dp_profile_enable(1))
             { std::lock_guard<std::mutex> lk(mu); inflight--; if (pending == 0 && inflight == 0) done_cv.notify_all(); }
@@ -237,9 +249,15 @@ extern "C" int dph_zkml_prove_concurrent(void *handle, int device, uint32_t n_wo
     if (!h->trace.valid()) throw dp::Error(DP_ERR_STATE, "dph_zkml_prove_concurrent: run inference first (mode 1)");
     ZkPool *pool;
     { std::lock_guard<std::mutex> lk(g_pools_mu); auto &pp = g_pools[handle]; if (!pp) { pp = std::make_unique<ZkPool>(); pp->h = h; pp->device = device; } pool = pp.get(); }
-    while (pool->th.size() < n_workers) pool->th.emplace_back([pool] { pool->worker(); });
+    while (pool->th.size() < n_workers) { const uint32_t idx = (uint32_t)pool->th.size(); pool->th.emplace_back([pool, idx] { pool->worker(idx); }); }
+    static const bool no_stagger = getenv("DP_NO_STAGGER") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
-    { std::lock_guard<std::mutex> lk(pool->mu); pool->label = label; pool->failed = false; pool->e2e = e2e != 0; pool->pending = n_proofs; }
+    {
+        std::lock_guard<std::mutex> lk(pool->mu);
+        pool->label = label; pool->failed = false; pool->e2e = e2e != 0; pool->pending = n_proofs; pool->active = n_workers; pool->call_gen++;
+        // stagger only when every worker gets several proofs (otherwise the ramps cost more than the overlap gains)
+        pool->stagger_s = (!no_stagger && n_workers > 1 && n_proofs >= 3 * n_workers && pool->n_timed > 0) ? pool->avg_proof_s / n_workers : 0.0;
+    }
     // only the first n_workers threads are woken usefully: notify_all, extra threads just compete for the same jobs
     pool->cv.notify_all();
     { std::unique_lock<std::mutex> lk(pool->mu); pool->done_cv.wait(lk, [&] { return pool->pending == 0 && pool->inflight == 0; }); }

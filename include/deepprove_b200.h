@@ -46,6 +46,12 @@ const char *dp_version(void);
 int dp_set_stream(void *cuda_stream);    /* run on a caller-owned cudaStream_t (e.g. torch's current stream) */
 int dp_synchronize(void);
 uint64_t dp_kernel_launches(void);       /* number of kernels this library launched so far */
+/* How a host thread waits for the device at the end of a round (process-wide).  0 (default) = spin on the completion word:
+ * lowest latency, one busy core per proof in flight.  1 = sleep on a futex that ONE poller thread of the library signals:
+ * ~5 us more per wait, but waiting proofs cost no CPU, so many more proofs than cores can be in flight per GPU (the
+ * reference gets the same effect from rayon's sleeping workers).  Env DP_WAIT_MODE=1 selects it at start-up. */
+int dp_set_wait_mode(int mode);
+int dp_get_wait_mode(void);
 /* Per-kernel timing with CUDA events recorded on the launch stream around each hot kernel (off by
  * default).  dp_profile_read fills parallel arrays (kernel name, launches, summed ms, summed algorithmic
  * bytes per SURVEY.md 8(d)) and returns the number of distinct kernels. */
