@@ -145,6 +145,26 @@ __global__ void k_expand(const T *__restrict__ c, T *__restrict__ out, u32 lg_m,
     }
 }
 
+// One polynomial's codeword sharded over G = 2^logG GPUs (BASELINE configs[3]): rank g owns the contiguous slice
+// [g S, (g+1) S), S = N / G, of the BIT-REVERSED codeword.  In a decimation-in-frequency NTT that slice is an independent
+// size-S transform of   y_r[t] = w_N^(t r) * sum_k x[t + k S] * w_G^(k r),   r = bitrev_logG(g),  x[j] = c[j] shift^j (zero for j >= N/2):
+// the first logG levels collapse into this one pass over the coefficients (every rank reads all of them once, no inter-GPU
+// butterfly exchange), the remaining levels are the ordinary tiled passes on the local slice.
+template <typename T>
+__global__ void k_shard_expand(const T *__restrict__ c, T *__restrict__ out, u32 lg_m, u32 logG, u32 r, PowTab shift_tab, PowTab tab) {
+    const u32 n_log = lg_m + 1;
+    const u64 S = 1ULL << (n_log - logG), terms = 1ULL << (logG - 1);      // x[t + k S] is zero for k >= G/2 (the zero-padded half)
+    u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+    for (; t < S; t += stride) {
+        T acc = t_mulb(c[t], tab_pow(shift_tab, t));
+        for (u64 k = 1; k < terms; k++) {
+            const u64 j = t + k * S;
+            const u64 w = gl_mul(tab_pow(shift_tab, j), tab_pow(tab, (u64)((k * r) & ((1ULL << logG) - 1)) << (32 - logG)));
+            acc = t_add(acc, t_mulb(c[j], w));
+        }
+        out[t] = t_mulb(acc, tab_pow(tab, (t * r) << (32 - n_log)));
+    }
+}
 
 // ---- small polynomials: bit reversal, hypercube interpolation, zero-pad + coset scale, and the whole DIF NTT in ONE block ----
 // (k_bitrev -> k_tile_pass<T,0> -> k_expand -> k_tile_pass<T,1> on a codeword that fits in shared memory: a 2^10 witness column
@@ -516,10 +536,11 @@ static void tree_free(DevTree &t) { if (t.own_levels) dp_dev_free(t.levels); t.l
 
 // ---- K10 FRI fold (commit_phase.rs:511-526, rs.rs:377-410, arithmetic.rs:120-132) ----
 // out[i] = y0 + (r - x0) * (y1 - y0) * w,  x0 = w_{2^(level+1)}^{rev(i, level)} * gamma_lvl,  w = -1/(2 x0)
-__global__ void k_fri_fold(const gle *__restrict__ in, gle *__restrict__ out, u32 level, gle r, u64 gamma_lvl, u64 neg_half_gamma_inv, PowTab tab) {
-    u64 n = 1ULL << level, i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
+// (`n` outputs starting at global index `off`: a rank of a sharded opening folds its own contiguous slice)
+__global__ void k_fri_fold(const gle *__restrict__ in, gle *__restrict__ out, u32 level, u64 n, u64 off, gle r, u64 gamma_lvl, u64 neg_half_gamma_inv, PowTab tab) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x, stride = (u64)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        u64 e = level ? (__brevll(i) >> (64 - level)) : 0;             // rev(i, level), exponent of w_{2^(level+1)}
+        u64 e = level ? (__brevll(i + off) >> (64 - level)) : 0;       // rev(i, level), exponent of w_{2^(level+1)}
         u64 L = 1ULL << (level + 1);
         u64 x0 = gl_mul(tab_pow(tab, e << (32 - (level + 1))), gamma_lvl);
         u64 x0inv_root = tab_pow(tab, ((L - e) & (L - 1)) << (32 - (level + 1)));   // w^{-e}
@@ -594,18 +615,30 @@ __global__ void k_lift(const u64 *__restrict__ src, gle *__restrict__ out, u64 n
 }
 
 // ---- K13 query gather: per (query, tree): [p0.c0 p0.c1 p1.c0 p1.c1][path digests x (lg-1)] ----
-struct QTree { const void *leaves; const u64 *levels; const u64 *level0; u64 off[34]; u32 lg; u32 ext; u32 shift; u32 pad; };
+// Sharded trees (logG > 0): `leaves` / `levels` are this rank's subtree over 2^lg_local leaves, `top_*` the replicated tree over the G
+// subtree roots; a query whose leaf pair another rank owns leaves its row untouched (zero) -- the ranks' rows are summed afterwards.
+struct QTree { const void *leaves; const u64 *levels; const u64 *level0; u64 off[34]; u32 lg; u32 ext; u32 shift; u32 logG;
+               u32 lg_local; u32 rank; const u64 *top_lvl0; const u64 *top_levels; u64 top_off[9]; };
 __global__ void k_query_gather(const QTree *__restrict__ trees, u32 n_trees, const u64 *__restrict__ xs, const u64 *__restrict__ out_off, u64 per_query, u64 *__restrict__ out) {
     u32 q = blockIdx.x, ti = blockIdx.y;
     QTree t = trees[ti];
     u64 idx = xs[q] >> t.shift;
     u64 p0 = (idx | 1) - 1;
     u64 *o = out + (u64)q * per_query + out_off[ti];
+    u64 owner = 0;
+    if (t.logG) { owner = p0 >> t.lg_local; if (owner != t.rank) return; p0 &= (1ULL << t.lg_local) - 1; }
+    const u32 lgl = t.logG ? t.lg_local : t.lg;
     for (u32 k = threadIdx.x; k < t.lg; k += blockDim.x) {
         if (k == 0) {
             if (t.ext) { gle a = ld_e((const gle *)t.leaves + p0), b = ld_e((const gle *)t.leaves + p0 + 1); o[0] = a.c0; o[1] = a.c1; o[2] = b.c0; o[3] = b.c1; }
             else { const u64 *l = (const u64 *)t.leaves; o[0] = l[p0]; o[1] = 0; o[2] = l[p0 + 1]; o[3] = 0; }
         }
+        if (k + 1 < t.lg && k + 1 >= lgl) {   // above this rank's subtree: the sibling subtree root, then the replicated top levels
+            const u32 kk = k + 1 - lgl;
+            const u64 *sd = kk == 0 ? t.top_lvl0 + 4 * (owner ^ 1) : t.top_levels + 4 * (t.top_off[kk] + ((owner >> kk) ^ 1));
+            u64 *d = o + 4 + 4 * k;
+            d[0] = sd[0]; d[1] = sd[1]; d[2] = sd[2]; d[3] = sd[3];
+        } else
         if (k + 1 < t.lg) {   // path entry k = inner[k][(p0 >> (k+1)) ^ 1]
             u64 node = (p0 >> (k + 1)) ^ 1;
             u64 *d = o + 4 + 4 * k;
@@ -631,9 +664,12 @@ struct dp_pcs_comm {
     u64 root[4] = {0, 0, 0, 0};
     std::vector<dp_pcs_comm *> parts;   // batch_commit: one (encode-only) commitment per polynomial; their trees are views of `tree`
     u64 *level0 = nullptr;              // batch_commit: digests of the leaf pairs
+    // dp_pcs_commit_shard: `codeword` / `bh_evals` / `tree` are this rank's contiguous slice (cw_len = local length); `top` is the
+    // replicated tree over the world's subtree roots (dp_pcs_comm_set_shard_roots), `root` the global root once it is set
+    u32 shard_rank = 0, shard_log = 0; DevTree top; u64 *top_lvl0 = nullptr; u64 local_root[4] = {0, 0, 0, 0};
 };
 
-struct OpenRound { gle *oracle = nullptr; u64 len = 0; DevTree tree; };
+struct OpenRound { gle *oracle = nullptr; u64 len = 0; DevTree tree; DevTree top; u64 *top_lvl0 = nullptr; };
 struct dp_pcs_open {
     u32 num_vars = 0, full_log = 0, num_rounds = 0, round = 0;
     std::vector<const dp_pcs_comm *> comms; std::vector<gle> coeffs; bool batch = false;
@@ -646,6 +682,7 @@ struct dp_pcs_open {
     gle final_msg[1 << BF_BASECODE_LOG]; bool have_final = false;
     gle *scratch_sum_evals = nullptr;
     u64 *h_root = nullptr; u64 root_seq = 0;     // mapped pinned: [0..3] root of the round's tree, [8] completion word
+    u32 shard_rank = 0, shard_log = 0;           // sharded opening (one commitment from dp_pcs_commit_shard): everything above is the local slice
 };
 
 static void msg_to_coeffs(const uint64_t *ev /* p(0),p(1),p(2) */, uint64_t *out /* c0,c1,c2 */) {
@@ -770,6 +807,107 @@ int dp_pcs_commit(const dp_mle *poly, uint32_t full_log, dp_pcs_comm **out) {
     return rc;
 }
 
+
+// shift^j tables per (full_log - nv): shared with commit_enqueue
+static int shift_powtab(u64 shift, PowTab *out) {
+    static std::map<u64, const u64 *> tabs;
+    std::lock_guard<std::mutex> lk(g_bf_mu);
+    auto it = tabs.find(shift);
+    if (it == tabs.end()) {
+        u64 *nt = nullptr;
+        DP_CUDA(cudaMalloc((void **)&nt, sizeof(u64) * 3 * 2048));
+        k_pow_table<<<24, 256, 0, dp_ctx().stream>>>(shift, nt); DP_LAUNCHED();
+        DP_CUDA(cudaStreamSynchronize(dp_ctx().stream));
+        it = tabs.emplace(shift, nt).first;
+    }
+    out->t0 = it->second; out->t1 = it->second + 2048; out->t2 = it->second + 4096;
+    return DP_OK;
+}
+// the replicated tree over the world's subtree roots: level "0" = the G roots, then log G levels of compress
+static int top_tree_build(DevTree &top, u64 **top_lvl0, const uint64_t *roots, u32 logG, u64 out_root[4]) {
+    DpCtx &c = dp_ctx();
+    const u64 G = 1ULL << logG;
+    if (int e = dp_dev_alloc((void **)top_lvl0, 32 * G)) return e;
+    u64 *pin = nullptr;
+    if (int e = dp_pinned_alloc((void **)&pin, 32 * G + 64)) return e;
+    for (u64 k = 0; k < 4 * G; k++) pin[k] = gl_canon(roots[k]);
+    DP_CUDA(cudaMemcpyAsync(*top_lvl0, pin, 32 * G, cudaMemcpyHostToDevice, c.stream));
+    int rc = tree_build(top, nullptr, false, 2 * G, *top_lvl0);
+    if (rc == DP_OK) rc = dp_d2h(out_root, top.root_dev, 32, c.stream);
+    else cudaStreamSynchronize(c.stream);
+    dp_pinned_free(pin);
+    return rc;
+}
+
+// Basefold::commit of ONE polynomial sharded over `world` = 2^k ranks (one process per GPU).  Every rank passes the whole
+// polynomial (resident on its GPU) and keeps only its contiguous slice of the bit-reversed evaluations, of the bit-reversed
+// codeword and the Merkle subtree over that slice; (*out)'s root is the SUBTREE root until dp_pcs_comm_set_shard_roots has been
+// given all ranks' subtree roots (one all-gather of 32 bytes per rank -- the only exchange of the commit).
+int dp_pcs_commit_shard(const dp_mle *poly, uint32_t full_log, uint32_t rank, uint32_t world, dp_pcs_comm **out) {
+    DP_HOST_TIMED("dp_pcs_commit_shard");
+    DP_REQUIRE_CTX();
+    DP_CHECK(poly && out, DP_ERR_INVALID, "dp_pcs_commit_shard: null argument");
+    u32 logG = 0; while ((1u << logG) < world) logG++;
+    DP_CHECK(world >= 2 && (1u << logG) == world && rank < world, DP_ERR_INVALID, "dp_pcs_commit_shard: world must be a power of two >= 2 and rank < world");
+    DP_CHECK(!blake_on(), DP_ERR_UNSUPPORTED, "dp_pcs_commit_shard: Poseidon2 trees only");
+    const u32 nv = poly->num_vars();
+    DP_CHECK(nv <= full_log, DP_ERR_INVALID, "PolynomialTooLarge");
+    DP_CHECK(logG <= 6 && nv >= BF_BASECODE_LOG + 4 && nv > logG + 11, DP_ERR_INVALID, "dp_pcs_commit_shard: polynomial too small to shard over this many ranks");
+    if (int e = bf_prepare()) return e;
+    DpCtx &c = dp_ctx();
+    dp_pcs_comm *cm = new dp_pcs_comm();
+    cm->num_vars = nv; cm->full_log = full_log; cm->is_base = !poly->is_ext; cm->shard_rank = rank; cm->shard_log = logG;
+    const size_t esz = poly->is_ext ? 16 : 8;
+    const u64 m = poly->len, N = m << BF_RATE_LOG, S = N >> logG, Ml = m >> logG; const u32 n_log = nv + BF_RATE_LOG;
+    cm->cw_len = S;
+    void *coef = nullptr;
+    auto fail = [&](int e) { dp_dev_free(coef); dp_pcs_comm_free(cm); return e; };
+    if (int e = dp_dev_alloc(&cm->bh_evals, esz * Ml)) return fail(e);
+    if (int e = dp_dev_alloc(&cm->codeword, esz * S)) return fail(e);
+    if (int e = dp_dev_alloc(&coef, esz * m)) return fail(e);
+    u64 shift = 7; for (u32 i = 0; i < full_log - nv; i++) shift = gl_sqr(shift);
+    PowTab st; if (int e = shift_powtab(shift, &st)) return fail(e);
+    const int g = dp_grid_for(m, 256, 8), gs = dp_grid_for(S, 256, 8);
+    u32 rev_rank = 0; for (u32 b = 0; b < logG; b++) if (rank >> b & 1) rev_rank |= 1u << (logG - 1 - b);
+    if (poly->is_ext) {
+        { DpProfScope p("k_bitrev", esz * m * 2); k_bitrev<gle><<<g, 256, 0, c.stream>>>((const gle *)poly->data, (gle *)coef, nv); DP_LAUNCHED(); }
+        cudaMemcpyAsync(cm->bh_evals, (const char *)coef + esz * Ml * rank, esz * Ml, cudaMemcpyDeviceToDevice, c.stream);
+        if (int e = run_levels<gle, 0>((gle *)coef, nv, 0, nv)) return fail(e);
+        { DpProfScope p("k_shard_expand", esz * (m + S)); k_shard_expand<gle><<<gs, 256, 0, c.stream>>>((const gle *)coef, (gle *)cm->codeword, nv, logG, rev_rank, st, root_tab()); DP_LAUNCHED(); }
+        if (int e = run_levels<gle, 1>((gle *)cm->codeword, n_log - logG, 0, n_log - logG)) return fail(e);
+    } else {
+        { DpProfScope p("k_bitrev", esz * m * 2); k_bitrev<u64><<<g, 256, 0, c.stream>>>((const u64 *)poly->data, (u64 *)coef, nv); DP_LAUNCHED(); }
+        cudaMemcpyAsync(cm->bh_evals, (const char *)coef + esz * Ml * rank, esz * Ml, cudaMemcpyDeviceToDevice, c.stream);
+        if (int e = run_levels<u64, 0>((u64 *)coef, nv, 0, nv)) return fail(e);
+        { DpProfScope p("k_shard_expand", esz * (m + S)); k_shard_expand<u64><<<gs, 256, 0, c.stream>>>((const u64 *)coef, (u64 *)cm->codeword, nv, logG, rev_rank, st, root_tab()); DP_LAUNCHED(); }
+        if (int e = run_levels<u64, 1>((u64 *)cm->codeword, n_log - logG, 0, n_log - logG)) return fail(e);
+    }
+    DP_CUDA(cudaGetLastError());
+    if (int e = tree_build(cm->tree, cm->codeword, poly->is_ext, S)) return fail(e);
+    if (int e = dp_d2h(cm->local_root, cm->tree.root_dev, 32, c.stream)) return fail(e);
+    dp_dev_free(coef); coef = nullptr;
+    memcpy(cm->root, cm->local_root, 32);
+    *out = cm;
+    return DP_OK;
+}
+// `roots`: world x 4 words, rank-major (the all-gathered subtree roots).  Builds the replicated top of the tree; afterwards
+// dp_pcs_comm_info returns the root of the whole 2^(nv+1)-leaf tree (identical to dp_pcs_commit's).
+int dp_pcs_comm_set_shard_roots(dp_pcs_comm *cm, const uint64_t *roots, uint64_t out_root[4]) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(cm && roots && cm->shard_log > 0, DP_ERR_INVALID, "dp_pcs_comm_set_shard_roots: not a sharded commitment");
+    DP_CHECK(!cm->top_lvl0, DP_ERR_STATE, "dp_pcs_comm_set_shard_roots: roots already set");
+    for (int k = 0; k < 4; k++) DP_CHECK(gl_canon(roots[4 * cm->shard_rank + k]) == cm->local_root[k], DP_ERR_INVALID, "dp_pcs_comm_set_shard_roots: this rank's entry is not its own subtree root");
+    if (int e = top_tree_build(cm->top, &cm->top_lvl0, roots, cm->shard_log, cm->root)) return e;
+    if (out_root) memcpy(out_root, cm->root, 32);
+    return DP_OK;
+}
+int dp_pcs_comm_shard_info(const dp_pcs_comm *cm, uint32_t *rank, uint32_t *world, uint64_t local_root[4]) {
+    DP_CHECK(cm, DP_ERR_INVALID, "dp_pcs_comm_shard_info: null");
+    if (rank) *rank = cm->shard_rank;
+    if (world) *world = 1u << cm->shard_log;
+    if (local_root) memcpy(local_root, cm->shard_log ? cm->local_root : cm->root, 32);
+    return DP_OK;
+}
 
 // Basefold::batch_commit (basefold.rs:356-452): n polynomials of the same size and field under ONE Merkle tree whose leaves
 // are the batches of values (merkle_tree.rs:68-74,286-312).  Encoding is the per-polynomial pipeline; the leaf level hashes
@@ -907,7 +1045,7 @@ int dp_pcs_comm_bh_evals(const dp_pcs_comm *cm, dp_mle **view) {
 int dp_pcs_comm_free(dp_pcs_comm *cm) {
     if (!cm) return DP_OK;
     std::lock_guard<std::recursive_mutex> lk(dp_ctx().mu);
-    if (dp_ctx().ready) { tree_free(cm->tree); if (!cm->trivial) dp_dev_free(cm->codeword); dp_dev_free(cm->bh_evals); dp_dev_free(cm->level0); }
+    if (dp_ctx().ready) { tree_free(cm->tree); if (!cm->trivial) dp_dev_free(cm->codeword); dp_dev_free(cm->bh_evals); dp_dev_free(cm->level0); tree_free(cm->top); dp_dev_free(cm->top_lvl0); }
     for (auto *p : cm->parts) dp_pcs_comm_free(p);
     delete cm;
     return DP_OK;
@@ -930,6 +1068,46 @@ int dp_pcs_open_begin(const dp_pcs_comm *const *comms, const uint64_t *coeffs, u
         if (coeffs) o->coeffs.push_back(e_make(gl_canon(coeffs[2 * i]), gl_canon(coeffs[2 * i + 1])));
     }
     DP_CHECK(num_vars > BF_BASECODE_LOG, DP_ERR_INVALID, "minimum number of variables must be greater than basecode_msg_size_log");
+    for (u32 i = 0; i < n_comms; i++) DP_CHECK(comms[i]->shard_log == 0 || (n_comms == 1 && !coeffs), DP_ERR_UNSUPPORTED, "dp_pcs_open_begin: a sharded commitment is opened alone");
+    if (comms[0]->shard_log) {
+        // Sharded opening: everything below works on this rank's contiguous slices; the messages it returns are PARTIAL sums (the
+        // coefficient form is linear in the evaluations), the roots SUBTREE roots -- the caller all-gathers and adds / combines them.
+        const dp_pcs_comm *cm = comms[0];
+        DP_CHECK(cm->num_vars == num_vars && cm->top_lvl0, DP_ERR_STATE, "dp_pcs_open_begin: sharded commitment needs num_vars variables and its shard roots set");
+        const u32 logG = cm->shard_log, nvl = num_vars - logG;
+        o->shard_rank = cm->shard_rank; o->shard_log = logG;
+        o->num_rounds = num_vars - BF_BASECODE_LOG;
+        const u64 Nl = cm->cw_len, Ml = 1ULL << nvl;
+        o->n0 = Nl;
+        if (int e = dp_dev_alloc((void **)&o->oracle0, sizeof(gle) * Nl)) return e;
+        if (cm->is_base) { k_lift<<<dp_grid_for(Nl, 256, 8), 256, 0, c.stream>>>((const u64 *)cm->codeword, o->oracle0, Nl); DP_LAUNCHED(); }
+        else DP_CUDA(cudaMemcpyAsync(o->oracle0, cm->codeword, sizeof(gle) * Nl, cudaMemcpyDeviceToDevice, c.stream));
+        dp_mle *ev = new dp_mle(); ev->len = Ml; ev->owned = false; ev->data = cm->bh_evals; ev->is_ext = !cm->is_base;
+        o->evals = ev;
+        // eq slice: the table over the low nvl variables of the reversed point, times the eq factor of this rank's top bits
+        std::vector<uint64_t> rp(2 * num_vars);
+        for (u32 i = 0; i < num_vars; i++) { rp[2 * i] = point[2 * (num_vars - 1 - i)]; rp[2 * i + 1] = point[2 * (num_vars - 1 - i) + 1]; }
+        dp_mle *eq_low = nullptr;
+        if (int e = dp_eq_build(rp.data(), nvl, &eq_low)) return e;
+        gle scal = e_one();
+        for (u32 j = 0; j < logG; j++) {
+            gle x = e_make(gl_canon(rp[2 * (nvl + j)]), gl_canon(rp[2 * (nvl + j) + 1]));
+            scal = e_mul(scal, ((cm->shard_rank >> j) & 1) ? x : e_sub(e_one(), x));
+        }
+        dp_mle *eq = new dp_mle(); eq->len = Ml; eq->is_ext = true; eq->owned = true;
+        if (int e = dp_dev_alloc(&eq->data, sizeof(gle) * Ml)) return e;
+        if (int e = lincomb_bcast((gle *)eq->data, nullptr, {LcTerm{eq_low->data, scal, true, 0}}, Ml)) return e;
+        dp_mle_free(eq_low);
+        o->eq = eq;
+        dp_mle *ms[2] = {o->eq, o->evals};
+        dp_sc_product pr; memset(&pr, 0, sizeof pr); pr.coef[0] = 1; pr.n_idx = 2; pr.idx[0] = 0; pr.idx[1] = 1;
+        if (int e = dp_sc_create(ms, 2, &pr, 1, nvl, 2, &o->sc)) return e;
+        uint64_t ev3[6];
+        if (int e = dp_sc_round(o->sc, nullptr, ev3)) return e;
+        msg_to_coeffs(ev3, first_msg);
+        *out = o;
+        return DP_OK;
+    }
     if (!o->batch) DP_CHECK(n_comms == 1 && comms[0]->num_vars == num_vars, DP_ERR_INVALID, "dp_pcs_open_begin: single open needs one commitment of num_vars variables");
     o->num_rounds = num_vars - BF_BASECODE_LOG;
     u64 N = 1ULL << (num_vars + BF_RATE_LOG), M = 1ULL << num_vars;
@@ -1000,7 +1178,7 @@ int dp_pcs_open_round(dp_pcs_open *o, const uint64_t challenge[2], uint64_t next
         }
     }
     // K10: fold the running oracle
-    u64 len = o->n0; u32 level = 0; while ((2ULL << level) < len) level++;   // log2(len) - 1
+    u64 len = o->n0; u32 level = 0; while ((2ULL << level) < (len << o->shard_log)) level++;   // log2(global len) - 1
     gle *folded = nullptr;
     if (int e = dp_dev_alloc((void **)&folded, sizeof(gle) * (len >> 1))) return e;
     {
@@ -1008,7 +1186,7 @@ int dp_pcs_open_round(dp_pcs_open *o, const uint64_t challenge[2], uint64_t next
         u64 gamma = 7; for (u32 k = 0; k < gexp; k++) gamma = gl_sqr(gamma);
         u64 nhgi = gl_neg(gl_mul(gl_inv(gamma), 0x7FFFFFFF80000001ULL));   // -(1/gamma_lvl)/2
         DpProfScope p("k_fri_fold", len * 16 + (len >> 1) * 16);
-        k_fri_fold<<<dp_grid_for(len >> 1, 256, 8), 256, 0, c.stream>>>(o->oracle0, folded, level, r, gamma, nhgi, root_tab()); DP_LAUNCHED();
+        k_fri_fold<<<dp_grid_for(len >> 1, 256, 8), 256, 0, c.stream>>>(o->oracle0, folded, level, len >> 1, (u64)o->shard_rank * (len >> 1), r, gamma, nhgi, root_tab()); DP_LAUNCHED();
         DP_CUDA(cudaGetLastError());
     }
     // the oracle just consumed is either round i-1's tree leaves (kept) or the initial / merged buffer (freed)
@@ -1035,10 +1213,13 @@ int dp_pcs_open_round(dp_pcs_open *o, const uint64_t challenge[2], uint64_t next
         if (int e = dp_sc_round(o->sc, ch, ev3)) return e;       // fold (the message it also computes is unused)
         dp_mle *view = nullptr;
         if (int e = dp_sc_current_mle(o->sc, 1, &view)) return e;
-        DP_CHECK(view->len == (1ULL << BF_BASECODE_LOG) && view->is_ext, DP_ERR_STATE, "dp_pcs_open_round: unexpected final message size");
+        DP_CHECK(view->len == ((1ULL << BF_BASECODE_LOG) >> o->shard_log) && view->is_ext, DP_ERR_STATE, "dp_pcs_open_round: unexpected final message size");
         gle tmp[1 << BF_BASECODE_LOG];
-        if (int e = dp_d2h(tmp, view->data, sizeof tmp, c.stream)) return e;
+        if (int e = dp_d2h(tmp, view->data, sizeof(gle) * view->len, c.stream)) return e;
         dp_mle_free(view);
+        if (o->shard_log) {   // this rank's slice of the bit-reversed final message: the caller concatenates the ranks' slices and un-bit-reverses
+            for (u32 k = 0; k < ((1u << BF_BASECODE_LOG) >> o->shard_log); k++) o->final_msg[k] = tmp[k];
+        } else
         for (u32 k = 0; k < (1u << BF_BASECODE_LOG); k++) { u32 j = 0; for (u32 b = 0; b < BF_BASECODE_LOG; b++) if (k >> b & 1) j |= 1u << (BF_BASECODE_LOG - 1 - b); o->final_msg[j] = tmp[k]; }
         o->have_final = true;
         *is_last = 1;
@@ -1047,10 +1228,24 @@ int dp_pcs_open_round(dp_pcs_open *o, const uint64_t challenge[2], uint64_t next
     return DP_OK;
 }
 
+// Sharded openings: after a round that returned a subtree root, the caller all-gathers the ranks' subtree roots and hands them back;
+// this builds the replicated top of that round's tree (needed for the query paths) and returns the root of the whole oracle tree.
+int dp_pcs_open_set_shard_roots(dp_pcs_open *o, const uint64_t *roots, uint64_t out_root[4]) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(o && roots && out_root && o->shard_log > 0 && !o->rounds.empty(), DP_ERR_INVALID, "dp_pcs_open_set_shard_roots: not a sharded opening with a pending round");
+    OpenRound &rd = o->rounds.back();
+    DP_CHECK(!rd.top_lvl0, DP_ERR_STATE, "dp_pcs_open_set_shard_roots: roots of this round already set");
+    u64 rt[4];
+    if (int e = top_tree_build(rd.top, &rd.top_lvl0, roots, o->shard_log, rt)) return e;
+    for (int k = 0; k < 4; k++) out_root[k] = rt[k];
+    return DP_OK;
+}
+
+// (sharded opening: this rank's (2^7 >> log world) entries of the BIT-REVERSED final message -- concatenate by rank, then un-bit-reverse)
 int dp_pcs_open_final_message(dp_pcs_open *o, uint64_t *out) {
     DP_CHECK(o && out, DP_ERR_INVALID, "dp_pcs_open_final_message: null argument");
     DP_CHECK(o->have_final, DP_ERR_STATE, "dp_pcs_open_final_message: commit phase not finished");
-    for (u32 k = 0; k < (1u << BF_BASECODE_LOG); k++) { out[2 * k] = o->final_msg[k].c0; out[2 * k + 1] = o->final_msg[k].c1; }
+    for (u32 k = 0; k < ((1u << BF_BASECODE_LOG) >> o->shard_log); k++) { out[2 * k] = o->final_msg[k].c0; out[2 * k + 1] = o->final_msg[k].c1; }
     return DP_OK;
 }
 
@@ -1058,8 +1253,8 @@ int dp_pcs_open_final_message(dp_pcs_open *o, uint64_t *out) {
 uint64_t dp_pcs_open_query_words(const dp_pcs_open *o) {
     if (!o) return 0;
     u64 w = 0;
-    for (auto cm : o->comms) { u32 lg = 0; while ((1ULL << lg) < cm->cw_len) lg++; w += 4 + 4 * (u64)(lg - 1); }
-    for (auto &rd : o->rounds) w += 4 + 4 * (u64)(rd.tree.lg - 1);
+    for (auto cm : o->comms) { u32 lg = 0; while ((1ULL << lg) < cm->cw_len) lg++; lg += o->shard_log; w += 4 + 4 * (u64)(lg - 1); }
+    for (auto &rd : o->rounds) w += 4 + 4 * (u64)(rd.tree.lg + o->shard_log - 1);
     return w;
 }
 
@@ -1074,14 +1269,18 @@ int dp_pcs_open_query(dp_pcs_open *o, const uint64_t *x_indices, uint32_t n, uin
     u32 nt = (u32)(o->comms.size() + o->rounds.size());
     std::vector<QTree> qt(nt); std::vector<u64> off(nt);
     u32 lgN = o->num_vars + BF_RATE_LOG; u64 w = 0; u32 k = 0;
-    auto fill = [&](const DevTree &t, u32 shift) {
+    const u32 logG = o->shard_log;
+    auto fill = [&](const DevTree &t, u32 shift, const DevTree *top, const u64 *top_lvl0) {
         QTree &q = qt[k]; memset(&q, 0, sizeof q);
-        q.leaves = t.leaves; q.levels = t.levels; q.level0 = t.level0; q.lg = t.lg; q.ext = t.ext; q.shift = shift;
+        q.leaves = t.leaves; q.levels = t.levels; q.level0 = t.level0; q.lg = t.lg + logG; q.ext = t.ext; q.shift = shift;
         for (u32 l = 1; l < t.lg && l < 34; l++) q.off[l] = t.lvl_off[l];
-        off[k] = w; w += 4 + 4 * (u64)(t.lg - 1); k++;
+        q.logG = logG; q.lg_local = t.lg; q.rank = o->shard_rank;
+        if (logG) { q.top_lvl0 = top_lvl0; q.top_levels = top->levels; for (u32 l = 1; l < top->lg && l < 9; l++) q.top_off[l] = top->lvl_off[l]; }
+        off[k] = w; w += 4 + 4 * (u64)(q.lg - 1); k++;
     };
-    for (auto cm : o->comms) fill(cm->tree, lgN - cm->tree.lg);
-    for (size_t i = 0; i < o->rounds.size(); i++) fill(o->rounds[i].tree, (u32)i + 1);
+    if (logG) for (auto &rd : o->rounds) DP_CHECK(rd.top_lvl0 != nullptr, DP_ERR_STATE, "dp_pcs_open_query: a round's shard roots were never set");
+    for (auto cm : o->comms) fill(cm->tree, lgN - (cm->tree.lg + logG), &cm->top, cm->top_lvl0);
+    for (size_t i = 0; i < o->rounds.size(); i++) fill(o->rounds[i].tree, (u32)i + 1, &o->rounds[i].top, o->rounds[i].top_lvl0);
     QTree *dq = nullptr; u64 *doff = nullptr, *dx = nullptr, *dout = nullptr;
     if (int e = dp_dev_alloc((void **)&dq, sizeof(QTree) * nt)) return e;
     if (int e = dp_dev_alloc((void **)&doff, 8 * nt)) return e;
@@ -1091,6 +1290,7 @@ int dp_pcs_open_query(dp_pcs_open *o, const uint64_t *x_indices, uint32_t n, uin
     DP_CUDA(cudaMemcpyAsync(doff, off.data(), 8 * nt, cudaMemcpyHostToDevice, c.stream));
     DP_CUDA(cudaMemcpyAsync(dx, x_indices, 8 * (size_t)n, cudaMemcpyHostToDevice, c.stream));
     DP_CUDA(dp_stream_sync(c.stream));   // qt/off are stack-owned host buffers
+    if (logG) DP_CUDA(cudaMemsetAsync(dout, 0, 8 * w * n, c.stream));   // rows of queries other ranks own stay zero
     k_query_gather<<<dim3(n, nt), 32, 0, c.stream>>>(dq, nt, dx, doff, w, dout); DP_LAUNCHED();
     DP_CUDA(cudaGetLastError());
     if (int e = dp_d2h(out, dout, 8 * w * n, c.stream)) return e;
@@ -1104,7 +1304,7 @@ int dp_pcs_open_free(dp_pcs_open *o) {
     if (dp_ctx().ready) {
         if (o->sc) dp_sc_destroy(o->sc);
         bool oracle_in_rounds = false;
-        for (auto &rd : o->rounds) { if (rd.oracle == o->oracle0) oracle_in_rounds = true; tree_free(rd.tree); dp_dev_free(rd.oracle); }
+        for (auto &rd : o->rounds) { if (rd.oracle == o->oracle0) oracle_in_rounds = true; tree_free(rd.tree); dp_dev_free(rd.oracle); tree_free(rd.top); dp_dev_free(rd.top_lvl0); }
         if (!oracle_in_rounds) dp_dev_free(o->oracle0);
         dp_dev_free(o->scratch_sum_evals);
     }

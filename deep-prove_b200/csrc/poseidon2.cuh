@@ -25,7 +25,12 @@ static inline cudaError_t p2_upload_constants(const u64 *ext /*64*/, const u64 *
 // reduction.  Only the four digest words are canonicalised at the end.  Every step is exact modular arithmetic,
 // so the digests are bit-identical to the canonical formulation.
 struct p2w { u64 lo; u32 hi; };                                                   // value = lo + hi * 2^64
-__device__ __forceinline__ u64 w_mul(u64 a, u64 b) { return gl_reduce128_weak(a * b, __umul64hi(a, b)); }
+#if GL_MULV == 2
+__device__ __forceinline__ u64 w_red(u64 lo, u64 hi) { return gl_reduce128_weak_alu(lo, hi); }
+#else
+__device__ __forceinline__ u64 w_red(u64 lo, u64 hi) { return gl_reduce128_weak(lo, hi); }
+#endif
+__device__ __forceinline__ u64 w_mul(u64 a, u64 b) { u64 lo, hi; gl_mul128(a, b, lo, hi); return w_red(lo, hi); }
 __device__ __forceinline__ u64 w_add_canon(u64 a, u64 c) {                        // a weak, c < p  ->  weak
     u64 r; asm("{\n\t.reg .u32 c;\n\t.reg .u64 t;\n\tadd.cc.u64 t, %1, %2;\n\taddc.u32 c, 0, 0;\n\tmad.wide.u32 %0, c, 0xFFFFFFFF, t;\n\t}" : "=l"(r) : "l"(a), "l"(c));
     return r;
@@ -44,9 +49,9 @@ __device__ __forceinline__ u64 ww_fold(p2w a) {                                 
 }
 // a * c + (sum as wide) -> weak, one reduction  (internal layer: s[i] * diag[i] + sum)
 __device__ __forceinline__ u64 w_mul_add(u64 a, u64 c, p2w sum) {
-    u64 lo = a * c, hi = __umul64hi(a, c);
+    u64 lo, hi; gl_mul128(a, c, lo, hi);
     asm("{\n\t.reg .u64 h64;\n\tcvt.u64.u32 h64, %3;\n\tadd.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, h64;\n\t}" : "+l"(lo), "+l"(hi) : "l"(sum.lo), "r"(sum.hi));
-    return gl_reduce128_weak(lo, hi);
+    return w_red(lo, hi);
 }
 __device__ __forceinline__ u64 p2_pow7(u64 x) { u64 x2 = w_mul(x, x), x4 = w_mul(x2, x2); return w_mul(w_mul(x2, x), x4); }
 // p3 MDSMat4 = circ(2,3,1,1) on each half, then state[i] += column sums: out[i] = 2 n[i] + n[i ^ 4]
@@ -95,9 +100,9 @@ __device__ __forceinline__ void p2_permute(u64 (&s)[8]) {      // weak in, weak 
 // multiply-add); y itself and the seven multiply-adds of the other words sit in the shadow of the next round's chain.  Two extra
 // multiplications per round, exact arithmetic, same digest.
 __device__ __forceinline__ u64 w_mul_addu(u64 a, u64 b, u64 c) {                  // a * b + c -> weak (a, b, c any u64)
-    u64 lo = a * b, hi = __umul64hi(a, b);
+    u64 lo, hi; gl_mul128(a, b, lo, hi);
     asm("{\n\tadd.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, 0;\n\t}" : "+l"(lo), "+l"(hi) : "l"(c));
-    return gl_reduce128_weak(lo, hi);
+    return w_red(lo, hi);
 }
 __device__ __forceinline__ void p2_permute_lat(u64 (&s)[8]) {  // weak in, weak out
     p2_mds_light(s);

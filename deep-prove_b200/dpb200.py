@@ -17,7 +17,7 @@ DP_OK, DP_ERR_INVALID, DP_ERR_CUDA, DP_ERR_NO_DEVICE, DP_ERR_STATE, DP_ERR_UNSUP
 # every symbol include/deepprove_b200.h declares (tests check the .so exports each one)
 ABI_SYMBOLS = [
     "dp_init", "dp_shutdown", "dp_device_count", "dp_last_error", "dp_version", "dp_set_stream", "dp_synchronize",
-    "dp_kernel_launches", "dp_profile_enable", "dp_profile_reset", "dp_profile_read", "dp_profile_read_ex", "dp_profile_flush",
+    "dp_kernel_launches", "dp_set_wait_mode", "dp_get_wait_mode", "dp_profile_enable", "dp_profile_reset", "dp_profile_read", "dp_profile_read_ex", "dp_profile_flush",
     "dp_mle_upload", "dp_mle_wrap_device", "dp_mle_clone", "dp_mle_download", "dp_mle_info", "dp_mle_device_ptr",
     "dp_mle_free", "dp_mle_fix_high", "dp_mle_fix_high_new", "dp_mle_fix_low", "dp_mle_evaluate", "dp_mle_evaluate_many", "dp_eq_build",
     "dp_sc_create", "dp_sc_round", "dp_sc_finish", "dp_sc_destroy", "dp_sc_last_round_bytes", "dp_sc_current_mle", "dp_sc_set_resident_tail",

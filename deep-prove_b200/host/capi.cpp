@@ -310,6 +310,41 @@ extern "C" int dph_sumcheck_prove_sharded(uint32_t world, uint32_t rank, dp_mle 
     DPH_CATCH
 }
 
+// Basefold commit + open of ONE polynomial sharded over `world` ranks (every rank passes the whole polynomial, resident on its
+// GPU).  Exchange as in dph_sumcheck_prove_sharded.  out = the flat proof image of dph_pcs_open (identical on every rank and
+// identical to the unsharded proof), out_root = the commitment root.  `times_ms` (optional, 2 doubles): commit / open wall time.
+extern "C" int dph_pcs_open_sharded(uint32_t world, uint32_t rank, dp_mle *poly, uint32_t full_log, const uint64_t *point, const char *label,
+                                    void *shm_region, uint64_t *shm_seq, CallbackExchange::Fn cb, void *user,
+                                    uint64_t *out, uint64_t cap, uint64_t *out_len, uint64_t *out_root, double *times_ms) {
+    DPH_TRY
+    uint64_t len; int ext; uint32_t nv; check(dp_mle_info(poly, &len, &ext, &nv));
+    DeviceMle m = DeviceMle::wrap_device(dp_mle_device_ptr(poly), len, ext);
+    BasefoldProverParams pp; pp.full_message_size_log = full_log;
+    ExtVec pt; for (uint32_t i = 0; i < nv; i++) pt.push_back(Ext(point[2 * i], point[2 * i + 1]));
+    DynTranscript t(label);
+    auto run = [&](Exchange &ex) {
+        auto t0 = std::chrono::steady_clock::now();
+        auto comm = Basefold::commit_sharded(pp, m, ex);
+        auto t1 = std::chrono::steady_clock::now();
+        if (out_root) memcpy(out_root, comm.root.v, 32);
+        BasefoldProof pr = Basefold::open_sharded(pp, comm, pt, t, ex);
+        auto t2 = std::chrono::steady_clock::now();
+        if (times_ms) { times_ms[0] = std::chrono::duration<double, std::milli>(t1 - t0).count(); times_ms[1] = std::chrono::duration<double, std::milli>(t2 - t1).count(); }
+        return pr.flatten();
+    };
+    std::vector<uint64_t> f;
+    if (shm_region) {
+        ShmExchange ex(shm_region, world, rank); if (shm_seq) ex.seq = *shm_seq;
+        try { f = run(ex); } catch (...) { ex.poison(); if (shm_seq) *shm_seq = ex.seq; throw; }
+        if (shm_seq) *shm_seq = ex.seq;
+    } else { if (!cb && world > 1) throw Error(DP_ERR_INVALID, "dph_pcs_open_sharded: no exchange given"); CallbackExchange ex(cb, user, world, rank); f = run(ex); }
+    *out_len = f.size();
+    if (f.size() > cap) { g_herr = "dph_pcs_open_sharded: output buffer too small"; return 2; }
+    memcpy(out, f.data(), 8 * f.size());
+    return 0;
+    DPH_CATCH
+}
+
 // prove_batch_polys over T contiguous slices of the caller's device MLEs (views, no copies)
 extern "C" int dph_sumcheck_prove_batch_polys(uint32_t T, dp_mle *const *mles, uint32_t n_mles, const dp_sc_product *products, uint32_t n_products,
                                               uint32_t max_nv, const char *label, uint64_t *out_point, uint64_t *out_msgs, uint64_t *out_final) {

@@ -123,6 +123,26 @@ class Basefold {
     }
     template <class T> static void write_commitment(const Digest &root, T &t) { for (int i = 0; i < 4; i++) t.append_field_element(root.v[i]); }
 
+    // Basefold::commit of one polynomial sharded over the ranks of `ex` (every rank holds the polynomial; csrc/basefold.cu
+    // dp_pcs_commit_shard): the one exchange is the all-gather of the 32-byte subtree roots.  Same root as commit().
+    static BasefoldCommitmentWithWitness commit_sharded(const BasefoldProverParams &pp, const DeviceMle &poly, Exchange &ex) {
+        dp_pcs_comm *h; check(dp_pcs_commit_shard(poly.handle(), pp.full_message_size_log, (uint32_t)ex.rank, (uint32_t)ex.world, &h));
+        BasefoldCommitmentWithWitness c(h);      // c.root = this rank's subtree root for now
+        std::vector<u64> all(4 * ex.world);
+        ex.allgather(c.root.v, 4, all.data());
+        check(dp_pcs_comm_set_shard_roots(h, all.data(), c.root.v));
+        return c;
+    }
+    // Basefold::open of a sharded commitment: the proof of open() on the unsharded polynomial, identical on every rank
+    template <class T>
+    static BasefoldProof open_sharded(const BasefoldProverParams &pp, const BasefoldCommitmentWithWitness &comm, const ExtVec &point, T &transcript, Exchange &ex) {
+        (void)pp;
+        BasefoldProof pr;
+        dp_pcs_comm *cs[1] = {comm.handle()};
+        run_commit_phase(cs, nullptr, 1, point, comm.num_vars, transcript, pr, /*batch=*/false, {comm.codeword_size()}, {comm.is_base}, &ex);
+        return pr;
+    }
+
     // Basefold::open (basefold.rs:466-539)
     template <class T>
     static BasefoldProof open(const BasefoldProverParams &pp, const DeviceMle &poly, const BasefoldCommitmentWithWitness &comm, const ExtVec &point, T &transcript) {
@@ -234,8 +254,11 @@ class Basefold {
 
   private:
     template <class T>
+    // `ex` != null (sharded opening, one commitment from dp_pcs_commit_shard per rank): the device calls return this rank's partial
+    // messages / subtree roots / query rows; every rank combines them through `ex` and runs the same transcript, so all ranks end
+    // with the identical proof -- the proof of the unsharded polynomial.
     static void run_commit_phase(dp_pcs_comm *const *cs, const ExtVec *coeffs, uint32_t n, const ExtVec &point, uint32_t num_vars, T &transcript,
-                                 BasefoldProof &pr, bool batch, const std::vector<u64> &cw_sizes, const std::vector<bool> &is_base) {
+                                 BasefoldProof &pr, bool batch, const std::vector<u64> &cw_sizes, const std::vector<bool> &is_base, Exchange *ex = nullptr) {
         if (point.size() != num_vars) throw Error(DP_ERR_INVALID, "open: point length does not match num_vars");
         auto pf = flatten(point);
         std::vector<u64> cf; if (coeffs) cf = flatten(*coeffs);
@@ -243,6 +266,11 @@ class Basefold {
         check(dp_pcs_open_begin(cs, coeffs ? cf.data() : nullptr, n, pf.data(), num_vars, &o, m));
         std::shared_ptr<dp_pcs_open> guard(o, [](dp_pcs_open *p) { dp_pcs_open_free(p); });
         uint32_t num_rounds = num_vars - RS_BASECODE_MSG_SIZE_LOG;
+        const size_t W = ex ? ex->world : 1;
+        auto sum_msgs = [&](const std::vector<u64> &all, size_t stride, u64 *out6) {     // add the ranks' coefficient triples mod p
+            for (int k = 0; k < 3; k++) { Ext s = Ext::zero(); for (size_t g = 0; g < W; g++) s += Ext(all[g * stride + 2 * k], all[g * stride + 2 * k + 1]); out6[2 * k] = s.c0; out6[2 * k + 1] = s.c1; }
+        };
+        if (ex) { std::vector<u64> all(6 * W); ex->allgather(m, 6, all.data()); sum_msgs(all, 6, m); }
         ExtVec last = {Ext(m[0], m[1]), Ext(m[2], m[3]), Ext(m[4], m[5])};
         for (uint32_t i = 0; i < num_rounds; i++) {
             transcript.append_field_element_exts(last);
@@ -250,6 +278,13 @@ class Basefold {
             Ext ch = transcript.get_and_append_challenge("commit round");
             u64 c[2] = {ch.c0, ch.c1}, nm[6]; Digest root; int is_last = 0;
             check(dp_pcs_open_round(o, c, nm, root.v, &is_last));
+            if (ex && !is_last) {   // partial message + subtree root of every rank -> the message and the oracle's root
+                u64 send[10]; memcpy(send, nm, 48); memcpy(send + 6, root.v, 32);
+                std::vector<u64> all(10 * W); ex->allgather(send, 10, all.data());
+                sum_msgs(all, 10, nm);
+                std::vector<u64> roots(4 * W); for (size_t g = 0; g < W; g++) memcpy(&roots[4 * g], &all[10 * g + 6], 32);
+                check(dp_pcs_open_set_shard_roots(o, roots.data(), root.v));
+            }
             if (!is_last) {
                 last = {Ext(nm[0], nm[1]), Ext(nm[2], nm[3]), Ext(nm[4], nm[5])};
                 for (int k = 0; k < 4; k++) transcript.append_field_element(root.v[k]);    // digest_to_transcript
@@ -257,6 +292,11 @@ class Basefold {
             } else {
                 std::vector<u64> fm(2ULL << RS_BASECODE_MSG_SIZE_LOG);
                 check(dp_pcs_open_final_message(o, fm.data()));
+                if (ex) {   // the ranks' slices of the bit-reversed message, rank-major, then un-bit-reverse (commit_phase.rs:132-146)
+                    const size_t per = fm.size() / W;
+                    std::vector<u64> all(fm.size()); ex->allgather(fm.data(), per, all.data());
+                    for (u64 k = 0; k < (1ULL << RS_BASECODE_MSG_SIZE_LOG); k++) { u64 j = 0; for (uint32_t b = 0; b < RS_BASECODE_MSG_SIZE_LOG; b++) if (k >> b & 1) j |= 1ULL << (RS_BASECODE_MSG_SIZE_LOG - 1 - b); fm[2 * j] = all[2 * k]; fm[2 * j + 1] = all[2 * k + 1]; }
+                }
                 for (size_t k = 0; k < fm.size() / 2; k++) pr.final_message.push_back(Ext(fm[2 * k], fm[2 * k + 1]));
                 transcript.append_field_element_exts(pr.final_message);
             }
@@ -268,6 +308,10 @@ class Basefold {
         u64 words = dp_pcs_open_query_words(o);
         std::vector<u64> buf(words * xs.size());
         check(dp_pcs_open_query(o, xs.data(), (uint32_t)xs.size(), buf.data()));
+        if (ex) {   // every row is filled by the one rank that owns its leaf pair: the word-wise sum of the ranks' buffers is the full gather
+            std::vector<u64> all(buf.size() * W); ex->allgather(buf.data(), buf.size(), all.data());
+            for (size_t i = 0; i < buf.size(); i++) { u64 s = 0; for (size_t g = 0; g < W; g++) s += all[g * buf.size() + i]; buf[i] = s; }
+        }
         uint32_t lgN = num_vars + RS_RATE_LOG;
         for (size_t q = 0; q < xs.size(); q++) {
             const u64 *p = buf.data() + q * words;

@@ -65,7 +65,7 @@ struct Exchange {
 // shortest path: ~1 us per exchange instead of a device collective's launch + copy-back.  Slots are double-buffered
 // by sequence parity; a slot is rewritten only two exchanges later, which every reader has passed by then.
 struct ShmMailbox {
-    static constexpr size_t MAX_WORLD = 16, PAYLOAD = 62;
+    static constexpr size_t MAX_WORLD = 16, PAYLOAD = 2046;     // 16 KB slots: round messages use a few words, the sharded Basefold query rows ~2 MB in ~120 exchanges
     struct alignas(64) Slot { volatile u64 seq; u64 n; u64 payload[PAYLOAD]; };
     Slot slots[MAX_WORLD][2];
 };

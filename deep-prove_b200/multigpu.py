@@ -215,3 +215,56 @@ def prove_sharded_native(local_mles, products, nv_total, rank, world, mailbox=No
                                            C.byref(mailbox.seq) if mailbox is not None else None, cb, None,
                                            point.ctypes.data, msgs.ctypes.data, fin.ctypes.data))
     return point, msgs, fin
+
+
+# ---- Basefold commit + open of ONE polynomial sharded over the ranks (BASELINE configs[3]: 2^24 evaluations, 1 vs 8 GPUs) --------
+class LocalMailbox:
+    """The ShmExchange mailbox in plain process memory: `world` threads of ONE process (each with its own library context on the
+    same GPU) can play the ranks -- how the single-GPU tests exercise the sharded protocol end to end."""
+
+    def __init__(self):
+        import ctypes as C
+        import dpb200 as dp
+        H = dp.host()
+        H.dph_shm_mailbox_bytes.restype = C.c_uint64
+        self.buf = (C.c_char * int(H.dph_shm_mailbox_bytes()))()
+        self.addr = C.addressof(self.buf)
+
+    def for_rank(self):
+        import ctypes as C
+
+        class _View:
+            pass
+        v = _View(); v.addr = self.addr; v.seq = C.c_uint64(0)
+        return v
+
+
+def basefold_commit_open_sharded(mle, full_log, point, rank, world, mailbox=None, allgather=None, label=b"m2vec", cap=1 << 24):
+    """Basefold::commit_sharded + open_sharded of the C++ host mirror (host/mpcs.hpp): `mle` is the WHOLE polynomial resident on
+    this rank's GPU; this rank keeps the slice [rank/world, (rank+1)/world) of the bit-reversed evaluations, codeword, oracles and
+    Merkle trees.  Exchange: `mailbox` (ShmMailbox / LocalMailbox view) or `allgather` (callable(words) -> [world, n]).
+    Returns (root[4], flat proof (same image as dpb200.pcs_open), (commit_ms, open_ms)) -- identical on every rank."""
+    import ctypes as C
+    import dpb200 as dp
+    dp._pcs_setup()
+    H = dp.host()
+    CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64))
+    H.dph_pcs_open_sharded.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_uint64), CB, C.c_void_p,
+                                       C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
+    p = np.ascontiguousarray(point, dtype=np.uint64).reshape(-1)
+    out = np.zeros(cap, dtype=np.uint64); n = C.c_uint64(); root = np.zeros(4, dtype=np.uint64); times = np.zeros(2, dtype=np.float64)
+
+    def cb_impl(user, send, n_words, recv):
+        try:
+            w = np.ctypeslib.as_array(send, shape=(n_words,)).copy()
+            got = np.ascontiguousarray(allgather(w), dtype=np.uint64).reshape(-1)
+            C.memmove(recv, got.ctypes.data, 8 * got.size)
+            return 0
+        except Exception:
+            return 1
+    cb = CB(cb_impl) if (mailbox is None and allgather is not None) else CB()
+    rc = H.dph_pcs_open_sharded(world, rank, mle.h, full_log, p.ctypes.data, label,
+                                C.c_void_p(mailbox.addr) if mailbox is not None else None, C.byref(mailbox.seq) if mailbox is not None else None, cb, None,
+                                out.ctypes.data, cap, C.byref(n), root.ctypes.data, times.ctypes.data)
+    dp.hcheck(rc)
+    return root, out[: n.value].copy(), (float(times[0]), float(times[1]))

@@ -212,6 +212,23 @@ uint64_t dp_pcs_open_query_words(const dp_pcs_open *o);
 int dp_pcs_open_query(dp_pcs_open *o, const uint64_t *x_indices, uint32_t n, uint64_t *out);
 int dp_pcs_open_free(dp_pcs_open *o);
 
+/* ---- ONE polynomial sharded over the GPUs of a node (BASELINE configs[3]; one process per GPU) ------------------
+ * The reference has no counterpart (it is single-host, rayon-parallel); the split follows its data layout: rank g of world = 2^k
+ * owns the contiguous slice [g L/world, (g+1) L/world) of every bit-reversed table of length L (evaluations, codeword, the folded
+ * oracles), so the folds (adjacent pairs), the Basefold-internal sumcheck (LSB-first) and the Merkle subtrees are local, and the
+ * per-round exchange is one all-gather of a partial 3-coefficient message plus a 32-byte subtree root.  The proof is bit-identical
+ * to the unsharded one.  Orchestration: deep-prove_b200/multigpu.py (basefold_commit_open_sharded). */
+/* every rank passes the whole polynomial; the handle keeps this rank's slices; root (dp_pcs_comm_shard_info) = SUBTREE root */
+int dp_pcs_commit_shard(const dp_mle *poly, uint32_t full_message_size_log, uint32_t rank, uint32_t world, dp_pcs_comm **out);
+int dp_pcs_comm_shard_info(const dp_pcs_comm *c, uint32_t *rank, uint32_t *world, uint64_t local_root[4]);
+/* roots: world x 4 words rank-major (all-gathered subtree roots) -> the root of the whole tree (== dp_pcs_commit's) */
+int dp_pcs_comm_set_shard_roots(dp_pcs_comm *c, const uint64_t *roots, uint64_t out_root[4]);
+/* dp_pcs_open_begin / dp_pcs_open_round on a sharded commitment return PARTIAL messages (add the ranks' coefficient triples
+ * mod p) and SUBTREE roots; after each round that returned a root, hand the all-gathered roots back with this call to obtain the
+ * oracle's root.  dp_pcs_open_final_message returns this rank's (2^7 / world) entries of the bit-reversed final message;
+ * dp_pcs_open_query fills the rows of the queries whose leaf pair this rank owns and zeroes the rest (sum the ranks' buffers). */
+int dp_pcs_open_set_shard_roots(dp_pcs_open *o, const uint64_t *roots, uint64_t out_root[4]);
+
 /* ---- quantised inference + lookup-witness generation on the device ---------------------------------
  * Replaces the host loops of Dense::op (zkml/src/layers/dense.rs), Requant::op / gen_lookup_witness
  * (layers/requant.rs:208-330), Activation::gen_lookup_witness (layers/activation.rs:238-323), Maxpool2D::op + compute_polys

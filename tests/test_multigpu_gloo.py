@@ -122,7 +122,7 @@ H = dp.host()
 H.dph_shm_allgather.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64, C.c_void_p]
 ok = True
 for it in range(2000):
-    n = [8, 1, 62, 63, 200][it %% 5]              # one slot, a full slot, and multi-chunk payloads
+    n = [8, 1, 2046, 2047, 5000][it %% 5]         # one slot, a full slot, and multi-chunk payloads (the sharded Basefold query rows)
     send = (np.arange(n, dtype=np.uint64) * np.uint64(1000003) + np.uint64(it * 17 + rank)).astype(np.uint64)
     recv = np.zeros(world * n, dtype=np.uint64)
     assert H.dph_shm_allgather(C.c_void_p(mb.addr), world, rank, C.byref(mb.seq), send.ctypes.data, n, recv.ctypes.data) == 0
@@ -146,4 +146,4 @@ def test_shared_memory_mailbox_allgather(tmp_path):
     r = _torchrun([str(w)])
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
-    assert out["ok"] is True and out["seq"] == 400 * (1 + 1 + 1 + 2 + 4)
+    assert out["ok"] is True and out["seq"] == 400 * (1 + 1 + 1 + 2 + 3)
