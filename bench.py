@@ -476,18 +476,21 @@ def cpu_arm(wl, O, steps, warm):
             "sample": wl.cpu_sample + " (C++ restatement of the reference algorithm, not the Rust reference; `cores` = hardware threads used)"}
 
 
-# ---- facts taken from the committed ncu captures (profiles/) ------------------------------------------------------
-# thread instructions per Poseidon2 permutation of the thread-per-hash level kernel: profiles/r01b_ncu_full_summary.csv
-# (3.34 G warp instructions for 2^23 permutations... = 12.7 k per compress); refreshed by tools/ncu_summary.py when a new capture lands
-P2_INSTR_PER_PERM = 6400.0
+# ---- facts taken from the committed ncu captures (profiles/ncu_facts.json, written next to the capture summaries) ----
+# The Poseidon2 kernels are bound by the FMA-heavy pipe that executes the 32 x 32 -> 64-bit multiplies (IMAD.WIDE) of the Goldilocks
+# products: ncu (profiles/r02d_ncu_full_k_merkle_up.csv) shows sm__pipe_fmaheavy_cycles_active = 90.65 % at 1.69 Gperm/s, i.e. a
+# ceiling of 1.865 Gperm/s per B200 at 1965 MHz for this formulation (12.85 k thread instructions per permutation).
+P2_INSTR_PER_PERM = 12850.0
+P2_CEILING_GPS, P2_CEILING_MHZ = 1.865, 1965.0
+P2_CEILING_SOURCE = "profiles/r02d_ncu_full_k_merkle_up.csv"
 NCU_TRAFFIC = {
     ("sumcheck20", "k_sc_round"): (7.69e6, "profiles/r01c_sumcheck20_rounds_ncu.csv: rounds 2-11 of one nu=20 proof, mean per launch (algorithmic 6.6 MB)"),
     ("dense4m", "k_sc_round"): (7.1e4, "profiles/r01_ncu_full_summary.csv: one small round (latency-bound)"),
-    ("basefold24", "k_merkle"): (1.87e8, "profiles/r01b_ncu_full_summary.csv: k_merkle_up levels 2-3 of the 2^25-leaf tree, mean per launch (269+105 MB and 134+37 MB; algorithmic 3 x 32 B x hashes = 403 / 201 MB incl. L2-absorbed writes)"),
 }
-try:   # newer captures override the round-1 numbers (written next to the profiles by tools/ncu_summary.py)
+try:
     _f = json.load(open(os.path.join(ROOT, "profiles", "ncu_facts.json")))
     P2_INSTR_PER_PERM = float(_f.get("p2_instr_per_perm", P2_INSTR_PER_PERM))
+    P2_CEILING_GPS = float(_f.get("p2_perm_ceiling_gps_at_1965mhz", P2_CEILING_GPS))
     for k_, v_ in _f.get("traffic", {}).items():
         NCU_TRAFFIC[tuple(k_.split("/"))] = (v_[0], v_[1])
 except Exception:
@@ -499,10 +502,11 @@ PUBLISHED = {"dense4m": 1.0 / 2.335, "cnn264k": 1.0 / 1.242}   # and "CNN 264k .
 
 def kernel_table(prof, peaks, sm_mhz, sm_count=148):
     """per-kernel rows from dp_profile_read_ex: each kernel against the bound that limits it.
-    Poseidon2 kernels: permutations/s against the INT32-issue ceiling  sm_count x 4 schedulers x 32 lanes x clock / (thread
-    instructions per permutation, from ncu); sumcheck rounds: field-ops/s and GB/s; everything else: GB/s vs measured HBM."""
-    clock = (sm_mhz or peaks.get("sm_max_mhz") or 1965.0) * 1e6
-    alu_perm_ceiling = sm_count * 4 * 32 * clock / P2_INSTR_PER_PERM
+    Poseidon2 kernels: permutations/s against the FMA-heavy-pipe ceiling measured with ncu (scaled by the SM clock and count);
+    sumcheck rounds: field-ops/s and GB/s against the measured HBM copy bandwidth; everything else: GB/s vs HBM.
+    Kernels that process a handful of elements per launch are latency chains and are labelled so (no roofline applies)."""
+    clock = (sm_mhz or peaks.get("sm_max_mhz") or 1965.0)
+    perm_ceiling = P2_CEILING_GPS * 1e9 * (clock / P2_CEILING_MHZ) * (sm_count / 148.0)
     rows = {}
     for name, (cnt, ms, by, units) in prof.items():
         sec = ms * 1e-3
@@ -511,15 +515,37 @@ def kernel_table(prof, peaks, sm_mhz, sm_count=148):
                "hbm_frac": round(by / sec / 1e9 / peaks["hbm_gbs"], 5) if sec > 0 else 0.0}
         if "poseidon2" in name:
             pps = units / sec if sec > 0 else 0.0
-            row.update({"bound": "int32-alu" if cnt and units / cnt > 20000 else "latency (dependent hash chain)",
-                        "perm_per_s": pps, "alu_ceiling_perm_per_s": alu_perm_ceiling, "alu_frac": round(pps / alu_perm_ceiling, 5)})
+            row.update({"bound": "fma-heavy pipe (IMAD.WIDE of the 64-bit field products)" if cnt and units / cnt > 60000 else "latency (dependent hash chain)",
+                        "perm_per_s": pps, "ceiling_perm_per_s": perm_ceiling, "pipe_frac": round(pps / perm_ceiling, 5)})
         elif name.startswith("k_sc_"):
             row.update({"bound": "hbm" if cnt and by / cnt > 4e6 else "latency (one round trip per Fiat-Shamir challenge)",
                         "field_ops_per_s": units / sec if sec > 0 else 0.0})
         else:
             row["bound"] = "hbm" if cnt and by / cnt > 4e6 else "latency"
         rows[name] = row
-    return rows, alu_perm_ceiling
+    return rows, perm_ceiling
+
+
+def roofline_block(wl_key, rows, ceiling, peaks, peak_kind, source):
+    """the dominant THROUGHPUT-bound kernel of a per-kernel table against its own bound (latency chains are listed, not rated)"""
+    cand = {k: r for k, r in rows.items() if not k.startswith("k_sc_res") and not r["bound"].startswith("latency")}
+    if not cand:
+        cand = {k: r for k, r in rows.items() if not k.startswith("k_sc_res")} or rows
+    name = max(cand, key=lambda k: cand[k]["ms"])
+    r = rows[name]
+    all_ms = sum(x["ms"] for k, x in rows.items() if not k.startswith("k_sc_res"))
+    traffic = NCU_TRAFFIC.get((wl_key, name.split("(")[0]))
+    if "perm_per_s" in r and not r["bound"].startswith("latency"):
+        roof = {"kernel": name, "bound": r["bound"], "achieved": r["perm_per_s"] / 1e9, "peak": ceiling / 1e9, "unit": "Gperm/s", "frac": r["pipe_frac"],
+                "peak_kind": "measured with ncu: the thread-per-hash level kernel reaches 1.69 Gperm/s at sm__pipe_fmaheavy_cycles_active = 90.65 %% (%s); scaled by SM clock" % P2_CEILING_SOURCE}
+    else:
+        roof = {"kernel": name, "bound": r["bound"], "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["hbm_frac"],
+                "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"}
+    roof.update({"hbm": {"achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["hbm_frac"]},
+                 "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
+                 "launches": r["launches"], "avg_us": r["avg_us"], "share_of_kernel_time": round(r["ms"] / all_ms, 4) if all_ms > 0 else None,
+                 "source": source})
+    return roof
 
 
 def run_gpu_workload(env, wl, K, W, full):
@@ -588,11 +614,13 @@ def run_gpu_workload(env, wl, K, W, full):
         ms_e2e, _ = timed(wl.step_e2e, K, 2)
     clocks = clk.summary()
 
-    # per-kernel leg: the SAME batch once more with per-launch CUDA events on every proving thread's stream
+    # per-kernel legs.  (1) the SAME concurrent batch once more with per-launch CUDA events on every proving thread's stream: what runs
+    # in the timed region (its per-kernel times overlap and stretch each other, so they give shares, not rates).  (2) for the
+    # batched workloads, one proof at a time: every kernel alone on the GPU -- the rates the roofline fraction is computed from.
     peaks, peak_kind = env["peaks"]
     dp.profile_reset(); dp.profile_enable(True)
     if batched:
-        wl.run_resident(min(K, 4), local_rank)
+        wl.run_resident(min(K, 2), local_rank)
     else:
         for i in range(min(K, 5)):
             if flush_buf is not None:
@@ -602,7 +630,17 @@ def run_gpu_workload(env, wl, K, W, full):
     prof = dp.profile_read(with_units=True)
     dp.profile_enable(False)
     dp.set_wait_mode(0)
-    rows, alu_ceiling = kernel_table(prof, peaks, clocks.get("sm_mhz"), env["sm_count"])
+    rows, ceiling = kernel_table(prof, peaks, clocks.get("sm_mhz"), env["sm_count"])
+    rows_alone = None
+    if batched:
+        dp.profile_reset(); dp.profile_enable(True)
+        for i in range(3):
+            if flush_buf is not None:
+                flush_buf.zero_()
+            wl.step_resident(i)
+        torch.cuda.synchronize()
+        rows_alone, _ = kernel_table(dp.profile_read(with_units=True), peaks, clocks.get("sm_mhz"), env["sm_count"])
+        dp.profile_enable(False)
 
     ups = getattr(wl, "units_per_step", 1)
     v = whole_job_value(K * ups, world, ms)
@@ -615,28 +653,24 @@ def run_gpu_workload(env, wl, K, W, full):
         res["hbm_frac_whole_proof"] = wl.alg_bytes * v / world / 1e9 / peaks["hbm_gbs"]
     if hasattr(wl, "permutations"):
         res["poseidon2_perm_per_s"] = wl.permutations * v / world
-        res["alu_frac_whole_step"] = wl.permutations * v / world / alu_ceiling
+        res["pipe_frac_whole_step"] = wl.permutations * v / world / ceiling
 
     roof = None
     if rows:
-        # the resident tail spans many rounds and its event time includes the host's Fiat-Shamir between them: listed, but never
-        # the "dominant kernel"
-        cand = {k: r for k, r in rows.items() if not k.startswith("k_sc_res")} or rows
-        name = max(cand, key=lambda k: cand[k]["ms"])
-        r = rows[name]
-        all_ms = sum(x["ms"] for x in cand.values())
-        traffic = NCU_TRAFFIC.get((wl.key, name.split("(")[0]))
-        if "perm_per_s" in r and r["bound"] == "int32-alu":
-            roof = {"kernel": name, "bound": "int32-alu", "achieved": r["perm_per_s"] / 1e9, "peak": alu_ceiling / 1e9, "unit": "Gperm/s", "frac": r["alu_frac"],
-                    "peak_kind": "derived: %d SMs x 4 schedulers x 32 lanes x %.0f MHz / %.0f thread-instructions per permutation (ncu)" % (env["sm_count"], clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0), P2_INSTR_PER_PERM)}
+        if batched and rows_alone:
+            roof = roofline_block(wl.key, rows_alone, ceiling, peaks, peak_kind, "profiled pass of single proofs (each kernel alone on the GPU, per-launch CUDA events on the launch stream)")
+            # the whole timed region against the same ceiling: Poseidon2 permutations of all Merkle kernels per second of the batch
+            perms = sum(u for n_, (c_, m_, b_, u) in prof.items() if "poseidon2" in n_)
+            proofs_profiled = min(K, 2) * ups
+            if proofs_profiled:
+                pps = perms / proofs_profiled * v / world
+                roof["whole_step"] = {"poseidon2_perm_per_proof": perms / proofs_profiled, "poseidon2_perm_per_s": pps, "frac_of_pipe_ceiling": round(pps / ceiling, 4),
+                                      "note": "all Merkle kernels of the concurrent timed region: permutations per proof x proofs/s, against the same fma-heavy-pipe ceiling"}
+            roof["kernels_concurrent_batch"] = dict(sorted(rows.items(), key=lambda kv: -kv[1]["ms"]))
+            roof["kernels"] = dict(sorted(rows_alone.items(), key=lambda kv: -kv[1]["ms"]))
         else:
-            roof = {"kernel": name, "bound": r["bound"], "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["hbm_frac"],
-                    "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"}
-        roof.update({"hbm": {"achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["hbm_frac"]},
-                     "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
-                     "launches": r["launches"], "avg_us": r["avg_us"], "share_of_kernel_time": round(r["ms"] / all_ms, 4) if all_ms > 0 else None,
-                     "source": "profiled pass of the same %s (per-launch CUDA events on each proving thread's stream)" % ("concurrent batch" if batched else "steps"),
-                     "kernels": dict(sorted(rows.items(), key=lambda kv: -kv[1]["ms"]))})
+            roof = roofline_block(wl.key, rows, ceiling, peaks, peak_kind, "profiled pass of the same steps (per-launch CUDA events on the launch stream)")
+            roof["kernels"] = dict(sorted(rows.items(), key=lambda kv: -kv[1]["ms"]))
     res["roofline"] = roof
 
     res["cpu_baseline"], res["parity_checked"] = None, None
@@ -812,7 +846,8 @@ def main():
         r2 = run_gpu_workload(env, w2, k2, 3, False)
         r2.pop("clocks", None)
         if r2.get("roofline"):
-            r2["roofline"].pop("kernels", None)     # the per-kernel table is printed for the headline workload only
+            r2["roofline"].pop("kernels", None)     # the per-kernel tables are printed for the headline workload only
+            r2["roofline"].pop("kernels_concurrent_batch", None)
         extra[k] = r2
         del w2
 
@@ -844,7 +879,7 @@ def main():
             "alg_GBps_whole_step": head["alg_GBps_whole_step"],
             "workloads": extra, "sharded": sharded,
         }
-        for k in ("field_ops_per_s", "hbm_frac_whole_proof", "poseidon2_perm_per_s", "alu_frac_whole_step", "parity_error"):
+        for k in ("field_ops_per_s", "hbm_frac_whole_proof", "poseidon2_perm_per_s", "pipe_frac_whole_step", "parity_error"):
             if k in head:
                 out[k] = head[k]
         print(json.dumps(out))
