@@ -287,15 +287,17 @@ __device__ __forceinline__ void mk_publish_root(const RootOut &rt, const u64 *ro
     if (rt.flag) { __threadfence_system(); *(volatile u64 *)rt.flag = rt.seq; }
 }
 template <bool EXT, bool FROM_LEAVES>
-__global__ void __launch_bounds__(256) k_merkle_small(const void *src, u32 first_level, u32 lg, u64 nl_first, u64 *levels, LvlOff lo, u32 *ticket, RootOut rt) {
+__global__ void __launch_bounds__(256) k_merkle_small(const void *src, u32 first_level, u32 lg, u64 nl_first, u64 *levels, LvlOff lo, u32 *ticket, RootOut rt, u32 sub_max, u32 tph_min) {
+    // (sub_max, tph_min) = (256, 64) with many proofs in flight (see above); (32, never) for a single proof: 64 blocks x one 8-lane pass
+    // per level is the shortest chain (~20 us per level against ~40 us for a thread per hash) and nothing else wants the issue slots
     const int lane8 = threadIdx.x & 7; const u32 grp = threadIdx.x >> 3;
-    const u32 sub = (u32)(nl_first < MK_SUB ? nl_first : MK_SUB);
+    const u32 sub = (u32)(nl_first < sub_max ? nl_first : sub_max);
     u32 l = first_level;
     for (u32 k = 0; (sub >> k) >= 1 && l < lg; k++, l++) {
         const u32 cnt = sub >> k; const u64 base = (u64)blockIdx.x * cnt;
         u64 *out = levels + 4 * lo.off[l];
         const u64 *prev = k == 0 ? (const u64 *)src : levels + 4 * lo.off[l - 1];
-        if (cnt >= 64) {                                   // one thread per hash
+        if (cnt >= tph_min) {                              // one thread per hash
             if (threadIdx.x < cnt) {
                 const u64 i = base + threadIdx.x;
                 u64 x[4], y[4], o[4];
@@ -310,8 +312,9 @@ __global__ void __launch_bounds__(256) k_merkle_small(const void *src, u32 first
                 *reinterpret_cast<ulonglong2 *>(out + 4 * i) = make_ulonglong2(o[0], o[1]);
                 *reinterpret_cast<ulonglong2 *>(out + 4 * i + 2) = make_ulonglong2(o[2], o[3]);
             }
-        } else if ((grp & ~3u) < cnt) {                    // 8 lanes per hash; warp-uniform (a warp holds 4 lane groups): idle warps skip the permutations
-            const bool live = grp < cnt; const u64 i = base + grp;
+        } else for (u32 b = 0; b < cnt; b += 32) {         // 8 lanes per hash, 32 hashes per pass
+            if (b + (grp & ~3u) >= cnt) continue;          // warp-uniform (a warp holds 4 lane groups): idle warps skip the permutations
+            const bool live = b + grp < cnt; const u64 i = base + b + grp;
             u64 xw = 0, yw = 0;
             if (live && lane8 < 4) {
                 if (k == 0 && FROM_LEAVES) { xw = leaf_pair_word<EXT>(src, 2 * i, lane8); yw = leaf_pair_word<EXT>(src, 2 * i + 1, lane8); }
@@ -495,12 +498,14 @@ static int tree_build(DevTree &t, const void *leaves, bool ext, u64 n, const u64
             const u64 in_bytes = from_leaves ? nl * (ext ? 64 : 32) : nl * 64;
             if (nl <= MK_SMALL && t.lg < 36) {   // this and every remaining level in one launch
                 DpProfScope prof("k_merkle_small(poseidon2 compress, all remaining levels)", in_bytes + (2 * nl - 1) * 32 * 2, 2 * (2 * nl - 1));
-                const unsigned g = (unsigned)((nl + MK_SUB - 1) / MK_SUB);
+                const bool many = dp_wait_mode() == DP_WAIT_BLOCK;     // the throughput configuration (many proofs in flight)
+                const u32 sub_max = many ? MK_SUB : 32, tph_min = many ? 64 : 0xFFFFFFFFu;
+                const unsigned g = (unsigned)((nl + sub_max - 1) / sub_max);
                 u32 *ticket = nullptr; if (int e = mk_ticket(&ticket)) return e;
                 const void *src = l == 1 ? (lvl0 ? (const void *)lvl0 : leaves) : (const void *)(t.levels + 4 * t.lvl_off[l - 1]);
                 RootOut ro = rt ? *rt : RootOut{nullptr, nullptr, 0};
-                if (from_leaves) { if (ext) k_merkle_small<true, true><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket, ro); else k_merkle_small<false, true><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket, ro); }
-                else k_merkle_small<false, false><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket, ro);
+                if (from_leaves) { if (ext) k_merkle_small<true, true><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket, ro, sub_max, tph_min); else k_merkle_small<false, true><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket, ro, sub_max, tph_min); }
+                else k_merkle_small<false, false><<<g, 256, 0, c.stream>>>(src, l, t.lg, nl, t.levels, lo_all, ticket, ro, sub_max, tph_min);
                 DP_LAUNCHED();
                 if (rt && rt_done) *rt_done = true;
                 break;

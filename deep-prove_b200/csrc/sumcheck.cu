@@ -460,27 +460,10 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
     gle r = r0;
     long long *const dbg = cfg->dbg;
 #define RES_MARK(ph) do { if (dbg && rank == 0 && threadIdx.x == 0) dbg[k * 8 + (ph)] = clock64(); } while (0)
-    for (u32 k = 0; k < nr; k++) {
-        const u64 seq = seq0 + k;
-        RES_MARK(0);
-        if (k > 0) {   // wait for the host's challenge for this round
-            if (rank == 0 && threadIdx.x == 0) {
-                long long t0 = clock64(); u64 v, status = 0;
-                while ((v = chal[0]) != seq) {
-                    if (v == SC_TAIL_ABORT) { status = 1; break; }
-                    if (clock64() - t0 > SC_RES_TIMEOUT) { status = 2; break; }
-                }
-                u64 c0 = 0, c1 = 0;
-                if (!status) { __threadfence_system(); c0 = chal[1]; c1 = chal[2]; }
-                __stcg(xctl + 1, c0); __stcg(xctl + 2, c1); __stcg(xctl, status);
-            }
-            cl_sync();
-            const u64 status = __ldcg(xctl);
-            if (status) { if (rank == 0 && threadIdx.x == 0 && status == 2) { __threadfence_system(); *flag = SC_TAIL_FAILED; } return; }   // uniform over the cluster
-            r = e_make(__ldcg(xctl + 1), __ldcg(xctl + 2));
-        }
-        RES_MARK(1);
-        const bool fold = (k > 0) || cfg->first_has_challenge;
+    // The descriptors of a round depend on the fold bookkeeping only, never on the challenge VALUE: they are rebuilt right after a
+    // round's message has been signalled, i.e. in the shadow of the host's Fiat-Shamir (phase clocks: ~2.2 us per round that used
+    // to sit between the challenge's arrival and the first load).
+    auto build_descs = [&](const bool fold) {
         for (u32 i = threadIdx.x; i < nm; i += blockDim.x) {
             bool f = fold && sm[i].len > 1;
             sfold[i] = f;
@@ -506,6 +489,28 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
             pd.d = pr.n_idx; pd.allbase = allbase; pd.konst = newlen == 1; pd.npairs = newlen >> 1;
         }
         __syncthreads();
+    };
+    build_descs(cfg->first_has_challenge != 0);
+    for (u32 k = 0; k < nr; k++) {
+        const u64 seq = seq0 + k;
+        RES_MARK(0);
+        if (k > 0) {   // wait for the host's challenge for this round
+            if (rank == 0 && threadIdx.x == 0) {
+                long long t0 = clock64(); u64 v, status = 0;
+                while ((v = chal[0]) != seq) {
+                    if (v == SC_TAIL_ABORT) { status = 1; break; }
+                    if (clock64() - t0 > SC_RES_TIMEOUT) { status = 2; break; }
+                }
+                u64 c0 = 0, c1 = 0;
+                if (!status) { __threadfence_system(); c0 = chal[1]; c1 = chal[2]; }
+                __stcg(xctl + 1, c0); __stcg(xctl + 2, c1); __stcg(xctl, status);
+            }
+            cl_sync();
+            const u64 status = __ldcg(xctl);
+            if (status) { if (rank == 0 && threadIdx.x == 0 && status == 2) { __threadfence_system(); *flag = SC_TAIL_FAILED; } return; }   // uniform over the cluster
+            r = e_make(__ldcg(xctl + 1), __ldcg(xctl + 2));
+        }
+        RES_MARK(1);
         RES_MARK(2);
         // work: slot (p, s) = sub-slice s of product p's pairs; warp gw owns slots gw, gw + W, ...
         for (u32 slot = gw; slot < np * G; slot += W) {
@@ -534,12 +539,7 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
         RES_MARK(3);
         cl_sync();                                             // warp partials and folded tables of every CTA are visible
         RES_MARK(4);
-        for (u32 i = threadIdx.x; i < nm; i += blockDim.x) if (sfold[i]) {
-            TMle &m = sm[i];
-            m.cur = sdst[i]; m.where = (sdst[i] == m.work) ? 1 : 2; m.len >>= 1; m.is_ext = 1;
-        }
-        __syncthreads();
-        if (rank == 0) {
+        if (rank == 0) {                                       // the message first: it is what the host is waiting for
             for (u32 x = threadIdx.x; x < np * SC_NACC; x += blockDim.x) {
                 const u32 p = x / SC_NACC, t = x % SC_NACC;
                 if (t > spd[p].d) continue;
@@ -547,6 +547,13 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
                 for (u32 s = 0; s < G; s++) { ulonglong2 q = __ldcg(reinterpret_cast<const ulonglong2 *>(xpart + ((u64)p * G + s) * SC_NACC + t)); v = e_add(v, e_make(q.x, q.y)); }
                 st_e(out + (u64)p * SC_NACC + t, v);
             }
+        }
+        for (u32 i = threadIdx.x; i < nm; i += blockDim.x) if (sfold[i]) {     // fold bookkeeping (every CTA keeps its own copy)
+            TMle &m = sm[i];
+            m.cur = sdst[i]; m.where = (sdst[i] == m.work) ? 1 : 2; m.len >>= 1; m.is_ext = 1;
+        }
+        __syncthreads();
+        if (rank == 0) {
             if (k == nr - 1) {   // last round: hand the (<= 2)-entry tables over with the message (k_sc_gather's job)
                 for (u32 i = threadIdx.x; i < nm; i += blockDim.x) {
                     const TMle &m = sm[i]; gle a, b;
@@ -554,12 +561,13 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
                     else { a = e_from_base(ldx_b<true>((const u64 *)m.cur)); b = m.len > 1 ? e_from_base(ldx_b<true>((const u64 *)m.cur + 1)) : a; }
                     st_e(pairs + 2 * i, a); st_e(pairs + 2 * i + 1, b);
                 }
+                __syncthreads();
             }
-            __syncthreads();
             RES_MARK(5);
             if (threadIdx.x == 0) { __threadfence_system(); *flag = seq; }
             RES_MARK(6);
         }
+        if (k + 1 < nr) build_descs(true);                     // next round's descriptors while the host hashes
         // CTAs other than 0 run ahead to the next cluster barrier; xpart is not rewritten before it (the work phase follows it)
     }
 }
