@@ -434,7 +434,10 @@ def cpu_arm(wl, O, steps, warm):
     once, each on an equal share of the host threads (the like-for-like comparison with the GPU's concurrent batch).
     Returns a dict; `value` is the better mode's units/s."""
     lib = O.lib()
-    hw = int(lib.dpo_num_threads())
+    hw_all = int(lib.dpo_num_threads())
+    # the container may be allowed fewer CPUs than the machine has hardware threads (cgroup cpu.max: 16 CPUs on the 1-GPU measurement
+    # boxes): more runnable threads than that only get throttled, so the CPU arm uses -- and reports -- what it can actually run on
+    hw = max(1, min(hw_all, int(round(cpu_budget() * max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))))))
     lib.dpo_set_threads(hw)
 
     def unit_seconds(i):
@@ -473,7 +476,8 @@ def cpu_arm(wl, O, steps, warm):
             "mode": "throughput" if (thr_v or 0.0) > lat_v else "latency",
             "latency_mode": {"value": lat_v, "sec_per_unit": tot / steps, "threads": hw},
             "throughput_mode": ({"value": thr_v, "concurrent": k, "threads_each": max(1, hw // k), "sec_per_batch": thr_wall} if thr_v else None),
-            "sample": wl.cpu_sample + " (C++ restatement of the reference algorithm, not the Rust reference; `cores` = hardware threads used)"}
+            "hardware_threads": hw_all,
+            "sample": wl.cpu_sample + " (C++ restatement of the reference algorithm, not the Rust reference; `cores` = threads used = the CPUs this container may run on: min(hardware threads, cgroup cpu.max))"}
 
 
 # ---- facts taken from the committed ncu captures (profiles/ncu_facts.json, written next to the capture summaries) ----

@@ -422,7 +422,7 @@ k_sc_lean(const ScProd *__restrict__ descs, const __grid_constant__ ScProd desc0
 // SC_RES_TIMEOUT cycles or when the host posts the abort value, and the other CTAs only ever wait on the cluster barrier.
 // Opt-in per handle (dp_sc_set_resident_tail): the caller promises not to wait on other work in the same stream between rounds.
 static constexpr u32 SC_RES_MAXM = 96, SC_RES_MAXP = 48, SC_RES_MAXCTA = 8;
-static constexpr u64 SC_RES_WORK = 16384;                    // resident once sum over products of (pairs this round) <= this
+static constexpr u64 SC_RES_WORK = 2048;                     // resident once sum over products of (pairs this round) <= this (larger rounds are faster in the multi-block kernels: profiles/r02x.log)
 static constexpr long long SC_RES_TIMEOUT = 6000000000LL;   // ~3 s at 1.9 GHz
 static constexpr u64 SC_TAIL_ABORT = ~0ULL, SC_TAIL_FAILED = ~0ULL - 1;
 struct TMle { const void *cur; gle *work; u64 len, len0; u32 is_ext, where; };
@@ -726,7 +726,8 @@ static bool sc_tail_eligible(const dp_sc *s, bool fold) {
     std::vector<char> used(s->n_mles, 0);
     for (auto &pr : s->products) for (u32 j = 0; j < pr.n_idx; j++) used[pr.idx[j]] = 1;
     for (u32 i = 0; i < s->n_mles; i++) if (!used[i] && s->mles[i].len > 1) return false;
-    return sc_round_work(s, fold) <= SC_RES_WORK;
+    static const u64 limit = [] { const char *e = getenv("DP_SC_RES_WORK"); return e ? (u64)atoll(e) : SC_RES_WORK; }();
+    return sc_round_work(s, fold) <= limit;
 }
 template <int DSEL>
 static cudaError_t sc_res_launch(u32 ncta, cudaStream_t st, const ScTail *cfg, gle r, gle *out, gle *pairs, u64 *flag, u64 *chal, u64 seq, gle *xpart, u64 *xctl) {

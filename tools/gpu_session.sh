@@ -1,4 +1,15 @@
 mkdir -p gpurun_out
-python tools/sc_rounds.py 26 1 b3 2>&1 | tail -1 > gpurun_out/r02w_sc26.log
-python tools/sc_rounds.py 24 1 e3 2>&1 | tail -1 >> gpurun_out/r02w_sc26.log
-cat gpurun_out/r02w_sc26.log
+L=gpurun_out/r02y.log; : > $L
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2 >> $L
+DP_WAIT_MODE=1 python -m pytest tests/test_zkml.py tests/test_gpu_cnn.py tests/test_gpu_mle_sumcheck.py tests/test_gpu_basefold.py -m gpu -x -q 2>&1 | tail -2 >> $L
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02y_bench_reference.json 2>> $L; echo "ref rc=$?" >> $L
+python bench.py > gpurun_out/r02y_bench_all.json 2> gpurun_out/r02y_bench_all.err; echo "bench rc=$?" >> $L
+cat $L
+python - <<'PY'
+import json
+for f in ("gpurun_out/r02y_bench_reference.json","gpurun_out/r02y_bench_all.json"):
+    d=json.loads([x for x in open(f) if x.startswith("{")][0])
+    print(f, d["value"], d.get("e2e",{}).get("value"), d.get("cpu_baseline",{}).get("cores"), d.get("cpu_baseline",{}).get("mode"), d.get("cpu_baseline",{}).get("value"))
+    for k,v in d.get("workloads",{}).items(): print("   ",k, v["value"], v.get("e2e",{}).get("value"), (v.get("cpu_baseline") or {}).get("value"))
+    if "run" in d: print("   latency", d["run"]["single_stream_latency_ms"])
+PY
