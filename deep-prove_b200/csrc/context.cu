@@ -179,7 +179,9 @@ u64 dp_wait_flag(volatile u64 *flag, u64 want, bool has_fail, u64 fail, double t
             if (const char *e = getenv("DP_WAIT_SPINNERS")) return atoi(e);
             double cpus = (double)std::thread::hardware_concurrency();
             if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) { char q[64]; double per = 0; if (fscanf(f, "%63s %lf", q, &per) == 2 && strcmp(q, "max") != 0 && per > 0) cpus = std::min(cpus, atof(q) / per); fclose(f); }
-            return std::max(0, (int)(cpus / 2) - 1);
+            // one process per GPU on a shared box (torchrun): this process's share of the CPUs, not the whole container's
+            if (const char *lw = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(lw); if (w > 1) cpus /= w; }
+            return std::max(0, (int)(cpus / 2) - 2);
         }();
         static std::atomic<int> spinners{0};
         if (spin_limit > 0 && spinners.fetch_add(1, std::memory_order_acq_rel) < spin_limit) {

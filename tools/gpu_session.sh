@@ -1,15 +1,8 @@
 mkdir -p gpurun_out
-L=gpurun_out/r02y.log; : > $L
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2 >> $L
-DP_WAIT_MODE=1 python -m pytest tests/test_zkml.py tests/test_gpu_cnn.py tests/test_gpu_mle_sumcheck.py tests/test_gpu_basefold.py -m gpu -x -q 2>&1 | tail -2 >> $L
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02y_bench_reference.json 2>> $L; echo "ref rc=$?" >> $L
-python bench.py > gpurun_out/r02y_bench_all.json 2> gpurun_out/r02y_bench_all.err; echo "bench rc=$?" >> $L
-cat $L
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 3 --warmup 3 > gpurun_out/r02z_bench_n4.json 2> gpurun_out/r02z_bench_n4.err
+echo "rc=$?"; grep -v "zkml\|^$\|\*\*\*\|OMP" gpurun_out/r02z_bench_n4.err | tail -5; cat /sys/fs/cgroup/cpu.max
 python - <<'PY'
 import json
-for f in ("gpurun_out/r02y_bench_reference.json","gpurun_out/r02y_bench_all.json"):
-    d=json.loads([x for x in open(f) if x.startswith("{")][0])
-    print(f, d["value"], d.get("e2e",{}).get("value"), d.get("cpu_baseline",{}).get("cores"), d.get("cpu_baseline",{}).get("mode"), d.get("cpu_baseline",{}).get("value"))
-    for k,v in d.get("workloads",{}).items(): print("   ",k, v["value"], v.get("e2e",{}).get("value"), (v.get("cpu_baseline") or {}).get("value"))
-    if "run" in d: print("   latency", d["run"]["single_stream_latency_ms"])
+d=json.loads([x for x in open("gpurun_out/r02z_bench_n4.json") if x.startswith("{")][0])
+print({k:d[k] for k in ("value","n_gpus","ms_per_step","e2e")}); print(d["run"]["parallelism"]); print(json.dumps(d["sharded"], indent=0)[:1500]); print({k:(v["value"], v["e2e"]["value"]) for k,v in d["workloads"].items()})
 PY
