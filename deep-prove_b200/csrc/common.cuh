@@ -48,7 +48,7 @@ struct DpProfScope {
 
 // host-side wall-clock accumulators (DP_HOST_PROF=1): where a round-granular call spends its CPU time
 struct DpHostTimer {
-    const char *name; double t0;
+    const char *name; double t0, c0;
     explicit DpHostTimer(const char *n);
     ~DpHostTimer();
 };

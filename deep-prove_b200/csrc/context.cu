@@ -98,20 +98,41 @@ static void arena_destroy() {
     g_arena.cls.clear(); g_arena.deferred.clear(); g_arena.defer = false;
 }
 
-struct PinnedBlk { void *p; size_t cap; bool used; };
-static std::vector<PinnedBlk> g_pinned;    // process-wide cache (cudaHostAlloc synchronises the device: never on the hot path)
-static std::mutex g_pinned_mu;
+// Pinned (mapped) host blocks: power-of-two size classes, a 64-byte header in front of every block holds its class, free blocks sit
+// in a PER-THREAD cache (no lock, O(1)); a process-wide pool takes the caches of threads that exit and serves cache misses before the
+// driver is asked (cudaHostAlloc costs ~ms and synchronises the device: never on the proving path once warm).  The first version
+// kept one process-wide list under a mutex and scanned it linearly on every alloc and free: with 48 proving threads and thousands
+// of blocks that was 18 ms of CPU per Dense-4M proof inside dp_sc_create / dp_sc_destroy (profiles/r03a_hostprof.log).
+static constexpr int PIN_CLASSES = 40;
+struct PinnedPool { std::mutex mu; std::vector<void *> free_[PIN_CLASSES]; };
+static PinnedPool g_pin_pool;
+struct PinnedCache {
+    std::vector<void *> free_[PIN_CLASSES];
+    ~PinnedCache() { std::lock_guard<std::mutex> lk(g_pin_pool.mu); for (int c = 0; c < PIN_CLASSES; c++) for (void *p : free_[c]) g_pin_pool.free_[c].push_back(p); }
+};
+static thread_local PinnedCache g_pin_cache;
 int dp_pinned_alloc(void **p, size_t bytes) {
-    size_t cap = 4096; while (cap < bytes) cap <<= 1;
-    std::lock_guard<std::mutex> lk(g_pinned_mu);
-    for (auto &b : g_pinned) if (!b.used && b.cap == cap) { b.used = true; *p = b.p; return DP_OK; }
-    void *q = nullptr;
-    DP_CUDA(cudaHostAlloc(&q, cap, cudaHostAllocMapped));   // device-visible: kernels read descriptors / write results in place
-    g_pinned.push_back({q, cap, true});
-    *p = q;
+    int c = 12; while (((size_t)1 << c) < bytes) c++;            // 4 KiB minimum, as before
+    if (c >= PIN_CLASSES) return dp_fail(DP_ERR_INVALID, "dp_pinned_alloc: request too large");
+    auto &mine = g_pin_cache.free_[c];
+    if (!mine.empty()) { *p = mine.back(); mine.pop_back(); return DP_OK; }
+    {
+        std::lock_guard<std::mutex> lk(g_pin_pool.mu);
+        auto &pool = g_pin_pool.free_[c];
+        if (!pool.empty()) { *p = pool.back(); pool.pop_back(); return DP_OK; }
+    }
+    char *q = nullptr;
+    DP_CUDA(cudaHostAlloc((void **)&q, ((size_t)1 << c) + 64, cudaHostAllocMapped));   // device-visible: kernels read descriptors / write results in place
+    *(int *)q = c;
+    *p = q + 64;
     return DP_OK;
 }
-void dp_pinned_free(void *p) { if (!p) return; std::lock_guard<std::mutex> lk(g_pinned_mu); for (auto &b : g_pinned) if (b.p == p) { b.used = false; return; } }
+void dp_pinned_free(void *p) {
+    if (!p) return;
+    const int c = *(const int *)((const char *)p - 64);
+    if (c < 12 || c >= PIN_CLASSES) return;      // not one of ours
+    g_pin_cache.free_[c].push_back(p);
+}
 
 #include <chrono>
 // ---- waiting without burning a core (see common.cuh) -------------------------------------------------------------------
@@ -267,12 +288,14 @@ int dp_zero_block_get(void **p) {
 void dp_zero_block_put(void *p) { if (p) g_ctx.zero_blocks.push_back(p); }
 
 static bool g_hostprof = getenv("DP_HOST_PROF") != nullptr;
-static thread_local std::map<std::string, std::pair<unsigned long long, double>> g_hostprof_acc;
+struct HostProfAcc { unsigned long long n = 0; double wall_us = 0, cpu_us = 0; };
+static thread_local std::map<std::string, HostProfAcc> g_hostprof_acc;
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-DpHostTimer::DpHostTimer(const char *n) : name(n), t0(g_hostprof ? now_us() : 0.0) {}
-DpHostTimer::~DpHostTimer() { if (g_hostprof) { auto &a = g_hostprof_acc[name]; a.first++; a.second += now_us() - t0; } }
-extern "C" void dp_hostprof_dump(void) {
-    for (auto &kv : g_hostprof_acc) fprintf(stderr, "[hostprof] %-32s n=%8llu total=%10.3f ms avg=%8.2f us\n", kv.first.c_str(), kv.second.first, kv.second.second / 1e3, kv.second.second / kv.second.first);
+static inline double thread_cpu_us() { struct timespec ts; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+DpHostTimer::DpHostTimer(const char *n) : name(n), t0(g_hostprof ? now_us() : 0.0), c0(g_hostprof ? thread_cpu_us() : 0.0) {}
+DpHostTimer::~DpHostTimer() { if (g_hostprof) { auto &a = g_hostprof_acc[name]; a.n++; a.wall_us += now_us() - t0; a.cpu_us += thread_cpu_us() - c0; } }
+extern "C" void dp_hostprof_dump(void) {   // wall = time inside the call, cpu = CPU time this thread burnt inside it (spinning shows up as cpu ~ wall)
+    for (auto &kv : g_hostprof_acc) fprintf(stderr, "[hostprof] %-32s n=%8llu wall=%10.3f ms cpu=%10.3f ms avg wall=%8.2f us cpu=%7.2f us\n", kv.first.c_str(), kv.second.n, kv.second.wall_us / 1e3, kv.second.cpu_us / 1e3, kv.second.wall_us / kv.second.n, kv.second.cpu_us / kv.second.n);
     g_hostprof_acc.clear();
 }
 

@@ -223,6 +223,7 @@ struct ZkPool {
                 if (!inited) { dp::check(dp_init(device)); inited = true; }
                 if (delay > 0.0) std::this_thread::sleep_for(std::chrono::duration<double>(delay));
                 auto t0 = std::chrono::steady_clock::now();
+                struct timespec cts0; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &cts0);
                 dp::DynTranscript t(label);
                 dp::zkml::Prover<dp::DynTranscript> prover(h->ctx, t);
                 if (e2e) {   // from the host input vector: inference, prove, serialised proof in host memory
@@ -231,6 +232,8 @@ struct ZkPool {
                     if (bytes.empty()) throw dp::Error(DP_ERR_STATE, "empty proof");
                 } else { dp::zkml::Proof p = prover.prove(h->trace); (void)p; }
                 const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (getenv("DP_HOST_PROF") && idx == 0) { struct timespec cts1; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &cts1);
+                    fprintf(stderr, "[worker0] proof wall %.2f ms, thread CPU %.2f ms, transcript permutations %llu\n", sec * 1e3, (cts1.tv_sec - cts0.tv_sec) * 1e3 + (cts1.tv_nsec - cts0.tv_nsec) * 1e-6, (unsigned long long)t.permutations()); }
                 if (!first_ever) { std::lock_guard<std::mutex> lk(mu); n_timed++; avg_proof_s += (sec - avg_proof_s) / (double)std::min<uint64_t>(n_timed, 64); }
             } catch (const std::exception &e) { std::lock_guard<std::mutex> lk(mu); failed = true; err = e.what(); }
             dp_profile_flush();   // per-kernel timing of the concurrent region (no-op unless dp_profile_enable(1))

@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 3 --warmup 3 > gpurun_out/r02z_bench_n4.json 2> gpurun_out/r02z_bench_n4.err
-echo "rc=$?"; grep -v "zkml\|^$\|\*\*\*\|OMP" gpurun_out/r02z_bench_n4.err | tail -5; cat /sys/fs/cgroup/cpu.max
-python - <<'PY'
-import json
-d=json.loads([x for x in open("gpurun_out/r02z_bench_n4.json") if x.startswith("{")][0])
-print({k:d[k] for k in ("value","n_gpus","ms_per_step","e2e")}); print(d["run"]["parallelism"]); print(json.dumps(d["sharded"], indent=0)[:1500]); print({k:(v["value"], v["e2e"]["value"]) for k,v in d["workloads"].items()})
-PY
+L=gpurun_out/r03b.log; : > $L
+python -m pytest tests/test_zkml.py tests/test_gpu_mle_sumcheck.py tests/test_gpu_basefold.py tests/test_gpu_cnn.py -m gpu -x -q 2>&1 | tail -2 >> $L
+DP_HOST_PROF=1 DP_WAIT_MODE=1 python tools/throughput_probe.py 48 2> gpurun_out/r03b_hostprof.err | grep workers >> $L
+grep "worker0" gpurun_out/r03b_hostprof.err | tail -3 >> $L; grep "hostprof.*dp_sc_\(create\|destroy\)" gpurun_out/r03b_hostprof.err >> $L
+DP_WAIT_MODE=1 python tools/throughput_probe.py 32 48 64 2>/dev/null | grep workers >> $L
+DP_WAIT_SPINNERS=0 DP_WAIT_MODE=1 python tools/throughput_probe.py 48 64 2>/dev/null | grep workers >> $L
+cat $L
