@@ -360,8 +360,11 @@ class CnnWorkload:
 WORKLOADS = {"dense4m": DenseWorkload, "cnn264k": CnnWorkload, "sumcheck20": SumcheckWorkload, "basefold24": BasefoldWorkload}
 
 
+_CPU_BUDGET = None
+
+
 def cpu_budget():
-    """CPUs this rank may use: the process's affinity mask and the cgroup CPU quota (the 1-GPU measurement boxes report 128 logical
+    """(cached at first call, i.e. before this rank pins itself to its GPU's NUMA node) CPUs this rank may use: the process's affinity mask and the cgroup CPU quota (the 1-GPU measurement boxes report 128 logical
     CPUs but run the container under cpu.max = 16 CPUs: a spinning thread per proof in flight is throttled beyond that),
     divided among the ranks of this node"""
     try:
@@ -374,8 +377,11 @@ def cpu_budget():
             cpus = min(cpus, float(quota) / float(period))
     except Exception:
         pass
-    world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
-    return max(2.0, cpus / max(world, 1))
+    global _CPU_BUDGET
+    if _CPU_BUDGET is None:
+        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        _CPU_BUDGET = max(2.0, cpus / max(world, 1))
+    return _CPU_BUDGET
 
 
 def host_workers(streams):
@@ -828,6 +834,7 @@ def main():
     if not torch.cuda.is_available() or dp.device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    cpu_budget()                                 # from the unpinned affinity mask and the container's quota
     pin_to_gpu_numa_node(torch, local_rank)
     dist = None
     if world > 1:

@@ -1,3 +1,8 @@
 mkdir -p gpurun_out
-DP_WAIT_MODE=1 ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none -c 3000 --csv --log-file gpurun_out/r03c_dense4m_inst_ncu.csv python tools/ncu_dense.py 1 > /dev/null 2>&1
-echo done
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/r03d_bench_n8.json 2> gpurun_out/r03d_bench_n8.err
+echo "rc=$?"; grep -v "zkml\|^$\|\*\*\*\|OMP" gpurun_out/r03d_bench_n8.err | tail -5; cat /sys/fs/cgroup/cpu.max
+python - <<'PY'
+import json
+d=json.loads([x for x in open("gpurun_out/r03d_bench_n8.json") if x.startswith("{")][0])
+print({k:d[k] for k in ("value","n_gpus","ms_per_step","e2e")}); print(d["run"]["parallelism"]); s=d["sharded"]; print({k:{q:v.get(q) for q in ("sharded_ms","single_gpu_ms","speedup","bit_identical_to_single_gpu_proof","error")} for k,v in s.items()}); print({k:(v["value"], v["e2e"]["value"]) for k,v in d["workloads"].items()})
+PY
