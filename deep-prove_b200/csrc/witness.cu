@@ -46,6 +46,19 @@ __global__ void k_wit_dense_small(const u64 *__restrict__ w, const u64 *__restri
     out[row] = i2f(acc);
 }
 
+// ---- MatMul::op (layers/matrix_mul.rs:230-311): out[r][c] = bias[c] + sum_k left[r][k] * right(k, c); right stored [K][C], or [C][K] with TransposeB ----
+// one thread per output element; the K-loop reads the left row (broadcast within the threads of a row) and a right column / row
+__global__ void k_wit_matmul(const u64 *__restrict__ left, const u64 *__restrict__ right, const u64 *__restrict__ bias, u32 R, u32 K, u32 C, int transposed, u64 *__restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (u64)R * C) return;
+    const u32 r = (u32)(i / C), c = (u32)(i % C);
+    long long acc = bias ? f2i(bias[c]) : 0;
+    const u64 *lr = left + (u64)r * K;
+    if (transposed) { const u64 *rr = right + (u64)c * K; for (u32 k = 0; k < K; k++) acc += f2i(lr[k]) * f2i(rr[k]); }
+    else for (u32 k = 0; k < K; k++) acc += f2i(lr[k]) * f2i(right[(u64)k * C + c]);
+    out[i] = i2f(acc);
+}
+
 // ---- Requant: tmp = v * m + 2^(shift-1); cin = tmp >> shift; cout = clamp(cin); chunks = bytes of (tmp & (2^shift - 1)) ----
 struct RqCols { u64 *cin, *cout, *chunk[8]; u32 n_chunks; };
 __global__ void k_wit_requant(const u64 *__restrict__ x, u64 n, u32 shift, long long fpm, long long lim, RqCols c, u32 *clamp_counts, u32 clamp_size, u32 *range_counts, u32 *err) {
@@ -128,6 +141,19 @@ int dp_wit_dense(const dp_mle *weights, const dp_mle *bias, const dp_mle *x, uin
     DpProfScope prof("k_wit_dense", weights->bytes() + x->bytes() + 16ull * nrows);
     if (ncols >= 2) k_wit_dense<<<(nrows * 32 + 255) / 256, 256, 0, dp_ctx().stream>>>((const u64 *)weights->data, (const u64 *)bias->data, (const u64 *)x->data, nrows, ncols, (u64 *)o->data);
     else k_wit_dense_small<<<(nrows + 255) / 256, 256, 0, dp_ctx().stream>>>((const u64 *)weights->data, (const u64 *)bias->data, (const u64 *)x->data, nrows, ncols, (u64 *)o->data);
+    DP_LAUNCHED(); DP_CUDA(cudaGetLastError());
+    *out = o;
+    return DP_OK;
+}
+
+int dp_wit_matmul(const dp_mle *left, const dp_mle *right, const dp_mle *bias, uint32_t R, uint32_t K, uint32_t C, int transposed, dp_mle **out) {
+    DP_REQUIRE_CTX();
+    DP_CHECK(left && right && out, DP_ERR_INVALID, "dp_wit_matmul: null argument");
+    DP_CHECK(!left->is_ext && !right->is_ext && (!bias || !bias->is_ext), DP_ERR_INVALID, "dp_wit_matmul: tensors are Base");
+    DP_CHECK(left->len == (u64)R * K && right->len == (u64)K * C && (!bias || bias->len == C), DP_ERR_INVALID, "Incompatible shape found for input matrix");   // matrix_mul.rs:277-283
+    dp_mle *o; if (int e = wit_new_base((u64)R * C, &o)) return e;
+    DpProfScope prof("k_wit_matmul", left->bytes() + right->bytes() + 8ull * R * C);
+    k_wit_matmul<<<(unsigned)(((u64)R * C + 255) / 256), 256, 0, dp_ctx().stream>>>((const u64 *)left->data, (const u64 *)right->data, bias ? (const u64 *)bias->data : nullptr, R, K, C, transposed, (u64 *)o->data);
     DP_LAUNCHED(); DP_CUDA(cudaGetLastError());
     *out = o;
     return DP_OK;

@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "dp_pcs_open_begin", "dp_pcs_open_round", "dp_pcs_open_final_message", "dp_pcs_open_query_words", "dp_pcs_open_query",
     "dp_pcs_open_free", "dp_pcs_commit_shard", "dp_pcs_comm_shard_info", "dp_pcs_comm_set_shard_roots", "dp_pcs_open_set_shard_roots",
     "dp_logup_build", "dp_logup_num_vars", "dp_logup_outputs", "dp_logup_layer_mles", "dp_logup_free", "dp_mle_linear_combination",
-    "dp_wit_begin", "dp_wit_dense", "dp_wit_requant", "dp_wit_relu", "dp_wit_pool", "dp_wit_finish", "dp_wit_free",
+    "dp_wit_begin", "dp_wit_dense", "dp_wit_matmul", "dp_wit_requant", "dp_wit_relu", "dp_wit_pool", "dp_wit_finish", "dp_wit_free",
     "dp_fft_rows", "dp_pad_rows", "dp_conv_prod", "dp_conv_output_elements", "dp_phi_g_init", "dp_phi_level", "dp_mle_repeat",
 ]
 

@@ -405,7 +405,7 @@ extern "C" int dph_conv_prove(uint32_t kw, uint32_t kx, uint32_t n_x, uint32_t r
 }
 
 // General model builder: `desc` holds 9 int64 per node {kind, 8 shape words} and `data` the weights in node order
-// (kind 0 Dense {nrows, ncols}: weights then bias; 1 Requant {right_shift, fp_scale, multiplier, intermediate_bits};
+// (kind 5 MatMul {rows, inner, cols, transposed, has_bias}: the constant right matrix then the bias; kind 0 Dense {nrows, ncols}: weights then bias; 1 Requant {right_shift, fp_scale, multiplier, intermediate_bits};
 //  2 ReLU; 3 Conv {kw, kx, nw, real_nw, unpadded_out[3]}: filter then bias; 4 Maxpool {C, H, W}).  Same handle type as
 // dph_zkml_context_new: dph_zkml_prove / dph_zkml_prove_concurrent / dph_zkml_context_free apply.
 extern "C" int dph_model_context_new(const int64_t *desc, uint32_t n_nodes, const int64_t *data, uint64_t input_len, void **out) {
@@ -423,6 +423,8 @@ extern "C" int dph_model_context_new(const int64_t *desc, uint32_t n_nodes, cons
         case 3: { n.op = Op::Conv; n.kw = d[1]; n.kx = d[2]; n.nw = d[3]; n.real_nw = d[4]; for (int k = 0; k < 3; k++) n.unpadded_out[k] = d[5 + k];
                   size_t fl = n.kw * n.kx * n.real_nw * n.real_nw; n.weights.assign(w, w + fl); w += fl; n.bias.assign(w, w + n.kw); w += n.kw; break; }
         case 4: n.op = Op::Pool; n.pool_c = d[1]; n.pool_h = d[2]; n.pool_w = d[3]; break;
+        case 5: n.op = Op::MatMul; n.mm_r = d[1]; n.mm_k = d[2]; n.mm_c = d[3]; n.mm_t = d[4] != 0; n.mm_bias = d[5] != 0; n.weights.assign(w, w + n.mm_k * n.mm_c); w += n.mm_k * n.mm_c;
+                if (n.mm_bias) { n.bias.assign(w, w + n.mm_c); w += n.mm_c; } break;
         default: delete h; throw Error(DP_ERR_INVALID, "dph_model_context_new: unknown node kind");
         }
         h->model.nodes.push_back(std::move(n));

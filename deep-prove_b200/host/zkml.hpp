@@ -40,11 +40,14 @@ struct Requant {                                            // layers/requant.rs
     }
 };
 
-enum class Op { Dense, Requant, Relu, Conv, Pool };
+enum class Op { Dense, Requant, Relu, Conv, Pool, MatMul };
 struct Node {
     Op op; size_t nrows = 0, ncols = 0; std::vector<Element> weights, bias; Requant rq;
     size_t kw = 0, kx = 0, nw = 0, real_nw = 0, unpadded_out[3] = {0, 0, 0};     // Conv: padded layer, `weights` = filter [kw][kx][real_nw][real_nw], `bias` [kw]
     size_t pool_c = 0, pool_h = 0, pool_w = 0;                                   // Pool: padded input shape [C][H][W] (Maxpool2D, kernel = stride = 2)
+    // MatMul (layers/matrix_mul.rs), OperandMatrix::Input x OperandMatrix::Weight: the node's input is the left matrix [mm_r][mm_k], `weights` the
+    // constant right matrix [mm_k][mm_c] ([mm_c][mm_k] with Config::TransposeB), `bias` (optional) one value per output column
+    size_t mm_r = 0, mm_k = 0, mm_c = 0; bool mm_t = false, mm_bias = false;
 };
 struct Model { std::vector<Node> nodes; size_t input_len = 0; };
 
@@ -173,6 +176,7 @@ class Context {
         size_t max_len = m.input_len; std::map<TableType, int> tabs;
         for (auto &n : m.nodes) {
             if (n.op == Op::Dense) max_len = std::max(max_len, std::max(n.nrows * n.ncols, n.nrows));
+            if (n.op == Op::MatMul) max_len = std::max(max_len, std::max(n.mm_k * n.mm_c, n.mm_c));
             if (n.op == Op::Requant) { tabs[TableType::range()] = 1; tabs[TableType::clamping(n.rq.clamping_size())] = 1; }
             if (n.op == Op::Relu) tabs[TableType::relu()] = 1;
             if (n.op == Op::Conv) max_len = std::max(max_len, std::max(n.weights.size(), n.kw * n.nw * n.nw));
@@ -186,6 +190,11 @@ class Context {
                 DeviceMle poly = DeviceMle::from_evaluations_vec(to_base(*kv.second));
                 c.model_comms[id][kv.first] = {Basefold::commit(c.pp, poly), poly};
             }
+        } else if (m.nodes[id].op == Op::MatMul) {   // MatMul::ctx (matrix_mul.rs:951-963): the constant matrix and the bias are model polynomials
+            const Node &n = m.nodes[id];
+            if (n.mm_bias) { DeviceMle poly = DeviceMle::from_evaluations_vec(to_base(n.bias)); c.model_comms[id]["MatMulBias"] = {Basefold::commit(c.pp, poly), poly}; }
+            DeviceMle poly = DeviceMle::from_evaluations_vec(to_base(n.weights));
+            c.model_comms[id]["MatMulWeight"] = {Basefold::commit(c.pp, poly), poly};
         } else if (m.nodes[id].op == Op::Conv) {   // convolution.rs:532-540: ConvBias, ConvFilter (BTreeMap order)
             const Node &n = m.nodes[id];
             Convolution cv; cv.kw = n.kw; cv.kx = n.kx; cv.nw = n.nw; cv.real_nw = n.real_nw; cv.filter = n.weights; cv.bias = n.bias;
@@ -236,6 +245,15 @@ inline std::vector<std::vector<Element>> run(const Model &m, const std::vector<E
         else if (n.op == Op::Requant) { Element lim = (Element)1 << n.rq.intermediate_bit_size; for (Element e : cur) { if (e > lim || e < -lim) throw Error(DP_ERR_INVALID, "Could not apply requantisation, tensor element had absolute value too large"); o.push_back(n.rq.apply(e)); } }
         else if (n.op == Op::Relu) for (Element e : cur) o.push_back(relu(e));
         else if (n.op == Op::Pool) o = maxpool2d(cur, n.pool_c, n.pool_h, n.pool_w);
+        else if (n.op == Op::MatMul) {
+            if (cur.size() != n.mm_r * n.mm_k) throw Error(DP_ERR_INVALID, "Incompatible shape found for input matrix");
+            o.assign(n.mm_r * n.mm_c, 0);
+            for (size_t r = 0; r < n.mm_r; r++) for (size_t c = 0; c < n.mm_c; c++) {
+                Element a = n.mm_bias ? n.bias[c] : 0;
+                for (size_t k = 0; k < n.mm_k; k++) a += cur[r * n.mm_k + k] * (n.mm_t ? n.weights[c * n.mm_k + k] : n.weights[k * n.mm_c + c]);
+                o[r * n.mm_c + c] = a;
+            }
+        }
         else {
             if (!ctx || !conv_data) throw Error(DP_ERR_INVALID, "run: a convolution needs the Context (resident FFT'd filters)");
             ConvData cd; o = ctx->convs.at(outs.size()).op(cur, cd); (*conv_data)[outs.size()] = std::move(cd);
@@ -288,6 +306,7 @@ inline DeviceTrace run_device(const Context &ctx, const std::vector<Element> &in
         else if (n.op == Op::Requant) o = wit_requant(wh.w, cur, n.rq, ti)[1];
         else if (n.op == Op::Relu) { dp_mle *h; check(dp_wit_relu(wh.w, cur.handle(), ti.at(TableType::relu()), &h)); o = wit_own(h); }
         else if (n.op == Op::Pool) o = wit_pool(wh.w, cur, n, ti)[4];
+        else if (n.op == Op::MatMul) { const auto &c = ctx.model_comms.at(id); dp_mle *h; check(dp_wit_matmul(cur.handle(), c.at("MatMulWeight").poly.handle(), n.mm_bias ? c.at("MatMulBias").poly.handle() : nullptr, (uint32_t)n.mm_r, (uint32_t)n.mm_k, (uint32_t)n.mm_c, n.mm_t ? 1 : 0, &h)); o = wit_own(h); }
         else { ConvData cd; std::vector<Element> out = ctx.convs.at(id).op(to_elements(cur), cd); tr.conv[id] = std::move(cd); o = DeviceMle::from_evaluations_vec(to_base(out)); }
         tr.outs.push_back(o); cur = o;
     }
@@ -335,6 +354,7 @@ class Prover {
             else if (n.op == Op::Requant) last = prove_requant(id, n, last);
             else if (n.op == Op::Relu) last = prove_activation(id, last);
             else if (n.op == Op::Pool) last = prove_pooling(id, n, last);
+            else if (n.op == Op::MatMul) last = prove_matmul(id, n, last, node_input(id));
             else {
                 if (!conv_data || !conv_data->count(id)) throw Error(DP_ERR_INVALID, "prove: no convolution proving data in the trace");
                 last = prove_convolution(id, last, conv_data->at(id));
@@ -434,6 +454,33 @@ class Prover {
         add_witness_claim(comms.at("DenseWeight"), {wp, fe[0]});
         proof_.dense[id] = {res.first, bias_eval, fe};
         return {res.first.point, fe[1]};
+    }
+
+    // MatMul::prove_step (layers/matrix_mul.rs:701-874) for Input x Weight: the output claim splits into the row part (fixes the HIGH variables of
+    // the left = input matrix) and the column part (fixes the LOW variables of the constant matrix, or its HIGH ones when it is stored
+    // transposed); one degree-2 sumcheck over the shared inner dimension; the left evaluation is the claim handed to the previous node
+    Claim prove_matmul(size_t id, const Node &n, const Claim &last_claim, const DeviceMle &input) {
+        const auto &comms = ctx_.model_comms.at(id);
+        const size_t vr = ceil_log2(n.mm_r), vc = ceil_log2(n.mm_c), vk = ceil_log2(n.mm_k);
+        if (last_claim.point.size() != vr + vc) throw Error(DP_ERR_INVALID, "Wrong length of last claim point");
+        const ExtVec p_right(last_claim.point.begin(), last_claim.point.begin() + vc), p_left(last_claim.point.begin() + vc, last_claim.point.end());   // split_claim
+        Ext bias_eval = Ext::zero();
+        if (n.mm_bias) bias_eval = comms.at("MatMulBias").poly.evaluate(p_right);
+        DeviceMle left = input.fix_high_variables(p_left);
+        const DeviceMle &w = comms.at("MatMulWeight").poly;
+        DeviceMle right = n.mm_t ? w.fix_high_variables(p_right) : w.fix_variables(p_right);
+        if (left.num_vars() != vk || right.num_vars() != vk) throw Error(DP_ERR_INVALID, "matmul: free variables of the two matrices differ");
+        VirtualPolynomial vp(vk);
+        vp.add_mle_list({left, right}, Ext::one());
+        auto res = IOPProverState::prove_parallel(std::move(vp), t_);
+        const ExtVec &fe = res.second.get_mle_final_evaluations();
+        ExtVec pl = res.first.point; pl.insert(pl.end(), p_left.begin(), p_left.end());                      // full_points
+        ExtVec pr;
+        if (n.mm_t) { pr = res.first.point; pr.insert(pr.end(), p_right.begin(), p_right.end()); } else { pr = p_right; pr.insert(pr.end(), res.first.point.begin(), res.first.point.end()); }
+        if (n.mm_bias) add_witness_claim(comms.at("MatMulBias"), {p_right, bias_eval});                       // BTreeMap order of PolyId
+        add_witness_claim(comms.at("MatMulWeight"), {pr, fe[1]});
+        proof_.dense[id] = {res.first, bias_eval, fe};                                                         // MatMulProof has DenseProof's shape
+        return {pl, fe[0]};
     }
 
     // Requant::prove_step (layers/requant.rs:531-680)

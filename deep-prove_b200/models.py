@@ -7,7 +7,7 @@ c1 = 12, c2 = 33, fc1 = 247, fc2 = 173:  [3,32,32] -> conv5x5(12) -> requant -> 
 -> relu -> maxpool -> flatten(33*5*5) -> fc 247 -> requant -> relu -> fc 173 -> requant -> relu -> fc 10."""
 import numpy as np
 
-DENSE, REQUANT, RELU, CONV, POOL = 0, 1, 2, 3, 4
+DENSE, REQUANT, RELU, CONV, POOL, MATMUL = 0, 1, 2, 3, 4, 5
 BIT_LEN = 8
 
 
@@ -75,3 +75,24 @@ def cnn(seed=1, img=32, c0=3, c1=12, c2=33, f1=247, f2=173, f3=10, k=5):
 
 def cnn_small(seed=1):
     return cnn(seed, img=16, c0=3, c1=4, c2=6, f1=24, f2=16, f3=10, k=3)
+
+
+def token_mlp(seed=1, tokens=8, d_model=64, d_hidden=128, transposed=(False, True), bias=(True, False)):
+    """A token-wise MLP as the transformer feed-forward block uses it (zkml/src/layers/matrix_mul.rs: OperandMatrix::Input x
+    OperandMatrix::Weight): X [tokens, d_model] -> MatMul(W1 [d_model, d_hidden] or its transpose, + bias) -> requant -> relu
+    -> MatMul(W2 [d_hidden, d_model]) .  All dimensions powers of two (the padded layout).  Returns (desc, data, input)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    desc, data = [], []
+    x = rng.integers(-127, 128, size=(tokens, d_model)).astype(np.int64)
+    dims = [(d_model, d_hidden), (d_hidden, d_model)]
+    for li, (k, c) in enumerate(dims):
+        w = rng.integers(-127, 128, size=(k, c)).astype(np.int64)
+        stored = w.T.copy() if transposed[li] else w          # Config::TransposeB keeps the matrix as [C][K]
+        desc.append([MATMUL, tokens, k, c, int(transposed[li]), int(bias[li]), 0, 0, 0])
+        data.append(stored.reshape(-1))
+        if bias[li]:
+            data.append(rng.integers(-127, 128, size=c).astype(np.int64))
+        if li == 0:
+            desc.append(_requant(_clog2(k), 2 * (BIT_LEN - 1) + _clog2(k) + 1))
+            desc.append([RELU] + [0] * 8)
+    return np.asarray(desc, dtype=np.int64), np.concatenate(data).astype(np.int64), x.reshape(-1)

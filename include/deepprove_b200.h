@@ -239,6 +239,9 @@ int dp_pcs_open_set_shard_roots(dp_pcs_open *o, const uint64_t *roots, uint64_t 
 typedef struct dp_wit dp_wit;
 int dp_wit_begin(uint32_t n_tables, const uint32_t *kinds, const uint32_t *sizes, dp_wit **out);
 int dp_wit_dense(const dp_mle *weights /* [nrows][ncols] */, const dp_mle *bias, const dp_mle *x, uint32_t nrows, uint32_t ncols, dp_mle **out);
+/* MatMul::op (layers/matrix_mul.rs:230-311): left [R][K] x right ([K][C], or [C][K] when `transposed`: Config::TransposeB) + bias[C] on every
+ * row (bias may be NULL) -> [R][C] */
+int dp_wit_matmul(const dp_mle *left, const dp_mle *right, const dp_mle *bias, uint32_t R, uint32_t K, uint32_t C, int transposed, dp_mle **out);
 /* cols[0] clamping input, cols[1] clamping output (= the node's output tensor), cols[2 ..] the shift / BIT_LEN byte chunks */
 int dp_wit_requant(dp_wit *w, const dp_mle *x, uint32_t shift, int64_t fixed_point_multiplier, uint32_t intermediate_bit_size,
                    uint32_t clamp_table, uint32_t range_table, dp_mle **cols, uint32_t n_cols);

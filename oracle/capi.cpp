@@ -390,6 +390,7 @@ extern "C" int dpo_model_prove(const int64_t *desc, u32 n_nodes, const int64_t *
             case 3: { n.kind = OP_CONV; auto c = std::make_shared<ConvLayer>(); c->kw = d[1]; c->kx = d[2]; c->nw = d[3]; c->real_nw = d[4]; for (int k = 0; k < 3; k++) c->unpadded_out[k] = d[5 + k];
                       size_t fl = c->kw * c->kx * c->real_nw * c->real_nw; c->filter.assign(w, w + fl); w += fl; c->bias.assign(w, w + c->kw); w += c->kw; n.conv = c; break; }
             case 4: n.kind = OP_POOL; n.pool_c = d[1]; n.pool_h = d[2]; n.pool_w = d[3]; break;
+            case 5: n.kind = OP_MATMUL; n.mm_r = d[1]; n.mm_k = d[2]; n.mm_c = d[3]; n.mm_t = d[4] != 0; n.mm_bias = d[5] != 0; n.weights.assign(w, w + n.mm_k * n.mm_c); w += n.mm_k * n.mm_c; if (n.mm_bias) { n.bias.assign(w, w + n.mm_c); w += n.mm_c; } break;
             default: throw std::runtime_error("dpo_model_prove: unknown node kind");
             }
             m.nodes.push_back(n);
@@ -471,6 +472,7 @@ extern "C" int dpo_model_prove_verify(const int64_t *desc, u32 n_nodes, const in
             case 3: { n.kind = OP_CONV; auto c = std::make_shared<ConvLayer>(); c->kw = d[1]; c->kx = d[2]; c->nw = d[3]; c->real_nw = d[4]; for (int k = 0; k < 3; k++) c->unpadded_out[k] = d[5 + k];
                       size_t fl = c->kw * c->kx * c->real_nw * c->real_nw; c->filter.assign(w, w + fl); w += fl; c->bias.assign(w, w + c->kw); w += c->kw; n.conv = c; break; }
             case 4: n.kind = OP_POOL; n.pool_c = d[1]; n.pool_h = d[2]; n.pool_w = d[3]; break;
+            case 5: n.kind = OP_MATMUL; n.mm_r = d[1]; n.mm_k = d[2]; n.mm_c = d[3]; n.mm_t = d[4] != 0; n.mm_bias = d[5] != 0; n.weights.assign(w, w + n.mm_k * n.mm_c); w += n.mm_k * n.mm_c; if (n.mm_bias) { n.bias.assign(w, w + n.mm_c); w += n.mm_c; } break;
             default: throw std::runtime_error("dpo_model_prove_verify: unknown node kind");
             }
             m.nodes.push_back(n);
@@ -483,6 +485,8 @@ extern "C" int dpo_model_prove_verify(const int64_t *desc, u32 n_nodes, const in
         if (tamper == 1) output[0] += 1;
         if (tamper == 2 && !p.conv.empty()) p.conv.begin()->second.partial_evals[0].c0 ^= 1;
         if (tamper == 3 && !p.pooling.empty()) p.pooling.begin()->second.zerocheck_evals[1].c1 ^= 1;
+        if (tamper == 4 && !p.dense.empty()) p.dense.begin()->second.individual_claims[0].c0 ^= 1;      // Dense / MatMul: a forged final evaluation
+        if (tamper == 5 && !p.dense.empty()) p.dense.begin()->second.bias_eval.c0 ^= 1;                 // ... a forged bias evaluation
         Transcript tv(label);
         zk_verify(ctx, in, output, p, tv);
         return 0;

@@ -221,6 +221,24 @@ static inline void zk_verify(const ZkContext &ctx, const std::vector<Element> &i
             E prod = E::one(); for (E e : p.individual_claims) prod = e_mul(prod, e);
             zk_ensure(prod == sub.expected_evaluation, "dense: sumcheck claim failed");
             last = {sub.point, p.individual_claims[1]};
+        } else if (n.kind == OP_MATMUL) {                                            // verify_matmul (matrix_mul.rs:1048-1139)
+            zk_ensure(proof.dense.count(id), "no matmul proof for node " + std::to_string(id));
+            const DenseProof &p = proof.dense.at(id);
+            const size_t vr = ceil_log2(n.mm_r), vc = ceil_log2(n.mm_c), vk = ceil_log2(n.mm_k);
+            zk_ensure(last.point.size() == vr + vc, "matmul: wrong claim point length");
+            const std::vector<E> p_right(last.point.begin(), last.point.begin() + vc), p_left(last.point.begin() + vc, last.point.end());
+            const auto &comms = ctx.model_comms.at(id);
+            E claim_eval = last.eval;
+            if (n.mm_bias) { cv.add_witness_claim(pure_of(comms.at("MatMulBias")->comm.root(), comms.at("MatMulBias")->comm.num_vars), {p_right, p.bias_eval}); claim_eval = e_sub(claim_eval, p.bias_eval); }
+            SumCheckSubClaim sub = sumcheck_verify(claim_eval, p.sumcheck, vk, 2, t);
+            zk_ensure(p.individual_claims.size() == 2, "matmul: two individual claims expected");
+            std::vector<E> pl = sub.point; pl.insert(pl.end(), p_left.begin(), p_left.end());
+            std::vector<E> pr;
+            if (n.mm_t) { pr = sub.point; pr.insert(pr.end(), p_right.begin(), p_right.end()); } else { pr = p_right; pr.insert(pr.end(), sub.point.begin(), sub.point.end()); }
+            cv.add_witness_claim(pure_of(comms.at("MatMulWeight")->comm.root(), comms.at("MatMulWeight")->comm.num_vars), {pr, p.individual_claims[1]});
+            used_model[id] = true;
+            zk_ensure(e_mul(p.individual_claims[0], p.individual_claims[1]) == sub.expected_evaluation, "matmul: sumcheck claim failed");
+            last = {pl, p.individual_claims[0]};
         } else if (n.kind == OP_REQUANT) {                                           // verify_requant (requant.rs:689-816)
             zk_ensure(proof.requant.count(id), "no requant proof for node " + std::to_string(id));
             const RequantProof &p = proof.requant.at(id);

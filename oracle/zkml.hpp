@@ -33,13 +33,17 @@ struct RequantParams {                                      // layers/requant.rs
     }
 };
 
-enum OpKind { OP_DENSE = 0, OP_REQUANT = 1, OP_RELU = 2, OP_CONV = 3, OP_POOL = 4 };
+enum OpKind { OP_DENSE = 0, OP_REQUANT = 1, OP_RELU = 2, OP_CONV = 3, OP_POOL = 4, OP_MATMUL = 5 };
 struct Node {
     OpKind kind; size_t nrows = 0, ncols = 0;
     std::vector<Element> weights, bias;   // Dense, row-major nrows x ncols
     RequantParams rq;
     std::shared_ptr<struct ConvLayer> conv;                  // OP_CONV (padded layer, conv.hpp)
     size_t pool_c = 0, pool_h = 0, pool_w = 0;               // OP_POOL: padded input shape [C][H][W], Maxpool2D kernel = stride = 2
+    // OP_MATMUL (layers/matrix_mul.rs, OperandMatrix::Input x OperandMatrix::Weight): the node's input is the LEFT matrix [mm_r][mm_k]
+    // (row-major), `weights` the constant RIGHT matrix stored [mm_k][mm_c] -- or [mm_c][mm_k] with Config::TransposeB (mm_t) --, `bias`
+    // (optional, mm_bias) has mm_c entries and is added to every output row (add_dim2); output [mm_r][mm_c]
+    size_t mm_r = 0, mm_k = 0, mm_c = 0; bool mm_t = false, mm_bias = false;
 };
 struct Model { std::vector<Node> nodes; size_t input_len = 0; };
 
@@ -221,6 +225,7 @@ static inline ZkContext zk_context(const Model &m) {
     size_t max_len = m.input_len; std::map<TableType, int> tabs;
     for (auto &n : m.nodes) {
         if (n.kind == OP_DENSE) max_len = std::max(max_len, std::max(n.nrows * n.ncols, n.nrows));
+        if (n.kind == OP_MATMUL) max_len = std::max(max_len, std::max(n.mm_k * n.mm_c, n.mm_c));
         if (n.kind == OP_REQUANT) { tabs[{TT_RANGE, 0}] = 1; tabs[{TT_CLAMPING, n.rq.clamping_size()}] = 1; }
         if (n.kind == OP_RELU) tabs[{TT_RELU, 0}] = 1;
         if (n.kind == OP_CONV) max_len = std::max(max_len, std::max(n.conv->filter.size(), n.conv->kw * n.conv->nw * n.conv->nw));
@@ -231,6 +236,9 @@ static inline ZkContext zk_context(const Model &m) {
     for (size_t id = 0; id < m.nodes.size(); id++) if (m.nodes[id].kind == OP_DENSE) {
         c.model_comms[id]["DenseBias"] = commit_base(to_base_vec(m.nodes[id].bias), c.full_log);
         c.model_comms[id]["DenseWeight"] = commit_base(to_base_vec(m.nodes[id].weights), c.full_log);
+    } else if (m.nodes[id].kind == OP_MATMUL) {               // matrix_mul.rs:951-963: MatMulWeight (+ MatMulBias)
+        if (m.nodes[id].mm_bias) c.model_comms[id]["MatMulBias"] = commit_base(to_base_vec(m.nodes[id].bias), c.full_log);
+        c.model_comms[id]["MatMulWeight"] = commit_base(to_base_vec(m.nodes[id].weights), c.full_log);
     } else if (m.nodes[id].kind == OP_CONV) {                 // convolution.rs:532-540 (ConvBias < ConvFilter in the BTreeMap)
         c.model_comms[id]["ConvBias"] = commit_base(to_base_vec(m.nodes[id].conv->bias), c.full_log);
         c.model_comms[id]["ConvFilter"] = commit_base(to_base_vec(m.nodes[id].conv->filter), c.full_log);
@@ -267,6 +275,15 @@ static inline std::vector<std::vector<Element>> zk_run(const Model &m, const std
         else if (n.kind == OP_REQUANT) { for (Element e : cur) { Element lim = (Element)1 << n.rq.intermediate_bit_size; if (e > lim || e < -lim) throw std::runtime_error("Could not apply requantisation, tensor element had absolute value too large"); o.push_back(n.rq.apply(e)); } }
         else if (n.kind == OP_CONV) { ConvData cd; o = conv_op(*n.conv, cur, n.conv->nw, cd); if (conv_data) (*conv_data)[outs.size()] = std::move(cd); }
         else if (n.kind == OP_POOL) o = maxpool2d(cur, n.pool_c, n.pool_h, n.pool_w);
+        else if (n.kind == OP_MATMUL) {   // MatMul::op (matrix_mul.rs:230-311): left x right (+ bias on every row)
+            if (cur.size() != n.mm_r * n.mm_k) throw std::runtime_error("Incompatible shape found for input matrix");
+            o.assign(n.mm_r * n.mm_c, 0);
+            for (size_t r = 0; r < n.mm_r; r++) for (size_t c = 0; c < n.mm_c; c++) {
+                Element a = n.mm_bias ? n.bias[c] : 0;
+                for (size_t k = 0; k < n.mm_k; k++) a += cur[r * n.mm_k + k] * (n.mm_t ? n.weights[c * n.mm_k + k] : n.weights[k * n.mm_c + c]);
+                o[r * n.mm_c + c] = a;
+            }
+        }
         else for (Element e : cur) o.push_back(relu(e));
         outs.push_back(o); cur = o;
     }
@@ -350,6 +367,29 @@ static inline ModelProof zk_prove(const ZkContext &ctx, const std::vector<Elemen
             add_witness_claim(comms.at("DenseWeight"), {wp, res.second[0]});
             proof.dense[id] = {res.first, bias_eval, res.second};
             last = {res.first.point, res.second[1]};
+        } else if (n.kind == OP_MATMUL) {   // MatMul::prove_step (matrix_mul.rs:701-874), left = the node's input, right = the constant matrix
+            const size_t vr = ceil_log2(n.mm_r), vc = ceil_log2(n.mm_c), vk = ceil_log2(n.mm_k);
+            if (last.point.size() != vr + vc) throw std::runtime_error("Wrong length of last claim point");
+            const std::vector<E> p_right(last.point.begin(), last.point.begin() + vc), p_left(last.point.begin() + vc, last.point.end());   // split_claim (:339-358)
+            const auto &comms = ctx.model_comms.at(id);
+            E claim_eval = last.eval, bias_eval = E::zero();
+            if (n.mm_bias) { bias_eval = mle_evaluate(*base_mle(to_base_vec(n.bias)), p_right); claim_eval = e_sub(claim_eval, bias_eval); }
+            MLE left = mle_fix_high_variables(*base_mle(to_base_vec(node_input(id))), p_left);            // rows of the left matrix are its HIGH variables
+            MLE right = n.mm_t ? mle_fix_high_variables(*base_mle(to_base_vec(n.weights)), p_right)       // transposed: the output column is a ROW of the stored matrix
+                               : mle_fix_variables(*base_mle(to_base_vec(n.weights)), p_right);           // else a column: the LOW variables
+            if (left.num_vars != vk || right.num_vars != vk) throw std::runtime_error("matmul: free variables differ");
+            auto lp = std::make_shared<MLE>(left); auto rp = std::make_shared<MLE>(right);
+            VirtualPolynomial vp(vk); vp.add_mle_list({lp, rp}, E::one());
+            auto res = sumcheck_prove(vp, t);
+            if (res.first.extract_sum() != claim_eval) throw std::runtime_error("matmul: sumcheck output weird");
+            // full_points (:364-383)
+            std::vector<E> pl = res.first.point; pl.insert(pl.end(), p_left.begin(), p_left.end());
+            std::vector<E> pr;
+            if (n.mm_t) { pr = res.first.point; pr.insert(pr.end(), p_right.begin(), p_right.end()); } else { pr = p_right; pr.insert(pr.end(), res.first.point.begin(), res.first.point.end()); }
+            if (n.mm_bias) add_witness_claim(comms.at("MatMulBias"), {p_right, bias_eval});               // add_common_claims walks the BTreeMap: MatMulBias < MatMulWeight
+            add_witness_claim(comms.at("MatMulWeight"), {pr, res.second[1]});
+            proof.dense[id] = {res.first, bias_eval, res.second};                                          // MatMulProof {sumcheck, individual_claims, bias_eval}: the same shape
+            last = {pl, res.second[0]};
         } else if (n.kind == OP_REQUANT) {   // requant.rs:531-680
             auto ws = lookup_witness.at(id);
             LogUpInput cin = logup_input(ws[0]), sin = logup_input(ws[1]);
