@@ -1,8 +1,3 @@
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/r03d_bench_n8.json 2> gpurun_out/r03d_bench_n8.err
-echo "rc=$?"; grep -v "zkml\|^$\|\*\*\*\|OMP" gpurun_out/r03d_bench_n8.err | tail -5; cat /sys/fs/cgroup/cpu.max
-python - <<'PY'
-import json
-d=json.loads([x for x in open("gpurun_out/r03d_bench_n8.json") if x.startswith("{")][0])
-print({k:d[k] for k in ("value","n_gpus","ms_per_step","e2e")}); print(d["run"]["parallelism"]); s=d["sharded"]; print({k:{q:v.get(q) for q in ("sharded_ms","single_gpu_ms","speedup","bit_identical_to_single_gpu_proof","error")} for k,v in s.items()}); print({k:(v["value"], v["e2e"]["value"]) for k,v in d["workloads"].items()})
-PY
+python -m pytest tests/test_gpu_matmul.py tests/test_zkml.py tests/test_gpu_witness.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r03e_matmul.log
+cat gpurun_out/r03e_matmul.log
