@@ -876,13 +876,13 @@ int dp_pcs_commit_shard(const dp_mle *poly, uint32_t full_log, uint32_t rank, ui
     u32 rev_rank = 0; for (u32 b = 0; b < logG; b++) if (rank >> b & 1) rev_rank |= 1u << (logG - 1 - b);
     if (poly->is_ext) {
         { DpProfScope p("k_bitrev", esz * m * 2); k_bitrev<gle><<<g, 256, 0, c.stream>>>((const gle *)poly->data, (gle *)coef, nv); DP_LAUNCHED(); }
-        cudaMemcpyAsync(cm->bh_evals, (const char *)coef + esz * Ml * rank, esz * Ml, cudaMemcpyDeviceToDevice, c.stream);
+        if (cudaMemcpyAsync(cm->bh_evals, (const char *)coef + esz * Ml * rank, esz * Ml, cudaMemcpyDeviceToDevice, c.stream) != cudaSuccess) return fail(dp_fail(DP_ERR_CUDA, "dp_pcs_commit_shard: copy of the evaluation slice failed"));
         if (int e = run_levels<gle, 0>((gle *)coef, nv, 0, nv)) return fail(e);
         { DpProfScope p("k_shard_expand", esz * (m + S)); k_shard_expand<gle><<<gs, 256, 0, c.stream>>>((const gle *)coef, (gle *)cm->codeword, nv, logG, rev_rank, st, root_tab()); DP_LAUNCHED(); }
         if (int e = run_levels<gle, 1>((gle *)cm->codeword, n_log - logG, 0, n_log - logG)) return fail(e);
     } else {
         { DpProfScope p("k_bitrev", esz * m * 2); k_bitrev<u64><<<g, 256, 0, c.stream>>>((const u64 *)poly->data, (u64 *)coef, nv); DP_LAUNCHED(); }
-        cudaMemcpyAsync(cm->bh_evals, (const char *)coef + esz * Ml * rank, esz * Ml, cudaMemcpyDeviceToDevice, c.stream);
+        if (cudaMemcpyAsync(cm->bh_evals, (const char *)coef + esz * Ml * rank, esz * Ml, cudaMemcpyDeviceToDevice, c.stream) != cudaSuccess) return fail(dp_fail(DP_ERR_CUDA, "dp_pcs_commit_shard: copy of the evaluation slice failed"));
         if (int e = run_levels<u64, 0>((u64 *)coef, nv, 0, nv)) return fail(e);
         { DpProfScope p("k_shard_expand", esz * (m + S)); k_shard_expand<u64><<<gs, 256, 0, c.stream>>>((const u64 *)coef, (u64 *)cm->codeword, nv, logG, rev_rank, st, root_tab()); DP_LAUNCHED(); }
         if (int e = run_levels<u64, 1>((u64 *)cm->codeword, n_log - logG, 0, n_log - logG)) return fail(e);
@@ -997,15 +997,19 @@ int dp_pcs_commit_many(const dp_mle *const *polys, uint32_t n, uint32_t full_log
     for (u32 i = 0; i < n; i++) DP_CHECK(polys[i] != nullptr, DP_ERR_INVALID, "dp_pcs_commit_many: null polynomial");
     if (int e = bf_prepare()) return e;
     DpCtx &c = dp_ctx();
-    static const u32 S = [] { const char *e = getenv("DP_COMMIT_STREAMS"); int v = e ? atoi(e) : 4; return (u32)(v < 1 ? 1 : (v > 8 ? 8 : v)); }();   // streams per host thread for independent commits
+    // streams per host thread for independent commits: 8 are created; a lone proof uses all of them (its 38 witness trees are a pure
+    // latency chain each), with many proofs in flight 4 are enough and keep the number of live streams near the 32 hardware queues
+    static const u32 SMAX = 8;
+    static const u32 S_ENV = [] { const char *e = getenv("DP_COMMIT_STREAMS"); int v = e ? atoi(e) : 0; return (u32)(v < 0 ? 0 : (v > 8 ? 8 : v)); }();
+    const u32 S = S_ENV ? S_ENV : (dp_wait_mode() == DP_WAIT_BLOCK ? 4u : 8u);
     (void)g_set_return;
     if (g_pool.empty()) {
         std::lock_guard<std::mutex> lk(g_sets_mu);
         if (!g_free_sets.empty()) { g_pool = g_free_sets.back().s; g_pool_ev = g_free_sets.back().e; g_main_ev = g_free_sets.back().main_ev; g_free_sets.pop_back(); }
     }
     if (g_pool.empty()) {
-        g_pool.resize(S); g_pool_ev.resize(S);
-        for (u32 s = 0; s < S; s++) { DP_CUDA(cudaStreamCreateWithFlags(&g_pool[s], cudaStreamNonBlocking)); DP_CUDA(cudaEventCreateWithFlags(&g_pool_ev[s], cudaEventDisableTiming)); }
+        g_pool.resize(SMAX); g_pool_ev.resize(SMAX);
+        for (u32 s = 0; s < SMAX; s++) { DP_CUDA(cudaStreamCreateWithFlags(&g_pool[s], cudaStreamNonBlocking)); DP_CUDA(cudaEventCreateWithFlags(&g_pool_ev[s], cudaEventDisableTiming)); }
         DP_CUDA(cudaEventCreateWithFlags(&g_main_ev, cudaEventDisableTiming));
     }
     u64 *pin = nullptr;

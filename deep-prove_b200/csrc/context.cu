@@ -149,7 +149,7 @@ int dp_wait_mode() {
 }
 static long futex_call(std::atomic<u32> *addr, int op, u32 val, const struct timespec *ts) { return syscall(SYS_futex, (u32 *)addr, op, val, ts, nullptr, 0); }
 struct WaitSlot {
-    std::atomic<u32> state{0};                 // 0 idle, 1 armed (the poller watches it), 2 fired
+    std::atomic<u32> state{0};                 // 0 idle, 1 armed (the poller watches it), 3 being fired by the poller, 2 fired
     volatile u64 *flag = nullptr; u64 want = 0, fail = 0; bool has_fail = false;
     u64 seen = 0;
     std::atomic<u32> wake{0};                  // futex word the owner sleeps on
@@ -172,6 +172,8 @@ static void poller_main() {
             if (w.state.load(std::memory_order_acquire) != 1) continue;
             const u64 v = *w.flag;
             if (v == w.want || (w.has_fail && v == w.fail)) {
+                u32 armed = 1;                               // claim the slot first: a waiter that is timing out withdraws it with the same CAS
+                if (!w.state.compare_exchange_strong(armed, 3, std::memory_order_acq_rel)) continue;
                 w.seen = v;
                 g_armed.fetch_sub(1, std::memory_order_acq_rel);
                 w.state.store(2, std::memory_order_release);

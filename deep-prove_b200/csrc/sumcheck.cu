@@ -77,7 +77,7 @@ __device__ __forceinline__ gle sc_load_const(const ScOp &op, gle r) {
 __device__ __noinline__ gle e_mul_ni(gle a, gle b) { return e_mul(a, b); }
 struct gle2 { gle lo, hi; };
 template <bool CG>
-__device__ __noinline__ gle2 sc_load_pair_ni(const ScOp *op, u64 i, gle r) {
+__device__ __noinline__ gle2 sc_load_pair_ni(const ScOp *op, u64 i, gle r, bool store = true) {
     gle2 o;
     switch (op->mode) {
     case OPM_B: { ulonglong2 v = ldx_b2<CG>((const u64 *)op->src + 2 * i); o.lo = e_from_base(v.x); o.hi = e_from_base(v.y); } break;
@@ -86,13 +86,13 @@ __device__ __noinline__ gle2 sc_load_pair_ni(const ScOp *op, u64 i, gle r) {
         const u64 *s = (const u64 *)op->src + 4 * i;
         ulonglong2 v0 = ldx_b2<CG>(s), v1 = ldx_b2<CG>(s + 2);
         o.lo = fold_b(v0.x, v0.y, r); o.hi = fold_b(v1.x, v1.y, r);
-        if (op->dst) { st_e(op->dst + 2 * i, o.lo); st_e(op->dst + 2 * i + 1, o.hi); }
+        if (store && op->dst) { st_e(op->dst + 2 * i, o.lo); st_e(op->dst + 2 * i + 1, o.hi); }
     } break;
     default: {
         const gle *s = (const gle *)op->src + 4 * i;
         gle f0 = ldx_e<CG>(s), f1 = ldx_e<CG>(s + 1), f2 = ldx_e<CG>(s + 2), f3 = ldx_e<CG>(s + 3);
         o.lo = e_add(f0, e_mul_ni(e_sub(f1, f0), r)); o.hi = e_add(f2, e_mul_ni(e_sub(f3, f2), r));
-        if (op->dst) { st_e(op->dst + 2 * i, o.lo); st_e(op->dst + 2 * i + 1, o.hi); }
+        if (store && op->dst) { st_e(op->dst + 2 * i, o.lo); st_e(op->dst + 2 * i + 1, o.hi); }
     } break;
     }
     return o;
@@ -174,6 +174,31 @@ __device__ __forceinline__ void sc_body(const ScProd &pd, gle r, gle acc[SC_NACC
     }
 #pragma unroll
     for (int t = 0; t <= D; t++) acc[t] = a[t];
+}
+
+// Small resident rounds (fewer pairs than a quarter of the lanes a product owns): one (pair, evaluation point) per LANE instead of one
+// pair per lane.  The 2^tpl lanes of a pair load and fold it redundantly (same instructions, no extra time), then each computes the
+// product at ITS point only -- the dependent chain per lane drops from D folds x 2 + (D+1)(D-1) extension multiplications to
+// D x 2 + (D-1) (8 instead of 14 for D = 3), which is most of a small round's device time (phase clocks: 6.2 us of "work" for <= 64
+// pairs).  Lane t == 0 of a pair writes the folded table; the other lanes' accumulators stay zero, so the ordinary reduction applies.
+template <int D, bool CG>
+__device__ __forceinline__ void sc_body_split(const ScProd &pd, gle r, gle acc[SC_NACC], const u64 L, const u32 tpl) {
+    const u64 i = L >> tpl; const u32 t = (u32)L & ((1u << tpl) - 1);
+    if (i >= pd.npairs || t > (u32)D) return;
+    gle cur[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        const gle2 v = sc_load_pair_ni<CG>(&pd.op[j], i, r, t == 0);
+        const gle st = e_sub(v.hi, v.lo);
+        gle c = v.lo;
+        for (u32 q = 0; q < t; q++) c = e_add(c, st);
+        cur[j] = c;
+    }
+    gle p = cur[0];
+#pragma unroll
+    for (int j = 1; j < D; j++) p = (pd.op[j].mode == OPM_B) ? e_mul_base(p, cur[j].c0) : e_mul_ni(p, cur[j]);
+#pragma unroll
+    for (int tt = 0; tt <= D; tt++) if (tt == (int)t) acc[tt] = p;
 }
 
 // completion signal: `out` and `flag` live in mapped pinned host memory, so the round message reaches the host
@@ -520,6 +545,18 @@ k_sc_res(const ScTail *__restrict__ cfg, gle r0, gle *out /* mapped */, gle *pai
 #pragma unroll
             for (int t = 0; t < SC_NACC; t++) acc[t] = e_zero();
             const u64 first = (u64)s * 32 + lane, stride = (u64)G * 32;
+            const u32 tpl = pd.d <= 3 ? 2 : 3;
+            const bool split = !pd.konst && !pd.allbase && (pd.npairs << tpl) <= stride;     // uniform over the warps of this product
+            if (split) {
+                if (DSEL != 0) sc_body_split<DSEL == 0 ? 1 : DSEL, true>(pd, r, acc, first, tpl);
+                else switch (pd.d) {
+                case 1: sc_body_split<1, true>(pd, r, acc, first, tpl); break;
+                case 2: sc_body_split<2, true>(pd, r, acc, first, tpl); break;
+                case 3: sc_body_split<3, true>(pd, r, acc, first, tpl); break;
+                case 4: sc_body_split<4, true>(pd, r, acc, first, tpl); break;
+                default: sc_body_split<5, true>(pd, r, acc, first, tpl); break;
+                }
+            } else
             if (DSEL != 0) sc_body<DSEL == 0 ? 1 : DSEL, true>(pd, r, acc, first, stride);
             else switch (pd.d) {
             case 1: sc_body<1, true>(pd, r, acc, first, stride); break;
