@@ -252,21 +252,6 @@ template <bool EXT> __device__ __forceinline__ u64 leaf_pair_word(const void *le
     if (EXT) return ((const u64 *)leaves)[4 * pair + w];
     return w < 2 ? ((const u64 *)leaves)[2 * pair + w] : 0ULL;
 }
-template <bool EXT, bool FROM_LEAVES>
-__global__ void __launch_bounds__(256) k_merkle_x8(const void *src, u64 n_out, u64 *__restrict__ out) {
-    const int lane8 = threadIdx.x & 7;
-    u64 h = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 3, stride = ((u64)gridDim.x * blockDim.x) >> 3;
-    // whole 8-lane groups stay together: the loop bound is uniform inside a group
-    for (; h < n_out; h += stride) {
-        u64 xw = 0, yw = 0;
-        if (lane8 < 4) {
-            if (FROM_LEAVES) { xw = leaf_pair_word<EXT>(src, 2 * h, lane8); yw = leaf_pair_word<EXT>(src, 2 * h + 1, lane8); }
-            else { const u64 *in = (const u64 *)src + 8 * h; xw = in[lane8]; yw = in[4 + lane8]; }
-        }
-        u64 s = p2x8_compress(xw, yw, lane8);
-        if (lane8 < 4) out[4 * h + (3 - lane8)] = s;
-    }
-}
 // Every remaining level of a tree whose current level has <= MK_SMALL hashes, in ONE launch.  Each block owns MK_SUB hashes of the
 // first level and walks that subtree up to its root with a block barrier per level; the last block to finish (ticket) folds the
 // <= 8 subtree roots.  A level with >= 64 hashes per block runs one THREAD per hash (latency-optimised permutation): the same

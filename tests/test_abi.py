@@ -44,3 +44,25 @@ def test_product_does_not_reference_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle/" not in txt.replace("Never imports anything from oracle/", "").replace("Nothing here touches oracle/", "") \
                     and "oracle_py" not in txt and "libdp_oracle" not in txt, f
+
+
+def test_wait_mode_switch_needs_no_device():
+    """dp_set_wait_mode / dp_get_wait_mode (how proving threads wait for the device: spin, or sleep on the library's poller) are plain
+    process-wide settings: usable before dp_init and without a GPU; an unknown mode is refused"""
+    lib = dpb200.lib()
+    before = lib.dp_get_wait_mode()
+    try:
+        assert lib.dp_set_wait_mode(1) == 0 and lib.dp_get_wait_mode() == 1
+        assert lib.dp_set_wait_mode(0) == 0 and lib.dp_get_wait_mode() == 0
+        assert lib.dp_set_wait_mode(7) == dpb200.DP_ERR_INVALID
+    finally:
+        lib.dp_set_wait_mode(before)
+
+
+def test_sharded_commit_refuses_without_gpu_and_bad_worlds():
+    lib = dpb200.lib()
+    if lib.dp_device_count() > 0:
+        return
+    import ctypes as C
+    h = C.c_void_p()
+    assert lib.dp_pcs_commit_shard(None, 20, 0, 2, C.byref(h)) == dpb200.DP_ERR_NO_DEVICE
