@@ -260,7 +260,7 @@ cudaError_t dp_stream_sync(cudaStream_t st) {
 }
 
 DpD2H::DpD2H(cudaStream_t s, size_t reserve_bytes) : st(s) { cap = reserve_bytes < 64 ? 64 : reserve_bytes; if (dp_pinned_alloc(&pin, cap) != DP_OK) { pin = nullptr; cap = 0; } }
-DpD2H::~DpD2H() { dp_pinned_free(pin); }
+DpD2H::~DpD2H() { if (!pieces.empty()) cudaStreamSynchronize(st); dp_pinned_free(pin); }   // copies still in flight (an error path skipped finish()): the block must not be recycled under them
 int DpD2H::add(void *host_dst, const void *dev_src, size_t bytes) {
     if (!pin || used + bytes > cap) return dp_fail(DP_ERR_CUDA, "DpD2H: staging buffer too small or not allocated");
     DP_CUDA(cudaMemcpyAsync((char *)pin + used, dev_src, bytes, cudaMemcpyDeviceToHost, st));
@@ -338,6 +338,9 @@ static void prof_resolve() {
 }
 
 extern "C" {
+
+// test hook (not part of the ABI): the wait service on an arbitrary word -- lets the CPU suite exercise the poller / futex path without a device
+uint64_t dp_debug_wait_flag(volatile uint64_t *flag, uint64_t want, double timeout_s) { return dp_wait_flag((volatile u64 *)flag, want, false, 0, timeout_s); }
 
 int dp_set_wait_mode(int mode) {
     if (mode != DP_WAIT_SPIN && mode != DP_WAIT_BLOCK) return dp_fail(DP_ERR_INVALID, "dp_set_wait_mode: 0 = spin, 1 = block on the poller thread");
