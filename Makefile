@@ -40,7 +40,14 @@ tools: $(PKG)/gl_selftest_bin
 $(PKG)/gl_selftest_bin: tools/gl_selftest.cu $(CU_HDRS) $(HOST_HDRS)
 	$(NVCC) $(ARCH) -O2 -std=c++17 -Iinclude -o $@ tools/gl_selftest.cu
 
+# developer tools (not part of `all`): kernel micro-benchmarks and the CUPTI timeline / API-census library (tools/trace_*.py)
+devtools: $(PKG)/kbench_bin $(PKG)/libdp_trace.so
+$(PKG)/kbench_bin: tools/kbench.cu $(CU_HDRS)
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -Iinclude -Xcompiler -pthread -o $@ tools/kbench.cu
+$(PKG)/libdp_trace.so: tools/cupti_trace.cpp
+	$(CXX) -O2 -shared -fPIC -I/usr/local/cuda/include -I/usr/local/cuda/extras/CUPTI/include -o $@ tools/cupti_trace.cpp -L/usr/local/cuda/lib64 -L/usr/local/cuda/extras/CUPTI/lib64 -lcupti -lcudart -Wl,-rpath,/usr/local/cuda/lib64
+
 clean:
 	rm -rf build $(PKG)/*.so oracle/*.so $(PKG)/gl_selftest_bin
 
-.PHONY: all product host oracle tools clean
+.PHONY: all product host oracle tools devtools clean

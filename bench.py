@@ -885,6 +885,8 @@ def main():
             "run": {"l2": head["l2"],
                     "parallelism": "replicas x%d GPUs (no data-path collective)%s" % (world, (", %d concurrent independent proofs per GPU" % host_workers(wl.STREAMS)) if hasattr(wl, "STREAMS") else ""),
                     "proofs_per_step": head["units_per_step"], "single_stream_latency_ms": head["single_stream_latency_ms"],
+                    "host_waits": "throughput legs: dp_set_wait_mode(1) -- proving threads sleep on the library's poller thread; latency leg: spin",
+                    "cpu_budget_per_rank": cpu_budget(),
                     "baseline_note": "vs_baseline divides by the reference README's proving time (Dense 4M 2335 ms / CNN 264k 1242 ms; hardware and exact architecture not stated)"},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
             "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"], "parity_checked": head["parity_checked"],
